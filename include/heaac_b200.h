@@ -1,0 +1,252 @@
+/*
+ * heaac_b200.h -- C-ABI of the B200-native HE-AAC synthesis back end.
+ *
+ * This library replaces ONE path of the reference decoder (aconverse/ffmpeg-heaac,
+ * libavcodec 52.78): everything from spectral_to_sample() downwards
+ *   libavcodec/aacdec.c:1903-1933  spectral_to_sample      (driver)
+ *   libavcodec/aacdec.c:1698-1736  apply_tns
+ *   libavcodec/aacdec.c:1741-1806  imdct_and_windowing
+ *   libavcodec/aacsbr.c:1716-1771  ff_sbr_apply            (QMF analysis, HF generation/adjustment, QMF synthesis)
+ *   libavcodec/aacps.c:973-992     ff_ps_apply             (hybrid analysis, decorrelation, stereo processing)
+ *   libavcodec/dsputil.c:3972-4001 float_to_int16_interleave
+ * for a BATCH of independent streams, on one B200.  Bitstream parsing stays on the host;
+ * the structs below are exactly the per-frame outputs of the reference's parsers
+ * (decode_ics / read_sbr_data / ff_ps_read_data) that the synthesis path consumes.
+ *
+ * Plain C, plain pointers and sizes; no CUDA, torch or C++ types appear in any signature.
+ * All functions return 0 (or a non-negative count) on success and a negative HEAAC_E_* code
+ * on failure -- the reference's own `int` convention (aacdec.c: -1 / AVERROR(x)).
+ * One handle per GPU; calls on one handle must be serialised by the caller; different
+ * handles are independent (same threading contract as AVCodecContext, utils.c:467-473).
+ */
+#ifndef HEAAC_B200_H
+#define HEAAC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEAAC_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------- */
+#define HEAAC_OK            0
+#define HEAAC_E_INVAL      (-22)   /* bad argument (EINVAL)                        */
+#define HEAAC_E_NOMEM      (-12)   /* host or device allocation failed (ENOMEM)    */
+#define HEAAC_E_NODEV      (-19)   /* no usable sm_100 device / CUDA runtime error */
+#define HEAAC_E_LAUNCH     (-5)    /* kernel launch or execution failed (EIO)      */
+#define HEAAC_E_UNSUPPORTED (-38)  /* valid request this build does not cover      */
+
+/* ---- element / window enums (values identical to aac.h:46-71) ------------------- */
+enum { HEAAC_TYPE_SCE = 0, HEAAC_TYPE_CPE = 1, HEAAC_TYPE_LFE = 3 };
+enum { HEAAC_ONLY_LONG = 0, HEAAC_LONG_START = 1, HEAAC_EIGHT_SHORT = 2, HEAAC_LONG_STOP = 3 };
+
+#define HEAAC_MAX_ELEMS     8      /* channel elements per stream in one layout      */
+#define HEAAC_MAX_CHANNELS  16
+#define HEAAC_FRAME_LEN     1024   /* core frame length (960 not supported, as in the reference) */
+#define HEAAC_TNS_MAX_ORDER 20     /* aac.h:44 */
+
+/* ---- per-frame side info: core (AAC-LC) channel ----------------------------------
+ * Mirrors the fields of IndividualChannelStream (aac.h:135-150) and
+ * TemporalNoiseShaping (aac.h:155-162) that apply_tns / imdct_and_windowing read.
+ * The previous frame's window_sequence / window_shape are device state. */
+typedef struct HeaacIcs {
+    uint8_t window_sequence;   /* ics.window_sequence[0]                         */
+    uint8_t window_shape;      /* ics.use_kb_window[0]: 1 = KBD, 0 = sine        */
+    uint8_t max_sfb;           /* ics.max_sfb                                    */
+    uint8_t tns_present;       /* tns.present                                    */
+    uint8_t reserved[4];
+} HeaacIcs;
+
+/* TNS filters in bitstream order.  Long blocks: window 0 holds up to 3 filters in slots
+ * 0..2.  EIGHT_SHORT: window w holds at most one filter, in slot w (aacdec.c:854-887). */
+typedef struct HeaacTns {
+    uint8_t n_filt[8];                        /* tns.n_filt[w]                     */
+    uint8_t length[8];                        /* tns.length[w][filt]               */
+    uint8_t order[8];                         /* tns.order[w][filt]                */
+    uint8_t direction[8];                     /* tns.direction[w][filt]            */
+    float   coef[8][HEAAC_TNS_MAX_ORDER];     /* tns.coef[w][filt][]: reflection coefficients (tns_tmp2_map values) */
+} HeaacTns;
+
+/* ---- per-frame side info: SBR ------------------------------------------------------
+ * Mirrors SBRData (sbr.h:59-107) bitstream fields as left by read_sbr_data
+ * (aacsbr.c:982-1021) BEFORE sbr_dequant: env_q / noise_q are the integer-valued
+ * env_facs[1..] / noise_facs[1..] rows. */
+typedef struct HeaacSbrChan {
+    uint8_t bs_num_env;
+    uint8_t bs_num_noise;
+    uint8_t bs_amp_res;
+    uint8_t bs_add_harmonic_flag;
+    int8_t  e_a[2];                 /* l_APrev, l_A (aacsbr.c:741-746)               */
+    uint8_t t_env_num_env_old;
+    uint8_t reserved0;
+    uint8_t bs_freq_res[8];         /* [0] = last of previous frame, [e+1] per envelope */
+    uint8_t t_env[8];
+    uint8_t t_q[4];
+    uint8_t bs_invf_mode[2][5];     /* [0] current, [1] previous frame               */
+    uint8_t reserved1[2];
+    uint8_t bs_add_harmonic[48];
+    int16_t env_q[5][48];           /* env_facs[e+1][k], quantised                   */
+    int16_t noise_q[2][5];          /* noise_facs[e+1][k], quantised                 */
+    uint8_t reserved2[4];
+} HeaacSbrChan;
+
+/* Mirrors the SpectralBandReplication fields (sbr.h:112-156) that ff_sbr_apply reads:
+ * header flags and the frequency tables derived by sbr_reset (aacsbr.c:1023-1034). */
+typedef struct HeaacSbrElem {
+    uint8_t start;                  /* sbr->start: 0 = pure upsampling mode          */
+    uint8_t reset;                  /* sbr->reset                                    */
+    uint8_t bs_coupling;
+    uint8_t bs_limiter_gains;
+    uint8_t bs_interpol_freq;
+    uint8_t bs_smoothing_mode;
+    uint8_t num_patches;
+    uint8_t n_q;
+    uint8_t n[2];                   /* N_low, N_high                                 */
+    uint8_t n_lim;
+    uint8_t k0;                     /* sbr->k[0]                                     */
+    uint8_t kx[2];                  /* kx' (previous frame), kx                      */
+    uint8_t m[2];                   /* M', M                                         */
+    uint8_t f_tablelow[25];
+    uint8_t f_tablehigh[49];
+    uint8_t f_tablenoise[6];
+    uint8_t f_tablelim[29];
+    uint8_t patch_num_subbands[6];
+    uint8_t patch_start_subband[6];
+    uint8_t reserved[3];
+    HeaacSbrChan ch[2];
+} HeaacSbrElem;
+
+/* ---- per-frame side info: Parametric Stereo ---------------------------------------
+ * Mirrors the PSContext bitstream fields (aacps.h:40-63) after ff_ps_read_data. */
+typedef struct HeaacPsFrame {
+    uint8_t start;                  /* ps->start: 0 = copy L to R (aacsbr.c:1751-1756) */
+    uint8_t num_env;
+    uint8_t num_env_old;
+    uint8_t iid_quant;
+    uint8_t nr_iid_par;
+    uint8_t nr_icc_par;
+    uint8_t nr_ipdopd_par;
+    uint8_t icc_mode;
+    uint8_t enable_ipdopd;
+    uint8_t is34bands;
+    uint8_t is34bands_old;
+    uint8_t reserved0;
+    int8_t  border_position[6];
+    uint8_t reserved1[2];
+    int8_t  iid_par[5][34];
+    int8_t  icc_par[5][34];
+    int8_t  ipd_par[5][34];
+    int8_t  opd_par[5][34];
+} HeaacPsFrame;
+
+/* ---- context configuration ---------------------------------------------------------
+ * A context decodes `n_streams` independent streams that share one channel layout
+ * (the BASELINE configs: stereo CPE, mono SCE + PS, 5.1 = SCE CPE CPE LFE, ...).
+ * Channel c of a stream is the c-th core channel in element order; the interleaved
+ * output order is the same (the reference orders output_data[] by element position,
+ * aacdec.c:150-190 -- for the layouts above this is bitstream element order). */
+typedef struct HeaacConfig {
+    uint32_t abi_version;           /* HEAAC_ABI_VERSION                             */
+    int32_t  device;                /* CUDA device ordinal                           */
+    int32_t  n_streams;
+    int32_t  n_elems;               /* elements per stream                           */
+    uint8_t  elem_type[HEAAC_MAX_ELEMS]; /* HEAAC_TYPE_*                             */
+    int32_t  sr_index;              /* MPEG-4 sampling frequency index of the CORE (aactab.c:1174-1207 tables) */
+    int32_t  sbr;                   /* 1: every SCE/CPE element carries SBR (m4ac.sbr == 1) */
+    int32_t  ps;                    /* 1: mono SCE + Parametric Stereo (m4ac.ps == 1) */
+    /* Scaling convention chosen by the front end (aacdec.c:573-581):
+     *   add_bias = 0,   sf_scale = -1/1024          -> samples in s16 units (SIMD path; default)
+     *   add_bias = 385, sf_scale = -1/(1024*32768)  -> C "bias" path
+     * coeffs[] must arrive already multiplied by sf_scale (as the reference's dequantiser does). */
+    float    add_bias;
+    float    sf_scale;
+    int32_t  max_frames_per_call;   /* T: capacity of the device staging buffers     */
+    int32_t  want_float_out;        /* also produce planar float PCM (debug / float parity) */
+    int32_t  keep_intermediates;    /* keep per-stage arrays readable via heaac_b200_debug_read */
+    int32_t  reserved[4];
+} HeaacConfig;
+
+/* One call = `n_frames` consecutive frames of every stream.  Arrays are frame-major:
+ *   coeffs [n_frames][n_streams][n_core_ch][1024]   float
+ *   ics    [n_frames][n_streams][n_core_ch]
+ *   tns    [n_frames][n_streams][n_core_ch]         (may be NULL if no channel has tns_present)
+ *   sbr    [n_frames][n_streams][n_sbr_elems]       (NULL unless cfg.sbr)
+ *   ps     [n_frames][n_streams]                    (NULL unless cfg.ps)
+ *   pcm    [n_frames][n_streams][frame_out_len][n_out_ch]  int16, interleaved
+ *   pcm_f32[n_frames][n_streams][n_out_ch][frame_out_len]  float, planar (optional)
+ * frame_out_len = 1024 (no SBR) or 2048 (SBR).  n_out_ch = n_core_ch, or 2 for ps.
+ * `on_device` != 0 means every pointer is a CUDA device pointer on cfg.device (no copies);
+ * otherwise they are host pointers and the call copies H2D / D2H itself. */
+typedef struct HeaacBatch {
+    int32_t n_frames;
+    int32_t on_device;
+    const float        *coeffs;
+    const HeaacIcs     *ics;
+    const HeaacTns     *tns;
+    const HeaacSbrElem *sbr;
+    const HeaacPsFrame *ps;
+    int16_t            *pcm;
+    float              *pcm_f32;
+} HeaacBatch;
+
+typedef struct HeaacContext HeaacContext;
+
+/* Lifetime.  create: replaces aac_decode_init's back-end half (aacdec.c:537-600: ff_mdct_init x2,
+ * window tables, ff_aac_sbr_init tables) + che_configure/ff_aac_sbr_ctx_init per stream
+ * (aacdec.c:192-214, aacsbr.c:128-137).  State starts as the reference's post-init state
+ * (kx' = 32, e_a[1] = -1, all histories zero). */
+int  heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out);
+void heaac_b200_destroy(HeaacContext *ctx);
+/* Re-initialise all per-stream state (as if freshly created). */
+int  heaac_b200_reset_state(HeaacContext *ctx);
+
+/* Layout queries derived from the config. */
+int  heaac_b200_n_core_channels(const HeaacContext *ctx);
+int  heaac_b200_n_out_channels(const HeaacContext *ctx);
+int  heaac_b200_frame_out_len(const HeaacContext *ctx);
+int  heaac_b200_n_sbr_elems(const HeaacContext *ctx);
+
+/* The hot path: replaces spectral_to_sample + float_to_int16_interleave
+ * (aacdec.c:2078, 2096-2097) for n_frames x n_streams frames.  Asynchronous on the
+ * context's stream when on_device != 0; heaac_b200_sync waits.  Host-pointer calls
+ * return after the PCM has landed in host memory. */
+int  heaac_b200_synth(HeaacContext *ctx, const HeaacBatch *batch);
+int  heaac_b200_sync(HeaacContext *ctx);
+
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+long long heaac_b200_launch_count(const HeaacContext *ctx);
+/* The cudaStream_t the context launches on, as an integer handle (for event timing). */
+uintptr_t heaac_b200_stream(const HeaacContext *ctx);
+
+/* Device memory helpers so a C/ctypes caller can stage device-resident batches without
+ * linking the CUDA runtime itself. */
+int  heaac_b200_dev_alloc(HeaacContext *ctx, size_t bytes, void **dptr);
+int  heaac_b200_dev_free(HeaacContext *ctx, void *dptr);
+int  heaac_b200_dev_upload(HeaacContext *ctx, void *dptr, const void *hptr, size_t bytes);
+int  heaac_b200_dev_download(HeaacContext *ctx, void *hptr, const void *dptr, size_t bytes);
+
+/* Event timing on the context's stream (CUDA events; milliseconds). */
+int  heaac_b200_timer_start(HeaacContext *ctx);
+int  heaac_b200_timer_stop(HeaacContext *ctx, float *ms);
+
+/* Stage-level inspection (requires cfg.keep_intermediates).  Copies the named array of
+ * the LAST frame processed to host.  Names and layouts: see DESIGN.md "intermediates". */
+int  heaac_b200_debug_read(HeaacContext *ctx, const char *name, void *dst, size_t bytes);
+
+/* ---- batch-of-one shims with the reference's own transform signatures -----------------
+ * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */
+typedef struct HeaacMdct HeaacMdct;
+int  heaac_b200_mdct_init(HeaacMdct **s, int nbits, int inverse, double scale);
+void heaac_b200_imdct_half(HeaacMdct *s, float *output, const float *input);  /* host pointers, N/2 in, N/2 out */
+void heaac_b200_mdct_end(HeaacMdct *s);
+
+const char *heaac_b200_version(void);
+const char *heaac_b200_strerror(int err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEAAC_B200_H */

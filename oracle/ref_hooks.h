@@ -1,0 +1,9 @@
+/* TEST INFRASTRUCTURE ONLY.  Force-included (-include) when oracle/Makefile compiles the
+ * reference's aacdec.c: declares the two hooks spliced around spectral_to_sample(ac)
+ * (aacdec.c:2078).  Defined in ref_harness.c. */
+#ifndef ORACLE_REF_HOOKS_H
+#define ORACLE_REF_HOOKS_H
+struct AACContext_tag;
+void heaac_ref_pre_hook(void *ac);
+void heaac_ref_post_hook(void *ac);
+#endif
