@@ -51,3 +51,60 @@ PS_FRAME = np.dtype([
 
 SIZES = {"HeaacIcs": ICS.itemsize, "HeaacTns": TNS.itemsize, "HeaacSbrChan": SBR_CHAN.itemsize,
          "HeaacSbrElem": SBR_ELEM.itemsize, "HeaacPsFrame": PS_FRAME.itemsize}
+
+# ---- ctypes mirrors of HeaacConfig / HeaacBatch (include/heaac_b200.h) -------------
+import ctypes as C
+
+ABI_VERSION = 1
+MAX_ELEMS = 8
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("device", C.c_int32), ("n_streams", C.c_int32), ("n_elems", C.c_int32),
+        ("elem_type", C.c_uint8 * MAX_ELEMS), ("sr_index", C.c_int32), ("sbr", C.c_int32), ("ps", C.c_int32),
+        ("add_bias", C.c_float), ("sf_scale", C.c_float), ("max_frames_per_call", C.c_int32),
+        ("want_float_out", C.c_int32), ("keep_intermediates", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("on_device", C.c_int32),
+        ("coeffs", C.c_void_p), ("ics", C.c_void_p), ("tns", C.c_void_p), ("sbr", C.c_void_p), ("ps", C.c_void_p),
+        ("pcm", C.c_void_p), ("pcm_f32", C.c_void_p),
+    ]
+
+
+def make_config(n_streams, elem_types, sr_index, sbr=False, ps=False, bias_mode=False, device=0,
+                max_frames=1, want_float=True, keep_intermediates=False):
+    """Build a HeaacConfig.  bias_mode selects the reference's C 'bias' scaling (aacdec.c:573-576),
+    otherwise the s16-unit scaling of its SIMD branch (aacdec.c:577-581)."""
+    c = Config()
+    c.abi_version = ABI_VERSION
+    c.device = device
+    c.n_streams = n_streams
+    c.n_elems = len(elem_types)
+    for i, t in enumerate(elem_types):
+        c.elem_type[i] = t
+    c.sr_index = sr_index
+    c.sbr = int(bool(sbr))
+    c.ps = int(bool(ps))
+    if bias_mode:
+        c.add_bias = 385.0
+        c.sf_scale = float(np.float32(1.0 / (-1024.0 * 32768.0)))
+    else:
+        c.add_bias = 0.0
+        c.sf_scale = float(np.float32(1.0 / -1024.0))
+    c.max_frames_per_call = max_frames
+    c.want_float_out = int(bool(want_float))
+    c.keep_intermediates = int(bool(keep_intermediates))
+    return c
+
+
+def n_core_channels(elem_types):
+    return sum(2 if t == TYPE_CPE else 1 for t in elem_types)
+
+
+def n_sbr_elems(elem_types):
+    return sum(1 for t in elem_types if t != TYPE_LFE)
