@@ -1,0 +1,223 @@
+"""B200-native HE-AAC synthesis back end: Python host mirror of the C-ABI (include/heaac_b200.h).
+
+This package is a thin ctypes binding over `libheaac_b200.so` (hand-written sm_100a CUDA kernels +
+C-ABI, built by `__graft_entry__.build()` / `csrc/Makefile`).  It mirrors the reference decoder's
+interface for the one path it replaces -- `spectral_to_sample` + `float_to_int16_interleave`
+(libavcodec/aacdec.c:1903-1933, 2096-2097) -- for a batch of independent streams.
+
+There is NO CPU path: importing works anywhere, but `Context(...)` raises if the shared library is
+missing or no sm_100 device is present.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi  # noqa: F401
+from .abi import (Batch, Config, make_config, ICS, TNS, SBR_ELEM, PS_FRAME,  # noqa: F401
+                  TYPE_SCE, TYPE_CPE, TYPE_LFE, ONLY_LONG, LONG_START, EIGHT_SHORT, LONG_STOP)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libheaac_b200.so")
+_lib = None
+
+ERRORS = {-22: "HEAAC_E_INVAL", -12: "HEAAC_E_NOMEM", -19: "HEAAC_E_NODEV", -5: "HEAAC_E_LAUNCH", -38: "HEAAC_E_UNSUPPORTED"}
+
+EXPORTS = [
+    "heaac_b200_create", "heaac_b200_destroy", "heaac_b200_reset_state", "heaac_b200_n_core_channels",
+    "heaac_b200_n_out_channels", "heaac_b200_frame_out_len", "heaac_b200_n_sbr_elems", "heaac_b200_synth",
+    "heaac_b200_sync", "heaac_b200_launch_count", "heaac_b200_stream", "heaac_b200_dev_alloc", "heaac_b200_dev_free",
+    "heaac_b200_dev_upload", "heaac_b200_dev_download", "heaac_b200_timer_start", "heaac_b200_timer_stop",
+    "heaac_b200_debug_read", "heaac_b200_mdct_init", "heaac_b200_imdct_half", "heaac_b200_mdct_end",
+    "heaac_b200_version", "heaac_b200_strerror", "heaac_b200_sizeof",
+]
+
+
+class HeaacError(RuntimeError):
+    def __init__(self, code, what):
+        super().__init__("%s failed: %s (%d)" % (what, ERRORS.get(code, "error"), code))
+        self.code = code
+
+
+def lib():
+    """Load libheaac_b200.so (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libheaac_b200.so not built (run __graft_entry__.build()); the product has no CPU path")
+        L = C.CDLL(LIB_PATH)
+        L.heaac_b200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.heaac_b200_destroy.argtypes = [C.c_void_p]
+        L.heaac_b200_destroy.restype = None
+        L.heaac_b200_reset_state.argtypes = [C.c_void_p]
+        for f in ("n_core_channels", "n_out_channels", "frame_out_len", "n_sbr_elems", "sync"):
+            getattr(L, "heaac_b200_" + f).argtypes = [C.c_void_p]
+        L.heaac_b200_synth.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.heaac_b200_launch_count.argtypes = [C.c_void_p]
+        L.heaac_b200_launch_count.restype = C.c_longlong
+        L.heaac_b200_stream.argtypes = [C.c_void_p]
+        L.heaac_b200_stream.restype = C.c_size_t
+        L.heaac_b200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.heaac_b200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_b200_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.heaac_b200_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.heaac_b200_timer_start.argtypes = [C.c_void_p]
+        L.heaac_b200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.heaac_b200_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.heaac_b200_mdct_init.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double]
+        L.heaac_b200_imdct_half.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.heaac_b200_imdct_half.restype = None
+        L.heaac_b200_mdct_end.argtypes = [C.c_void_p]
+        L.heaac_b200_mdct_end.restype = None
+        L.heaac_b200_version.restype = C.c_char_p
+        L.heaac_b200_strerror.restype = C.c_char_p
+        L.heaac_b200_sizeof.argtypes = [C.c_char_p]
+        for name, size in abi.SIZES.items():
+            got = L.heaac_b200_sizeof(name.encode())
+            if got != size:
+                raise ImportError("ABI mismatch for %s: library %d, abi.py %d" % (name, got, size))
+        if L.heaac_b200_sizeof(b"HeaacConfig") != C.sizeof(Config) or L.heaac_b200_sizeof(b"HeaacBatch") != C.sizeof(Batch):
+            raise ImportError("ABI mismatch for HeaacConfig/HeaacBatch")
+        _lib = L
+    return _lib
+
+
+def _check(r, what):
+    if r < 0:
+        raise HeaacError(r, what)
+    return r
+
+
+class DeviceBuffer:
+    """A device allocation owned by a Context (plain pointer + size, no torch types)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        _check(lib().heaac_b200_dev_alloc(ctx.h, self.nbytes, C.byref(p)), "dev_alloc")
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(lib().heaac_b200_dev_upload(self.ctx.h, self.ptr, arr.ctypes.data, arr.nbytes), "dev_upload")
+        return self
+
+    def download(self, dtype, shape):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _check(lib().heaac_b200_dev_download(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes), "dev_download")
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().heaac_b200_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One batched decoder back end on one GPU (HeaacContext).
+
+    synth(...) is the drop-in for the reference's per-frame `spectral_to_sample(ac)` +
+    `float_to_int16_interleave` pair, for `n_frames` consecutive frames of `n_streams` streams.
+    """
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        h = C.c_void_p()
+        _check(lib().heaac_b200_create(C.byref(cfg), C.byref(h)), "heaac_b200_create")
+        self.h = h.value
+        self.ncc = lib().heaac_b200_n_core_channels(self.h)
+        self.nout = lib().heaac_b200_n_out_channels(self.h)
+        self.out_len = lib().heaac_b200_frame_out_len(self.h)
+        self.nse = lib().heaac_b200_n_sbr_elems(self.h)
+        self.S = cfg.n_streams
+
+    # -- host-pointer path: copies H2D / D2H inside the call (the e2e path) --
+    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=False, pcm_out=None):
+        coeffs = np.ascontiguousarray(coeffs, np.float32)
+        T = coeffs.size // (self.S * self.ncc * 1024)
+        keep = [coeffs, np.ascontiguousarray(ics, ICS)]
+        b = Batch()
+        b.n_frames, b.on_device = T, 0
+        b.coeffs, b.ics = keep[0].ctypes.data, keep[1].ctypes.data
+        for name, arr, dt in (("tns", tns, TNS), ("sbr", sbr, SBR_ELEM), ("ps", ps, PS_FRAME)):
+            if arr is not None:
+                a = np.ascontiguousarray(arr, dt)
+                keep.append(a)
+                setattr(b, name, a.ctypes.data)
+        pcm = pcm_out if pcm_out is not None else np.empty((T, self.S, self.out_len, self.nout), np.int16)
+        b.pcm = pcm.ctypes.data
+        f32 = None
+        if want_float:
+            f32 = np.empty((T, self.S, self.nout, self.out_len), np.float32)
+            b.pcm_f32 = f32.ctypes.data
+        _check(lib().heaac_b200_synth(self.h, C.byref(b)), "heaac_b200_synth")
+        return pcm, f32
+
+    # -- device-resident path: pointers are DeviceBuffer.ptr; asynchronous --
+    def synth_device(self, n_frames, coeffs, ics, pcm, tns=None, sbr=None, ps=None, pcm_f32=None):
+        b = Batch()
+        b.n_frames, b.on_device = n_frames, 1
+        b.coeffs, b.ics, b.pcm = coeffs.ptr, ics.ptr, pcm.ptr if pcm is not None else None
+        b.tns = tns.ptr if tns is not None else None
+        b.sbr = sbr.ptr if sbr is not None else None
+        b.ps = ps.ptr if ps is not None else None
+        b.pcm_f32 = pcm_f32.ptr if pcm_f32 is not None else None
+        _check(lib().heaac_b200_synth(self.h, C.byref(b)), "heaac_b200_synth")
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def sync(self):
+        _check(lib().heaac_b200_sync(self.h), "heaac_b200_sync")
+
+    def reset_state(self):
+        _check(lib().heaac_b200_reset_state(self.h), "heaac_b200_reset_state")
+
+    def timer_start(self):
+        _check(lib().heaac_b200_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(lib().heaac_b200_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return lib().heaac_b200_launch_count(self.h)
+
+    def debug_read(self, name, dtype, shape):
+        out = np.zeros(shape, dtype)
+        _check(lib().heaac_b200_debug_read(self.h, name.encode(), out.ctypes.data, out.nbytes), "debug_read")
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().heaac_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mdct:
+    """ff_mdct_init / ff_imdct_half / ff_mdct_end (mdct.c:61,124,226) as a batch-of-one device transform."""
+
+    def __init__(self, nbits, inverse, scale):
+        h = C.c_void_p()
+        _check(lib().heaac_b200_mdct_init(C.byref(h), nbits, inverse, scale), "heaac_b200_mdct_init")
+        self.h, self.n = h.value, 1 << nbits
+
+    def imdct_half(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(self.n // 2, np.float32)
+        lib().heaac_b200_imdct_half(self.h, out.ctypes.data, x.ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().heaac_b200_mdct_end(self.h)
+            self.h = None

@@ -1,0 +1,522 @@
+/*
+ * heaac_api.cu -- C-ABI (include/heaac_b200.h) and kernel launches of the B200 HE-AAC
+ * synthesis back end.  sm_100a only; there is no CPU path: every entry point fails with
+ * HEAAC_E_NODEV when no CUDA device is usable.
+ *
+ * One frame tick of a batch = up to four launches, each with one CTA per unit of work:
+ *   k_core   one CTA per core channel   TNS + IMDCT + window + overlap-add   (aacdec.c:1698-1806)
+ *   k_sbr    one CTA per SBR channel    QMF analysis .. X generation         (aacsbr.c:1089-1714)
+ *   k_ps     one CTA per PS stream      hybrid analysis .. hybrid synthesis  (aacps.c:283-992)
+ *   k_synth  one CTA per output channel QMF synthesis + float->s16           (aacsbr.c:1175-1230)
+ * All per-stream state stays in HBM between launches (heaac_dev.cuh).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "heaac_kernels.cuh"
+
+extern "C" void heaac_build_tables(HeaacDevTables *t);
+
+#define HEAAC_THREADS 256
+
+/* ------------------------------------------------------------------------------------ */
+struct HeaacContext {
+    HeaacConfig cfg;
+    HeaacGeom geom;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    HeaacDevTables *d_tables;
+    HeaacChanState *d_chan;          /* [S][ncc] */
+    HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
+    HeaacPsState *d_ps;              /* [S] (PS only) */
+    float *d_core_time;              /* [S][ncc][1024] (SBR only) */
+    float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
+    /* staging for host-pointer batches, sized for max_frames_per_call */
+    float *s_coeffs; HeaacIcs *s_ics; HeaacTns *s_tns; HeaacSbrElem *s_sbr; HeaacPsFrame *s_ps;
+    int16_t *s_pcm; float *s_pcm_f32;
+    long long launches;
+    size_t smem_core, smem_sbr, smem_ps, smem_synth;
+};
+
+/* ------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
+       const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *core_time,
+       int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
+    float *out = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));
+    const int gc = blockIdx.x;                       /* global core channel = s * ncc + c */
+    const int s = gc / g.ncc, c = gc - s * g.ncc;
+    const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
+    heaac_core_channel(sm, coeffs + (size_t)gc * 1024, ics + gc, tns ? tns + gc : nullptr,
+                       chan + gc, out, bias, g.sr_index, T, threadIdx.x, blockDim.x);
+    if (g.sbr) {
+        float *dst = core_time + (size_t)gc * 1024;
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = out[i];
+    } else {
+        const int bias_mode = g.add_bias != 0.0f;
+        if (pcm) {
+            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + c;
+            for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
+        }
+        if (pcm_f32) {
+            float *dst = pcm_f32 + ((size_t)s * g.nout + c) * 1024;
+            for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = out[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_sbr(HeaacGeom g, const float *__restrict__ core_time, const HeaacSbrElem *__restrict__ sbr,
+      HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeaacSbrSmem *sm = reinterpret_cast<HeaacSbrSmem *>(smem_raw);
+    const int gc = blockIdx.x;
+    const int s = gc / g.ncc, c = gc - s * g.ncc;
+    const int se = g.ch_sbr_elem[c];
+    if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
+    const float qmf_scale = -1024.0f * g.sf_scale;   /* aacsbr.c:1764 */
+    const float ana_scale = 1 / qmf_scale;           /* aacsbr.c:1730 */
+    float *Xc = X + ((size_t)s * g.nout + c) * (2 * 38 * 64);
+    heaac_sbr_channel(sm, core_time + (size_t)gc * 1024, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
+                      g.elem_is_cpe[c], chan + gc, Xc, ana_scale, T, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__restrict__ sbr,
+     HeaacPsState *pstate, float *X, const HeaacDevTables *__restrict__ T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeaacPsSmem *sm = reinterpret_cast<HeaacPsSmem *>(smem_raw);
+    const int s = blockIdx.x;
+    float *XL = X + (size_t)s * 2 * (2 * 38 * 64), *XR = XL + 2 * 38 * 64;
+    const HeaacSbrElem *e = sbr + (size_t)s * g.nse;
+    heaac_ps_stream(sm, ps + s, pstate + s, XL, XR, (int)e->kx[1] + (int)e->m[1], T, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
+        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeaacSynthSmem *sm = reinterpret_cast<HeaacSynthSmem *>(smem_raw);
+    const int go = blockIdx.x;                       /* s * nout + c */
+    const int s = go / g.nout, c = go - s * g.nout;
+    const float qmf_scale = -1024.0f * g.sf_scale;
+    heaac_synth_channel(sm, X + (size_t)go * (2 * 38 * 64), synth + go,
+                        pcm ? pcm + (size_t)s * 2048 * g.nout + c : nullptr, g.nout,
+                        pcm_f32 ? pcm_f32 + (size_t)go * 2048 : nullptr,
+                        qmf_scale, g.add_bias, T, threadIdx.x, blockDim.x);
+}
+
+/* ------------------------------------------------------------------------------------ */
+static int cuda_err(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    fprintf(stderr, "heaac_b200: %s: %s\n", what, cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation) return HEAAC_E_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return HEAAC_E_NODEV;
+    return HEAAC_E_LAUNCH;
+}
+#define CK(call) do { int r_ = cuda_err((call), #call); if (r_) return r_; } while (0)
+
+static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
+{
+    memset(g, 0, sizeof(*g));
+    g->n_streams = cfg->n_streams;
+    g->n_elems = cfg->n_elems;
+    int ch = 0, se = 0;
+    for (int e = 0; e < cfg->n_elems; e++) {
+        g->elem_type[e] = cfg->elem_type[e];
+        int nch = cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+        for (int c = 0; c < nch; c++, ch++) {
+            g->ch_elem[ch] = (uint8_t)e;
+            g->ch_in_elem[ch] = (uint8_t)c;
+            g->ch_sbr_elem[ch] = cfg->elem_type[e] == HEAAC_TYPE_LFE ? 0xff : (uint8_t)se;
+            g->elem_is_cpe[ch] = nch == 2;
+        }
+        if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
+    }
+    g->ncc = ch;
+    g->nse = se;
+    g->nout = cfg->ps ? 2 : ch;
+    g->out_len = cfg->sbr ? 2048 : 1024;
+    g->sr_index = cfg->sr_index;
+    g->sbr = cfg->sbr != 0;
+    g->ps = cfg->ps != 0;
+    g->add_bias = cfg->add_bias;
+    g->sf_scale = cfg->sf_scale;
+}
+
+static int init_state(HeaacContext *c)
+{
+    const HeaacGeom *g = &c->geom;
+    size_t nch = (size_t)g->n_streams * g->ncc;
+    CK(cudaMemsetAsync(c->d_chan, 0, nch * sizeof(HeaacChanState), c->stream));
+    if (g->sbr) {
+        CK(cudaMemsetAsync(c->d_synth, 0, (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState), c->stream));
+        CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * 2 * 38 * 64 * sizeof(float), c->stream));
+        CK(cudaMemsetAsync(c->d_core_time, 0, nch * 1024 * sizeof(float), c->stream));
+    }
+    if (g->ps) CK(cudaMemsetAsync(c->d_ps, 0, (size_t)g->n_streams * sizeof(HeaacPsState), c->stream));
+    /* everything the reference initialises to non-zero (kx' = 32, e_a[1] = -1; aacsbr.c:128-137) lives in
+     * the parser-owned parameter structs, so the all-zero block IS the post-init state. */
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
+{
+    if (!cfg || !out) return HEAAC_E_INVAL;
+    *out = nullptr;
+    if (cfg->abi_version != HEAAC_ABI_VERSION) return HEAAC_E_INVAL;
+    if (cfg->n_streams <= 0 || cfg->n_elems <= 0 || cfg->n_elems > HEAAC_MAX_ELEMS) return HEAAC_E_INVAL;
+    if (cfg->sr_index < 0 || cfg->sr_index > 12) return HEAAC_E_INVAL;
+    if (cfg->max_frames_per_call <= 0) return HEAAC_E_INVAL;
+    int nch = 0, has_lfe = 0;
+    for (int e = 0; e < cfg->n_elems; e++) {
+        int t = cfg->elem_type[e];
+        if (t != HEAAC_TYPE_SCE && t != HEAAC_TYPE_CPE && t != HEAAC_TYPE_LFE) return HEAAC_E_INVAL;
+        nch += t == HEAAC_TYPE_CPE ? 2 : 1;
+        has_lfe |= t == HEAAC_TYPE_LFE;
+    }
+    if (nch > HEAAC_MAX_CHANNELS) return HEAAC_E_INVAL;
+    if (cfg->ps && !(cfg->sbr && cfg->n_elems == 1 && cfg->elem_type[0] == HEAAC_TYPE_SCE)) return HEAAC_E_INVAL;
+    if (cfg->sbr && has_lfe) return HEAAC_E_UNSUPPORTED;     /* see DESIGN.md "out of scope" */
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        fprintf(stderr, "heaac_b200: no usable CUDA device (this library has no CPU path)\n");
+        return HEAAC_E_NODEV;
+    }
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) {
+        fprintf(stderr, "heaac_b200: device %d is sm_%d%d; this build targets sm_100a only\n", cfg->device, prop.major, prop.minor);
+        return HEAAC_E_NODEV;
+    }
+
+    HeaacContext *c = new (std::nothrow) HeaacContext();
+    if (!c) return HEAAC_E_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    build_geom(cfg, &c->geom);
+    const HeaacGeom *g = &c->geom;
+    int r = 0;
+#define CKX(call) do { r = cuda_err((call), #call); if (r) { heaac_b200_destroy(c); return r; } } while (0)
+    CKX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKX(cudaEventCreate(&c->ev0));
+    CKX(cudaEventCreate(&c->ev1));
+    {
+        HeaacDevTables *h = (HeaacDevTables *)malloc(sizeof(HeaacDevTables));
+        if (!h) { heaac_b200_destroy(c); return HEAAC_E_NOMEM; }
+        heaac_build_tables(h);
+        r = cuda_err(cudaMalloc(&c->d_tables, sizeof(HeaacDevTables)), "cudaMalloc tables");
+        if (!r) r = cuda_err(cudaMemcpy(c->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "upload tables");
+        free(h);
+        if (r) { heaac_b200_destroy(c); return r; }
+    }
+    size_t S = g->n_streams, T = cfg->max_frames_per_call;
+    CKX(cudaMalloc(&c->d_chan, S * g->ncc * sizeof(HeaacChanState)));
+    if (g->sbr) {
+        CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
+        CKX(cudaMalloc(&c->d_X, S * g->nout * 2 * 38 * 64 * sizeof(float)));
+        CKX(cudaMalloc(&c->d_core_time, S * g->ncc * 1024 * sizeof(float)));
+    }
+    if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
+    CKX(cudaMalloc(&c->s_coeffs, T * S * g->ncc * 1024 * sizeof(float)));
+    CKX(cudaMalloc(&c->s_ics, T * S * g->ncc * sizeof(HeaacIcs)));
+    CKX(cudaMalloc(&c->s_tns, T * S * g->ncc * sizeof(HeaacTns)));
+    if (g->sbr) CKX(cudaMalloc(&c->s_sbr, T * S * g->nse * sizeof(HeaacSbrElem)));
+    if (g->ps)  CKX(cudaMalloc(&c->s_ps, T * S * sizeof(HeaacPsFrame)));
+    CKX(cudaMalloc(&c->s_pcm, T * S * g->out_len * g->nout * sizeof(int16_t)));
+    if (cfg->want_float_out) CKX(cudaMalloc(&c->s_pcm_f32, T * S * g->out_len * g->nout * sizeof(float)));
+
+    c->smem_core = sizeof(HeaacCoreSmem) + 1024 * sizeof(float);
+    c->smem_sbr = sizeof(HeaacSbrSmem);
+    c->smem_ps = sizeof(HeaacPsSmem);
+    c->smem_synth = sizeof(HeaacSynthSmem);
+    CKX(cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_core));
+    CKX(cudaFuncSetAttribute(k_sbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sbr));
+    CKX(cudaFuncSetAttribute(k_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_ps));
+    CKX(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_synth));
+    r = init_state(c);
+    if (r) { heaac_b200_destroy(c); return r; }
+#undef CKX
+    *out = c;
+    return 0;
+}
+
+extern "C" void heaac_b200_destroy(HeaacContext *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
+    cudaFree(c->d_core_time); cudaFree(c->d_X);
+    cudaFree(c->s_coeffs); cudaFree(c->s_ics); cudaFree(c->s_tns); cudaFree(c->s_sbr); cudaFree(c->s_ps);
+    cudaFree(c->s_pcm); cudaFree(c->s_pcm_f32);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int heaac_b200_reset_state(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    return init_state(c);
+}
+
+extern "C" int heaac_b200_n_core_channels(const HeaacContext *c) { return c ? c->geom.ncc : HEAAC_E_INVAL; }
+extern "C" int heaac_b200_n_out_channels(const HeaacContext *c)  { return c ? c->geom.nout : HEAAC_E_INVAL; }
+extern "C" int heaac_b200_frame_out_len(const HeaacContext *c)   { return c ? c->geom.out_len : HEAAC_E_INVAL; }
+extern "C" int heaac_b200_n_sbr_elems(const HeaacContext *c)     { return c ? c->geom.nse : HEAAC_E_INVAL; }
+extern "C" long long heaac_b200_launch_count(const HeaacContext *c) { return c ? c->launches : 0; }
+extern "C" uintptr_t heaac_b200_stream(const HeaacContext *c) { return c ? (uintptr_t)c->stream : 0; }
+
+/* launches for frames [0, n) of a device-resident batch */
+static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
+                         const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32)
+{
+    const HeaacGeom g = c->geom;
+    const size_t S = g.n_streams;
+    const size_t pcm_frame = S * g.out_len * g.nout;
+    for (int f = 0; f < n_frames; f++) {
+        const float *co = coeffs + (size_t)f * S * g.ncc * 1024;
+        const HeaacIcs *ic = ics + (size_t)f * S * g.ncc;
+        const HeaacTns *tn = tns ? tns + (size_t)f * S * g.ncc : nullptr;
+        int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
+        float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+        k_core<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_core, c->stream>>>(
+            g, co, ic, tn, c->d_chan, c->d_core_time, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+        c->launches++;
+        if (g.sbr) {
+            const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
+            k_sbr<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_sbr, c->stream>>>(
+                g, c->d_core_time, sb, c->d_chan, c->d_X, c->d_tables);
+            c->launches++;
+            if (g.ps) {
+                k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(
+                    g, ps + (size_t)f * S, sb, c->d_ps, c->d_X, c->d_tables);
+                c->launches++;
+            }
+            k_synth<<<(unsigned)(S * g.nout), HEAAC_THREADS, c->smem_synth, c->stream>>>(
+                g, c->d_X, c->d_synth, pc, pf, c->d_tables);
+            c->launches++;
+        }
+    }
+    return cuda_err(cudaGetLastError(), "kernel launch");
+}
+
+extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
+{
+    if (!c || !b || b->n_frames <= 0 || !b->coeffs || !b->ics) return HEAAC_E_INVAL;
+    const HeaacGeom *g = &c->geom;
+    if (g->sbr && !b->sbr) return HEAAC_E_INVAL;
+    if (g->ps && !b->ps) return HEAAC_E_INVAL;
+    if (!b->pcm && !b->pcm_f32) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    if (b->on_device)
+        return launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32);
+
+    if (b->pcm_f32 && !c->s_pcm_f32) return HEAAC_E_INVAL;   /* context created without want_float_out */
+    const size_t S = g->n_streams;
+    const int Tmax = c->cfg.max_frames_per_call;
+    for (int f0 = 0; f0 < b->n_frames; f0 += Tmax) {
+        int n = b->n_frames - f0 < Tmax ? b->n_frames - f0 : Tmax;
+        size_t nch = (size_t)n * S * g->ncc, och = (size_t)f0 * S * g->ncc;
+        CK(cudaMemcpyAsync(c->s_coeffs, b->coeffs + och * 1024, nch * 1024 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->s_ics, b->ics + och, nch * sizeof(HeaacIcs), cudaMemcpyHostToDevice, c->stream));
+        if (b->tns) CK(cudaMemcpyAsync(c->s_tns, b->tns + och, nch * sizeof(HeaacTns), cudaMemcpyHostToDevice, c->stream));
+        if (g->sbr) CK(cudaMemcpyAsync(c->s_sbr, b->sbr + (size_t)f0 * S * g->nse, (size_t)n * S * g->nse * sizeof(HeaacSbrElem),
+                                       cudaMemcpyHostToDevice, c->stream));
+        if (g->ps)  CK(cudaMemcpyAsync(c->s_ps, b->ps + (size_t)f0 * S, (size_t)n * S * sizeof(HeaacPsFrame),
+                                       cudaMemcpyHostToDevice, c->stream));
+        int r = launch_frames(c, n, c->s_coeffs, c->s_ics, b->tns ? c->s_tns : nullptr, c->s_sbr, c->s_ps,
+                              c->s_pcm, b->pcm_f32 ? c->s_pcm_f32 : nullptr);
+        if (r) return r;
+        size_t pcm_n = (size_t)n * S * g->out_len * g->nout, pcm_o = (size_t)f0 * S * g->out_len * g->nout;
+        if (b->pcm) CK(cudaMemcpyAsync(b->pcm + pcm_o, c->s_pcm, pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+        if (b->pcm_f32) CK(cudaMemcpyAsync(b->pcm_f32 + pcm_o, c->s_pcm_f32, pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int heaac_b200_sync(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    return cuda_err(cudaGetLastError(), "sync");
+}
+
+extern "C" int heaac_b200_dev_alloc(HeaacContext *c, size_t bytes, void **dptr)
+{
+    if (!c || !dptr) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMalloc(dptr, bytes));
+    return 0;
+}
+extern "C" int heaac_b200_dev_free(HeaacContext *c, void *dptr)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaFree(dptr));
+    return 0;
+}
+extern "C" int heaac_b200_dev_upload(HeaacContext *c, void *dptr, const void *hptr, size_t bytes)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int heaac_b200_dev_download(HeaacContext *c, void *hptr, const void *dptr, size_t bytes)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int heaac_b200_timer_start(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+extern "C" int heaac_b200_timer_stop(HeaacContext *c, float *ms)
+{
+    if (!c || !ms) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+extern "C" int heaac_b200_debug_read(HeaacContext *c, const char *name, void *dst, size_t bytes)
+{
+    if (!c || !name || !dst) return HEAAC_E_INVAL;
+    const HeaacGeom *g = &c->geom;
+    const void *src = nullptr; size_t avail = 0;
+    if (!strcmp(name, "X") && c->d_X) { src = c->d_X; avail = (size_t)g->n_streams * g->nout * 2 * 38 * 64 * sizeof(float); }
+    else if (!strcmp(name, "core_time") && c->d_core_time) { src = c->d_core_time; avail = (size_t)g->n_streams * g->ncc * 1024 * sizeof(float); }
+    else if (!strcmp(name, "chan_state")) { src = c->d_chan; avail = (size_t)g->n_streams * g->ncc * sizeof(HeaacChanState); }
+    else if (!strcmp(name, "synth_state") && c->d_synth) { src = c->d_synth; avail = (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState); }
+    else if (!strcmp(name, "ps_state") && c->d_ps) { src = c->d_ps; avail = (size_t)g->n_streams * sizeof(HeaacPsState); }
+    else if (!strcmp(name, "tables")) { src = c->d_tables; avail = sizeof(HeaacDevTables); }
+    if (!src) return HEAAC_E_INVAL;
+    if (bytes > avail) bytes = avail;
+    return heaac_b200_dev_download(c, dst, src, bytes) ? HEAAC_E_LAUNCH : (int)(bytes > 0x7fffffff ? 0x7fffffff : bytes);
+}
+
+/* ---- ff_mdct_init / ff_imdct_half / ff_mdct_end shims (batch of one) -------------------- */
+struct HeaacMdct {
+    int nbits; float *d_tcos, *d_tsin, *d_in, *d_out; HeaacDevTables *d_tables; cudaStream_t stream;
+};
+
+__global__ void k_imdct_half_one(float *out, const float *in, const float *tcos, const float *tsin,
+                                 int log2n4, const HeaacDevTables *T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *buf = reinterpret_cast<float *>(smem_raw);
+    const int n4 = 1 << log2n4, n2 = n4 * 2;
+    float *zr = buf + n2, *zi = zr + n4;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) buf[i] = in[i];
+    __syncthreads();
+    heaac_imdct_half_smem(buf, buf, zr, zi, log2n4, 1, tcos, tsin, T, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) out[i] = buf[i];
+}
+
+extern "C" int heaac_b200_mdct_init(HeaacMdct **out, int nbits, int inverse, double scale)
+{
+    if (!out || !inverse) return HEAAC_E_INVAL;
+    if (nbits < 5 || nbits > 11) return HEAAC_E_UNSUPPORTED;    /* FFT twiddle table covers up to 512 points */
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return HEAAC_E_NODEV;
+    HeaacMdct *m = (HeaacMdct *)calloc(1, sizeof(*m));
+    if (!m) return HEAAC_E_NOMEM;
+    m->nbits = nbits;
+    int n = 1 << nbits, n4 = n >> 2;
+    float *tc = (float *)malloc(sizeof(float) * n4 * 2), *ts = tc + n4;
+    double theta = 1.0 / 8.0 + (scale < 0 ? n4 : 0), sc = sqrt(fabs(scale));
+    for (int i = 0; i < n4; i++) {
+        double alpha = 2 * 3.14159265358979323846 * (i + theta) / n;
+        tc[i] = -cos(alpha) * sc; ts[i] = -sin(alpha) * sc;
+    }
+    HeaacDevTables *h = (HeaacDevTables *)malloc(sizeof(HeaacDevTables));
+    heaac_build_tables(h);
+    int r = 0;
+    if (!r) r = cuda_err(cudaMalloc(&m->d_tables, sizeof(HeaacDevTables)), "cudaMalloc");
+    if (!r) r = cuda_err(cudaMemcpy(m->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "cudaMemcpy");
+    if (!r) r = cuda_err(cudaMalloc(&m->d_tcos, sizeof(float) * n4 * 2), "cudaMalloc");
+    if (!r) r = cuda_err(cudaMemcpy(m->d_tcos, tc, sizeof(float) * n4 * 2, cudaMemcpyHostToDevice), "cudaMemcpy");
+    if (!r) r = cuda_err(cudaMalloc(&m->d_in, sizeof(float) * n), "cudaMalloc");
+    free(h); free(tc);
+    if (r) { heaac_b200_mdct_end(m); return r; }
+    m->d_tsin = m->d_tcos + n4;
+    m->d_out = m->d_in + n / 2;
+    *out = m;
+    return 0;
+}
+
+extern "C" void heaac_b200_imdct_half(HeaacMdct *m, float *output, const float *input)
+{
+    if (!m) return;
+    int n = 1 << m->nbits, n2 = n >> 1, n4 = n >> 2;
+    cudaMemcpy(m->d_in, input, sizeof(float) * n2, cudaMemcpyHostToDevice);
+    k_imdct_half_one<<<1, 256, sizeof(float) * (n2 + 2 * n4)>>>(m->d_out, m->d_in, m->d_tcos, m->d_tsin,
+                                                                 m->nbits - 2, m->d_tables);
+    cudaMemcpy(output, m->d_out, sizeof(float) * n2, cudaMemcpyDeviceToHost);
+}
+
+extern "C" void heaac_b200_mdct_end(HeaacMdct *m)
+{
+    if (!m) return;
+    cudaFree(m->d_tables); cudaFree(m->d_tcos); cudaFree(m->d_in);
+    free(m);
+}
+
+extern "C" const char *heaac_b200_version(void) { return "heaac_b200 0.1 (sm_100a)"; }
+extern "C" const char *heaac_b200_strerror(int err)
+{
+    switch (err) {
+    case HEAAC_OK: return "ok";
+    case HEAAC_E_INVAL: return "invalid argument";
+    case HEAAC_E_NOMEM: return "out of memory";
+    case HEAAC_E_NODEV: return "no usable sm_100 CUDA device (no CPU path exists)";
+    case HEAAC_E_LAUNCH: return "CUDA launch or runtime failure";
+    case HEAAC_E_UNSUPPORTED: return "not supported by this build";
+    default: return "unknown error";
+    }
+}
+
+/* struct sizes, so that language bindings can assert their mirrors (abi.py) */
+extern "C" int heaac_b200_sizeof(const char *name)
+{
+    if (!strcmp(name, "HeaacIcs")) return (int)sizeof(HeaacIcs);
+    if (!strcmp(name, "HeaacTns")) return (int)sizeof(HeaacTns);
+    if (!strcmp(name, "HeaacSbrChan")) return (int)sizeof(HeaacSbrChan);
+    if (!strcmp(name, "HeaacSbrElem")) return (int)sizeof(HeaacSbrElem);
+    if (!strcmp(name, "HeaacPsFrame")) return (int)sizeof(HeaacPsFrame);
+    if (!strcmp(name, "HeaacConfig")) return (int)sizeof(HeaacConfig);
+    if (!strcmp(name, "HeaacBatch")) return (int)sizeof(HeaacBatch);
+    if (!strcmp(name, "HeaacChanState")) return (int)sizeof(HeaacChanState);
+    if (!strcmp(name, "HeaacSynthState")) return (int)sizeof(HeaacSynthState);
+    if (!strcmp(name, "HeaacPsState")) return (int)sizeof(HeaacPsState);
+    if (!strcmp(name, "HeaacDevTables")) return (int)sizeof(HeaacDevTables);
+    return -1;
+}

@@ -1,0 +1,1199 @@
+/*
+ * heaac_kernels.cuh -- CTA-level routines of the HE-AAC synthesis path (sm_100a).
+ *
+ * Each routine is executed by one CTA that owns one channel (or one PS stream) for one
+ * frame.  Work inside a routine is expressed as strided loops over `tid/nt` separated by
+ * HEAAC_SYNC(), with every intermediate of the frame staged in shared memory; HBM is touched
+ * only for the frame's inputs, the per-channel state block and the outputs.
+ *
+ * Reference functions restated here (all from /root/reference/libavcodec):
+ *   core_channel   : apply_tns aacdec.c:1698-1736 (+ lpc.h:61-103), imdct_and_windowing
+ *                    aacdec.c:1741-1806, ff_imdct_half_c mdct.c:124-159,
+ *                    ff_vector_fmul_window_c dsputil.c:3832-3845
+ *   sbr_channel    : sbr_dequant aacsbr.c:1089-1128, sbr_qmf_analysis 1136-1169, sbr_lf_gen
+ *                    1337-1357, sbr_hf_inverse_filter 1232-1313, sbr_chirp 1316-1334, sbr_hf_gen
+ *                    1360-1409, sbr_mapping 1451-1496, sbr_env_estimate 1499-1546, sbr_gain_calc
+ *                    1552-1605, sbr_hf_assemble 1608-1714, sbr_x_gen 1412-1446
+ *   ps_stream      : ff_ps_apply aacps.c:973-992 and everything it calls (283-971)
+ *   synth_channel  : sbr_qmf_synthesis aacsbr.c:1175-1230, float_to_int16 dsputil.c:3972-4001
+ */
+#ifndef HEAAC_KERNELS_CUH
+#define HEAAC_KERNELS_CUH
+
+#include "heaac_dev.cuh"
+
+#ifdef HEAAC_HOST_EMU
+#define HEAAC_CONST_TABLE static const
+#else
+#define HEAAC_CONST_TABLE __device__ const
+#endif
+/* double literals narrowed to float exactly as the reference's `static const float` tables are */
+HEAAC_CONST_TABLE float heaac_h_smooth[5] = { (float)0.33333333333333, (float)0.30150283239582, (float)0.21816949906249,
+                                              (float)0.11516383427084, (float)0.03183050093751 };   /* aacsbr.c:1616-1622 */
+HEAAC_CONST_TABLE float heaac_limgain[4] = { (float)0.70795, (float)1.0, (float)1.41254, (float)10000000000.0 };  /* aacsbr.c:1557 */
+
+#define HEAAC_MIN(a, b) ((a) > (b) ? (b) : (a))     /* FFMIN semantics incl. NaN behaviour */
+#define HEAAC_MAX(a, b) ((a) > (b) ? (a) : (b))     /* FFMAX */
+
+/* ------------------------------------------------------------------------------------
+ * float -> int16 (dsputil.c:3972-3982 for the C "bias" convention; cvtps2dq-style RNE +
+ * saturation for the s16-unit convention; both give the same s16)
+ * ---------------------------------------------------------------------------------- */
+HEAAC_DEV int16_t heaac_to_s16(float x, int bias_mode)
+{
+    if (bias_mode) {
+        int32_t bits;
+#ifdef HEAAC_HOST_EMU
+        memcpy(&bits, &x, 4);
+#else
+        bits = __float_as_int(x);
+#endif
+        long long tmp = bits;
+        if (tmp & 0xf0000) tmp = (0x43c0ffffLL - tmp) >> 31;
+        return (int16_t)(tmp - 0x8000);
+    }
+    float r = heaac_rint(x);
+    r = r < -32768.0f ? -32768.0f : (r > 32767.0f ? 32767.0f : r);
+    return (int16_t)(int)r;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Batched in-place complex FFT in shared memory, X[m] = sum_k x[k] e^{+2 pi i km/n}
+ * (the un-normalised inverse convention of ff_fft_calc with inverse = 1, fft.c:81-176).
+ * Input must already be in bit-reversed order.  `nbatch` transforms of 2^log2n points lie
+ * back to back.  Radix-2, one butterfly per work item, log2n barriers.
+ * ---------------------------------------------------------------------------------- */
+HEAAC_DEV void heaac_fft_smem(float *re, float *im, int log2n, int nbatch,
+                              const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    const int hn = 1 << (log2n - 1);
+    const int total = nbatch * hn;
+    for (int s = 1; s <= log2n; s++) {
+        const int half = 1 << (s - 1);
+        const int tw_stride = 512 >> s;
+        for (int w = tid; w < total; w += nt) {
+            int b = w >> (log2n - 1), r = w & (hn - 1);
+            int j = r & (half - 1), grp = r >> (s - 1);
+            int i0 = (b << log2n) + (grp << s) + j, i1 = i0 + half;
+            float wr = T->fft_wre[j * tw_stride], wi = T->fft_wim[j * tw_stride];
+            float xr = re[i1], xi = im[i1];
+            float tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
+            float ar = re[i0], ai = im[i0];
+            re[i1] = ar - tr; im[i1] = ai - ti;
+            re[i0] = ar + tr; im[i0] = ai + ti;
+        }
+        HEAAC_SYNC();
+    }
+}
+
+HEAAC_DEV int heaac_bitrev(int k, int bits)
+{
+#ifdef HEAAC_HOST_EMU
+    int r = 0;
+    for (int b = 0; b < bits; b++) r |= ((k >> b) & 1) << (bits - 1 - b);
+    return r;
+#else
+    return (int)(__brev((unsigned)k) >> (32 - bits));
+#endif
+}
+
+/* Batched half-IMDCT of size N = 4 * n4 (mdct.c:124-159): `in` holds nbatch * N/2 inputs,
+ * `out` receives nbatch * N/2 outputs; in and out may alias (input is consumed by the
+ * pre-rotation before anything is written).  zr/zi: nbatch * n4 floats of scratch each. */
+HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, float *zi,
+                                     int log2n4, int nbatch,
+                                     const float *HEAAC_RESTRICT tcos, const float *HEAAC_RESTRICT tsin,
+                                     const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    const int n4 = 1 << log2n4, n2 = n4 << 1, n8 = n4 >> 1;
+    for (int w = tid; w < nbatch * n4; w += nt) {
+        int b = w >> log2n4, k = w & (n4 - 1);
+        const float *x = in + b * n2;
+        float a = x[n2 - 1 - 2 * k], c = x[2 * k];
+        int rk = heaac_bitrev(k, log2n4);
+        zr[b * n4 + rk] = a * tcos[k] - c * tsin[k];
+        zi[b * n4 + rk] = a * tsin[k] + c * tcos[k];
+    }
+    HEAAC_SYNC();
+    heaac_fft_smem(zr, zi, log2n4, nbatch, T, tid, nt);
+    for (int w = tid; w < nbatch * n8; w += nt) {
+        int b = w / n8, k = w - b * n8;
+        int p = n8 - k - 1, q = n8 + k;
+        const float *r_ = zr + b * n4, *i_ = zi + b * n4;
+        float *o = out + b * n2;
+        float r0 = i_[p] * tsin[p] - r_[p] * tcos[p];
+        float i1 = i_[p] * tcos[p] + r_[p] * tsin[p];
+        float r1 = i_[q] * tsin[q] - r_[q] * tcos[q];
+        float i0 = i_[q] * tcos[q] + r_[q] * tsin[q];
+        o[2 * p] = r0; o[2 * p + 1] = i0;
+        o[2 * q] = r1; o[2 * q + 1] = i1;
+    }
+    HEAAC_SYNC();
+}
+
+/* ====================================================================================
+ * AAC-LC core: TNS + IMDCT + windowing + overlap-add for one channel-frame
+ * ================================================================================== */
+struct HeaacCoreSmem {
+    float c[1024];          /* coefficients, then the half-IMDCT output ("buf") */
+    float zr[512], zi[512];
+    float temp[128];
+    float lpc[8][HEAAC_TNS_MAX_ORDER];
+    int   tns_start[8], tns_size[8], tns_inc[8], tns_order[8];
+};
+
+HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const float *HEAAC_RESTRICT win,
+                         float bias, int len, int tid, int nt)
+{
+    for (int i = tid; i < len; i += nt) {
+        int j = 2 * len - 1 - i;
+        float a = s0[i], b = s1[len - 1 - i], wi = win[i], wj = win[j];
+        dst[i] = a * wj - b * wi + bias;
+        dst[j] = a * wi + b * wj + bias;
+    }
+}
+
+/* `out` : 1024 floats in shared or global memory (time-domain output, bias included) */
+HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT coeffs,
+                                  const HeaacIcs *HEAAC_RESTRICT ics_p, const HeaacTns *HEAAC_RESTRICT tns,
+                                  HeaacChanState *st, float *out, float bias, int sr_index,
+                                  const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    const HeaacIcs ics = *ics_p;
+    const int ws0 = ics.window_sequence, ws1 = st->prev_ws, shape_prev = st->prev_shape;
+    const int is8 = ws0 == HEAAC_EIGHT_SHORT;
+
+    for (int i = tid; i < 1024; i += nt) sm->c[i] = coeffs[i];
+
+    /* ---- TNS: set up the (at most 8) independent filters, aacdec.c:1701-1728 ---- */
+    const int use_tns = ics.tns_present && tns;
+    if (use_tns) {
+        for (int slot = tid; slot < 8; slot += nt) {
+            sm->tns_size[slot] = 0;
+            int w = is8 ? slot : 0;
+            int nf = tns->n_filt[w];
+            int f = is8 ? 0 : slot;
+            if (f >= nf || (is8 ? 0 : slot >= 3)) continue;
+            const uint16_t *swb = is8 ? T->swb_offset_128[sr_index] : T->swb_offset_1024[sr_index];
+            int num_swb = is8 ? T->num_swb_128[sr_index] : T->num_swb_1024[sr_index];
+            int tmb = is8 ? T->tns_max_bands_128[sr_index] : T->tns_max_bands_1024[sr_index];
+            int mmm = HEAAC_MIN(tmb, (int)ics.max_sfb);
+            int bottom = num_swb, top = num_swb;
+            for (int g = 0; g <= f; g++) {           /* walk down to this filter's band range */
+                int sl = is8 ? w : g;
+                top = bottom;
+                bottom = HEAAC_MAX(0, top - (int)tns->length[sl]);
+            }
+            int order = tns->order[slot];
+            if (!order) continue;
+            float *lpc = sm->lpc[slot];
+            for (int i = 0; i < order; i++) {        /* compute_lpc_coefs(normalize = 0), lpc.h:75-96 */
+                float r = -tns->coef[slot][i];
+                lpc[i] = r;
+                for (int j = 0; j < (i + 1) >> 1; j++) {
+                    float a = lpc[j], b = lpc[i - 1 - j];
+                    lpc[j] = a + r * b;
+                    lpc[i - 1 - j] = b + r * a;
+                }
+            }
+            int start = swb[HEAAC_MIN(bottom, mmm)], end = swb[HEAAC_MIN(top, mmm)];
+            int size = end - start, inc = 1;
+            if (size <= 0) continue;
+            if (tns->direction[slot]) { inc = -1; start = end - 1; }
+            sm->tns_start[slot] = start + w * 128;
+            sm->tns_size[slot] = size;
+            sm->tns_inc[slot] = inc;
+            sm->tns_order[slot] = order;
+        }
+    }
+    HEAAC_SYNC();
+    if (use_tns) {
+        /* all-pole filters over disjoint coefficient ranges: one serial chain per work item */
+        for (int slot = tid; slot < 8; slot += nt) {
+            int size = sm->tns_size[slot];
+            if (size <= 0) continue;
+            int start = sm->tns_start[slot], inc = sm->tns_inc[slot], order = sm->tns_order[slot];
+            const float *lpc = sm->lpc[slot];
+            for (int m = 0; m < size; m++, start += inc) {
+                float acc = sm->c[start];
+                int lim = HEAAC_MIN(m, order);
+                for (int i = 1; i <= lim; i++)
+                    acc -= sm->c[start - i * inc] * lpc[i - 1];
+                sm->c[start] = acc;
+            }
+        }
+        HEAAC_SYNC();
+    }
+
+    /* ---- half IMDCT: 1 x N=2048 or 8 x N=256, aacdec.c:1755-1763 ---- */
+    if (is8)
+        heaac_imdct_half_smem(sm->c, sm->c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid, nt);
+    else
+        heaac_imdct_half_smem(sm->c, sm->c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid, nt);
+
+    /* ---- windowing + overlap-add, aacdec.c:1771-1805 ---- */
+    const float *buf = sm->c;
+    float *saved = st->saved;
+    const float *sw      = ics.window_shape ? T->kbd_128 : T->sine_128;
+    const float *lw_prev = shape_prev ? T->kbd_1024 : T->sine_1024;
+    const float *sw_prev = shape_prev ? T->kbd_128 : T->sine_128;
+    const int prev_long = ws1 == HEAAC_ONLY_LONG || ws1 == HEAAC_LONG_STOP;
+
+    if (prev_long && (ws0 == HEAAC_ONLY_LONG || ws0 == HEAAC_LONG_START)) {
+        heaac_vfw(out, saved, buf, lw_prev, bias, 512, tid, nt);
+    } else {
+        for (int i = tid; i < 448; i += nt) out[i] = saved[i] + bias;
+        heaac_vfw(out + 448, saved + 448, buf, sw_prev, bias, 64, tid, nt);
+        if (is8) {
+            for (int j = 1; j < 4; j++)
+                heaac_vfw(out + 448 + 128 * j, buf + 128 * (j - 1) + 64, buf + 128 * j, sw, bias, 64, tid, nt);
+            heaac_vfw(sm->temp, buf + 3 * 128 + 64, buf + 4 * 128, sw, bias, 64, tid, nt);
+        } else {
+            for (int i = 576 + tid; i < 1024; i += nt) out[i] = buf[i - 512] + bias;
+        }
+    }
+    HEAAC_SYNC();        /* all reads of the old `saved` are done; temp[] is complete */
+    if (is8) {
+        for (int i = tid; i < 64; i += nt) {
+            out[960 + i] = sm->temp[i];
+            saved[i] = sm->temp[64 + i] - bias;
+        }
+        for (int j = 0; j < 3; j++)
+            heaac_vfw(saved + 64 + 128 * j, buf + (4 + j) * 128 + 64, buf + (5 + j) * 128, sw, 0.0f, 64, tid, nt);
+        for (int i = tid; i < 64; i += nt) saved[448 + i] = buf[7 * 128 + 64 + i];
+    } else if (ws0 == HEAAC_LONG_START) {
+        for (int i = tid; i < 448; i += nt) saved[i] = buf[512 + i];
+        for (int i = tid; i < 64; i += nt)  saved[448 + i] = buf[7 * 128 + 64 + i];
+    } else {
+        for (int i = tid; i < 512; i += nt) saved[i] = buf[512 + i];
+    }
+    if (tid == 0) { st->prev_ws = ws0; st->prev_shape = ics.window_shape; }
+    HEAAC_SYNC();
+}
+
+/* ====================================================================================
+ * SBR, one channel-frame: QMF analysis .. X generation
+ * ================================================================================== */
+struct HeaacSbrSmem {
+    float x[1312];                  /* analysis input window: 288 history + 1024 new */
+    float fr[32 * 32], fi[32 * 32]; /* 32 slots x 32-point complex FFT work area */
+    float t[32 * 64];               /* folded + shuffled analysis inputs, then imdct outputs */
+    float xlow[32][40][2];          /* X_low */
+    float xhigh[48][40][2];         /* X_high rows kx .. kx+m-1 */
+    float alpha0[32][2], alpha1[32][2];
+    float env[5][48];               /* dequantised env_facs[1..5] */
+    float noise[2][8];              /* dequantised noise_facs[1..2] */
+    float e_orig[5][48], q_map[5][48], e_curr[5][48], gain[5][48], q_m[5][48], s_m[5][48];
+    float bw[8];
+    uint8_t s_idx[6][48];           /* s_indexmapped[0..5] */
+    uint8_t s_map[5][48];
+    int8_t  env_of_slot[48];        /* envelope index covering QMF slot i (or -1) */
+    float   ynew[6 * 64 * 2];       /* Y[1][32..37] computed this frame */
+    uint8_t ynew_valid[6 * 64];
+    HeaacSbrElem p;                 /* this frame's parameters */
+};
+
+/* exact 2^(k/2): exp2f of a multiple of 0.5 equals ldexp(1 or sqrt2, n) in glibc too */
+HEAAC_DEV float heaac_exp2_half(float x)
+{
+    float fl = floorf(x);
+    int n = (int)fl;
+    float m = (x != fl) ? 1.41421356237309504880f : 1.0f;
+#ifdef HEAAC_HOST_EMU
+    return ldexpf(m, n);
+#else
+    return ldexpf(m, n);
+#endif
+}
+
+HEAAC_DEV void heaac_sbr_dequant(HeaacSbrSmem *sm, int ch, int is_cpe, int tid, int nt)
+{
+    const HeaacSbrElem *p = &sm->p;
+    const HeaacSbrChan *pc = &p->ch[ch];
+    if (is_cpe && p->bs_coupling) {
+        const HeaacSbrChan *p0 = &p->ch[0], *p1 = &p->ch[1];
+        float alpha      = p0->bs_amp_res ?  1.0f :  0.5f;
+        float pan_offset = p0->bs_amp_res ? 12.0f : 24.0f;
+        for (int w = tid; w < p0->bs_num_env * 48; w += nt) {
+            int e = w / 48, k = w - e * 48;
+            if (k >= p->n[p0->bs_freq_res[e + 1]]) continue;
+            float t1 = heaac_exp2_half((float)p0->env_q[e][k] * alpha + 7.0f);
+            float t2 = heaac_exp2_half((pan_offset - (float)p1->env_q[e][k]) * alpha);
+            float fac = heaac_fdiv(t1, 1.0f + t2);
+            sm->env[e][k] = ch ? fac * t2 : fac;
+        }
+        for (int w = tid; w < p0->bs_num_noise * 8; w += nt) {
+            int e = w >> 3, k = w & 7;
+            if (k >= p->n_q) continue;
+            float t1 = heaac_exp2_half(6.0f - (float)p0->noise_q[e][k] + 1);
+            float t2 = heaac_exp2_half(12 - (float)p1->noise_q[e][k]);
+            float fac = heaac_fdiv(t1, 1.0f + t2);
+            sm->noise[e][k] = ch ? fac * t2 : fac;
+        }
+    } else {
+        float alpha = pc->bs_amp_res ? 1.0f : 0.5f;
+        for (int w = tid; w < pc->bs_num_env * 48; w += nt) {
+            int e = w / 48, k = w - e * 48;
+            if (k >= p->n[pc->bs_freq_res[e + 1]]) continue;
+            sm->env[e][k] = heaac_exp2_half(alpha * (float)pc->env_q[e][k] + 6.0f);
+        }
+        for (int w = tid; w < pc->bs_num_noise * 8; w += nt) {
+            int e = w >> 3, k = w & 7;
+            if (k >= p->n_q) continue;
+            sm->noise[e][k] = heaac_exp2_half(6.0f - (float)pc->noise_q[e][k]);
+        }
+    }
+}
+
+struct HeaacYCtx {
+    int h_SL, i_lo, i_hi, t_old2, kx, m_max, reset, e_a0, e_a1;
+    uint32_t noise0, sine0;
+};
+
+/* Y[1][i][kx + m] of sbr_hf_assemble (aacsbr.c:1649-1710) for one (slot, band).
+ * g_temp/q_temp row r (= i + h_SL - j) holds gain[env(r - h_SL)] when slot r - h_SL belongs to this
+ * frame, otherwise one of the four history rows (aacsbr.c:1632-1640). */
+HEAAC_DEV void heaac_sbr_y(const HeaacSbrSmem *sm, const HeaacChanState *st, const HeaacYCtx *y,
+                           const HeaacDevTables *HEAAC_RESTRICT T, int i, int m, float *yre_o, float *yim_o)
+{
+    const int e = sm->env_of_slot[i];
+    const int at_border = (e == y->e_a0 || e == y->e_a1);
+    float g_filt, q_filt;
+    if (y->h_SL && !at_border) {
+        g_filt = 0.0f; q_filt = 0.0f;
+        for (int j = 0; j <= 4; j++) {
+            int src = i - j;
+            float gv, qv;
+            if (src >= y->i_lo) {
+                int es = sm->env_of_slot[src];
+                gv = sm->gain[es][m]; qv = sm->q_m[es][m];
+            } else if (y->reset) {
+                gv = sm->gain[0][m]; qv = sm->q_m[0][m];
+            } else {
+                int hr = y->t_old2 + (src + 4 - y->i_lo) - 32;     /* history row relative to row 32 */
+                gv = (hr >= 0 && hr < 10) ? st->g_hist[hr * 48 + m] : 0.0f;
+                qv = (hr >= 0 && hr < 10) ? st->q_hist[hr * 48 + m] : 0.0f;
+            }
+            g_filt = heaac_fadd(g_filt, heaac_fmul(gv, heaac_h_smooth[j]));
+            q_filt = heaac_fadd(q_filt, heaac_fmul(qv, heaac_h_smooth[j]));
+        }
+    } else {
+        g_filt = sm->gain[e][m];
+        q_filt = sm->q_m[e][m];
+    }
+    float yre = heaac_fmul(sm->xhigh[m][i + 2][0], g_filt);
+    float yim = heaac_fmul(sm->xhigh[m][i + 2][1], g_filt);
+    const int indexsine = (int)((y->sine0 + (uint32_t)(i - y->i_lo)) & 3);
+    const int phi_sign = (1 - 2 * (y->kx & 1)) * ((m & 1) ? -1 : 1);
+    const int phi_re = indexsine == 0 ? 1 : indexsine == 2 ? -1 : 0;
+    const int phi_im = indexsine == 1 ? 1 : indexsine == 3 ? -1 : 0;
+    const float s = sm->s_m[e][m];
+    if (!at_border && !s) {
+        uint32_t idx = (y->noise0 + (uint32_t)(i - y->i_lo) * (uint32_t)y->m_max + (uint32_t)m + 1u) & 0x1ff;
+        yre = heaac_fadd(yre, heaac_fmul(q_filt, T->noise[2 * idx]));
+        yim = heaac_fadd(yim, heaac_fmul(q_filt, T->noise[2 * idx + 1]));
+    } else {
+        yre = heaac_fadd(yre, heaac_fmul(s, (float)phi_re));
+        yim = heaac_fadd(yim, heaac_fmul(s, (float)(phi_im * phi_sign)));
+    }
+    *yre_o = yre; *yim_o = yim;
+}
+
+/* core_time: 1024 floats (global) of this channel's IMDCT output.
+ * X_out   : this channel's X[2][38][64] plane in global scratch. */
+HEAAC_DEV void heaac_sbr_channel(HeaacSbrSmem *sm, const float *HEAAC_RESTRICT core_time,
+                                 const HeaacSbrElem *HEAAC_RESTRICT elem, int ch, int is_cpe,
+                                 HeaacChanState *st, float *X_out, float ana_scale,
+                                 const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    /* ---- stage parameters and the analysis input window ---- */
+    {
+        const uint32_t *src = (const uint32_t *)elem;
+        uint32_t *dst = (uint32_t *)&sm->p;
+        for (int i = tid; i < (int)(sizeof(HeaacSbrElem) / 4); i += nt) dst[i] = src[i];
+    }
+    for (int i = tid; i < 288; i += nt) sm->x[i] = st->ana_hist[i];
+    for (int i = tid; i < 1024; i += nt) {
+        float v = core_time[i];
+        sm->x[288 + i] = ana_scale != 1.0f ? v * ana_scale : v;
+    }
+    HEAAC_SYNC();
+    const HeaacSbrElem *p = &sm->p;
+    const HeaacSbrChan *pc = &p->ch[ch];
+    const int kx = p->kx[1], kx0 = p->kx[0], m_max = p->m[1], m0 = p->m[0];
+    const int nenv = pc->bs_num_env;
+    for (int i = tid; i < 288; i += nt) st->ana_hist[i] = sm->x[1024 + i];
+
+    /* ---- QMF analysis, aacsbr.c:1147-1168: window + 5-way fold + shuffle ---- */
+    for (int w = tid; w < 32 * 64; w += nt) {
+        int i = w >> 6, k = w & 63;
+        const float *x = sm->x + 32 * i;
+        float f = T->qmf_ds[k] * x[319 - k];
+        f = f + T->qmf_ds[k + 64]  * x[319 - k - 64];
+        f = f + T->qmf_ds[k + 128] * x[319 - k - 128];
+        f = f + T->qmf_ds[k + 192] * x[319 - k - 192];
+        f = f + T->qmf_ds[k + 256] * x[319 - k - 256];
+        /* t[0] = u[0]; t[2k-1] = u[k], t[2k] = -u[64-k] (k = 1..31); t[63] = u[32] */
+        int pos; float val = f;
+        if (k == 0) pos = 0;
+        else if (k < 32) pos = 2 * k - 1;
+        else if (k == 32) pos = 63;
+        else { pos = 2 * (64 - k); val = -f; }
+        sm->t[i * 64 + pos] = val;
+    }
+    HEAAC_SYNC();
+    /* 32 half-IMDCTs of N = 128, scale -2 (mdct_ana, aacsbr.c:135) */
+    heaac_imdct_half_smem(sm->t, sm->t, sm->fr, sm->fi, 5, 32, T->tcos_ana, T->tsin_ana, T, tid, nt);
+
+    /* ---- sbr_lf_gen: X_low[k][i] from W (this frame, i >= 8) and the saved W tail (i < 8) ---- */
+    for (int w = tid; w < 32 * 40; w += nt) {
+        int k = w & 31, i = w >> 5;
+        float re = 0.0f, im = 0.0f;
+        if (i >= 8) {
+            if (k < kx) { re = -sm->t[(i - 8) * 64 + 63 - k]; im = sm->t[(i - 8) * 64 + k]; }
+        } else if (k < kx0) {
+            re = st->w_tail[(i * 32 + k) * 2]; im = st->w_tail[(i * 32 + k) * 2 + 1];
+        }
+        sm->xlow[k][i][0] = re; sm->xlow[k][i][1] = im;
+    }
+    HEAAC_SYNC();
+    for (int w = tid; w < 8 * 32; w += nt) {           /* new W tail: slots 24..31, all 32 bands */
+        int i = w >> 5, k = w & 31;
+        st->w_tail[(i * 32 + k) * 2]     = -sm->t[(24 + i) * 64 + 63 - k];
+        st->w_tail[(i * 32 + k) * 2 + 1] =  sm->t[(24 + i) * 64 + k];
+    }
+
+    if (p->start) {
+        /* ---- inverse filter (one band per work item) + chirp + dequant ---- */
+        for (int k = tid; k < p->k0; k += nt) {
+            const float (*x)[2] = sm->xlow[k];
+            float rs0 = 0.0f, rs1 = 0.0f, is1 = 0.0f, rs2 = 0.0f, is2 = 0.0f;
+            for (int i = 1; i < 38; i++) {
+                rs0 = heaac_fadd(rs0, heaac_fadd(heaac_fmul(x[i][0], x[i][0]), heaac_fmul(x[i][1], x[i][1])));
+                rs1 = heaac_fadd(rs1, heaac_fadd(heaac_fmul(x[i][0], x[i + 1][0]), heaac_fmul(x[i][1], x[i + 1][1])));
+                is1 = heaac_fadd(is1, heaac_fsub(heaac_fmul(x[i][0], x[i + 1][1]), heaac_fmul(x[i][1], x[i + 1][0])));
+                rs2 = heaac_fadd(rs2, heaac_fadd(heaac_fmul(x[i][0], x[i + 2][0]), heaac_fmul(x[i][1], x[i + 2][1])));
+                is2 = heaac_fadd(is2, heaac_fsub(heaac_fmul(x[i][0], x[i + 2][1]), heaac_fmul(x[i][1], x[i + 2][0])));
+            }
+            /* phi[a][b][c] as in autocorrelate(), aacsbr.c:1242-1253 */
+            float phi210 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(x[0][0], x[0][0])), heaac_fmul(x[0][1], x[0][1]));
+            float phi100 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(x[38][0], x[38][0])), heaac_fmul(x[38][1], x[38][1]));
+            float phi110 = heaac_fadd(heaac_fadd(rs1, heaac_fmul(x[0][0], x[1][0])), heaac_fmul(x[0][1], x[1][1]));
+            float phi111 = heaac_fsub(heaac_fadd(is1, heaac_fmul(x[0][0], x[1][1])), heaac_fmul(x[0][1], x[1][0]));
+            float phi000 = heaac_fadd(heaac_fadd(rs1, heaac_fmul(x[38][0], x[39][0])), heaac_fmul(x[38][1], x[39][1]));
+            float phi001 = heaac_fsub(heaac_fadd(is1, heaac_fmul(x[38][0], x[39][1])), heaac_fmul(x[38][1], x[39][0]));
+            float phi010 = heaac_fadd(heaac_fadd(rs2, heaac_fmul(x[0][0], x[2][0])), heaac_fmul(x[0][1], x[2][1]));
+            float phi011 = heaac_fsub(heaac_fadd(is2, heaac_fmul(x[0][0], x[2][1])), heaac_fmul(x[0][1], x[2][0]));
+            float dk = heaac_fsub(heaac_fmul(phi210, phi100),
+                                  heaac_fdiv(heaac_fadd(heaac_fmul(phi110, phi110), heaac_fmul(phi111, phi111)), 1.000001f));
+            float a1r, a1i, a0r, a0i;
+            if (!dk) {
+                a1r = a1i = 0.0f;
+            } else {
+                float tr = heaac_fsub(heaac_fsub(heaac_fmul(phi000, phi110), heaac_fmul(phi001, phi111)), heaac_fmul(phi010, phi100));
+                float ti = heaac_fsub(heaac_fadd(heaac_fmul(phi000, phi111), heaac_fmul(phi001, phi110)), heaac_fmul(phi011, phi100));
+                a1r = heaac_fdiv(tr, dk);
+                a1i = heaac_fdiv(ti, dk);
+            }
+            if (!phi100) {
+                a0r = a0i = 0.0f;
+            } else {
+                float tr = heaac_fadd(heaac_fadd(phi000, heaac_fmul(a1r, phi110)), heaac_fmul(a1i, phi111));
+                float ti = heaac_fsub(heaac_fadd(phi001, heaac_fmul(a1i, phi110)), heaac_fmul(a1r, phi111));
+                a0r = heaac_fdiv(-tr, phi100);
+                a0i = heaac_fdiv(-ti, phi100);
+            }
+            if (heaac_fadd(heaac_fmul(a1r, a1r), heaac_fmul(a1i, a1i)) >= 16.0f ||
+                heaac_fadd(heaac_fmul(a0r, a0r), heaac_fmul(a0i, a0i)) >= 16.0f)
+                a1r = a1i = a0r = a0i = 0.0f;
+            sm->alpha0[k][0] = a0r; sm->alpha0[k][1] = a0i;
+            sm->alpha1[k][0] = a1r; sm->alpha1[k][1] = a1i;
+        }
+        for (int i = tid; i < p->n_q; i += nt) {        /* sbr_chirp */
+            float old = st->bw_array[i], nb;
+            int m0_ = pc->bs_invf_mode[0][i], m1_ = pc->bs_invf_mode[1][i];
+            if (m0_ + m1_ == 1) nb = 0.6f;
+            else nb = m0_ == 0 ? 0.0f : m0_ == 1 ? 0.75f : m0_ == 2 ? 0.9f : 0.98f;
+            if (nb < old) nb = heaac_fadd(heaac_fmul(0.75f, nb), heaac_fmul(0.25f, old));
+            else          nb = heaac_fadd(heaac_fmul(0.90625f, nb), heaac_fmul(0.09375f, old));
+            nb = nb < 0.015625f ? 0.0f : nb;
+            sm->bw[i] = nb;
+            st->bw_array[i] = nb;
+        }
+        heaac_sbr_dequant(sm, ch, is_cpe, tid, nt);
+        for (int i = tid; i < 48; i += nt) {
+            int e = -1;
+            for (int q = 0; q < nenv; q++)
+                if (i >= 2 * pc->t_env[q] && i < 2 * pc->t_env[q + 1]) e = q;
+            sm->env_of_slot[i] = (int8_t)e;
+        }
+        HEAAC_SYNC();
+
+        /* ---- sbr_hf_gen: one (target band, slot) per work item ---- */
+        {
+            const int i_lo = 2 * pc->t_env[0], i_hi = 2 * pc->t_env[nenv];
+            for (int w = tid; w < m_max * 40; w += nt) {
+                int m = w / 40, d = w - m * 40;           /* d = slot index inside X_high (i + 2) */
+                int k = kx + m;
+                /* which patch does band k belong to? */
+                int acc = kx, q = -1;
+                for (int j = 0; j < p->num_patches; j++) {
+                    int nsb = p->patch_num_subbands[j];
+                    if (k < acc + nsb) { q = p->patch_start_subband[j] + (k - acc); break; }
+                    acc += nsb;
+                }
+                int i = d - 2;
+                if (q < 0) {                              /* beyond the last patch: memset(X_high + k, 0) */
+                    sm->xhigh[m][d][0] = 0.0f; sm->xhigh[m][d][1] = 0.0f;
+                    continue;
+                }
+                if (i < i_lo || i >= i_hi) continue;      /* the reference leaves these untouched (never read) */
+                int g = 0;
+                while (g < p->n_q && k >= p->f_tablenoise[g + 1]) g++;
+                float bw = sm->bw[g];
+                float a0 = sm->alpha1[q][0] * bw * bw, a1 = sm->alpha1[q][1] * bw * bw;
+                float a2 = sm->alpha0[q][0] * bw,      a3 = sm->alpha0[q][1] * bw;
+                const float (*xl)[2] = sm->xlow[q];
+                sm->xhigh[m][d][0] = xl[d - 2][0] * a0 - xl[d - 2][1] * a1 + xl[d - 1][0] * a2 - xl[d - 1][1] * a3 + xl[d][0];
+                sm->xhigh[m][d][1] = xl[d - 2][1] * a0 + xl[d - 2][0] * a1 + xl[d - 1][1] * a2 + xl[d - 1][0] * a3 + xl[d][1];
+            }
+        }
+        /* ---- sbr_mapping ---- */
+        for (int w = tid; w < 6 * 48; w += nt) {
+            int e = w / 48, m = w - e * 48;
+            sm->s_idx[e][m] = e == 0 ? st->s_index0[m] : 0;
+        }
+        HEAAC_SYNC();
+        for (int w = tid; w < nenv * 48; w += nt) {
+            int e = w / 48, m = w - e * 48;
+            if (m >= m_max) continue;
+            int band = kx + m;
+            int fr = pc->bs_freq_res[e + 1];
+            const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
+            int i = 0;
+            while (i + 1 < p->n[fr] && band >= tab[i + 1]) i++;
+            sm->e_orig[e][m] = sm->env[e][i];
+            int kq = (pc->bs_num_noise > 1) && (pc->t_env[e] >= pc->t_q[1]);
+            int g = 0;
+            while (g + 1 < p->n_q && band >= p->f_tablenoise[g + 1]) g++;
+            sm->q_map[e][m] = sm->noise[kq][g];
+        }
+        if (pc->bs_add_harmonic_flag) {
+            for (int w = tid; w < nenv * 48; w += nt) {
+                int e = w / 48, i = w - e * 48;
+                if (i >= p->n[1]) continue;
+                int mid = ((int)p->f_tablehigh[i] + (int)p->f_tablehigh[i + 1]) >> 1;
+                sm->s_idx[e + 1][mid - kx] = pc->bs_add_harmonic[i] *
+                    (e >= pc->e_a[1] || sm->s_idx[0][mid - kx] == 1);
+            }
+        }
+        HEAAC_SYNC();
+        for (int w = tid; w < nenv * 48; w += nt) {
+            int e = w / 48, m = w - e * 48;
+            if (m >= m_max) continue;
+            int band = kx + m;
+            int fr = pc->bs_freq_res[e + 1];
+            const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
+            int i = 0;
+            while (i + 1 < p->n[fr] && band >= tab[i + 1]) i++;
+            int present = 0;
+            for (int mm = tab[i]; mm < tab[i + 1]; mm++)
+                if (sm->s_idx[e + 1][mm - kx]) { present = 1; break; }
+            sm->s_map[e][m] = (uint8_t)present;
+        }
+        /* ---- sbr_env_estimate ---- */
+        for (int w = tid; w < nenv * 48; w += nt) {
+            int e = w / 48, m = w - e * 48;
+            if (m >= m_max) continue;
+            int ilb = pc->t_env[e] * 2 + 2, iub = pc->t_env[e + 1] * 2 + 2;
+            if (p->bs_interpol_freq) {
+                float recip = heaac_fdiv(0.5f, (float)(pc->t_env[e + 1] - pc->t_env[e]));
+                float sum = 0.0f;
+                for (int i = ilb; i < iub; i++)
+                    sum = heaac_fadd(sum, heaac_fadd(heaac_fmul(sm->xhigh[m][i][0], sm->xhigh[m][i][0]),
+                                                     heaac_fmul(sm->xhigh[m][i][1], sm->xhigh[m][i][1])));
+                sm->e_curr[e][m] = heaac_fmul(sum, recip);
+            } else {
+                int band = kx + m;
+                int fr = pc->bs_freq_res[e + 1];
+                const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
+                int b = 0;
+                while (b + 1 < p->n[fr] && band >= tab[b + 1]) b++;
+                if (band != tab[b]) continue;            /* first band of the group does the whole group */
+                int env_size = 2 * (pc->t_env[e + 1] - pc->t_env[e]);
+                int den = env_size * (tab[b + 1] - tab[b]);
+                float sum = 0.0f;
+                for (int k = tab[b]; k < tab[b + 1]; k++)
+                    for (int i = ilb; i < iub; i++)
+                        sum = heaac_fadd(sum, heaac_fadd(heaac_fmul(sm->xhigh[k - kx][i][0], sm->xhigh[k - kx][i][0]),
+                                                         heaac_fmul(sm->xhigh[k - kx][i][1], sm->xhigh[k - kx][i][1])));
+                sum = heaac_fdiv(sum, (float)den);
+                for (int k = tab[b]; k < tab[b + 1]; k++) sm->e_curr[e][k - kx] = sum;
+            }
+        }
+        HEAAC_SYNC();
+        /* ---- sbr_gain_calc: one (envelope, limiter band) per work item ---- */
+        for (int w = tid; w < nenv * p->n_lim; w += nt) {
+            int e = w / p->n_lim, k = w - e * p->n_lim;
+            int delta = !((e == pc->e_a[1]) || (e == pc->e_a[0]));
+            int lo = p->f_tablelim[k] - kx, hi = p->f_tablelim[k + 1] - kx;
+            const float limgain = heaac_limgain[p->bs_limiter_gains & 3];
+            float sum0 = 0.0f, sum1 = 0.0f;
+            for (int m = lo; m < hi; m++) {
+                float eo = sm->e_orig[e][m], qm = sm->q_map[e][m], ec = sm->e_curr[e][m];
+                float temp = heaac_fdiv(eo, heaac_fadd(1.0f, qm));
+                sm->q_m[e][m] = heaac_fsqrt(heaac_fmul(temp, qm));
+                sm->s_m[e][m] = heaac_fsqrt(heaac_fmul(temp, (float)sm->s_idx[e + 1][m]));
+                if (!sm->s_map[e][m])
+                    sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(eo, heaac_fmul(heaac_fadd(1.0f, ec),
+                                                 heaac_fadd(1.0f, heaac_fmul(qm, (float)delta)))));
+                else
+                    sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(heaac_fmul(eo, qm),
+                                                 heaac_fmul(heaac_fadd(1.0f, ec), heaac_fadd(1.0f, qm))));
+            }
+            for (int m = lo; m < hi; m++) { sum0 = heaac_fadd(sum0, sm->e_orig[e][m]); sum1 = heaac_fadd(sum1, sm->e_curr[e][m]); }
+            float gain_max = heaac_fmul(limgain, heaac_fsqrt(heaac_fdiv(heaac_fadd(1.1920928955078125e-07f, sum0),
+                                                                       heaac_fadd(1.1920928955078125e-07f, sum1))));
+            gain_max = HEAAC_MIN(100000.0f, gain_max);
+            for (int m = lo; m < hi; m++) {
+                float q_m_max = heaac_fdiv(heaac_fmul(sm->q_m[e][m], gain_max), sm->gain[e][m]);
+                sm->q_m[e][m]  = HEAAC_MIN(sm->q_m[e][m], q_m_max);
+                sm->gain[e][m] = HEAAC_MIN(sm->gain[e][m], gain_max);
+            }
+            sum0 = sum1 = 0.0f;
+            for (int m = lo; m < hi; m++) {
+                float g = sm->gain[e][m], s = sm->s_m[e][m], q = sm->q_m[e][m];
+                sum0 = heaac_fadd(sum0, sm->e_orig[e][m]);
+                float t3 = heaac_fmul(heaac_fmul((float)(delta && !s), q), q);
+                float acc = heaac_fadd(heaac_fadd(heaac_fmul(heaac_fmul(sm->e_curr[e][m], g), g), heaac_fmul(s, s)), t3);
+                sum1 = heaac_fadd(sum1, acc);
+            }
+            float gain_boost = heaac_fsqrt(heaac_fdiv(heaac_fadd(1.1920928955078125e-07f, sum0),
+                                                      heaac_fadd(1.1920928955078125e-07f, sum1)));
+            /* FFMIN(1.584893192 (double), gain_boost) then narrowed to float */
+            gain_boost = (1.584893192 > (double)gain_boost) ? gain_boost : (float)1.584893192;
+            for (int m = lo; m < hi; m++) {
+                sm->gain[e][m] = heaac_fmul(sm->gain[e][m], gain_boost);
+                sm->q_m[e][m]  = heaac_fmul(sm->q_m[e][m], gain_boost);
+                sm->s_m[e][m]  = heaac_fmul(sm->s_m[e][m], gain_boost);
+            }
+        }
+        HEAAC_SYNC();
+    }
+
+    /* ---- sbr_hf_assemble fused with sbr_x_gen: write X[re/im][slot][band] ---- */
+    {
+        HeaacYCtx y;
+        y.h_SL = 4 * !p->bs_smoothing_mode;
+        y.i_lo = p->start ? 2 * pc->t_env[0] : 0;
+        y.i_hi = p->start ? 2 * pc->t_env[nenv] : 0;
+        y.t_old2 = 2 * pc->t_env_num_env_old;
+        y.noise0 = p->reset ? 0u : st->f_indexnoise;
+        y.sine0 = st->f_indexsine;
+        y.kx = kx; y.m_max = m_max; y.reset = p->reset;
+        y.e_a0 = pc->e_a[0]; y.e_a1 = pc->e_a[1];
+        const int i_Temp = HEAAC_MAX(y.t_old2 - 32, 0);
+        float *Xre = X_out, *Xim = X_out + 38 * 64;
+        for (int w = tid; w < 38 * 64; w += nt) {
+            int i = w >> 6, k = w & 63;
+            float re = 0.0f, im = 0.0f;
+            const int in_hf = p->start && i >= y.i_lo && i < y.i_hi && k >= kx && k < kx + m_max;
+            float yre = 0.0f, yim = 0.0f;
+            if (in_hf) heaac_sbr_y(sm, st, &y, T, i, k - kx, &yre, &yim);
+            /* sbr_x_gen, aacsbr.c:1412-1446 */
+            if (i < i_Temp) {
+                if (k < kx0) { re = sm->xlow[k][i + 2][0]; im = sm->xlow[k][i + 2][1]; }
+                else if (k < kx0 + m0) { re = st->y_tail[(i * 64 + k) * 2]; im = st->y_tail[(i * 64 + k) * 2 + 1]; }
+            } else {
+                if (k < kx) { re = sm->xlow[k][i + 2][0]; im = sm->xlow[k][i + 2][1]; }
+                else if (k < kx + m_max && i < 32 && in_hf) { re = yre; im = yim; }
+                /* (slots of Y[1] the envelope grid does not cover would hold stale data of an older
+                 *  frame in the reference; a valid grid always covers [i_Temp, 32)) */
+            }
+            Xre[w] = re; Xim[w] = im;
+            if (i >= 32) {                                /* Y[1][32..37]: next frame's Y[0] tail */
+                sm->ynew[((i - 32) * 64 + k) * 2]     = yre;
+                sm->ynew[((i - 32) * 64 + k) * 2 + 1] = yim;
+                sm->ynew_valid[(i - 32) * 64 + k] = (uint8_t)in_hf;
+            }
+        }
+        HEAAC_SYNC();      /* every read of the old y_tail / g_hist / q_hist is done */
+        for (int w = tid; w < 6 * 64; w += nt)
+            if (sm->ynew_valid[w]) {
+                st->y_tail[2 * w]     = sm->ynew[2 * w];
+                st->y_tail[2 * w + 1] = sm->ynew[2 * w + 1];
+            }
+        if (p->start) {
+            /* g_temp / q_temp rows 32..41 for the next frame, aacsbr.c:1642-1647 */
+            for (int w = tid; w < 10 * 48; w += nt) {
+                int r = 32 + w / 48, m = w % 48;
+                int src = r - y.h_SL;
+                if (m < m_max && src >= y.i_lo && src < y.i_hi) {
+                    int es = sm->env_of_slot[src];
+                    st->g_hist[w] = sm->gain[es][m];
+                    st->q_hist[w] = sm->q_m[es][m];
+                }
+            }
+            for (int m = tid; m < 48; m += nt) st->s_index0[m] = sm->s_idx[nenv][m];
+            if (tid == 0) {
+                st->f_indexnoise = (y.noise0 + (uint32_t)(y.i_hi - y.i_lo) * (uint32_t)m_max) & 0x1ff;
+                st->f_indexsine = (y.sine0 + (uint32_t)(y.i_hi - y.i_lo)) & 3;
+            }
+        }
+        HEAAC_SYNC();
+    }
+}
+
+/* ====================================================================================
+ * Parametric Stereo for one stream-frame (ff_ps_apply, aacps.c:973-992)
+ * ================================================================================== */
+struct HeaacPsSmem {
+    float L[91][32][2];             /* Lbuf: hybrid-domain mono signal, then left output */
+    float R[91][32][2];             /* Rbuf: decorrelated signal, then right output */
+    float in[5][44][2];             /* in_buf: 6 history + 38 new slots of QMF bands 0..4 */
+    float power[34][32];
+    float tgain[34][32];
+    float H[4][2][6][34];           /* H11,H12,H21,H22 [re/im][envelope 0..5][band] */
+    int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
+    HeaacPsFrame p;
+};
+
+HEAAC_DEV void heaac_ps_hyb_cx(const float (*in)[2], const float (*f)[2], float *re, float *im)
+{
+    float sr = f[6][0] * in[6][0], si = f[6][0] * in[6][1];          /* aacps.c:311,344 */
+    for (int j = 0; j < 6; j++) {
+        float a_re = in[j][0], a_im = in[j][1], b_re = in[12 - j][0], b_im = in[12 - j][1];
+        sr += f[j][0] * (a_re + b_re) - f[j][1] * (a_im - b_im);
+        si += f[j][0] * (a_im + b_im) + f[j][1] * (a_re - b_re);
+    }
+    *re = sr; *im = si;
+}
+
+/* index remapping between 10/20/34 parameter bands (aacps.c:461-605) */
+HEAAC_DEV int heaac_ps_map_idx(const int8_t *par, int num_par, int is34, int full, int b)
+{
+    /* returns the remapped index for target band b; caller guarantees b is a band the reference writes */
+    if (is34) {
+        if (num_par == 20 || num_par == 11) {
+            if (b == 4) return (par[2] + par[3]) / 2;
+            if (b == 1) return (par[0] + par[1]) / 2;
+            const int8_t src[34] = { 0, 0, 1, 2, 0, 3, 4, 4, 5, 5, 6, 7, 8, 8, 9, 9, 10, 11, 12, 13,
+                                     14, 14, 15, 15, 16, 16, 17, 17, 18, 18, 18, 18, 19, 19 };
+            return par[src[b]];
+        } else if (num_par == 10 || num_par == 5) {
+            const int8_t src[34] = { 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6,
+                                     7, 7, 7, 7, 8, 8, 8, 8, 9, 9, 9, 9, 9, 9 };
+            if (!full && b == 16) return 0;
+            return par[src[b]];
+        }
+        return par[b];
+    }
+    if (num_par == 34 || num_par == 17) {
+        switch (b) {
+        case 0:  return (2 * par[0] + par[1]) / 3;
+        case 1:  return (par[1] + 2 * par[2]) / 3;
+        case 2:  return (2 * par[3] + par[4]) / 3;
+        case 3:  return (par[4] + 2 * par[5]) / 3;
+        case 4:  return (par[6] + par[7]) / 2;
+        case 5:  return (par[8] + par[9]) / 2;
+        case 6:  return par[10];
+        case 7:  return par[11];
+        case 8:  return (par[12] + par[13]) / 2;
+        case 9:  return (par[14] + par[15]) / 2;
+        case 10: return par[16];
+        case 11: return par[17];
+        case 12: return par[18];
+        case 13: return par[19];
+        case 14: return (par[20] + par[21]) / 2;
+        case 15: return (par[22] + par[23]) / 2;
+        case 16: return (par[24] + par[25]) / 2;
+        case 17: return (par[26] + par[27]) / 2;
+        case 18: return (par[28] + par[29] + par[30] + par[31]) / 4;
+        default: return (par[32] + par[33]) / 2;
+        }
+    } else if (num_par == 10 || num_par == 5) {
+        if (!full && b == 10) return 0;
+        return par[b >> 1];
+    }
+    return par[b];
+}
+
+/* map_val_20_to_34 / map_val_34_to_20 on one row of 34 floats (aacps.c:501-523, 607-643) */
+HEAAC_DEV void heaac_ps_map_val(float *v, int to34)
+{
+    float o[34];
+    if (to34) {
+        const int8_t src[34] = { 0, 0, 1, 2, 0, 3, 4, 4, 5, 5, 6, 7, 8, 8, 9, 9, 10, 11, 12, 13,
+                                 14, 14, 15, 15, 16, 16, 17, 17, 18, 18, 18, 18, 19, 19 };
+        for (int b = 0; b < 34; b++) o[b] = v[src[b]];
+        o[4] = (v[2] + v[3]) * 0.5f;
+        o[1] = (v[0] + v[1]) * 0.5f;
+    } else {
+        for (int b = 0; b < 34; b++) o[b] = v[b];
+        o[0] = (2 * v[0] + v[1]) * 0.33333333f;   o[1] = (v[1] + 2 * v[2]) * 0.33333333f;
+        o[2] = (2 * v[3] + v[4]) * 0.33333333f;   o[3] = (v[4] + 2 * v[5]) * 0.33333333f;
+        o[4] = (v[6] + v[7]) * 0.5f;              o[5] = (v[8] + v[9]) * 0.5f;
+        o[6] = v[10];                             o[7] = v[11];
+        o[8] = (v[12] + v[13]) * 0.5f;            o[9] = (v[14] + v[15]) * 0.5f;
+        o[10] = v[16]; o[11] = v[17]; o[12] = v[18]; o[13] = v[19];
+        o[14] = (v[20] + v[21]) * 0.5f;           o[15] = (v[22] + v[23]) * 0.5f;
+        o[16] = (v[24] + v[25]) * 0.5f;           o[17] = (v[26] + v[27]) * 0.5f;
+        o[18] = (v[28] + v[29] + v[30] + v[31]) * 0.25f;
+        o[19] = (v[32] + v[33]) * 0.5f;
+    }
+    for (int b = 0; b < 34; b++) v[b] = o[b];
+}
+
+/* XL / XR: the element's X[2][38][64] planes in global scratch (XL in/out, XR out).
+ * top_in = kx + m of the SBR element (aacsbr.c:1753). */
+HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRICT frame, HeaacPsState *st,
+                               float *XL, float *XR, int top_in,
+                               const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    {
+        const uint32_t *src = (const uint32_t *)frame;
+        uint32_t *dst = (uint32_t *)&sm->p;
+        for (int i = tid; i < (int)(sizeof(HeaacPsFrame) / 4); i += nt) dst[i] = src[i];
+    }
+    HEAAC_SYNC();
+    const HeaacPsFrame *p = &sm->p;
+    const float *Lre = XL, *Lim = XL + 38 * 64;
+    if (!p->start) {                                      /* aacsbr.c:1755: R = copy of L */
+        for (int i = tid; i < 2 * 38 * 64; i += nt) XR[i] = XL[i];
+        HEAAC_SYNC();
+        return;
+    }
+    const int is34 = p->is34bands;
+    const int nr_bands = is34 ? 91 : 71, nr_par = is34 ? 34 : 20, nr_ap = is34 ? 50 : 30;
+    const int short_delay_band = is34 ? 62 : 42, decay_cutoff = is34 ? 32 : 10;
+    const int8_t *k_to_i = is34 ? T->k_to_i_34 : T->k_to_i_20;
+    const int top = top_in + nr_bands - 64;
+    const int switched = is34 != p->is34bands_old;        /* aacps.c:665-671: all decorrelator state is cleared */
+
+    /* ---- hybrid analysis, aacps.c:359-395 ---- */
+    for (int w = tid; w < 5 * 44; w += nt) {
+        int i = w / 44, j = w - i * 44;
+        if (j < 6) { sm->in[i][j][0] = st->in_hist[i][j][0]; sm->in[i][j][1] = st->in_hist[i][j][1]; }
+        else       { sm->in[i][j][0] = Lre[(j - 6) * 64 + i]; sm->in[i][j][1] = Lim[(j - 6) * 64 + i]; }
+    }
+    HEAAC_SYNC();
+    for (int w = tid; w < 5 * 6; w += nt) {
+        int i = w / 6, j = w - i * 6;
+        st->in_hist[i][j][0] = sm->in[i][32 + j][0]; st->in_hist[i][j][1] = sm->in[i][32 + j][1];
+    }
+    if (is34) {
+        for (int w = tid; w < 32 * 32; w += nt) {         /* 12 + 8 + 4 + 4 + 4 sub-subbands x 32 slots */
+            int q = w >> 5, n = w & 31;
+            int band, sub; const float (*f)[7][2];
+            if (q < 12)      { band = 0; sub = q;      f = T->f34_0_12; }
+            else if (q < 20) { band = 1; sub = q - 12; f = T->f34_1_8; }
+            else             { band = 2 + ((q - 20) >> 2); sub = (q - 20) & 3; f = T->f34_2_4; }
+            heaac_ps_hyb_cx(&sm->in[band][n], f[sub], &sm->L[q][n][0], &sm->L[q][n][1]);
+        }
+        for (int w = tid; w < 59 * 32; w += nt) {
+            int i = w >> 5, n = w & 31;
+            sm->L[i + 32][n][0] = Lre[n * 64 + i + 5]; sm->L[i + 32][n][1] = Lim[n * 64 + i + 5];
+        }
+    } else {
+        for (int n = tid; n < 32; n += nt) {              /* hybrid6_cx + 2 x hybrid2_re */
+            float t[8][2];
+            for (int q = 0; q < 8; q++) heaac_ps_hyb_cx(&sm->in[0][n], T->f20_0_8[q], &t[q][0], &t[q][1]);
+            for (int c = 0; c < 2; c++) {
+                sm->L[0][n][c] = t[6][c]; sm->L[1][n][c] = t[7][c]; sm->L[2][n][c] = t[0][c]; sm->L[3][n][c] = t[1][c];
+                sm->L[4][n][c] = t[2][c] + t[5][c];
+                sm->L[5][n][c] = t[3][c] + t[4][c];
+            }
+            for (int b = 1; b <= 2; b++) {                /* aacps.c:283-300, reverse = (b == 1) */
+                const float (*in)[2] = &sm->in[b][n];
+                const float *f = T->g1_Q2;
+                float re_in = f[6] * in[6][0], re_op = 0.0f, im_in = f[6] * in[6][1], im_op = 0.0f;
+                for (int j = 0; j < 6; j += 2) {
+                    re_op += f[j + 1] * (in[j + 1][0] + in[12 - j - 1][0]);
+                    im_op += f[j + 1] * (in[j + 1][1] + in[12 - j - 1][1]);
+                }
+                int rev = b == 1, base = 6 + 2 * (b - 1);
+                sm->L[base + rev][n][0]  = re_in + re_op; sm->L[base + rev][n][1]  = im_in + im_op;
+                sm->L[base + !rev][n][0] = re_in - re_op; sm->L[base + !rev][n][1] = im_in - im_op;
+            }
+        }
+        for (int w = tid; w < 61 * 32; w += nt) {
+            int i = w >> 5, n = w & 31;
+            sm->L[i + 10][n][0] = Lre[n * 64 + i + 3]; sm->L[i + 10][n][1] = Lim[n * 64 + i + 3];
+        }
+    }
+    HEAAC_SYNC();
+
+    /* ---- decorrelation, aacps.c:645-754 ---- */
+    for (int w = tid; w < nr_par * 32; w += nt) {
+        int i = w >> 5, n = w & 31;
+        float pw = 0.0f;
+        for (int k = 0; k < nr_bands; k++)
+            if (k_to_i[k] == i) pw += sm->L[k][n][0] * sm->L[k][n][0] + sm->L[k][n][1] * sm->L[k][n][1];
+        sm->power[i][n] = pw;
+    }
+    HEAAC_SYNC();
+    for (int i = tid; i < nr_par; i += nt) {              /* transient detection: serial in time */
+        float pdn = switched ? 0.0f : st->peak_decay_nrg[i];
+        float psm = switched ? 0.0f : st->power_smooth[i];
+        float pds = switched ? 0.0f : st->peak_decay_diff_smooth[i];
+        for (int n = 0; n < 32; n++) {
+            float pw = sm->power[i][n];
+            float decayed = 0.76592833836465f * pdn;
+            pdn = HEAAC_MAX(decayed, pw);
+            psm += 0.25f * (pw - psm);
+            pds += 0.25f * (pdn - pw - pds);
+            float denom = 1.5f * pds;
+            sm->tgain[i][n] = (denom > psm) ? heaac_fdiv(psm, denom) : 1.0f;
+        }
+        st->peak_decay_nrg[i] = pdn; st->power_smooth[i] = psm; st->peak_decay_diff_smooth[i] = pds;
+    }
+    if (switched)
+        for (int i = nr_par + tid; i < 34; i += nt) {
+            st->peak_decay_nrg[i] = 0.0f; st->power_smooth[i] = 0.0f; st->peak_decay_diff_smooth[i] = 0.0f;
+        }
+    HEAAC_SYNC();
+    for (int k = tid; k < nr_bands; k += nt) {            /* one hybrid band per work item, serial in time */
+        const int b = k_to_i[k];
+        const int cleared = switched || k >= top;         /* aacps.c:980-983 + 665-671 */
+        float hist[14][2];
+        for (int j = 0; j < 14; j++) {
+            hist[j][0] = cleared ? 0.0f : st->delay[k][j][0];
+            hist[j][1] = cleared ? 0.0f : st->delay[k][j][1];
+        }
+        if (k < nr_ap) {
+            float g = 1.f - 0.05f * (k - decay_cutoff);
+            g = g < 0.f ? 0.f : (g > 1.f ? 1.f : g);
+            const float a_[3] = { 0.65143905753106f, 0.56471812200776f, 0.48954165955695f };
+            float ag[3], ap[3][5][2];
+            for (int m = 0; m < 3; m++) {
+                ag[m] = a_[m] * g;
+                for (int j = 0; j < 5; j++) {
+                    ap[m][j][0] = cleared ? 0.0f : st->ap_delay[k][m][j][0];
+                    ap[m][j][1] = cleared ? 0.0f : st->ap_delay[k][m][j][1];
+                }
+            }
+            const float pf_re = T->phi_fract[is34][k][0], pf_im = T->phi_fract[is34][k][1];
+            for (int n = 0; n < 32; n++) {
+                /* delay[k][n + 12]: two slots back */
+                float d_re = n < 2 ? hist[12 + n][0] : sm->L[k][n - 2][0];
+                float d_im = n < 2 ? hist[12 + n][1] : sm->L[k][n - 2][1];
+                float in_re = d_re * pf_re - d_im * pf_im;
+                float in_im = d_re * pf_im + d_im * pf_re;
+                for (int m = 0; m < 3; m++) {
+                    /* ap_delay[k][m][n + 5 - link_delay], link_delay = 3 + m: ring of the last 5 values, ap[m][4] newest */
+                    float a_re = ag[m] * in_re, a_im = ag[m] * in_im;
+                    float ld_re = ap[m][2 - m][0], ld_im = ap[m][2 - m][1];
+                    float fd_re = T->Q_fract_allpass[is34][k][m][0], fd_im = T->Q_fract_allpass[is34][k][m][1];
+                    float nw_re = in_re, nw_im = in_im;
+                    in_re = ld_re * fd_re - ld_im * fd_im - a_re;
+                    in_im = ld_re * fd_im + ld_im * fd_re - a_im;
+                    nw_re += ag[m] * in_re;
+                    nw_im += ag[m] * in_im;
+                    for (int j = 0; j < 4; j++) { ap[m][j][0] = ap[m][j + 1][0]; ap[m][j][1] = ap[m][j + 1][1]; }
+                    ap[m][4][0] = nw_re; ap[m][4][1] = nw_im;
+                }
+                sm->R[k][n][0] = sm->tgain[b][n] * in_re;
+                sm->R[k][n][1] = sm->tgain[b][n] * in_im;
+            }
+            for (int m = 0; m < 3; m++)
+                for (int j = 0; j < 5; j++) { st->ap_delay[k][m][j][0] = ap[m][j][0]; st->ap_delay[k][m][j][1] = ap[m][j][1]; }
+        } else {
+            const int d = k < short_delay_band ? 14 : 1;
+            for (int n = 0; n < 32; n++) {
+                int pos = n + 14 - d;                     /* index into [hist(14) | this frame(32)] */
+                float d_re = pos < 14 ? hist[pos][0] : sm->L[k][pos - 14][0];
+                float d_im = pos < 14 ? hist[pos][1] : sm->L[k][pos - 14][1];
+                sm->R[k][n][0] = sm->tgain[b][n] * d_re;
+                sm->R[k][n][1] = sm->tgain[b][n] * d_im;
+            }
+        }
+        for (int j = 0; j < 14; j++) { st->delay[k][j][0] = sm->L[k][18 + j][0]; st->delay[k][j][1] = sm->L[k][18 + j][1]; }
+    }
+    /* bands beyond nr_bands keep their state unless everything was cleared */
+    if (switched) {
+        for (int w = tid; w < (91 - nr_bands) * 14; w += nt) {
+            int k = nr_bands + w / 14, j = w % 14;
+            st->delay[k][j][0] = 0.0f; st->delay[k][j][1] = 0.0f;
+        }
+        for (int w = tid; w < (50 - nr_ap) * 15; w += nt) {
+            int k = nr_ap + w / 15, r = w % 15;
+            st->ap_delay[k][r / 5][r % 5][0] = 0.0f; st->ap_delay[k][r / 5][r % 5][1] = 0.0f;
+        }
+    }
+    /* ap_delay of all-pass bands at or above `top` that this frame did not run: cleared (aacps.c:982-983) */
+    /* (bands < nr_ap are always run above, with cleared history when k >= top) */
+
+    /* ---- stereo_processing, aacps.c:794-971: H matrices ---- */
+    for (int w = tid; w < 4 * 2 * 34; w += nt) {
+        int h = w / 68, c = (w / 34) & 1, b = w % 34;
+        sm->H[h][c][0][b] = st->H[h][c][p->num_env_old][b];
+        for (int e = 1; e < 6; e++) sm->H[h][c][e][b] = st->H[h][c][e][b];
+    }
+    for (int w = tid; w < p->num_env * 34; w += nt) {
+        int e = w / 34, b = w - e * 34;
+        if (b >= nr_par) continue;
+        sm->iid[e][b] = (int8_t)heaac_ps_map_idx(p->iid_par[e], p->nr_iid_par, is34, 1, b);
+        sm->icc[e][b] = (int8_t)heaac_ps_map_idx(p->icc_par[e], p->nr_icc_par, is34, 1, b);
+        if (p->enable_ipdopd && b < (is34 ? 17 : 11)) {
+            sm->ipd[e][b] = (int8_t)heaac_ps_map_idx(p->ipd_par[e], p->nr_ipdopd_par, is34, 0, b);
+            sm->opd[e][b] = (int8_t)heaac_ps_map_idx(p->opd_par[e], p->nr_ipdopd_par, is34, 0, b);
+        }
+    }
+    HEAAC_SYNC();
+    if (switched) {
+        for (int w = tid; w < 8; w += nt) heaac_ps_map_val(sm->H[w >> 1][w & 1][0], is34);
+        for (int b = tid; b < 17; b += nt) { st->ipd_hist[b] = 0; st->opd_hist[b] = 0; }   /* ipdopd_reset, aacps.c:141-148 */
+    }
+    HEAAC_SYNC();
+    {
+        const float (*H_LUT)[8][4] = p->icc_mode < 3 ? T->HA : T->HB;
+        for (int b = tid; b < nr_par; b += nt) {          /* serial over envelopes: the phase smoother has memory */
+            int oh = st->opd_hist[b < 34 ? b : 0], ih = st->ipd_hist[b < 34 ? b : 0];
+            for (int e = 0; e < p->num_env; e++) {
+                const float *lut = H_LUT[sm->iid[e][b] + 7 + 23 * p->iid_quant][sm->icc[e][b]];
+                float h11 = lut[0], h12 = lut[1], h21 = lut[2], h22 = lut[3];
+                if (p->enable_ipdopd && b < p->nr_ipdopd_par) {
+                    int opd_idx = oh * 8 + sm->opd[e][b];
+                    int ipd_idx = ih * 8 + sm->ipd[e][b];
+                    float opd_re = T->pd_re_smooth[opd_idx], opd_im = T->pd_im_smooth[opd_idx];
+                    float ipd_re = T->pd_re_smooth[ipd_idx], ipd_im = T->pd_im_smooth[ipd_idx];
+                    oh = opd_idx & 0x3F; ih = ipd_idx & 0x3F;
+                    float adj_re = opd_re * ipd_re + opd_im * ipd_im;
+                    float adj_im = opd_im * ipd_re - opd_re * ipd_im;
+                    sm->H[0][1][e + 1][b] = h11 * opd_im;  h11 = h11 * opd_re;
+                    sm->H[1][1][e + 1][b] = h12 * adj_im;  h12 = h12 * adj_re;
+                    sm->H[2][1][e + 1][b] = h21 * opd_im;  h21 = h21 * opd_re;
+                    sm->H[3][1][e + 1][b] = h22 * adj_im;  h22 = h22 * adj_re;
+                }
+                sm->H[0][0][e + 1][b] = h11; sm->H[1][0][e + 1][b] = h12;
+                sm->H[2][0][e + 1][b] = h21; sm->H[3][0][e + 1][b] = h22;
+            }
+            st->opd_hist[b] = (int8_t)oh; st->ipd_hist[b] = (int8_t)ih;
+        }
+    }
+    HEAAC_SYNC();
+    for (int w = tid; w < 4 * 2 * 34; w += nt) {          /* persist H (all rows: stale rows are re-read by later frames) */
+        int h = w / 68, c = (w / 34) & 1, b = w % 34;
+        for (int e = 0; e < 6; e++) st->H[h][c][e][b] = sm->H[h][c][e][b];
+    }
+    /* ---- mixing: one hybrid band per work item, serial over envelopes and slots ---- */
+    for (int k = tid; k < nr_bands; k += nt) {
+        const int b = k_to_i[k];
+        const int neg = p->enable_ipdopd && ((is34 && k <= 13 && k >= 9) || (!is34 && k <= 1));
+        for (int e = 0; e < p->num_env; e++) {
+            int start = p->border_position[e], stop = p->border_position[e + 1];
+            float width = heaac_fdiv(1.f, (float)(stop - start));
+            float hr[4], hi[4], hrs[4], his[4];
+            for (int h = 0; h < 4; h++) {
+                hr[h] = sm->H[h][0][e][b];
+                hrs[h] = (sm->H[h][0][e + 1][b] - hr[h]) * width;
+                hi[h] = 0.0f; his[h] = 0.0f;
+                if (p->enable_ipdopd) {
+                    hi[h] = neg ? -sm->H[h][1][e][b] : sm->H[h][1][e][b];
+                    his[h] = (sm->H[h][1][e + 1][b] - hi[h]) * width;
+                }
+            }
+            for (int n = start + 1; n <= stop; n++) {
+                float l_re = sm->L[k][n][0], l_im = sm->L[k][n][1], r_re = sm->R[k][n][0], r_im = sm->R[k][n][1];
+                for (int h = 0; h < 4; h++) hr[h] += hrs[h];
+                if (p->enable_ipdopd) {
+                    for (int h = 0; h < 4; h++) hi[h] += his[h];
+                    sm->L[k][n][0] = hr[0] * l_re + hr[2] * r_re - hi[0] * l_im - hi[2] * r_im;
+                    sm->L[k][n][1] = hr[0] * l_im + hr[2] * r_im + hi[0] * l_re + hi[2] * r_re;
+                    sm->R[k][n][0] = hr[1] * l_re + hr[3] * r_re - hi[1] * l_im - hi[3] * r_im;
+                    sm->R[k][n][1] = hr[1] * l_im + hr[3] * r_im + hi[1] * l_re + hi[3] * r_re;
+                } else {
+                    sm->L[k][n][0] = hr[0] * l_re + hr[2] * r_re;
+                    sm->L[k][n][1] = hr[0] * l_im + hr[2] * r_im;
+                    sm->R[k][n][0] = hr[1] * l_re + hr[3] * r_re;
+                    sm->R[k][n][1] = hr[1] * l_im + hr[3] * r_im;
+                }
+            }
+        }
+    }
+    HEAAC_SYNC();
+
+    /* ---- hybrid synthesis x 2, aacps.c:397-445: back to 64 QMF bands, slots 0..31 ---- */
+    for (int w = tid; w < 2 * 32 * 64; w += nt) {
+        int side = w >> 11, n = (w >> 6) & 31, q = w & 63;
+        const float (*in)[32][2] = side ? sm->R : sm->L;
+        float *X = side ? XR : XL;
+        float re, im;
+        if (is34) {
+            if (q < 5) {
+                int lo = q == 0 ? 0 : q == 1 ? 12 : 20 + 4 * (q - 2);
+                int cnt = q == 0 ? 12 : q == 1 ? 8 : 4;
+                re = 0.0f; im = 0.0f;
+                for (int i = 0; i < cnt; i++) { re += in[lo + i][n][0]; im += in[lo + i][n][1]; }
+            } else { re = in[q + 27][n][0]; im = in[q + 27][n][1]; }
+        } else {
+            if (q == 0) {
+                re = in[0][n][0] + in[1][n][0] + in[2][n][0] + in[3][n][0] + in[4][n][0] + in[5][n][0];
+                im = in[0][n][1] + in[1][n][1] + in[2][n][1] + in[3][n][1] + in[4][n][1] + in[5][n][1];
+            } else if (q == 1) { re = in[6][n][0] + in[7][n][0]; im = in[6][n][1] + in[7][n][1]; }
+            else if (q == 2)   { re = in[8][n][0] + in[9][n][0]; im = in[8][n][1] + in[9][n][1]; }
+            else               { re = in[q + 7][n][0]; im = in[q + 7][n][1]; }
+        }
+        X[n * 64 + q] = re;
+        X[38 * 64 + n * 64 + q] = im;
+    }
+    HEAAC_SYNC();
+}
+
+/* ====================================================================================
+ * QMF synthesis for one output channel-frame: X[2][38][64] -> 2048 PCM samples
+ * ================================================================================== */
+struct HeaacSynthSmem {
+    float v[1152 + 32 * 128];       /* [0, 4096): this frame's 32 v-blocks, newest first; then history */
+    float in[64 * 64];              /* 64 transforms x 64 inputs (slot-major: 2 per slot) */
+    float zr[64 * 32], zi[64 * 32];
+};
+
+HEAAC_DEV void heaac_synth_channel(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st,
+                                   int16_t *pcm, int pcm_stride, float *pcm_f32,
+                                   float scale, float bias,
+                                   const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+{
+    const float *Xre = X, *Xim = X + 38 * 64;
+    for (int i = tid; i < 1152; i += nt) sm->v[4096 + i] = st->v[i];
+    for (int w = tid; w < 32 * 64; w += nt) {
+        int i = w >> 6, n = w & 63;
+        sm->in[(2 * i) * 64 + n] = Xre[w];
+        float xi = Xim[w];
+        sm->in[(2 * i + 1) * 64 + n] = (n & 1) ? -xi : xi;       /* aacsbr.c:1205-1207 */
+    }
+    HEAAC_SYNC();
+    heaac_imdct_half_smem(sm->in, sm->in, sm->zr, sm->zi, 5, 64, T->tcos_syn, T->tsin_syn, T, tid, nt);
+    for (int w = tid; w < 32 * 64; w += nt) {                     /* aacsbr.c:1210-1213 */
+        int i = w >> 6, n = w & 63;
+        const float *b0 = sm->in + (2 * i) * 64, *b1 = b0 + 64;
+        float *v = sm->v + (31 - i) * 128;
+        v[n]       = -b0[63 - n] + b1[n];
+        v[127 - n] =  b0[63 - n] + b1[n];
+    }
+    HEAAC_SYNC();
+    const int scale_and_bias = scale != 1.0f || bias != 0.0f;
+    const int bias_mode = bias != 0.0f;
+    for (int w = tid; w < 32 * 64; w += nt) {                     /* aacsbr.c:1215-1227 */
+        int i = w >> 6, n = w & 63;
+        const float *v = sm->v + (31 - i) * 128 + n;
+        const float *win = T->qmf_us + n;
+        float acc = v[0] * win[0] + 0.0f;
+        acc = v[192]  * win[64]  + acc;
+        acc = v[256]  * win[128] + acc;
+        acc = v[448]  * win[192] + acc;
+        acc = v[512]  * win[256] + acc;
+        acc = v[704]  * win[320] + acc;
+        acc = v[768]  * win[384] + acc;
+        acc = v[960]  * win[448] + acc;
+        acc = v[1024] * win[512] + acc;
+        acc = v[1216] * win[576] + acc;
+        if (scale_and_bias) acc = acc * scale + bias;
+        if (pcm)     pcm[(size_t)w * pcm_stride] = heaac_to_s16(acc, bias_mode);
+        if (pcm_f32) pcm_f32[w] = acc;
+    }
+    for (int i = tid; i < 1152; i += nt) st->v[i] = sm->v[i];
+    HEAAC_SYNC();
+}
+
+#endif /* HEAAC_KERNELS_CUH */

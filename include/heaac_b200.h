@@ -243,6 +243,10 @@ int  heaac_b200_mdct_init(HeaacMdct **s, int nbits, int inverse, double scale);
 void heaac_b200_imdct_half(HeaacMdct *s, float *output, const float *input);  /* host pointers, N/2 in, N/2 out */
 void heaac_b200_mdct_end(HeaacMdct *s);
 
+/* sizeof() of an ABI or device-state struct by name ("HeaacSbrElem", ...), -1 if unknown; lets
+ * language bindings assert that their struct mirrors match this build. */
+int  heaac_b200_sizeof(const char *name);
+
 const char *heaac_b200_version(void);
 const char *heaac_b200_strerror(int err);
 

@@ -5,8 +5,9 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "ffmpeg-heaac_b200"))
-import abi  # noqa: E402
+sys.path.insert(0, os.path.dirname(_HERE))
+import ffmpeg_heaac_b200  # noqa: E402  (host-side ABI mirrors only; no kernels are called from here)
+abi = ffmpeg_heaac_b200.abi
 
 _LIB_PATH = os.path.join(_HERE, "libheaac_oracle.so")
 _lib = None

@@ -12,8 +12,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-sys.path.insert(0, os.path.join(_ROOT, "ffmpeg-heaac_b200"))
-import abi  # noqa: E402
+sys.path.insert(0, _ROOT)
+import ffmpeg_heaac_b200  # noqa: E402  (host-side ABI mirrors only; no kernels are called from here)
+abi = ffmpeg_heaac_b200.abi
 
 _LIB_PATH = os.path.join(_HERE, "_ref", "libheaac_ref.so")
 PADDING = 8  # FF_INPUT_BUFFER_PADDING_SIZE (avcodec.h:3432)

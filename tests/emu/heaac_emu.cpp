@@ -1,0 +1,142 @@
+/*
+ * tests/emu/heaac_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles the product's CTA-level kernel source (ffmpeg-heaac_b200/csrc/heaac_kernels.cuh)
+ * as plain C++ with HEAAC_HOST_EMU (one "thread" per CTA, barriers are no-ops) so that the
+ * kernel LOGIC (indexing, state hand-over, parameter handling) can be checked against the
+ * oracle on machines without a GPU.  It is not a fallback: the product library
+ * (libheaac_b200.so) never contains, loads or calls this, and data races / barrier bugs can
+ * only be found on the GPU (tests/ -m gpu).  Exports heaac_emu_* mirroring heaac_b200_*.
+ */
+#define HEAAC_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "../../ffmpeg-heaac_b200/csrc/heaac_kernels.cuh"
+
+extern "C" void heaac_build_tables(HeaacDevTables *t);
+
+struct EmuCtx {
+    HeaacConfig cfg; HeaacGeom g;
+    HeaacDevTables *T;
+    HeaacChanState *chan; HeaacSynthState *synth; HeaacPsState *ps;
+    float *core_time, *X;
+    HeaacCoreSmem *sm_core; HeaacSbrSmem *sm_sbr; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
+};
+
+static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
+{
+    memset(g, 0, sizeof(*g));
+    g->n_streams = cfg->n_streams; g->n_elems = cfg->n_elems;
+    int ch = 0, se = 0;
+    for (int e = 0; e < cfg->n_elems; e++) {
+        g->elem_type[e] = cfg->elem_type[e];
+        int nch = cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+        for (int c = 0; c < nch; c++, ch++) {
+            g->ch_elem[ch] = e; g->ch_in_elem[ch] = c;
+            g->ch_sbr_elem[ch] = cfg->elem_type[e] == HEAAC_TYPE_LFE ? 0xff : se;
+            g->elem_is_cpe[ch] = nch == 2;
+        }
+        if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
+    }
+    g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch; g->out_len = cfg->sbr ? 2048 : 1024;
+    g->sr_index = cfg->sr_index; g->sbr = cfg->sbr != 0; g->ps = cfg->ps != 0;
+    g->add_bias = cfg->add_bias; g->sf_scale = cfg->sf_scale;
+}
+
+extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
+{
+    EmuCtx *c = (EmuCtx *)calloc(1, sizeof(EmuCtx));
+    c->cfg = *cfg; build_geom(cfg, &c->g);
+    c->T = (HeaacDevTables *)malloc(sizeof(HeaacDevTables));
+    heaac_build_tables(c->T);
+    size_t S = c->g.n_streams;
+    c->chan = (HeaacChanState *)calloc(S * c->g.ncc, sizeof(HeaacChanState));
+    c->synth = (HeaacSynthState *)calloc(S * c->g.nout, sizeof(HeaacSynthState));
+    c->ps = (HeaacPsState *)calloc(S, sizeof(HeaacPsState));
+    c->core_time = (float *)calloc(S * c->g.ncc * 1024, sizeof(float));
+    c->X = (float *)calloc(S * c->g.nout * 2 * 38 * 64, sizeof(float));
+    c->sm_core = (HeaacCoreSmem *)calloc(1, sizeof(HeaacCoreSmem));
+    c->sm_sbr = (HeaacSbrSmem *)calloc(1, sizeof(HeaacSbrSmem));
+    c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
+    c->sm_synth = (HeaacSynthSmem *)calloc(1, sizeof(HeaacSynthSmem));
+    return c;
+}
+
+extern "C" void heaac_emu_destroy(EmuCtx *c)
+{
+    if (!c) return;
+    free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->core_time); free(c->X);
+    free(c->sm_core); free(c->sm_sbr); free(c->sm_ps); free(c->sm_synth); free(c);
+}
+
+extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
+{
+    const HeaacGeom g = c->g;
+    const size_t S = g.n_streams;
+    const float qmf_scale = -1024.0f * g.sf_scale;
+    for (int f = 0; f < b->n_frames; f++) {
+        const float *co = b->coeffs + (size_t)f * S * g.ncc * 1024;
+        const HeaacIcs *ic = b->ics + (size_t)f * S * g.ncc;
+        const HeaacTns *tn = b->tns ? b->tns + (size_t)f * S * g.ncc : nullptr;
+        const HeaacSbrElem *sb = b->sbr ? b->sbr + (size_t)f * S * g.nse : nullptr;
+        const HeaacPsFrame *ps = b->ps ? b->ps + (size_t)f * S : nullptr;
+        size_t pcm_frame = S * g.out_len * g.nout;
+        int16_t *pc = b->pcm ? b->pcm + (size_t)f * pcm_frame : nullptr;
+        float *pf = b->pcm_f32 ? b->pcm_f32 + (size_t)f * pcm_frame : nullptr;
+        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core */
+            size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
+            float out[1024];
+            float bias = g.sbr ? 0.0f : g.add_bias;
+            memset(c->sm_core, 0xA5, sizeof(HeaacCoreSmem));      /* poison "shared memory" */
+            heaac_core_channel(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, c->chan + gc, out, bias,
+                               g.sr_index, c->T, 0, 1);
+            if (g.sbr) memcpy(c->core_time + gc * 1024, out, sizeof(out));
+            else for (int i = 0; i < 1024; i++) {
+                if (pc) pc[(s * 1024 + i) * g.nout + ch] = heaac_to_s16(out[i], g.add_bias != 0.0f);
+                if (pf) pf[(s * g.nout + ch) * 1024 + i] = out[i];
+            }
+        }
+        if (!g.sbr) continue;
+        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_sbr */
+            size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
+            int se = g.ch_sbr_elem[ch];
+            if (se == 0xff) continue;
+            memset(c->sm_sbr, 0xA5, sizeof(HeaacSbrSmem));
+            heaac_sbr_channel(c->sm_sbr, c->core_time + gc * 1024, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
+                              c->chan + gc, c->X + (s * g.nout + ch) * (2 * 38 * 64), 1 / qmf_scale, c->T, 0, 1);
+        }
+        if (g.ps)
+            for (size_t s = 0; s < S; s++) {                      /* k_ps */
+                float *XL = c->X + s * 2 * (2 * 38 * 64), *XR = XL + 2 * 38 * 64;
+                const HeaacSbrElem *e = sb + s * g.nse;
+                memset(c->sm_ps, 0xA5, sizeof(HeaacPsSmem));
+                heaac_ps_stream(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0, 1);
+            }
+        for (size_t go = 0; go < S * g.nout; go++) {              /* k_synth */
+            size_t s = go / g.nout; int ch = (int)(go - s * g.nout);
+            memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
+            heaac_synth_channel(c->sm_synth, c->X + go * (2 * 38 * 64), c->synth + go,
+                                pc ? pc + s * 2048 * g.nout + ch : nullptr, g.nout,
+                                pf ? pf + go * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0, 1);
+        }
+    }
+    return 0;
+}
+
+extern "C" int heaac_emu_tables(HeaacDevTables *out) { heaac_build_tables(out); return (int)sizeof(HeaacDevTables); }
+
+extern "C" int heaac_emu_peek(EmuCtx *c, const char *name, void *dst, int cap)
+{
+    const void *p = nullptr; size_t n = 0;
+    size_t S = c->g.n_streams;
+    if (!strcmp(name, "X")) { p = c->X; n = S * c->g.nout * 2 * 38 * 64 * sizeof(float); }
+    else if (!strcmp(name, "core_time")) { p = c->core_time; n = S * c->g.ncc * 1024 * sizeof(float); }
+    else if (!strcmp(name, "chan_state")) { p = c->chan; n = S * c->g.ncc * sizeof(HeaacChanState); }
+    else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacSbrSmem); }
+    else if (!strcmp(name, "ps_smem")) { p = c->sm_ps; n = sizeof(HeaacPsSmem); }
+    if (!p) return -1;
+    if (n > (size_t)cap) n = cap;
+    memcpy(dst, p, n);
+    return (int)n;
+}

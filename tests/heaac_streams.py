@@ -16,7 +16,7 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(_ROOT, "oracle"))
 import pyref  # noqa: E402
-import abi    # noqa: E402  (path set by pyref)
+abi = pyref.abi
 
 
 class BitWriter:
@@ -242,8 +242,12 @@ def _write_noise(bw, rng, st, grid, n_q, coupled_bal):
 
 
 class PsState:
+    """Encoder-side mirror of the PSContext fields the parser keeps between frames (aacps.h:40-63)."""
+
     def __init__(self):
-        self.iid_mode = 0; self.icc_mode = 0; self.enable_iid = 0; self.enable_icc = 0; self.enable_ext = 0
+        self.enable_iid = 0; self.enable_icc = 0; self.enable_ext = 0
+        self.nr_iid = 0; self.nr_icc = 0; self.nr_pd = 0; self.quant = 0     # as the decoder holds them
+        self.is34 = 0; self.enable_ipdopd = 0
         self.prev = {"iid": None, "icc": None, "ipd": None, "opd": None}
         self.have_header = False
 
@@ -288,21 +292,31 @@ def _ps_par(bw, rng, ps, kind, num, table_df, table_dt, offset, lo, hi, step, mo
 
 
 def write_ps_data(bw, rng, ps, frame_idx, header_period=8, ipdopd=True, fixed_modes=None):
-    """ps_data(), aacps.c:150-279."""
+    """ps_data(), aacps.c:150-279.  Tracks the decoder's retained fields so that the stream never drives
+    the reference into its one undefined corner: 20-band processing with nr_ipdopd_par == 17 and IPD/OPD
+    enabled reads uninitialised stack (remap20 with full = 0 fills 11 of the 17 entries, aacps.c:845-848)."""
     header = (not ps.have_header) or (frame_idx % header_period == 0)
     bw.put(1 if header else 0, 1)
     if header:
         if fixed_modes is None:
-            ps.iid_mode = int(rng.integers(0, 6)); ps.icc_mode = int(rng.integers(0, 6))
+            iid_mode = int(rng.integers(0, 6)); icc_mode = int(rng.integers(0, 6))
         else:
-            ps.iid_mode, ps.icc_mode = fixed_modes
-        ps.enable_iid = 1 if rng.random() < 0.9 else 0
+            iid_mode, icc_mode = fixed_modes
+        ps.enable_iid = 1 if (rng.random() < 0.9 or not ps.have_header) else 0
         ps.enable_icc = 1 if rng.random() < 0.9 else 0
-        ps.enable_ext = 1 if (ipdopd and ps.enable_iid and rng.random() < 0.5) else 0
         bw.put(ps.enable_iid, 1)
-        if ps.enable_iid: bw.put(ps.iid_mode, 3)
+        if ps.enable_iid:
+            bw.put(iid_mode, 3)
+            ps.nr_iid, ps.quant, ps.nr_pd = NR_IIDICC[iid_mode], int(iid_mode > 2), NR_IPDOPD[iid_mode]
         bw.put(ps.enable_icc, 1)
-        if ps.enable_icc: bw.put(ps.icc_mode, 3)
+        if ps.enable_icc:
+            bw.put(icc_mode, 3)
+            ps.nr_icc = NR_IIDICC[icc_mode]
+        if ps.enable_iid or ps.enable_icc:
+            ps.is34 = int((ps.enable_iid and ps.nr_iid == 34) or (ps.enable_icc and ps.nr_icc == 34))
+        hazard = (not ps.is34) and ps.nr_pd == 17
+        # the extension is the only way to clear a stale enable_ipdopd: always send it when the hazard exists
+        ps.enable_ext = 1 if (hazard or (ipdopd and rng.random() < 0.5)) else 0
         bw.put(ps.enable_ext, 1)
         ps.have_header = True
         ps.prev = {"iid": None, "icc": None, "ipd": None, "opd": None}
@@ -314,25 +328,25 @@ def write_ps_data(bw, rng, ps, frame_idx, header_period=8, ipdopd=True, fixed_mo
     if frame_class:
         borders = sorted(rng.choice(np.arange(0, 32), size=num_env, replace=False).tolist())
         for b in borders: bw.put(int(b), 5)
-    quant = 1 if ps.iid_mode > 2 else 0
-    nr_iid, nr_icc, nr_pd = NR_IIDICC[ps.iid_mode], NR_IIDICC[ps.icc_mode], NR_IPDOPD[ps.iid_mode]
     if ps.enable_iid:
-        lim = 7 + 8 * quant
+        lim = min(7 + 8 * ps.quant, 6 + 5 * ps.quant)
         for e in range(num_env):
-            _ps_par(bw, rng, ps, "iid", nr_iid, "huff_iid_df%d" % quant, "huff_iid_dt%d" % quant,
-                    30 if quant else 14, -min(lim, 6 + 5 * quant), min(lim, 6 + 5 * quant), 2, False)
+            _ps_par(bw, rng, ps, "iid", ps.nr_iid, "huff_iid_df%d" % ps.quant, "huff_iid_dt%d" % ps.quant,
+                    30 if ps.quant else 14, -lim, lim, 2, False)
     if ps.enable_icc:
         for e in range(num_env):
-            _ps_par(bw, rng, ps, "icc", nr_icc, "huff_icc_df", "huff_icc_dt", 7, 0, 7, 1, False)
+            _ps_par(bw, rng, ps, "icc", ps.nr_icc, "huff_icc_df", "huff_icc_dt", 7, 0, 7, 1, False)
     if ps.enable_ext:
+        hazard = (not ps.is34) and ps.nr_pd == 17
         ext = BitWriter()
         ext.put(0, 2)                      # ps_extension_id 0 = IPD/OPD
-        en = 1 if rng.random() < 0.85 else 0
+        en = 1 if (rng.random() < 0.85 and not hazard and ipdopd) else 0
         ext.put(en, 1)
+        ps.enable_ipdopd = en
         if en:
             for e in range(num_env):
-                _ps_par(ext, rng, ps, "ipd", nr_pd, "huff_ipd_df", "huff_ipd_dt", 0, 0, 7, 1, True)
-                _ps_par(ext, rng, ps, "opd", nr_pd, "huff_opd_df", "huff_opd_dt", 0, 0, 7, 1, True)
+                _ps_par(ext, rng, ps, "ipd", ps.nr_pd, "huff_ipd_df", "huff_ipd_dt", 0, 0, 7, 1, True)
+                _ps_par(ext, rng, ps, "opd", ps.nr_pd, "huff_opd_df", "huff_opd_dt", 0, 0, 7, 1, True)
         ext.put(0, 1)                      # reserved_ps
         cnt = (len(ext) + 7) // 8
         if cnt < 15:
@@ -341,8 +355,8 @@ def write_ps_data(bw, rng, ps, frame_idx, header_period=8, ipdopd=True, fixed_mo
             bw.put(15, 4); bw.put(cnt - 15, 8)
         for b in ext.bits: bw.put(b, 1)
         bw.put(0, cnt * 8 - len(ext))
-    if num_env == 0:
-        pass  # decoder re-uses the previous envelope's parameters (aacps.c:235-252)
+    elif ps.enable_ipdopd and (not ps.is34) and ps.nr_pd == 17:
+        raise AssertionError("generator bug: stale IPD/OPD would hit the reference's uninitialised read")
 
 
 class HeAacStreamGen:
@@ -377,7 +391,9 @@ class HeAacStreamGen:
         bw.put(0, 1)                                        # bs_data_extra
         coupling = 0
         if self.stereo:
-            coupling = 1 if rng.random() < 0.4 else 0
+            # a coupled frame shares one grid: only conformant when both channels' previous grids ended at
+            # the same border (otherwise channel 1 would have QMF slots no envelope covers)
+            coupling = 1 if (rng.random() < 0.4 and self.ch[0].prev_trail == self.ch[1].prev_trail) else 0
             bw.put(coupling, 1)
             if coupling != getattr(self, "_last_coupling", coupling):
                 # channel 1 switches between level and balance domains: restart its delta-time coding
