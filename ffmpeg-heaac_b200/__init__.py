@@ -28,7 +28,8 @@ EXPORTS = [
     "heaac_b200_sync", "heaac_b200_launch_count", "heaac_b200_stream", "heaac_b200_dev_alloc", "heaac_b200_dev_free",
     "heaac_b200_dev_upload", "heaac_b200_dev_download", "heaac_b200_timer_start", "heaac_b200_timer_stop",
     "heaac_b200_debug_read", "heaac_b200_mdct_init", "heaac_b200_imdct_half", "heaac_b200_mdct_end",
-    "heaac_b200_version", "heaac_b200_strerror", "heaac_b200_sizeof",
+    "heaac_b200_version", "heaac_b200_strerror", "heaac_b200_sizeof", "heaac_b200_sbr_tables",
+    "heaac_b200_profile_enable", "heaac_b200_profile_read",
 ]
 
 
@@ -71,6 +72,9 @@ def lib():
         L.heaac_b200_version.restype = C.c_char_p
         L.heaac_b200_strerror.restype = C.c_char_p
         L.heaac_b200_sizeof.argtypes = [C.c_char_p]
+        L.heaac_b200_sbr_tables.argtypes = [C.c_int] * 8 + [C.c_void_p]
+        L.heaac_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.heaac_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
         for name, size in abi.SIZES.items():
             got = L.heaac_b200_sizeof(name.encode())
             if got != size:
@@ -182,6 +186,16 @@ class Context:
         _check(lib().heaac_b200_timer_stop(self.h, C.byref(ms)), "timer_stop")
         return ms.value
 
+    def profile_enable(self, capacity):
+        _check(lib().heaac_b200_profile_enable(self.h, capacity), "profile_enable")
+
+    def profile_read(self):
+        """{kernel: (total_ms, launches)} since profile_enable / the last read."""
+        ms = (C.c_float * 4)()
+        n = (C.c_longlong * 4)()
+        _check(lib().heaac_b200_profile_read(self.h, ms, n), "profile_read")
+        return {k: (ms[i], n[i]) for i, k in enumerate(("k_core", "k_sbr", "k_ps", "k_synth"))}
+
     @property
     def launch_count(self):
         return lib().heaac_b200_launch_count(self.h)
@@ -201,6 +215,17 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def sbr_tables(core_sample_rate, start_freq, stop_freq, xover=0, freq_scale=2, alter_scale=1, noise_bands=2,
+               limiter_bands=2):
+    """SBR frequency tables for a header (host code; the defaults are the bitstream defaults of
+    read_sbr_header, aacsbr.c:233-252).  Returns a 1-element SBR_ELEM array with the table fields set."""
+    e = np.zeros(1, SBR_ELEM)
+    r = lib().heaac_b200_sbr_tables(core_sample_rate, start_freq, stop_freq, xover, freq_scale, alter_scale,
+                                    noise_bands, limiter_bands, e.ctypes.data)
+    _check(r, "heaac_b200_sbr_tables")
+    return e
 
 
 class Mdct:

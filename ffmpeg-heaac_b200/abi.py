@@ -64,7 +64,7 @@ class Config(C.Structure):
         ("abi_version", C.c_uint32), ("device", C.c_int32), ("n_streams", C.c_int32), ("n_elems", C.c_int32),
         ("elem_type", C.c_uint8 * MAX_ELEMS), ("sr_index", C.c_int32), ("sbr", C.c_int32), ("ps", C.c_int32),
         ("add_bias", C.c_float), ("sf_scale", C.c_float), ("max_frames_per_call", C.c_int32),
-        ("want_float_out", C.c_int32), ("keep_intermediates", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("want_float_out", C.c_int32), ("keep_intermediates", C.c_int32), ("out_slot", C.c_uint8 * 16),
     ]
 
 
@@ -76,8 +76,41 @@ class Batch(C.Structure):
     ]
 
 
+# aac_channel_layout_map (aacdectab.h:74-82): output order of the reference per channel configuration
+_LAYOUT_MAP = {
+    1: [(TYPE_SCE, 0)], 2: [(TYPE_CPE, 0)], 3: [(TYPE_CPE, 0), (TYPE_SCE, 0)],
+    4: [(TYPE_CPE, 0), (TYPE_SCE, 0), (TYPE_SCE, 1)], 5: [(TYPE_CPE, 0), (TYPE_SCE, 0), (TYPE_CPE, 1)],
+    6: [(TYPE_CPE, 0), (TYPE_SCE, 0), (TYPE_LFE, 0), (TYPE_CPE, 1)],
+    7: [(TYPE_CPE, 0), (TYPE_SCE, 0), (TYPE_LFE, 0), (TYPE_CPE, 2), (TYPE_CPE, 1)],
+}
+_CHAN_CONFIG = {(TYPE_SCE,): 1, (TYPE_CPE,): 2, (TYPE_SCE, TYPE_CPE): 3, (TYPE_SCE, TYPE_CPE, TYPE_SCE): 4,
+                (TYPE_SCE, TYPE_CPE, TYPE_CPE): 5, (TYPE_SCE, TYPE_CPE, TYPE_CPE, TYPE_LFE): 6,
+                (TYPE_SCE, TYPE_CPE, TYPE_CPE, TYPE_CPE, TYPE_LFE): 7}
+
+
+def reference_out_slots(elem_types):
+    """Output slot of every core channel (bitstream element order) in the reference's output order
+    (output_configure, aacdec.c:214-272).  Identity for layouts outside the default configurations."""
+    cc = _CHAN_CONFIG.get(tuple(elem_types))
+    ncc = n_core_channels(elem_types)
+    if cc is None:
+        return list(range(ncc))
+    ids, cnt = [], {}
+    for t in elem_types:
+        ids.append((t, cnt.get(t, 0)))
+        cnt[t] = cnt.get(t, 0) + 1
+    first_slot, pos = {}, 0
+    for key in _LAYOUT_MAP[cc]:
+        first_slot[key] = pos
+        pos += 2 if key[0] == TYPE_CPE else 1
+    slots = []
+    for key in ids:
+        slots += [first_slot[key] + i for i in range(2 if key[0] == TYPE_CPE else 1)]
+    return slots
+
+
 def make_config(n_streams, elem_types, sr_index, sbr=False, ps=False, bias_mode=False, device=0,
-                max_frames=1, want_float=True, keep_intermediates=False):
+                max_frames=1, want_float=True, keep_intermediates=False, out_slots="reference"):
     """Build a HeaacConfig.  bias_mode selects the reference's C 'bias' scaling (aacdec.c:573-576),
     otherwise the s16-unit scaling of its SIMD branch (aacdec.c:577-581)."""
     c = Config()
@@ -99,6 +132,11 @@ def make_config(n_streams, elem_types, sr_index, sbr=False, ps=False, bias_mode=
     c.max_frames_per_call = max_frames
     c.want_float_out = int(bool(want_float))
     c.keep_intermediates = int(bool(keep_intermediates))
+    if out_slots == "reference":
+        out_slots = reference_out_slots(list(elem_types)) if not ps else [0]
+    if out_slots is not None:
+        for i, v in enumerate(out_slots):
+            c.out_slot[i] = v
     return c
 
 

@@ -39,7 +39,26 @@ struct HeaacContext {
     int16_t *s_pcm; float *s_pcm_f32;
     long long launches;
     size_t smem_core, smem_sbr, smem_ps, smem_synth;
+    /* optional per-kernel event timing (heaac_b200_profile_*) */
+    int prof_on, prof_n, prof_cap;
+    cudaEvent_t *prof_ev;            /* 2 events per recorded launch */
+    unsigned char *prof_kind;        /* HEAAC_K_* per recorded launch */
 };
+
+enum { HEAAC_K_CORE = 0, HEAAC_K_SBR = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
+
+static void prof_begin(HeaacContext *c, int kind)
+{
+    if (!c->prof_on || c->prof_n >= c->prof_cap) return;
+    c->prof_kind[c->prof_n] = (unsigned char)kind;
+    cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream);
+}
+static void prof_end(HeaacContext *c)
+{
+    if (!c->prof_on || c->prof_n >= c->prof_cap) return;
+    cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream);
+    c->prof_n++;
+}
 
 /* ------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(HEAAC_THREADS)
@@ -61,11 +80,11 @@ k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict
     } else {
         const int bias_mode = g.add_bias != 0.0f;
         if (pcm) {
-            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + c;
+            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
             for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
         }
         if (pcm_f32) {
-            float *dst = pcm_f32 + ((size_t)s * g.nout + c) * 1024;
+            float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
             for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = out[i];
         }
     }
@@ -110,8 +129,8 @@ k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
     const int s = go / g.nout, c = go - s * g.nout;
     const float qmf_scale = -1024.0f * g.sf_scale;
     heaac_synth_channel(sm, X + (size_t)go * (2 * 38 * 64), synth + go,
-                        pcm ? pcm + (size_t)s * 2048 * g.nout + c : nullptr, g.nout,
-                        pcm_f32 ? pcm_f32 + (size_t)go * 2048 : nullptr,
+                        pcm ? pcm + (size_t)s * 2048 * g.nout + g.out_slot[c] : nullptr, g.nout,
+                        pcm_f32 ? pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 2048 : nullptr,
                         qmf_scale, g.add_bias, T, threadIdx.x, blockDim.x);
 }
 
@@ -152,6 +171,11 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
     g->ps = cfg->ps != 0;
     g->add_bias = cfg->add_bias;
     g->sf_scale = cfg->sf_scale;
+    {
+        int any = 0;
+        for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
+        for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) g->out_slot[i] = (any && !cfg->ps) ? cfg->out_slot[i] : (uint8_t)i;
+    }
 }
 
 static int init_state(HeaacContext *c)
@@ -189,6 +213,16 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (nch > HEAAC_MAX_CHANNELS) return HEAAC_E_INVAL;
     if (cfg->ps && !(cfg->sbr && cfg->n_elems == 1 && cfg->elem_type[0] == HEAAC_TYPE_SCE)) return HEAAC_E_INVAL;
     if (cfg->sbr && has_lfe) return HEAAC_E_UNSUPPORTED;     /* see DESIGN.md "out of scope" */
+    {
+        int any = 0, seen = 0;
+        for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
+        if (any && !cfg->ps) {
+            for (int i = 0; i < nch; i++) {
+                if (cfg->out_slot[i] >= nch || (seen >> cfg->out_slot[i]) & 1) return HEAAC_E_INVAL;
+                seen |= 1 << cfg->out_slot[i];
+            }
+        }
+    }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
@@ -263,6 +297,8 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaFree(c->d_core_time); cudaFree(c->d_X);
     cudaFree(c->s_coeffs); cudaFree(c->s_ics); cudaFree(c->s_tns); cudaFree(c->s_sbr); cudaFree(c->s_ps);
     cudaFree(c->s_pcm); cudaFree(c->s_pcm_f32);
+    for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]);
+    free(c->prof_ev); free(c->prof_kind);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -296,21 +332,29 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
         const HeaacTns *tn = tns ? tns + (size_t)f * S * g.ncc : nullptr;
         int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
         float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+        prof_begin(c, HEAAC_K_CORE);
         k_core<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_core, c->stream>>>(
             g, co, ic, tn, c->d_chan, c->d_core_time, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+        prof_end(c);
         c->launches++;
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
+            prof_begin(c, HEAAC_K_SBR);
             k_sbr<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_sbr, c->stream>>>(
                 g, c->d_core_time, sb, c->d_chan, c->d_X, c->d_tables);
+            prof_end(c);
             c->launches++;
             if (g.ps) {
+                prof_begin(c, HEAAC_K_PS);
                 k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(
                     g, ps + (size_t)f * S, sb, c->d_ps, c->d_X, c->d_tables);
+                prof_end(c);
                 c->launches++;
             }
+            prof_begin(c, HEAAC_K_SYNTH);
             k_synth<<<(unsigned)(S * g.nout), HEAAC_THREADS, c->smem_synth, c->stream>>>(
                 g, c->d_X, c->d_synth, pc, pf, c->d_tables);
+            prof_end(c);
             c->launches++;
         }
     }
@@ -404,6 +448,41 @@ extern "C" int heaac_b200_timer_stop(HeaacContext *c, float *ms)
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+/* Per-kernel timing with CUDA events on the context's stream.  enable(capacity) starts recording up to
+ * `capacity` launches; read() synchronises and returns total milliseconds and launch counts per kernel
+ * kind (0 core, 1 sbr, 2 ps, 3 synth), then clears the record. */
+extern "C" int heaac_b200_profile_enable(HeaacContext *c, int capacity)
+{
+    if (!c || capacity < 0) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    if (capacity > c->prof_cap) {
+        cudaEvent_t *ev = (cudaEvent_t *)realloc(c->prof_ev, sizeof(cudaEvent_t) * 2 * capacity);
+        unsigned char *kd = (unsigned char *)realloc(c->prof_kind, capacity);
+        if (!ev || !kd) return HEAAC_E_NOMEM;
+        c->prof_ev = ev; c->prof_kind = kd;
+        for (int i = 2 * c->prof_cap; i < 2 * capacity; i++) CK(cudaEventCreate(&c->prof_ev[i]));
+        c->prof_cap = capacity;
+    }
+    c->prof_n = 0;
+    c->prof_on = capacity > 0;
+    return 0;
+}
+extern "C" int heaac_b200_profile_read(HeaacContext *c, float ms[4], long long counts[4])
+{
+    if (!c || !ms || !counts) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < HEAAC_K_COUNT; k++) { ms[k] = 0.0f; counts[k] = 0; }
+    for (int i = 0; i < c->prof_n; i++) {
+        float t = 0.0f;
+        CK(cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        ms[c->prof_kind[i]] += t;
+        counts[c->prof_kind[i]]++;
+    }
+    c->prof_n = 0;
     return 0;
 }
 

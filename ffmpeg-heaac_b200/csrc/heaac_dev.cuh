@@ -115,6 +115,7 @@ struct HeaacGeom {
     uint8_t ch_in_elem[HEAAC_MAX_CHANNELS];  /* core channel -> 0/1 inside its element */
     uint8_t ch_sbr_elem[HEAAC_MAX_CHANNELS]; /* core channel -> SBR element index (0xff for LFE) */
     uint8_t elem_is_cpe[HEAAC_MAX_CHANNELS]; /* per core channel: its element is a CPE */
+    uint8_t out_slot[HEAAC_MAX_CHANNELS];    /* core (or synthesised) channel -> position in the output */
 };
 
 #endif

@@ -1050,11 +1050,16 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         for (int b = tid; b < nr_par; b += nt) {          /* serial over envelopes: the phase smoother has memory */
             int oh = st->opd_hist[b < 34 ? b : 0], ih = st->ipd_hist[b < 34 ? b : 0];
             for (int e = 0; e < p->num_env; e++) {
-                const float *lut = H_LUT[sm->iid[e][b] + 7 + 23 * p->iid_quant][sm->icc[e][b]];
+                /* indices are range-checked by the parser (aacps.c:116-117); clamp so that a corrupt
+                 * parameter block can never index outside the table */
+                int li = sm->iid[e][b] + 7 + 23 * p->iid_quant, lc = sm->icc[e][b];
+                li = li < 0 ? 0 : (li > 45 ? 45 : li);
+                lc = lc < 0 ? 0 : (lc > 7 ? 7 : lc);
+                const float *lut = H_LUT[li][lc];
                 float h11 = lut[0], h12 = lut[1], h21 = lut[2], h22 = lut[3];
                 if (p->enable_ipdopd && b < p->nr_ipdopd_par) {
-                    int opd_idx = oh * 8 + sm->opd[e][b];
-                    int ipd_idx = ih * 8 + sm->ipd[e][b];
+                    int opd_idx = (oh * 8 + (sm->opd[e][b] & 7)) & 511;
+                    int ipd_idx = (ih * 8 + (sm->ipd[e][b] & 7)) & 511;
                     float opd_re = T->pd_re_smooth[opd_idx], opd_im = T->pd_im_smooth[opd_idx];
                     float ipd_re = T->pd_re_smooth[ipd_idx], ipd_im = T->pd_im_smooth[ipd_idx];
                     oh = opd_idx & 0x3F; ih = ipd_idx & 0x3F;

@@ -145,9 +145,8 @@ typedef struct HeaacPsFrame {
 /* ---- context configuration ---------------------------------------------------------
  * A context decodes `n_streams` independent streams that share one channel layout
  * (the BASELINE configs: stereo CPE, mono SCE + PS, 5.1 = SCE CPE CPE LFE, ...).
- * Channel c of a stream is the c-th core channel in element order; the interleaved
- * output order is the same (the reference orders output_data[] by element position,
- * aacdec.c:150-190 -- for the layouts above this is bitstream element order). */
+ * Channel c of a stream is the c-th core channel in element (bitstream) order; cfg.out_slot[c]
+ * gives its position in the interleaved / planar output. */
 typedef struct HeaacConfig {
     uint32_t abi_version;           /* HEAAC_ABI_VERSION                             */
     int32_t  device;                /* CUDA device ordinal                           */
@@ -166,7 +165,10 @@ typedef struct HeaacConfig {
     int32_t  max_frames_per_call;   /* T: capacity of the device staging buffers     */
     int32_t  want_float_out;        /* also produce planar float PCM (debug / float parity) */
     int32_t  keep_intermediates;    /* keep per-stage arrays readable via heaac_b200_debug_read */
-    int32_t  reserved[4];
+    /* Interleaved output position of core channel c.  The reference orders its output by
+     * aac_channel_layout_map (aacdectab.h:74-82, output_configure aacdec.c:214-272), e.g. 5.1 =
+     * {CPE0, SCE0, LFE0, CPE1} while the bitstream order is {SCE0, CPE0, CPE1, LFE0}.  All zero = identity. */
+    uint8_t  out_slot[HEAAC_MAX_CHANNELS];
 } HeaacConfig;
 
 /* One call = `n_frames` consecutive frames of every stream.  Arrays are frame-major:
@@ -232,9 +234,24 @@ int  heaac_b200_dev_download(HeaacContext *ctx, void *hptr, const void *dptr, si
 int  heaac_b200_timer_start(HeaacContext *ctx);
 int  heaac_b200_timer_stop(HeaacContext *ctx, float *ms);
 
+/* Per-kernel event timing on the context's stream.  enable(capacity > 0) records up to `capacity`
+ * launches (0 disables); read() synchronises, returns total ms and launch counts per kernel kind
+ * (0 core, 1 sbr, 2 ps, 3 synth) and clears the record. */
+int  heaac_b200_profile_enable(HeaacContext *ctx, int capacity);
+int  heaac_b200_profile_read(HeaacContext *ctx, float ms[4], long long counts[4]);
+
 /* Stage-level inspection (requires cfg.keep_intermediates).  Copies the named array of
  * the LAST frame processed to host.  Names and layouts: see DESIGN.md "intermediates". */
 int  heaac_b200_debug_read(HeaacContext *ctx, const char *name, void *dst, size_t bytes);
+
+/* ---- host front-end helper: SBR frequency tables -------------------------------------------
+ * What the reference's sbr_reset() derives when a header changes (aacsbr.c:1023-1034 ->
+ * sbr_make_f_master 303-488, sbr_make_f_derived 541-593, sbr_hf_calc_npatches 490-539,
+ * sbr_make_f_tablelim 159-205).  Pure host code, no GPU needed.  Fills k0, kx[1], m[1], n[], n_q,
+ * n_lim, f_table*, patch_* of *out; returns HEAAC_E_INVAL where the reference rejects the header. */
+int  heaac_b200_sbr_tables(int core_sample_rate, int bs_start_freq, int bs_stop_freq, int bs_xover_band,
+                           int bs_freq_scale, int bs_alter_scale, int bs_noise_bands, int bs_limiter_bands,
+                           HeaacSbrElem *out);
 
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */

@@ -57,6 +57,8 @@ def lib():
         L.ref_enc_close.argtypes = [C.c_void_p]
         L.ref_table.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ref_set_log_level.argtypes = [C.c_int]
+        L.ref_dec_decode_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_dec_decode_many.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -166,6 +168,18 @@ class Decoder:
             r["pcm_f32"] = f32[:ns * ch].reshape(ch, ns).copy()
         r["consumed"] = ret
         return r
+
+    def decode_many(self, pkts, repeat=1):
+        """Decode the packet list `repeat` times in one C call (CPU-baseline timing); returns samples/channel."""
+        sizes = np.asarray([len(p) for p in pkts], np.int32)
+        offs = np.zeros(len(pkts), np.int32)
+        blob = bytearray()
+        for i, p in enumerate(pkts):
+            offs[i] = len(blob)
+            blob += p + bytes(PADDING)
+        blob = np.frombuffer(bytes(blob), np.uint8)
+        self._keep = (blob, offs, sizes)
+        return lib().ref_dec_decode_many(self.h, _ptr(blob), _ptr(offs), _ptr(sizes), len(pkts), repeat)
 
     def peek(self, name, dtype, shape, elem=0, ch=0):
         a = np.zeros(shape, dtype)

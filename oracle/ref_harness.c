@@ -271,6 +271,29 @@ int ref_dec_decode(RefDec *d, const uint8_t *pkt, int size, int16_t *out, int *o
     return ret;
 }
 
+/* Timing helper for the CPU baseline: decode `n` packets (concatenated in `blob`, each followed by
+ * FF_INPUT_BUFFER_PADDING_SIZE zero bytes; offsets/sizes given) `repeat` times through the same context,
+ * entirely in C.  Returns the number of output samples per channel produced, or <0 on error. */
+long long ref_dec_decode_many(RefDec *d, const uint8_t *blob, const int *offsets, const int *sizes, int n, int repeat)
+{
+    static __thread int16_t out[8 * 2048 + 64] __attribute__((aligned(16)));
+    long long samples = 0;
+    for (int r = 0; r < repeat; r++)
+        for (int i = 0; i < n; i++) {
+            AVPacket avpkt;
+            int out_bytes = sizeof(out);
+            memset(&avpkt, 0, sizeof(avpkt));
+            avpkt.data = (uint8_t *)blob + offsets[i];
+            avpkt.size = sizes[i];
+            cur_dec = d;
+            int ret = aac_decoder.decode(&d->avctx, out, &out_bytes, &avpkt);
+            cur_dec = NULL;
+            if (ret < 0) return -1;
+            samples += d->avctx.channels ? out_bytes / 2 / d->avctx.channels : 0;
+        }
+    return samples;
+}
+
 int ref_dec_channels(RefDec *d)    { return d->avctx.channels; }
 int ref_dec_sample_rate(RefDec *d) { return d->avctx.sample_rate; }
 int ref_dec_sbr(RefDec *d)         { return ((AACContext *)d->avctx.priv_data)->m4ac.sbr; }

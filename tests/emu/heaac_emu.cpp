@@ -42,6 +42,9 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
     g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch; g->out_len = cfg->sbr ? 2048 : 1024;
     g->sr_index = cfg->sr_index; g->sbr = cfg->sbr != 0; g->ps = cfg->ps != 0;
     g->add_bias = cfg->add_bias; g->sf_scale = cfg->sf_scale;
+    int any = 0;
+    for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
+    for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) g->out_slot[i] = (any && !cfg->ps) ? cfg->out_slot[i] : (uint8_t)i;
 }
 
 extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
@@ -93,8 +96,8 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
                                g.sr_index, c->T, 0, 1);
             if (g.sbr) memcpy(c->core_time + gc * 1024, out, sizeof(out));
             else for (int i = 0; i < 1024; i++) {
-                if (pc) pc[(s * 1024 + i) * g.nout + ch] = heaac_to_s16(out[i], g.add_bias != 0.0f);
-                if (pf) pf[(s * g.nout + ch) * 1024 + i] = out[i];
+                if (pc) pc[(s * 1024 + i) * g.nout + g.out_slot[ch]] = heaac_to_s16(out[i], g.add_bias != 0.0f);
+                if (pf) pf[(s * g.nout + g.out_slot[ch]) * 1024 + i] = out[i];
             }
         }
         if (!g.sbr) continue;
@@ -117,8 +120,8 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             size_t s = go / g.nout; int ch = (int)(go - s * g.nout);
             memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
             heaac_synth_channel(c->sm_synth, c->X + go * (2 * 38 * 64), c->synth + go,
-                                pc ? pc + s * 2048 * g.nout + ch : nullptr, g.nout,
-                                pf ? pf + go * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0, 1);
+                                pc ? pc + s * 2048 * g.nout + g.out_slot[ch] : nullptr, g.nout,
+                                pf ? pf + (s * g.nout + g.out_slot[ch]) * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0, 1);
         }
     }
     return 0;

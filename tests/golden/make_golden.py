@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, needs /root/reference to build).
+
+Each file holds, for a short synthetic stream: the raw_data_block packets and extradata, what the
+reference's parsers hand to spectral_to_sample (aacdec.c:2078) packed into the C-ABI structs, and the
+reference decoder's own output for them (s16 from the default C 'bias' path and full-precision float PCM
+from its SIMD-scaling path).  Committed so that the oracle and the CUDA path can be pinned where the
+reference is absent (the GPU box).  Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import pyref  # noqa: E402
+import heaac_streams as hs  # noqa: E402
+
+abi = pyref.abi
+
+
+def lc_stream(seed, nfr, channels, rate, layout):
+    pcm = pyref.lcg_noise(1024 * (nfr + 1), channels, seed=seed).astype(np.int32)
+    for st in (3000, 7000, 8200, 15000):
+        pcm[st:st + 300] *= 6          # attacks -> LONG_START / EIGHT_SHORT / LONG_STOP
+    enc = pyref.Encoder(rate, channels, 64000 * channels)
+    pk = enc.encode(np.clip(pcm, -32768, 32767).astype(np.int16))[:nfr]
+    ed = enc.extradata
+    enc.close()
+    return pk, ed, rate, channels, layout
+
+
+def capture(pkts, ed, rate, channels, layout):
+    df = pyref.Decoder(ed, rate, channels, layout, float_mode=True)
+    db = pyref.Decoder(ed, rate, channels, layout, float_mode=False)
+    fr = [df.decode(p) for p in pkts]
+    frb = [db.decode(p, capture=False) for p in pkts]
+    out = {k: np.stack([f[k] for f in fr]) for k in ("coeffs", "ics", "tns", "sbr", "ps", "pcm_f32")}
+    out["pcm_s16_simd_path"] = np.stack([f["pcm"] for f in fr])
+    out["pcm_s16_c_path"] = np.stack([f["pcm"] for f in frb])
+    out["sr_index"] = np.int32(df.sr_index)
+    out["sbr_flag"] = np.int32(1 if df.sbr == 1 else 0)
+    out["ps_flag"] = np.int32(1 if df.ps == 1 and channels == 1 else 0)
+    out["elem_types"] = np.asarray(pyref.LAYOUTS[layout][0], np.int32)
+    out["extradata"] = np.frombuffer(ed, np.uint8)
+    out["pkt_sizes"] = np.asarray([len(p) for p in pkts], np.int32)
+    out["pkt_blob"] = np.frombuffer(b"".join(pkts), np.uint8)
+    out["core_rate"] = np.int32(rate)
+    df.close(); db.close()
+    return out
+
+
+def main():
+    cases = {
+        "lc_stereo_44k": lc_stream(1234, 10, 2, 44100, "stereo"),
+        "lc_51_48k": lc_stream(77, 6, 6, 48000, "5.1"),
+    }
+    for name, seed, stereo, ps in (("heaac_v1_stereo", 7, True, False), ("heaac_v2_ps", 26, False, True)):
+        pkts, ed, info = hs.make_stream(seed, 12, stereo=stereo, ps=ps)
+        cases[name] = (pkts, ed, 24000, 2 if stereo else 1, "stereo" if stereo else "mono")
+    for name, c in cases.items():
+        d = capture(*c)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **d)
+        print(name, d["coeffs"].shape, d["pcm_f32"].shape, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+"""Pins the oracle (oracle/heaac_oracle.c): against the committed golden vectors produced by the reference
+decoder, and -- where oracle/_ref is available -- against the reference itself on fresh synthetic streams."""
+import numpy as np
+import pytest
+
+import pyoracle
+from common import GOLDEN_CASES, abi, assert_pcm_close, golden_args, golden_config, golden_ref_pcm, load_golden
+from conftest import needs_ref
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("bias_mode", [False, True])
+def test_oracle_reproduces_golden_vectors(name, bias_mode):
+    d = load_golden(name)
+    orc = pyoracle.Oracle(golden_config(d, bias_mode=bias_mode))
+    pcm, f32 = orc.synth(*golden_args(d, bias_mode=bias_mode))
+    orc.close()
+    ref_f32, ref_s16 = golden_ref_pcm(d)
+    if bias_mode:      # the C bias path carries the signal as 385 + x/32768: compare s16 only
+        assert int(np.abs(pcm[:, 0].astype(np.int32) - ref_s16).max()) <= 1
+    else:
+        assert_pcm_close(f32[:, 0], ref_f32, pcm[:, 0], ref_s16, name)
+
+
+def test_golden_both_reference_scalings_agree():
+    """The reference's C-bias and SIMD-scaling paths give bit-identical s16."""
+    for name in GOLDEN_CASES:
+        d = load_golden(name)
+        assert np.array_equal(d["pcm_s16_c_path"], d["pcm_s16_simd_path"]), name
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,seed", [("v1", 101), ("v1", 102), ("v2", 201), ("v2", 202), ("v2", 203)])
+def test_oracle_matches_reference_on_fresh_heaac_streams(mode, seed):
+    import heaac_streams as hs
+    stereo, ps = mode == "v1", mode == "v2"
+    pkts, ed, info = hs.make_stream(seed, 28, stereo=stereo, ps=ps)
+    frames, d = hs.decode_with_reference(pkts, ed, 24000, 2 if stereo else 1)
+    assert d.sbr == 1 and (d.ps == 1) == ps
+    cfg = abi.make_config(1, [abi.TYPE_CPE] if stereo else [abi.TYPE_SCE], d.sr_index, sbr=True, ps=ps)
+    st = lambda k: np.stack([f[k] for f in frames])[:, None]
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), st("sbr"), st("ps")[:, :, 0] if ps else None)
+    orc.close()
+    assert_pcm_close(f32[:, 0], np.stack([f["pcm_f32"] for f in frames]), pcm[:, 0],
+                     np.stack([f["pcm"] for f in frames]), "%s/%d" % (mode, seed))
+    if ps:      # the fixture must really exercise PS: 20- and 34-band modes, IPD/OPD
+        assert any(int(f["ps"][0]["start"]) for f in frames)
+
+
+@needs_ref
+def test_oracle_stage_arrays_match_reference():
+    """Stage-by-stage: W, X_low, alpha, X_high, e_curr, gain, Y of the last frame (SURVEY 8c 'stage-level oracle')."""
+    import heaac_streams as hs
+    pkts, ed, info = hs.make_stream(55, 10, stereo=True)
+    frames, d = hs.decode_with_reference(pkts, ed, 24000, 2)
+    cfg = abi.make_config(1, [abi.TYPE_CPE], d.sr_index, sbr=True)
+    st = lambda k: np.stack([f[k] for f in frames])[:, None]
+    orc = pyoracle.Oracle(cfg)
+    orc.synth(st("coeffs"), st("ics"), st("tns"), st("sbr"))
+    s = frames[-1]["sbr"][0]
+    kx, m = int(s["kx"][1]), int(s["m"][1])
+    for ch in (0, 1):
+        W_ref = d.peek("W", np.float32, (2, 32, 32, 2), ch=ch)
+        W = orc.peek("W", np.float32, (2, 32, 32, 2), ch=ch)
+        assert np.abs(W - W_ref).max() <= 1e-5 * np.abs(W_ref).max()
+        Y_ref = d.peek("Y", np.float32, (2, 38, 64, 2), ch=ch)
+        Y = orc.peek("Y", np.float32, (2, 38, 64, 2), ch=ch)
+        assert np.abs(Y[1, :32, kx:kx + m] - Y_ref[1, :32, kx:kx + m]).max() <= 2e-5 * np.abs(Y_ref).max()
+    # element-level scratch holds the LAST processed channel (1)
+    for name, shape, rows in (("X_low", (32, 40, 2), slice(0, kx)), ("X_high", (64, 40, 2), slice(kx, kx + m)),
+                              ("alpha0", (64, 2), slice(0, int(s["k0"]))), ("alpha1", (64, 2), slice(0, int(s["k0"])))):
+        a_ref = d.peek(name, np.float32, shape, ch=1)[rows]
+        a = orc.peek(name, np.float32, shape, ch=1)[rows]
+        tol = 1e-3 if name.startswith("alpha") else 2e-5 * np.abs(a_ref).max()
+        assert np.abs(a - a_ref).max() <= tol, name
+    orc.close()
+
+
+@needs_ref
+def test_reference_output_channel_order():
+    """cfg.out_slot (abi.reference_out_slots) reproduces the reference's 5.1 output order FL FR FC LFE BL BR."""
+    assert abi.reference_out_slots([abi.TYPE_SCE, abi.TYPE_CPE, abi.TYPE_CPE, abi.TYPE_LFE]) == [2, 0, 1, 4, 5, 3]
+    d = load_golden("lc_51_48k")
+    orc = pyoracle.Oracle(golden_config(d))
+    pcm, f32 = orc.synth(*golden_args(d))
+    orc.close()
+    for c in range(6):
+        assert np.abs(f32[:, 0, c] - d["pcm_f32"][:, c]).max() / 32768.0 <= 1e-5, "channel %d" % c
