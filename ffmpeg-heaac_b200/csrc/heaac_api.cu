@@ -102,7 +102,7 @@ k_sbr(HeaacGeom g, const float *__restrict__ core_time, const HeaacSbrElem *__re
     if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
     const float qmf_scale = -1024.0f * g.sf_scale;   /* aacsbr.c:1764 */
     const float ana_scale = 1 / qmf_scale;           /* aacsbr.c:1730 */
-    float *Xc = X + ((size_t)s * g.nout + c) * (2 * 38 * 64);
+    float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
     heaac_sbr_channel(sm, core_time + (size_t)gc * 1024, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
                       g.elem_is_cpe[c], chan + gc, Xc, ana_scale, T, threadIdx.x, blockDim.x);
 }
@@ -114,24 +114,26 @@ k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacPsSmem *sm = reinterpret_cast<HeaacPsSmem *>(smem_raw);
     const int s = blockIdx.x;
-    float *XL = X + (size_t)s * 2 * (2 * 38 * 64), *XR = XL + 2 * 38 * 64;
+    float *XL = X + (size_t)s * 2 * HEAAC_X_FLOATS, *XR = XL + HEAAC_X_FLOATS;
     const HeaacSbrElem *e = sbr + (size_t)s * g.nse;
     heaac_ps_stream(sm, ps + s, pstate + s, XL, XR, (int)e->kx[1] + (int)e->m[1], T, threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(HEAAC_THREADS)
+__global__ void __launch_bounds__(128)
 k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
         int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacSynthSmem *sm = reinterpret_cast<HeaacSynthSmem *>(smem_raw);
-    const int go = blockIdx.x;                       /* s * nout + c */
-    const int s = go / g.nout, c = go - s * g.nout;
+    /* one CTA per (stream, SBR element): its 1 or 2 output channels */
+    const int s = blockIdx.x / g.nse, e = blockIdx.x - s * g.nse;
+    const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
     const float qmf_scale = -1024.0f * g.sf_scale;
-    heaac_synth_channel(sm, X + (size_t)go * (2 * 38 * 64), synth + go,
-                        pcm ? pcm + (size_t)s * 2048 * g.nout + g.out_slot[c] : nullptr, g.nout,
-                        pcm_f32 ? pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 2048 : nullptr,
-                        qmf_scale, g.add_bias, T, threadIdx.x, blockDim.x);
+    const size_t go = (size_t)s * g.nout + c0;
+    heaac_synth_stream(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
+                       pcm ? pcm + (size_t)s * 2048 * g.nout : nullptr,
+                       pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 2048 : nullptr,
+                       qmf_scale, g.add_bias, T, threadIdx.x, blockDim.x);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -162,6 +164,21 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
         }
         if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
     }
+    /* synthesis works per SBR element: its first output channel and channel count (PS: mono in, 2 out) */
+    {
+        int o = 0, k = 0;
+        g->max_elem_ch = 1;
+        for (int e = 0; e < cfg->n_elems; e++) {
+            int nch = cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+            if (cfg->elem_type[e] != HEAAC_TYPE_LFE) {
+                g->elem_first_out[k] = (uint8_t)o;
+                g->elem_nout[k] = (uint8_t)(cfg->ps ? 2 : nch);
+                if (nch > g->max_elem_ch) g->max_elem_ch = nch;
+                k++;
+            }
+            o += nch;
+        }
+    }
     g->ncc = ch;
     g->nse = se;
     g->nout = cfg->ps ? 2 : ch;
@@ -185,7 +202,7 @@ static int init_state(HeaacContext *c)
     CK(cudaMemsetAsync(c->d_chan, 0, nch * sizeof(HeaacChanState), c->stream));
     if (g->sbr) {
         CK(cudaMemsetAsync(c->d_synth, 0, (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState), c->stream));
-        CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * 2 * 38 * 64 * sizeof(float), c->stream));
+        CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
         CK(cudaMemsetAsync(c->d_core_time, 0, nch * 1024 * sizeof(float), c->stream));
     }
     if (g->ps) CK(cudaMemsetAsync(c->d_ps, 0, (size_t)g->n_streams * sizeof(HeaacPsState), c->stream));
@@ -261,7 +278,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     CKX(cudaMalloc(&c->d_chan, S * g->ncc * sizeof(HeaacChanState)));
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
-        CKX(cudaMalloc(&c->d_X, S * g->nout * 2 * 38 * 64 * sizeof(float)));
+        CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
         CKX(cudaMalloc(&c->d_core_time, S * g->ncc * 1024 * sizeof(float)));
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
@@ -352,7 +369,7 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            k_synth<<<(unsigned)(S * g.nout), HEAAC_THREADS, c->smem_synth, c->stream>>>(
+            k_synth<<<(unsigned)(S * g.nse), 64 * (g.ps ? 2 : g.max_elem_ch), c->smem_synth, c->stream>>>(
                 g, c->d_X, c->d_synth, pc, pf, c->d_tables);
             prof_end(c);
             c->launches++;
@@ -491,7 +508,7 @@ extern "C" int heaac_b200_debug_read(HeaacContext *c, const char *name, void *ds
     if (!c || !name || !dst) return HEAAC_E_INVAL;
     const HeaacGeom *g = &c->geom;
     const void *src = nullptr; size_t avail = 0;
-    if (!strcmp(name, "X") && c->d_X) { src = c->d_X; avail = (size_t)g->n_streams * g->nout * 2 * 38 * 64 * sizeof(float); }
+    if (!strcmp(name, "X") && c->d_X) { src = c->d_X; avail = (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float); }
     else if (!strcmp(name, "core_time") && c->d_core_time) { src = c->d_core_time; avail = (size_t)g->n_streams * g->ncc * 1024 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { src = c->d_chan; avail = (size_t)g->n_streams * g->ncc * sizeof(HeaacChanState); }
     else if (!strcmp(name, "synth_state") && c->d_synth) { src = c->d_synth; avail = (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState); }

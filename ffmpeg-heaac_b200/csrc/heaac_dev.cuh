@@ -104,6 +104,13 @@ struct HeaacPsState {
     uint32_t pad[3];
 };
 
+/* Inter-kernel QMF-domain buffer of one channel: X[plane re/im][band 0..63][slot], slot fastest so that
+ * kernels whose lanes are time slots read and write it coalesced (the reference's sbr->X is
+ * [2][38][64], sbr.h:162). */
+#define HEAAC_XS        40                   /* slot stride (38 used) */
+#define HEAAC_X_PLANE   (64 * HEAAC_XS)
+#define HEAAC_X_FLOATS  (2 * HEAAC_X_PLANE)
+
 /* compact per-launch geometry */
 struct HeaacGeom {
     int n_streams, ncc, nout, nse, out_len;
@@ -116,6 +123,9 @@ struct HeaacGeom {
     uint8_t ch_sbr_elem[HEAAC_MAX_CHANNELS]; /* core channel -> SBR element index (0xff for LFE) */
     uint8_t elem_is_cpe[HEAAC_MAX_CHANNELS]; /* per core channel: its element is a CPE */
     uint8_t out_slot[HEAAC_MAX_CHANNELS];    /* core (or synthesised) channel -> position in the output */
+    uint8_t elem_first_out[HEAAC_MAX_ELEMS]; /* SBR element -> its first output channel */
+    uint8_t elem_nout[HEAAC_MAX_ELEMS];      /* SBR element -> number of output channels (2 with PS) */
+    int max_elem_ch;
 };
 
 #endif

@@ -21,6 +21,7 @@
 #define HEAAC_KERNELS_CUH
 
 #include "heaac_dev.cuh"
+#include "heaac_regfft.cuh"
 
 #ifdef HEAAC_HOST_EMU
 #define HEAAC_CONST_TABLE static const
@@ -400,7 +401,7 @@ HEAAC_DEV void heaac_sbr_y(const HeaacSbrSmem *sm, const HeaacChanState *st, con
 }
 
 /* core_time: 1024 floats (global) of this channel's IMDCT output.
- * X_out   : this channel's X[2][38][64] plane in global scratch. */
+ * X_out   : this channel's X[2][64][HEAAC_XS] (band-major) buffer in global scratch. */
 HEAAC_DEV void heaac_sbr_channel(HeaacSbrSmem *sm, const float *HEAAC_RESTRICT core_time,
                                  const HeaacSbrElem *HEAAC_RESTRICT elem, int ch, int is_cpe,
                                  HeaacChanState *st, float *X_out, float ana_scale,
@@ -693,9 +694,10 @@ HEAAC_DEV void heaac_sbr_channel(HeaacSbrSmem *sm, const float *HEAAC_RESTRICT c
         y.kx = kx; y.m_max = m_max; y.reset = p->reset;
         y.e_a0 = pc->e_a[0]; y.e_a1 = pc->e_a[1];
         const int i_Temp = HEAAC_MAX(y.t_old2 - 32, 0);
-        float *Xre = X_out, *Xim = X_out + 38 * 64;
-        for (int w = tid; w < 38 * 64; w += nt) {
-            int i = w >> 6, k = w & 63;
+        float *Xre = X_out, *Xim = X_out + HEAAC_X_PLANE;
+        for (int w = tid; w < 64 * HEAAC_XS; w += nt) {
+            int k = w / HEAAC_XS, i = w - k * HEAAC_XS;      /* slot fastest: coalesced band-major store */
+            if (i >= 38) continue;
             float re = 0.0f, im = 0.0f;
             const int in_hf = p->start && i >= y.i_lo && i < y.i_hi && k >= kx && k < kx + m_max;
             float yre = 0.0f, yim = 0.0f;
@@ -844,7 +846,7 @@ HEAAC_DEV void heaac_ps_map_val(float *v, int to34)
     for (int b = 0; b < 34; b++) v[b] = o[b];
 }
 
-/* XL / XR: the element's X[2][38][64] planes in global scratch (XL in/out, XR out).
+/* XL / XR: the element's band-major X buffers in global scratch (XL in/out, XR out).
  * top_in = kx + m of the SBR element (aacsbr.c:1753). */
 HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRICT frame, HeaacPsState *st,
                                float *XL, float *XR, int top_in,
@@ -857,9 +859,9 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     }
     HEAAC_SYNC();
     const HeaacPsFrame *p = &sm->p;
-    const float *Lre = XL, *Lim = XL + 38 * 64;
+    const float *Lre = XL, *Lim = XL + HEAAC_X_PLANE;
     if (!p->start) {                                      /* aacsbr.c:1755: R = copy of L */
-        for (int i = tid; i < 2 * 38 * 64; i += nt) XR[i] = XL[i];
+        for (int i = tid; i < HEAAC_X_FLOATS; i += nt) XR[i] = XL[i];
         HEAAC_SYNC();
         return;
     }
@@ -874,7 +876,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     for (int w = tid; w < 5 * 44; w += nt) {
         int i = w / 44, j = w - i * 44;
         if (j < 6) { sm->in[i][j][0] = st->in_hist[i][j][0]; sm->in[i][j][1] = st->in_hist[i][j][1]; }
-        else       { sm->in[i][j][0] = Lre[(j - 6) * 64 + i]; sm->in[i][j][1] = Lim[(j - 6) * 64 + i]; }
+        else       { sm->in[i][j][0] = Lre[i * HEAAC_XS + (j - 6)]; sm->in[i][j][1] = Lim[i * HEAAC_XS + (j - 6)]; }
     }
     HEAAC_SYNC();
     for (int w = tid; w < 5 * 6; w += nt) {
@@ -892,7 +894,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         }
         for (int w = tid; w < 59 * 32; w += nt) {
             int i = w >> 5, n = w & 31;
-            sm->L[i + 32][n][0] = Lre[n * 64 + i + 5]; sm->L[i + 32][n][1] = Lim[n * 64 + i + 5];
+            sm->L[i + 32][n][0] = Lre[(i + 5) * HEAAC_XS + n]; sm->L[i + 32][n][1] = Lim[(i + 5) * HEAAC_XS + n];
         }
     } else {
         for (int n = tid; n < 32; n += nt) {              /* hybrid6_cx + 2 x hybrid2_re */
@@ -918,7 +920,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         }
         for (int w = tid; w < 61 * 32; w += nt) {
             int i = w >> 5, n = w & 31;
-            sm->L[i + 10][n][0] = Lre[n * 64 + i + 3]; sm->L[i + 10][n][1] = Lim[n * 64 + i + 3];
+            sm->L[i + 10][n][0] = Lre[(i + 3) * HEAAC_XS + n]; sm->L[i + 10][n][1] = Lim[(i + 3) * HEAAC_XS + n];
         }
     }
     HEAAC_SYNC();
@@ -1120,7 +1122,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
 
     /* ---- hybrid synthesis x 2, aacps.c:397-445: back to 64 QMF bands, slots 0..31 ---- */
     for (int w = tid; w < 2 * 32 * 64; w += nt) {
-        int side = w >> 11, n = (w >> 6) & 31, q = w & 63;
+        int side = w >> 11, q = (w >> 5) & 63, n = w & 31;      /* slot fastest */
         const float (*in)[32][2] = side ? sm->R : sm->L;
         float *X = side ? XR : XL;
         float re, im;
@@ -1139,65 +1141,96 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
             else if (q == 2)   { re = in[8][n][0] + in[9][n][0]; im = in[8][n][1] + in[9][n][1]; }
             else               { re = in[q + 7][n][0]; im = in[q + 7][n][1]; }
         }
-        X[n * 64 + q] = re;
-        X[38 * 64 + n * 64 + q] = im;
+        X[q * HEAAC_XS + n] = re;
+        X[HEAAC_X_PLANE + q * HEAAC_XS + n] = im;
     }
     HEAAC_SYNC();
 }
 
 /* ====================================================================================
- * QMF synthesis for one output channel-frame: X[2][38][64] -> 2048 PCM samples
+ * QMF synthesis (sbr_qmf_synthesis, aacsbr.c:1175-1230) + float->s16 for the 1 or 2 output channels of
+ * one stream-frame.  64 threads per channel:
+ *   phase 1  thread = (plane re/im, slot i): one half-IMDCT (N = 128, scale 1/64) in registers, inputs read
+ *            coalesced from the band-major X buffer (lanes = slots)
+ *   phase 2  the im-plane threads combine b0/b1 into the slot's 128-sample v block (aacsbr.c:1210-1213)
+ *   phase 3  thread = (sample n, channel): the 10-tap polyphase sum for all 32 slots with the window
+ *            column w[64 j + n] held in registers; s16 stores of the two channels interleave into
+ *            contiguous bytes
+ * v blocks use a row stride of 129 floats: phase 2 (lanes = slots) and phase 3 (lanes = samples) are both
+ * free of bank conflicts.
  * ================================================================================== */
+#define HEAAC_V_STRIDE 129
+#define HEAAC_SYN_CH_FLOATS (41 * HEAAC_V_STRIDE + 64 * 32 + 7)    /* = 16 (mod 32): the 2nd channel starts 16 banks away */
 struct HeaacSynthSmem {
-    float v[1152 + 32 * 128];       /* [0, 4096): this frame's 32 v-blocks, newest first; then history */
-    float in[64 * 64];              /* 64 transforms x 64 inputs (slot-major: 2 per slot) */
-    float zr[64 * 32], zi[64 * 32];
+    float ch[2][HEAAC_SYN_CH_FLOATS];   /* per channel: v[41][129] (block 0 = newest) then b0[64][32] */
 };
 
-HEAAC_DEV void heaac_synth_channel(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st,
-                                   int16_t *pcm, int pcm_stride, float *pcm_f32,
-                                   float scale, float bias,
-                                   const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nout,
+                                  int out_slot0, int out_slot1, int16_t *pcm, float *pcm_f32, float scale, float bias,
+                                  const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
 {
-    const float *Xre = X, *Xim = X + 38 * 64;
-    for (int i = tid; i < 1152; i += nt) sm->v[4096 + i] = st->v[i];
-    for (int w = tid; w < 32 * 64; w += nt) {
-        int i = w >> 6, n = w & 63;
-        sm->in[(2 * i) * 64 + n] = Xre[w];
-        float xi = Xim[w];
-        sm->in[(2 * i + 1) * 64 + n] = (n & 1) ? -xi : xi;       /* aacsbr.c:1205-1207 */
+    const int nthr = 64 * nout;
+    for (int w = tid; w < nout * 1152; w += nt) {          /* history: blocks 32..40 */
+        int c = w / 1152, r = w - c * 1152;
+        sm->ch[c][(32 + (r >> 7)) * HEAAC_V_STRIDE + (r & 127)] = st[c].v[r];
+    }
+    /* ---- phase 1: 64 transforms per channel ---- */
+    for (int t = tid; t < nthr; t += nt) {
+        const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
+        const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
+        float *b0 = sm->ch[c] + 41 * HEAAC_V_STRIDE;
+        if (plane == 0) {
+            heaac_imdct128_reg<HEAAC_MDCT_SYN>(
+                [&](int j) { return x[j * HEAAC_XS]; },
+                [&](int j, float v) { b0[j * 32 + i] = v; });
+        }
     }
     HEAAC_SYNC();
-    heaac_imdct_half_smem(sm->in, sm->in, sm->zr, sm->zi, 5, 64, T->tcos_syn, T->tsin_syn, T, tid, nt);
-    for (int w = tid; w < 32 * 64; w += nt) {                     /* aacsbr.c:1210-1213 */
-        int i = w >> 6, n = w & 63;
-        const float *b0 = sm->in + (2 * i) * 64, *b1 = b0 + 64;
-        float *v = sm->v + (31 - i) * 128;
-        v[n]       = -b0[63 - n] + b1[n];
-        v[127 - n] =  b0[63 - n] + b1[n];
+    /* ---- phase 1b + 2: im-plane transform, then v = (-b0 + b1, b0 + b1) ---- */
+    for (int t = tid; t < nthr; t += nt) {
+        const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
+        if (plane == 0) continue;
+        const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
+        const float *b0 = sm->ch[c] + 41 * HEAAC_V_STRIDE;
+        float b1[64];
+        heaac_imdct128_reg<HEAAC_MDCT_SYN>(
+            [&](int j) { float v = x[j * HEAAC_XS]; return (j & 1) ? -v : v; },     /* aacsbr.c:1205-1207 */
+            [&](int j, float v) { b1[j] = v; });
+        float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;
+        HEAAC_UNROLL
+        for (int n = 0; n < 64; n++) {
+            const float p = b0[(63 - n) * 32 + i], q = b1[n];
+            v[n]       = -p + q;
+            v[127 - n] =  p + q;
+        }
     }
     HEAAC_SYNC();
+    /* ---- phase 3: windowing, out[n] = sum_j v[off_j + n] w[64 j + n] (aacsbr.c:1215-1227) ---- */
     const int scale_and_bias = scale != 1.0f || bias != 0.0f;
     const int bias_mode = bias != 0.0f;
-    for (int w = tid; w < 32 * 64; w += nt) {                     /* aacsbr.c:1215-1227 */
-        int i = w >> 6, n = w & 63;
-        const float *v = sm->v + (31 - i) * 128 + n;
-        const float *win = T->qmf_us + n;
-        float acc = v[0] * win[0] + 0.0f;
-        acc = v[192]  * win[64]  + acc;
-        acc = v[256]  * win[128] + acc;
-        acc = v[448]  * win[192] + acc;
-        acc = v[512]  * win[256] + acc;
-        acc = v[704]  * win[320] + acc;
-        acc = v[768]  * win[384] + acc;
-        acc = v[960]  * win[448] + acc;
-        acc = v[1024] * win[512] + acc;
-        acc = v[1216] * win[576] + acc;
-        if (scale_and_bias) acc = acc * scale + bias;
-        if (pcm)     pcm[(size_t)w * pcm_stride] = heaac_to_s16(acc, bias_mode);
-        if (pcm_f32) pcm_f32[w] = acc;
+    for (int t = tid; t < nthr; t += nt) {
+        const int c = nout == 2 ? (t & 1) : 0, n = nout == 2 ? (t >> 1) : t;
+        float w[10];
+        HEAAC_UNROLL
+        for (int j = 0; j < 10; j++) w[j] = T->qmf_us[64 * j + n];
+        const float *vb = sm->ch[c] + n;
+        const int slot = c ? out_slot1 : out_slot0;
+        for (int i = 0; i < 32; i++) {
+            const float *v = vb + (31 - i) * HEAAC_V_STRIDE;
+            float acc = v[0] * w[0] + 0.0f;
+            HEAAC_UNROLL
+            for (int j = 1; j < 10; j++)
+                acc = v[j * HEAAC_V_STRIDE + ((j & 1) ? 64 : 0)] * w[j] + acc;
+            if (scale_and_bias) acc = acc * scale + bias;
+            const int o = i * 64 + n;
+            if (pcm)     pcm[(size_t)o * nout + slot] = heaac_to_s16(acc, bias_mode);
+            if (pcm_f32) pcm_f32[(size_t)slot * 2048 + o] = acc;
+        }
     }
-    for (int i = tid; i < 1152; i += nt) st->v[i] = sm->v[i];
+    for (int w = tid; w < nout * 1152; w += nt) {          /* newest 9 blocks become the next frame's history */
+        int c = w / 1152, r = w - c * 1152;
+        st[c].v[r] = sm->ch[c][(r >> 7) * HEAAC_V_STRIDE + (r & 127)];
+    }
     HEAAC_SYNC();
 }
 

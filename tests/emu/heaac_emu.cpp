@@ -58,7 +58,7 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
     c->synth = (HeaacSynthState *)calloc(S * c->g.nout, sizeof(HeaacSynthState));
     c->ps = (HeaacPsState *)calloc(S, sizeof(HeaacPsState));
     c->core_time = (float *)calloc(S * c->g.ncc * 1024, sizeof(float));
-    c->X = (float *)calloc(S * c->g.nout * 2 * 38 * 64, sizeof(float));
+    c->X = (float *)calloc(S * c->g.nout * HEAAC_X_FLOATS, sizeof(float));
     c->sm_core = (HeaacCoreSmem *)calloc(1, sizeof(HeaacCoreSmem));
     c->sm_sbr = (HeaacSbrSmem *)calloc(1, sizeof(HeaacSbrSmem));
     c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
@@ -107,21 +107,30 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             if (se == 0xff) continue;
             memset(c->sm_sbr, 0xA5, sizeof(HeaacSbrSmem));
             heaac_sbr_channel(c->sm_sbr, c->core_time + gc * 1024, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
-                              c->chan + gc, c->X + (s * g.nout + ch) * (2 * 38 * 64), 1 / qmf_scale, c->T, 0, 1);
+                              c->chan + gc, c->X + (s * g.nout + ch) * (HEAAC_X_FLOATS), 1 / qmf_scale, c->T, 0, 1);
         }
         if (g.ps)
             for (size_t s = 0; s < S; s++) {                      /* k_ps */
-                float *XL = c->X + s * 2 * (2 * 38 * 64), *XR = XL + 2 * 38 * 64;
+                float *XL = c->X + s * 2 * (HEAAC_X_FLOATS), *XR = XL + HEAAC_X_FLOATS;
                 const HeaacSbrElem *e = sb + s * g.nse;
                 memset(c->sm_ps, 0xA5, sizeof(HeaacPsSmem));
                 heaac_ps_stream(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0, 1);
             }
-        for (size_t go = 0; go < S * g.nout; go++) {              /* k_synth */
-            size_t s = go / g.nout; int ch = (int)(go - s * g.nout);
-            memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
-            heaac_synth_channel(c->sm_synth, c->X + go * (2 * 38 * 64), c->synth + go,
-                                pc ? pc + s * 2048 * g.nout + g.out_slot[ch] : nullptr, g.nout,
-                                pf ? pf + (s * g.nout + g.out_slot[ch]) * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0, 1);
+        for (size_t s = 0; s < S; s++) {                          /* k_synth: one CTA per (stream, SBR element) */
+            int o = 0;
+            for (int e = 0; e < g.n_elems; e++) {
+                int nch = g.elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+                if (g.elem_type[e] != HEAAC_TYPE_LFE) {
+                    int no = g.ps ? 2 : nch;
+                    size_t go = s * g.nout + o;
+                    memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
+                    heaac_synth_stream(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no,
+                                       g.out_slot[o], g.out_slot[o + (no > 1)],
+                                       pc ? pc + s * 2048 * g.nout : nullptr, pf ? pf + s * g.nout * 2048 : nullptr,
+                                       qmf_scale, g.add_bias, c->T, 0, 1);
+                }
+                o += nch;
+            }
         }
     }
     return 0;
@@ -133,7 +142,7 @@ extern "C" int heaac_emu_peek(EmuCtx *c, const char *name, void *dst, int cap)
 {
     const void *p = nullptr; size_t n = 0;
     size_t S = c->g.n_streams;
-    if (!strcmp(name, "X")) { p = c->X; n = S * c->g.nout * 2 * 38 * 64 * sizeof(float); }
+    if (!strcmp(name, "X")) { p = c->X; n = S * c->g.nout * HEAAC_X_FLOATS * sizeof(float); }
     else if (!strcmp(name, "core_time")) { p = c->core_time; n = S * c->g.ncc * 1024 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { p = c->chan; n = S * c->g.ncc * sizeof(HeaacChanState); }
     else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacSbrSmem); }
