@@ -32,7 +32,7 @@ struct HeaacContext {
     HeaacChanState *d_chan;          /* [S][ncc] */
     HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
     HeaacPsState *d_ps;              /* [S] (PS only) */
-    float *d_core_time;              /* [S][ncc][1024] (SBR only) */
+    float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
     float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
     float *s_coeffs; HeaacIcs *s_ics; HeaacTns *s_tns; HeaacSbrElem *s_sbr; HeaacPsFrame *s_ps;
@@ -63,21 +63,33 @@ static void prof_end(HeaacContext *c)
 /* ------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(HEAAC_THREADS)
 k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
-       const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *core_time,
+       const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
-    float *out = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));
+    float *x = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [288 history | 1024 new] */
+    float *out = x + 288;
     const int gc = blockIdx.x;                       /* global core channel = s * ncc + c */
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
+    HeaacChanState *st = chan + gc;
+    const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
+    if (ana)
+        for (int i = threadIdx.x; i < 288; i += blockDim.x) x[i] = st->ana_hist[i];
     heaac_core_channel(sm, coeffs + (size_t)gc * 1024, ics + gc, tns ? tns + gc : nullptr,
-                       chan + gc, out, bias, g.sr_index, T, threadIdx.x, blockDim.x);
-    if (g.sbr) {
-        float *dst = core_time + (size_t)gc * 1024;
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = out[i];
-    } else {
+                       st, out, bias, g.sr_index, T, threadIdx.x, blockDim.x);
+    if (ana) {
+        /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
+        const float ana_scale = 1 / (-1024.0f * g.sf_scale);                   /* aacsbr.c:1730 */
+        if (ana_scale != 1.0f) {
+            for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = out[i] * ana_scale;
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < 288; i += blockDim.x) st->ana_hist[i] = x[1024 + i];
+        float *tb = x + 1312;
+        heaac_qmf_analysis(x, tb, W + (size_t)gc * 2048, T, threadIdx.x, blockDim.x);
+    } else if (!g.sbr) {
         const int bias_mode = g.add_bias != 0.0f;
         if (pcm) {
             int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
@@ -91,20 +103,18 @@ k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)
-k_sbr(HeaacGeom g, const float *__restrict__ core_time, const HeaacSbrElem *__restrict__ sbr,
+k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__ sbr,
       HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HeaacSbrSmem *sm = reinterpret_cast<HeaacSbrSmem *>(smem_raw);
+    HeaacHfSmem *sm = reinterpret_cast<HeaacHfSmem *>(smem_raw);
     const int gc = blockIdx.x;
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
     if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
-    const float qmf_scale = -1024.0f * g.sf_scale;   /* aacsbr.c:1764 */
-    const float ana_scale = 1 / qmf_scale;           /* aacsbr.c:1730 */
     float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
-    heaac_sbr_channel(sm, core_time + (size_t)gc * 1024, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
-                      g.elem_is_cpe[c], chan + gc, Xc, ana_scale, T, threadIdx.x, blockDim.x);
+    heaac_hf_channel(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
+                     g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x, blockDim.x);
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)
@@ -203,7 +213,7 @@ static int init_state(HeaacContext *c)
     if (g->sbr) {
         CK(cudaMemsetAsync(c->d_synth, 0, (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState), c->stream));
         CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
-        CK(cudaMemsetAsync(c->d_core_time, 0, nch * 1024 * sizeof(float), c->stream));
+        CK(cudaMemsetAsync(c->d_W, 0, nch * 2048 * sizeof(float), c->stream));
     }
     if (g->ps) CK(cudaMemsetAsync(c->d_ps, 0, (size_t)g->n_streams * sizeof(HeaacPsState), c->stream));
     /* everything the reference initialises to non-zero (kx' = 32, e_a[1] = -1; aacsbr.c:128-137) lives in
@@ -279,7 +289,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
         CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
-        CKX(cudaMalloc(&c->d_core_time, S * g->ncc * 1024 * sizeof(float)));
+        CKX(cudaMalloc(&c->d_W, S * g->ncc * 2048 * sizeof(float)));
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
     CKX(cudaMalloc(&c->s_coeffs, T * S * g->ncc * 1024 * sizeof(float)));
@@ -290,8 +300,8 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     CKX(cudaMalloc(&c->s_pcm, T * S * g->out_len * g->nout * sizeof(int16_t)));
     if (cfg->want_float_out) CKX(cudaMalloc(&c->s_pcm_f32, T * S * g->out_len * g->nout * sizeof(float)));
 
-    c->smem_core = sizeof(HeaacCoreSmem) + 1024 * sizeof(float);
-    c->smem_sbr = sizeof(HeaacSbrSmem);
+    c->smem_core = sizeof(HeaacCoreSmem) + (g->sbr ? 1312 + 64 * 33 : 1312) * sizeof(float);
+    c->smem_sbr = sizeof(HeaacHfSmem);
     c->smem_ps = sizeof(HeaacPsSmem);
     c->smem_synth = sizeof(HeaacSynthSmem);
     CKX(cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_core));
@@ -311,7 +321,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_core_time); cudaFree(c->d_X);
+    cudaFree(c->d_W); cudaFree(c->d_X);
     cudaFree(c->s_coeffs); cudaFree(c->s_ics); cudaFree(c->s_tns); cudaFree(c->s_sbr); cudaFree(c->s_ps);
     cudaFree(c->s_pcm); cudaFree(c->s_pcm_f32);
     for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]);
@@ -351,14 +361,14 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
         float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
         prof_begin(c, HEAAC_K_CORE);
         k_core<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_core, c->stream>>>(
-            g, co, ic, tn, c->d_chan, c->d_core_time, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+            g, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
         prof_end(c);
         c->launches++;
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
             prof_begin(c, HEAAC_K_SBR);
             k_sbr<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_sbr, c->stream>>>(
-                g, c->d_core_time, sb, c->d_chan, c->d_X, c->d_tables);
+                g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables);
             prof_end(c);
             c->launches++;
             if (g.ps) {
@@ -509,7 +519,7 @@ extern "C" int heaac_b200_debug_read(HeaacContext *c, const char *name, void *ds
     const HeaacGeom *g = &c->geom;
     const void *src = nullptr; size_t avail = 0;
     if (!strcmp(name, "X") && c->d_X) { src = c->d_X; avail = (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float); }
-    else if (!strcmp(name, "core_time") && c->d_core_time) { src = c->d_core_time; avail = (size_t)g->n_streams * g->ncc * 1024 * sizeof(float); }
+    else if (!strcmp(name, "W") && c->d_W) { src = c->d_W; avail = (size_t)g->n_streams * g->ncc * 2048 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { src = c->d_chan; avail = (size_t)g->n_streams * g->ncc * sizeof(HeaacChanState); }
     else if (!strcmp(name, "synth_state") && c->d_synth) { src = c->d_synth; avail = (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState); }
     else if (!strcmp(name, "ps_state") && c->d_ps) { src = c->d_ps; avail = (size_t)g->n_streams * sizeof(HeaacPsState); }

@@ -78,8 +78,8 @@ struct HeaacChanState {
     int32_t prev_ws, prev_shape;    /* ics.window_sequence[1], ics.use_kb_window[1] */
     /* SBR (only touched when cfg.sbr) */
     float ana_hist[288];            /* analysis_filterbank_samples[0..287] */
-    float w_tail[8 * 32 * 2];       /* W[1][24..31][32][2] of the previous frame */
-    float y_tail[6 * 64 * 2];       /* Y[1][32..37][64][2] */
+    float w_tail[2 * 32 * 8];       /* W[1][24..31] of the previous frame, [plane][band][slot - 24] */
+    float y_tail[2 * 64 * 8];       /* Y[1][32..37], [plane][band][slot - 32] (6 of 8 slots used) */
     float g_hist[10 * 48];          /* g_temp rows 32..41 (the only rows ever read as history) */
     float q_hist[10 * 48];          /* q_temp rows 32..41 */
     float bw_array[8];

@@ -272,479 +272,7 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
     HEAAC_SYNC();
 }
 
-/* ====================================================================================
- * SBR, one channel-frame: QMF analysis .. X generation
- * ================================================================================== */
-struct HeaacSbrSmem {
-    float x[1312];                  /* analysis input window: 288 history + 1024 new */
-    float fr[32 * 32], fi[32 * 32]; /* 32 slots x 32-point complex FFT work area */
-    float t[32 * 64];               /* folded + shuffled analysis inputs, then imdct outputs */
-    float xlow[32][40][2];          /* X_low */
-    float xhigh[48][40][2];         /* X_high rows kx .. kx+m-1 */
-    float alpha0[32][2], alpha1[32][2];
-    float env[5][48];               /* dequantised env_facs[1..5] */
-    float noise[2][8];              /* dequantised noise_facs[1..2] */
-    float e_orig[5][48], q_map[5][48], e_curr[5][48], gain[5][48], q_m[5][48], s_m[5][48];
-    float bw[8];
-    uint8_t s_idx[6][48];           /* s_indexmapped[0..5] */
-    uint8_t s_map[5][48];
-    int8_t  env_of_slot[48];        /* envelope index covering QMF slot i (or -1) */
-    float   ynew[6 * 64 * 2];       /* Y[1][32..37] computed this frame */
-    uint8_t ynew_valid[6 * 64];
-    HeaacSbrElem p;                 /* this frame's parameters */
-};
-
-/* exact 2^(k/2): exp2f of a multiple of 0.5 equals ldexp(1 or sqrt2, n) in glibc too */
-HEAAC_DEV float heaac_exp2_half(float x)
-{
-    float fl = floorf(x);
-    int n = (int)fl;
-    float m = (x != fl) ? 1.41421356237309504880f : 1.0f;
-#ifdef HEAAC_HOST_EMU
-    return ldexpf(m, n);
-#else
-    return ldexpf(m, n);
-#endif
-}
-
-HEAAC_DEV void heaac_sbr_dequant(HeaacSbrSmem *sm, int ch, int is_cpe, int tid, int nt)
-{
-    const HeaacSbrElem *p = &sm->p;
-    const HeaacSbrChan *pc = &p->ch[ch];
-    if (is_cpe && p->bs_coupling) {
-        const HeaacSbrChan *p0 = &p->ch[0], *p1 = &p->ch[1];
-        float alpha      = p0->bs_amp_res ?  1.0f :  0.5f;
-        float pan_offset = p0->bs_amp_res ? 12.0f : 24.0f;
-        for (int w = tid; w < p0->bs_num_env * 48; w += nt) {
-            int e = w / 48, k = w - e * 48;
-            if (k >= p->n[p0->bs_freq_res[e + 1]]) continue;
-            float t1 = heaac_exp2_half((float)p0->env_q[e][k] * alpha + 7.0f);
-            float t2 = heaac_exp2_half((pan_offset - (float)p1->env_q[e][k]) * alpha);
-            float fac = heaac_fdiv(t1, 1.0f + t2);
-            sm->env[e][k] = ch ? fac * t2 : fac;
-        }
-        for (int w = tid; w < p0->bs_num_noise * 8; w += nt) {
-            int e = w >> 3, k = w & 7;
-            if (k >= p->n_q) continue;
-            float t1 = heaac_exp2_half(6.0f - (float)p0->noise_q[e][k] + 1);
-            float t2 = heaac_exp2_half(12 - (float)p1->noise_q[e][k]);
-            float fac = heaac_fdiv(t1, 1.0f + t2);
-            sm->noise[e][k] = ch ? fac * t2 : fac;
-        }
-    } else {
-        float alpha = pc->bs_amp_res ? 1.0f : 0.5f;
-        for (int w = tid; w < pc->bs_num_env * 48; w += nt) {
-            int e = w / 48, k = w - e * 48;
-            if (k >= p->n[pc->bs_freq_res[e + 1]]) continue;
-            sm->env[e][k] = heaac_exp2_half(alpha * (float)pc->env_q[e][k] + 6.0f);
-        }
-        for (int w = tid; w < pc->bs_num_noise * 8; w += nt) {
-            int e = w >> 3, k = w & 7;
-            if (k >= p->n_q) continue;
-            sm->noise[e][k] = heaac_exp2_half(6.0f - (float)pc->noise_q[e][k]);
-        }
-    }
-}
-
-struct HeaacYCtx {
-    int h_SL, i_lo, i_hi, t_old2, kx, m_max, reset, e_a0, e_a1;
-    uint32_t noise0, sine0;
-};
-
-/* Y[1][i][kx + m] of sbr_hf_assemble (aacsbr.c:1649-1710) for one (slot, band).
- * g_temp/q_temp row r (= i + h_SL - j) holds gain[env(r - h_SL)] when slot r - h_SL belongs to this
- * frame, otherwise one of the four history rows (aacsbr.c:1632-1640). */
-HEAAC_DEV void heaac_sbr_y(const HeaacSbrSmem *sm, const HeaacChanState *st, const HeaacYCtx *y,
-                           const HeaacDevTables *HEAAC_RESTRICT T, int i, int m, float *yre_o, float *yim_o)
-{
-    const int e = sm->env_of_slot[i];
-    const int at_border = (e == y->e_a0 || e == y->e_a1);
-    float g_filt, q_filt;
-    if (y->h_SL && !at_border) {
-        g_filt = 0.0f; q_filt = 0.0f;
-        for (int j = 0; j <= 4; j++) {
-            int src = i - j;
-            float gv, qv;
-            if (src >= y->i_lo) {
-                int es = sm->env_of_slot[src];
-                gv = sm->gain[es][m]; qv = sm->q_m[es][m];
-            } else if (y->reset) {
-                gv = sm->gain[0][m]; qv = sm->q_m[0][m];
-            } else {
-                int hr = y->t_old2 + (src + 4 - y->i_lo) - 32;     /* history row relative to row 32 */
-                gv = (hr >= 0 && hr < 10) ? st->g_hist[hr * 48 + m] : 0.0f;
-                qv = (hr >= 0 && hr < 10) ? st->q_hist[hr * 48 + m] : 0.0f;
-            }
-            g_filt = heaac_fadd(g_filt, heaac_fmul(gv, heaac_h_smooth[j]));
-            q_filt = heaac_fadd(q_filt, heaac_fmul(qv, heaac_h_smooth[j]));
-        }
-    } else {
-        g_filt = sm->gain[e][m];
-        q_filt = sm->q_m[e][m];
-    }
-    float yre = heaac_fmul(sm->xhigh[m][i + 2][0], g_filt);
-    float yim = heaac_fmul(sm->xhigh[m][i + 2][1], g_filt);
-    const int indexsine = (int)((y->sine0 + (uint32_t)(i - y->i_lo)) & 3);
-    const int phi_sign = (1 - 2 * (y->kx & 1)) * ((m & 1) ? -1 : 1);
-    const int phi_re = indexsine == 0 ? 1 : indexsine == 2 ? -1 : 0;
-    const int phi_im = indexsine == 1 ? 1 : indexsine == 3 ? -1 : 0;
-    const float s = sm->s_m[e][m];
-    if (!at_border && !s) {
-        uint32_t idx = (y->noise0 + (uint32_t)(i - y->i_lo) * (uint32_t)y->m_max + (uint32_t)m + 1u) & 0x1ff;
-        yre = heaac_fadd(yre, heaac_fmul(q_filt, T->noise[2 * idx]));
-        yim = heaac_fadd(yim, heaac_fmul(q_filt, T->noise[2 * idx + 1]));
-    } else {
-        yre = heaac_fadd(yre, heaac_fmul(s, (float)phi_re));
-        yim = heaac_fadd(yim, heaac_fmul(s, (float)(phi_im * phi_sign)));
-    }
-    *yre_o = yre; *yim_o = yim;
-}
-
-/* core_time: 1024 floats (global) of this channel's IMDCT output.
- * X_out   : this channel's X[2][64][HEAAC_XS] (band-major) buffer in global scratch. */
-HEAAC_DEV void heaac_sbr_channel(HeaacSbrSmem *sm, const float *HEAAC_RESTRICT core_time,
-                                 const HeaacSbrElem *HEAAC_RESTRICT elem, int ch, int is_cpe,
-                                 HeaacChanState *st, float *X_out, float ana_scale,
-                                 const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
-{
-    /* ---- stage parameters and the analysis input window ---- */
-    {
-        const uint32_t *src = (const uint32_t *)elem;
-        uint32_t *dst = (uint32_t *)&sm->p;
-        for (int i = tid; i < (int)(sizeof(HeaacSbrElem) / 4); i += nt) dst[i] = src[i];
-    }
-    for (int i = tid; i < 288; i += nt) sm->x[i] = st->ana_hist[i];
-    for (int i = tid; i < 1024; i += nt) {
-        float v = core_time[i];
-        sm->x[288 + i] = ana_scale != 1.0f ? v * ana_scale : v;
-    }
-    HEAAC_SYNC();
-    const HeaacSbrElem *p = &sm->p;
-    const HeaacSbrChan *pc = &p->ch[ch];
-    const int kx = p->kx[1], kx0 = p->kx[0], m_max = p->m[1], m0 = p->m[0];
-    const int nenv = pc->bs_num_env;
-    for (int i = tid; i < 288; i += nt) st->ana_hist[i] = sm->x[1024 + i];
-
-    /* ---- QMF analysis, aacsbr.c:1147-1168: window + 5-way fold + shuffle ---- */
-    for (int w = tid; w < 32 * 64; w += nt) {
-        int i = w >> 6, k = w & 63;
-        const float *x = sm->x + 32 * i;
-        float f = T->qmf_ds[k] * x[319 - k];
-        f = f + T->qmf_ds[k + 64]  * x[319 - k - 64];
-        f = f + T->qmf_ds[k + 128] * x[319 - k - 128];
-        f = f + T->qmf_ds[k + 192] * x[319 - k - 192];
-        f = f + T->qmf_ds[k + 256] * x[319 - k - 256];
-        /* t[0] = u[0]; t[2k-1] = u[k], t[2k] = -u[64-k] (k = 1..31); t[63] = u[32] */
-        int pos; float val = f;
-        if (k == 0) pos = 0;
-        else if (k < 32) pos = 2 * k - 1;
-        else if (k == 32) pos = 63;
-        else { pos = 2 * (64 - k); val = -f; }
-        sm->t[i * 64 + pos] = val;
-    }
-    HEAAC_SYNC();
-    /* 32 half-IMDCTs of N = 128, scale -2 (mdct_ana, aacsbr.c:135) */
-    heaac_imdct_half_smem(sm->t, sm->t, sm->fr, sm->fi, 5, 32, T->tcos_ana, T->tsin_ana, T, tid, nt);
-
-    /* ---- sbr_lf_gen: X_low[k][i] from W (this frame, i >= 8) and the saved W tail (i < 8) ---- */
-    for (int w = tid; w < 32 * 40; w += nt) {
-        int k = w & 31, i = w >> 5;
-        float re = 0.0f, im = 0.0f;
-        if (i >= 8) {
-            if (k < kx) { re = -sm->t[(i - 8) * 64 + 63 - k]; im = sm->t[(i - 8) * 64 + k]; }
-        } else if (k < kx0) {
-            re = st->w_tail[(i * 32 + k) * 2]; im = st->w_tail[(i * 32 + k) * 2 + 1];
-        }
-        sm->xlow[k][i][0] = re; sm->xlow[k][i][1] = im;
-    }
-    HEAAC_SYNC();
-    for (int w = tid; w < 8 * 32; w += nt) {           /* new W tail: slots 24..31, all 32 bands */
-        int i = w >> 5, k = w & 31;
-        st->w_tail[(i * 32 + k) * 2]     = -sm->t[(24 + i) * 64 + 63 - k];
-        st->w_tail[(i * 32 + k) * 2 + 1] =  sm->t[(24 + i) * 64 + k];
-    }
-
-    if (p->start) {
-        /* ---- inverse filter (one band per work item) + chirp + dequant ---- */
-        for (int k = tid; k < p->k0; k += nt) {
-            const float (*x)[2] = sm->xlow[k];
-            float rs0 = 0.0f, rs1 = 0.0f, is1 = 0.0f, rs2 = 0.0f, is2 = 0.0f;
-            for (int i = 1; i < 38; i++) {
-                rs0 = heaac_fadd(rs0, heaac_fadd(heaac_fmul(x[i][0], x[i][0]), heaac_fmul(x[i][1], x[i][1])));
-                rs1 = heaac_fadd(rs1, heaac_fadd(heaac_fmul(x[i][0], x[i + 1][0]), heaac_fmul(x[i][1], x[i + 1][1])));
-                is1 = heaac_fadd(is1, heaac_fsub(heaac_fmul(x[i][0], x[i + 1][1]), heaac_fmul(x[i][1], x[i + 1][0])));
-                rs2 = heaac_fadd(rs2, heaac_fadd(heaac_fmul(x[i][0], x[i + 2][0]), heaac_fmul(x[i][1], x[i + 2][1])));
-                is2 = heaac_fadd(is2, heaac_fsub(heaac_fmul(x[i][0], x[i + 2][1]), heaac_fmul(x[i][1], x[i + 2][0])));
-            }
-            /* phi[a][b][c] as in autocorrelate(), aacsbr.c:1242-1253 */
-            float phi210 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(x[0][0], x[0][0])), heaac_fmul(x[0][1], x[0][1]));
-            float phi100 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(x[38][0], x[38][0])), heaac_fmul(x[38][1], x[38][1]));
-            float phi110 = heaac_fadd(heaac_fadd(rs1, heaac_fmul(x[0][0], x[1][0])), heaac_fmul(x[0][1], x[1][1]));
-            float phi111 = heaac_fsub(heaac_fadd(is1, heaac_fmul(x[0][0], x[1][1])), heaac_fmul(x[0][1], x[1][0]));
-            float phi000 = heaac_fadd(heaac_fadd(rs1, heaac_fmul(x[38][0], x[39][0])), heaac_fmul(x[38][1], x[39][1]));
-            float phi001 = heaac_fsub(heaac_fadd(is1, heaac_fmul(x[38][0], x[39][1])), heaac_fmul(x[38][1], x[39][0]));
-            float phi010 = heaac_fadd(heaac_fadd(rs2, heaac_fmul(x[0][0], x[2][0])), heaac_fmul(x[0][1], x[2][1]));
-            float phi011 = heaac_fsub(heaac_fadd(is2, heaac_fmul(x[0][0], x[2][1])), heaac_fmul(x[0][1], x[2][0]));
-            float dk = heaac_fsub(heaac_fmul(phi210, phi100),
-                                  heaac_fdiv(heaac_fadd(heaac_fmul(phi110, phi110), heaac_fmul(phi111, phi111)), 1.000001f));
-            float a1r, a1i, a0r, a0i;
-            if (!dk) {
-                a1r = a1i = 0.0f;
-            } else {
-                float tr = heaac_fsub(heaac_fsub(heaac_fmul(phi000, phi110), heaac_fmul(phi001, phi111)), heaac_fmul(phi010, phi100));
-                float ti = heaac_fsub(heaac_fadd(heaac_fmul(phi000, phi111), heaac_fmul(phi001, phi110)), heaac_fmul(phi011, phi100));
-                a1r = heaac_fdiv(tr, dk);
-                a1i = heaac_fdiv(ti, dk);
-            }
-            if (!phi100) {
-                a0r = a0i = 0.0f;
-            } else {
-                float tr = heaac_fadd(heaac_fadd(phi000, heaac_fmul(a1r, phi110)), heaac_fmul(a1i, phi111));
-                float ti = heaac_fsub(heaac_fadd(phi001, heaac_fmul(a1i, phi110)), heaac_fmul(a1r, phi111));
-                a0r = heaac_fdiv(-tr, phi100);
-                a0i = heaac_fdiv(-ti, phi100);
-            }
-            if (heaac_fadd(heaac_fmul(a1r, a1r), heaac_fmul(a1i, a1i)) >= 16.0f ||
-                heaac_fadd(heaac_fmul(a0r, a0r), heaac_fmul(a0i, a0i)) >= 16.0f)
-                a1r = a1i = a0r = a0i = 0.0f;
-            sm->alpha0[k][0] = a0r; sm->alpha0[k][1] = a0i;
-            sm->alpha1[k][0] = a1r; sm->alpha1[k][1] = a1i;
-        }
-        for (int i = tid; i < p->n_q; i += nt) {        /* sbr_chirp */
-            float old = st->bw_array[i], nb;
-            int m0_ = pc->bs_invf_mode[0][i], m1_ = pc->bs_invf_mode[1][i];
-            if (m0_ + m1_ == 1) nb = 0.6f;
-            else nb = m0_ == 0 ? 0.0f : m0_ == 1 ? 0.75f : m0_ == 2 ? 0.9f : 0.98f;
-            if (nb < old) nb = heaac_fadd(heaac_fmul(0.75f, nb), heaac_fmul(0.25f, old));
-            else          nb = heaac_fadd(heaac_fmul(0.90625f, nb), heaac_fmul(0.09375f, old));
-            nb = nb < 0.015625f ? 0.0f : nb;
-            sm->bw[i] = nb;
-            st->bw_array[i] = nb;
-        }
-        heaac_sbr_dequant(sm, ch, is_cpe, tid, nt);
-        for (int i = tid; i < 48; i += nt) {
-            int e = -1;
-            for (int q = 0; q < nenv; q++)
-                if (i >= 2 * pc->t_env[q] && i < 2 * pc->t_env[q + 1]) e = q;
-            sm->env_of_slot[i] = (int8_t)e;
-        }
-        HEAAC_SYNC();
-
-        /* ---- sbr_hf_gen: one (target band, slot) per work item ---- */
-        {
-            const int i_lo = 2 * pc->t_env[0], i_hi = 2 * pc->t_env[nenv];
-            for (int w = tid; w < m_max * 40; w += nt) {
-                int m = w / 40, d = w - m * 40;           /* d = slot index inside X_high (i + 2) */
-                int k = kx + m;
-                /* which patch does band k belong to? */
-                int acc = kx, q = -1;
-                for (int j = 0; j < p->num_patches; j++) {
-                    int nsb = p->patch_num_subbands[j];
-                    if (k < acc + nsb) { q = p->patch_start_subband[j] + (k - acc); break; }
-                    acc += nsb;
-                }
-                int i = d - 2;
-                if (q < 0) {                              /* beyond the last patch: memset(X_high + k, 0) */
-                    sm->xhigh[m][d][0] = 0.0f; sm->xhigh[m][d][1] = 0.0f;
-                    continue;
-                }
-                if (i < i_lo || i >= i_hi) continue;      /* the reference leaves these untouched (never read) */
-                int g = 0;
-                while (g < p->n_q && k >= p->f_tablenoise[g + 1]) g++;
-                float bw = sm->bw[g];
-                float a0 = sm->alpha1[q][0] * bw * bw, a1 = sm->alpha1[q][1] * bw * bw;
-                float a2 = sm->alpha0[q][0] * bw,      a3 = sm->alpha0[q][1] * bw;
-                const float (*xl)[2] = sm->xlow[q];
-                sm->xhigh[m][d][0] = xl[d - 2][0] * a0 - xl[d - 2][1] * a1 + xl[d - 1][0] * a2 - xl[d - 1][1] * a3 + xl[d][0];
-                sm->xhigh[m][d][1] = xl[d - 2][1] * a0 + xl[d - 2][0] * a1 + xl[d - 1][1] * a2 + xl[d - 1][0] * a3 + xl[d][1];
-            }
-        }
-        /* ---- sbr_mapping ---- */
-        for (int w = tid; w < 6 * 48; w += nt) {
-            int e = w / 48, m = w - e * 48;
-            sm->s_idx[e][m] = e == 0 ? st->s_index0[m] : 0;
-        }
-        HEAAC_SYNC();
-        for (int w = tid; w < nenv * 48; w += nt) {
-            int e = w / 48, m = w - e * 48;
-            if (m >= m_max) continue;
-            int band = kx + m;
-            int fr = pc->bs_freq_res[e + 1];
-            const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
-            int i = 0;
-            while (i + 1 < p->n[fr] && band >= tab[i + 1]) i++;
-            sm->e_orig[e][m] = sm->env[e][i];
-            int kq = (pc->bs_num_noise > 1) && (pc->t_env[e] >= pc->t_q[1]);
-            int g = 0;
-            while (g + 1 < p->n_q && band >= p->f_tablenoise[g + 1]) g++;
-            sm->q_map[e][m] = sm->noise[kq][g];
-        }
-        if (pc->bs_add_harmonic_flag) {
-            for (int w = tid; w < nenv * 48; w += nt) {
-                int e = w / 48, i = w - e * 48;
-                if (i >= p->n[1]) continue;
-                int mid = ((int)p->f_tablehigh[i] + (int)p->f_tablehigh[i + 1]) >> 1;
-                sm->s_idx[e + 1][mid - kx] = pc->bs_add_harmonic[i] *
-                    (e >= pc->e_a[1] || sm->s_idx[0][mid - kx] == 1);
-            }
-        }
-        HEAAC_SYNC();
-        for (int w = tid; w < nenv * 48; w += nt) {
-            int e = w / 48, m = w - e * 48;
-            if (m >= m_max) continue;
-            int band = kx + m;
-            int fr = pc->bs_freq_res[e + 1];
-            const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
-            int i = 0;
-            while (i + 1 < p->n[fr] && band >= tab[i + 1]) i++;
-            int present = 0;
-            for (int mm = tab[i]; mm < tab[i + 1]; mm++)
-                if (sm->s_idx[e + 1][mm - kx]) { present = 1; break; }
-            sm->s_map[e][m] = (uint8_t)present;
-        }
-        /* ---- sbr_env_estimate ---- */
-        for (int w = tid; w < nenv * 48; w += nt) {
-            int e = w / 48, m = w - e * 48;
-            if (m >= m_max) continue;
-            int ilb = pc->t_env[e] * 2 + 2, iub = pc->t_env[e + 1] * 2 + 2;
-            if (p->bs_interpol_freq) {
-                float recip = heaac_fdiv(0.5f, (float)(pc->t_env[e + 1] - pc->t_env[e]));
-                float sum = 0.0f;
-                for (int i = ilb; i < iub; i++)
-                    sum = heaac_fadd(sum, heaac_fadd(heaac_fmul(sm->xhigh[m][i][0], sm->xhigh[m][i][0]),
-                                                     heaac_fmul(sm->xhigh[m][i][1], sm->xhigh[m][i][1])));
-                sm->e_curr[e][m] = heaac_fmul(sum, recip);
-            } else {
-                int band = kx + m;
-                int fr = pc->bs_freq_res[e + 1];
-                const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
-                int b = 0;
-                while (b + 1 < p->n[fr] && band >= tab[b + 1]) b++;
-                if (band != tab[b]) continue;            /* first band of the group does the whole group */
-                int env_size = 2 * (pc->t_env[e + 1] - pc->t_env[e]);
-                int den = env_size * (tab[b + 1] - tab[b]);
-                float sum = 0.0f;
-                for (int k = tab[b]; k < tab[b + 1]; k++)
-                    for (int i = ilb; i < iub; i++)
-                        sum = heaac_fadd(sum, heaac_fadd(heaac_fmul(sm->xhigh[k - kx][i][0], sm->xhigh[k - kx][i][0]),
-                                                         heaac_fmul(sm->xhigh[k - kx][i][1], sm->xhigh[k - kx][i][1])));
-                sum = heaac_fdiv(sum, (float)den);
-                for (int k = tab[b]; k < tab[b + 1]; k++) sm->e_curr[e][k - kx] = sum;
-            }
-        }
-        HEAAC_SYNC();
-        /* ---- sbr_gain_calc: one (envelope, limiter band) per work item ---- */
-        for (int w = tid; w < nenv * p->n_lim; w += nt) {
-            int e = w / p->n_lim, k = w - e * p->n_lim;
-            int delta = !((e == pc->e_a[1]) || (e == pc->e_a[0]));
-            int lo = p->f_tablelim[k] - kx, hi = p->f_tablelim[k + 1] - kx;
-            const float limgain = heaac_limgain[p->bs_limiter_gains & 3];
-            float sum0 = 0.0f, sum1 = 0.0f;
-            for (int m = lo; m < hi; m++) {
-                float eo = sm->e_orig[e][m], qm = sm->q_map[e][m], ec = sm->e_curr[e][m];
-                float temp = heaac_fdiv(eo, heaac_fadd(1.0f, qm));
-                sm->q_m[e][m] = heaac_fsqrt(heaac_fmul(temp, qm));
-                sm->s_m[e][m] = heaac_fsqrt(heaac_fmul(temp, (float)sm->s_idx[e + 1][m]));
-                if (!sm->s_map[e][m])
-                    sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(eo, heaac_fmul(heaac_fadd(1.0f, ec),
-                                                 heaac_fadd(1.0f, heaac_fmul(qm, (float)delta)))));
-                else
-                    sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(heaac_fmul(eo, qm),
-                                                 heaac_fmul(heaac_fadd(1.0f, ec), heaac_fadd(1.0f, qm))));
-            }
-            for (int m = lo; m < hi; m++) { sum0 = heaac_fadd(sum0, sm->e_orig[e][m]); sum1 = heaac_fadd(sum1, sm->e_curr[e][m]); }
-            float gain_max = heaac_fmul(limgain, heaac_fsqrt(heaac_fdiv(heaac_fadd(1.1920928955078125e-07f, sum0),
-                                                                       heaac_fadd(1.1920928955078125e-07f, sum1))));
-            gain_max = HEAAC_MIN(100000.0f, gain_max);
-            for (int m = lo; m < hi; m++) {
-                float q_m_max = heaac_fdiv(heaac_fmul(sm->q_m[e][m], gain_max), sm->gain[e][m]);
-                sm->q_m[e][m]  = HEAAC_MIN(sm->q_m[e][m], q_m_max);
-                sm->gain[e][m] = HEAAC_MIN(sm->gain[e][m], gain_max);
-            }
-            sum0 = sum1 = 0.0f;
-            for (int m = lo; m < hi; m++) {
-                float g = sm->gain[e][m], s = sm->s_m[e][m], q = sm->q_m[e][m];
-                sum0 = heaac_fadd(sum0, sm->e_orig[e][m]);
-                float t3 = heaac_fmul(heaac_fmul((float)(delta && !s), q), q);
-                float acc = heaac_fadd(heaac_fadd(heaac_fmul(heaac_fmul(sm->e_curr[e][m], g), g), heaac_fmul(s, s)), t3);
-                sum1 = heaac_fadd(sum1, acc);
-            }
-            float gain_boost = heaac_fsqrt(heaac_fdiv(heaac_fadd(1.1920928955078125e-07f, sum0),
-                                                      heaac_fadd(1.1920928955078125e-07f, sum1)));
-            /* FFMIN(1.584893192 (double), gain_boost) then narrowed to float */
-            gain_boost = (1.584893192 > (double)gain_boost) ? gain_boost : (float)1.584893192;
-            for (int m = lo; m < hi; m++) {
-                sm->gain[e][m] = heaac_fmul(sm->gain[e][m], gain_boost);
-                sm->q_m[e][m]  = heaac_fmul(sm->q_m[e][m], gain_boost);
-                sm->s_m[e][m]  = heaac_fmul(sm->s_m[e][m], gain_boost);
-            }
-        }
-        HEAAC_SYNC();
-    }
-
-    /* ---- sbr_hf_assemble fused with sbr_x_gen: write X[re/im][slot][band] ---- */
-    {
-        HeaacYCtx y;
-        y.h_SL = 4 * !p->bs_smoothing_mode;
-        y.i_lo = p->start ? 2 * pc->t_env[0] : 0;
-        y.i_hi = p->start ? 2 * pc->t_env[nenv] : 0;
-        y.t_old2 = 2 * pc->t_env_num_env_old;
-        y.noise0 = p->reset ? 0u : st->f_indexnoise;
-        y.sine0 = st->f_indexsine;
-        y.kx = kx; y.m_max = m_max; y.reset = p->reset;
-        y.e_a0 = pc->e_a[0]; y.e_a1 = pc->e_a[1];
-        const int i_Temp = HEAAC_MAX(y.t_old2 - 32, 0);
-        float *Xre = X_out, *Xim = X_out + HEAAC_X_PLANE;
-        for (int w = tid; w < 64 * HEAAC_XS; w += nt) {
-            int k = w / HEAAC_XS, i = w - k * HEAAC_XS;      /* slot fastest: coalesced band-major store */
-            if (i >= 38) continue;
-            float re = 0.0f, im = 0.0f;
-            const int in_hf = p->start && i >= y.i_lo && i < y.i_hi && k >= kx && k < kx + m_max;
-            float yre = 0.0f, yim = 0.0f;
-            if (in_hf) heaac_sbr_y(sm, st, &y, T, i, k - kx, &yre, &yim);
-            /* sbr_x_gen, aacsbr.c:1412-1446 */
-            if (i < i_Temp) {
-                if (k < kx0) { re = sm->xlow[k][i + 2][0]; im = sm->xlow[k][i + 2][1]; }
-                else if (k < kx0 + m0) { re = st->y_tail[(i * 64 + k) * 2]; im = st->y_tail[(i * 64 + k) * 2 + 1]; }
-            } else {
-                if (k < kx) { re = sm->xlow[k][i + 2][0]; im = sm->xlow[k][i + 2][1]; }
-                else if (k < kx + m_max && i < 32 && in_hf) { re = yre; im = yim; }
-                /* (slots of Y[1] the envelope grid does not cover would hold stale data of an older
-                 *  frame in the reference; a valid grid always covers [i_Temp, 32)) */
-            }
-            Xre[w] = re; Xim[w] = im;
-            if (i >= 32) {                                /* Y[1][32..37]: next frame's Y[0] tail */
-                sm->ynew[((i - 32) * 64 + k) * 2]     = yre;
-                sm->ynew[((i - 32) * 64 + k) * 2 + 1] = yim;
-                sm->ynew_valid[(i - 32) * 64 + k] = (uint8_t)in_hf;
-            }
-        }
-        HEAAC_SYNC();      /* every read of the old y_tail / g_hist / q_hist is done */
-        for (int w = tid; w < 6 * 64; w += nt)
-            if (sm->ynew_valid[w]) {
-                st->y_tail[2 * w]     = sm->ynew[2 * w];
-                st->y_tail[2 * w + 1] = sm->ynew[2 * w + 1];
-            }
-        if (p->start) {
-            /* g_temp / q_temp rows 32..41 for the next frame, aacsbr.c:1642-1647 */
-            for (int w = tid; w < 10 * 48; w += nt) {
-                int r = 32 + w / 48, m = w % 48;
-                int src = r - y.h_SL;
-                if (m < m_max && src >= y.i_lo && src < y.i_hi) {
-                    int es = sm->env_of_slot[src];
-                    st->g_hist[w] = sm->gain[es][m];
-                    st->q_hist[w] = sm->q_m[es][m];
-                }
-            }
-            for (int m = tid; m < 48; m += nt) st->s_index0[m] = sm->s_idx[nenv][m];
-            if (tid == 0) {
-                st->f_indexnoise = (y.noise0 + (uint32_t)(y.i_hi - y.i_lo) * (uint32_t)m_max) & 0x1ff;
-                st->f_indexsine = (y.sine0 + (uint32_t)(y.i_hi - y.i_lo)) & 3;
-            }
-        }
-        HEAAC_SYNC();
-    }
-}
+#include "heaac_sbr.cuh"
 
 /* ====================================================================================
  * Parametric Stereo for one stream-frame (ff_ps_apply, aacps.c:973-992)

@@ -20,8 +20,8 @@ struct EmuCtx {
     HeaacConfig cfg; HeaacGeom g;
     HeaacDevTables *T;
     HeaacChanState *chan; HeaacSynthState *synth; HeaacPsState *ps;
-    float *core_time, *X;
-    HeaacCoreSmem *sm_core; HeaacSbrSmem *sm_sbr; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
+    float *W, *X;
+    HeaacCoreSmem *sm_core; HeaacHfSmem *sm_sbr; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
 };
 
 static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
@@ -57,10 +57,10 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
     c->chan = (HeaacChanState *)calloc(S * c->g.ncc, sizeof(HeaacChanState));
     c->synth = (HeaacSynthState *)calloc(S * c->g.nout, sizeof(HeaacSynthState));
     c->ps = (HeaacPsState *)calloc(S, sizeof(HeaacPsState));
-    c->core_time = (float *)calloc(S * c->g.ncc * 1024, sizeof(float));
+    c->W = (float *)calloc(S * c->g.ncc * 2048, sizeof(float));
     c->X = (float *)calloc(S * c->g.nout * HEAAC_X_FLOATS, sizeof(float));
     c->sm_core = (HeaacCoreSmem *)calloc(1, sizeof(HeaacCoreSmem));
-    c->sm_sbr = (HeaacSbrSmem *)calloc(1, sizeof(HeaacSbrSmem));
+    c->sm_sbr = (HeaacHfSmem *)calloc(1, sizeof(HeaacHfSmem));
     c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
     c->sm_synth = (HeaacSynthSmem *)calloc(1, sizeof(HeaacSynthSmem));
     return c;
@@ -69,7 +69,7 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
 extern "C" void heaac_emu_destroy(EmuCtx *c)
 {
     if (!c) return;
-    free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->core_time); free(c->X);
+    free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->W); free(c->X);
     free(c->sm_core); free(c->sm_sbr); free(c->sm_ps); free(c->sm_synth); free(c);
 }
 
@@ -87,15 +87,24 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
         size_t pcm_frame = S * g.out_len * g.nout;
         int16_t *pc = b->pcm ? b->pcm + (size_t)f * pcm_frame : nullptr;
         float *pf = b->pcm_f32 ? b->pcm_f32 + (size_t)f * pcm_frame : nullptr;
-        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core */
+        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core (+ QMF analysis) */
             size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
-            float out[1024];
+            static float x[1312 + 64 * 33];
+            float *out = x + 288;
             float bias = g.sbr ? 0.0f : g.add_bias;
+            HeaacChanState *st = c->chan + gc;
+            bool ana = g.sbr && g.ch_sbr_elem[ch] != 0xff;
             memset(c->sm_core, 0xA5, sizeof(HeaacCoreSmem));      /* poison "shared memory" */
-            heaac_core_channel(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, c->chan + gc, out, bias,
+            memset(x, 0xA5, sizeof(x));
+            if (ana) memcpy(x, st->ana_hist, 288 * sizeof(float));
+            heaac_core_channel(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
                                g.sr_index, c->T, 0, 1);
-            if (g.sbr) memcpy(c->core_time + gc * 1024, out, sizeof(out));
-            else for (int i = 0; i < 1024; i++) {
+            if (ana) {
+                const float ana_scale = 1 / qmf_scale;
+                if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
+                memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
+                heaac_qmf_analysis(x, x + 1312, c->W + gc * 2048, c->T, 0, 1);
+            } else if (!g.sbr) for (int i = 0; i < 1024; i++) {
                 if (pc) pc[(s * 1024 + i) * g.nout + g.out_slot[ch]] = heaac_to_s16(out[i], g.add_bias != 0.0f);
                 if (pf) pf[(s * g.nout + g.out_slot[ch]) * 1024 + i] = out[i];
             }
@@ -105,9 +114,9 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
             int se = g.ch_sbr_elem[ch];
             if (se == 0xff) continue;
-            memset(c->sm_sbr, 0xA5, sizeof(HeaacSbrSmem));
-            heaac_sbr_channel(c->sm_sbr, c->core_time + gc * 1024, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
-                              c->chan + gc, c->X + (s * g.nout + ch) * (HEAAC_X_FLOATS), 1 / qmf_scale, c->T, 0, 1);
+            memset(c->sm_sbr, 0xA5, sizeof(HeaacHfSmem));
+            heaac_hf_channel(c->sm_sbr, c->W + gc * 2048, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
+                             c->chan + gc, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, c->T, 0, 1);
         }
         if (g.ps)
             for (size_t s = 0; s < S; s++) {                      /* k_ps */
@@ -143,9 +152,9 @@ extern "C" int heaac_emu_peek(EmuCtx *c, const char *name, void *dst, int cap)
     const void *p = nullptr; size_t n = 0;
     size_t S = c->g.n_streams;
     if (!strcmp(name, "X")) { p = c->X; n = S * c->g.nout * HEAAC_X_FLOATS * sizeof(float); }
-    else if (!strcmp(name, "core_time")) { p = c->core_time; n = S * c->g.ncc * 1024 * sizeof(float); }
+    else if (!strcmp(name, "W")) { p = c->W; n = S * c->g.ncc * 2048 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { p = c->chan; n = S * c->g.ncc * sizeof(HeaacChanState); }
-    else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacSbrSmem); }
+    else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacHfSmem); }
     else if (!strcmp(name, "ps_smem")) { p = c->sm_ps; n = sizeof(HeaacPsSmem); }
     if (!p) return -1;
     if (n > (size_t)cap) n = cap;
