@@ -35,8 +35,13 @@ struct HeaacContext {
     float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
     float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
-    float *s_coeffs; HeaacIcs *s_ics; HeaacTns *s_tns; HeaacSbrElem *s_sbr; HeaacPsFrame *s_ps;
-    int16_t *s_pcm; float *s_pcm_f32;
+    /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
+     * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
+    int chunk;
+    float *s_coeffs[2]; HeaacIcs *s_ics[2]; HeaacTns *s_tns[2]; HeaacSbrElem *s_sbr[2]; HeaacPsFrame *s_ps[2];
+    int16_t *s_pcm[2]; float *s_pcm_f32[2];
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
     long long launches;
     size_t smem_core, smem_sbr, smem_ps, smem_synth;
     /* optional per-kernel event timing (heaac_b200_profile_*) */
@@ -292,13 +297,26 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
         CKX(cudaMalloc(&c->d_W, S * g->ncc * 2048 * sizeof(float)));
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
-    CKX(cudaMalloc(&c->s_coeffs, T * S * g->ncc * 1024 * sizeof(float)));
-    CKX(cudaMalloc(&c->s_ics, T * S * g->ncc * sizeof(HeaacIcs)));
-    CKX(cudaMalloc(&c->s_tns, T * S * g->ncc * sizeof(HeaacTns)));
-    if (g->sbr) CKX(cudaMalloc(&c->s_sbr, T * S * g->nse * sizeof(HeaacSbrElem)));
-    if (g->ps)  CKX(cudaMalloc(&c->s_ps, T * S * sizeof(HeaacPsFrame)));
-    CKX(cudaMalloc(&c->s_pcm, T * S * g->out_len * g->nout * sizeof(int16_t)));
-    if (cfg->want_float_out) CKX(cudaMalloc(&c->s_pcm_f32, T * S * g->out_len * g->nout * sizeof(float)));
+    c->chunk = (int)((T + 3) / 4);
+    if (c->chunk > 8) c->chunk = 8;
+    if (c->chunk < 1) c->chunk = 1;
+    {
+        const size_t Tc = c->chunk;
+        CKX(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CKX(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CKX(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CKX(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CKX(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+            CKX(cudaMalloc(&c->s_coeffs[i], Tc * S * g->ncc * 1024 * sizeof(float)));
+            CKX(cudaMalloc(&c->s_ics[i], Tc * S * g->ncc * sizeof(HeaacIcs)));
+            CKX(cudaMalloc(&c->s_tns[i], Tc * S * g->ncc * sizeof(HeaacTns)));
+            if (g->sbr) CKX(cudaMalloc(&c->s_sbr[i], Tc * S * g->nse * sizeof(HeaacSbrElem)));
+            if (g->ps)  CKX(cudaMalloc(&c->s_ps[i], Tc * S * sizeof(HeaacPsFrame)));
+            CKX(cudaMalloc(&c->s_pcm[i], Tc * S * g->out_len * g->nout * sizeof(int16_t)));
+            if (cfg->want_float_out) CKX(cudaMalloc(&c->s_pcm_f32[i], Tc * S * g->out_len * g->nout * sizeof(float)));
+        }
+    }
 
     c->smem_core = sizeof(HeaacCoreSmem) + (g->sbr ? 1312 + 64 * 33 : 1312) * sizeof(float);
     c->smem_sbr = sizeof(HeaacHfSmem);
@@ -322,8 +340,15 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
     cudaFree(c->d_W); cudaFree(c->d_X);
-    cudaFree(c->s_coeffs); cudaFree(c->s_ics); cudaFree(c->s_tns); cudaFree(c->s_sbr); cudaFree(c->s_ps);
-    cudaFree(c->s_pcm); cudaFree(c->s_pcm_f32);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
+        cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]);
     free(c->prof_ev); free(c->prof_kind);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -399,27 +424,41 @@ extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
     if (b->on_device)
         return launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32);
 
-    if (b->pcm_f32 && !c->s_pcm_f32) return HEAAC_E_INVAL;   /* context created without want_float_out */
+    if (b->pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;   /* context created without want_float_out */
     const size_t S = g->n_streams;
-    const int Tmax = c->cfg.max_frames_per_call;
-    for (int f0 = 0; f0 < b->n_frames; f0 += Tmax) {
-        int n = b->n_frames - f0 < Tmax ? b->n_frames - f0 : Tmax;
-        size_t nch = (size_t)n * S * g->ncc, och = (size_t)f0 * S * g->ncc;
-        CK(cudaMemcpyAsync(c->s_coeffs, b->coeffs + och * 1024, nch * 1024 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->s_ics, b->ics + och, nch * sizeof(HeaacIcs), cudaMemcpyHostToDevice, c->stream));
-        if (b->tns) CK(cudaMemcpyAsync(c->s_tns, b->tns + och, nch * sizeof(HeaacTns), cudaMemcpyHostToDevice, c->stream));
-        if (g->sbr) CK(cudaMemcpyAsync(c->s_sbr, b->sbr + (size_t)f0 * S * g->nse, (size_t)n * S * g->nse * sizeof(HeaacSbrElem),
-                                       cudaMemcpyHostToDevice, c->stream));
-        if (g->ps)  CK(cudaMemcpyAsync(c->s_ps, b->ps + (size_t)f0 * S, (size_t)n * S * sizeof(HeaacPsFrame),
-                                       cudaMemcpyHostToDevice, c->stream));
-        int r = launch_frames(c, n, c->s_coeffs, c->s_ics, b->tns ? c->s_tns : nullptr, c->s_sbr, c->s_ps,
-                              c->s_pcm, b->pcm_f32 ? c->s_pcm_f32 : nullptr);
+    const int Tc = c->chunk;
+    /* the kernels must not start before earlier work on the context's stream has finished with the state */
+    int k = 0;
+    for (int f0 = 0; f0 < b->n_frames; f0 += Tc, k++) {
+        const int buf = k & 1;
+        const int n = b->n_frames - f0 < Tc ? b->n_frames - f0 : Tc;
+        const size_t nch = (size_t)n * S * g->ncc, och = (size_t)f0 * S * g->ncc;
+        /* H2D on s_in: staging set `buf` is free once the kernels of chunk k-2 are done */
+        if (k >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));
+        CK(cudaMemcpyAsync(c->s_coeffs[buf], b->coeffs + och * 1024, nch * 1024 * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->s_ics[buf], b->ics + och, nch * sizeof(HeaacIcs), cudaMemcpyHostToDevice, c->s_in));
+        if (b->tns) CK(cudaMemcpyAsync(c->s_tns[buf], b->tns + och, nch * sizeof(HeaacTns), cudaMemcpyHostToDevice, c->s_in));
+        if (g->sbr) CK(cudaMemcpyAsync(c->s_sbr[buf], b->sbr + (size_t)f0 * S * g->nse, (size_t)n * S * g->nse * sizeof(HeaacSbrElem),
+                                       cudaMemcpyHostToDevice, c->s_in));
+        if (g->ps)  CK(cudaMemcpyAsync(c->s_ps[buf], b->ps + (size_t)f0 * S, (size_t)n * S * sizeof(HeaacPsFrame),
+                                       cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(c->ev_in[buf], c->s_in));
+        /* kernels on the context stream: need the inputs, and the PCM staging set drained by chunk k-2's D2H */
+        CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
+        int r = launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], b->tns ? c->s_tns[buf] : nullptr, c->s_sbr[buf], c->s_ps[buf],
+                              c->s_pcm[buf], b->pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
         if (r) return r;
-        size_t pcm_n = (size_t)n * S * g->out_len * g->nout, pcm_o = (size_t)f0 * S * g->out_len * g->nout;
-        if (b->pcm) CK(cudaMemcpyAsync(b->pcm + pcm_o, c->s_pcm, pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
-        if (b->pcm_f32) CK(cudaMemcpyAsync(b->pcm_f32 + pcm_o, c->s_pcm_f32, pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventRecord(c->ev_done[buf], c->stream));
+        /* D2H on s_out */
+        const size_t pcm_n = (size_t)n * S * g->out_len * g->nout, pcm_o = (size_t)f0 * S * g->out_len * g->nout;
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_done[buf], 0));
+        if (b->pcm) CK(cudaMemcpyAsync(b->pcm + pcm_o, c->s_pcm[buf], pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_out));
+        if (b->pcm_f32) CK(cudaMemcpyAsync(b->pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaEventRecord(c->ev_out[buf], c->s_out));
     }
+    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

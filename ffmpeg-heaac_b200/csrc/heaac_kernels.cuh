@@ -53,9 +53,15 @@ HEAAC_DEV int16_t heaac_to_s16(float x, int bias_mode)
         if (tmp & 0xf0000) tmp = (0x43c0ffffLL - tmp) >> 31;
         return (int16_t)(tmp - 0x8000);
     }
+#ifdef HEAAC_HOST_EMU
     float r = heaac_rint(x);
     r = r < -32768.0f ? -32768.0f : (r > 32767.0f ? 32767.0f : r);
     return (int16_t)(int)r;
+#else
+    short r;                                   /* round-to-nearest-even + saturate in one instruction */
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return r;
+#endif
 }
 
 /* ------------------------------------------------------------------------------------
@@ -680,7 +686,8 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
  * one stream-frame.  64 threads per channel:
  *   phase 1  thread = (plane re/im, slot i): one half-IMDCT (N = 128, scale 1/64) in registers, inputs read
  *            coalesced from the band-major X buffer (lanes = slots)
- *   phase 2  the im-plane threads combine b0/b1 into the slot's 128-sample v block (aacsbr.c:1210-1213)
+ *   phase 2  the im-plane threads combine b0 (parked in the slot's own v block) and b1 (registers) into the
+ *            slot's 128-sample v block in place (aacsbr.c:1210-1213)
  *   phase 3  thread = (sample n, channel): the 10-tap polyphase sum for all 32 slots with the window
  *            column w[64 j + n] held in registers; s16 stores of the two channels interleave into
  *            contiguous bytes
@@ -688,9 +695,9 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
  * free of bank conflicts.
  * ================================================================================== */
 #define HEAAC_V_STRIDE 129
-#define HEAAC_SYN_CH_FLOATS (41 * HEAAC_V_STRIDE + 64 * 32 + 7)    /* = 16 (mod 32): the 2nd channel starts 16 banks away */
+#define HEAAC_SYN_CH_FLOATS (41 * HEAAC_V_STRIDE + 7)    /* = 16 (mod 32): the 2nd channel starts 16 banks away */
 struct HeaacSynthSmem {
-    float ch[2][HEAAC_SYN_CH_FLOATS];   /* per channel: v[41][129] (block 0 = newest) then b0[64][32] */
+    float ch[2][HEAAC_SYN_CH_FLOATS];   /* per channel: v[41][129], block 0 = newest, blocks 32..40 = history */
 };
 
 HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nout,
@@ -706,11 +713,11 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
     for (int t = tid; t < nthr; t += nt) {
         const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
         const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
-        float *b0 = sm->ch[c] + 41 * HEAAC_V_STRIDE;
+        float *row = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;      /* b0 is parked in the slot's own v block */
         if (plane == 0) {
             heaac_imdct128_reg<HEAAC_MDCT_SYN>(
                 [&](int j) { return x[j * HEAAC_XS]; },
-                [&](int j, float v) { b0[j * 32 + i] = v; });
+                [&](int j, float v) { row[j] = v; });
         }
     }
     HEAAC_SYNC();
@@ -719,17 +726,18 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
         const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
         if (plane == 0) continue;
         const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
-        const float *b0 = sm->ch[c] + 41 * HEAAC_V_STRIDE;
         float b1[64];
         heaac_imdct128_reg<HEAAC_MDCT_SYN>(
             [&](int j) { float v = x[j * HEAAC_XS]; return (j & 1) ? -v : v; },     /* aacsbr.c:1205-1207 */
             [&](int j, float v) { b1[j] = v; });
-        float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;
+        float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;       /* holds b0[0..63]; becomes v[0..127] in place */
         HEAAC_UNROLL
-        for (int n = 0; n < 64; n++) {
-            const float p = b0[(63 - n) * 32 + i], q = b1[n];
-            v[n]       = -p + q;
-            v[127 - n] =  p + q;
+        for (int n = 0; n < 32; n++) {
+            const float p1 = v[63 - n], p2 = v[n], q1 = b1[n], q2 = b1[63 - n];
+            v[n]       = -p1 + q1;
+            v[127 - n] =  p1 + q1;
+            v[63 - n]  = -p2 + q2;
+            v[64 + n]  =  p2 + q2;
         }
     }
     HEAAC_SYNC();

@@ -23,6 +23,14 @@
 
 #define HEAAC_QS 41                 /* row stride of the [band][slot] arrays (40 slots used) */
 
+/* (row, lane) loop nests: rows are dealt to warps, the fastest index to lanes, so that everything that
+ * depends only on the row is computed once per warp iteration.  With nt = 1 (host emulation) they
+ * degenerate to plain nested loops. */
+#define HEAAC_WARP(tid, nt)    ((nt) >= 32 ? (tid) >> 5 : 0)
+#define HEAAC_NWARPS(nt)       ((nt) >= 32 ? (nt) >> 5 : 1)
+#define HEAAC_LANE(tid, nt)    ((nt) >= 32 ? (tid) & 31 : 0)
+#define HEAAC_LSTRIDE(nt)      ((nt) >= 32 ? 32 : 1)
+
 /* ------------------------------------------------------------------------------------
  * QMF analysis.  x: 1312 floats in shared memory (288 history + 1024 new, already scaled).
  * tb: 64 * 33 floats of scratch (folded + shuffled transform inputs, [input index][slot], stride 33).
@@ -80,6 +88,9 @@ struct HeaacHfSmem {
     uint8_t patch_src[48];          /* low-band source of kx + m in the HF generator, 255 = beyond the last patch */
     uint8_t ynew_valid[64][8];
     int8_t  env_of_slot[48];
+    uint8_t slot_border[48];        /* slot lies in an envelope adjacent to a transient border (l_A / l_APrev) */
+    uint8_t smooth_src[40][5];      /* row of gall/qall feeding tap j of the 5-tap gain smoother at slot i */
+    float gall[16][48], qall[16][48];   /* rows 0..4: this frame's envelopes, 5..14: g_temp/q_temp history rows 32..41, 15: zero */
     HeaacSbrElem p;
 };
 
@@ -135,36 +146,24 @@ struct HeaacYCtx {
     uint32_t noise0, sine0;
 };
 
-/* Y[1][i][kx + m] of sbr_hf_assemble (aacsbr.c:1649-1710) for one (slot, band).
- * g_temp/q_temp row r (= i + h_SL - j) holds gain[env(r - h_SL)] when slot r - h_SL belongs to this
- * frame, otherwise one of the four history rows (aacsbr.c:1632-1640). */
-HEAAC_DEV void heaac_sbr_y(const HeaacHfSmem *sm, const HeaacChanState *st, const HeaacYCtx *y,
+/* Y[1][i][kx + m] of sbr_hf_assemble (aacsbr.c:1649-1710) for one (slot, band).  The g_temp/q_temp rows the
+ * 5-tap smoother reads (aacsbr.c:1632-1647, 1653-1658) are resolved per slot into sm->smooth_src. */
+HEAAC_DEV void heaac_sbr_y(const HeaacHfSmem *sm, const HeaacYCtx *y,
                            const HeaacDevTables *HEAAC_RESTRICT T, int i, int m, float *yre_o, float *yim_o)
 {
     const int e = sm->env_of_slot[i];
-    const int at_border = (e == y->e_a0 || e == y->e_a1);
+    const int at_border = sm->slot_border[i];
     float g_filt, q_filt;
     if (y->h_SL && !at_border) {
         g_filt = 0.0f; q_filt = 0.0f;
         for (int j = 0; j <= 4; j++) {
-            int src = i - j;
-            float gv, qv;
-            if (src >= y->i_lo) {
-                int es = sm->env_of_slot[src];
-                gv = sm->gain[es][m]; qv = sm->q_m[es][m];
-            } else if (y->reset) {
-                gv = sm->gain[0][m]; qv = sm->q_m[0][m];
-            } else {
-                int hr = y->t_old2 + (src + 4 - y->i_lo) - 32;     /* history row relative to row 32 */
-                gv = (hr >= 0 && hr < 10) ? st->g_hist[hr * 48 + m] : 0.0f;
-                qv = (hr >= 0 && hr < 10) ? st->q_hist[hr * 48 + m] : 0.0f;
-            }
-            g_filt = heaac_fadd(g_filt, heaac_fmul(gv, heaac_h_smooth[j]));
-            q_filt = heaac_fadd(q_filt, heaac_fmul(qv, heaac_h_smooth[j]));
+            const int r = sm->smooth_src[i][j];
+            g_filt = heaac_fadd(g_filt, heaac_fmul(sm->gall[r][m], heaac_h_smooth[j]));
+            q_filt = heaac_fadd(q_filt, heaac_fmul(sm->qall[r][m], heaac_h_smooth[j]));
         }
     } else {
-        g_filt = sm->gain[e][m];
-        q_filt = sm->q_m[e][m];
+        g_filt = sm->gall[e][m];
+        q_filt = sm->qall[e][m];
     }
     float yre = heaac_fmul(sm->xh_re[m][i + 2], g_filt);
     float yim = heaac_fmul(sm->xh_im[m][i + 2], g_filt);
@@ -203,16 +202,20 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
     const int nenv = pc->bs_num_env;
     const int i_lo = p->start ? 2 * pc->t_env[0] : 0, i_hi = p->start ? 2 * pc->t_env[nenv] : 0;
 
+    const int warp = HEAAC_WARP(tid, nt), nwarps = HEAAC_NWARPS(nt), lane = HEAAC_LANE(tid, nt), ls = HEAAC_LSTRIDE(nt);
     /* ---- sbr_lf_gen: X_low[k][i] = W[k][i - 8] (i >= 8, k < kx) | previous frame's W[k][24 + i] (i < 8, k < kx') ---- */
-    for (int w = tid; w < 32 * 40; w += nt) {
-        const int k = w / 40, i = w - k * 40;
-        float re = 0.0f, im = 0.0f;
-        if (i >= 8) {
-            if (k < kx) { re = W_in[k * 32 + i - 8]; im = W_in[1024 + k * 32 + i - 8]; }
-        } else if (k < kx0) {
-            re = st->w_tail[k * 8 + i]; im = st->w_tail[256 + k * 8 + i];
+    for (int k = warp; k < 32; k += nwarps) {             /* slots 8..39 = this frame's W[k][0..31]: one full warp per row */
+        const int cur = k < kx;
+        const float *wr = W_in + k * 32, *wi = wr + 1024;
+        for (int i = lane; i < 32; i += ls) {
+            sm->xl_re[k][8 + i] = cur ? wr[i] : 0.0f;
+            sm->xl_im[k][8 + i] = cur ? wi[i] : 0.0f;
         }
-        sm->xl_re[k][i] = re; sm->xl_im[k][i] = im;
+    }
+    for (int w = tid; w < 32 * 8; w += nt) {               /* slots 0..7 = previous frame's W[k][24..31] */
+        const int k = w >> 3, i = w & 7, old = k < kx0;
+        sm->xl_re[k][i] = old ? st->w_tail[w] : 0.0f;
+        sm->xl_im[k][i] = old ? st->w_tail[256 + w] : 0.0f;
     }
     /* per-sub-band lookup tables */
     for (int m = tid; m < 48; m += nt) {
@@ -244,6 +247,30 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
         for (int q2 = 0; q2 < nenv; q2++)
             if (m >= 2 * pc->t_env[q2] && m < 2 * pc->t_env[q2 + 1]) e = q2;
         sm->env_of_slot[m] = (int8_t)e;                    /* (index m doubles as the slot index here) */
+        sm->slot_border[m] = (uint8_t)(e == pc->e_a[0] || e == pc->e_a[1]);
+        if (m < 40) {
+            /* g_temp row (i + 4 - j) of the smoother: slot i - j of this frame, else a history row, aacsbr.c:1632-1647 */
+            const int t_old2_ = 2 * pc->t_env_num_env_old;
+            for (int j = 0; j <= 4; j++) {
+                int src = m - j, r;
+                if (src >= i_lo) {
+                    r = 15;
+                    for (int q2 = 0; q2 < nenv; q2++)
+                        if (src >= 2 * pc->t_env[q2] && src < 2 * pc->t_env[q2 + 1]) r = q2;
+                } else if (p->reset) {
+                    r = 0;
+                } else {
+                    int hr = t_old2_ + (src + 4 - i_lo) - 32;      /* history row relative to row 32 */
+                    r = (hr >= 0 && hr < 10) ? 5 + hr : 15;
+                }
+                sm->smooth_src[m][j] = (uint8_t)r;
+            }
+        }
+    }
+    for (int w = tid; w < 11 * 48; w += nt) {              /* history rows of g_temp / q_temp, plus the zero row */
+        const int r = w / 48, m = w - r * 48;
+        sm->gall[5 + r][m] = r < 10 ? st->g_hist[w] : 0.0f;
+        sm->qall[5 + r][m] = r < 10 ? st->q_hist[w] : 0.0f;
     }
     HEAAC_SYNC();
     for (int w = tid; w < 2 * 32 * 8; w += nt) {           /* next frame's W tail: slots 24..31, all 32 bands */
@@ -340,12 +367,26 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             }
         }
         HEAAC_SYNC();
-        /* ---- sbr_hf_gen (lanes = slots) ---- */
-        for (int w = tid; w < m_max * 40; w += nt) {
-            const int m = w / 40, d = w - m * 40;          /* d = slot index inside X_high (i + 2) */
+        /* ---- sbr_hf_gen (rows = target bands, lanes = slots) ---- */
+        for (int m = warp; m < m_max; m += nwarps) {
             const int q = sm->patch_src[m];
-            if (q == 255) { sm->xh_re[m][d] = 0.0f; sm->xh_im[m][d] = 0.0f; continue; }   /* memset(X_high + k, 0) */
-            if (d - 2 < i_lo || d - 2 >= i_hi) continue;   /* left untouched by the reference, never read */
+            if (q == 255) {                                /* beyond the last patch: memset(X_high + k, 0) */
+                for (int d = lane; d < 40; d += ls) { sm->xh_re[m][d] = 0.0f; sm->xh_im[m][d] = 0.0f; }
+                continue;
+            }
+            const float bw = sm->bw[sm->noise_idx[m]];
+            const float a0 = sm->alpha[q][2] * bw * bw, a1 = sm->alpha[q][3] * bw * bw;
+            const float a2 = sm->alpha[q][0] * bw,      a3 = sm->alpha[q][1] * bw;
+            for (int d = i_lo + 2 + lane; d < i_lo + 34 && d < i_hi + 2; d += ls) {   /* first 32 slots of the grid */
+                const float *xr = sm->xl_re[q] + d, *xi = sm->xl_im[q] + d;
+                sm->xh_re[m][d] = xr[-2] * a0 - xi[-2] * a1 + xr[-1] * a2 - xi[-1] * a3 + xr[0];
+                sm->xh_im[m][d] = xi[-2] * a0 + xr[-2] * a1 + xi[-1] * a2 + xr[-1] * a3 + xi[0];
+            }
+        }
+        for (int w = tid; w < m_max * 8; w += nt) {        /* the (at most 6) remaining slots, all bands at once */
+            const int m = w >> 3, d = i_lo + 34 + (w & 7);
+            const int q = sm->patch_src[m];
+            if (q == 255 || d >= i_hi + 2) continue;
             const float bw = sm->bw[sm->noise_idx[m]];
             const float a0 = sm->alpha[q][2] * bw * bw, a1 = sm->alpha[q][3] * bw * bw;
             const float a2 = sm->alpha[q][0] * bw,      a3 = sm->alpha[q][1] * bw;
@@ -451,8 +492,9 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             int e = w / 48, m = w - e * 48;
             if (m >= m_max) continue;
             float gain_boost = sm->gboost[e][sm->lim_idx[m]];
-            sm->gain[e][m] = heaac_fmul(sm->gain[e][m], gain_boost);
-            sm->q_m[e][m]  = heaac_fmul(sm->q_m[e][m], gain_boost);
+            const float gf = heaac_fmul(sm->gain[e][m], gain_boost), qf = heaac_fmul(sm->q_m[e][m], gain_boost);
+            sm->gain[e][m] = gf; sm->gall[e][m] = gf;
+            sm->q_m[e][m]  = qf; sm->qall[e][m] = qf;
             sm->s_m[e][m]  = heaac_fmul(sm->s_m[e][m], gain_boost);
         }
         HEAAC_SYNC();
@@ -470,28 +512,35 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
         y.e_a0 = pc->e_a[0]; y.e_a1 = pc->e_a[1];
         const int i_Temp = HEAAC_MAX(y.t_old2 - 32, 0);
         float *Xre = X_out, *Xim = X_out + HEAAC_X_PLANE;
-        for (int w = tid; w < 64 * HEAAC_XS; w += nt) {
-            const int k = w / HEAAC_XS, i = w - k * HEAAC_XS;
-            if (i >= 38) continue;
-            float re = 0.0f, im = 0.0f;
-            const int in_hf = p->start && i >= i_lo && i < i_hi && k >= kx && k < kx + m_max;
-            float yre = 0.0f, yim = 0.0f;
-            if (in_hf) heaac_sbr_y(sm, st, &y, T, i, k - kx, &yre, &yim);
-            /* sbr_x_gen, aacsbr.c:1412-1446 */
-            if (i < i_Temp) {
-                if (k < kx0) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
-                else if (k < kx0 + m0) { re = st->y_tail[k * 8 + i]; im = st->y_tail[512 + k * 8 + i]; }
-            } else {
-                if (k < kx) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
-                else if (k < kx + m_max && i < 32 && in_hf) { re = yre; im = yim; }
-                /* (slots of Y[1] the envelope grid does not cover would hold stale data of an older
-                 *  frame in the reference; a conformant grid always covers [i_Temp, 32)) */
+        for (int k = warp; k < 64; k += nwarps) {          /* rows = QMF bands, lanes = slots 0..31 */
+            const int low_cur = k < kx, low_old = k < kx0;
+            const int hf_cur = p->start && k >= kx && k < kx + m_max, hf_old = k >= kx0 && k < kx0 + m0;
+            const int m = k - kx;
+            for (int i = lane; i < 32; i += ls) {
+                float re = 0.0f, im = 0.0f;
+                /* sbr_x_gen, aacsbr.c:1412-1446 */
+                if (i < i_Temp) {
+                    if (low_old) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
+                    else if (hf_old) { re = st->y_tail[k * 8 + i]; im = st->y_tail[512 + k * 8 + i]; }
+                } else {
+                    if (low_cur) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
+                    else if (hf_cur && i >= i_lo && i < i_hi) heaac_sbr_y(sm, &y, T, i, m, &re, &im);
+                    /* (slots of Y[1] the envelope grid does not cover would hold stale data of an older
+                     *  frame in the reference; a conformant grid always covers [i_Temp, 32)) */
+                }
+                Xre[k * HEAAC_XS + i] = re; Xim[k * HEAAC_XS + i] = im;
             }
-            Xre[w] = re; Xim[w] = im;
-            if (i >= 32) {                                /* Y[1][32..37]: next frame's Y[0] tail */
-                sm->ynew_re[k][i - 32] = yre; sm->ynew_im[k][i - 32] = yim;
-                sm->ynew_valid[k][i - 32] = (uint8_t)in_hf;
-            }
+        }
+        for (int w = tid; w < 64 * 8; w += nt) {           /* slots 32..37: low band for PS look-ahead; Y tail for the next frame */
+            const int k = w >> 3, j = w & 7, i = 32 + j;
+            if (j >= 6) continue;
+            float re = 0.0f, im = 0.0f, yre = 0.0f, yim = 0.0f;
+            const int in_hf = p->start && k >= kx && k < kx + m_max && i < i_hi;
+            if (in_hf) heaac_sbr_y(sm, &y, T, i, k - kx, &yre, &yim);
+            if (k < kx) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
+            Xre[k * HEAAC_XS + i] = re; Xim[k * HEAAC_XS + i] = im;
+            sm->ynew_re[k][j] = yre; sm->ynew_im[k][j] = yim;
+            sm->ynew_valid[k][j] = (uint8_t)in_hf;
         }
         HEAAC_SYNC();      /* every read of the old y_tail / g_hist / q_hist is done */
         for (int w = tid; w < 64 * 8; w += nt) {
