@@ -21,6 +21,9 @@
 extern "C" void heaac_build_tables(HeaacDevTables *t);
 
 #define HEAAC_THREADS 256
+#ifndef HEAAC_CORE_MIN_BLOCKS
+#define HEAAC_CORE_MIN_BLOCKS 4
+#endif
 
 /* ------------------------------------------------------------------------------------ */
 struct HeaacContext {
@@ -66,7 +69,7 @@ static void prof_end(HeaacContext *c)
 }
 
 /* ------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(HEAAC_THREADS)
+__global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
 k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
        const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
@@ -81,28 +84,28 @@ k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict
     HeaacChanState *st = chan + gc;
     const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
     if (ana)
-        for (int i = threadIdx.x; i < 288; i += blockDim.x) x[i] = st->ana_hist[i];
-    heaac_core_channel(sm, coeffs + (size_t)gc * 1024, ics + gc, tns ? tns + gc : nullptr,
-                       st, out, bias, g.sr_index, T, threadIdx.x, blockDim.x);
+        for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
+    heaac_core_channel<HEAAC_THREADS>(sm, coeffs + (size_t)gc * 1024, ics + gc, tns ? tns + gc : nullptr,
+                       st, out, bias, g.sr_index, T, threadIdx.x);
     if (ana) {
         /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
         const float ana_scale = 1 / (-1024.0f * g.sf_scale);                   /* aacsbr.c:1730 */
         if (ana_scale != 1.0f) {
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = out[i] * ana_scale;
+            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) out[i] = out[i] * ana_scale;
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < 288; i += blockDim.x) st->ana_hist[i] = x[1024 + i];
+        for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
         float *tb = x + 1312;
-        heaac_qmf_analysis(x, tb, W + (size_t)gc * 2048, T, threadIdx.x, blockDim.x);
+        heaac_qmf_analysis<HEAAC_THREADS>(x, tb, W + (size_t)gc * 2048, T, threadIdx.x);
     } else if (!g.sbr) {
         const int bias_mode = g.add_bias != 0.0f;
         if (pcm) {
             int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
+            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
         }
         if (pcm_f32) {
             float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
-            for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = out[i];
+            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
         }
     }
 }
@@ -118,8 +121,8 @@ k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__
     const int se = g.ch_sbr_elem[c];
     if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
     float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
-    heaac_hf_channel(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
-                     g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x, blockDim.x);
+    heaac_hf_channel<HEAAC_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
+                     g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)
@@ -131,7 +134,7 @@ k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__res
     const int s = blockIdx.x;
     float *XL = X + (size_t)s * 2 * HEAAC_X_FLOATS, *XR = XL + HEAAC_X_FLOATS;
     const HeaacSbrElem *e = sbr + (size_t)s * g.nse;
-    heaac_ps_stream(sm, ps + s, pstate + s, XL, XR, (int)e->kx[1] + (int)e->m[1], T, threadIdx.x, blockDim.x);
+    heaac_ps_stream<HEAAC_THREADS>(sm, ps + s, pstate + s, XL, XR, (int)e->kx[1] + (int)e->m[1], T, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(128)
@@ -145,10 +148,10 @@ k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
-    heaac_synth_stream(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
+    heaac_synth_stream<128>(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
                        pcm ? pcm + (size_t)s * 2048 * g.nout : nullptr,
                        pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 2048 : nullptr,
-                       qmf_scale, g.add_bias, T, threadIdx.x, blockDim.x);
+                       qmf_scale, g.add_bias, T, threadIdx.x);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -404,7 +407,7 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            k_synth<<<(unsigned)(S * g.nse), 64 * (g.ps ? 2 : g.max_elem_ch), c->smem_synth, c->stream>>>(
+            k_synth<<<(unsigned)(S * g.nse), 128, c->smem_synth, c->stream>>>(
                 g, c->d_X, c->d_synth, pc, pf, c->d_tables);
             prof_end(c);
             c->launches++;
@@ -582,7 +585,7 @@ __global__ void k_imdct_half_one(float *out, const float *in, const float *tcos,
     float *zr = buf + n2, *zi = zr + n4;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) buf[i] = in[i];
     __syncthreads();
-    heaac_imdct_half_smem(buf, buf, zr, zi, log2n4, 1, tcos, tsin, T, threadIdx.x, blockDim.x);
+    heaac_imdct_half_smem<HEAAC_THREADS>(buf, buf, zr, zi, log2n4, 1, tcos, tsin, T, threadIdx.x);
     for (int i = threadIdx.x; i < n2; i += blockDim.x) out[i] = buf[i];
 }
 

@@ -70,9 +70,11 @@ HEAAC_DEV int16_t heaac_to_s16(float x, int bias_mode)
  * Input must already be in bit-reversed order.  `nbatch` transforms of 2^log2n points lie
  * back to back.  Radix-2, one butterfly per work item, log2n barriers.
  * ---------------------------------------------------------------------------------- */
+template <int NT>
 HEAAC_DEV void heaac_fft_smem(float *re, float *im, int log2n, int nbatch,
-                              const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                              const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     const int hn = 1 << (log2n - 1);
     const int total = nbatch * hn;
     for (int s = 1; s <= log2n; s++) {
@@ -107,11 +109,13 @@ HEAAC_DEV int heaac_bitrev(int k, int bits)
 /* Batched half-IMDCT of size N = 4 * n4 (mdct.c:124-159): `in` holds nbatch * N/2 inputs,
  * `out` receives nbatch * N/2 outputs; in and out may alias (input is consumed by the
  * pre-rotation before anything is written).  zr/zi: nbatch * n4 floats of scratch each. */
+template <int NT>
 HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, float *zi,
                                      int log2n4, int nbatch,
                                      const float *HEAAC_RESTRICT tcos, const float *HEAAC_RESTRICT tsin,
-                                     const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                                     const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     const int n4 = 1 << log2n4, n2 = n4 << 1, n8 = n4 >> 1;
     for (int w = tid; w < nbatch * n4; w += nt) {
         int b = w >> log2n4, k = w & (n4 - 1);
@@ -122,7 +126,7 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
         zi[b * n4 + rk] = a * tsin[k] + c * tcos[k];
     }
     HEAAC_SYNC();
-    heaac_fft_smem(zr, zi, log2n4, nbatch, T, tid, nt);
+    heaac_fft_smem<NT>(zr, zi, log2n4, nbatch, T, tid);
     for (int w = tid; w < nbatch * n8; w += nt) {
         int b = w / n8, k = w - b * n8;
         int p = n8 - k - 1, q = n8 + k;
@@ -149,9 +153,11 @@ struct HeaacCoreSmem {
     int   tns_start[8], tns_size[8], tns_inc[8], tns_order[8];
 };
 
+template <int NT>
 HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const float *HEAAC_RESTRICT win,
-                         float bias, int len, int tid, int nt)
+                         float bias, int len,  int tid)
 {
+    constexpr int nt = NT;
     for (int i = tid; i < len; i += nt) {
         int j = 2 * len - 1 - i;
         float a = s0[i], b = s1[len - 1 - i], wi = win[i], wj = win[j];
@@ -161,11 +167,13 @@ HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const flo
 }
 
 /* `out` : 1024 floats in shared or global memory (time-domain output, bias included) */
+template <int NT>
 HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT coeffs,
                                   const HeaacIcs *HEAAC_RESTRICT ics_p, const HeaacTns *HEAAC_RESTRICT tns,
                                   HeaacChanState *st, float *out, float bias, int sr_index,
-                                  const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                                  const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     const HeaacIcs ics = *ics_p;
     const int ws0 = ics.window_sequence, ws1 = st->prev_ws, shape_prev = st->prev_shape;
     const int is8 = ws0 == HEAAC_EIGHT_SHORT;
@@ -234,9 +242,9 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
 
     /* ---- half IMDCT: 1 x N=2048 or 8 x N=256, aacdec.c:1755-1763 ---- */
     if (is8)
-        heaac_imdct_half_smem(sm->c, sm->c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid, nt);
+        heaac_imdct_half_smem<NT>(sm->c, sm->c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid);
     else
-        heaac_imdct_half_smem(sm->c, sm->c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid, nt);
+        heaac_imdct_half_smem<NT>(sm->c, sm->c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid);
 
     /* ---- windowing + overlap-add, aacdec.c:1771-1805 ---- */
     const float *buf = sm->c;
@@ -247,14 +255,14 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
     const int prev_long = ws1 == HEAAC_ONLY_LONG || ws1 == HEAAC_LONG_STOP;
 
     if (prev_long && (ws0 == HEAAC_ONLY_LONG || ws0 == HEAAC_LONG_START)) {
-        heaac_vfw(out, saved, buf, lw_prev, bias, 512, tid, nt);
+        heaac_vfw<NT>(out, saved, buf, lw_prev, bias, 512, tid);
     } else {
         for (int i = tid; i < 448; i += nt) out[i] = saved[i] + bias;
-        heaac_vfw(out + 448, saved + 448, buf, sw_prev, bias, 64, tid, nt);
+        heaac_vfw<NT>(out + 448, saved + 448, buf, sw_prev, bias, 64, tid);
         if (is8) {
             for (int j = 1; j < 4; j++)
-                heaac_vfw(out + 448 + 128 * j, buf + 128 * (j - 1) + 64, buf + 128 * j, sw, bias, 64, tid, nt);
-            heaac_vfw(sm->temp, buf + 3 * 128 + 64, buf + 4 * 128, sw, bias, 64, tid, nt);
+                heaac_vfw<NT>(out + 448 + 128 * j, buf + 128 * (j - 1) + 64, buf + 128 * j, sw, bias, 64, tid);
+            heaac_vfw<NT>(sm->temp, buf + 3 * 128 + 64, buf + 4 * 128, sw, bias, 64, tid);
         } else {
             for (int i = 576 + tid; i < 1024; i += nt) out[i] = buf[i - 512] + bias;
         }
@@ -266,7 +274,7 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
             saved[i] = sm->temp[64 + i] - bias;
         }
         for (int j = 0; j < 3; j++)
-            heaac_vfw(saved + 64 + 128 * j, buf + (4 + j) * 128 + 64, buf + (5 + j) * 128, sw, 0.0f, 64, tid, nt);
+            heaac_vfw<NT>(saved + 64 + 128 * j, buf + (4 + j) * 128 + 64, buf + (5 + j) * 128, sw, 0.0f, 64, tid);
         for (int i = tid; i < 64; i += nt) saved[448 + i] = buf[7 * 128 + 64 + i];
     } else if (ws0 == HEAAC_LONG_START) {
         for (int i = tid; i < 448; i += nt) saved[i] = buf[512 + i];
@@ -382,10 +390,12 @@ HEAAC_DEV void heaac_ps_map_val(float *v, int to34)
 
 /* XL / XR: the element's band-major X buffers in global scratch (XL in/out, XR out).
  * top_in = kx + m of the SBR element (aacsbr.c:1753). */
+template <int NT>
 HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRICT frame, HeaacPsState *st,
                                float *XL, float *XR, int top_in,
-                               const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                               const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     {
         const uint32_t *src = (const uint32_t *)frame;
         uint32_t *dst = (uint32_t *)&sm->p;
@@ -700,10 +710,12 @@ struct HeaacSynthSmem {
     float ch[2][HEAAC_SYN_CH_FLOATS];   /* per channel: v[41][129], block 0 = newest, blocks 32..40 = history */
 };
 
+template <int NT>
 HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nout,
                                   int out_slot0, int out_slot1, int16_t *pcm, float *pcm_f32, float scale, float bias,
-                                  const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                                  const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     const int nthr = 64 * nout;
     for (int w = tid; w < nout * 1152; w += nt) {          /* history: blocks 32..40 */
         int c = w / 1152, r = w - c * 1152;

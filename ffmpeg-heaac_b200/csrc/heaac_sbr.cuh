@@ -36,9 +36,11 @@
  * tb: 64 * 33 floats of scratch (folded + shuffled transform inputs, [input index][slot], stride 33).
  * W_out: this channel's W buffer in global memory, [2 planes][32 bands][32 slots].
  * ---------------------------------------------------------------------------------- */
+template <int NT>
 HEAAC_DEV void heaac_qmf_analysis(const float *x, float *tb, float *W_out,
-                                  const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                                  const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     for (int w = tid; w < 32 * 64; w += nt) {              /* aacsbr.c:1149-1160 */
         const int i = w >> 6, k = w & 63;
         const float *xs = x + 32 * i + 319 - k;
@@ -75,10 +77,10 @@ struct HeaacHfSmem {
     float alpha[32][4];             /* a0.re a0.im a1.re a1.im */
     float env[5][48];               /* dequantised env_facs[1..5] */
     float noise[2][8];
-    float e_orig[5][48], q_map[5][48], e_curr[5][48], gain[5][48], q_m[5][48], s_m[5][48];
+    float e_orig[5][48], q_map[5][48], e_curr[5][48], s_m[5][48];     /* gain / q_m live in gall / qall rows 0..4 */
     float gmax[5][8], gboost[5][8];
     float bw[8];
-    float ynew_re[64][8], ynew_im[64][8];   /* Y[1][32..37] of this frame, [band][slot - 32] */
+    float ynew_re[48][8], ynew_im[48][8];   /* Y[1][32..37][kx + m] of this frame, [m][slot - 32] */
     uint8_t s_idx[6][48];           /* s_indexmapped[0..5] */
     uint8_t s_map[5][48];
     uint8_t band_idx[2][48];        /* envelope band (low / high resolution table) containing kx + m */
@@ -86,7 +88,7 @@ struct HeaacHfSmem {
     uint8_t noise_idx[48];          /* noise-floor band containing kx + m */
     uint8_t lim_idx[48];            /* limiter band containing kx + m */
     uint8_t patch_src[48];          /* low-band source of kx + m in the HF generator, 255 = beyond the last patch */
-    uint8_t ynew_valid[64][8];
+    uint8_t ynew_valid[48][8];
     int8_t  env_of_slot[48];
     uint8_t slot_border[48];        /* slot lies in an envelope adjacent to a transient border (l_A / l_APrev) */
     uint8_t smooth_src[40][5];      /* row of gall/qall feeding tap j of the 5-tap gain smoother at slot i */
@@ -102,8 +104,10 @@ HEAAC_DEV float heaac_exp2_half(float x)
     return ldexpf(m, (int)fl);
 }
 
-HEAAC_DEV void heaac_sbr_dequant(HeaacHfSmem *sm, int ch, int is_cpe, int tid, int nt)
+template <int NT>
+HEAAC_DEV void heaac_sbr_dequant(HeaacHfSmem *sm, int ch, int is_cpe,  int tid)
 {
+    constexpr int nt = NT;
     const HeaacSbrElem *p = &sm->p;
     const HeaacSbrChan *pc = &p->ch[ch];
     if (is_cpe && p->bs_coupling) {
@@ -185,11 +189,13 @@ HEAAC_DEV void heaac_sbr_y(const HeaacHfSmem *sm, const HeaacYCtx *y,
 
 /* W_in  : this channel's W of the current frame, [2][32 bands][32 slots] (global, written by the core kernel)
  * X_out : this channel's X[2][64][HEAAC_XS] (band-major) buffer in global scratch. */
+template <int NT>
 HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_in,
                                 const HeaacSbrElem *HEAAC_RESTRICT elem, int ch, int is_cpe,
                                 HeaacChanState *st, float *X_out,
-                                const HeaacDevTables *HEAAC_RESTRICT T, int tid, int nt)
+                                const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    constexpr int nt = NT;
     {
         const uint32_t *src = (const uint32_t *)elem;
         uint32_t *dst = (uint32_t *)&sm->p;
@@ -305,7 +311,7 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             sm->bw[i] = nb;
             st->bw_array[i] = nb;
         }
-        heaac_sbr_dequant(sm, ch, is_cpe, tid, nt);
+        heaac_sbr_dequant<NT>(sm, ch, is_cpe, tid);
         for (int w = tid; w < 6 * 48; w += nt) {
             int e = w / 48, m = w - e * 48;
             sm->s_idx[e][m] = e == 0 ? st->s_index0[m] : 0;
@@ -441,13 +447,13 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             int delta = !((e == pc->e_a[1]) || (e == pc->e_a[0]));
             float eo = sm->e_orig[e][m], qm = sm->q_map[e][m], ec = sm->e_curr[e][m];
             float temp = heaac_fdiv(eo, heaac_fadd(1.0f, qm));
-            sm->q_m[e][m] = heaac_fsqrt(heaac_fmul(temp, qm));
+            sm->qall[e][m] = heaac_fsqrt(heaac_fmul(temp, qm));
             sm->s_m[e][m] = heaac_fsqrt(heaac_fmul(temp, (float)sm->s_idx[e + 1][m]));
             if (!sm->s_map[e][m])
-                sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(eo, heaac_fmul(heaac_fadd(1.0f, ec),
+                sm->gall[e][m] = heaac_fsqrt(heaac_fdiv(eo, heaac_fmul(heaac_fadd(1.0f, ec),
                                              heaac_fadd(1.0f, heaac_fmul(qm, (float)delta)))));
             else
-                sm->gain[e][m] = heaac_fsqrt(heaac_fdiv(heaac_fmul(eo, qm),
+                sm->gall[e][m] = heaac_fsqrt(heaac_fdiv(heaac_fmul(eo, qm),
                                              heaac_fmul(heaac_fadd(1.0f, ec), heaac_fadd(1.0f, qm))));
         }
         for (int w = tid; w < nenv * p->n_lim; w += nt) {
@@ -465,9 +471,9 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             int e = w / 48, m = w - e * 48;
             if (m >= m_max) continue;
             float gain_max = sm->gmax[e][sm->lim_idx[m]];
-            float q_m_max = heaac_fdiv(heaac_fmul(sm->q_m[e][m], gain_max), sm->gain[e][m]);
-            sm->q_m[e][m]  = HEAAC_MIN(sm->q_m[e][m], q_m_max);
-            sm->gain[e][m] = HEAAC_MIN(sm->gain[e][m], gain_max);
+            float q_m_max = heaac_fdiv(heaac_fmul(sm->qall[e][m], gain_max), sm->gall[e][m]);
+            sm->qall[e][m]  = HEAAC_MIN(sm->qall[e][m], q_m_max);
+            sm->gall[e][m] = HEAAC_MIN(sm->gall[e][m], gain_max);
         }
         HEAAC_SYNC();
         for (int w = tid; w < nenv * p->n_lim; w += nt) {
@@ -476,7 +482,7 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             int lo = p->f_tablelim[k] - kx, hi = p->f_tablelim[k + 1] - kx;
             float sum0 = 0.0f, sum1 = 0.0f;
             for (int m = lo; m < hi; m++) {
-                float g = sm->gain[e][m], s = sm->s_m[e][m], q = sm->q_m[e][m];
+                float g = sm->gall[e][m], s = sm->s_m[e][m], q = sm->qall[e][m];
                 sum0 = heaac_fadd(sum0, sm->e_orig[e][m]);
                 float t3 = heaac_fmul(heaac_fmul((float)(delta && !s), q), q);
                 float acc = heaac_fadd(heaac_fadd(heaac_fmul(heaac_fmul(sm->e_curr[e][m], g), g), heaac_fmul(s, s)), t3);
@@ -492,9 +498,9 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             int e = w / 48, m = w - e * 48;
             if (m >= m_max) continue;
             float gain_boost = sm->gboost[e][sm->lim_idx[m]];
-            const float gf = heaac_fmul(sm->gain[e][m], gain_boost), qf = heaac_fmul(sm->q_m[e][m], gain_boost);
-            sm->gain[e][m] = gf; sm->gall[e][m] = gf;
-            sm->q_m[e][m]  = qf; sm->qall[e][m] = qf;
+            const float gf = heaac_fmul(sm->gall[e][m], gain_boost), qf = heaac_fmul(sm->qall[e][m], gain_boost);
+            sm->gall[e][m] = gf;
+            sm->qall[e][m] = qf;
             sm->s_m[e][m]  = heaac_fmul(sm->s_m[e][m], gain_boost);
         }
         HEAAC_SYNC();
@@ -539,13 +545,17 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
             if (in_hf) heaac_sbr_y(sm, &y, T, i, k - kx, &yre, &yim);
             if (k < kx) { re = sm->xl_re[k][i + 2]; im = sm->xl_im[k][i + 2]; }
             Xre[k * HEAAC_XS + i] = re; Xim[k * HEAAC_XS + i] = im;
-            sm->ynew_re[k][j] = yre; sm->ynew_im[k][j] = yim;
-            sm->ynew_valid[k][j] = (uint8_t)in_hf;
+            if (k >= kx && k < kx + 48) {
+                sm->ynew_re[k - kx][j] = yre; sm->ynew_im[k - kx][j] = yim;
+                sm->ynew_valid[k - kx][j] = (uint8_t)in_hf;
+            }
         }
         HEAAC_SYNC();      /* every read of the old y_tail / g_hist / q_hist is done */
-        for (int w = tid; w < 64 * 8; w += nt) {
-            const int k = w >> 3, j = w & 7;
-            if (j < 6 && sm->ynew_valid[k][j]) { st->y_tail[w] = sm->ynew_re[k][j]; st->y_tail[512 + w] = sm->ynew_im[k][j]; }
+        for (int w = tid; w < 48 * 8; w += nt) {
+            const int m = w >> 3, j = w & 7, k = kx + m;
+            if (j < 6 && k < 64 && sm->ynew_valid[m][j]) {
+                st->y_tail[k * 8 + j] = sm->ynew_re[m][j]; st->y_tail[512 + k * 8 + j] = sm->ynew_im[m][j];
+            }
         }
         if (p->start) {
             /* g_temp / q_temp rows 32..41 for the next frame, aacsbr.c:1642-1647 */
@@ -554,8 +564,8 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
                 int src = r - y.h_SL;
                 if (m < m_max && src >= i_lo && src < i_hi) {
                     int es = sm->env_of_slot[src];
-                    st->g_hist[w] = sm->gain[es][m];
-                    st->q_hist[w] = sm->q_m[es][m];
+                    st->g_hist[w] = sm->gall[es][m];
+                    st->q_hist[w] = sm->qall[es][m];
                 }
             }
             for (int m = tid; m < 48; m += nt) st->s_index0[m] = sm->s_idx[nenv][m];

@@ -97,13 +97,13 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             memset(c->sm_core, 0xA5, sizeof(HeaacCoreSmem));      /* poison "shared memory" */
             memset(x, 0xA5, sizeof(x));
             if (ana) memcpy(x, st->ana_hist, 288 * sizeof(float));
-            heaac_core_channel(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
-                               g.sr_index, c->T, 0, 1);
+            heaac_core_channel<1>(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
+                               g.sr_index, c->T, 0);
             if (ana) {
                 const float ana_scale = 1 / qmf_scale;
                 if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
                 memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
-                heaac_qmf_analysis(x, x + 1312, c->W + gc * 2048, c->T, 0, 1);
+                heaac_qmf_analysis<1>(x, x + 1312, c->W + gc * 2048, c->T, 0);
             } else if (!g.sbr) for (int i = 0; i < 1024; i++) {
                 if (pc) pc[(s * 1024 + i) * g.nout + g.out_slot[ch]] = heaac_to_s16(out[i], g.add_bias != 0.0f);
                 if (pf) pf[(s * g.nout + g.out_slot[ch]) * 1024 + i] = out[i];
@@ -115,15 +115,15 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             int se = g.ch_sbr_elem[ch];
             if (se == 0xff) continue;
             memset(c->sm_sbr, 0xA5, sizeof(HeaacHfSmem));
-            heaac_hf_channel(c->sm_sbr, c->W + gc * 2048, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
-                             c->chan + gc, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, c->T, 0, 1);
+            heaac_hf_channel<1>(c->sm_sbr, c->W + gc * 2048, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
+                             c->chan + gc, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, c->T, 0);
         }
         if (g.ps)
             for (size_t s = 0; s < S; s++) {                      /* k_ps */
                 float *XL = c->X + s * 2 * (HEAAC_X_FLOATS), *XR = XL + HEAAC_X_FLOATS;
                 const HeaacSbrElem *e = sb + s * g.nse;
                 memset(c->sm_ps, 0xA5, sizeof(HeaacPsSmem));
-                heaac_ps_stream(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0, 1);
+                heaac_ps_stream<1>(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0);
             }
         for (size_t s = 0; s < S; s++) {                          /* k_synth: one CTA per (stream, SBR element) */
             int o = 0;
@@ -133,10 +133,10 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
                     int no = g.ps ? 2 : nch;
                     size_t go = s * g.nout + o;
                     memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
-                    heaac_synth_stream(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no,
+                    heaac_synth_stream<1>(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no,
                                        g.out_slot[o], g.out_slot[o + (no > 1)],
                                        pc ? pc + s * 2048 * g.nout : nullptr, pf ? pf + s * g.nout * 2048 : nullptr,
-                                       qmf_scale, g.add_bias, c->T, 0, 1);
+                                       qmf_scale, g.add_bias, c->T, 0);
                 }
                 o += nch;
             }
