@@ -47,6 +47,7 @@ struct HeaacContext {
     cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
     long long launches;
     size_t smem_core, smem_sbr, smem_ps, smem_synth;
+    int core_grid;                   /* persistent k_core: resident CTAs on the whole GPU */
     /* optional per-kernel event timing (heaac_b200_profile_*) */
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;            /* 2 events per recorded launch */
@@ -69,44 +70,60 @@ static void prof_end(HeaacContext *c)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Persistent: each CTA walks channels gc = blockIdx.x, + gridDim.x, ... and stages the NEXT channel's
+ * coefficients into the other half of a double buffer with cp.async while it works on the current one. */
 __global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
-k_core(HeaacGeom g, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
+k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
        const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
-    float *x = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [288 history | 1024 new] */
+    float *stage = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [2][1024] */
+    float *x = stage + 2048;                         /* [288 history | 1024 new] (+ 64*33 analysis scratch) */
     float *out = x + 288;
-    const int gc = blockIdx.x;                       /* global core channel = s * ncc + c */
-    const int s = gc / g.ncc, c = gc - s * g.ncc;
     const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
-    HeaacChanState *st = chan + gc;
-    const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
-    if (ana)
-        for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
-    heaac_core_channel<HEAAC_THREADS>(sm, coeffs + (size_t)gc * 1024, ics + gc, tns ? tns + gc : nullptr,
-                       st, out, bias, g.sr_index, T, threadIdx.x);
-    if (ana) {
-        /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
-        const float ana_scale = 1 / (-1024.0f * g.sf_scale);                   /* aacsbr.c:1730 */
-        if (ana_scale != 1.0f) {
-            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) out[i] = out[i] * ana_scale;
-            __syncthreads();
+    int gc = blockIdx.x;
+    if (gc < n_channels)
+        heaac_cp_async16(stage + 4 * threadIdx.x, coeffs + (size_t)gc * 1024 + 4 * threadIdx.x);
+    heaac_cp_async_commit();
+    for (int it = 0; gc < n_channels; gc += gridDim.x, it++) {
+        const int s = gc / g.ncc, c = gc - s * g.ncc;
+        HeaacChanState *st = chan + gc;
+        const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
+        float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
+        const int gn = gc + gridDim.x;
+        if (gn < n_channels)
+            heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
+        heaac_cp_async_commit();
+        if (ana)
+            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
+        heaac_cp_async_wait<1>();                    /* everything but the group just committed has landed */
+        __syncthreads();
+        heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
+                                          st, out, bias, g.sr_index, T, threadIdx.x);
+        if (ana) {
+            /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
+            const float ana_scale = 1 / (-1024.0f * g.sf_scale);               /* aacsbr.c:1730 */
+            if (ana_scale != 1.0f) {
+                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) out[i] = out[i] * ana_scale;
+                __syncthreads();
+            }
+            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
+            float *tb = x + 1312;
+            heaac_qmf_analysis<HEAAC_THREADS>(x, tb, W + (size_t)gc * 2048, T, threadIdx.x);
+        } else if (!g.sbr) {
+            const int bias_mode = g.add_bias != 0.0f;
+            if (pcm) {
+                int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
+                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
+            }
+            if (pcm_f32) {
+                float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
+                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
+            }
         }
-        for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
-        float *tb = x + 1312;
-        heaac_qmf_analysis<HEAAC_THREADS>(x, tb, W + (size_t)gc * 2048, T, threadIdx.x);
-    } else if (!g.sbr) {
-        const int bias_mode = g.add_bias != 0.0f;
-        if (pcm) {
-            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
-            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
-        }
-        if (pcm_f32) {
-            float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
-            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
-        }
+        __syncthreads();                             /* x / tb / stage are reused by the next channel */
     }
 }
 
@@ -321,7 +338,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
         }
     }
 
-    c->smem_core = sizeof(HeaacCoreSmem) + (g->sbr ? 1312 + 64 * 33 : 1312) * sizeof(float);
+    c->smem_core = sizeof(HeaacCoreSmem) + (2048 + (g->sbr ? 1312 + 64 * 33 : 1312)) * sizeof(float);
     c->smem_sbr = sizeof(HeaacHfSmem);
     c->smem_ps = sizeof(HeaacPsSmem);
     c->smem_synth = sizeof(HeaacSynthSmem);
@@ -329,6 +346,11 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     CKX(cudaFuncSetAttribute(k_sbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sbr));
     CKX(cudaFuncSetAttribute(k_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_ps));
     CKX(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_synth));
+    {
+        int per_sm = 0;
+        CKX(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_core, HEAAC_THREADS, c->smem_core));
+        c->core_grid = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+    }
     r = init_state(c);
     if (r) { heaac_b200_destroy(c); return r; }
 #undef CKX
@@ -388,8 +410,12 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
         int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
         float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
         prof_begin(c, HEAAC_K_CORE);
-        k_core<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_core, c->stream>>>(
-            g, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+        {
+            const unsigned n_ch = (unsigned)(S * g.ncc);
+            const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
+            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(
+                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+        }
         prof_end(c);
         c->launches++;
         if (g.sbr) {

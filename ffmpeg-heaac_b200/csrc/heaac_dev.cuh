@@ -44,6 +44,27 @@ __device__ __forceinline__ float heaac_fsqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ float heaac_rint(float a) { return rintf(a); }
 #endif
 
+/* ---- asynchronous global -> shared copies (LDGSTS): issue early, wait right before first use ---- */
+#ifdef HEAAC_HOST_EMU
+static inline void heaac_cp_async4(float *dst, const float *src) { *dst = *src; }
+static inline void heaac_cp_async16(float *dst, const float *src) { memcpy(dst, src, 16); }
+static inline void heaac_cp_async_commit() {}
+template <int N> static inline void heaac_cp_async_wait() {}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void heaac_cp_async4(float *dst, const float *src)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void heaac_cp_async16(float *dst, const float *src)     /* both 16-byte aligned */
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void heaac_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void heaac_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
+
 /* ---- read-only tables, built on the host (heaac_tables.cpp) and copied to HBM once ---- */
 struct HeaacDevTables {
     float sine_1024[1024], sine_128[128], kbd_1024[1024], kbd_128[128];   /* aacdec.c:593-596 */

@@ -146,7 +146,6 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
  * AAC-LC core: TNS + IMDCT + windowing + overlap-add for one channel-frame
  * ================================================================================== */
 struct HeaacCoreSmem {
-    float c[1024];          /* coefficients, then the half-IMDCT output ("buf") */
     float zr[512], zi[512];
     float temp[128];
     float lpc[8][HEAAC_TNS_MAX_ORDER];
@@ -166,9 +165,11 @@ HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const flo
     }
 }
 
-/* `out` : 1024 floats in shared or global memory (time-domain output, bias included) */
+/* `c`   : 1024 coefficients of this channel-frame, already staged in shared memory; overwritten (TNS in
+ *         place, then the half-IMDCT output "buf")
+ * `out` : 1024 floats in shared or global memory (time-domain output, bias included) */
 template <int NT>
-HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT coeffs,
+HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
                                   const HeaacIcs *HEAAC_RESTRICT ics_p, const HeaacTns *HEAAC_RESTRICT tns,
                                   HeaacChanState *st, float *out, float bias, int sr_index,
                                   const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
@@ -177,8 +178,6 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
     const HeaacIcs ics = *ics_p;
     const int ws0 = ics.window_sequence, ws1 = st->prev_ws, shape_prev = st->prev_shape;
     const int is8 = ws0 == HEAAC_EIGHT_SHORT;
-
-    for (int i = tid; i < 1024; i += nt) sm->c[i] = coeffs[i];
 
     /* ---- TNS: set up the (at most 8) independent filters, aacdec.c:1701-1728 ---- */
     const int use_tns = ics.tns_present && tns;
@@ -230,11 +229,11 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
             int start = sm->tns_start[slot], inc = sm->tns_inc[slot], order = sm->tns_order[slot];
             const float *lpc = sm->lpc[slot];
             for (int m = 0; m < size; m++, start += inc) {
-                float acc = sm->c[start];
+                float acc = c[start];
                 int lim = HEAAC_MIN(m, order);
                 for (int i = 1; i <= lim; i++)
-                    acc -= sm->c[start - i * inc] * lpc[i - 1];
-                sm->c[start] = acc;
+                    acc -= c[start - i * inc] * lpc[i - 1];
+                c[start] = acc;
             }
         }
         HEAAC_SYNC();
@@ -242,12 +241,12 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, const float *HEAAC_RESTRICT
 
     /* ---- half IMDCT: 1 x N=2048 or 8 x N=256, aacdec.c:1755-1763 ---- */
     if (is8)
-        heaac_imdct_half_smem<NT>(sm->c, sm->c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid);
+        heaac_imdct_half_smem<NT>(c, c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid);
     else
-        heaac_imdct_half_smem<NT>(sm->c, sm->c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid);
+        heaac_imdct_half_smem<NT>(c, c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid);
 
     /* ---- windowing + overlap-add, aacdec.c:1771-1805 ---- */
-    const float *buf = sm->c;
+    const float *buf = c;
     float *saved = st->saved;
     const float *sw      = ics.window_shape ? T->kbd_128 : T->sine_128;
     const float *lw_prev = shape_prev ? T->kbd_1024 : T->sine_1024;
@@ -717,10 +716,11 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
 {
     constexpr int nt = NT;
     const int nthr = 64 * nout;
-    for (int w = tid; w < nout * 1152; w += nt) {          /* history: blocks 32..40 */
+    for (int w = tid; w < nout * 1152; w += nt) {          /* history -> blocks 32..40, asynchronously: first needed in phase 3 */
         int c = w / 1152, r = w - c * 1152;
-        sm->ch[c][(32 + (r >> 7)) * HEAAC_V_STRIDE + (r & 127)] = st[c].v[r];
+        heaac_cp_async4(&sm->ch[c][(32 + (r >> 7)) * HEAAC_V_STRIDE + (r & 127)], &st[c].v[r]);
     }
+    heaac_cp_async_commit();
     /* ---- phase 1: 64 transforms per channel ---- */
     for (int t = tid; t < nthr; t += nt) {
         const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
@@ -752,6 +752,7 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
             v[64 + n]  =  p2 + q2;
         }
     }
+    heaac_cp_async_wait<0>();
     HEAAC_SYNC();
     /* ---- phase 3: windowing, out[n] = sum_j v[off_j + n] w[64 j + n] (aacsbr.c:1215-1227) ---- */
     const int scale_and_bias = scale != 1.0f || bias != 0.0f;

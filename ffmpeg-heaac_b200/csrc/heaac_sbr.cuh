@@ -196,6 +196,12 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
                                 const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
     constexpr int nt = NT;
+    /* this frame's W goes straight into X_low slots 8..39, asynchronously; bands >= kx are cleared once kx is known */
+    for (int w = tid; w < 2 * 32 * 32; w += nt) {
+        const int pl = w >> 10, k = (w >> 5) & 31, i = w & 31;
+        heaac_cp_async4(pl ? &sm->xl_im[k][8 + i] : &sm->xl_re[k][8 + i], W_in + w);
+    }
+    heaac_cp_async_commit();
     {
         const uint32_t *src = (const uint32_t *)elem;
         uint32_t *dst = (uint32_t *)&sm->p;
@@ -210,14 +216,6 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
 
     const int warp = HEAAC_WARP(tid, nt), nwarps = HEAAC_NWARPS(nt), lane = HEAAC_LANE(tid, nt), ls = HEAAC_LSTRIDE(nt);
     /* ---- sbr_lf_gen: X_low[k][i] = W[k][i - 8] (i >= 8, k < kx) | previous frame's W[k][24 + i] (i < 8, k < kx') ---- */
-    for (int k = warp; k < 32; k += nwarps) {             /* slots 8..39 = this frame's W[k][0..31]: one full warp per row */
-        const int cur = k < kx;
-        const float *wr = W_in + k * 32, *wi = wr + 1024;
-        for (int i = lane; i < 32; i += ls) {
-            sm->xl_re[k][8 + i] = cur ? wr[i] : 0.0f;
-            sm->xl_im[k][8 + i] = cur ? wi[i] : 0.0f;
-        }
-    }
     for (int w = tid; w < 32 * 8; w += nt) {               /* slots 0..7 = previous frame's W[k][24..31] */
         const int k = w >> 3, i = w & 7, old = k < kx0;
         sm->xl_re[k][i] = old ? st->w_tail[w] : 0.0f;
@@ -279,10 +277,14 @@ HEAAC_DEV void heaac_hf_channel(HeaacHfSmem *sm, const float *HEAAC_RESTRICT W_i
         sm->qall[5 + r][m] = r < 10 ? st->q_hist[w] : 0.0f;
     }
     HEAAC_SYNC();
+    heaac_cp_async_wait<0>();
+    HEAAC_SYNC();
     for (int w = tid; w < 2 * 32 * 8; w += nt) {           /* next frame's W tail: slots 24..31, all 32 bands */
         const int pl = w >> 8, k = (w >> 3) & 31, i = w & 7;
-        st->w_tail[pl * 256 + k * 8 + i] = W_in[pl * 1024 + k * 32 + 24 + i];
+        st->w_tail[pl * 256 + k * 8 + i] = pl ? sm->xl_im[k][32 + i] : sm->xl_re[k][32 + i];
     }
+    /* (sbr_lf_gen zeroes bands >= kx; nothing below ever reads those rows: the LPC uses k < k0 <= kx, the
+     *  patches copy from below k0, and X generation takes the low band only for k < kx) */
 
     if (p->start) {
         /* ---- autocorrelation: five independent 37-term chains per low band, aacsbr.c:1232-1255 ---- */

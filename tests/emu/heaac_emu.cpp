@@ -97,7 +97,9 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             memset(c->sm_core, 0xA5, sizeof(HeaacCoreSmem));      /* poison "shared memory" */
             memset(x, 0xA5, sizeof(x));
             if (ana) memcpy(x, st->ana_hist, 288 * sizeof(float));
-            heaac_core_channel<1>(c->sm_core, co + gc * 1024, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
+            static float cbuf[1024];
+            memcpy(cbuf, co + gc * 1024, sizeof(cbuf));           /* the kernel stages the coefficients with cp.async */
+            heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
                                g.sr_index, c->T, 0);
             if (ana) {
                 const float ana_scale = 1 / qmf_scale;

@@ -9,7 +9,7 @@ h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]; ci = hdr.index("Instructions Executed"); si = hdr.index("Source")
 mix = {}; tot = 0
 for r in rows[h + 1:]:
-    if len(r) <= ci: continue
+    if len(r) <= ci or r[0] == "Address": continue
     m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[si])
     if not m: continue
     op = m.group(2); n = int(float(r[ci] or 0))
