@@ -21,6 +21,9 @@
 extern "C" void heaac_build_tables(HeaacDevTables *t);
 
 #define HEAAC_THREADS 256
+#ifndef HEAAC_SBR_THREADS
+#define HEAAC_SBR_THREADS 256
+#endif
 #ifndef HEAAC_CORE_MIN_BLOCKS
 #define HEAAC_CORE_MIN_BLOCKS 4
 #endif
@@ -127,7 +130,10 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
     }
 }
 
-__global__ void __launch_bounds__(HEAAC_THREADS)
+#ifndef HEAAC_SBR_MIN_BLOCKS
+#define HEAAC_SBR_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(HEAAC_SBR_THREADS, HEAAC_SBR_MIN_BLOCKS)
 k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__ sbr,
       HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T)
 {
@@ -138,7 +144,7 @@ k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__
     const int se = g.ch_sbr_elem[c];
     if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
     float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
-    heaac_hf_channel<HEAAC_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
+    heaac_hf_channel<HEAAC_SBR_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
                      g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x);
 }
 
@@ -421,7 +427,7 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
             prof_begin(c, HEAAC_K_SBR);
-            k_sbr<<<(unsigned)(S * g.ncc), HEAAC_THREADS, c->smem_sbr, c->stream>>>(
+            k_sbr<<<(unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(
                 g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables);
             prof_end(c);
             c->launches++;
