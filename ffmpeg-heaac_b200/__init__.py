@@ -30,6 +30,7 @@ EXPORTS = [
     "heaac_b200_debug_read", "heaac_b200_mdct_init", "heaac_b200_imdct_half", "heaac_b200_mdct_end",
     "heaac_b200_version", "heaac_b200_strerror", "heaac_b200_sizeof", "heaac_b200_sbr_tables",
     "heaac_b200_profile_enable", "heaac_b200_profile_read",
+    "heaac_fe_open", "heaac_fe_close", "heaac_fe_parse", "heaac_fe_info",
 ]
 
 
@@ -73,6 +74,11 @@ def lib():
         L.heaac_b200_strerror.restype = C.c_char_p
         L.heaac_b200_sizeof.argtypes = [C.c_char_p]
         L.heaac_b200_sbr_tables.argtypes = [C.c_int] * 8 + [C.c_void_p]
+        L.heaac_fe_open.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.heaac_fe_close.argtypes = [C.c_void_p]
+        L.heaac_fe_close.restype = None
+        L.heaac_fe_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.heaac_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
         for name, size in abi.SIZES.items():
@@ -226,6 +232,47 @@ def sbr_tables(core_sample_rate, start_freq, stop_freq, xover=0, freq_scale=2, a
                                     noise_bands, limiter_bands, e.ctypes.data)
     _check(r, "heaac_b200_sbr_tables")
     return e
+
+
+class Frontend:
+    """The repo's own host parser for one stream (heaac_fe_*): packets -> per-frame C-ABI structures.
+    Mirrors what the reference's aac_decode_frame does up to spectral_to_sample (aacdec.c:1973-2076)."""
+
+    def __init__(self, extradata=b"", sample_rate=0, channels=0, bias_mode=False):
+        h = C.c_void_p()
+        ed = np.frombuffer(extradata, np.uint8).copy() if extradata else np.zeros(0, np.uint8)
+        _check(lib().heaac_fe_open(C.byref(h), ed.ctypes.data if ed.size else None, ed.size, sample_rate, channels,
+                                   int(bool(bias_mode))), "heaac_fe_open")
+        self.h = h.value
+        self._refresh()
+
+    def _refresh(self):
+        v = [C.c_int() for _ in range(5)]
+        et = (C.c_uint8 * 8)()
+        n = lib().heaac_fe_info(self.h, *[C.byref(x) for x in v], et)
+        self.ncc, self.nse, self.sbr, self.ps, self.sr_index = [x.value for x in v]
+        self.elem_types = [int(et[i]) for i in range(max(n, 0))]
+
+    def parse(self, pkt):
+        """Returns dict(coeffs [ncc,1024], ics [ncc], tns [ncc], sbr [nse], ps [1], consumed)."""
+        buf = np.frombuffer(pkt, np.uint8)
+        # sized for the largest configuration: an ADTS header inside this very packet may (re)configure the stream
+        r = {"coeffs": np.zeros((16, 1024), np.float32), "ics": np.zeros(16, ICS), "tns": np.zeros(16, TNS),
+             "sbr": np.zeros(8, SBR_ELEM), "ps": np.zeros(1, PS_FRAME)}
+        n = lib().heaac_fe_parse(self.h, buf.ctypes.data, buf.size, r["coeffs"].ctypes.data, r["ics"].ctypes.data,
+                                 r["tns"].ctypes.data, r["sbr"].ctypes.data, r["ps"].ctypes.data)
+        _check(n, "heaac_fe_parse")
+        self._refresh()
+        for k in ("coeffs", "ics", "tns"):
+            r[k] = r[k][:max(self.ncc, 1)]
+        r["sbr"] = r["sbr"][:max(self.nse, 1)]
+        r["consumed"] = n
+        return r
+
+    def close(self):
+        if self.h:
+            lib().heaac_fe_close(self.h)
+            self.h = None
 
 
 class Mdct:

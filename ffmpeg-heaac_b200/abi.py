@@ -13,7 +13,7 @@ ONLY_LONG, LONG_START, EIGHT_SHORT, LONG_STOP = 0, 1, 2, 3
 
 ICS = np.dtype([
     ("window_sequence", "u1"), ("window_shape", "u1"), ("max_sfb", "u1"), ("tns_present", "u1"),
-    ("reserved", "u1", (4,)),
+    ("prev_valid", "u1"), ("prev_window_sequence", "u1"), ("prev_window_shape", "u1"), ("reserved", "u1"),
 ], align=True)
 
 TNS = np.dtype([

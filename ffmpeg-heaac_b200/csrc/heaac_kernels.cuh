@@ -176,7 +176,9 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
 {
     constexpr int nt = NT;
     const HeaacIcs ics = *ics_p;
-    const int ws0 = ics.window_sequence, ws1 = st->prev_ws, shape_prev = st->prev_shape;
+    const int ws0 = ics.window_sequence;
+    const int ws1 = ics.prev_valid ? (int)ics.prev_window_sequence : st->prev_ws;
+    const int shape_prev = ics.prev_valid ? (int)ics.prev_window_shape : st->prev_shape;
     const int is8 = ws0 == HEAAC_EIGHT_SHORT;
 
     /* ---- TNS: set up the (at most 8) independent filters, aacdec.c:1701-1728 ---- */

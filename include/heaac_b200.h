@@ -57,7 +57,14 @@ typedef struct HeaacIcs {
     uint8_t window_shape;      /* ics.use_kb_window[0]: 1 = KBD, 0 = sine        */
     uint8_t max_sfb;           /* ics.max_sfb                                    */
     uint8_t tns_present;       /* tns.present                                    */
-    uint8_t reserved[4];
+    /* Optional: the parser's own record of the previous frame (ics.window_sequence[1], ics.use_kb_window[1]).
+     * When prev_valid == 0 the back end uses what it saw in the previous frame of this channel; a front end that
+     * mirrors the reference's bookkeeping exactly (a CPE with common_window copies channel 0's previous sequence
+     * to channel 1, aacdec.c:1467-1469) sets prev_valid = 1. */
+    uint8_t prev_valid;
+    uint8_t prev_window_sequence;
+    uint8_t prev_window_shape;
+    uint8_t reserved;
 } HeaacIcs;
 
 /* TNS filters in bitstream order.  Long blocks: window 0 holds up to 3 filters in slots
@@ -252,6 +259,28 @@ int  heaac_b200_debug_read(HeaacContext *ctx, const char *name, void *dst, size_
 int  heaac_b200_sbr_tables(int core_sample_rate, int bs_start_freq, int bs_stop_freq, int bs_xover_band,
                            int bs_freq_scale, int bs_alter_scale, int bs_noise_bands, int bs_limiter_bands,
                            HeaacSbrElem *out);
+
+/* ---- host front end (own C): packets -> per-frame structures -------------------------------
+ * One HeaacFrontend per stream plays the role of the reference's parsers up to the spectral_to_sample()
+ * call site (aacdec.c:1973-2076 element loop, decode_ics / decode_cpe, ff_decode_sbr_extension,
+ * ff_ps_read_data): heaac_fe_parse() takes one packet (bare raw_data_block, or an ADTS frame) and fills the
+ * frame's coeffs / HeaacIcs / HeaacTns / HeaacSbrElem / HeaacPsFrame, ready for heaac_b200_synth().
+ * Pure host code (no GPU); different front ends may be driven from different threads.
+ * extradata = AudioSpecificConfig (may be NULL for ADTS); bias_mode selects the scaling convention
+ * (0: s16 units, sf_scale = -1/1024; 1: the C "bias" path, aacdec.c:573-576). */
+typedef struct HeaacFrontend HeaacFrontend;
+int  heaac_fe_open(HeaacFrontend **fe, const uint8_t *extradata, int extradata_size, int sample_rate, int channels,
+                   int bias_mode);
+void heaac_fe_close(HeaacFrontend *fe);
+/* returns bytes consumed (>= 0) or a negative HEAAC_E_* code; sbr / ps / tns may be NULL.  Arrays are indexed by
+ * core channel (coeffs [n_core_ch][1024], ics, tns) and by element (sbr); a stream configured in-band (ADTS)
+ * can change layout inside the call, so size them for 16 channels / HEAAC_MAX_ELEMS elements in that case. */
+int  heaac_fe_parse(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                    HeaacSbrElem *sbr, HeaacPsFrame *ps);
+/* layout of the stream: returns the number of elements and fills the optional outputs; sbr / ps reflect
+ * implicit signalling once the first frame has been parsed (aacdec.c:1659-1676) */
+int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,
+                   uint8_t elem_type[HEAAC_MAX_ELEMS]);
 
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */

@@ -98,6 +98,9 @@ static void pack_ics(HeaacIcs *o, const SingleChannelElement *sce)
     o->window_shape    = sce->ics.use_kb_window[0];
     o->max_sfb         = sce->ics.max_sfb;
     o->tns_present     = sce->tns.present;
+    o->prev_valid = 1;
+    o->prev_window_sequence = sce->ics.window_sequence[1];
+    o->prev_window_shape    = sce->ics.use_kb_window[1];
 }
 
 static void pack_tns(HeaacTns *o, const SingleChannelElement *sce)

@@ -1,0 +1,145 @@
+"""The repo's own host front end (heaac_fe_*, csrc/heaac_frontend.c): packets -> C-ABI frame structures.
+
+Pinned (1) against the committed golden captures of what the REFERENCE's parsers handed to spectral_to_sample
+(aacdec.c:2078) for the same packets, (2) where oracle/_ref is available, against the reference's parsers on
+fresh streams, and (3) end to end: own front end -> oracle / CUDA back end -> PCM vs the reference decoder's
+output.  With (3) the reference is not on the path at all."""
+import numpy as np
+import pytest
+
+import ffmpeg_heaac_b200 as hb
+import pyoracle
+from common import (GOLDEN_CASES, abi, assert_pcm_close, diff_parsed, golden_config, golden_packets, golden_ref_pcm,
+                    load_golden)
+from conftest import needs_ref
+
+
+def parse_golden(d):
+    n_ch = d["coeffs"].shape[1]
+    out_ch = d["pcm_f32"].shape[1]
+    fe = hb.Frontend(d["extradata"].tobytes(), int(d["core_rate"]), out_ch if not d["ps_flag"] else 1)
+    frames = [fe.parse(p) for p in golden_packets(d)]
+    return fe, frames, n_ch
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_frontend_reproduces_reference_parser_on_golden_packets(name):
+    d = load_golden(name)
+    fe, frames, n_ch = parse_golden(d)
+    assert fe.ncc == n_ch and fe.sr_index == int(d["sr_index"])
+    assert fe.elem_types == [int(x) for x in d["elem_types"]]
+    assert bool(fe.sbr) == bool(d["sbr_flag"]) and bool(fe.ps) == bool(d["ps_flag"])
+    for t, (m, size) in enumerate(zip(frames, d["pkt_sizes"])):
+        ref = {k: d[k][t] for k in ("coeffs", "ics", "tns", "sbr", "ps")}
+        bad = diff_parsed(ref, m, n_ch, bool(d["sbr_flag"]), bool(d["ps_flag"]))
+        assert not bad, "%s frame %d: %s" % (name, t, bad[:6])
+        assert m["consumed"] == int(size)
+    fe.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_frontend_plus_oracle_reproduces_reference_pcm(name):
+    d = load_golden(name)
+    fe, frames, n_ch = parse_golden(d)
+    st = lambda k: np.ascontiguousarray(np.stack([f[k] for f in frames])[:, None])
+    cfg = abi.make_config(1, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames))
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), st("sbr") if fe.sbr else None,
+                         st("ps")[:, :, 0] if fe.ps else None)
+    orc.close(); fe.close()
+    ref_f32, ref_s16 = golden_ref_pcm(d)
+    assert_pcm_close(f32[:, 0], ref_f32, pcm[:, 0], ref_s16, name)
+
+
+def test_frontend_rejects_bad_input():
+    fe = hb.Frontend(b"", 0, 0)                      # no extradata: the configuration must come from an ADTS header
+    with pytest.raises(RuntimeError):
+        fe.parse(bytes([0x21, 0x00, 0x49, 0x90]))    # ... and this is not one (aacdec.c:1994-2006)
+    fe.close()
+    fe = hb.Frontend(bytes([0x12, 0x10]), 44100, 2)  # AAC-LC 44.1 kHz stereo
+    with pytest.raises(RuntimeError):
+        fe.parse(b"")                                # empty packet
+    with pytest.raises(RuntimeError):
+        fe.parse(bytes([0xFF] * 7))                  # element id 7 == END with nothing decoded / overread
+    fe.close()
+
+
+def test_frontend_bias_mode_scales_coefficients():
+    """bias_mode front end = the reference's C output path (sf_scale 1/32768 folded into the spectrum, aacdec.c:573-581)."""
+    d = load_golden("lc_stereo_44k")
+    pk = golden_packets(d)
+    a = hb.Frontend(d["extradata"].tobytes(), 44100, 2, bias_mode=False)
+    b = hb.Frontend(d["extradata"].tobytes(), 44100, 2, bias_mode=True)
+    for p in pk[:4]:
+        ca, cb = a.parse(p)["coeffs"], b.parse(p)["coeffs"]
+        nz = ca != 0
+        assert nz.any() and np.allclose(cb[nz] / ca[nz], 1.0 / 32768.0, rtol=1e-6)
+    a.close(); b.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,seed", [("lc", 3), ("51", 4), ("v1", 111), ("v1", 112), ("v2", 211), ("v2", 212), ("v2", 213)])
+def test_frontend_matches_reference_parser_on_fresh_streams(mode, seed):
+    import heaac_streams as hs
+    import pyref
+    nfr = 24
+    if mode in ("lc", "51"):
+        ch, rate, layout = (2, 44100, "stereo") if mode == "lc" else (6, 48000, "5.1")
+        pcm = pyref.lcg_noise(1024 * (nfr + 1), ch, seed=seed).astype(np.int32)
+        for s0 in (5000, 12000, 13500, 22000):
+            pcm[s0:s0 + 300] *= 8                     # attacks: block switching, TNS
+        enc = pyref.Encoder(rate, ch, 64000 * ch)
+        pkts, ed = enc.encode(np.clip(pcm, -32768, 32767).astype(np.int16))[:nfr], enc.extradata
+        enc.close()
+    else:
+        stereo = mode == "v1"
+        pkts, ed, _ = hs.make_stream(seed, nfr, stereo=stereo, ps=mode == "v2")
+        ch, rate, layout = (2, 24000, "stereo") if stereo else (1, 24000, "mono")
+    ref = pyref.Decoder(ed, rate, ch, layout)
+    fe = hb.Frontend(ed, rate, ch)
+    for t, p in enumerate(pkts):
+        r, m = ref.decode(p), fe.parse(p)
+        bad = diff_parsed(r, m, fe.ncc, ref.sbr == 1, ref.ps == 1 and ch == 1)
+        assert not bad, "%s/%d frame %d: %s" % (mode, seed, t, bad[:6])
+        assert r["consumed"] == m["consumed"]
+    ref.close(); fe.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_frontend_plus_cuda_reproduces_reference_pcm(name):
+    """packets -> own parser -> CUDA back end -> PCM, against the reference decoder's PCM for those packets."""
+    d = load_golden(name)
+    fe, frames, n_ch = parse_golden(d)
+    S = 2
+    st = lambda k: np.ascontiguousarray(np.repeat(np.stack([f[k] for f in frames])[:, None], S, axis=1))
+    cfg = abi.make_config(S, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames))
+    ctx = hb.Context(cfg)
+    pcm, f32 = ctx.synth(st("coeffs"), st("ics"), st("tns"), st("sbr") if fe.sbr else None,
+                         st("ps")[:, :, 0] if fe.ps else None, want_float=True)
+    assert ctx.launch_count > 0
+    ctx.close(); fe.close()
+    ref_f32, ref_s16 = golden_ref_pcm(d)
+    for s in range(S):
+        assert_pcm_close(f32[:, s], ref_f32, pcm[:, s], ref_s16, "%s stream %d" % (name, s))
+
+
+def adts_wrap(pkt, sr_index, chan_config, profile=1):
+    n = len(pkt) + 7
+    bits = (0xFFF << 44) | (0 << 43) | (0 << 41) | (1 << 40) | (profile << 38) | (sr_index << 34) | (0 << 33) | \
+           (chan_config << 30) | (0 << 26) | (n << 13) | (0x7FF << 2) | 0
+    return bits.to_bytes(7, "big") + pkt
+
+
+@pytest.mark.parametrize("name,chan_config", [("lc_stereo_44k", 2), ("lc_51_48k", 6)])
+def test_frontend_adts_framing_equals_raw_with_extradata(name, chan_config):
+    """ADTS-framed input with no extradata (aacdec.c:1994-2006, parse_adts_frame_header 1925-1960)."""
+    d = load_golden(name)
+    raw = hb.Frontend(d["extradata"].tobytes(), int(d["core_rate"]), chan_config)
+    adts = hb.Frontend(b"", 0, 0)
+    for p in golden_packets(d):
+        a, b = raw.parse(p), adts.parse(adts_wrap(p, int(d["sr_index"]), chan_config))
+        assert b["consumed"] == a["consumed"] + 7
+        assert adts.ncc == raw.ncc and adts.elem_types == raw.elem_types and adts.sr_index == raw.sr_index
+        assert not diff_parsed(a, b, raw.ncc, False, False)
+    raw.close(); adts.close()
