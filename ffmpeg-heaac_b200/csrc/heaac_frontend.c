@@ -70,7 +70,7 @@ static int vlc_get(BR *b, const Vlc *v)
 }
 
 static Vlc vlc_sf, vlc_spec[11], vlc_sbr[10], vlc_ps[10];
-static float pow2sf_tab[428], pow43_tab[8192];
+static float pow2sf_tab[428], pow43_tab[8192], cb_val[16];
 static int tables_ready;
 static const int spec_sizes[11] = { 81, 81, 81, 81, 81, 81, 64, 64, 169, 169, 289 };
 
@@ -98,7 +98,9 @@ static void fe_tables(void)
     VB(vlc_ps[PS_IPD_DF], heaac_ps_huff_ipd_df); VB(vlc_ps[PS_IPD_DT], heaac_ps_huff_ipd_dt);
     VB(vlc_ps[PS_OPD_DF], heaac_ps_huff_opd_df); VB(vlc_ps[PS_OPD_DT], heaac_ps_huff_opd_dt);
     for (int i = 0; i < 428; i++) pow2sf_tab[i] = pow(2, (i - 200) / 4.);      /* aac_tablegen.h:33-38 */
-    for (int i = 0; i < 8192; i++) pow43_tab[i] = cbrtf(i) * i;               /* cbrt_tablegen.h:35-44 */
+    for (int i = 0; i < 8192; i++) pow43_tab[i] = cbrtf(i) * i;               /* escapes: cbrt_tablegen.h:35-44 */
+    for (int i = 0; i < 16; i++) cb_val[i] = (float)pow(i, 4.0 / 3.0);        /* in-book values: correctly rounded
+                                                                                  * literals of codebook_vector*_vals, aactab.c:899-1008 */
     tables_ready = 1;
 }
 
@@ -397,7 +399,7 @@ static int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, co
                         if (is_signed) {
                             for (int d = 0; d < dim; d++) {
                                 int s = q[d] - lav;
-                                float m = pow43_tab[s < 0 ? -s : s];
+                                float m = cb_val[s < 0 ? -s : s];
                                 cfo[k + d] = (s < 0 ? -m : m) * sf;
                             }
                         } else {
@@ -405,13 +407,14 @@ static int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, co
                             for (int d = 0; d < dim; d++) neg[d] = q[d] ? (int)br_get1(b) : 0;
                             for (int d = 0; d < dim; d++) {
                                 int m = q[d];
+                                float val;
                                 if (bt == 11 && m == 16) {         /* escape sequence, aacdec.c:1177-1209 */
                                     int n = 0;
                                     while (br_get1(b)) { if (++n > 8) return HEAAC_E_INVAL; }
                                     n += 4;
-                                    m = (1 << n) + br_get(b, n);
-                                }
-                                float val = pow43_tab[m];
+                                    val = pow43_tab[(1 << n) + br_get(b, n)];
+                                } else
+                                    val = cb_val[m];
                                 cfo[k + d] = (neg[d] ? -val : val) * sf;
                             }
                         }

@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pyref  # noqa: E402
 import heaac_streams as hs  # noqa: E402
+import lc_writer  # noqa: E402
 
 abi = pyref.abi
 
@@ -61,6 +62,10 @@ def main():
     for name, seed, stereo, ps in (("heaac_v1_stereo", 7, True, False), ("heaac_v2_ps", 26, False, True)):
         pkts, ed, info = hs.make_stream(seed, 12, stereo=stereo, ps=ps)
         cases[name] = (pkts, ed, 24000, 2 if stereo else 1, "stereo" if stereo else "mono")
+    # own AAC-LC writer: TNS, sine + KBD windows, grouped short blocks, PNS, intensity, pulses, escapes (config 4)
+    pkts, ed, w = lc_writer.make_lc_stream(4004, 8, "5.1", 3)
+    cases["lc_51_tns_rich"] = (pkts, ed, 48000, 6, "5.1")
+    print("lc_51_tns_rich content:", w.stats)
     for name, c in cases.items():
         d = capture(*c)
         path = os.path.join(HERE, name + ".npz")

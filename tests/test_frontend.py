@@ -105,6 +105,27 @@ def test_frontend_matches_reference_parser_on_fresh_streams(mode, seed):
     ref.close(); fe.close()
 
 
+@needs_ref
+@pytest.mark.parametrize("layout,sr_index,seed", [("stereo", 4, 21), ("5.1", 3, 22), ("mono", 6, 23), ("stereo", 11, 24), ("5.1", 0, 25)])
+def test_frontend_matches_reference_parser_on_rich_lc_streams(layout, sr_index, seed):
+    """PNS (shared LCG state), intensity stereo, M/S masks, pulse data, escape codes, TNS data, grouping."""
+    import lc_writer
+    import pyref
+    pkts, ed, w = lc_writer.make_lc_stream(seed, 30, layout, sr_index)
+    rate = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000][sr_index]
+    nch = lc_writer.CHAN_CONFIG[layout]
+    ref = pyref.Decoder(ed, rate, nch, layout)
+    fe = hb.Frontend(ed, rate, nch)
+    for t, p in enumerate(pkts):
+        r, m = ref.decode(p), fe.parse(p)
+        bad = diff_parsed(r, m, fe.ncc, False, False)
+        assert not bad, "%s/%d frame %d: %s" % (layout, seed, t, bad[:6])
+        assert r["consumed"] == m["consumed"]
+    for k in ("pns", "esc", "pulse", "tns"):
+        assert w.stats[k] > 0, k
+    ref.close(); fe.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_frontend_plus_cuda_reproduces_reference_pcm(name):

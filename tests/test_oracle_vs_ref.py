@@ -49,6 +49,34 @@ def test_oracle_matches_reference_on_fresh_heaac_streams(mode, seed):
 
 
 @needs_ref
+@pytest.mark.parametrize("layout,sr_index,seed", [("stereo", 4, 11), ("5.1", 3, 12), ("mono", 6, 13), ("stereo", 8, 14)])
+def test_oracle_matches_reference_on_rich_lc_streams(layout, sr_index, seed):
+    """TNS (both directions, orders to 12/7), sine + KBD windows, grouped short blocks and every window-sequence pair
+    (a few illegal ones included), on streams from the repo's own AAC-LC writer (SURVEY 8c fixture 3, config 4)."""
+    import lc_writer
+    import pyref
+    pkts, ed, w = lc_writer.make_lc_stream(seed, 36, layout, sr_index)
+    rate = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000][sr_index]
+    nch = lc_writer.CHAN_CONFIG[layout]
+    dec = pyref.Decoder(ed, rate, nch, layout, float_mode=True)
+    frames = [dec.decode(p) for p in pkts]
+    dec.close()
+    assert w.stats["tns"] > 0.3 * w.stats["chan_frames"] and w.stats["short"] > 0 and w.stats["sine"] > 0
+    assert any(f["tns"]["order"].max() >= (7 if layout != "mono" else 4) for f in frames)
+    cfg = abi.make_config(1, pyref.LAYOUTS[layout][0], sr_index, sbr=False, ps=False, max_frames=len(frames))
+    st = lambda k: np.stack([f[k] for f in frames])[:, None]
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), None, None)
+    orc.close()
+    ref_f32 = np.stack([f["pcm_f32"] for f in frames])
+    # the float criterion is relative to the larger of full scale and the stream's own peak (a hot TNS filter can
+    # push float PCM far beyond s16 range, where it clips identically in both decoders)
+    scale = max(32768.0, float(np.abs(ref_f32).max()))
+    assert float(np.abs(f32[:, 0].astype(np.float64) - ref_f32).max()) / scale <= 1e-5
+    assert int(np.abs(pcm[:, 0].astype(np.int32) - np.stack([f["pcm"] for f in frames]).astype(np.int32)).max()) <= 1
+
+
+@needs_ref
 def test_oracle_stage_arrays_match_reference():
     """Stage-by-stage: W, X_low, alpha, X_high, e_curr, gain, Y of the last frame (SURVEY 8c 'stage-level oracle')."""
     import heaac_streams as hs
