@@ -31,6 +31,9 @@ EXPORTS = [
     "heaac_b200_version", "heaac_b200_strerror", "heaac_b200_sizeof", "heaac_b200_sbr_tables",
     "heaac_b200_profile_enable", "heaac_b200_profile_read",
     "heaac_fe_open", "heaac_fe_close", "heaac_fe_parse", "heaac_fe_info",
+    "heaac_b200_synth_submit", "heaac_b200_inputs_consumed", "heaac_b200_wait", "heaac_b200_chunk_frames",
+    "heaac_b200_reference_out_slots", "heaac_b200_host_alloc", "heaac_b200_host_free",
+    "heaac_dec_open", "heaac_dec_close", "heaac_dec_decode", "heaac_dec_info",
 ]
 
 
@@ -79,14 +82,27 @@ def lib():
         L.heaac_fe_close.restype = None
         L.heaac_fe_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
+        L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.heaac_b200_inputs_consumed.argtypes = [C.c_void_p]
+        L.heaac_b200_wait.argtypes = [C.c_void_p]
+        L.heaac_b200_chunk_frames.argtypes = [C.c_void_p]
+        L.heaac_b200_reference_out_slots.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.heaac_b200_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.heaac_b200_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_dec_open.argtypes = [C.POINTER(abi.DecoderConfig), C.POINTER(C.c_void_p)]
+        L.heaac_dec_close.argtypes = [C.c_void_p]
+        L.heaac_dec_close.restype = None
+        L.heaac_dec_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.heaac_dec_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_longlong)] * 2
         L.heaac_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.heaac_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
         for name, size in abi.SIZES.items():
             got = L.heaac_b200_sizeof(name.encode())
             if got != size:
                 raise ImportError("ABI mismatch for %s: library %d, abi.py %d" % (name, got, size))
-        if L.heaac_b200_sizeof(b"HeaacConfig") != C.sizeof(Config) or L.heaac_b200_sizeof(b"HeaacBatch") != C.sizeof(Batch):
-            raise ImportError("ABI mismatch for HeaacConfig/HeaacBatch")
+        if L.heaac_b200_sizeof(b"HeaacConfig") != C.sizeof(Config) or L.heaac_b200_sizeof(b"HeaacBatch") != C.sizeof(Batch) \
+                or L.heaac_b200_sizeof(b"HeaacDecoderConfig") != C.sizeof(abi.DecoderConfig):
+            raise ImportError("ABI mismatch for HeaacConfig/HeaacBatch/HeaacDecoderConfig")
         _lib = L
     return _lib
 
@@ -272,6 +288,79 @@ class Frontend:
     def close(self):
         if self.h:
             lib().heaac_fe_close(self.h)
+            self.h = None
+
+
+class PacketBatch:
+    """n_frames x n_streams packets laid out the way heaac_dec_decode takes them (pointer + size arrays over one
+    contiguous host blob).  Build it once; decoding does not copy the payload."""
+
+    def __init__(self, packets):
+        """packets[t][s] = bytes of stream s's frame t."""
+        self.T, self.S = len(packets), len(packets[0])
+        flat = [p for row in packets for p in row]
+        assert len(flat) == self.T * self.S
+        self.sizes = np.asarray([len(p) for p in flat], np.int32)
+        pad = 8                                        # FF_INPUT_BUFFER_PADDING_SIZE-style zero tail per packet
+        ofs = np.concatenate([[0], np.cumsum(self.sizes.astype(np.int64) + pad)])
+        self.blob = np.zeros(int(ofs[-1]), np.uint8)
+        for p, o in zip(flat, ofs[:-1]):
+            self.blob[o:o + len(p)] = np.frombuffer(p, np.uint8)
+        self.ptrs = (self.blob.ctypes.data + ofs[:-1]).astype(np.uint64)
+        self.nbytes = int(self.sizes.sum())
+
+
+class Decoder:
+    """Batched packets -> PCM decoder (heaac_dec_*): S host front ends + the GPU back end, the counterpart of the
+    reference's aac_decode_init / aac_decode_frame / aac_decode_close for n_streams streams."""
+
+    def __init__(self, n_streams, extradata=b"", sample_rate=0, channels=0, max_frames=32, n_threads=0, device=0,
+                 want_float=False):
+        self._ed = np.frombuffer(extradata, np.uint8).copy() if extradata else np.zeros(0, np.uint8)
+        cfg = abi.DecoderConfig()
+        cfg.abi_version, cfg.device, cfg.n_streams = abi.ABI_VERSION, device, n_streams
+        cfg.sample_rate, cfg.channels, cfg.max_frames_per_call = sample_rate, channels, max_frames
+        cfg.n_threads, cfg.want_float_out = n_threads, int(bool(want_float))
+        cfg.extradata, cfg.extradata_size = (self._ed.ctypes.data if self._ed.size else None), self._ed.size
+        h = C.c_void_p()
+        _check(lib().heaac_dec_open(C.byref(cfg), C.byref(h)), "heaac_dec_open")
+        self.h, self.S, self.want_float = h.value, n_streams, bool(want_float)
+        self.nout = self.out_len = None
+
+    def info(self):
+        v = [C.c_int() for _ in range(4)]
+        w = [C.c_longlong() for _ in range(2)]
+        ok = lib().heaac_dec_info(self.h, *[C.byref(x) for x in v], *[C.byref(x) for x in w])
+        return {"configured": bool(ok), "n_out_channels": v[0].value, "frame_out_len": v[1].value, "sbr": v[2].value,
+                "ps": v[3].value, "parse_errors": w[0].value, "gpu_launches": w[1].value}
+
+    def decode(self, batch, pcm_out=None, out_shape=None):
+        """batch: PacketBatch.  Returns (pcm s16 [T, S, out_len, nout], pcm_f32 or None, consumed [T, S]).
+        Before the first call the output geometry is unknown: pass out_shape=(out_len, nout) or let the first call
+        allocate for the largest case and trim."""
+        T = batch.T
+        assert batch.S == self.S
+        consumed = np.zeros((T, self.S), np.int32)
+        if self.nout is None and out_shape is None:
+            cap = (2048, 16)
+        else:
+            cap = out_shape or (self.out_len, self.nout)
+        pcm = pcm_out if pcm_out is not None else np.zeros((T, self.S, cap[0], cap[1]), np.int16)
+        f32 = np.zeros((T, self.S, cap[1], cap[0]), np.float32) if self.want_float else None
+        _check(lib().heaac_dec_decode(self.h, T, batch.ptrs.ctypes.data, batch.sizes.ctypes.data, pcm.ctypes.data,
+                                      f32.ctypes.data if f32 is not None else None, consumed.ctypes.data), "heaac_dec_decode")
+        i = self.info()
+        self.nout, self.out_len = i["n_out_channels"], i["frame_out_len"]
+        if pcm_out is None and cap != (self.out_len, self.nout):
+            n = T * self.S * self.out_len * self.nout
+            pcm = pcm.reshape(-1)[:n].reshape(T, self.S, self.out_len, self.nout).copy()
+            if f32 is not None:
+                f32 = f32.reshape(-1)[:n].reshape(T, self.S, self.nout, self.out_len).copy()
+        return pcm, f32, consumed
+
+    def close(self):
+        if self.h:
+            lib().heaac_dec_close(self.h)
             self.h = None
 
 

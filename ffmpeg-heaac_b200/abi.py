@@ -76,6 +76,14 @@ class Batch(C.Structure):
     ]
 
 
+class DecoderConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("device", C.c_int32), ("n_streams", C.c_int32), ("sample_rate", C.c_int32),
+        ("channels", C.c_int32), ("max_frames_per_call", C.c_int32), ("n_threads", C.c_int32),
+        ("want_float_out", C.c_int32), ("extradata", C.c_void_p), ("extradata_size", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 # aac_channel_layout_map (aacdectab.h:74-82): output order of the reference per channel configuration
 _LAYOUT_MAP = {
     1: [(TYPE_SCE, 0)], 2: [(TYPE_CPE, 0)], 3: [(TYPE_CPE, 0), (TYPE_SCE, 0)],

@@ -44,6 +44,7 @@ struct HeaacContext {
     /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
      * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
     int chunk;
+    unsigned long long seq;            /* staged chunks so far (selects the staging set) */
     float *s_coeffs[2]; HeaacIcs *s_ics[2]; HeaacTns *s_tns[2]; HeaacSbrElem *s_sbr[2]; HeaacPsFrame *s_ps[2];
     int16_t *s_pcm[2]; float *s_pcm_f32[2];
     cudaStream_t s_in, s_out;
@@ -448,7 +449,9 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
     return cuda_err(cudaGetLastError(), "kernel launch");
 }
 
-extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
+/* Enqueue a batch.  Host-pointer batches go through the double-buffered staging sets; `seq` counts staged
+ * chunks over the life of the context so that submissions may follow one another without a host sync. */
+extern "C" int heaac_b200_synth_submit(HeaacContext *c, const HeaacBatch *b)
 {
     if (!c || !b || b->n_frames <= 0 || !b->coeffs || !b->ics) return HEAAC_E_INVAL;
     const HeaacGeom *g = &c->geom;
@@ -462,14 +465,12 @@ extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
     if (b->pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;   /* context created without want_float_out */
     const size_t S = g->n_streams;
     const int Tc = c->chunk;
-    /* the kernels must not start before earlier work on the context's stream has finished with the state */
-    int k = 0;
-    for (int f0 = 0; f0 < b->n_frames; f0 += Tc, k++) {
-        const int buf = k & 1;
+    for (int f0 = 0; f0 < b->n_frames; f0 += Tc, c->seq++) {
+        const int buf = (int)(c->seq & 1);
         const int n = b->n_frames - f0 < Tc ? b->n_frames - f0 : Tc;
         const size_t nch = (size_t)n * S * g->ncc, och = (size_t)f0 * S * g->ncc;
-        /* H2D on s_in: staging set `buf` is free once the kernels of chunk k-2 are done */
-        if (k >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));
+        /* H2D on s_in: staging set `buf` is free once the kernels of the chunk two back are done */
+        if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));
         CK(cudaMemcpyAsync(c->s_coeffs[buf], b->coeffs + och * 1024, nch * 1024 * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(c->s_ics[buf], b->ics + och, nch * sizeof(HeaacIcs), cudaMemcpyHostToDevice, c->s_in));
         if (b->tns) CK(cudaMemcpyAsync(c->s_tns[buf], b->tns + och, nch * sizeof(HeaacTns), cudaMemcpyHostToDevice, c->s_in));
@@ -478,9 +479,9 @@ extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
         if (g->ps)  CK(cudaMemcpyAsync(c->s_ps[buf], b->ps + (size_t)f0 * S, (size_t)n * S * sizeof(HeaacPsFrame),
                                        cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(c->ev_in[buf], c->s_in));
-        /* kernels on the context stream: need the inputs, and the PCM staging set drained by chunk k-2's D2H */
+        /* kernels on the context stream: need the inputs, and the PCM staging set drained by the D2H two chunks back */
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
-        if (k >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
+        if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
         int r = launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], b->tns ? c->s_tns[buf] : nullptr, c->s_sbr[buf], c->s_ps[buf],
                               c->s_pcm[buf], b->pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
         if (r) return r;
@@ -492,9 +493,93 @@ extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
         if (b->pcm_f32) CK(cudaMemcpyAsync(b->pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[buf], c->s_out));
     }
-    CK(cudaStreamSynchronize(c->s_out));
-    CK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+/* all host INPUT buffers of the batches submitted so far have been read (they may be overwritten) */
+extern "C" int heaac_b200_inputs_consumed(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->s_in));
+    return 0;
+}
+
+/* everything submitted so far is complete: PCM is in the caller's buffers */
+extern "C" int heaac_b200_wait(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->s_in));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->s_out));
+    return cuda_err(cudaGetLastError(), "wait");
+}
+
+extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
+{
+    int r = heaac_b200_synth_submit(c, b);
+    if (r) return r;
+    if (b->on_device) return 0;                 /* device-resident batches stay asynchronous on the context's stream */
+    return heaac_b200_wait(c);
+}
+
+/* page-locked host memory: what the H2D / D2H copies of the host-pointer path overlap best with */
+extern "C" int heaac_b200_host_alloc(HeaacContext *c, size_t bytes, void **hptr)
+{
+    if (!c || !hptr) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    cudaError_t e = cudaHostAlloc(hptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return HEAAC_E_NOMEM; }
+    return 0;
+}
+
+extern "C" int heaac_b200_host_free(HeaacContext *c, void *hptr)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaFreeHost(hptr));
+    return 0;
+}
+
+extern "C" int heaac_b200_chunk_frames(const HeaacContext *c) { return c ? c->chunk : HEAAC_E_INVAL; }
+
+/* aac_channel_layout_map (aacdectab.h:74-82): output order of the reference for channel configurations 1..7 as
+ * (element type, instance) pairs; output_configure (aacdec.c:214-272) assigns output channels in this order. */
+extern "C" int heaac_b200_reference_out_slots(const uint8_t *elem_type, int n_elems, uint8_t out_slot[HEAAC_MAX_CHANNELS])
+{
+    static const uint8_t cfg_elems[7][5] = {
+        { HEAAC_TYPE_SCE }, { HEAAC_TYPE_CPE }, { HEAAC_TYPE_SCE, HEAAC_TYPE_CPE }, { HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_SCE },
+        { HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE }, { HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE, HEAAC_TYPE_LFE },
+        { HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE, HEAAC_TYPE_LFE } };
+    static const uint8_t cfg_n[7] = { 1, 1, 2, 3, 3, 4, 5 };
+    static const uint8_t order[7][5][2] = {                      /* {type, instance} in output order */
+        { { HEAAC_TYPE_SCE, 0 } }, { { HEAAC_TYPE_CPE, 0 } }, { { HEAAC_TYPE_CPE, 0 }, { HEAAC_TYPE_SCE, 0 } },
+        { { HEAAC_TYPE_CPE, 0 }, { HEAAC_TYPE_SCE, 0 }, { HEAAC_TYPE_SCE, 1 } },
+        { { HEAAC_TYPE_CPE, 0 }, { HEAAC_TYPE_SCE, 0 }, { HEAAC_TYPE_CPE, 1 } },
+        { { HEAAC_TYPE_CPE, 0 }, { HEAAC_TYPE_SCE, 0 }, { HEAAC_TYPE_LFE, 0 }, { HEAAC_TYPE_CPE, 1 } },
+        { { HEAAC_TYPE_CPE, 0 }, { HEAAC_TYPE_SCE, 0 }, { HEAAC_TYPE_LFE, 0 }, { HEAAC_TYPE_CPE, 2 }, { HEAAC_TYPE_CPE, 1 } } };
+    if (!elem_type || !out_slot || n_elems <= 0 || n_elems > HEAAC_MAX_ELEMS) return HEAAC_E_INVAL;
+    int ncc = 0;
+    for (int e = 0; e < n_elems; e++) ncc += elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+    if (ncc > HEAAC_MAX_CHANNELS) return HEAAC_E_INVAL;
+    memset(out_slot, 0, HEAAC_MAX_CHANNELS);
+    int cc = -1;
+    for (int k = 0; k < 7 && cc < 0; k++)
+        if (cfg_n[k] == n_elems && !memcmp(cfg_elems[k], elem_type, n_elems)) cc = k;
+    if (cc < 0) { for (int c = 0; c < ncc; c++) out_slot[c] = (uint8_t)c; return ncc; }     /* identity */
+    int ch = 0, seen[8] = { 0 };
+    for (int e = 0; e < n_elems; e++) {
+        const int type = elem_type[e], inst = seen[type & 7]++;
+        int pos = 0;
+        for (int k = 0; k < n_elems; k++) {
+            if (order[cc][k][0] == type && order[cc][k][1] == inst) break;
+            pos += order[cc][k][0] == HEAAC_TYPE_CPE ? 2 : 1;
+        }
+        out_slot[ch++] = (uint8_t)pos;
+        if (type == HEAAC_TYPE_CPE) out_slot[ch++] = (uint8_t)(pos + 1);
+    }
+    return ncc;
 }
 
 extern "C" int heaac_b200_sync(HeaacContext *c)
@@ -694,6 +779,7 @@ extern "C" int heaac_b200_sizeof(const char *name)
     if (!strcmp(name, "HeaacPsFrame")) return (int)sizeof(HeaacPsFrame);
     if (!strcmp(name, "HeaacConfig")) return (int)sizeof(HeaacConfig);
     if (!strcmp(name, "HeaacBatch")) return (int)sizeof(HeaacBatch);
+    if (!strcmp(name, "HeaacDecoderConfig")) return (int)sizeof(HeaacDecoderConfig);
     if (!strcmp(name, "HeaacChanState")) return (int)sizeof(HeaacChanState);
     if (!strcmp(name, "HeaacSynthState")) return (int)sizeof(HeaacSynthState);
     if (!strcmp(name, "HeaacPsState")) return (int)sizeof(HeaacPsState);

@@ -1,0 +1,284 @@
+/*
+ * heaac_decoder.cpp -- batched packets -> PCM decoder: S host front ends + one GPU back end.
+ *
+ * Plays the role of the reference's AVCodec entry points for a batch of independent streams:
+ *   heaac_dec_open    ~ aac_decode_init   (aacdec.c:537-598)
+ *   heaac_dec_decode  ~ aac_decode_frame  (aacdec.c:1962-2106), for n_frames x n_streams packets per call
+ *   heaac_dec_close   ~ aac_decode_close  (aacdec.c:2108-2124)
+ * The element loop / entropy decoding runs on host threads (heaac_frontend.c, one HeaacFrontend per stream, streams
+ * split across a persistent worker pool); everything from spectral_to_sample() down runs on the GPU
+ * (heaac_b200_synth_submit).  Parsing of chunk k+1 overlaps the H2D / kernels / D2H of chunk k: two page-locked
+ * parameter sets, heaac_b200_inputs_consumed() as the hand-back point.
+ *
+ * No CUDA calls in this file: the device is reached through the C-ABI only.
+ */
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/heaac_b200.h"
+
+namespace {
+
+struct ParamSet {                    /* one chunk of parsed frames, frame-major [t][s]..., page-locked */
+    float *coeffs = nullptr;
+    HeaacIcs *ics = nullptr;
+    HeaacTns *tns = nullptr;
+    HeaacSbrElem *sbr = nullptr;
+    HeaacPsFrame *ps = nullptr;
+};
+
+struct Job {                         /* what the pool is working on */
+    const uint8_t *const *pkt = nullptr;
+    const int *size = nullptr;
+    int *consumed = nullptr;
+    int n_frames = 0;                /* frames in this chunk */
+    ParamSet *set = nullptr;
+};
+
+}  // namespace
+
+struct HeaacDecoder {
+    HeaacDecoderConfig cfg;
+    std::vector<uint8_t> extradata;
+    std::vector<HeaacFrontend *> fe;
+    HeaacContext *be = nullptr;
+    int ncc = 0, nse = 0, sbr = 0, ps = 0, sr_index = 0, n_elems = 0, chunk = 1;
+    uint8_t elem_type[HEAAC_MAX_ELEMS] = { 0 };
+    ParamSet set[2];
+    std::atomic<long long> parse_errors{0};
+
+    /* worker pool */
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    Job job;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool quit = false;
+};
+
+namespace {
+
+/* a frame that failed to parse is replaced by digital silence so that the lock-step batch can go on; the error is
+ * reported through consumed[] (the reference returns -1 for such a packet and emits nothing, aacdec.c:2064-2070) */
+void silent_frame(HeaacDecoder *d, ParamSet *p, size_t idx)
+{
+    memset(p->coeffs + idx * d->ncc * 1024, 0, sizeof(float) * d->ncc * 1024);
+    memset(p->ics + idx * d->ncc, 0, sizeof(HeaacIcs) * d->ncc);
+    memset(p->tns + idx * d->ncc, 0, sizeof(HeaacTns) * d->ncc);
+    if (d->sbr) memset(p->sbr + idx * d->nse, 0, sizeof(HeaacSbrElem) * d->nse);
+    if (d->ps)  memset(p->ps + idx, 0, sizeof(HeaacPsFrame));
+}
+
+void parse_range(HeaacDecoder *d, const Job &j, int s0, int s1)
+{
+    const size_t S = d->cfg.n_streams;
+    for (int s = s0; s < s1; s++) {
+        for (int t = 0; t < j.n_frames; t++) {
+            const size_t idx = (size_t)t * S + s;
+            ParamSet *p = j.set;
+            int r = heaac_fe_parse(d->fe[s], j.pkt[idx], j.size[idx], p->coeffs + idx * d->ncc * 1024, p->ics + idx * d->ncc,
+                                   p->tns + idx * d->ncc, d->sbr ? p->sbr + idx * d->nse : nullptr, d->ps ? p->ps + idx : nullptr);
+            if (r < 0) { silent_frame(d, p, idx); d->parse_errors++; }
+            if (j.consumed) j.consumed[idx] = r;
+        }
+    }
+}
+
+void worker_main(HeaacDecoder *d, int me, int n)
+{
+    unsigned long long seen = 0;
+    for (;;) {
+        Job j;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_go.wait(lk, [&] { return d->quit || d->generation != seen; });
+            if (d->quit) return;
+            seen = d->generation;
+            j = d->job;
+        }
+        const int S = d->cfg.n_streams;
+        const int s0 = (int)((long long)S * me / n), s1 = (int)((long long)S * (me + 1) / n);
+        parse_range(d, j, s0, s1);
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            if (--d->pending == 0) d->cv_done.notify_all();
+        }
+    }
+}
+
+void run_job(HeaacDecoder *d, const Job &j)
+{
+    if (d->workers.empty()) { parse_range(d, j, 0, d->cfg.n_streams); return; }
+    std::unique_lock<std::mutex> lk(d->mu);
+    d->job = j;
+    d->pending = (int)d->workers.size();
+    d->generation++;
+    d->cv_go.notify_all();
+    d->cv_done.wait(lk, [&] { return d->pending == 0; });
+}
+
+void free_sets(HeaacDecoder *d)
+{
+    for (auto &p : d->set) {
+        if (!d->be) break;
+        if (p.coeffs) heaac_b200_host_free(d->be, p.coeffs);
+        if (p.ics) heaac_b200_host_free(d->be, p.ics);
+        if (p.tns) heaac_b200_host_free(d->be, p.tns);
+        if (p.sbr) heaac_b200_host_free(d->be, p.sbr);
+        if (p.ps) heaac_b200_host_free(d->be, p.ps);
+        p = ParamSet();
+    }
+}
+
+/* Stream layout, SBR and PS presence are known for certain only after one frame has been parsed (ADTS
+ * configuration, implicit SBR / PS signalling: aacdec.c:1659-1676, 1994-2006): parse the first packet of stream 0
+ * with a scratch front end, then build the back end to match. */
+int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
+{
+    HeaacFrontend *probe = nullptr;
+    const uint8_t *ed = d->extradata.empty() ? nullptr : d->extradata.data();
+    int r = heaac_fe_open(&probe, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0);
+    if (r) return r;
+    {
+        std::vector<float> co(16 * 1024);
+        std::vector<HeaacIcs> ic(16);
+        std::vector<HeaacTns> tn(16);
+        std::vector<HeaacSbrElem> sb(HEAAC_MAX_ELEMS);
+        HeaacPsFrame ps;
+        r = heaac_fe_parse(probe, pkt, size, co.data(), ic.data(), tn.data(), sb.data(), &ps);
+    }
+    if (r >= 0) {
+        d->n_elems = heaac_fe_info(probe, &d->ncc, &d->nse, &d->sbr, &d->ps, &d->sr_index, d->elem_type);
+        r = d->n_elems > 0 ? 0 : HEAAC_E_INVAL;
+    }
+    heaac_fe_close(probe);
+    if (r < 0) return r;
+
+    HeaacConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = HEAAC_ABI_VERSION;
+    cfg.device = d->cfg.device;
+    cfg.n_streams = d->cfg.n_streams;
+    cfg.n_elems = d->n_elems;
+    memcpy(cfg.elem_type, d->elem_type, sizeof(cfg.elem_type));
+    cfg.sr_index = d->sr_index;
+    cfg.sbr = d->sbr;
+    cfg.ps = d->ps;
+    cfg.add_bias = 0.0f;
+    cfg.sf_scale = -1.0f / 1024.0f;                   /* s16-unit convention, aacdec.c:577-581 */
+    cfg.max_frames_per_call = d->cfg.max_frames_per_call;
+    cfg.want_float_out = d->cfg.want_float_out;
+    heaac_b200_reference_out_slots(cfg.elem_type, cfg.n_elems, cfg.out_slot);
+    if ((r = heaac_b200_create(&cfg, &d->be))) return r;
+
+    d->chunk = heaac_b200_chunk_frames(d->be);
+    const size_t n = (size_t)d->chunk * d->cfg.n_streams;
+    for (auto &p : d->set) {
+        if (heaac_b200_host_alloc(d->be, n * d->ncc * 1024 * sizeof(float), (void **)&p.coeffs) ||
+            heaac_b200_host_alloc(d->be, n * d->ncc * sizeof(HeaacIcs), (void **)&p.ics) ||
+            heaac_b200_host_alloc(d->be, n * d->ncc * sizeof(HeaacTns), (void **)&p.tns) ||
+            (d->sbr && heaac_b200_host_alloc(d->be, n * d->nse * sizeof(HeaacSbrElem), (void **)&p.sbr)) ||
+            (d->ps && heaac_b200_host_alloc(d->be, n * sizeof(HeaacPsFrame), (void **)&p.ps)))
+            return HEAAC_E_NOMEM;
+    }
+    for (int s = 0; s < d->cfg.n_streams; s++) {
+        HeaacFrontend *f = nullptr;
+        if ((r = heaac_fe_open(&f, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0))) return r;
+        d->fe.push_back(f);
+    }
+    int nt = d->cfg.n_threads > 0 ? d->cfg.n_threads : (int)std::thread::hardware_concurrency();
+    if (nt > d->cfg.n_streams) nt = d->cfg.n_streams;
+    if (nt > 1)
+        for (int i = 0; i < nt; i++) d->workers.emplace_back(worker_main, d, i, nt);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int heaac_dec_open(const HeaacDecoderConfig *cfg, HeaacDecoder **out)
+{
+    if (!cfg || !out || cfg->abi_version != HEAAC_ABI_VERSION || cfg->n_streams <= 0 || cfg->max_frames_per_call <= 0)
+        return HEAAC_E_INVAL;
+    if (cfg->extradata_size < 0 || (cfg->extradata_size > 0 && !cfg->extradata)) return HEAAC_E_INVAL;
+    HeaacDecoder *d = new (std::nothrow) HeaacDecoder();
+    if (!d) return HEAAC_E_NOMEM;
+    d->cfg = *cfg;
+    if (cfg->extradata_size) d->extradata.assign(cfg->extradata, cfg->extradata + cfg->extradata_size);
+    d->cfg.extradata = nullptr;
+    if (!d->extradata.empty()) {                      /* reject an unusable configuration now, like aac_decode_init */
+        HeaacFrontend *probe = nullptr;
+        int r = heaac_fe_open(&probe, d->extradata.data(), (int)d->extradata.size(), cfg->sample_rate, cfg->channels, 0);
+        if (r) { delete d; return r; }
+        heaac_fe_close(probe);
+    }
+    *out = d;
+    return 0;
+}
+
+extern "C" void heaac_dec_close(HeaacDecoder *d)
+{
+    if (!d) return;
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        d->quit = true;
+        d->cv_go.notify_all();
+    }
+    for (auto &t : d->workers) t.join();
+    if (d->be) heaac_b200_wait(d->be);
+    free_sets(d);
+    for (auto f : d->fe) heaac_fe_close(f);
+    if (d->be) heaac_b200_destroy(d->be);
+    delete d;
+}
+
+extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                                int16_t *pcm, float *pcm_f32, int *consumed)
+{
+    if (!d || n_frames <= 0 || !pkt || !pkt_size || (!pcm && !pcm_f32)) return HEAAC_E_INVAL;
+    if (n_frames > d->cfg.max_frames_per_call) return HEAAC_E_INVAL;
+    int r;
+    if (!d->be && (r = configure(d, pkt[0], pkt_size[0]))) return r;
+    if (pcm_f32 && !d->cfg.want_float_out) return HEAAC_E_INVAL;
+    const size_t S = d->cfg.n_streams;
+    const size_t out_frame = S * heaac_b200_frame_out_len(d->be) * heaac_b200_n_out_channels(d->be);
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += d->chunk, k++) {
+        const int n = n_frames - f0 < d->chunk ? n_frames - f0 : d->chunk;
+        ParamSet *p = &d->set[k & 1];
+        /* set k&1 was handed to the GPU two chunks ago: its H2D copies must be over before it is overwritten */
+        if (k >= 2 && (r = heaac_b200_inputs_consumed(d->be))) return r;
+        Job j;
+        j.pkt = pkt + (size_t)f0 * S; j.size = pkt_size + (size_t)f0 * S;
+        j.consumed = consumed ? consumed + (size_t)f0 * S : nullptr;
+        j.n_frames = n; j.set = p;
+        run_job(d, j);
+        HeaacBatch b;
+        memset(&b, 0, sizeof(b));
+        b.n_frames = n;
+        b.coeffs = p->coeffs; b.ics = p->ics; b.tns = p->tns; b.sbr = p->sbr; b.ps = p->ps;
+        b.pcm = pcm ? pcm + (size_t)f0 * out_frame : nullptr;
+        b.pcm_f32 = pcm_f32 ? pcm_f32 + (size_t)f0 * out_frame : nullptr;
+        if ((r = heaac_b200_synth_submit(d->be, &b))) return r;
+    }
+    return heaac_b200_wait(d->be);
+}
+
+extern "C" int heaac_dec_info(const HeaacDecoder *d, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,
+                              long long *parse_errors, long long *gpu_launches)
+{
+    if (!d) return HEAAC_E_INVAL;
+    if (parse_errors) *parse_errors = d->parse_errors.load();
+    if (!d->be) return 0;                              /* not configured yet: nothing decoded so far */
+    if (n_out_channels) *n_out_channels = heaac_b200_n_out_channels(d->be);
+    if (frame_out_len) *frame_out_len = heaac_b200_frame_out_len(d->be);
+    if (sbr) *sbr = d->sbr;
+    if (ps) *ps = d->ps;
+    if (gpu_launches) *gpu_launches = heaac_b200_launch_count(d->be);
+    return 1;
+}

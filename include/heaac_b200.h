@@ -224,6 +224,19 @@ int  heaac_b200_n_sbr_elems(const HeaacContext *ctx);
  * return after the PCM has landed in host memory. */
 int  heaac_b200_synth(HeaacContext *ctx, const HeaacBatch *batch);
 int  heaac_b200_sync(HeaacContext *ctx);
+/* The same call split for pipelined callers: submit() only enqueues (host-pointer batches are streamed
+ * through the staging sets chunk by chunk); inputs_consumed() returns once every host INPUT buffer submitted so
+ * far has been read and may be overwritten; wait() returns once all PCM submitted so far is in host memory.
+ * heaac_b200_synth == submit + wait for host-pointer batches. */
+int  heaac_b200_synth_submit(HeaacContext *ctx, const HeaacBatch *batch);
+int  heaac_b200_inputs_consumed(HeaacContext *ctx);
+int  heaac_b200_wait(HeaacContext *ctx);
+/* frames per staging chunk of the host-pointer path (derived from max_frames_per_call) */
+int  heaac_b200_chunk_frames(const HeaacContext *ctx);
+/* cfg.out_slot[] for the reference's output channel order (aac_channel_layout_map, aacdectab.h:74-82;
+ * output_configure, aacdec.c:214-272); identity outside the default channel configurations.  Returns the
+ * number of core channels. */
+int  heaac_b200_reference_out_slots(const uint8_t *elem_type, int n_elems, uint8_t out_slot[HEAAC_MAX_CHANNELS]);
 
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 long long heaac_b200_launch_count(const HeaacContext *ctx);
@@ -236,6 +249,9 @@ int  heaac_b200_dev_alloc(HeaacContext *ctx, size_t bytes, void **dptr);
 int  heaac_b200_dev_free(HeaacContext *ctx, void *dptr);
 int  heaac_b200_dev_upload(HeaacContext *ctx, void *dptr, const void *hptr, size_t bytes);
 int  heaac_b200_dev_download(HeaacContext *ctx, void *hptr, const void *dptr, size_t bytes);
+/* page-locked host memory (what the H2D / D2H copies of the host-pointer path overlap best with) */
+int  heaac_b200_host_alloc(HeaacContext *ctx, size_t bytes, void **hptr);
+int  heaac_b200_host_free(HeaacContext *ctx, void *hptr);
 
 /* Event timing on the context's stream (CUDA events; milliseconds). */
 int  heaac_b200_timer_start(HeaacContext *ctx);
@@ -281,6 +297,39 @@ int  heaac_fe_parse(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coef
  * implicit signalling once the first frame has been parsed (aacdec.c:1659-1676) */
 int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,
                    uint8_t elem_type[HEAAC_MAX_ELEMS]);
+
+/* ---- batched decoder: packets -> PCM ------------------------------------------------------------
+ * S front ends + one back end behind the reference's AVCodec entry points (aacdec.c:2128-2142):
+ *   heaac_dec_open   ~ init   (aac_decode_init,  aacdec.c:537-598)
+ *   heaac_dec_decode ~ decode (aac_decode_frame, aacdec.c:1962-2106) for n_frames x n_streams packets
+ *   heaac_dec_close  ~ close  (aac_decode_close, aacdec.c:2108-2124)
+ * All streams of a decoder share one configuration (extradata, or ADTS headers that agree).  Entropy decoding
+ * runs on `n_threads` host threads and overlaps the GPU work of the previous chunk of frames.
+ * pkt / pkt_size / consumed are frame-major [n_frames][n_streams]; consumed[i] = bytes used or a negative
+ * HEAAC_E_* for a packet that failed to parse (that frame is then decoded as silence; the call goes on).
+ * pcm: interleaved s16 [n_frames][n_streams][frame_out_len][n_out_ch] (caller-owned, page-locked preferred);
+ * pcm_f32 (optional, needs want_float_out): planar float [n_frames][n_streams][n_out_ch][frame_out_len]. */
+typedef struct HeaacDecoder HeaacDecoder;
+typedef struct HeaacDecoderConfig {
+    uint32_t abi_version;           /* HEAAC_ABI_VERSION */
+    int32_t  device;
+    int32_t  n_streams;
+    int32_t  sample_rate;           /* AVCodecContext.sample_rate / channels: used only without extradata */
+    int32_t  channels;
+    int32_t  max_frames_per_call;
+    int32_t  n_threads;             /* host parser threads; 0 = one per hardware thread */
+    int32_t  want_float_out;
+    const uint8_t *extradata;       /* AudioSpecificConfig, or NULL for ADTS input */
+    int32_t  extradata_size;
+    int32_t  reserved;
+} HeaacDecoderConfig;
+int  heaac_dec_open(const HeaacDecoderConfig *cfg, HeaacDecoder **dec);
+void heaac_dec_close(HeaacDecoder *dec);
+int  heaac_dec_decode(HeaacDecoder *dec, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                      int16_t *pcm, float *pcm_f32, int *consumed);
+/* returns 1 once the first call has configured the decoder (0 before), and fills the optional outputs */
+int  heaac_dec_info(const HeaacDecoder *dec, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,
+                    long long *parse_errors, long long *gpu_launches);
 
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */
