@@ -93,13 +93,17 @@ class SbrChanState:
         self.prev_trail = 0       # abs_bord_trail - 16 of the previous frame
 
 
-def _gen_grid(rng, st, allow_var):
+def _gen_grid(rng, st, allow_var, end_at_frame_border=False):
     """One SBR time/frequency grid (read_sbr_grid, aacsbr.c:609-749).
-    Returns dict(fc, num_env, t_env, res, pointer, trail, fields=[(value, nbits)...], num_noise)."""
+    Returns dict(fc, num_env, t_env, res, pointer, trail, fields=[(value, nbits)...], num_noise).
+    end_at_frame_border: only classes whose last border is the frame border (FIXFIX / VARFIX), so that the
+    stream may be followed by its own first frame (looped bench fixtures)."""
     lead = st.prev_trail
     while True:
         if lead == 0 and (not allow_var or rng.random() < 0.6):
             fc = 0
+        elif end_at_frame_border:
+            fc = 2
         elif lead == 0:
             fc = int(rng.choice([1, 2, 3]))
         else:
@@ -377,6 +381,7 @@ class HeAacStreamGen:
         self.ps_state = PsState()
         self.ps_modes, self.ps_ipdopd = ps_modes, ps_ipdopd
         self.frame = 0
+        self.loop_frames = None   # if set, frame loop_frames-1 ends at the frame border (stream can be looped)
         self.tables = tables      # dict(n=(N_low, N_high), n_q=..) from probe_tables()
 
     def sbr_payload(self):
@@ -404,7 +409,7 @@ class HeAacStreamGen:
             if c == 1 and coupling:
                 g = dict(grids[0])
             else:
-                g = _gen_grid(rng, self.ch[c], self.allow_var)
+                g = _gen_grid(rng, self.ch[c], self.allow_var, self.loop_frames is not None and self.frame == self.loop_frames - 1)
                 for v, nb in g["fields"]:
                     bw.put(v, nb)
             grids.append(g)
@@ -512,8 +517,10 @@ def core_noise(n_samples, channels, seed, div=8):
     return pyref.lcg_noise(n_samples, channels, seed=seed, div=div)
 
 
-def make_stream(seed, n_frames, stereo=True, ps=False, core_rate=24000, bitrate_per_ch=32000, **gen_kw):
-    """Returns (packets, extradata, info).  n_frames packets, each a raw_data_block with SBR."""
+def make_stream(seed, n_frames, stereo=True, ps=False, core_rate=24000, bitrate_per_ch=32000, loopable=False, **gen_kw):
+    """Returns (packets, extradata, info).  n_frames packets, each a raw_data_block with SBR.
+    loopable: the last frame's grid ends at the frame border and n_frames should be a multiple of the header
+    period, so frame 0 may follow frame n_frames-1."""
     ch = 2 if stereo else 1
     pcm = core_noise(1024 * (n_frames + 1), ch, seed)
     enc = pyref.Encoder(core_rate, ch, bitrate_per_ch * ch)
@@ -522,6 +529,8 @@ def make_stream(seed, n_frames, stereo=True, ps=False, core_rate=24000, bitrate_
     enc.close()
     gen = HeAacStreamGen(seed, stereo, ps=ps, **gen_kw)
     gen.tables = probe_tables(core[0], extradata, core_rate, ch, gen.hdr)
+    if loopable:
+        gen.loop_frames = n_frames
     pkts = [splice_fil(p, gen.sbr_payload()) for p in core]
     return pkts, extradata, {"tables": gen.tables, "channels": ch, "core_rate": core_rate}
 
