@@ -326,36 +326,43 @@ def main():
         pk = [[blob[ofs[k * N + i]:ofs[k * N + i + 1]] for i in range(N)] for k in range(K)]
         nb = max(1, N // T)
         batches = [hb.PacketBatch([[pk[(s + rank) % K][(b * T + t) % N] for s in range(S)] for t in range(T)]) for b in range(nb)]
-        dec = hb.Decoder(S, z["extradata"].tobytes(), int(z["core_rate"]), int(z["channels"]), max_frames=T, device=dev)
         out_t2 = torch.empty(pcm_bytes, dtype=torch.uint8).pin_memory()
         out2 = out_t2.numpy().view(np.int16).reshape(T, S, ctx.out_len, ctx.nout)
-        step_i = [0]
 
-        def pkt_step():
-            dec.decode(batches[step_i[0] % nb], pcm_out=out2, out_shape=(ctx.out_len, ctx.nout))
-            step_i[0] += 1
-            return int(out2[0, 0, 0, 0])
+        def packets_run(gpu_parse):
+            dec = hb.Decoder(S, z["extradata"].tobytes(), int(z["core_rate"]), int(z["channels"]), max_frames=T, device=dev,
+                             gpu_parse=gpu_parse)
+            step_i = [0]
 
-        for _ in range(2):
-            pkt_step()
-        barrier()
-        n_pk = max(2, min(args.steps, 6))
-        l0p = dec.info()["gpu_launches"]
-        t0 = time.perf_counter()
-        for _ in range(n_pk):
-            pkt_step()
-        dtp = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dtp], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtp = float(t.item())
-        inf = dec.info()
-        e2e_packets = {"value": audio_seconds(args.workload, S, T) * n_pk * world / dtp, "unit": "audio-s/s",
-                       "packet_bytes_per_step": int(batches[0].nbytes), "d2h_bytes_per_step": int(pcm_bytes), "steps": n_pk,
-                       "host_threads": os.cpu_count(), "parse_errors": inf["parse_errors"],
-                       "gpu_launches": int(inf["gpu_launches"] - l0p),
-                       "input": "%d looped fixture streams x %d frames replicated over %d streams" % (K, N, S)}
-        dec.close()
+            def pkt_step():
+                dec.decode(batches[step_i[0] % nb], pcm_out=out2, out_shape=(ctx.out_len, ctx.nout))
+                step_i[0] += 1
+                return int(out2[0, 0, 0, 0])
+
+            for _ in range(2):
+                pkt_step()
+            barrier()
+            n_pk = max(2, min(args.steps, 6))
+            l0p = dec.info()["gpu_launches"]
+            t0 = time.perf_counter()
+            for _ in range(n_pk):
+                pkt_step()
+            dtp = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dtp], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtp = float(t.item())
+            inf = dec.info()
+            dec.close()
+            return {"value": audio_seconds(args.workload, S, T) * n_pk * world / dtp, "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(batches[0].nbytes) if gpu_parse else int(in_bytes),
+                    "d2h_bytes_per_step": int(pcm_bytes), "steps": n_pk,
+                    "parser": "gpu (k_parse, one thread per stream)" if gpu_parse else "host (%d threads)" % (os.cpu_count() or 1),
+                    "parse_errors": inf["parse_errors"], "gpu_launches": int(inf["gpu_launches"] - l0p),
+                    "input": "%d looped fixture streams x %d frames replicated over %d streams" % (K, N, S)}
+
+        e2e_packets = packets_run(True)
+        e2e_packets["host_parser"] = packets_run(False)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

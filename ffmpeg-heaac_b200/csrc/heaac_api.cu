@@ -17,6 +17,7 @@
 #include <new>
 
 #include "heaac_kernels.cuh"
+#include "heaac_context.cuh"
 
 extern "C" void heaac_build_tables(HeaacDevTables *t);
 
@@ -27,38 +28,6 @@ extern "C" void heaac_build_tables(HeaacDevTables *t);
 #ifndef HEAAC_CORE_MIN_BLOCKS
 #define HEAAC_CORE_MIN_BLOCKS 4
 #endif
-
-/* ------------------------------------------------------------------------------------ */
-struct HeaacContext {
-    HeaacConfig cfg;
-    HeaacGeom geom;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    HeaacDevTables *d_tables;
-    HeaacChanState *d_chan;          /* [S][ncc] */
-    HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
-    HeaacPsState *d_ps;              /* [S] (PS only) */
-    float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
-    float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
-    /* staging for host-pointer batches, sized for max_frames_per_call */
-    /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
-     * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
-    int chunk;
-    unsigned long long seq;            /* staged chunks so far (selects the staging set) */
-    float *s_coeffs[2]; HeaacIcs *s_ics[2]; HeaacTns *s_tns[2]; HeaacSbrElem *s_sbr[2]; HeaacPsFrame *s_ps[2];
-    int16_t *s_pcm[2]; float *s_pcm_f32[2];
-    cudaStream_t s_in, s_out;
-    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
-    long long launches;
-    size_t smem_core, smem_sbr, smem_ps, smem_synth;
-    int core_grid;                   /* persistent k_core: resident CTAs on the whole GPU */
-    /* optional per-kernel event timing (heaac_b200_profile_*) */
-    int prof_on, prof_n, prof_cap;
-    cudaEvent_t *prof_ev;            /* 2 events per recorded launch */
-    unsigned char *prof_kind;        /* HEAAC_K_* per recorded launch */
-};
-
-enum { HEAAC_K_CORE = 0, HEAAC_K_SBR = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
 
 static void prof_begin(HeaacContext *c, int kind)
 {
@@ -179,7 +148,7 @@ k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
 }
 
 /* ------------------------------------------------------------------------------------ */
-static int cuda_err(cudaError_t e, const char *what)
+int heaac_cuda_err(cudaError_t e, const char *what)
 {
     if (e == cudaSuccess) return 0;
     fprintf(stderr, "heaac_b200: %s: %s\n", what, cudaGetErrorString(e));
@@ -187,7 +156,6 @@ static int cuda_err(cudaError_t e, const char *what)
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return HEAAC_E_NODEV;
     return HEAAC_E_LAUNCH;
 }
-#define CK(call) do { int r_ = cuda_err((call), #call); if (r_) return r_; } while (0)
 
 static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
 {
@@ -303,7 +271,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     build_geom(cfg, &c->geom);
     const HeaacGeom *g = &c->geom;
     int r = 0;
-#define CKX(call) do { r = cuda_err((call), #call); if (r) { heaac_b200_destroy(c); return r; } } while (0)
+#define CKX(call) do { r = heaac_cuda_err((call), #call); if (r) { heaac_b200_destroy(c); return r; } } while (0)
     CKX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKX(cudaEventCreate(&c->ev0));
     CKX(cudaEventCreate(&c->ev1));
@@ -311,8 +279,8 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
         HeaacDevTables *h = (HeaacDevTables *)malloc(sizeof(HeaacDevTables));
         if (!h) { heaac_b200_destroy(c); return HEAAC_E_NOMEM; }
         heaac_build_tables(h);
-        r = cuda_err(cudaMalloc(&c->d_tables, sizeof(HeaacDevTables)), "cudaMalloc tables");
-        if (!r) r = cuda_err(cudaMemcpy(c->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "upload tables");
+        r = heaac_cuda_err(cudaMalloc(&c->d_tables, sizeof(HeaacDevTables)), "cudaMalloc tables");
+        if (!r) r = heaac_cuda_err(cudaMemcpy(c->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "upload tables");
         free(h);
         if (r) { heaac_b200_destroy(c); return r; }
     }
@@ -404,7 +372,7 @@ extern "C" long long heaac_b200_launch_count(const HeaacContext *c) { return c ?
 extern "C" uintptr_t heaac_b200_stream(const HeaacContext *c) { return c ? (uintptr_t)c->stream : 0; }
 
 /* launches for frames [0, n) of a device-resident batch */
-static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
+int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
                          const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32)
 {
     const HeaacGeom g = c->geom;
@@ -446,7 +414,7 @@ static int launch_frames(HeaacContext *c, int n_frames, const float *coeffs, con
             c->launches++;
         }
     }
-    return cuda_err(cudaGetLastError(), "kernel launch");
+    return heaac_cuda_err(cudaGetLastError(), "kernel launch");
 }
 
 /* Enqueue a batch.  Host-pointer batches go through the double-buffered staging sets; `seq` counts staged
@@ -460,7 +428,7 @@ extern "C" int heaac_b200_synth_submit(HeaacContext *c, const HeaacBatch *b)
     if (!b->pcm && !b->pcm_f32) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
     if (b->on_device)
-        return launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32);
+        return heaac_launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32);
 
     if (b->pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;   /* context created without want_float_out */
     const size_t S = g->n_streams;
@@ -482,7 +450,7 @@ extern "C" int heaac_b200_synth_submit(HeaacContext *c, const HeaacBatch *b)
         /* kernels on the context stream: need the inputs, and the PCM staging set drained by the D2H two chunks back */
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
-        int r = launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], b->tns ? c->s_tns[buf] : nullptr, c->s_sbr[buf], c->s_ps[buf],
+        int r = heaac_launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], b->tns ? c->s_tns[buf] : nullptr, c->s_sbr[buf], c->s_ps[buf],
                               c->s_pcm[buf], b->pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
         if (r) return r;
         CK(cudaEventRecord(c->ev_done[buf], c->stream));
@@ -513,7 +481,7 @@ extern "C" int heaac_b200_wait(HeaacContext *c)
     CK(cudaStreamSynchronize(c->s_in));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->s_out));
-    return cuda_err(cudaGetLastError(), "wait");
+    return heaac_cuda_err(cudaGetLastError(), "wait");
 }
 
 extern "C" int heaac_b200_synth(HeaacContext *c, const HeaacBatch *b)
@@ -587,7 +555,7 @@ extern "C" int heaac_b200_sync(HeaacContext *c)
     if (!c) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->stream));
-    return cuda_err(cudaGetLastError(), "sync");
+    return heaac_cuda_err(cudaGetLastError(), "sync");
 }
 
 extern "C" int heaac_b200_dev_alloc(HeaacContext *c, size_t bytes, void **dptr)
@@ -725,11 +693,11 @@ extern "C" int heaac_b200_mdct_init(HeaacMdct **out, int nbits, int inverse, dou
     HeaacDevTables *h = (HeaacDevTables *)malloc(sizeof(HeaacDevTables));
     heaac_build_tables(h);
     int r = 0;
-    if (!r) r = cuda_err(cudaMalloc(&m->d_tables, sizeof(HeaacDevTables)), "cudaMalloc");
-    if (!r) r = cuda_err(cudaMemcpy(m->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "cudaMemcpy");
-    if (!r) r = cuda_err(cudaMalloc(&m->d_tcos, sizeof(float) * n4 * 2), "cudaMalloc");
-    if (!r) r = cuda_err(cudaMemcpy(m->d_tcos, tc, sizeof(float) * n4 * 2, cudaMemcpyHostToDevice), "cudaMemcpy");
-    if (!r) r = cuda_err(cudaMalloc(&m->d_in, sizeof(float) * n), "cudaMalloc");
+    if (!r) r = heaac_cuda_err(cudaMalloc(&m->d_tables, sizeof(HeaacDevTables)), "cudaMalloc");
+    if (!r) r = heaac_cuda_err(cudaMemcpy(m->d_tables, h, sizeof(HeaacDevTables), cudaMemcpyHostToDevice), "cudaMemcpy");
+    if (!r) r = heaac_cuda_err(cudaMalloc(&m->d_tcos, sizeof(float) * n4 * 2), "cudaMalloc");
+    if (!r) r = heaac_cuda_err(cudaMemcpy(m->d_tcos, tc, sizeof(float) * n4 * 2, cudaMemcpyHostToDevice), "cudaMemcpy");
+    if (!r) r = heaac_cuda_err(cudaMalloc(&m->d_in, sizeof(float) * n), "cudaMalloc");
     free(h); free(tc);
     if (r) { heaac_b200_mdct_end(m); return r; }
     m->d_tsin = m->d_tcos + n4;

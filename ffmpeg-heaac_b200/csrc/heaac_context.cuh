@@ -1,0 +1,48 @@
+/*
+ * heaac_context.cuh -- the back-end context shared by the translation units of the library
+ * (heaac_api.cu: kernels + C-ABI, heaac_parse_gpu.cu: device front end).  Internal; not part of the ABI.
+ */
+#ifndef HEAAC_CONTEXT_CUH
+#define HEAAC_CONTEXT_CUH
+#include <cuda_runtime.h>
+#include "heaac_dev.cuh"
+
+/* ------------------------------------------------------------------------------------ */
+struct HeaacContext {
+    HeaacConfig cfg;
+    HeaacGeom geom;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    HeaacDevTables *d_tables;
+    HeaacChanState *d_chan;          /* [S][ncc] */
+    HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
+    HeaacPsState *d_ps;              /* [S] (PS only) */
+    float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
+    float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
+    /* staging for host-pointer batches, sized for max_frames_per_call */
+    /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
+     * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
+    int chunk;
+    unsigned long long seq;            /* staged chunks so far (selects the staging set) */
+    float *s_coeffs[2]; HeaacIcs *s_ics[2]; HeaacTns *s_tns[2]; HeaacSbrElem *s_sbr[2]; HeaacPsFrame *s_ps[2];
+    int16_t *s_pcm[2]; float *s_pcm_f32[2];
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    long long launches;
+    size_t smem_core, smem_sbr, smem_ps, smem_synth;
+    int core_grid;                   /* persistent k_core: resident CTAs on the whole GPU */
+    /* optional per-kernel event timing (heaac_b200_profile_*) */
+    int prof_on, prof_n, prof_cap;
+    cudaEvent_t *prof_ev;            /* 2 events per recorded launch */
+    unsigned char *prof_kind;        /* HEAAC_K_* per recorded launch */
+};
+
+enum { HEAAC_K_CORE = 0, HEAAC_K_SBR = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
+
+/* launches for frames [0, n) of a device-resident batch on c->stream (heaac_api.cu) */
+int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
+                        const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32);
+int heaac_cuda_err(cudaError_t e, const char *what);
+#define CK(call) do { int _r = heaac_cuda_err((call), #call); if (_r) return _r; } while (0)
+
+#endif

@@ -47,6 +47,8 @@ struct HeaacDecoder {
     std::vector<uint8_t> extradata;
     std::vector<HeaacFrontend *> fe;
     HeaacContext *be = nullptr;
+    HeaacGpuParser *gpu = nullptr;                    /* cfg.gpu_parse: the device front end replaces fe[] + workers */
+    std::vector<int> scratch_consumed;
     int ncc = 0, nse = 0, sbr = 0, ps = 0, sr_index = 0, n_elems = 0, chunk = 1;
     uint8_t elem_type[HEAAC_MAX_ELEMS] = { 0 };
     ParamSet set[2];
@@ -178,6 +180,13 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     if ((r = heaac_b200_create(&cfg, &d->be))) return r;
 
     d->chunk = heaac_b200_chunk_frames(d->be);
+    if (d->cfg.gpu_parse) {
+        HeaacFrontend *f = nullptr;
+        if ((r = heaac_fe_open(&f, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0))) return r;
+        r = heaac_b200_parser_create(d->be, f, 0, &d->gpu);
+        heaac_fe_close(f);
+        return r;
+    }
     const size_t n = (size_t)d->chunk * d->cfg.n_streams;
     for (auto &p : d->set) {
         if (heaac_b200_host_alloc(d->be, n * d->ncc * 1024 * sizeof(float), (void **)&p.coeffs) ||
@@ -231,6 +240,7 @@ extern "C" void heaac_dec_close(HeaacDecoder *d)
     }
     for (auto &t : d->workers) t.join();
     if (d->be) heaac_b200_wait(d->be);
+    if (d->gpu) heaac_b200_parser_destroy(d->gpu);
     free_sets(d);
     for (auto f : d->fe) heaac_fe_close(f);
     if (d->be) heaac_b200_destroy(d->be);
@@ -246,6 +256,15 @@ extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *co
     if (!d->be && (r = configure(d, pkt[0], pkt_size[0]))) return r;
     if (pcm_f32 && !d->cfg.want_float_out) return HEAAC_E_INVAL;
     const size_t S = d->cfg.n_streams;
+    if (d->gpu) {
+        int *cons = consumed;
+        if (!cons) { d->scratch_consumed.resize((size_t)n_frames * S); cons = d->scratch_consumed.data(); }
+        if ((r = heaac_b200_parser_decode(d->gpu, n_frames, pkt, pkt_size, pcm, pcm_f32, cons))) return r;
+        long long bad = 0;
+        for (size_t i = 0; i < (size_t)n_frames * S; i++) bad += cons[i] < 0;
+        d->parse_errors += bad;
+        return 0;
+    }
     const size_t out_frame = S * heaac_b200_frame_out_len(d->be) * heaac_b200_n_out_channels(d->be);
     int k = 0;
     for (int f0 = 0; f0 < n_frames; f0 += d->chunk, k++) {
@@ -279,6 +298,6 @@ extern "C" int heaac_dec_info(const HeaacDecoder *d, int *n_out_channels, int *f
     if (frame_out_len) *frame_out_len = heaac_b200_frame_out_len(d->be);
     if (sbr) *sbr = d->sbr;
     if (ps) *ps = d->ps;
-    if (gpu_launches) *gpu_launches = heaac_b200_launch_count(d->be);
+    if (gpu_launches) *gpu_launches = heaac_b200_launch_count(d->be) + heaac_b200_parser_launch_count(d->gpu);
     return 1;
 }

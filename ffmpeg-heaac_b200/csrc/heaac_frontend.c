@@ -1,194 +1,114 @@
 /*
- * heaac_frontend.c -- the repo's own host front end: raw_data_block / ADTS parsing for AAC-LC, HE-AAC v1
- * and v2 into the per-frame structures of the batched C-ABI (include/heaac_b200.h).
- *
- * The serial, branchy half of the decoder stays on the host (north star).  This file restates, in own C, what
- * the reference's parsers do up to the spectral_to_sample() call site (libavcodec/aacdec.c:2078):
+ * heaac_frontend.c -- host build of the front end (heaac_fe_core.h): table construction, AudioSpecificConfig
+ * parsing and the heaac_fe_* entry points.  One HeaacFrontend per stream; different front ends may be driven
+ * from different threads.
  *   AudioSpecificConfig          mpeg4audio.c:77-130, aacdec.c:462-500
- *   ADTS header                  aac_parser.c:29-67, aacdec.c:1935-1971
- *   element loop                 aacdec.c:2002-2076
- *   ics_info / section / scalefactors / pulse / TNS / spectrum  aacdec.c:645-1245, 1332-1385
- *   CPE, M/S, intensity          aacdec.c:1390-1494
- *   fill element / implicit SBR  aacdec.c:1650-1690
- *   SBR header, grid, envelopes, noise, harmonics, extension   aacsbr.c:207-259, 609-1086
- *   PS data                      aacps.c:84-279
- * Dequantised coefficients are produced with the reference's arithmetic (|q|^(4/3) table as cbrtf(i)*i,
- * 2^((sf-200)/4) scalefactor table) so that they equal the reference's `coeffs[]` value for value.
- * Not supported (as in the scope table): PCE / channel_config 0, CCE, AAC-Main prediction, LTP, SSR, 960 frames.
  */
-#include <math.h>
-#include <stdlib.h>
-#include <string.h>
-#include "../../include/heaac_b200.h"
+#include <pthread.h>
+#include "heaac_fe_core.h"
 #include "heaac_huff_data.h"
+#include "heaac_tables_data.h"
 
-#define FE_MAX_CH 16
-
-/* ---------------------------------------------------------------- bit reader */
-typedef struct { const uint8_t *buf; int nbits, pos; } BR;
-
-static inline unsigned br_show(const BR *b, int n)            /* n <= 25; reads past the end return zero bits */
+/* ---------------------------------------------------------------- table construction (host only) */
+static void vlc_build(FeTables *T, Vlc *v, const uint32_t *codes, const uint8_t *bits, int n)
 {
-    const int byte = b->pos >> 3, avail = (b->nbits + 7) >> 3;
-    unsigned long long w = 0;
-    for (int i = 0; i < 5; i++) w = (w << 8) | (byte + i >= 0 && byte + i < avail ? b->buf[byte + i] : 0u);
-    return (unsigned)((w >> (40 - (b->pos & 7) - n)) & ((1u << n) - 1));
-}
-static inline unsigned br_get(BR *b, int n) { if (!n) return 0; unsigned v = br_show(b, n); b->pos += n; return v; }
-static inline unsigned br_get1(BR *b) { return br_get(b, 1); }
-static inline void br_skip(BR *b, int n) { b->pos += n; }
-static inline int br_left(const BR *b) { return b->nbits - b->pos; }
-
-/* ---------------------------------------------------------------- Huffman decoding */
-#define VLC_PRIM 10
-typedef struct { int n, maxlen; const uint32_t *codes; const uint8_t *bits; uint16_t lut[1 << VLC_PRIM]; } Vlc;
-
-static void vlc_build(Vlc *v, const uint32_t *codes, const uint8_t *bits, int n)
-{
-    v->n = n; v->codes = codes; v->bits = bits; v->maxlen = 0;
-    memset(v->lut, 0, sizeof(v->lut));
+    int sub_bits[1 << VLC_PRIM], sub_off[1 << VLC_PRIM], total = 1 << VLC_PRIM;
+    memset(sub_bits, 0, sizeof(sub_bits));
+    v->maxlen = 0;
     for (int i = 0; i < n; i++) {
-        int l = bits[i];
+        const int l = bits[i];
         if (l > v->maxlen) v->maxlen = l;
-        if (l && l <= VLC_PRIM) {
-            unsigned base = codes[i] << (VLC_PRIM - l);
-            for (unsigned k = 0; k < (1u << (VLC_PRIM - l)); k++) v->lut[base + k] = (uint16_t)((i << 5) | l);
+        if (l > VLC_PRIM) {
+            const unsigned prefix = codes[i] >> (l - VLC_PRIM);
+            if (l - VLC_PRIM > sub_bits[prefix]) sub_bits[prefix] = l - VLC_PRIM;
+        }
+    }
+    for (int p = 0; p < (1 << VLC_PRIM); p++) { sub_off[p] = total; total += sub_bits[p] ? 1 << sub_bits[p] : 0; }
+    if (T->pool_used + (uint32_t)total > FE_POOL_WORDS) abort();                 /* sized for the normative tables */
+    v->off = T->pool_used;
+    T->pool_used += (uint32_t)total;
+    uint32_t *tab = T->pool + v->off;
+    for (int p = 0; p < (1 << VLC_PRIM); p++)
+        if (sub_bits[p]) tab[p] = ((uint32_t)sub_off[p] << 8) | 0x80u | (uint32_t)sub_bits[p];
+    for (int i = 0; i < n; i++) {
+        const int l = bits[i];
+        if (!l) continue;
+        if (l <= VLC_PRIM) {
+            const unsigned base = codes[i] << (VLC_PRIM - l);
+            for (unsigned k = 0; k < (1u << (VLC_PRIM - l)); k++) tab[base + k] = ((uint32_t)i << 8) | (uint32_t)l;
+        } else {
+            const int r = l - VLC_PRIM;
+            const unsigned prefix = codes[i] >> r, rem = codes[i] & ((1u << r) - 1);
+            const int sb = sub_bits[prefix];
+            const unsigned base = sub_off[prefix] + (rem << (sb - r));
+            for (unsigned k = 0; k < (1u << (sb - r)); k++) tab[base + k] = ((uint32_t)i << 8) | (uint32_t)l;
         }
     }
 }
-static int vlc_get(BR *b, const Vlc *v)
+
+#define VB(v, name) vlc_build(T, &(v), name##_codes, name##_bits, (int)(sizeof(name##_bits)))
+static void fe_tables_once(void)
 {
-    unsigned e = v->lut[br_show(b, VLC_PRIM)];
-    if (e) { b->pos += e & 31; return e >> 5; }
-    for (int l = VLC_PRIM + 1; l <= v->maxlen; l++) {
-        unsigned c = br_show(b, l);
-        for (int i = 0; i < v->n; i++)
-            if (v->bits[i] == l && v->codes[i] == c) { b->pos += l; return i; }
+    FeTables *T = (FeTables *)calloc(1, sizeof(FeTables));
+    if (!T) abort();
+    VB(T->vsf, heaac_sf);
+    VB(T->vspec[0], heaac_spec1); VB(T->vspec[1], heaac_spec2); VB(T->vspec[2], heaac_spec3); VB(T->vspec[3], heaac_spec4);
+    VB(T->vspec[4], heaac_spec5); VB(T->vspec[5], heaac_spec6); VB(T->vspec[6], heaac_spec7); VB(T->vspec[7], heaac_spec8);
+    VB(T->vspec[8], heaac_spec9); VB(T->vspec[9], heaac_spec10); VB(T->vspec[10], heaac_spec11);
+    VB(T->vsbr[T_ENV_15], heaac_sbr_t_huffman_env_1_5dB); VB(T->vsbr[F_ENV_15], heaac_sbr_f_huffman_env_1_5dB);
+    VB(T->vsbr[T_ENV_BAL_15], heaac_sbr_t_huffman_env_bal_1_5dB); VB(T->vsbr[F_ENV_BAL_15], heaac_sbr_f_huffman_env_bal_1_5dB);
+    VB(T->vsbr[T_ENV_30], heaac_sbr_t_huffman_env_3_0dB); VB(T->vsbr[F_ENV_30], heaac_sbr_f_huffman_env_3_0dB);
+    VB(T->vsbr[T_ENV_BAL_30], heaac_sbr_t_huffman_env_bal_3_0dB); VB(T->vsbr[F_ENV_BAL_30], heaac_sbr_f_huffman_env_bal_3_0dB);
+    VB(T->vsbr[T_NOISE_30], heaac_sbr_t_huffman_noise_3_0dB); VB(T->vsbr[T_NOISE_BAL_30], heaac_sbr_t_huffman_noise_bal_3_0dB);
+    VB(T->vps[PS_IID_DF1], heaac_ps_huff_iid_df1); VB(T->vps[PS_IID_DT1], heaac_ps_huff_iid_dt1);
+    VB(T->vps[PS_IID_DF0], heaac_ps_huff_iid_df0); VB(T->vps[PS_IID_DT0], heaac_ps_huff_iid_dt0);
+    VB(T->vps[PS_ICC_DF], heaac_ps_huff_icc_df); VB(T->vps[PS_ICC_DT], heaac_ps_huff_icc_dt);
+    VB(T->vps[PS_IPD_DF], heaac_ps_huff_ipd_df); VB(T->vps[PS_IPD_DT], heaac_ps_huff_ipd_dt);
+    VB(T->vps[PS_OPD_DF], heaac_ps_huff_opd_df); VB(T->vps[PS_OPD_DT], heaac_ps_huff_opd_dt);
+    for (int i = 0; i < 428; i++) T->pow2sf[i] = pow(2, (i - 200) / 4.);
+    for (int i = 0; i < 8192; i++) T->pow43[i] = cbrtf(i) * i;
+    for (int i = 0; i < 16; i++) T->cb_val[i] = (float)pow(i, 4.0 / 3.0);      /* == the correctly rounded literals */
+    for (int bk = 0; bk < 11; bk++) {                                         /* index = sum (q_j + off) range^(dim-1-j) */
+        const int bt = bk + 1, dim = bt < 5 ? 4 : 2;
+        const int range = bt < 5 ? 3 : bt < 7 ? 9 : bt < 9 ? 8 : bt < 11 ? 13 : 17;
+        const int lav = (bt == 1 || bt == 2) ? 1 : (bt == 5 || bt == 6) ? 4 : 0;
+        for (int code = 0; code < spec_sizes[bk]; code++) {
+            int c = code;
+            for (int d = dim - 1; d >= 0; d--) {
+                const int q = c % range - lav;
+                c /= range;
+                T->spec_val[bk][code][d] = q < 0 ? -T->cb_val[-q] : T->cb_val[q > 15 ? 0 : q];     /* 16 = escape marker */
+            }
+        }
     }
-    b->pos += v->maxlen;
-    return -1;
+    memcpy(T->tns_map, heaac_tns_map, sizeof(T->tns_map));
+    memcpy(T->swb1024, heaac_swb_offset_1024, sizeof(T->swb1024));
+    memcpy(T->swb128, heaac_swb_offset_128, sizeof(T->swb128));
+    memcpy(T->num_swb1024, heaac_num_swb_1024, sizeof(T->num_swb1024));
+    memcpy(T->num_swb128, heaac_num_swb_128, sizeof(T->num_swb128));
+    fe_tb_host = T;
 }
+static pthread_once_t fe_once = PTHREAD_ONCE_INIT;
+static void fe_tables(void) { pthread_once(&fe_once, fe_tables_once); }
 
-static Vlc vlc_sf, vlc_spec[11], vlc_sbr[10], vlc_ps[10];
-static float pow2sf_tab[428], pow43_tab[8192], cb_val[16];
-static int tables_ready;
-static const int spec_sizes[11] = { 81, 81, 81, 81, 81, 81, 64, 64, 169, 169, 289 };
-
-enum { T_ENV_15, F_ENV_15, T_ENV_BAL_15, F_ENV_BAL_15, T_ENV_30, F_ENV_30, T_ENV_BAL_30, F_ENV_BAL_30, T_NOISE_30, T_NOISE_BAL_30 };
-static const int8_t sbr_lav[10] = { 60, 60, 24, 24, 31, 31, 12, 12, 31, 12 };      /* aacsbr.c:73-74 */
-enum { PS_IID_DF1, PS_IID_DT1, PS_IID_DF0, PS_IID_DT0, PS_ICC_DF, PS_ICC_DT, PS_IPD_DF, PS_IPD_DT, PS_OPD_DF, PS_OPD_DT };
-static const int8_t ps_off[10] = { 30, 30, 14, 14, 7, 7, 0, 0, 0, 0 };             /* aacpsdata.c:136-142 */
-
-#define VB(v, name) vlc_build(&(v), name##_codes, name##_bits, (int)(sizeof(name##_bits)))
-static void fe_tables(void)
+/* the built tables, for the device front end to upload (heaac_parse_gpu.cu) */
+const void *heaac_fe_tables_blob(size_t *bytes)
 {
-    if (tables_ready) return;
-    VB(vlc_sf, heaac_sf);
-    VB(vlc_spec[0], heaac_spec1); VB(vlc_spec[1], heaac_spec2); VB(vlc_spec[2], heaac_spec3); VB(vlc_spec[3], heaac_spec4);
-    VB(vlc_spec[4], heaac_spec5); VB(vlc_spec[5], heaac_spec6); VB(vlc_spec[6], heaac_spec7); VB(vlc_spec[7], heaac_spec8);
-    VB(vlc_spec[8], heaac_spec9); VB(vlc_spec[9], heaac_spec10); VB(vlc_spec[10], heaac_spec11);
-    VB(vlc_sbr[T_ENV_15], heaac_sbr_t_huffman_env_1_5dB); VB(vlc_sbr[F_ENV_15], heaac_sbr_f_huffman_env_1_5dB);
-    VB(vlc_sbr[T_ENV_BAL_15], heaac_sbr_t_huffman_env_bal_1_5dB); VB(vlc_sbr[F_ENV_BAL_15], heaac_sbr_f_huffman_env_bal_1_5dB);
-    VB(vlc_sbr[T_ENV_30], heaac_sbr_t_huffman_env_3_0dB); VB(vlc_sbr[F_ENV_30], heaac_sbr_f_huffman_env_3_0dB);
-    VB(vlc_sbr[T_ENV_BAL_30], heaac_sbr_t_huffman_env_bal_3_0dB); VB(vlc_sbr[F_ENV_BAL_30], heaac_sbr_f_huffman_env_bal_3_0dB);
-    VB(vlc_sbr[T_NOISE_30], heaac_sbr_t_huffman_noise_3_0dB); VB(vlc_sbr[T_NOISE_BAL_30], heaac_sbr_t_huffman_noise_bal_3_0dB);
-    VB(vlc_ps[PS_IID_DF1], heaac_ps_huff_iid_df1); VB(vlc_ps[PS_IID_DT1], heaac_ps_huff_iid_dt1);
-    VB(vlc_ps[PS_IID_DF0], heaac_ps_huff_iid_df0); VB(vlc_ps[PS_IID_DT0], heaac_ps_huff_iid_dt0);
-    VB(vlc_ps[PS_ICC_DF], heaac_ps_huff_icc_df); VB(vlc_ps[PS_ICC_DT], heaac_ps_huff_icc_dt);
-    VB(vlc_ps[PS_IPD_DF], heaac_ps_huff_ipd_df); VB(vlc_ps[PS_IPD_DT], heaac_ps_huff_ipd_dt);
-    VB(vlc_ps[PS_OPD_DF], heaac_ps_huff_opd_df); VB(vlc_ps[PS_OPD_DT], heaac_ps_huff_opd_dt);
-    for (int i = 0; i < 428; i++) pow2sf_tab[i] = pow(2, (i - 200) / 4.);      /* aac_tablegen.h:33-38 */
-    for (int i = 0; i < 8192; i++) pow43_tab[i] = cbrtf(i) * i;               /* escapes: cbrt_tablegen.h:35-44 */
-    for (int i = 0; i < 16; i++) cb_val[i] = (float)pow(i, 4.0 / 3.0);        /* in-book values: correctly rounded
-                                                                                  * literals of codebook_vector*_vals, aactab.c:899-1008 */
-    tables_ready = 1;
+    fe_tables();
+    if (bytes) *bytes = sizeof(FeTables);
+    return fe_tb_host;
 }
+size_t heaac_fe_state_size(void) { return sizeof(FE); }
 
-#include "heaac_tables_data.h"
-static const uint16_t *heaac_fe_swb_offset(int sr_index, int is8, int *num_swb)
-{
-    *num_swb = is8 ? heaac_num_swb_128[sr_index] : heaac_num_swb_1024[sr_index];
-    return is8 ? heaac_swb_offset_128[sr_index] : heaac_swb_offset_1024[sr_index];
-}
-
-/* ---------------------------------------------------------------- state */
-typedef struct FeChan {
-    int ws[2], shape[2];                        /* window_sequence / use_kb_window [current, previous] */
-    int max_sfb, num_groups, group_len[8], num_windows, num_swb;
-    const uint16_t *swb;
-    uint8_t band_type[128];
-    uint8_t run_end[128];
-    float sf[128];
-    HeaacTns tns; int tns_present;
-} FeChan;
-
-typedef struct FeSbrCh {
-    int frame_class, num_env, num_noise, amp_res, add_harmonic_flag;
-    uint8_t freq_res[8], t_env[8], t_q[4], df_env[5], df_noise[2], invf[2][5], add_harmonic[48];
-    int e_a[2], t_env_num_env_old;
-    int env[6][48], noise[3][5];                /* row 0 = last row of the previous frame (delta-time base) */
-} FeSbrCh;
-
-typedef struct FeSbr {
-    int start, reset, amp_res_header, coupling;
-    int start_freq, stop_freq, xover, freq_scale, alter_scale, noise_bands;
-    int limiter_bands, limiter_gains, interpol_freq, smoothing_mode;
-    HeaacSbrElem t;                             /* derived tables + kx/m */
-    FeSbrCh ch[2];
-} FeSbr;
-
-typedef struct FePs {
-    int start, enable_iid, iid_quant, nr_iid_par, nr_ipdopd_par, enable_icc, icc_mode, nr_icc_par, enable_ext;
-    int frame_class, num_env_old, num_env, enable_ipdopd, is34, is34_old;
-    int border[6];
-    int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
-} FePs;
-
-struct HeaacFrontend {
-    int sample_rate, sr_index, chan_config, object_type;
-    int sbr, ps;                                /* -1 unknown (implicit signalling), 0 absent, 1 present */
-    int ext_sample_rate, locked;
-    int n_elems, elem_type[HEAAC_MAX_ELEMS];
-    int elem_ch0[HEAAC_MAX_ELEMS];              /* first core channel of each element */
-    int ncc, nse;
-    int sf_offset;                              /* 60: s16-unit scaling, 0: C bias scaling (aacdec.c:573-581) */
-    int random_state;
-    FeChan ch[FE_MAX_CH];
-    FeSbr sbr_el[HEAAC_MAX_ELEMS];
-    FePs psx;
-    float *coeffs;                              /* current frame output [ncc][1024] */
-};
-typedef struct HeaacFrontend FE;
-
-static const int sample_rates[16] = { 96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000, 7350, 0, 0, 0 };
-
-/* ---------------------------------------------------------------- configuration */
-static int set_layout(FE *fe, int chan_config)
-{
-    static const int lay[8][6] = {   /* element types in bitstream order (set_default_channel_config, aacdec.c) */
-        { 0 }, { 1, HEAAC_TYPE_SCE }, { 1, HEAAC_TYPE_CPE }, { 2, HEAAC_TYPE_SCE, HEAAC_TYPE_CPE },
-        { 3, HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_SCE }, { 3, HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE },
-        { 4, HEAAC_TYPE_SCE, HEAAC_TYPE_CPE, HEAAC_TYPE_CPE, HEAAC_TYPE_LFE }, { 0 } };
-    if (chan_config < 1 || chan_config > 6) return HEAAC_E_UNSUPPORTED;
-    fe->chan_config = chan_config;
-    fe->n_elems = lay[chan_config][0];
-    fe->ncc = fe->nse = 0;
-    for (int e = 0; e < fe->n_elems; e++) {
-        fe->elem_type[e] = lay[chan_config][1 + e];
-        fe->elem_ch0[e] = fe->ncc;
-        fe->ncc += fe->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
-        fe->nse += fe->elem_type[e] != HEAAC_TYPE_LFE;
-    }
-    return 0;
-}
-
+/* ---------------------------------------------------------------- configuration (host only) */
 static int get_aot(BR *b) { int t = br_get(b, 5); if (t == 31) t = 32 + br_get(b, 6); return t; }
 static int get_rate(BR *b, int *idx) { *idx = br_get(b, 4); return *idx == 15 ? (int)br_get(b, 24) : sample_rates[*idx]; }
 
 /* AudioSpecificConfig, mpeg4audio.c:77-130 + GASpecificConfig aacdec.c:425-455 */
 static int parse_asc(FE *fe, const uint8_t *d, int size)
 {
-    BR b = { d, size * 8, 0 };
+    BR b;
+    br_init(&b, d, size);
     int idx, ext_idx;
     fe->object_type = get_aot(&b);
     fe->sample_rate = get_rate(&b, &idx);
@@ -221,6 +141,7 @@ static int parse_asc(FE *fe, const uint8_t *d, int size)
     return set_layout(fe, chan_config);
 }
 
+
 int heaac_fe_open(FE **out, const uint8_t *extradata, int extradata_size, int sample_rate, int channels, int bias_mode)
 {
     if (!out) return HEAAC_E_INVAL;
@@ -244,671 +165,10 @@ int heaac_fe_open(FE **out, const uint8_t *extradata, int extradata_size, int sa
         fe->sbr_el[e].t.kx[0] = fe->sbr_el[e].t.kx[1] = 32;
         fe->sbr_el[e].ch[0].e_a[1] = fe->sbr_el[e].ch[1].e_a[1] = -1;
     }
-    fe->coeffs = (float *)calloc(FE_MAX_CH * 1024, sizeof(float));
     *out = fe;
     return 0;
 }
-void heaac_fe_close(FE *fe) { if (fe) { free(fe->coeffs); free(fe); } }
-
-/* ---------------------------------------------------------------- ICS */
-static int ics_info(FE *fe, FeChan *c, BR *b)                     /* aacdec.c:645-710 */
-{
-    if (br_get1(b)) return HEAAC_E_INVAL;
-    c->ws[1] = c->ws[0]; c->ws[0] = br_get(b, 2);
-    c->shape[1] = c->shape[0]; c->shape[0] = br_get1(b);
-    c->num_groups = 1; c->group_len[0] = 1;
-    if (c->ws[0] == HEAAC_EIGHT_SHORT) {
-        c->max_sfb = br_get(b, 4);
-        for (int i = 0; i < 7; i++) {
-            if (br_get1(b)) c->group_len[c->num_groups - 1]++;
-            else { c->num_groups++; c->group_len[c->num_groups - 1] = 1; }
-        }
-        c->num_windows = 8;
-        c->swb = heaac_fe_swb_offset(fe->sr_index, 1, &c->num_swb);
-    } else {
-        c->max_sfb = br_get(b, 6);
-        c->num_windows = 1;
-        c->swb = heaac_fe_swb_offset(fe->sr_index, 0, &c->num_swb);
-        if (br_get1(b)) return HEAAC_E_UNSUPPORTED;                /* predictor_data_present: not AAC-LC */
-    }
-    if (c->max_sfb > c->num_swb) return HEAAC_E_INVAL;
-    return 0;
-}
-
-static int band_types(FeChan *c, BR *b)                           /* aacdec.c:720-756 */
-{
-    int idx = 0;
-    const int bits = c->ws[0] == HEAAC_EIGHT_SHORT ? 3 : 5;
-    for (int g = 0; g < c->num_groups; g++) {
-        int k = 0;
-        while (k < c->max_sfb) {
-            int end = k, incr, bt = br_get(b, 4);
-            if (bt == 12) return HEAAC_E_INVAL;
-            while ((incr = br_get(b, bits)) == (1 << bits) - 1) end += incr;
-            end += incr;
-            if (br_left(b) < 0 || end > c->max_sfb) return HEAAC_E_INVAL;
-            for (; k < end; k++) { c->band_type[idx] = bt; c->run_end[idx++] = end; }
-        }
-    }
-    return 0;
-}
-
-static int scalefactors(FE *fe, FeChan *c, BR *b, int global_gain)     /* aacdec.c:768-822 */
-{
-    const int sf_offset = fe->sf_offset + (c->ws[0] == HEAAC_EIGHT_SHORT ? 12 : 0);
-    int idx = 0, noise_flag = 1;
-    int offset[3] = { global_gain, global_gain - 90, 100 };
-    for (int g = 0; g < c->num_groups; g++) {
-        for (int i = 0; i < c->max_sfb;) {
-            int end = c->run_end[idx], bt = c->band_type[idx];
-            if (bt == 0) {
-                for (; i < end; i++, idx++) c->sf[idx] = 0.f;
-            } else if (bt == 14 || bt == 15) {
-                for (; i < end; i++, idx++) {
-                    offset[2] += vlc_get(b, &vlc_sf) - 60;
-                    if ((unsigned)offset[2] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = pow2sf_tab[-offset[2] + 300];
-                }
-            } else if (bt == 13) {
-                for (; i < end; i++, idx++) {
-                    if (noise_flag-- > 0) offset[1] += br_get(b, 9) - 256;
-                    else offset[1] += vlc_get(b, &vlc_sf) - 60;
-                    if ((unsigned)offset[1] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = -pow2sf_tab[offset[1] + sf_offset + 100];
-                }
-            } else {
-                for (; i < end; i++, idx++) {
-                    offset[0] += vlc_get(b, &vlc_sf) - 60;
-                    if ((unsigned)offset[0] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = -pow2sf_tab[offset[0] + sf_offset];
-                }
-            }
-        }
-    }
-    return 0;
-}
-
-static int tns_data(FeChan *c, BR *b)                             /* aacdec.c:854-887 */
-{
-    const int is8 = c->ws[0] == HEAAC_EIGHT_SHORT;
-    const int max_order = is8 ? 7 : 12;
-    memset(&c->tns, 0, sizeof(c->tns));
-    for (int w = 0; w < c->num_windows; w++) {
-        int nf = br_get(b, 2 - is8);
-        c->tns.n_filt[w] = nf;
-        if (!nf) continue;
-        int coef_res = br_get1(b);
-        for (int f = 0; f < nf; f++) {
-            int slot = is8 ? w : f;
-            c->tns.length[slot] = br_get(b, 6 - 2 * is8);
-            int order = br_get(b, 5 - 2 * is8);
-            if (order > max_order) return HEAAC_E_INVAL;
-            c->tns.order[slot] = order;
-            if (order) {
-                c->tns.direction[slot] = br_get1(b);
-                int compress = br_get1(b), len = coef_res + 3 - compress, map = 2 * compress + coef_res;
-                for (int i = 0; i < order; i++) c->tns.coef[slot][i] = heaac_tns_map[map][br_get(b, len)];
-            }
-        }
-    }
-    return 0;
-}
-
-/* spectral data + dequantisation, aacdec.c:988-1245.  Value of a coefficient: sign * |q|^(4/3) * sf with the
- * products evaluated exactly as the reference does (table value times scalefactor). */
-static int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, const int *ppos, const int *pamp, int npulse)
-{
-    const int cw = 1024 / c->num_windows;
-    const uint16_t *off = c->swb;
-    float *base = coef;
-    int idx = 0;
-    for (int g = 0; g < c->num_windows; g++)
-        memset(coef + g * 128 + off[c->max_sfb], 0, sizeof(float) * (cw - off[c->max_sfb]));
-    for (int g = 0; g < c->num_groups; g++) {
-        int glen = c->group_len[g];
-        for (int i = 0; i < c->max_sfb; i++, idx++) {
-            const int bt = c->band_type[idx];
-            float *cfo = coef + off[i];
-            const int len = off[i + 1] - off[i];
-            const float sf = c->sf[idx];
-            if (bt == 0 || bt >= 14) {
-                for (int w = 0; w < glen; w++, cfo += 128) memset(cfo, 0, len * sizeof(float));
-            } else if (bt == 13) {                                 /* PNS, aacdec.c:1021-1036 */
-                for (int w = 0; w < glen; w++, cfo += 128) {
-                    float energy = 0.0f;
-                    for (int k = 0; k < len; k++) {
-                        fe->random_state = (int)((unsigned)fe->random_state * 1664525u + 1013904223u);   /* lcg_random, aacdec.c:508-511 */
-                        cfo[k] = fe->random_state;
-                    }
-                    for (int k = 0; k < len; k++) energy += cfo[k] * cfo[k];
-                    float scale = sf / sqrtf(energy);
-                    for (int k = 0; k < len; k++) cfo[k] = cfo[k] * scale;
-                }
-            } else {
-                const Vlc *v = &vlc_spec[bt - 1];
-                const int dim = bt < 5 ? 4 : 2;
-                const int is_signed = bt == 1 || bt == 2 || bt == 5 || bt == 6;
-                const int range = bt < 3 ? 3 : bt < 5 ? 3 : bt < 7 ? 9 : bt < 9 ? 8 : bt < 11 ? 13 : 17;
-                const int lav = bt < 3 ? 1 : bt < 7 ? 4 : 0;       /* offset of the signed books (1,2: 1; 5,6: 4) */
-                for (int w = 0; w < glen; w++, cfo += 128) {
-                    for (int k = 0; k < len; k += dim) {
-                        int code = vlc_get(b, v);
-                        if (code < 0 || code >= spec_sizes[bt - 1]) return HEAAC_E_INVAL;
-                        int q[4];
-                        for (int d = dim - 1; d >= 0; d--) { q[d] = code % range; code /= range; }
-                        if (is_signed) {
-                            for (int d = 0; d < dim; d++) {
-                                int s = q[d] - lav;
-                                float m = cb_val[s < 0 ? -s : s];
-                                cfo[k + d] = (s < 0 ? -m : m) * sf;
-                            }
-                        } else {
-                            int neg[4];
-                            for (int d = 0; d < dim; d++) neg[d] = q[d] ? (int)br_get1(b) : 0;
-                            for (int d = 0; d < dim; d++) {
-                                int m = q[d];
-                                float val;
-                                if (bt == 11 && m == 16) {         /* escape sequence, aacdec.c:1177-1209 */
-                                    int n = 0;
-                                    while (br_get1(b)) { if (++n > 8) return HEAAC_E_INVAL; }
-                                    n += 4;
-                                    val = pow43_tab[(1 << n) + br_get(b, n)];
-                                } else
-                                    val = cb_val[m];
-                                cfo[k + d] = (neg[d] ? -val : val) * sf;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        coef += glen << 7;
-    }
-    if (pulse_present) {                                           /* aacdec.c:1219-1234 */
-        idx = 0;
-        for (int i = 0; i < npulse; i++) {
-            float co = base[ppos[i]];
-            while (off[idx + 1] <= ppos[i]) idx++;
-            if (c->band_type[idx] != 13 && c->sf[idx]) {
-                float ico = -pamp[i];
-                if (co) {
-                    co /= c->sf[idx];
-                    ico = co / sqrtf(sqrtf(fabsf(co))) + (co > 0 ? -ico : ico);
-                }
-                base[ppos[i]] = cbrtf(fabsf(ico)) * ico * c->sf[idx];
-            }
-        }
-    }
-    return 0;
-}
-
-static int decode_ics(FE *fe, FeChan *c, BR *b, float *coef, int common_window)       /* aacdec.c:1332-1385 */
-{
-    int r, ppos[4], pamp[4], npulse = 0, pulse_present;
-    int global_gain = br_get(b, 8);
-    if (!common_window && (r = ics_info(fe, c, b))) return r;
-    if ((r = band_types(c, b))) return r;
-    if ((r = scalefactors(fe, c, b, global_gain))) return r;
-    if ((pulse_present = br_get1(b))) {                            /* aacdec.c:829-847 */
-        if (c->ws[0] == HEAAC_EIGHT_SHORT) return HEAAC_E_INVAL;
-        npulse = br_get(b, 2) + 1;
-        int swb = br_get(b, 6);
-        if (swb >= c->num_swb) return HEAAC_E_INVAL;
-        ppos[0] = c->swb[swb] + br_get(b, 5);
-        if (ppos[0] > 1023) return HEAAC_E_INVAL;
-        pamp[0] = br_get(b, 4);
-        for (int i = 1; i < npulse; i++) {
-            ppos[i] = br_get(b, 5) + ppos[i - 1];
-            if (ppos[i] > 1023) return HEAAC_E_INVAL;
-            pamp[i] = br_get(b, 4);
-        }
-    }
-    if ((c->tns_present = br_get1(b)) && (r = tns_data(c, b))) return r;
-    if (br_get1(b)) return HEAAC_E_UNSUPPORTED;                    /* gain control (SSR) */
-    return spectrum(fe, c, b, coef, pulse_present, ppos, pamp, npulse);
-}
-
-static int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *co1)  /* aacdec.c:1460-1494 */
-{
-    uint8_t ms_mask[128];
-    int r, ms_present = 0;
-    int common = br_get1(b);
-    memset(ms_mask, 0, sizeof(ms_mask));
-    if (common) {
-        if ((r = ics_info(fe, c0, b))) return r;
-        int keep = c1->shape[0];
-        c1->ws[0] = c0->ws[0]; c1->ws[1] = c0->ws[1]; c1->shape[0] = c0->shape[0]; c1->shape[1] = keep;
-        c1->max_sfb = c0->max_sfb; c1->num_groups = c0->num_groups; memcpy(c1->group_len, c0->group_len, sizeof(c0->group_len));
-        c1->num_windows = c0->num_windows; c1->num_swb = c0->num_swb; c1->swb = c0->swb;
-        ms_present = br_get(b, 2);
-        if (ms_present == 3) return HEAAC_E_INVAL;
-        if (ms_present == 1) for (int i = 0; i < c0->num_groups * c0->max_sfb; i++) ms_mask[i] = br_get1(b);
-        else if (ms_present == 2) memset(ms_mask, 1, c0->num_groups * c0->max_sfb);
-    }
-    if ((r = decode_ics(fe, c0, b, co0, common))) return r;
-    if ((r = decode_ics(fe, c1, b, co1, common))) return r;
-    if (common && ms_present) {                                    /* apply_mid_side_stereo, aacdec.c:1390-1411 */
-        float *a = co0, *d = co1;
-        int idx = 0;
-        for (int g = 0; g < c0->num_groups; g++) {
-            for (int i = 0; i < c0->max_sfb; i++, idx++) {
-                if (ms_mask[idx] && c0->band_type[idx] < 13 && c1->band_type[idx] < 13)
-                    for (int w = 0; w < c0->group_len[g]; w++)
-                        for (int k = c0->swb[i]; k < c0->swb[i + 1]; k++) {
-                            float t = a[w * 128 + k] - d[w * 128 + k];
-                            a[w * 128 + k] += d[w * 128 + k];
-                            d[w * 128 + k] = t;
-                        }
-            }
-            a += c0->group_len[g] * 128; d += c0->group_len[g] * 128;
-        }
-    }
-    {                                                              /* apply_intensity_stereo, aacdec.c:1420-1452 */
-        float *a = co0, *d = co1;
-        int idx = 0;
-        for (int g = 0; g < c1->num_groups; g++) {
-            for (int i = 0; i < c1->max_sfb;) {
-                if (c1->band_type[idx] == 14 || c1->band_type[idx] == 15) {
-                    int end = c1->run_end[idx];
-                    for (; i < end; i++, idx++) {
-                        int cs = -1 + 2 * (c1->band_type[idx] - 14);
-                        if (ms_present) cs *= 1 - 2 * ms_mask[idx];
-                        float scale = cs * c1->sf[idx];
-                        for (int w = 0; w < c1->group_len[g]; w++)
-                            for (int k = c1->swb[i]; k < c1->swb[i + 1]; k++) d[w * 128 + k] = scale * a[w * 128 + k];
-                    }
-                } else {
-                    int end = c1->run_end[idx];
-                    idx += end - i; i = end;
-                }
-            }
-            a += c1->group_len[g] * 128; d += c1->group_len[g] * 128;
-        }
-    }
-    return 0;
-}
-
-/* ---------------------------------------------------------------- SBR */
-static const int8_t ceil_log2[6] = { 0, 1, 2, 2, 3, 3 };
-
-static int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, aacsbr.c:1023-1034 */
-{
-    HeaacSbrElem t = s->t;
-    int r = heaac_b200_sbr_tables(fe->sample_rate, s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale,
-                                  s->noise_bands, s->limiter_bands, &t);
-    if (r) return r;
-    s->t = t;
-    return 0;
-}
-
-static void sbr_header(FE *fe, FeSbr *s, BR *b)                   /* read_sbr_header, aacsbr.c:207-259 */
-{
-    int old[6] = { s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale, s->noise_bands };
-    int old_lim = s->limiter_bands;
-    s->start = 1;
-    s->amp_res_header = br_get1(b);
-    s->start_freq = br_get(b, 4); s->stop_freq = br_get(b, 4); s->xover = br_get(b, 3);
-    br_skip(b, 2);
-    int extra1 = br_get1(b), extra2 = br_get1(b);
-    if (extra1) { s->freq_scale = br_get(b, 2); s->alter_scale = br_get1(b); s->noise_bands = br_get(b, 2); }
-    else { s->freq_scale = 2; s->alter_scale = 1; s->noise_bands = 2; }
-    int now[6] = { s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale, s->noise_bands };
-    if (memcmp(old, now, sizeof(old))) s->reset = 1;
-    if (extra2) { s->limiter_bands = br_get(b, 2); s->limiter_gains = br_get(b, 2); s->interpol_freq = br_get1(b); s->smoothing_mode = br_get1(b); }
-    else { s->limiter_bands = 2; s->limiter_gains = 2; s->interpol_freq = 1; s->smoothing_mode = 1; }
-    if (s->limiter_bands != old_lim && !s->reset) {               /* sbr_make_f_tablelim only */
-        HeaacSbrElem t = s->t;
-        if (!heaac_b200_sbr_tables(fe->sample_rate, s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale,
-                                   s->noise_bands, s->limiter_bands, &t)) {
-            memcpy(s->t.f_tablelim, t.f_tablelim, sizeof(t.f_tablelim));
-            s->t.n_lim = t.n_lim;
-        }
-    }
-}
-
-static int sbr_grid(FeSbr *s, FeSbrCh *c, BR *b)                  /* read_sbr_grid, aacsbr.c:609-749 */
-{
-    unsigned ptr = 0;
-    int abs_trail = 16, nlead, ntrail, i;
-    int num_env_old = c->num_env;
-    c->freq_res[0] = c->freq_res[c->num_env];
-    c->amp_res = s->amp_res_header;
-    c->t_env_num_env_old = c->t_env[num_env_old];
-    switch (c->frame_class = br_get(b, 2)) {
-    case 0:
-        c->num_env = 1 << br_get(b, 2);
-        nlead = c->num_env - 1;
-        if (c->num_env == 1) c->amp_res = 0;
-        if (c->num_env > 4) return -1;
-        c->t_env[0] = 0; c->t_env[c->num_env] = abs_trail;
-        abs_trail = (abs_trail + (c->num_env >> 1)) / c->num_env;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + abs_trail;
-        c->freq_res[1] = br_get1(b);
-        for (i = 1; i < c->num_env; i++) c->freq_res[i + 1] = c->freq_res[1];
-        break;
-    case 1:
-        abs_trail += br_get(b, 2); ntrail = br_get(b, 2);
-        c->num_env = ntrail + 1;
-        c->t_env[0] = 0; c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < ntrail; i++) c->t_env[c->num_env - 1 - i] = c->t_env[c->num_env - i] - 2 * br_get(b, 2) - 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[c->num_env - i] = br_get1(b);
-        break;
-    case 2:
-        c->t_env[0] = br_get(b, 2); nlead = br_get(b, 2);
-        c->num_env = nlead + 1;
-        c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + 2 * br_get(b, 2) + 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[i + 1] = br_get1(b);
-        break;
-    default:
-        c->t_env[0] = br_get(b, 2); abs_trail += br_get(b, 2);
-        nlead = br_get(b, 2); ntrail = br_get(b, 2);
-        c->num_env = nlead + ntrail + 1;
-        if (c->num_env > 5) return -1;
-        c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + 2 * br_get(b, 2) + 2;
-        for (i = 0; i < ntrail; i++) c->t_env[c->num_env - 1 - i] = c->t_env[c->num_env - i] - 2 * br_get(b, 2) - 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[i + 1] = br_get1(b);
-        break;
-    }
-    if (ptr > (unsigned)c->num_env + 1) return -1;
-    for (i = 1; i <= c->num_env; i++) if (c->t_env[i - 1] > c->t_env[i]) return -1;
-    c->num_noise = (c->num_env > 1) + 1;
-    c->t_q[0] = c->t_env[0]; c->t_q[c->num_noise] = c->t_env[c->num_env];
-    if (c->num_noise > 1) {
-        unsigned idx;
-        if (c->frame_class == 0) idx = c->num_env >> 1;
-        else if (c->frame_class & 1) {                             /* FFMAX(bs_pointer - 1, 1) on an UNSIGNED pointer: 0 wraps, aacsbr.c:729 */
-            unsigned a = ptr - 1u;
-            idx = (unsigned)c->num_env - (a > 1u ? a : 1u);
-        }
-        else idx = !ptr ? 1 : (ptr == 1 ? (unsigned)c->num_env - 1 : ptr - 1);
-        c->t_q[1] = c->t_env[idx];
-    }
-    c->e_a[0] = -(c->e_a[1] != num_env_old);
-    c->e_a[1] = -1;
-    if ((c->frame_class & 1) && ptr) c->e_a[1] = c->num_env + 1 - ptr;
-    else if (c->frame_class == 2 && ptr > 1) c->e_a[1] = ptr - 1;
-    return 0;
-}
-
-static void sbr_copy_grid(FeSbrCh *d, const FeSbrCh *s)           /* copy_sbr_grid, aacsbr.c:751-766 */
-{
-    d->freq_res[0] = d->freq_res[d->num_env];
-    d->t_env_num_env_old = d->t_env[d->num_env];
-    d->e_a[0] = -(d->e_a[1] != d->num_env);
-    memcpy(d->freq_res + 1, s->freq_res + 1, 6);
-    memcpy(d->t_env, s->t_env, sizeof(d->t_env));
-    memcpy(d->t_q, s->t_q, 3);
-    d->num_env = s->num_env; d->amp_res = s->amp_res; d->num_noise = s->num_noise;
-    d->frame_class = s->frame_class; d->e_a[1] = s->e_a[1];
-}
-
-static void sbr_dtdf(FeSbrCh *c, BR *b)
-{
-    for (int i = 0; i < c->num_env; i++) c->df_env[i] = br_get1(b);
-    for (int i = 0; i < c->num_noise; i++) c->df_noise[i] = br_get1(b);
-}
-static void sbr_invf(FeSbr *s, FeSbrCh *c, BR *b)
-{
-    memcpy(c->invf[1], c->invf[0], 5);
-    for (int i = 0; i < s->t.n_q; i++) c->invf[0][i] = br_get(b, 2);
-}
-
-static void sbr_envelope(FeSbr *s, FeSbrCh *c, BR *b, int ch)     /* read_sbr_envelope, aacsbr.c:787-854 */
-{
-    int bits, th, fh;
-    const int delta = (ch == 1 && s->coupling == 1) + 1, odd = s->t.n[1] & 1;
-    if (s->coupling && ch) {
-        if (c->amp_res) { bits = 5; th = T_ENV_BAL_30; fh = F_ENV_BAL_30; } else { bits = 6; th = T_ENV_BAL_15; fh = F_ENV_BAL_15; }
-    } else {
-        if (c->amp_res) { bits = 6; th = T_ENV_30; fh = F_ENV_30; } else { bits = 7; th = T_ENV_15; fh = F_ENV_15; }
-    }
-    for (int i = 0; i < c->num_env; i++) {
-        const int nb = s->t.n[c->freq_res[i + 1]];
-        if (c->df_env[i]) {
-            if (c->freq_res[i + 1] == c->freq_res[i]) {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][j] + delta * (vlc_get(b, &vlc_sbr[th]) - sbr_lav[th]);
-            } else if (c->freq_res[i + 1]) {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][(j + odd) >> 1] + delta * (vlc_get(b, &vlc_sbr[th]) - sbr_lav[th]);
-            } else {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][j ? 2 * j - odd : 0] + delta * (vlc_get(b, &vlc_sbr[th]) - sbr_lav[th]);
-            }
-        } else {
-            c->env[i + 1][0] = delta * br_get(b, bits);
-            for (int j = 1; j < nb; j++) c->env[i + 1][j] = c->env[i + 1][j - 1] + delta * (vlc_get(b, &vlc_sbr[fh]) - sbr_lav[fh]);
-        }
-    }
-    memcpy(c->env[0], c->env[c->num_env], sizeof(c->env[0]));
-}
-
-static void sbr_noise(FeSbr *s, FeSbrCh *c, BR *b, int ch)        /* read_sbr_noise, aacsbr.c:856-890 */
-{
-    int th, fh;
-    const int delta = (ch == 1 && s->coupling == 1) + 1;
-    if (s->coupling && ch) { th = T_NOISE_BAL_30; fh = F_ENV_BAL_30; } else { th = T_NOISE_30; fh = F_ENV_30; }
-    for (int i = 0; i < c->num_noise; i++) {
-        if (c->df_noise[i]) {
-            for (int j = 0; j < s->t.n_q; j++) c->noise[i + 1][j] = c->noise[i][j] + delta * (vlc_get(b, &vlc_sbr[th]) - sbr_lav[th]);
-        } else {
-            c->noise[i + 1][0] = delta * br_get(b, 5);
-            for (int j = 1; j < s->t.n_q; j++) c->noise[i + 1][j] = c->noise[i + 1][j - 1] + delta * (vlc_get(b, &vlc_sbr[fh]) - sbr_lav[fh]);
-        }
-    }
-    memcpy(c->noise[0], c->noise[c->num_noise], sizeof(c->noise[0]));
-}
-
-/* ---------------------------------------------------------------- PS (ff_ps_read_data, aacps.c:150-279) */
-static const int8_t nr_iidicc_tab[6] = { 10, 20, 34, 10, 20, 34 }, nr_ipdopd_tab[6] = { 5, 11, 17, 5, 11, 17 };
-static const int8_t num_env_tab[2][4] = { { 0, 1, 2, 4 }, { 1, 2, 3, 4 } };
-
-static int ps_par(FePs *p, BR *b, int8_t (*par)[34], int table, int e, int dt, int num, int kind)
-{
-    /* kind 0: iid (range check), 1: icc, 2: ipd/opd (modulo 8, no offset) */
-    const int off = kind == 2 ? 0 : ps_off[table];
-    if (dt) {
-        int e_prev = e ? e - 1 : p->num_env_old - 1;
-        if (e_prev < 0) e_prev = 0;
-        for (int k = 0; k < num; k++) {
-            int val = par[e_prev][k] + vlc_get(b, &vlc_ps[table]) - off;
-            if (kind == 2) val &= 7;
-            par[e][k] = (int8_t)val;
-            if (kind == 0 && abs(par[e][k]) > 7 + 8 * p->iid_quant) return -1;
-            if (kind == 1 && (unsigned)par[e][k] > 7U) return -1;
-        }
-    } else {
-        int val = 0;
-        for (int k = 0; k < num; k++) {
-            val += vlc_get(b, &vlc_ps[table]) - off;
-            if (kind == 2) val &= 7;
-            par[e][k] = (int8_t)val;
-            if (kind == 0 && abs(par[e][k]) > 7 + 8 * p->iid_quant) return -1;
-            if (kind == 1 && (unsigned)par[e][k] > 7U) return -1;
-        }
-    }
-    return 0;
-}
-
-static int ps_read(FePs *p, BR *host, int bits_left)
-{
-    BR bb = *host, *b = &bb;
-    const int start_pos = host->pos;
-    int header = br_get1(b);
-    if (header) {
-        p->enable_iid = br_get1(b);
-        if (p->enable_iid) {
-            int m = br_get(b, 3);
-            if (m > 5) goto err;
-            p->nr_iid_par = nr_iidicc_tab[m]; p->iid_quant = m > 2; p->nr_ipdopd_par = nr_ipdopd_tab[m];
-        }
-        p->enable_icc = br_get1(b);
-        if (p->enable_icc) {
-            p->icc_mode = br_get(b, 3);
-            if (p->icc_mode > 5) goto err;
-            p->nr_icc_par = nr_iidicc_tab[p->icc_mode];
-        }
-        p->enable_ext = br_get1(b);
-    }
-    p->frame_class = br_get1(b);
-    p->num_env_old = p->num_env;
-    p->num_env = num_env_tab[p->frame_class][br_get(b, 2)];
-    p->border[0] = -1;
-    if (p->frame_class) for (int e = 1; e <= p->num_env; e++) p->border[e] = br_get(b, 5);
-    else for (int e = 1; e <= p->num_env; e++) p->border[e] = (e * 32 >> (p->num_env == 4 ? 2 : p->num_env == 2 ? 1 : 0)) - 1;
-    if (p->enable_iid) {
-        static const int tab[4] = { PS_IID_DF0, PS_IID_DF1, PS_IID_DT0, PS_IID_DT1 };
-        for (int e = 0; e < p->num_env; e++) {
-            int dt = br_get1(b);
-            if (ps_par(p, b, p->iid, tab[2 * dt + p->iid_quant], e, dt, p->nr_iid_par, 0)) goto err;
-        }
-    } else memset(p->iid, 0, sizeof(p->iid));
-    if (p->enable_icc) {
-        for (int e = 0; e < p->num_env; e++) {
-            int dt = br_get1(b);
-            if (ps_par(p, b, p->icc, dt ? PS_ICC_DT : PS_ICC_DF, e, dt, p->nr_icc_par, 1)) goto err;
-        }
-    } else memset(p->icc, 0, sizeof(p->icc));
-    if (p->enable_ext) {
-        int cnt = br_get(b, 4);
-        if (cnt == 15) cnt += br_get(b, 8);
-        cnt *= 8;
-        while (cnt > 7) {
-            int id = br_get(b, 2), used = 0;
-            if (id == 0) {                                         /* ps_read_extension_data, aacps.c:120-139 */
-                int p0 = b->pos;
-                p->enable_ipdopd = br_get1(b);
-                if (p->enable_ipdopd)
-                    for (int e = 0; e < p->num_env; e++) {
-                        int dt = br_get1(b);
-                        ps_par(p, b, p->ipd, dt ? PS_IPD_DT : PS_IPD_DF, e, dt, p->nr_ipdopd_par, 2);
-                        dt = br_get1(b);
-                        ps_par(p, b, p->opd, dt ? PS_OPD_DT : PS_OPD_DF, e, dt, p->nr_ipdopd_par, 2);
-                    }
-                br_skip(b, 1);
-                used = b->pos - p0;
-            }
-            cnt -= 2 + used;
-        }
-        if (cnt < 0) goto err;
-        br_skip(b, cnt);
-    }
-    if (!p->num_env || p->border[p->num_env] < 31) {               /* fake envelope, aacps.c:235-252 */
-        int source = p->num_env ? p->num_env - 1 : p->num_env_old - 1;
-        if (source >= 0 && source != p->num_env) {
-            if (p->enable_iid) memcpy(p->iid[p->num_env], p->iid[source], 34);
-            if (p->enable_icc) memcpy(p->icc[p->num_env], p->icc[source], 34);
-            if (p->enable_ipdopd) { memcpy(p->ipd[p->num_env], p->ipd[source], 34); memcpy(p->opd[p->num_env], p->opd[source], 34); }
-        }
-        p->num_env++;
-        p->border[p->num_env] = 31;
-    }
-    p->is34_old = p->is34;
-    if (p->enable_iid || p->enable_icc)
-        p->is34 = (p->enable_iid && p->nr_iid_par == 34) || (p->enable_icc && p->nr_icc_par == 34);
-    if (!p->enable_ipdopd) { memset(p->ipd, 0, sizeof(p->ipd)); memset(p->opd, 0, sizeof(p->opd)); }
-    if (header) p->start = 1;
-    {
-        int consumed = b->pos - start_pos;
-        if (consumed <= bits_left) { host->pos += consumed; return consumed; }
-    }
-err:
-    p->start = 0;
-    host->pos = start_pos + bits_left;
-    return bits_left;
-}
-
-/* ---------------------------------------------------------------- SBR payload */
-static int sbr_data(FE *fe, FeSbr *s, BR *b, int is_cpe)          /* read_sbr_data, aacsbr.c:982-1021 */
-{
-    if (!is_cpe) {
-        if (br_get1(b)) br_skip(b, 4);
-        if (sbr_grid(s, &s->ch[0], b)) return -1;
-        sbr_dtdf(&s->ch[0], b); sbr_invf(s, &s->ch[0], b);
-        sbr_envelope(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[0], b, 0);
-        if ((s->ch[0].add_harmonic_flag = br_get1(b))) for (int i = 0; i < s->t.n[1]; i++) s->ch[0].add_harmonic[i] = br_get1(b);
-    } else {
-        if (br_get1(b)) br_skip(b, 8);
-        if ((s->coupling = br_get1(b))) {
-            if (sbr_grid(s, &s->ch[0], b)) return -1;
-            sbr_copy_grid(&s->ch[1], &s->ch[0]);
-            sbr_dtdf(&s->ch[0], b); sbr_dtdf(&s->ch[1], b);
-            sbr_invf(s, &s->ch[0], b);
-            memcpy(s->ch[1].invf[1], s->ch[1].invf[0], 5);
-            memcpy(s->ch[1].invf[0], s->ch[0].invf[0], 5);
-            sbr_envelope(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[0], b, 0);
-            sbr_envelope(s, &s->ch[1], b, 1); sbr_noise(s, &s->ch[1], b, 1);
-        } else {
-            if (sbr_grid(s, &s->ch[0], b) || sbr_grid(s, &s->ch[1], b)) return -1;
-            sbr_dtdf(&s->ch[0], b); sbr_dtdf(&s->ch[1], b);
-            sbr_invf(s, &s->ch[0], b); sbr_invf(s, &s->ch[1], b);
-            sbr_envelope(s, &s->ch[0], b, 0); sbr_envelope(s, &s->ch[1], b, 1);
-            sbr_noise(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[1], b, 1);
-        }
-        for (int c = 0; c < 2; c++)
-            if ((s->ch[c].add_harmonic_flag = br_get1(b))) for (int i = 0; i < s->t.n[1]; i++) s->ch[c].add_harmonic[i] = br_get1(b);
-    }
-    if (br_get1(b)) {                                              /* bs_extended_data */
-        int left = br_get(b, 4);
-        if (left == 15) left += br_get(b, 8);
-        left <<= 3;
-        while (left > 7) {
-            left -= 2;
-            int id = br_get(b, 2);
-            if (id == 2 && fe->ps == 1) left -= ps_read(&fe->psx, b, left);     /* EXTENSION_ID_PS */
-            else { br_skip(b, left); left = 0; }
-        }
-        if (left > 0) br_skip(b, left);
-    }
-    return 0;
-}
-
-static void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cpe)   /* ff_decode_sbr_extension, aacsbr.c:1044-1086 */
-{
-    BR bb = *host, *b = &bb;
-    host->pos += cnt * 8 - 4;
-    s->reset = 0;
-    if (!fe->ext_sample_rate) fe->ext_sample_rate = 2 * fe->sample_rate;
-    if (crc) br_skip(b, 10);
-    s->t.kx[0] = s->t.kx[1];
-    s->t.m[0] = s->t.m[1];
-    if (br_get1(b)) sbr_header(fe, s, b);
-    if (s->reset && sbr_tables(fe, s)) s->start = 0;               /* "pure upsampling mode" */
-    if (s->start && sbr_data(fe, s, b, is_cpe)) s->start = 0;
-}
-
-/* ---------------------------------------------------------------- frame */
-static void pack_sbr(const FeSbr *s, HeaacSbrElem *o)
-{
-    *o = s->t;
-    o->start = s->start; o->reset = s->reset; o->bs_coupling = s->coupling;
-    o->bs_limiter_gains = s->limiter_gains; o->bs_interpol_freq = s->interpol_freq; o->bs_smoothing_mode = s->smoothing_mode;
-    for (int c = 0; c < 2; c++) {
-        const FeSbrCh *d = &s->ch[c];
-        HeaacSbrChan *oc = &o->ch[c];
-        memset(oc, 0, sizeof(*oc));
-        oc->bs_num_env = d->num_env; oc->bs_num_noise = d->num_noise; oc->bs_amp_res = d->amp_res;
-        oc->bs_add_harmonic_flag = d->add_harmonic_flag;
-        oc->e_a[0] = d->e_a[0]; oc->e_a[1] = d->e_a[1]; oc->t_env_num_env_old = d->t_env_num_env_old;
-        memcpy(oc->bs_freq_res, d->freq_res, 7); memcpy(oc->t_env, d->t_env, 8); memcpy(oc->t_q, d->t_q, 3);
-        memcpy(oc->bs_invf_mode, d->invf, 10); memcpy(oc->bs_add_harmonic, d->add_harmonic, 48);
-        for (int e = 0; e < 5; e++) for (int k = 0; k < 48; k++) oc->env_q[e][k] = (int16_t)d->env[e + 1][k];
-        for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = (int16_t)d->noise[e + 1][k];
-    }
-}
-
-static void pack_ps(const FePs *p, HeaacPsFrame *o)
-{
-    memset(o, 0, sizeof(*o));
-    o->start = p->start; o->num_env = p->num_env; o->num_env_old = p->num_env_old; o->iid_quant = p->iid_quant;
-    o->nr_iid_par = p->nr_iid_par; o->nr_icc_par = p->nr_icc_par; o->nr_ipdopd_par = p->nr_ipdopd_par; o->icc_mode = p->icc_mode;
-    o->enable_ipdopd = p->enable_ipdopd; o->is34bands = p->is34; o->is34bands_old = p->is34_old;
-    for (int i = 0; i < 6; i++) o->border_position[i] = (int8_t)p->border[i];
-    memcpy(o->iid_par, p->iid, sizeof(o->iid_par)); memcpy(o->icc_par, p->icc, sizeof(o->icc_par));
-    memcpy(o->ipd_par, p->ipd, sizeof(o->ipd_par)); memcpy(o->opd_par, p->opd, sizeof(o->opd_par));
-}
+void heaac_fe_close(FE *fe) { free(fe); }
 
 /* One packet (an ADTS frame or a bare raw_data_block) -> the frame's C-ABI structures.
  * coeffs [ncc][1024]; ics/tns [ncc]; sbr [nse] (may be NULL for LC); ps (may be NULL).
@@ -916,88 +176,11 @@ static void pack_ps(const FePs *p, HeaacPsFrame *o)
 int heaac_fe_parse(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                    HeaacSbrElem *sbr, HeaacPsFrame *ps)
 {
-    if (!fe || !pkt || size <= 0 || !coeffs || !ics) return HEAAC_E_INVAL;
-    BR br = { pkt, size * 8, 0 }, *b = &br;
-    if (br_show(b, 12) == 0xfff) {                                 /* ADTS header, aac_parser.c:29-67 */
-        br_skip(b, 12);
-        br_skip(b, 1); br_skip(b, 2);
-        int crc_absent = br_get1(b);
-        br_skip(b, 2);                                            /* profile */
-        int sr = br_get(b, 4);
-        if (!sample_rates[sr]) return HEAAC_E_INVAL;
-        br_skip(b, 1);
-        int ch = br_get(b, 3);
-        br_skip(b, 4);
-        int fsize = br_get(b, 13);
-        if (fsize < 7) return HEAAC_E_INVAL;
-        br_skip(b, 11);
-        int rdb = br_get(b, 2);
-        if (rdb) return HEAAC_E_UNSUPPORTED;
-        if (!crc_absent) br_skip(b, 16);
-        if (!fe->locked && ch) { int r = set_layout(fe, ch); if (r) return r; fe->sample_rate = sample_rates[sr]; fe->sr_index = sr; }
-    }
-    if (!fe->n_elems) return HEAAC_E_INVAL;
-    int seen[4] = { 0, 0, 0, 0 };
-    int prev_elem = -1, prev_type = 7, type;
-    while ((type = br_get(b, 3)) != 7) {
-        int id = br_get(b, 4), e = -1, r = 0;
-        if (type == 0 || type == 1 || type == 3) {                 /* k-th element of this type in the layout */
-            int k = 0;
-            for (int i = 0; i < fe->n_elems; i++)
-                if (fe->elem_type[i] == type && k++ == seen[type]) { e = i; break; }
-            if (e < 0) return HEAAC_E_INVAL;
-            seen[type]++;
-        }
-        switch (type) {
-        case 0: case 3: r = decode_ics(fe, &fe->ch[fe->elem_ch0[e]], b, coeffs + 1024 * fe->elem_ch0[e], 0); break;
-        case 1: r = decode_cpe(fe, &fe->ch[fe->elem_ch0[e]], &fe->ch[fe->elem_ch0[e] + 1], b,
-                               coeffs + 1024 * fe->elem_ch0[e], coeffs + 1024 * (fe->elem_ch0[e] + 1)); break;
-        case 4: {                                                  /* DSE, aacdec.c:1190-1200 region */
-            int align = br_get1(b), cnt = br_get(b, 8);
-            if (cnt == 255) cnt += br_get(b, 8);
-            if (align) b->pos = (b->pos + 7) & ~7;
-            br_skip(b, 8 * cnt);
-            break; }
-        case 6: {                                                  /* FIL */
-            int cnt = id;
-            if (cnt == 15) cnt += br_get(b, 8) - 1;
-            if (br_left(b) < 8 * cnt) return HEAAC_E_INVAL;
-            while (cnt > 0) {                                      /* decode_extension_payload, aacdec.c:1650-1690 */
-                int ext = br_get(b, 4), res = cnt;
-                if (ext == 0xd || ext == 0xe) {
-                    if (prev_elem < 0 || fe->sbr == 0 || (fe->sbr == -1 && fe->locked)) {
-                        br_skip(b, 8 * cnt - 4);
-                    } else {
-                        if (fe->ps == -1 && !fe->locked && fe->ncc == 1) { fe->sbr = 1; fe->ps = 1; }
-                        else fe->sbr = 1;
-                        int se = 0;
-                        for (int i = 0; i < prev_elem; i++) se += fe->elem_type[i] != HEAAC_TYPE_LFE;
-                        sbr_extension(fe, &fe->sbr_el[se], b, ext == 0xe, cnt, prev_type == 1);
-                    }
-                } else br_skip(b, 8 * cnt - 4);
-                cnt -= res;
-            }
-            break; }
-        default: return HEAAC_E_UNSUPPORTED;                       /* CCE, PCE */
-        }
-        if (r) return r;
-        if (type <= 3) { prev_elem = e; prev_type = type; } else if (type != 6) { prev_elem = -1; prev_type = type; }
-        if (br_left(b) < 3) return HEAAC_E_INVAL;
-    }
-    fe->locked = 1;
-    for (int c = 0; c < fe->ncc; c++) {
-        const FeChan *fc = &fe->ch[c];
-        memset(&ics[c], 0, sizeof(ics[c]));
-        ics[c].window_sequence = fc->ws[0]; ics[c].window_shape = fc->shape[0]; ics[c].max_sfb = fc->max_sfb;
-        ics[c].tns_present = fc->tns_present;
-        ics[c].prev_valid = 1; ics[c].prev_window_sequence = fc->ws[1]; ics[c].prev_window_shape = fc->shape[1];
-        if (tns) { if (fc->tns_present) tns[c] = fc->tns; else memset(&tns[c], 0, sizeof(tns[c])); }
-    }
-    if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr(&fe->sbr_el[se], &sbr[se]), se++;
-    if (ps) pack_ps(&fe->psx, ps);
-    int consumed = (b->pos + 7) >> 3;
-    return consumed > size ? size : consumed;
+    return fe_parse_frame(fe, pkt, size, coeffs, ics, tns, sbr, ps);
 }
+
+/* the state block of an opened front end, for the device front end to replicate per stream */
+const void *heaac_fe_state_blob(const FE *fe) { return fe; }
 
 /* Stream properties known after open (explicit config) or after the first parsed frame (implicit SBR/PS). */
 int heaac_fe_info(const FE *fe, int *ncc, int *nse, int *sbr, int *ps, int *sr_index, uint8_t elem_type[HEAAC_MAX_ELEMS])

@@ -1,0 +1,225 @@
+/*
+ * heaac_parse_gpu.cu -- the front end on the GPU: packets in, PCM out, nothing but bitstreams over PCIe.
+ *
+ * The same parser source as the host front end (heaac_fe_core.h, compiled here with FE_DEVICE) runs with one
+ * GPU thread per stream: entropy decoding is serial inside a stream but the streams of a batch are independent,
+ * and a B200 has room for thousands of such threads next to the synthesis kernels.  k_parse writes coeffs / ICS /
+ * TNS / SBR / PS structures straight into the back end's device staging sets, so the host-to-device traffic of a
+ * batch shrinks from the dequantised spectra (4 KiB per channel-frame) to the packets themselves (~0.2 KiB).
+ *
+ * Each warp runs `lanes` streams (1 by default: divergent serial code, and warps are plentiful); per-stream parser
+ * state (struct HeaacFrontend) lives in HBM between calls.  Chunks are double buffered exactly like the
+ * host-pointer path of heaac_b200_synth_submit: packets H2D + k_parse on s_in, synthesis kernels on the
+ * context's stream, PCM D2H on s_out.
+ */
+#define FE_DEVICE 1
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "heaac_context.cuh"
+#include "heaac_fe_core.h"
+
+extern "C" const void *heaac_fe_tables_blob(size_t *bytes);
+extern "C" size_t heaac_fe_state_size(void);
+extern "C" const void *heaac_fe_state_blob(const HeaacFrontend *fe);
+
+struct HeaacGpuParser {
+    HeaacContext *ctx;
+    FE *d_fe;                        /* [S] parser state */
+    FE *d_template;                  /* state right after open, for reset */
+    FeTables *d_tb;
+    int lanes;                       /* streams per warp */
+    /* per staging set: packets of one chunk, 8-byte aligned and zero padded */
+    uint8_t *h_blob[2], *d_blob[2];
+    uint32_t *h_off[2], *d_off[2];   /* [chunk][S] byte offset of each packet in the blob */
+    int *h_size[2], *d_size[2];
+    int *d_consumed[2];
+    size_t blob_cap;
+    cudaEvent_t ev_h2d[2];
+    long long launches;
+};
+
+/* one thread per stream; frames of the chunk in order (parser state is sequential within a stream) */
+__global__ void __launch_bounds__(128)
+k_parse(FE *fes, const uint8_t *blob, const uint32_t *off, const int *size, int n_frames, int S, int ncc, int nse,
+        int has_sbr, int has_ps, int lanes, float *coeffs, HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr,
+        HeaacPsFrame *ps, int *consumed)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (lane >= lanes) return;
+    const int s = warp * lanes + lane;
+    if (s >= S) return;
+    FE *fe = fes + s;
+    for (int t = 0; t < n_frames; t++) {
+        const size_t idx = (size_t)t * S + s;
+        float *co = coeffs + idx * ncc * 1024;
+        HeaacIcs *ic = ics + idx * ncc;
+        HeaacTns *tn = tns + idx * ncc;
+        HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
+        HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
+        int r = fe_parse_frame(fe, blob + off[idx], size[idx], co, ic, tn, sb, pp);
+        if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;          /* layout differs from the batch's */
+        if (r < 0) {                                                /* silent frame; the batch goes on */
+            fe_zero(co, ncc * 1024);
+            memset(ic, 0, sizeof(HeaacIcs) * ncc);
+            memset(tn, 0, sizeof(HeaacTns) * ncc);
+            if (sb) memset(sb, 0, sizeof(HeaacSbrElem) * nse);
+            if (pp) memset(pp, 0, sizeof(HeaacPsFrame));
+        }
+        consumed[idx] = r;
+    }
+}
+
+static void parser_free(HeaacGpuParser *p)
+{
+    if (!p) return;
+    for (int b = 0; b < 2; b++) {
+        if (p->h_blob[b]) cudaFreeHost(p->h_blob[b]);
+        if (p->h_off[b]) cudaFreeHost(p->h_off[b]);
+        if (p->h_size[b]) cudaFreeHost(p->h_size[b]);
+        if (p->d_blob[b]) cudaFree(p->d_blob[b]);
+        if (p->d_off[b]) cudaFree(p->d_off[b]);
+        if (p->d_size[b]) cudaFree(p->d_size[b]);
+        if (p->d_consumed[b]) cudaFree(p->d_consumed[b]);
+        if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]);
+    }
+    if (p->d_fe) cudaFree(p->d_fe);
+    if (p->d_template) cudaFree(p->d_template);
+    if (p->d_tb) cudaFree(p->d_tb);
+    delete p;
+}
+
+extern "C" void heaac_b200_parser_destroy(HeaacGpuParser *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->cfg.device);
+    cudaStreamSynchronize(p->ctx->s_in);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaStreamSynchronize(p->ctx->s_out);
+    parser_free(p);
+}
+
+extern "C" int heaac_b200_parser_reset(HeaacGpuParser *p)
+{
+    if (!p) return HEAAC_E_INVAL;
+    HeaacContext *c = p->ctx;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->s_in));
+    for (int s = 0; s < c->geom.n_streams; s++)
+        CK(cudaMemcpyAsync(p->d_fe + s, p->d_template, sizeof(FE), cudaMemcpyDeviceToDevice, c->s_in));
+    CK(cudaStreamSynchronize(c->s_in));
+    return 0;
+}
+
+/* `fe` = a host front end opened for this stream configuration and not yet used: its state block is the initial
+ * state of every stream's device parser. */
+extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe, size_t max_packet_bytes, HeaacGpuParser **out)
+{
+    if (!c || !fe || !out) return HEAAC_E_INVAL;
+    if (heaac_fe_state_size() != sizeof(FE)) return HEAAC_E_INVAL;            /* host and device builds must agree */
+    CK(cudaSetDevice(c->cfg.device));
+    HeaacGpuParser *p = new (std::nothrow) HeaacGpuParser();
+    if (!p) return HEAAC_E_NOMEM;
+    memset(p, 0, sizeof(*p));
+    p->ctx = c;
+    p->lanes = 1;
+    const char *env = getenv("HEAAC_PARSE_LANES");
+    if (env && atoi(env) >= 1 && atoi(env) <= 32) p->lanes = atoi(env);
+    const size_t S = c->geom.n_streams, n = (size_t)c->chunk * S;
+    if (!max_packet_bytes) max_packet_bytes = 6144 / 8 * c->geom.ncc + 64;    /* 6144 bits per channel, aacenc.c:595 */
+    p->blob_cap = n * ((max_packet_bytes + 15) & ~(size_t)7);
+    int r = 0;
+#define CKP(call) do { if (!r) r = heaac_cuda_err((call), #call); } while (0)
+    size_t tb_bytes = 0;
+    const void *tb = heaac_fe_tables_blob(&tb_bytes);
+    if (tb_bytes != sizeof(FeTables)) r = HEAAC_E_INVAL;
+    CKP(cudaMalloc(&p->d_tb, sizeof(FeTables)));
+    CKP(cudaMemcpy(p->d_tb, tb, sizeof(FeTables), cudaMemcpyHostToDevice));
+    CKP(cudaMemcpyToSymbol(fe_tb_dev, &p->d_tb, sizeof(p->d_tb)));
+    CKP(cudaMalloc(&p->d_fe, S * sizeof(FE)));
+    CKP(cudaMalloc(&p->d_template, sizeof(FE)));
+    CKP(cudaMemcpy(p->d_template, heaac_fe_state_blob(fe), sizeof(FE), cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2 && !r; b++) {
+        CKP(cudaHostAlloc(&p->h_blob[b], p->blob_cap, cudaHostAllocDefault));
+        CKP(cudaHostAlloc(&p->h_off[b], n * sizeof(uint32_t), cudaHostAllocDefault));
+        CKP(cudaHostAlloc(&p->h_size[b], n * sizeof(int), cudaHostAllocDefault));
+        CKP(cudaMalloc(&p->d_blob[b], p->blob_cap));
+        CKP(cudaMalloc(&p->d_off[b], n * sizeof(uint32_t)));
+        CKP(cudaMalloc(&p->d_size[b], n * sizeof(int)));
+        CKP(cudaMalloc(&p->d_consumed[b], n * sizeof(int)));
+        CKP(cudaEventCreateWithFlags(&p->ev_h2d[b], cudaEventDisableTiming));
+    }
+#undef CKP
+    if (r) { parser_free(p); return r; }
+    *out = p;
+    r = heaac_b200_parser_reset(p);
+    if (r) { parser_free(p); *out = nullptr; }
+    return r;
+}
+
+extern "C" long long heaac_b200_parser_launch_count(const HeaacGpuParser *p) { return p ? p->launches : 0; }
+
+/* n_frames x n_streams packets -> PCM.  pkt / size / consumed are frame-major [n_frames][n_streams] host arrays;
+ * pcm / pcm_f32 are host buffers as in heaac_b200_synth.  Returns after the PCM has landed. */
+extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,
+                                        int16_t *pcm, float *pcm_f32, int *consumed)
+{
+    if (!p || n_frames <= 0 || !pkt || !size || (!pcm && !pcm_f32)) return HEAAC_E_INVAL;
+    HeaacContext *c = p->ctx;
+    const HeaacGeom *g = &c->geom;
+    if (pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    const size_t S = g->n_streams;
+    const int Tc = c->chunk;
+    for (int f0 = 0; f0 < n_frames; f0 += Tc, c->seq++) {
+        const int buf = (int)(c->seq & 1);
+        const int n = n_frames - f0 < Tc ? n_frames - f0 : Tc;
+        const size_t np = (size_t)n * S;
+        /* the pinned packet set `buf` was last read by the H2D recorded in ev_h2d[buf] */
+        if (c->seq >= 2) CK(cudaEventSynchronize(p->ev_h2d[buf]));
+        size_t used = 0;
+        for (size_t i = 0; i < np; i++) {                          /* gather: 8-byte aligned, >= 8 zero bytes after each */
+            const int sz = size[(size_t)f0 * S + i];
+            const size_t room = ((size_t)(sz > 0 ? sz : 0) + 15) & ~(size_t)7;
+            if (sz < 0 || used + room > p->blob_cap) return HEAAC_E_INVAL;
+            memcpy(p->h_blob[buf] + used, pkt[(size_t)f0 * S + i], sz);
+            memset(p->h_blob[buf] + used + sz, 0, room - sz);
+            p->h_off[buf][i] = (uint32_t)used;
+            p->h_size[buf][i] = sz;
+            used += room;
+        }
+        if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));     /* staging set free again */
+        CK(cudaMemcpyAsync(p->d_blob[buf], p->h_blob[buf], used, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(p->d_off[buf], p->h_off[buf], np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(p->d_size[buf], p->h_size[buf], np * sizeof(int), cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(p->ev_h2d[buf], c->s_in));
+        if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));      /* d_consumed[buf] drained */
+        {
+            const int threads = 128, warps_per_cta = threads / 32;
+            const int n_warps = (int)((S + p->lanes - 1) / p->lanes);
+            const int grid = (n_warps + warps_per_cta - 1) / warps_per_cta;
+            k_parse<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_blob[buf], p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc,
+                                                   g->nse, g->sbr, g->ps, p->lanes, c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf],
+                                                   c->s_sbr[buf], c->s_ps[buf], p->d_consumed[buf]);
+            CK(cudaGetLastError());
+            p->launches++;
+        }
+        CK(cudaEventRecord(c->ev_in[buf], c->s_in));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
+        if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
+        int r = heaac_launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf],
+                                    c->s_pcm[buf], pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
+        if (r) return r;
+        CK(cudaEventRecord(c->ev_done[buf], c->stream));
+        const size_t pcm_n = np * g->out_len * g->nout, pcm_o = (size_t)f0 * S * g->out_len * g->nout;
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_done[buf], 0));
+        if (pcm) CK(cudaMemcpyAsync(pcm + pcm_o, c->s_pcm[buf], pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_out));
+        if (pcm_f32) CK(cudaMemcpyAsync(pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+        if (consumed) CK(cudaMemcpyAsync(consumed + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaEventRecord(c->ev_out[buf], c->s_out));
+    }
+    return heaac_b200_wait(c);
+}

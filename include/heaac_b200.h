@@ -321,7 +321,7 @@ typedef struct HeaacDecoderConfig {
     int32_t  want_float_out;
     const uint8_t *extradata;       /* AudioSpecificConfig, or NULL for ADTS input */
     int32_t  extradata_size;
-    int32_t  reserved;
+    int32_t  gpu_parse;             /* 1: entropy decoding on the GPU too (heaac_b200_parser_*): only packets cross PCIe */
 } HeaacDecoderConfig;
 int  heaac_dec_open(const HeaacDecoderConfig *cfg, HeaacDecoder **dec);
 void heaac_dec_close(HeaacDecoder *dec);
@@ -330,6 +330,20 @@ int  heaac_dec_decode(HeaacDecoder *dec, int n_frames, const uint8_t *const *pkt
 /* returns 1 once the first call has configured the decoder (0 before), and fills the optional outputs */
 int  heaac_dec_info(const HeaacDecoder *dec, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,
                     long long *parse_errors, long long *gpu_launches);
+
+/* ---- device front end: the parser of heaac_fe_* compiled for the GPU, one thread per stream ---------
+ * parser_create takes a host front end that was opened for the streams' configuration and not used yet (its
+ * state becomes the initial state of every stream); parser_decode is heaac_dec_decode's GPU-parse path:
+ * packets are gathered into page-locked memory, copied, parsed by k_parse straight into the back end's staging
+ * sets, synthesised, and the PCM copied back; chunks of frames are pipelined across three streams.
+ * max_packet_bytes 0 = the AAC limit of 768 bytes per channel. */
+typedef struct HeaacGpuParser HeaacGpuParser;
+int  heaac_b200_parser_create(HeaacContext *ctx, const HeaacFrontend *fe, size_t max_packet_bytes, HeaacGpuParser **out);
+void heaac_b200_parser_destroy(HeaacGpuParser *p);
+int  heaac_b200_parser_reset(HeaacGpuParser *p);
+int  heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                              int16_t *pcm, float *pcm_f32, int *consumed);
+long long heaac_b200_parser_launch_count(const HeaacGpuParser *p);
 
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */

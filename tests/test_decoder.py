@@ -65,11 +65,12 @@ def test_reference_out_slots_matches_python_mirror():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("threads", [1, 3])
+@pytest.mark.parametrize("threads", [1, 3, "gpu"])
 def test_decoder_reproduces_reference_pcm(name, threads):
+    """threads = host parser threads, or "gpu": entropy decoding by the device front end (k_parse)."""
     d = load_golden(name)
     S = 5
-    dec = open_for(d, S, n_threads=threads, want_float=True)
+    dec = open_for(d, S, want_float=True, **({"gpu_parse": True} if threads == "gpu" else {"n_threads": threads}))
     pk = golden_packets(d)
     pcm, f32, consumed = dec.decode(hb.PacketBatch([[p] * S for p in pk]))
     i = dec.info()
