@@ -35,7 +35,7 @@ EXPORTS = [
     "heaac_b200_reference_out_slots", "heaac_b200_host_alloc", "heaac_b200_host_free",
     "heaac_dec_open", "heaac_dec_close", "heaac_dec_decode", "heaac_dec_info",
     "heaac_b200_parser_create", "heaac_b200_parser_destroy", "heaac_b200_parser_reset", "heaac_b200_parser_decode",
-    "heaac_b200_parser_launch_count",
+    "heaac_b200_parser_launch_count", "heaac_b200_parser_stats", "heaac_dec_parse_kernel_ms",
 ]
 
 
@@ -96,6 +96,8 @@ def lib():
         L.heaac_dec_close.restype = None
         L.heaac_dec_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.heaac_dec_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_longlong)] * 2
+        L.heaac_dec_parse_kernel_ms.argtypes = [C.c_void_p]
+        L.heaac_dec_parse_kernel_ms.restype = C.c_double
         L.heaac_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.heaac_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
         for name, size in abi.SIZES.items():
@@ -334,7 +336,8 @@ class Decoder:
         w = [C.c_longlong() for _ in range(2)]
         ok = lib().heaac_dec_info(self.h, *[C.byref(x) for x in v], *[C.byref(x) for x in w])
         return {"configured": bool(ok), "n_out_channels": v[0].value, "frame_out_len": v[1].value, "sbr": v[2].value,
-                "ps": v[3].value, "parse_errors": w[0].value, "gpu_launches": w[1].value}
+                "ps": v[3].value, "parse_errors": w[0].value, "gpu_launches": w[1].value,
+                "k_parse_ms": lib().heaac_dec_parse_kernel_ms(self.h)}
 
     def decode(self, batch, pcm_out=None, out_shape=None):
         """batch: PacketBatch.  Returns (pcm s16 [T, S, out_len, nout], pcm_f32 or None, consumed [T, S]).

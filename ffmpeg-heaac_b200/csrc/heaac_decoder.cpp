@@ -301,3 +301,10 @@ extern "C" int heaac_dec_info(const HeaacDecoder *d, int *n_out_channels, int *f
     if (gpu_launches) *gpu_launches = heaac_b200_launch_count(d->be) + heaac_b200_parser_launch_count(d->gpu);
     return 1;
 }
+
+extern "C" double heaac_dec_parse_kernel_ms(const HeaacDecoder *d)
+{
+    double ms = 0.0;
+    if (d && d->gpu) heaac_b200_parser_stats(d->gpu, &ms, nullptr);
+    return ms;
+}

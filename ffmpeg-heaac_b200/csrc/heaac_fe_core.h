@@ -35,48 +35,46 @@
 #endif
 
 /* ---------------------------------------------------------------- bit reader */
-/* MSB-first.  Host: while at least 8 bytes remain (pos < safe) a field is one unaligned 64-bit load; the tail of
- * the buffer goes through a byte-wise path that returns zero bits past the end, so no input padding is required.
- * Device: packets sit 8-byte aligned in the staging blob followed by >= 8 zero bytes; a field is two aligned
- * 32-bit loads and a funnel shift (positions past the packet end read as zero, like the host). */
-typedef struct { const uint8_t *buf; int nbits, pos, safe; } BR;
+/* MSB-first, with a 64-bit window held in registers: `cache` = bits [cpos, cpos + 64) of the packet, cpos a
+ * multiple of 32.  A field of up to 25 bits is two shifts while it lies inside the window; otherwise the window
+ * is reloaded at the 32-bit word that holds `pos` (so at least 33 bits follow).
+ * Host: the reload is one unaligned 64-bit load while 8 bytes remain, a byte-wise zero-filling path at the tail,
+ * so no input padding is required.  Device: packets sit 8-byte aligned in the staging blob followed by >= 8 zero
+ * bytes, the reload is two aligned 32-bit loads.  Positions past the packet end read as zero on both. */
+typedef struct { const uint8_t *buf; int nbits, pos, cpos; uint64_t cache; } BR;
 
-FE_FN void br_init(BR *b, const uint8_t *buf, int size)
+FE_INL void br_refill(BR *b)
+{
+    const int w = b->pos >> 5;                                  /* 32-bit word that holds pos */
+    b->cpos = w << 5;
+    if (b->pos < 0 || b->pos >= b->nbits) { b->cache = 0; b->cpos = b->pos & ~31; return; }
+#ifdef FE_DEVICE
+    const unsigned *p = (const unsigned *)b->buf + w;
+    b->cache = ((uint64_t)__byte_perm(p[0], 0, 0x0123) << 32) | __byte_perm(p[1], 0, 0x0123);
+#else
+    const int byte = w * 4, size = (b->nbits + 7) >> 3;
+    if (byte + 8 <= size) {
+        uint64_t v;
+        memcpy(&v, b->buf + byte, 8);
+        b->cache = __builtin_bswap64(v);
+    } else {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++) v = (v << 8) | (byte + i < size ? b->buf[byte + i] : 0u);
+        b->cache = v;
+    }
+#endif
+}
+FE_INL void br_init(BR *b, const uint8_t *buf, int size)
 {
     b->buf = buf; b->nbits = size * 8; b->pos = 0;
-#ifdef FE_DEVICE
-    b->safe = b->nbits;
-#else
-    b->safe = size >= 8 ? (size - 7) * 8 : 0;
-#endif
+    br_refill(b);
 }
-#ifdef FE_DEVICE
-FE_INL unsigned br_show(const BR *b, int n)                    /* 1 <= n <= 25 */
+FE_INL unsigned br_show(BR *b, int n)                         /* 1 <= n <= 25 */
 {
-    if (b->pos >= b->safe || b->pos < 0) return 0;
-    const unsigned *w = (const unsigned *)b->buf + (b->pos >> 5);
-    const unsigned hi = __byte_perm(w[0], 0, 0x0123), lo = __byte_perm(w[1], 0, 0x0123);
-    return __funnelshift_l(lo, hi, b->pos & 31) >> (32 - n);
+    unsigned off = (unsigned)(b->pos - b->cpos);
+    if (off > (unsigned)(64 - n)) { br_refill(b); off = (unsigned)(b->pos - b->cpos); }
+    return (unsigned)((b->cache << off) >> (64 - n));
 }
-#else
-static unsigned br_show_tail(const BR *b, int n)
-{
-    const int byte = b->pos >> 3, avail = (b->nbits + 7) >> 3;
-    unsigned long long w = 0;
-    for (int i = 0; i < 5; i++) w = (w << 8) | (byte + i >= 0 && byte + i < avail ? b->buf[byte + i] : 0u);
-    return (unsigned)((w >> (40 - (b->pos & 7) - n)) & ((1u << n) - 1));
-}
-FE_INL unsigned br_show(const BR *b, int n)                   /* 1 <= n <= 25 */
-{
-    if (b->pos < b->safe) {
-        uint64_t w;
-        memcpy(&w, b->buf + (b->pos >> 3), 8);
-        w = __builtin_bswap64(w);
-        return (unsigned)((w << (b->pos & 7)) >> (64 - n));
-    }
-    return br_show_tail(b, n);
-}
-#endif
 FE_INL unsigned br_get(BR *b, int n) { if (!n) return 0; unsigned v = br_show(b, n); b->pos += n; return v; }
 FE_INL unsigned br_get1(BR *b) { return br_get(b, 1); }
 FE_INL void br_skip(BR *b, int n) { b->pos += n; }
@@ -100,7 +98,7 @@ typedef struct FeTables {
     float pow2sf[428];                 /* 2^((i-200)/4), aac_tablegen.h:33-38 */
     float pow43[8192];                 /* escapes: cbrtf(i)*i, cbrt_tablegen.h:35-44 */
     float cb_val[16];                  /* in-book values: the literals of codebook_vector*_vals, aactab.c:899-1008 */
-    float spec_val[11][289][4];        /* codeword -> dequantised values (signed books) / magnitudes */
+    float spec_val[11][289][4] __attribute__((aligned(16)));   /* codeword -> dequantised values (signed books) / magnitudes */
     float tns_map[4][16];              /* tns_tmp2_map, aacdectab.h:43-69 */
     uint16_t swb1024[13][64], swb128[13][32];
     uint8_t num_swb1024[13], num_swb128[13];
@@ -119,17 +117,36 @@ FE_TAB int spec_sizes[11] = { 81, 81, 81, 81, 81, 81, 64, 64, 169, 169, 289 };
 FE_TAB int8_t sbr_lav[10] = { 60, 60, 24, 24, 31, 31, 12, 12, 31, 12 };      /* aacsbr.c:73-74 */
 FE_TAB int8_t ps_off[10] = { 30, 30, 14, 14, 7, 7, 0, 0, 0, 0 };             /* aacpsdata.c:136-142 */
 
-FE_INL int vlc_get(BR *b, const Vlc *v)
+FE_INL int vlc_get_tab(BR *b, const uint32_t *tab, int maxlen)       /* all code lengths are <= 25 - ... <= 20 bits */
 {
-    const uint32_t *tab = TB->pool + v->off;
-    uint32_t e = tab[br_show(b, VLC_PRIM)];
+    const unsigned x = br_show(b, 25);
+    uint32_t e = tab[x >> (25 - VLC_PRIM)];
     if (e & 0x80u) {
         const int sb = e & 31;
-        e = tab[(e >> 8) + (br_show(b, VLC_PRIM + sb) & ((1u << sb) - 1))];
+        e = tab[(e >> 8) + ((x >> (25 - VLC_PRIM - sb)) & ((1u << sb) - 1))];
     }
-    if (!e) { b->pos += v->maxlen; return -1; }
+    if (!e) { b->pos += maxlen; return -1; }
     b->pos += e & 31;
     return (int)(e >> 8);
+}
+FE_INL int vlc_get(BR *b, const Vlc *v) { return vlc_get_tab(b, TB->pool + v->off, v->maxlen); }
+
+/* 4 / 2 consecutive coefficients at once (band offsets are multiples of 4, pair positions of 2) */
+FE_INL void fe_store4(float *p, float a, float b_, float c, float d)
+{
+#ifdef FE_DEVICE
+    *(float4 *)p = make_float4(a, b_, c, d);
+#else
+    p[0] = a; p[1] = b_; p[2] = c; p[3] = d;
+#endif
+}
+FE_INL void fe_store2(float *p, float a, float b_)
+{
+#ifdef FE_DEVICE
+    *(float2 *)p = make_float2(a, b_);
+#else
+    p[0] = a; p[1] = b_;
+#endif
 }
 
 FE_FN const uint16_t *heaac_fe_swb_offset(int sr_index, int is8, int *num_swb)
@@ -138,7 +155,23 @@ FE_FN const uint16_t *heaac_fe_swb_offset(int sr_index, int is8, int *num_swb)
     return is8 ? TB->swb128[sr_index] : TB->swb1024[sr_index];
 }
 
-FE_FN void fe_zero(float *p, int n) { for (int i = 0; i < n; i++) p[i] = 0.0f; }
+FE_FN void fe_zero(float *p, int n)                             /* p 16-byte aligned and n a multiple of 4 wherever it matters */
+{
+    int i = 0;
+    if (!((uintptr_t)p & 15)) for (; i + 4 <= n; i += 4) fe_store4(p + i, 0.0f, 0.0f, 0.0f, 0.0f);
+    for (; i < n; i++) p[i] = 0.0f;
+}
+FE_INL void fe_copy32(void *dst, const void *src, int nwords)   /* both 4-byte aligned */
+{
+    uint32_t *d = (uint32_t *)dst;
+    const uint32_t *q = (const uint32_t *)src;
+    for (int i = 0; i < nwords; i++) d[i] = q[i];
+}
+FE_INL void fe_zero32(void *dst, int nwords)
+{
+    uint32_t *d = (uint32_t *)dst;
+    for (int i = 0; i < nwords; i++) d[i] = 0;
+}
 
 /* ---------------------------------------------------------------- state */
 typedef struct FeChan {
@@ -153,9 +186,9 @@ typedef struct FeChan {
 
 typedef struct FeSbrCh {
     int frame_class, num_env, num_noise, amp_res, add_harmonic_flag;
-    uint8_t freq_res[8], t_env[8], t_q[4], df_env[5], df_noise[2], invf[2][5], add_harmonic[48];
+    uint8_t freq_res[8], t_env[8], t_q[4], add_harmonic[48] /* 4-byte aligned */, df_env[5], df_noise[2], invf[2][5];
     int e_a[2], t_env_num_env_old;
-    int env[6][48], noise[3][5];                /* row 0 = last row of the previous frame (delta-time base) */
+    int16_t env[6][48], noise[3][5];            /* row 0 = last row of the previous frame (delta-time base) */
 } FeSbrCh;
 
 typedef struct FeSbr {
@@ -346,47 +379,58 @@ FE_FN int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, con
                     for (int k = 0; k < len; k++) cfo[k] = cfo[k] * scale;
                 }
             } else {
-                const Vlc *v = &TB->vspec[bt - 1];
+                const uint32_t *tab = TB->pool + TB->vspec[bt - 1].off;
+                const int maxlen = TB->vspec[bt - 1].maxlen;
                 const float (*val)[4] = TB->spec_val[bt - 1];
                 const int size = spec_sizes[bt - 1];
                 if (bt == 1 || bt == 2) {                          /* signed quads */
                     for (int w = 0; w < glen; w++, cfo += 128)
                         for (int k = 0; k < len; k += 4) {
-                            const int code = vlc_get(b, v);
+                            const int code = vlc_get_tab(b, tab, maxlen);
                             if ((unsigned)code >= (unsigned)size) return HEAAC_E_INVAL;
-                            for (int d = 0; d < 4; d++) cfo[k + d] = val[code][d] * sf;
+                            const float *v = val[code];
+                            fe_store4(cfo + k, v[0] * sf, v[1] * sf, v[2] * sf, v[3] * sf);
                         }
                 } else if (bt == 5 || bt == 6) {                   /* signed pairs */
                     for (int w = 0; w < glen; w++, cfo += 128)
                         for (int k = 0; k < len; k += 2) {
-                            const int code = vlc_get(b, v);
+                            const int code = vlc_get_tab(b, tab, maxlen);
                             if ((unsigned)code >= (unsigned)size) return HEAAC_E_INVAL;
-                            cfo[k] = val[code][0] * sf; cfo[k + 1] = val[code][1] * sf;
+                            fe_store2(cfo + k, val[code][0] * sf, val[code][1] * sf);
                         }
-                } else if (bt < 5) {                               /* unsigned quads + sign bits */
+                } else if (bt < 5) {                               /* unsigned quads + one sign bit per non-zero value */
                     for (int w = 0; w < glen; w++, cfo += 128)
                         for (int k = 0; k < len; k += 4) {
-                            const int code = vlc_get(b, v);
+                            const int code = vlc_get_tab(b, tab, maxlen);
                             if ((unsigned)code >= (unsigned)size) return HEAAC_E_INVAL;
+                            const float *v = val[code];
+                            unsigned sg = br_show(b, 4) << 28;     /* next sign bit in the MSB */
+                            int used = 0;
+                            float m[4];
                             for (int d = 0; d < 4; d++) {
-                                const float m = val[code][d];
-                                cfo[k + d] = (m != 0.0f && br_get1(b) ? -m : m) * sf;
+                                m[d] = v[d];
+                                if (m[d] != 0.0f) { if (sg & 0x80000000u) m[d] = -m[d]; sg <<= 1; used++; }
                             }
+                            b->pos += used;
+                            fe_store4(cfo + k, m[0] * sf, m[1] * sf, m[2] * sf, m[3] * sf);
                         }
                 } else if (bt < 11) {                              /* unsigned pairs + sign bits */
                     for (int w = 0; w < glen; w++, cfo += 128)
                         for (int k = 0; k < len; k += 2) {
-                            const int code = vlc_get(b, v);
+                            const int code = vlc_get_tab(b, tab, maxlen);
                             if ((unsigned)code >= (unsigned)size) return HEAAC_E_INVAL;
-                            for (int d = 0; d < 2; d++) {
-                                const float m = val[code][d];
-                                cfo[k + d] = (m != 0.0f && br_get1(b) ? -m : m) * sf;
-                            }
+                            unsigned sg = br_show(b, 2) << 30;
+                            int used = 0;
+                            float m0 = val[code][0], m1 = val[code][1];
+                            if (m0 != 0.0f) { if (sg & 0x80000000u) m0 = -m0; sg <<= 1; used++; }
+                            if (m1 != 0.0f) { if (sg & 0x80000000u) m1 = -m1; used++; }
+                            b->pos += used;
+                            fe_store2(cfo + k, m0 * sf, m1 * sf);
                         }
                 } else {                                           /* book 11: pairs, sign bits, escapes (aacdec.c:1177-1209) */
                     for (int w = 0; w < glen; w++, cfo += 128)
                         for (int k = 0; k < len; k += 2) {
-                            const int code = vlc_get(b, v);
+                            const int code = vlc_get_tab(b, tab, maxlen);
                             if ((unsigned)code >= (unsigned)size) return HEAAC_E_INVAL;
                             const int q0 = code / 17, q1 = code % 17;
                             const int n0 = q0 ? (int)br_get1(b) : 0, n1 = q1 ? (int)br_get1(b) : 0;
@@ -403,7 +447,7 @@ FE_FN int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, con
                                 n += 4;
                                 m1 = TB->pow43[(1 << n) + br_get(b, n)];
                             }
-                            cfo[k] = (n0 ? -m0 : m0) * sf; cfo[k + 1] = (n1 ? -m1 : m1) * sf;
+                            fe_store2(cfo + k, (n0 ? -m0 : m0) * sf, (n1 ? -m1 : m1) * sf);
                         }
                 }
             }
@@ -480,10 +524,12 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
             for (int i = 0; i < c0->max_sfb; i++, idx++) {
                 if (ms_mask[idx] && c0->band_type[idx] < 13 && c1->band_type[idx] < 13)
                     for (int w = 0; w < c0->group_len[g]; w++)
-                        for (int k = c0->swb[i]; k < c0->swb[i + 1]; k++) {
-                            float t = a[w * 128 + k] - d[w * 128 + k];
-                            a[w * 128 + k] += d[w * 128 + k];
-                            d[w * 128 + k] = t;
+                        for (int k = c0->swb[i]; k < c0->swb[i + 1]; k += 4) {        /* band widths are multiples of 4 */
+                            float *pa = a + w * 128 + k, *pd = d + w * 128 + k;
+                            const float a0 = pa[0], a1 = pa[1], a2 = pa[2], a3 = pa[3];
+                            const float d0 = pd[0], d1 = pd[1], d2 = pd[2], d3 = pd[3];
+                            fe_store4(pa, a0 + d0, a1 + d1, a2 + d2, a3 + d3);
+                            fe_store4(pd, a0 - d0, a1 - d1, a2 - d2, a3 - d3);
                         }
             }
             a += c0->group_len[g] * 128; d += c0->group_len[g] * 128;
@@ -865,34 +911,39 @@ FE_FN void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cp
 }
 
 /* ---------------------------------------------------------------- frame */
+/* HeaacSbrElem: 140 bytes of header + tables, then ch[2] of 592 bytes each (env_q at +88); HeaacPsFrame: 20 bytes of
+ * header, then the four parameter arrays back to back.  Everything is 4-byte aligned, so the copies go by words. */
 FE_FN void pack_sbr(const FeSbr *s, HeaacSbrElem *o)
 {
-    *o = s->t;
+    fe_copy32(o, &s->t, 140 / 4);
     o->start = s->start; o->reset = s->reset; o->bs_coupling = s->coupling;
     o->bs_limiter_gains = s->limiter_gains; o->bs_interpol_freq = s->interpol_freq; o->bs_smoothing_mode = s->smoothing_mode;
     for (int c = 0; c < 2; c++) {
         const FeSbrCh *d = &s->ch[c];
         HeaacSbrChan *oc = &o->ch[c];
-        memset(oc, 0, sizeof(*oc));
+        fe_zero32(oc, 88 / 4);
         oc->bs_num_env = d->num_env; oc->bs_num_noise = d->num_noise; oc->bs_amp_res = d->amp_res;
         oc->bs_add_harmonic_flag = d->add_harmonic_flag;
         oc->e_a[0] = d->e_a[0]; oc->e_a[1] = d->e_a[1]; oc->t_env_num_env_old = d->t_env_num_env_old;
-        memcpy(oc->bs_freq_res, d->freq_res, 7); memcpy(oc->t_env, d->t_env, 8); memcpy(oc->t_q, d->t_q, 3);
-        memcpy(oc->bs_invf_mode, d->invf, 10); memcpy(oc->bs_add_harmonic, d->add_harmonic, 48);
-        for (int e = 0; e < 5; e++) for (int k = 0; k < 48; k++) oc->env_q[e][k] = (int16_t)d->env[e + 1][k];
-        for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = (int16_t)d->noise[e + 1][k];
+        for (int i = 0; i < 7; i++) oc->bs_freq_res[i] = d->freq_res[i];
+        for (int i = 0; i < 8; i++) oc->t_env[i] = d->t_env[i];
+        for (int i = 0; i < 3; i++) oc->t_q[i] = d->t_q[i];
+        for (int i = 0; i < 5; i++) { oc->bs_invf_mode[0][i] = d->invf[0][i]; oc->bs_invf_mode[1][i] = d->invf[1][i]; }
+        if (d->add_harmonic_flag) fe_copy32(oc->bs_add_harmonic, d->add_harmonic, 48 / 4);
+        fe_copy32(oc->env_q, d->env[1], 5 * 48 * 2 / 4);
+        for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = d->noise[e + 1][k];
+        fe_zero32(oc->reserved2, 1);
     }
 }
 
 FE_FN void pack_ps(const FePs *p, HeaacPsFrame *o)
 {
-    memset(o, 0, sizeof(*o));
+    fe_zero32(o, 20 / 4);
     o->start = p->start; o->num_env = p->num_env; o->num_env_old = p->num_env_old; o->iid_quant = p->iid_quant;
     o->nr_iid_par = p->nr_iid_par; o->nr_icc_par = p->nr_icc_par; o->nr_ipdopd_par = p->nr_ipdopd_par; o->icc_mode = p->icc_mode;
     o->enable_ipdopd = p->enable_ipdopd; o->is34bands = p->is34; o->is34bands_old = p->is34_old;
     for (int i = 0; i < 6; i++) o->border_position[i] = (int8_t)p->border[i];
-    memcpy(o->iid_par, p->iid, sizeof(o->iid_par)); memcpy(o->icc_par, p->icc, sizeof(o->icc_par));
-    memcpy(o->ipd_par, p->ipd, sizeof(o->ipd_par)); memcpy(o->opd_par, p->opd, sizeof(o->opd_par));
+    fe_copy32(o->iid_par, p->iid, 4 * 5 * 34 / 4);         /* iid, icc, ipd, opd are contiguous in both structures */
 }
 
 /* One packet (an ADTS frame or a bare raw_data_block) -> the frame's C-ABI structures.
@@ -973,11 +1024,14 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
     fe->locked = 1;
     for (int c = 0; c < fe->ncc; c++) {
         const FeChan *fc = &fe->ch[c];
-        memset(&ics[c], 0, sizeof(ics[c]));
+        fe_zero32(&ics[c], 2);
         ics[c].window_sequence = fc->ws[0]; ics[c].window_shape = fc->shape[0]; ics[c].max_sfb = fc->max_sfb;
         ics[c].tns_present = fc->tns_present;
         ics[c].prev_valid = 1; ics[c].prev_window_sequence = fc->ws[1]; ics[c].prev_window_shape = fc->shape[1];
-        if (tns) { if (fc->tns_present) tns[c] = fc->tns; else memset(&tns[c], 0, sizeof(tns[c])); }
+        if (tns) {                                                 /* read by the back end only when tns_present */
+            if (fc->tns_present) fe_copy32(&tns[c], &fc->tns, (int)(sizeof(HeaacTns) / 4));
+            else fe_zero32(tns[c].n_filt, 2);
+        }
     }
     if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr(&fe->sbr_el[se], &sbr[se]), se++;
     if (ps) pack_ps(&fe->psx, ps);

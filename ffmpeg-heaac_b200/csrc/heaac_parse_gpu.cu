@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <new>
 
 #include "heaac_context.cuh"
@@ -37,8 +38,13 @@ struct HeaacGpuParser {
     uint32_t *h_off[2], *d_off[2];   /* [chunk][S] byte offset of each packet in the blob */
     int *h_size[2], *d_size[2];
     int *d_consumed[2];
+    int *h_consumed;                 /* page-locked, [max_frames_per_call][S]: keeps the D2H asynchronous */
     size_t blob_cap;
     cudaEvent_t ev_h2d[2];
+    cudaEvent_t ev_k0[2], ev_k1[2];  /* around k_parse, for parser_stats */
+    int timed[2];
+    double k_ms;
+    long long k_timed;
     long long launches;
 };
 
@@ -85,7 +91,10 @@ static void parser_free(HeaacGpuParser *p)
         if (p->d_size[b]) cudaFree(p->d_size[b]);
         if (p->d_consumed[b]) cudaFree(p->d_consumed[b]);
         if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]);
+        if (p->ev_k0[b]) cudaEventDestroy(p->ev_k0[b]);
+        if (p->ev_k1[b]) cudaEventDestroy(p->ev_k1[b]);
     }
+    if (p->h_consumed) cudaFreeHost(p->h_consumed);
     if (p->d_fe) cudaFree(p->d_fe);
     if (p->d_template) cudaFree(p->d_template);
     if (p->d_tb) cudaFree(p->d_tb);
@@ -142,6 +151,7 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     CKP(cudaMalloc(&p->d_fe, S * sizeof(FE)));
     CKP(cudaMalloc(&p->d_template, sizeof(FE)));
     CKP(cudaMemcpy(p->d_template, heaac_fe_state_blob(fe), sizeof(FE), cudaMemcpyHostToDevice));
+    CKP(cudaHostAlloc(&p->h_consumed, (size_t)c->cfg.max_frames_per_call * S * sizeof(int), cudaHostAllocDefault));
     for (int b = 0; b < 2 && !r; b++) {
         CKP(cudaHostAlloc(&p->h_blob[b], p->blob_cap, cudaHostAllocDefault));
         CKP(cudaHostAlloc(&p->h_off[b], n * sizeof(uint32_t), cudaHostAllocDefault));
@@ -151,6 +161,8 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
         CKP(cudaMalloc(&p->d_size[b], n * sizeof(int)));
         CKP(cudaMalloc(&p->d_consumed[b], n * sizeof(int)));
         CKP(cudaEventCreateWithFlags(&p->ev_h2d[b], cudaEventDisableTiming));
+        CKP(cudaEventCreate(&p->ev_k0[b]));
+        CKP(cudaEventCreate(&p->ev_k1[b]));
     }
 #undef CKP
     if (r) { parser_free(p); return r; }
@@ -162,6 +174,15 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
 
 extern "C" long long heaac_b200_parser_launch_count(const HeaacGpuParser *p) { return p ? p->launches : 0; }
 
+/* average k_parse duration (CUDA events on its stream) over the launches harvested so far */
+extern "C" int heaac_b200_parser_stats(const HeaacGpuParser *p, double *ms_per_launch, long long *timed_launches)
+{
+    if (!p) return HEAAC_E_INVAL;
+    if (ms_per_launch) *ms_per_launch = p->k_timed ? p->k_ms / (double)p->k_timed : 0.0;
+    if (timed_launches) *timed_launches = p->k_timed;
+    return 0;
+}
+
 /* n_frames x n_streams packets -> PCM.  pkt / size / consumed are frame-major [n_frames][n_streams] host arrays;
  * pcm / pcm_f32 are host buffers as in heaac_b200_synth.  Returns after the PCM has landed. */
 extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,
@@ -171,15 +192,26 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
     HeaacContext *c = p->ctx;
     const HeaacGeom *g = &c->geom;
     if (pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;
+    if (n_frames > c->cfg.max_frames_per_call) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
     const size_t S = g->n_streams;
     const int Tc = c->chunk;
+    static const int dbg = getenv("HEAAC_DEBUG_TIMING") != nullptr;
+    double t_sync = 0, t_gather = 0, t_submit = 0, t_wait = 0;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     for (int f0 = 0; f0 < n_frames; f0 += Tc, c->seq++) {
         const int buf = (int)(c->seq & 1);
         const int n = n_frames - f0 < Tc ? n_frames - f0 : Tc;
         const size_t np = (size_t)n * S;
+        const double t0 = now();
         /* the pinned packet set `buf` was last read by the H2D recorded in ev_h2d[buf] */
         if (c->seq >= 2) CK(cudaEventSynchronize(p->ev_h2d[buf]));
+        if (p->timed[buf] && cudaEventQuery(p->ev_k1[buf]) == cudaSuccess) {        /* harvest the timing of two chunks ago */
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p->ev_k0[buf], p->ev_k1[buf]) == cudaSuccess) { p->k_ms += ms; p->k_timed++; }
+            p->timed[buf] = 0;
+        }
+        const double t1 = now();
         size_t used = 0;
         for (size_t i = 0; i < np; i++) {                          /* gather: 8-byte aligned, >= 8 zero bytes after each */
             const int sz = size[(size_t)f0 * S + i];
@@ -191,6 +223,7 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
             p->h_size[buf][i] = sz;
             used += room;
         }
+        const double t2 = now();
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));     /* staging set free again */
         CK(cudaMemcpyAsync(p->d_blob[buf], p->h_blob[buf], used, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(p->d_off[buf], p->h_off[buf], np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_in));
@@ -201,10 +234,12 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
             const int threads = 128, warps_per_cta = threads / 32;
             const int n_warps = (int)((S + p->lanes - 1) / p->lanes);
             const int grid = (n_warps + warps_per_cta - 1) / warps_per_cta;
+            if (!p->timed[buf]) CK(cudaEventRecord(p->ev_k0[buf], c->s_in));
             k_parse<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_blob[buf], p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc,
                                                    g->nse, g->sbr, g->ps, p->lanes, c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf],
                                                    c->s_sbr[buf], c->s_ps[buf], p->d_consumed[buf]);
             CK(cudaGetLastError());
+            if (!p->timed[buf]) { CK(cudaEventRecord(p->ev_k1[buf], c->s_in)); p->timed[buf] = 1; }
             p->launches++;
         }
         CK(cudaEventRecord(c->ev_in[buf], c->s_in));
@@ -218,8 +253,15 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
         CK(cudaStreamWaitEvent(c->s_out, c->ev_done[buf], 0));
         if (pcm) CK(cudaMemcpyAsync(pcm + pcm_o, c->s_pcm[buf], pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_out));
         if (pcm_f32) CK(cudaMemcpyAsync(pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
-        if (consumed) CK(cudaMemcpyAsync(consumed + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync(p->h_consumed + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[buf], c->s_out));
+        const double t3 = now();
+        t_sync += t1 - t0; t_gather += t2 - t1; t_submit += t3 - t2;
     }
-    return heaac_b200_wait(c);
+    const double t4 = now();
+    int r = heaac_b200_wait(c);
+    t_wait = now() - t4;
+    if (!r && consumed) memcpy(consumed, p->h_consumed, (size_t)n_frames * S * sizeof(int));
+    if (dbg) fprintf(stderr, "parser_decode: sync %.2f gather %.2f submit %.2f wait %.2f ms\n", t_sync, t_gather, t_submit, t_wait);
+    return r;
 }

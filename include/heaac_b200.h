@@ -330,6 +330,8 @@ int  heaac_dec_decode(HeaacDecoder *dec, int n_frames, const uint8_t *const *pkt
 /* returns 1 once the first call has configured the decoder (0 before), and fills the optional outputs */
 int  heaac_dec_info(const HeaacDecoder *dec, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,
                     long long *parse_errors, long long *gpu_launches);
+/* gpu_parse decoders: average k_parse duration in ms per launch (0 otherwise) */
+double heaac_dec_parse_kernel_ms(const HeaacDecoder *dec);
 
 /* ---- device front end: the parser of heaac_fe_* compiled for the GPU, one thread per stream ---------
  * parser_create takes a host front end that was opened for the streams' configuration and not used yet (its
@@ -344,6 +346,8 @@ int  heaac_b200_parser_reset(HeaacGpuParser *p);
 int  heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
                               int16_t *pcm, float *pcm_f32, int *consumed);
 long long heaac_b200_parser_launch_count(const HeaacGpuParser *p);
+/* average k_parse duration in ms (CUDA events on its stream) and how many launches that average covers */
+int  heaac_b200_parser_stats(const HeaacGpuParser *p, double *ms_per_launch, long long *timed_launches);
 
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */

@@ -10,8 +10,14 @@ rep, kern, lib = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "-" not in f.split(".sm_")[0]] or os.listdir(tmp)
-dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin[0])], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for f in sorted(os.listdir(tmp)):          # one cubin per translation unit: take the one that holds the kernel
+    if not f.endswith(".cubin"):
+        continue
+    d = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], capture_output=True, text=True).stdout.splitlines()
+    if any(l.startswith("//----") and ".text." in l and re.search(kern, l) for l in d):
+        dis = d
+        break
 # locate the kernel's section
 start = next(i for i, l in enumerate(dis) if l.startswith("//----") and ".text." in l and re.search(kern, l))
 lines, cur, in_group = [], None, False
