@@ -36,6 +36,9 @@ EXPORTS = [
     "heaac_dec_open", "heaac_dec_close", "heaac_dec_decode", "heaac_dec_info",
     "heaac_b200_parser_create", "heaac_b200_parser_destroy", "heaac_b200_parser_reset", "heaac_b200_parser_decode",
     "heaac_b200_parser_launch_count", "heaac_b200_parser_stats", "heaac_dec_parse_kernel_ms",
+    "heaac_fe_parse_two_phase", "heaac_fe_copy_layout",
+    "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
+    "heaac_b200_ticket", "heaac_b200_ticket_wait",
 ]
 
 
@@ -83,6 +86,8 @@ def lib():
         L.heaac_fe_close.argtypes = [C.c_void_p]
         L.heaac_fe_close.restype = None
         L.heaac_fe_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.heaac_fe_parse_two_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.heaac_fe_copy_layout.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.heaac_b200_inputs_consumed.argtypes = [C.c_void_p]
@@ -95,6 +100,12 @@ def lib():
         L.heaac_dec_close.argtypes = [C.c_void_p]
         L.heaac_dec_close.restype = None
         L.heaac_dec_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.heaac_dec_submit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.heaac_dec_submit.restype = C.c_longlong
+        L.heaac_dec_wait.argtypes = [C.c_void_p, C.c_longlong]
+        L.heaac_b200_ticket.argtypes = [C.c_void_p]
+        L.heaac_b200_ticket.restype = C.c_longlong
+        L.heaac_b200_ticket_wait.argtypes = [C.c_void_p, C.c_longlong]
         L.heaac_dec_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_longlong)] * 2
         L.heaac_dec_parse_kernel_ms.argtypes = [C.c_void_p]
         L.heaac_dec_parse_kernel_ms.restype = C.c_double
@@ -273,14 +284,16 @@ class Frontend:
         self.ncc, self.nse, self.sbr, self.ps, self.sr_index = [x.value for x in v]
         self.elem_types = [int(et[i]) for i in range(max(n, 0))]
 
-    def parse(self, pkt):
-        """Returns dict(coeffs [ncc,1024], ics [ncc], tns [ncc], sbr [nse], ps [1], consumed)."""
+    def parse(self, pkt, two_phase=False):
+        """Returns dict(coeffs [ncc,1024], ics [ncc], tns [ncc], sbr [nse], ps [1], consumed).
+        two_phase: go through heaac_fe_parse_two_phase (the device front end's decomposition)."""
         buf = np.frombuffer(pkt, np.uint8)
         # sized for the largest configuration: an ADTS header inside this very packet may (re)configure the stream
         r = {"coeffs": np.zeros((16, 1024), np.float32), "ics": np.zeros(16, ICS), "tns": np.zeros(16, TNS),
              "sbr": np.zeros(8, SBR_ELEM), "ps": np.zeros(1, PS_FRAME)}
-        n = lib().heaac_fe_parse(self.h, buf.ctypes.data, buf.size, r["coeffs"].ctypes.data, r["ics"].ctypes.data,
-                                 r["tns"].ctypes.data, r["sbr"].ctypes.data, r["ps"].ctypes.data)
+        fn = lib().heaac_fe_parse_two_phase if two_phase else lib().heaac_fe_parse
+        n = fn(self.h, buf.ctypes.data, buf.size, r["coeffs"].ctypes.data, r["ics"].ctypes.data,
+               r["tns"].ctypes.data, r["sbr"].ctypes.data, r["ps"].ctypes.data)
         _check(n, "heaac_fe_parse")
         self._refresh()
         for k in ("coeffs", "ics", "tns"):
@@ -362,6 +375,16 @@ class Decoder:
             if f32 is not None:
                 f32 = f32.reshape(-1)[:n].reshape(T, self.S, self.nout, self.out_len).copy()
         return pcm, f32, consumed
+
+    def submit(self, batch, pcm_out, consumed_out=None):
+        """Asynchronous decode into caller-owned (page-locked) pcm_out; returns a ticket for wait()."""
+        t = lib().heaac_dec_submit(self.h, batch.T, batch.ptrs.ctypes.data, batch.sizes.ctypes.data, pcm_out.ctypes.data, None,
+                                   consumed_out.ctypes.data if consumed_out is not None else None)
+        _check(t, "heaac_dec_submit")
+        return t
+
+    def wait(self, ticket):
+        _check(lib().heaac_dec_wait(self.h, ticket), "heaac_dec_wait")
 
     def close(self):
         if self.h:

@@ -294,11 +294,15 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
     c->chunk = (int)((T + 3) / 4);
     if (c->chunk > 8) c->chunk = 8;
+    if (getenv("HEAAC_CHUNK_FRAMES")) c->chunk = atoi(getenv("HEAAC_CHUNK_FRAMES"));     /* tuning knob */
+    if (c->chunk > 32) c->chunk = 32;
+    if ((size_t)c->chunk > T) c->chunk = (int)T;
     if (c->chunk < 1) c->chunk = 1;
     {
         const size_t Tc = c->chunk;
         CKX(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CKX(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) CKX(cudaEventCreateWithFlags(&c->ev_ticket[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             CKX(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             CKX(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -347,6 +351,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
+    for (int i = 0; i < 8; i++) if (c->ev_ticket[i]) cudaEventDestroy(c->ev_ticket[i]);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]);
@@ -471,6 +476,25 @@ extern "C" int heaac_b200_inputs_consumed(HeaacContext *c)
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaStreamSynchronize(c->s_in));
     return 0;
+}
+
+/* A ticket marks "all host-pointer work submitted so far": ticket_wait returns once the PCM of everything submitted
+ * before the ticket was taken is in host memory, without waiting for later submissions.  Up to 8 outstanding. */
+extern "C" long long heaac_b200_ticket(HeaacContext *c)
+{
+    if (!c) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaEventRecord(c->ev_ticket[c->n_tickets & 7], c->s_out));
+    return c->n_tickets++;
+}
+
+extern "C" int heaac_b200_ticket_wait(HeaacContext *c, long long ticket)
+{
+    if (!c || ticket < 0 || ticket >= c->n_tickets) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    if (c->n_tickets - ticket > 8) return 0;                   /* its event has been reused: that work finished long ago */
+    CK(cudaEventSynchronize(c->ev_ticket[ticket & 7]));
+    return heaac_cuda_err(cudaGetLastError(), "ticket_wait");
 }
 
 /* everything submitted so far is complete: PCM is in the caller's buffers */

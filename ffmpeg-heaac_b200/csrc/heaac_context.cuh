@@ -28,6 +28,8 @@ struct HeaacContext {
     int16_t *s_pcm[2]; float *s_pcm_f32[2];
     cudaStream_t s_in, s_out;
     cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    cudaEvent_t ev_ticket[8];          /* completion marks on s_out, heaac_b200_ticket_* */
+    long long n_tickets;
     long long launches;
     size_t smem_core, smem_sbr, smem_ps, smem_synth;
     int core_grid;                   /* persistent k_core: resident CTAs on the whole GPU */

@@ -48,7 +48,11 @@ struct HeaacDecoder {
     std::vector<HeaacFrontend *> fe;
     HeaacContext *be = nullptr;
     HeaacGpuParser *gpu = nullptr;                    /* cfg.gpu_parse: the device front end replaces fe[] + workers */
-    std::vector<int> scratch_consumed;
+    std::vector<int> scratch_consumed[8];
+    int *pending_consumed[8] = { nullptr };
+    size_t pending_n[8] = { 0 };
+    long long pending_ticket[8] = { 0 };
+    long long n_submitted = 0, n_chunks = 0;
     int ncc = 0, nse = 0, sbr = 0, ps = 0, sr_index = 0, n_elems = 0, chunk = 1;
     uint8_t elem_type[HEAAC_MAX_ELEMS] = { 0 };
     ParamSet set[2];
@@ -159,8 +163,8 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
         d->n_elems = heaac_fe_info(probe, &d->ncc, &d->nse, &d->sbr, &d->ps, &d->sr_index, d->elem_type);
         r = d->n_elems > 0 ? 0 : HEAAC_E_INVAL;
     }
-    heaac_fe_close(probe);
-    if (r < 0) return r;
+    if (r < 0) { heaac_fe_close(probe); return r; }
+    struct ProbeGuard { HeaacFrontend *p; ~ProbeGuard() { heaac_fe_close(p); } } guard{probe};
 
     HeaacConfig cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -183,6 +187,7 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     if (d->cfg.gpu_parse) {
         HeaacFrontend *f = nullptr;
         if ((r = heaac_fe_open(&f, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0))) return r;
+        heaac_fe_copy_layout(f, probe);               /* ADTS input: every stream starts from the layout packet 0 announced */
         r = heaac_b200_parser_create(d->be, f, 0, &d->gpu);
         heaac_fe_close(f);
         return r;
@@ -247,8 +252,10 @@ extern "C" void heaac_dec_close(HeaacDecoder *d)
     delete d;
 }
 
-extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
-                                int16_t *pcm, float *pcm_f32, int *consumed)
+/* Asynchronous form: the packets are consumed (parsed, or copied for the GPU parser) before the call returns;
+ * pcm / pcm_f32 / consumed are complete once heaac_dec_wait(ticket) returns.  Up to 8 calls may be outstanding. */
+extern "C" long long heaac_dec_submit(HeaacDecoder *d, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                                      int16_t *pcm, float *pcm_f32, int *consumed)
 {
     if (!d || n_frames <= 0 || !pkt || !pkt_size || (!pcm && !pcm_f32)) return HEAAC_E_INVAL;
     if (n_frames > d->cfg.max_frames_per_call) return HEAAC_E_INVAL;
@@ -258,20 +265,20 @@ extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *co
     const size_t S = d->cfg.n_streams;
     if (d->gpu) {
         int *cons = consumed;
-        if (!cons) { d->scratch_consumed.resize((size_t)n_frames * S); cons = d->scratch_consumed.data(); }
-        if ((r = heaac_b200_parser_decode(d->gpu, n_frames, pkt, pkt_size, pcm, pcm_f32, cons))) return r;
-        long long bad = 0;
-        for (size_t i = 0; i < (size_t)n_frames * S; i++) bad += cons[i] < 0;
-        d->parse_errors += bad;
-        return 0;
+        const int slot = (int)(d->n_submitted & 7);
+        if (!cons) { d->scratch_consumed[slot].resize((size_t)n_frames * S); cons = d->scratch_consumed[slot].data(); }
+        long long t = heaac_b200_parser_submit(d->gpu, n_frames, pkt, pkt_size, pcm, pcm_f32, cons);
+        if (t < 0) return t;
+        d->pending_consumed[slot] = cons; d->pending_n[slot] = (size_t)n_frames * S; d->pending_ticket[slot] = t;
+        d->n_submitted++;
+        return t;
     }
     const size_t out_frame = S * heaac_b200_frame_out_len(d->be) * heaac_b200_n_out_channels(d->be);
-    int k = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += d->chunk, k++) {
+    for (int f0 = 0; f0 < n_frames; f0 += d->chunk, d->n_chunks++) {
         const int n = n_frames - f0 < d->chunk ? n_frames - f0 : d->chunk;
-        ParamSet *p = &d->set[k & 1];
-        /* set k&1 was handed to the GPU two chunks ago: its H2D copies must be over before it is overwritten */
-        if (k >= 2 && (r = heaac_b200_inputs_consumed(d->be))) return r;
+        ParamSet *p = &d->set[d->n_chunks & 1];
+        /* this set was handed to the GPU two chunks ago: its H2D copies must be over before it is overwritten */
+        if (d->n_chunks >= 2 && (r = heaac_b200_inputs_consumed(d->be))) return r;
         Job j;
         j.pkt = pkt + (size_t)f0 * S; j.size = pkt_size + (size_t)f0 * S;
         j.consumed = consumed ? consumed + (size_t)f0 * S : nullptr;
@@ -285,7 +292,31 @@ extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *co
         b.pcm_f32 = pcm_f32 ? pcm_f32 + (size_t)f0 * out_frame : nullptr;
         if ((r = heaac_b200_synth_submit(d->be, &b))) return r;
     }
-    return heaac_b200_wait(d->be);
+    d->n_submitted++;
+    return heaac_b200_ticket(d->be);
+}
+
+extern "C" int heaac_dec_wait(HeaacDecoder *d, long long ticket)
+{
+    if (!d || !d->be) return HEAAC_E_INVAL;
+    if (!d->gpu) return heaac_b200_ticket_wait(d->be, ticket);
+    int r = heaac_b200_parser_wait(d->gpu, ticket);
+    if (r) return r;
+    for (int slot = 0; slot < 8; slot++)
+        if (d->pending_consumed[slot] && d->pending_ticket[slot] == ticket) {
+            long long bad = 0;
+            for (size_t i = 0; i < d->pending_n[slot]; i++) bad += d->pending_consumed[slot][i] < 0;
+            d->parse_errors += bad;
+            d->pending_consumed[slot] = nullptr;
+        }
+    return 0;
+}
+
+extern "C" int heaac_dec_decode(HeaacDecoder *d, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                                int16_t *pcm, float *pcm_f32, int *consumed)
+{
+    long long t = heaac_dec_submit(d, n_frames, pkt, pkt_size, pcm, pcm_f32, consumed);
+    return t < 0 ? (int)t : heaac_dec_wait(d, t);
 }
 
 extern "C" int heaac_dec_info(const HeaacDecoder *d, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,

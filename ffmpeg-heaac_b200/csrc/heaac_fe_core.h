@@ -22,6 +22,7 @@
 #ifndef HEAAC_FE_CORE_H
 #define HEAAC_FE_CORE_H
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include "../../include/heaac_b200.h"
@@ -206,6 +207,16 @@ typedef struct FePs {
     int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
 } FePs;
 
+/* What the stateless first phase of the two-phase parse (fe_phase_a / fe_phase_b below) leaves for the second. */
+#define FE_MAX_TODO 8
+typedef struct FeTodo {
+    int result;                                 /* phase A's return value: bytes consumed or a negative error */
+    int serial;                                 /* the frame has to go through the one-pass parser (PNS, errors, overflow) */
+    int n_sbr;
+    struct { int pos, cnt, crc, prev_elem, prev_type; } sbr[FE_MAX_TODO];   /* SBR fill payloads: where and after what */
+    uint8_t chan[FE_MAX_CH];                    /* 0 absent, 1 read its own ics_info, 2 shares the previous channel's */
+} FeTodo;
+
 struct HeaacFrontend {
     int sample_rate, sr_index, chan_config, object_type;
     int sbr, ps;                                /* -1 unknown (implicit signalling), 0 absent, 1 present */
@@ -215,6 +226,8 @@ struct HeaacFrontend {
     int ncc, nse;
     int sf_offset;                              /* 60: s16-unit scaling, 0: C bias scaling (aacdec.c:573-581) */
     int random_state;
+    int phase_a, saw_pns, last_common;          /* two-phase parse bookkeeping */
+    FeTodo *todo;
     FeChan ch[FE_MAX_CH];
     FeSbr sbr_el[HEAAC_MAX_ELEMS];
     FePs psx;
@@ -368,6 +381,7 @@ FE_FN int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, con
             if (bt == 0 || bt >= 14) {
                 for (int w = 0; w < glen; w++, cfo += 128) fe_zero(cfo, len);
             } else if (bt == 13) {                                 /* PNS, aacdec.c:1021-1036 */
+                fe->saw_pns = 1;
                 for (int w = 0; w < glen; w++, cfo += 128) {
                     float energy = 0.0f;
                     for (int k = 0; k < len; k++) {
@@ -503,6 +517,7 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
     uint8_t ms_mask[128];
     int r, ms_present = 0;
     int common = br_get1(b);
+    fe->last_common = common;
     memset(ms_mask, 0, sizeof(ms_mask));
     if (common) {
         if ((r = ics_info(fe, c0, b))) return r;
@@ -946,6 +961,22 @@ FE_FN void pack_ps(const FePs *p, HeaacPsFrame *o)
     fe_copy32(o->iid_par, p->iid, 4 * 5 * 34 / 4);         /* iid, icc, ipd, opd are contiguous in both structures */
 }
 
+/* An SBR fill payload met after element `prev_elem` (decode_extension_payload, aacdec.c:1650-1690): implicit
+ * signalling, then ff_decode_sbr_extension.  `b` stands right after the 4-bit extension type; leaves it after
+ * the payload. */
+FE_FN void fe_sbr_payload(FE *fe, BR *b, int crc, int cnt, int prev_elem, int prev_type)
+{
+    if (prev_elem < 0 || fe->sbr == 0 || (fe->sbr == -1 && fe->locked)) {
+        br_skip(b, 8 * cnt - 4);
+        return;
+    }
+    if (fe->ps == -1 && !fe->locked && fe->ncc == 1) { fe->sbr = 1; fe->ps = 1; }
+    else fe->sbr = 1;
+    int se = 0;
+    for (int i = 0; i < prev_elem; i++) se += fe->elem_type[i] != HEAAC_TYPE_LFE;
+    sbr_extension(fe, &fe->sbr_el[se], b, crc, cnt, prev_type == 1);
+}
+
 /* One packet (an ADTS frame or a bare raw_data_block) -> the frame's C-ABI structures.
  * coeffs [ncc][1024]; ics/tns [ncc]; sbr [nse] (may be NULL for LC); ps (may be NULL).
  * Returns bytes consumed (>= 0) or a negative HEAAC_E_* code (the reference returns -1). */
@@ -986,9 +1017,15 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
             seen[type]++;
         }
         switch (type) {
-        case 0: case 3: r = decode_ics(fe, &fe->ch[fe->elem_ch0[e]], b, coeffs + 1024 * fe->elem_ch0[e], 0); break;
-        case 1: r = decode_cpe(fe, &fe->ch[fe->elem_ch0[e]], &fe->ch[fe->elem_ch0[e] + 1], b,
-                               coeffs + 1024 * fe->elem_ch0[e], coeffs + 1024 * (fe->elem_ch0[e] + 1)); break;
+        case 0: case 3:
+            r = decode_ics(fe, &fe->ch[fe->elem_ch0[e]], b, coeffs + 1024 * fe->elem_ch0[e], 0);
+            if (fe->phase_a) fe->todo->chan[fe->elem_ch0[e]] = 1;
+            break;
+        case 1:
+            r = decode_cpe(fe, &fe->ch[fe->elem_ch0[e]], &fe->ch[fe->elem_ch0[e] + 1], b,
+                           coeffs + 1024 * fe->elem_ch0[e], coeffs + 1024 * (fe->elem_ch0[e] + 1));
+            if (fe->phase_a) { fe->todo->chan[fe->elem_ch0[e]] = 1; fe->todo->chan[fe->elem_ch0[e] + 1] = fe->last_common ? 2 : 1; }
+            break;
         case 4: {                                                  /* DSE, aacdec.c:1190-1200 region */
             int align = br_get1(b), cnt = br_get(b, 8);
             if (cnt == 255) cnt += br_get(b, 8);
@@ -1002,15 +1039,16 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
             while (cnt > 0) {                                      /* decode_extension_payload, aacdec.c:1650-1690 */
                 int ext = br_get(b, 4), res = cnt;
                 if (ext == 0xd || ext == 0xe) {
-                    if (prev_elem < 0 || fe->sbr == 0 || (fe->sbr == -1 && fe->locked)) {
+                    if (fe->phase_a) {                             /* stateless phase: note it for phase B, skip the bits */
+                        FeTodo *td = fe->todo;
+                        if (td->n_sbr < FE_MAX_TODO) {
+                            td->sbr[td->n_sbr].pos = b->pos; td->sbr[td->n_sbr].cnt = cnt; td->sbr[td->n_sbr].crc = ext == 0xe;
+                            td->sbr[td->n_sbr].prev_elem = prev_elem; td->sbr[td->n_sbr].prev_type = prev_type;
+                            td->n_sbr++;
+                        } else td->serial = 1;
                         br_skip(b, 8 * cnt - 4);
-                    } else {
-                        if (fe->ps == -1 && !fe->locked && fe->ncc == 1) { fe->sbr = 1; fe->ps = 1; }
-                        else fe->sbr = 1;
-                        int se = 0;
-                        for (int i = 0; i < prev_elem; i++) se += fe->elem_type[i] != HEAAC_TYPE_LFE;
-                        sbr_extension(fe, &fe->sbr_el[se], b, ext == 0xe, cnt, prev_type == 1);
-                    }
+                    } else
+                        fe_sbr_payload(fe, b, ext == 0xe, cnt, prev_elem, prev_type);
                 } else br_skip(b, 8 * cnt - 4);
                 cnt -= res;
             }
@@ -1039,5 +1077,61 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
     return consumed > size ? size : consumed;
 }
 
+
+
+/* ---------------------------------------------------------------- two-phase parse
+ * The device front end spreads the frames of a chunk over the lanes of a warp.  Entropy decoding of the core
+ * elements -- nearly all of the work -- needs nothing from the previous frame, so phase A runs fe_parse_frame on a
+ * frame-local scratch state (head + channel blocks only) and merely notes where the SBR payloads are.  Phase B then
+ * walks the frames in order on the stream's persistent state: previous-window bookkeeping (ics_info and the
+ * common_window copy of decode_cpe, aacdec.c:645-710, 1464-1470), implicit signalling, the SBR / PS payloads (delta
+ * coded against the previous frame) and the packing.  Frames that touch sequential state inside the core elements
+ * (PNS draws from the stream's random generator) or that failed are simply redone by the one-pass parser. */
+FE_FN size_t fe_scratch_bytes(int ncc) { return offsetof(FE, ch) + (size_t)ncc * sizeof(FeChan); }
+
+FE_FN void fe_phase_a(const FE *stream, FE *scratch, FeTodo *todo, const uint8_t *pkt, int size, float *coeffs,
+                      HeaacIcs *ics, HeaacTns *tns)
+{
+    fe_copy32(scratch, stream, (int)(offsetof(FE, ch) / 4));
+    scratch->phase_a = 1; scratch->saw_pns = 0; scratch->todo = todo;
+    todo->serial = 0; todo->n_sbr = 0;
+    for (int c = 0; c < FE_MAX_CH; c++) todo->chan[c] = 0;
+    todo->result = fe_parse_frame(scratch, pkt, size, coeffs, ics, tns, NULL, NULL);
+    if (todo->result < 0 || scratch->saw_pns || scratch->ncc != stream->ncc) todo->serial = 1;
+    else
+        for (int c = 0; c < stream->ncc; c++) if (!todo->chan[c]) fe_zero(coeffs + 1024 * c, 1024);
+}
+
+FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                     HeaacSbrElem *sbr, HeaacPsFrame *ps)
+{
+    if (todo->serial) return fe_parse_frame(fe, pkt, size, coeffs, ics, tns, sbr, ps);
+    for (int c = 0; c < fe->ncc; c++) {
+        FeChan *st = &fe->ch[c];
+        if (todo->chan[c] == 1) {
+            st->ws[1] = st->ws[0]; st->ws[0] = ics[c].window_sequence;
+            st->shape[1] = st->shape[0]; st->shape[0] = ics[c].window_shape;
+        } else if (todo->chan[c] == 2) {
+            const int keep = st->shape[0];
+            st->ws[0] = st[-1].ws[0]; st->ws[1] = st[-1].ws[1]; st->shape[0] = st[-1].shape[0]; st->shape[1] = keep;
+        } else {
+            fe_zero32(&ics[c], 2);
+            ics[c].window_sequence = (uint8_t)st->ws[0]; ics[c].window_shape = (uint8_t)st->shape[0];
+        }
+        ics[c].prev_valid = 1; ics[c].prev_window_sequence = (uint8_t)st->ws[1]; ics[c].prev_window_shape = (uint8_t)st->shape[1];
+    }
+    if (todo->n_sbr) {
+        BR br;
+        br_init(&br, pkt, size);
+        for (int k = 0; k < todo->n_sbr; k++) {
+            br.pos = todo->sbr[k].pos;
+            fe_sbr_payload(fe, &br, todo->sbr[k].crc, todo->sbr[k].cnt, todo->sbr[k].prev_elem, todo->sbr[k].prev_type);
+        }
+    }
+    fe->locked = 1;
+    if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr(&fe->sbr_el[se], &sbr[se]), se++;
+    if (ps) pack_ps(&fe->psx, ps);
+    return todo->result;
+}
 
 #endif

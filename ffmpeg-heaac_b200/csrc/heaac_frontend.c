@@ -179,6 +179,28 @@ int heaac_fe_parse(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs
     return fe_parse_frame(fe, pkt, size, coeffs, ics, tns, sbr, ps);
 }
 
+/* The two-phase parse the device front end uses (fe_phase_a + fe_phase_b), run on the host: same results as
+ * heaac_fe_parse by construction -- tests hold it to that. */
+int heaac_fe_parse_two_phase(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                             HeaacSbrElem *sbr, HeaacPsFrame *ps)
+{
+    if (!fe || !pkt || size <= 0 || !coeffs || !ics || !tns) return HEAAC_E_INVAL;
+    FE *scratch = (FE *)malloc(sizeof(FE));
+    FeTodo todo;
+    if (!scratch) return HEAAC_E_NOMEM;
+    fe_phase_a(fe, scratch, &todo, pkt, size, coeffs, ics, tns);
+    free(scratch);
+    return fe_phase_b(fe, &todo, pkt, size, coeffs, ics, tns, sbr, ps);
+}
+
+/* give an unconfigured front end (ADTS input, nothing parsed yet) the layout another one has found */
+int heaac_fe_copy_layout(FE *dst, const FE *src)
+{
+    if (!dst || !src) return HEAAC_E_INVAL;
+    dst->sample_rate = src->sample_rate; dst->sr_index = src->sr_index;
+    return src->chan_config ? set_layout(dst, src->chan_config) : 0;
+}
+
 /* the state block of an opened front end, for the device front end to replicate per stream */
 const void *heaac_fe_state_blob(const FE *fe) { return fe; }
 

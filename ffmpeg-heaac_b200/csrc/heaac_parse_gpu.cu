@@ -7,13 +7,15 @@
  * TNS / SBR / PS structures straight into the back end's device staging sets, so the host-to-device traffic of a
  * batch shrinks from the dequantised spectra (4 KiB per channel-frame) to the packets themselves (~0.2 KiB).
  *
- * Each warp runs `lanes` streams (1 by default: divergent serial code, and warps are plentiful); per-stream parser
- * state (struct HeaacFrontend) lives in HBM between calls.  Chunks are double buffered exactly like the
+ * One warp per stream: the frames of a chunk are spread over the lanes for the stateless part of the parse and
+ * finished in order by lane 0 (two-phase parse, heaac_fe_core.h); per-stream parser state (struct
+ * HeaacFrontend) lives in HBM between calls.  Chunks are double buffered exactly like the
  * host-pointer path of heaac_b200_synth_submit: packets H2D + k_parse on s_in, synthesis kernels on the
  * context's stream, PCM D2H on s_out.
  */
 #define FE_DEVICE 1
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,13 +34,17 @@ struct HeaacGpuParser {
     FE *d_fe;                        /* [S] parser state */
     FE *d_template;                  /* state right after open, for reset */
     FeTables *d_tb;
-    int lanes;                       /* streams per warp */
+    uint8_t *d_scratch;              /* [S][32] frame-local parser states of phase A (head + channel blocks) */
+    size_t scratch_stride;
+    FeTodo *d_todo;                  /* [S][32] */
     /* per staging set: packets of one chunk, 8-byte aligned and zero padded */
     uint8_t *h_blob[2], *d_blob[2];
     uint32_t *h_off[2], *d_off[2];   /* [chunk][S] byte offset of each packet in the blob */
     int *h_size[2], *d_size[2];
     int *d_consumed[2];
-    int *h_consumed;                 /* page-locked, [max_frames_per_call][S]: keeps the D2H asynchronous */
+    int *h_consumed[8];              /* page-locked, [max_frames_per_call][S] per outstanding call: keeps the D2H asynchronous */
+    int *user_consumed[8];           /* where each outstanding call's consumed[] goes once it is waited for */
+    int user_n[8];
     size_t blob_cap;
     cudaEvent_t ev_h2d[2];
     cudaEvent_t ev_k0[2], ev_k1[2];  /* around k_parse, for parser_stats */
@@ -48,34 +54,47 @@ struct HeaacGpuParser {
     long long launches;
 };
 
-/* one thread per stream; frames of the chunk in order (parser state is sequential within a stream) */
+/* One warp per stream.  Phase A: lane t parses the core elements of the chunk's frame t on a frame-local scratch
+ * state (independent of the other frames); phase B: lane 0 walks the frames in order on the stream's persistent
+ * state (window history, SBR / PS payloads, packing).  See heaac_fe_core.h, "two-phase parse". */
 __global__ void __launch_bounds__(128)
-k_parse(FE *fes, const uint8_t *blob, const uint32_t *off, const int *size, int n_frames, int S, int ncc, int nse,
-        int has_sbr, int has_ps, int lanes, float *coeffs, HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr,
-        HeaacPsFrame *ps, int *consumed)
+k_parse(FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const uint8_t *blob, const uint32_t *off,
+        const int *size, int n_frames, int S, int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics,
+        HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (lane >= lanes) return;
-    const int s = warp * lanes + lane;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= S) return;
     FE *fe = fes + s;
-    for (int t = 0; t < n_frames; t++) {
-        const size_t idx = (size_t)t * S + s;
-        float *co = coeffs + idx * ncc * 1024;
-        HeaacIcs *ic = ics + idx * ncc;
-        HeaacTns *tn = tns + idx * ncc;
-        HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
-        HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
-        int r = fe_parse_frame(fe, blob + off[idx], size[idx], co, ic, tn, sb, pp);
-        if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;          /* layout differs from the batch's */
-        if (r < 0) {                                                /* silent frame; the batch goes on */
-            fe_zero(co, ncc * 1024);
-            memset(ic, 0, sizeof(HeaacIcs) * ncc);
-            memset(tn, 0, sizeof(HeaacTns) * ncc);
-            if (sb) memset(sb, 0, sizeof(HeaacSbrElem) * nse);
-            if (pp) memset(pp, 0, sizeof(HeaacPsFrame));
+    for (int t0 = 0; t0 < n_frames; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < n_frames) {
+            const size_t idx = (size_t)t * S + s;
+            fe_phase_a(fe, (FE *)(scratch + ((size_t)s * 32 + lane) * scratch_stride), todo + (size_t)s * 32 + lane,
+                       blob + off[idx], size[idx], coeffs + idx * ncc * 1024, ics + idx * ncc, tns + idx * ncc);
         }
-        consumed[idx] = r;
+        __syncwarp();
+        if (lane == 0) {
+            const int n = n_frames - t0 < 32 ? n_frames - t0 : 32;
+            for (int k = 0; k < n; k++) {
+                const size_t idx = (size_t)(t0 + k) * S + s;
+                float *co = coeffs + idx * ncc * 1024;
+                HeaacIcs *ic = ics + idx * ncc;
+                HeaacTns *tn = tns + idx * ncc;
+                HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
+                HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
+                int r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, sb, pp);
+                if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;      /* layout differs from the batch's */
+                if (r < 0) {                                            /* silent frame; the batch goes on */
+                    fe_zero(co, ncc * 1024);
+                    fe_zero32(ic, (int)(sizeof(HeaacIcs) * ncc / 4));
+                    fe_zero32(tn, (int)(sizeof(HeaacTns) * ncc / 4));
+                    if (sb) fe_zero32(sb, (int)(sizeof(HeaacSbrElem) * nse / 4));
+                    if (pp) fe_zero32(pp, (int)(sizeof(HeaacPsFrame) / 4));
+                }
+                consumed[idx] = r;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -94,9 +113,11 @@ static void parser_free(HeaacGpuParser *p)
         if (p->ev_k0[b]) cudaEventDestroy(p->ev_k0[b]);
         if (p->ev_k1[b]) cudaEventDestroy(p->ev_k1[b]);
     }
-    if (p->h_consumed) cudaFreeHost(p->h_consumed);
+    for (int i = 0; i < 8; i++) if (p->h_consumed[i]) cudaFreeHost(p->h_consumed[i]);
     if (p->d_fe) cudaFree(p->d_fe);
     if (p->d_template) cudaFree(p->d_template);
+    if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->d_todo) cudaFree(p->d_todo);
     if (p->d_tb) cudaFree(p->d_tb);
     delete p;
 }
@@ -134,9 +155,6 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     if (!p) return HEAAC_E_NOMEM;
     memset(p, 0, sizeof(*p));
     p->ctx = c;
-    p->lanes = 1;
-    const char *env = getenv("HEAAC_PARSE_LANES");
-    if (env && atoi(env) >= 1 && atoi(env) <= 32) p->lanes = atoi(env);
     const size_t S = c->geom.n_streams, n = (size_t)c->chunk * S;
     if (!max_packet_bytes) max_packet_bytes = 6144 / 8 * c->geom.ncc + 64;    /* 6144 bits per channel, aacenc.c:595 */
     p->blob_cap = n * ((max_packet_bytes + 15) & ~(size_t)7);
@@ -150,8 +168,11 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     CKP(cudaMemcpyToSymbol(fe_tb_dev, &p->d_tb, sizeof(p->d_tb)));
     CKP(cudaMalloc(&p->d_fe, S * sizeof(FE)));
     CKP(cudaMalloc(&p->d_template, sizeof(FE)));
+    p->scratch_stride = (offsetof(FE, ch) + (size_t)c->geom.ncc * sizeof(FeChan) + 15) & ~(size_t)15;
+    CKP(cudaMalloc(&p->d_scratch, S * 32 * p->scratch_stride));
+    CKP(cudaMalloc(&p->d_todo, S * 32 * sizeof(FeTodo)));
     CKP(cudaMemcpy(p->d_template, heaac_fe_state_blob(fe), sizeof(FE), cudaMemcpyHostToDevice));
-    CKP(cudaHostAlloc(&p->h_consumed, (size_t)c->cfg.max_frames_per_call * S * sizeof(int), cudaHostAllocDefault));
+    for (int i = 0; i < 8; i++) CKP(cudaHostAlloc(&p->h_consumed[i], (size_t)c->cfg.max_frames_per_call * S * sizeof(int), cudaHostAllocDefault));
     for (int b = 0; b < 2 && !r; b++) {
         CKP(cudaHostAlloc(&p->h_blob[b], p->blob_cap, cudaHostAllocDefault));
         CKP(cudaHostAlloc(&p->h_off[b], n * sizeof(uint32_t), cudaHostAllocDefault));
@@ -183,10 +204,12 @@ extern "C" int heaac_b200_parser_stats(const HeaacGpuParser *p, double *ms_per_l
     return 0;
 }
 
-/* n_frames x n_streams packets -> PCM.  pkt / size / consumed are frame-major [n_frames][n_streams] host arrays;
- * pcm / pcm_f32 are host buffers as in heaac_b200_synth.  Returns after the PCM has landed. */
-extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,
-                                        int16_t *pcm, float *pcm_f32, int *consumed)
+/* n_frames x n_streams packets -> PCM, asynchronously.  pkt / size / consumed are frame-major [n_frames][n_streams]
+ * host arrays; pcm / pcm_f32 are host buffers as in heaac_b200_synth.  The packets are copied before the call
+ * returns; pcm / pcm_f32 / consumed are filled by the time heaac_b200_parser_wait(ticket) returns.
+ * Returns the ticket (>= 0) or a negative error. */
+extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,
+                                              int16_t *pcm, float *pcm_f32, int *consumed)
 {
     if (!p || n_frames <= 0 || !pkt || !size || (!pcm && !pcm_f32)) return HEAAC_E_INVAL;
     HeaacContext *c = p->ctx;
@@ -196,6 +219,7 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
     CK(cudaSetDevice(c->cfg.device));
     const size_t S = g->n_streams;
     const int Tc = c->chunk;
+    const int slot = (int)(c->n_tickets & 7);
     static const int dbg = getenv("HEAAC_DEBUG_TIMING") != nullptr;
     double t_sync = 0, t_gather = 0, t_submit = 0, t_wait = 0;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -208,7 +232,7 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
         if (c->seq >= 2) CK(cudaEventSynchronize(p->ev_h2d[buf]));
         if (p->timed[buf] && cudaEventQuery(p->ev_k1[buf]) == cudaSuccess) {        /* harvest the timing of two chunks ago */
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, p->ev_k0[buf], p->ev_k1[buf]) == cudaSuccess) { p->k_ms += ms; p->k_timed++; }
+            if (cudaEventElapsedTime(&ms, p->ev_k0[buf], p->ev_k1[buf]) == cudaSuccess && p->launches > 8) { p->k_ms += ms; p->k_timed++; }
             p->timed[buf] = 0;
         }
         const double t1 = now();
@@ -232,12 +256,12 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));      /* d_consumed[buf] drained */
         {
             const int threads = 128, warps_per_cta = threads / 32;
-            const int n_warps = (int)((S + p->lanes - 1) / p->lanes);
-            const int grid = (n_warps + warps_per_cta - 1) / warps_per_cta;
+            const int grid = (int)((S + warps_per_cta - 1) / warps_per_cta);
             if (!p->timed[buf]) CK(cudaEventRecord(p->ev_k0[buf], c->s_in));
-            k_parse<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_blob[buf], p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc,
-                                                   g->nse, g->sbr, g->ps, p->lanes, c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf],
-                                                   c->s_sbr[buf], c->s_ps[buf], p->d_consumed[buf]);
+            k_parse<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_scratch, p->scratch_stride, p->d_todo, p->d_blob[buf],
+                                                   p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc, g->nse, g->sbr, g->ps,
+                                                   c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf],
+                                                   p->d_consumed[buf]);
             CK(cudaGetLastError());
             if (!p->timed[buf]) { CK(cudaEventRecord(p->ev_k1[buf], c->s_in)); p->timed[buf] = 1; }
             p->launches++;
@@ -253,15 +277,33 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
         CK(cudaStreamWaitEvent(c->s_out, c->ev_done[buf], 0));
         if (pcm) CK(cudaMemcpyAsync(pcm + pcm_o, c->s_pcm[buf], pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_out));
         if (pcm_f32) CK(cudaMemcpyAsync(pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
-        CK(cudaMemcpyAsync(p->h_consumed + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync(p->h_consumed[slot] + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[buf], c->s_out));
         const double t3 = now();
         t_sync += t1 - t0; t_gather += t2 - t1; t_submit += t3 - t2;
     }
-    const double t4 = now();
-    int r = heaac_b200_wait(c);
-    t_wait = now() - t4;
-    if (!r && consumed) memcpy(consumed, p->h_consumed, (size_t)n_frames * S * sizeof(int));
-    if (dbg) fprintf(stderr, "parser_decode: sync %.2f gather %.2f submit %.2f wait %.2f ms\n", t_sync, t_gather, t_submit, t_wait);
-    return r;
+    p->user_consumed[slot] = consumed; p->user_n[slot] = (int)((size_t)n_frames * S);
+    if (dbg) fprintf(stderr, "parser_submit: sync %.2f gather %.2f submit %.2f ms\n", t_sync, t_gather, t_submit);
+    (void)t_wait;
+    return heaac_b200_ticket(c);
+}
+
+extern "C" int heaac_b200_parser_wait(HeaacGpuParser *p, long long ticket)
+{
+    if (!p) return HEAAC_E_INVAL;
+    int r = heaac_b200_ticket_wait(p->ctx, ticket);
+    if (r) return r;
+    const int slot = (int)(ticket & 7);
+    if (p->ctx->n_tickets - ticket <= 8 && p->user_consumed[slot]) {
+        memcpy(p->user_consumed[slot], p->h_consumed[slot], (size_t)p->user_n[slot] * sizeof(int));
+        p->user_consumed[slot] = nullptr;
+    }
+    return 0;
+}
+
+extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,
+                                        int16_t *pcm, float *pcm_f32, int *consumed)
+{
+    long long t = heaac_b200_parser_submit(p, n_frames, pkt, size, pcm, pcm_f32, consumed);
+    return t < 0 ? (int)t : heaac_b200_parser_wait(p, t);
 }

@@ -231,6 +231,10 @@ int  heaac_b200_sync(HeaacContext *ctx);
 int  heaac_b200_synth_submit(HeaacContext *ctx, const HeaacBatch *batch);
 int  heaac_b200_inputs_consumed(HeaacContext *ctx);
 int  heaac_b200_wait(HeaacContext *ctx);
+/* A ticket marks "all host-pointer work submitted so far": ticket_wait(t) returns once everything submitted before
+ * ticket t was taken has its PCM in host memory, without waiting for later submissions (8 may be outstanding). */
+long long heaac_b200_ticket(HeaacContext *ctx);
+int  heaac_b200_ticket_wait(HeaacContext *ctx, long long ticket);
 /* frames per staging chunk of the host-pointer path (derived from max_frames_per_call) */
 int  heaac_b200_chunk_frames(const HeaacContext *ctx);
 /* cfg.out_slot[] for the reference's output channel order (aac_channel_layout_map, aacdectab.h:74-82;
@@ -293,6 +297,12 @@ void heaac_fe_close(HeaacFrontend *fe);
  * can change layout inside the call, so size them for 16 channels / HEAAC_MAX_ELEMS elements in that case. */
 int  heaac_fe_parse(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                     HeaacSbrElem *sbr, HeaacPsFrame *ps);
+/* heaac_fe_parse computed the way the device front end does it (a stateless pass over the core elements, then a
+ * sequential pass over the SBR / PS payloads); same results, kept callable for tests.  tns must not be NULL. */
+int  heaac_fe_parse_two_phase(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                              HeaacSbrElem *sbr, HeaacPsFrame *ps);
+/* copy sample rate and channel layout (not the stream state) from a front end that has seen a frame */
+int  heaac_fe_copy_layout(HeaacFrontend *dst, const HeaacFrontend *src);
 /* layout of the stream: returns the number of elements and fills the optional outputs; sbr / ps reflect
  * implicit signalling once the first frame has been parsed (aacdec.c:1659-1676) */
 int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,
@@ -327,6 +337,12 @@ int  heaac_dec_open(const HeaacDecoderConfig *cfg, HeaacDecoder **dec);
 void heaac_dec_close(HeaacDecoder *dec);
 int  heaac_dec_decode(HeaacDecoder *dec, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
                       int16_t *pcm, float *pcm_f32, int *consumed);
+/* The same call split for streaming callers: submit() returns as soon as the packets have been taken over (parsed,
+ * or copied for the GPU parser) with a ticket >= 0; pcm / pcm_f32 / consumed are complete once wait(ticket)
+ * returns.  Up to 8 calls may be outstanding, each with its own output buffers.  decode == submit + wait. */
+long long heaac_dec_submit(HeaacDecoder *dec, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                           int16_t *pcm, float *pcm_f32, int *consumed);
+int  heaac_dec_wait(HeaacDecoder *dec, long long ticket);
 /* returns 1 once the first call has configured the decoder (0 before), and fills the optional outputs */
 int  heaac_dec_info(const HeaacDecoder *dec, int *n_out_channels, int *frame_out_len, int *sbr, int *ps,
                     long long *parse_errors, long long *gpu_launches);
@@ -345,6 +361,10 @@ void heaac_b200_parser_destroy(HeaacGpuParser *p);
 int  heaac_b200_parser_reset(HeaacGpuParser *p);
 int  heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
                               int16_t *pcm, float *pcm_f32, int *consumed);
+/* asynchronous form: submit returns a ticket (>= 0) once the packets are copied; outputs are complete after wait */
+long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *pkt_size,
+                                   int16_t *pcm, float *pcm_f32, int *consumed);
+int  heaac_b200_parser_wait(HeaacGpuParser *p, long long ticket);
 long long heaac_b200_parser_launch_count(const HeaacGpuParser *p);
 /* average k_parse duration in ms (CUDA events on its stream) and how many launches that average covers */
 int  heaac_b200_parser_stats(const HeaacGpuParser *p, double *ms_per_launch, long long *timed_launches);

@@ -121,3 +121,28 @@ def test_decoder_survives_a_corrupt_packet():
     for s in (0, 2):
         assert int(np.abs(pcm[:, s].astype(np.int32) - ref_s16).max()) <= 1
     assert int(np.abs(pcm[:4, 1].astype(np.int32) - ref_s16[:4]).max()) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpu_parse", [False, True])
+def test_decoder_pipelined_submit_wait(gpu_parse):
+    """Three calls in flight (heaac_dec_submit / heaac_dec_wait), each with its own output buffers, give the same
+    PCM and consumed[] as one synchronous call."""
+    d = load_golden("heaac_v2_ps")
+    pk = golden_packets(d)
+    S = 6
+    one = open_for(d, S, gpu_parse=gpu_parse)
+    whole, _, cons = one.decode(hb.PacketBatch([[p] * S for p in pk]))
+    one.close()
+    dec = open_for(d, S, gpu_parse=gpu_parse)
+    parts = [pk[0:4], pk[4:8], pk[8:12]]
+    first, _, _ = dec.decode(hb.PacketBatch([[p] * S for p in parts[0]]))      # configures; geometry known from here on
+    outs = [np.zeros((4, S) + whole.shape[2:], np.int16) for _ in parts[1:]]
+    cns = [np.zeros((4, S), np.int32) for _ in parts[1:]]
+    tickets = [dec.submit(hb.PacketBatch([[p] * S for p in part]), o, c) for part, o, c in zip(parts[1:], outs, cns)]
+    for tk in tickets:
+        dec.wait(tk)
+    assert dec.info()["parse_errors"] == 0
+    dec.close()
+    assert np.array_equal(np.concatenate([first] + outs), whole)
+    assert np.array_equal(np.concatenate(cns), cons[4:])

@@ -164,3 +164,31 @@ def test_frontend_adts_framing_equals_raw_with_extradata(name, chan_config):
         assert adts.ncc == raw.ncc and adts.elem_types == raw.elem_types and adts.sr_index == raw.sr_index
         assert not diff_parsed(a, b, raw.ncc, False, False)
     raw.close(); adts.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES + ("bench_heaac_v1_stereo_packets", "bench_heaac_v2_ps_packets"))
+def test_two_phase_parse_equals_one_pass(name):
+    """fe_phase_a + fe_phase_b (how the device front end spreads frames over lanes) == heaac_fe_parse, byte for byte,
+    including streams with PNS (serial fallback), common_window transitions and looped bench fixtures."""
+    import os
+    from common import GOLDEN
+    if name.startswith("bench_"):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        ofs = np.concatenate([[0], np.cumsum(z["pkt_sizes"].ravel())])
+        blob = z["pkt_blob"].tobytes()
+        n = z["pkt_sizes"].shape[1]
+        pk = [blob[ofs[2 * n + i]:ofs[2 * n + i + 1]] for i in range(n)]        # stream 2 of the fixture
+        pk = pk + pk[:16]                                                       # ... looped
+        ed, rate, ch = z["extradata"].tobytes(), int(z["core_rate"]), int(z["channels"])
+    else:
+        d = load_golden(name)
+        pk, ed, rate = golden_packets(d), d["extradata"].tobytes(), int(d["core_rate"])
+        ch = d["pcm_f32"].shape[1] if not d["ps_flag"] else 1
+    a, b = hb.Frontend(ed, rate, ch), hb.Frontend(ed, rate, ch)
+    for t, p in enumerate(pk):
+        x, y = a.parse(p), b.parse(p, two_phase=True)
+        assert x["consumed"] == y["consumed"], (name, t)
+        for k in ("coeffs", "ics", "sbr", "ps"):
+            assert x[k].tobytes() == y[k].tobytes(), "%s frame %d: %s differs" % (name, t, k)
+        assert not diff_parsed(x, y, a.ncc, bool(a.sbr), bool(a.ps)), (name, t)
+    a.close(); b.close()
