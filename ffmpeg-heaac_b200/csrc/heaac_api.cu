@@ -43,36 +43,42 @@ static void prof_end(HeaacContext *c)
 }
 
 /* ------------------------------------------------------------------------------------ */
-/* Persistent: each CTA walks channels gc = blockIdx.x, + gridDim.x, ... and stages the NEXT channel's
- * coefficients into the other half of a double buffer with cp.async while it works on the current one. */
+/* Persistent: the CTAs of the grid claim channels from a device counter (so CTAs that are scheduled late, e.g.
+ * behind a concurrently running parse kernel, do not hold the kernel up) and stage the NEXT claimed channel's
+ * coefficients into the other half of a double buffer with cp.async while working on the current one.
+ * work[0] = next unclaimed channel, work[1] = CTAs finished; the last CTA out resets both for the next launch. */
 __global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
 k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
        const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
-       int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
+       int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, unsigned *work)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_claim[2];
     HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
     float *stage = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [2][1024] */
     float *x = stage + 2048;                         /* [288 history | 1024 new] (+ 64*33 analysis scratch) */
     float *out = x + 288;
     const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
-    int gc = blockIdx.x;
+    if (threadIdx.x == 0) s_claim[0] = (int)atomicAdd(&work[0], 1u);
+    __syncthreads();
+    int gc = s_claim[0];
     if (gc < n_channels)
         heaac_cp_async16(stage + 4 * threadIdx.x, coeffs + (size_t)gc * 1024 + 4 * threadIdx.x);
     heaac_cp_async_commit();
-    for (int it = 0; gc < n_channels; gc += gridDim.x, it++) {
+    for (int it = 0; gc < n_channels; it++) {
         const int s = gc / g.ncc, c = gc - s * g.ncc;
         HeaacChanState *st = chan + gc;
         const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
         float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
-        const int gn = gc + gridDim.x;
+        if (threadIdx.x == 0) s_claim[(it + 1) & 1] = (int)atomicAdd(&work[0], 1u);
+        if (ana)
+            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
+        heaac_cp_async_wait<0>();                    /* this channel's coefficients have landed */
+        __syncthreads();
+        const int gn = s_claim[(it + 1) & 1];
         if (gn < n_channels)
             heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
         heaac_cp_async_commit();
-        if (ana)
-            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
-        heaac_cp_async_wait<1>();                    /* everything but the group just committed has landed */
-        __syncthreads();
         heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
                                           st, out, bias, g.sr_index, T, threadIdx.x);
         if (ana) {
@@ -97,7 +103,9 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
             }
         }
         __syncthreads();                             /* x / tb / stage are reused by the next channel */
+        gc = gn;
     }
+    if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; }
 }
 
 #ifndef HEAAC_SBR_MIN_BLOCKS
@@ -286,6 +294,8 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     }
     size_t S = g->n_streams, T = cfg->max_frames_per_call;
     CKX(cudaMalloc(&c->d_chan, S * g->ncc * sizeof(HeaacChanState)));
+    CKX(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
+    CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
         CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
@@ -343,7 +353,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_W); cudaFree(c->d_X);
+    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
         cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
@@ -394,7 +404,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             const unsigned n_ch = (unsigned)(S * g.ncc);
             const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
             k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(
-                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables);
+                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work);
         }
         prof_end(c);
         c->launches++;

@@ -52,12 +52,18 @@ struct HeaacGpuParser {
     double k_ms;
     long long k_timed;
     long long launches;
+    /* HEAAC_DEBUG_TIMING: device timeline of the last submissions */
+    cudaEvent_t dbg_base, dbg_ev[64][4];
+    int dbg_n, dbg_on;
 };
 
 /* One warp per stream.  Phase A: lane t parses the core elements of the chunk's frame t on a frame-local scratch
  * state (independent of the other frames); phase B: lane 0 walks the frames in order on the stream's persistent
  * state (window history, SBR / PS payloads, packing).  See heaac_fe_core.h, "two-phase parse". */
-__global__ void __launch_bounds__(128)
+#ifndef HEAAC_PARSE_MIN_BLOCKS
+#define HEAAC_PARSE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, HEAAC_PARSE_MIN_BLOCKS)
 k_parse(FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const uint8_t *blob, const uint32_t *off,
         const int *size, int n_frames, int S, int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics,
         HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
@@ -122,9 +128,11 @@ static void parser_free(HeaacGpuParser *p)
     delete p;
 }
 
+extern "C" void heaac_b200_parser_debug_timeline(HeaacGpuParser *p);
 extern "C" void heaac_b200_parser_destroy(HeaacGpuParser *p)
 {
     if (!p) return;
+    heaac_b200_parser_debug_timeline(p);
     cudaSetDevice(p->ctx->cfg.device);
     cudaStreamSynchronize(p->ctx->s_in);
     cudaStreamSynchronize(p->ctx->stream);
@@ -187,6 +195,11 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     }
 #undef CKP
     if (r) { parser_free(p); return r; }
+    if (getenv("HEAAC_DEBUG_TIMING")) {
+        p->dbg_on = 1;
+        cudaEventCreate(&p->dbg_base);
+        for (int i = 0; i < 64; i++) for (int k = 0; k < 4; k++) cudaEventCreate(&p->dbg_ev[i][k]);
+    }
     *out = p;
     r = heaac_b200_parser_reset(p);
     if (r) { parser_free(p); *out = nullptr; }
@@ -253,6 +266,9 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
         CK(cudaMemcpyAsync(p->d_off[buf], p->h_off[buf], np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(p->d_size[buf], p->h_size[buf], np * sizeof(int), cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(p->ev_h2d[buf], c->s_in));
+        const int di = p->dbg_on && p->dbg_n < 64 ? p->dbg_n++ : -1;
+        if (di == 0) CK(cudaEventRecord(p->dbg_base, c->s_in));
+        if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][0], c->s_in));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));      /* d_consumed[buf] drained */
         {
             const int threads = 128, warps_per_cta = threads / 32;
@@ -267,18 +283,21 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
             p->launches++;
         }
         CK(cudaEventRecord(c->ev_in[buf], c->s_in));
+        if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][1], c->s_in));
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
         int r = heaac_launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf],
                                     c->s_pcm[buf], pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
         if (r) return r;
         CK(cudaEventRecord(c->ev_done[buf], c->stream));
+        if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][2], c->stream));
         const size_t pcm_n = np * g->out_len * g->nout, pcm_o = (size_t)f0 * S * g->out_len * g->nout;
         CK(cudaStreamWaitEvent(c->s_out, c->ev_done[buf], 0));
         if (pcm) CK(cudaMemcpyAsync(pcm + pcm_o, c->s_pcm[buf], pcm_n * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_out));
         if (pcm_f32) CK(cudaMemcpyAsync(pcm_f32 + pcm_o, c->s_pcm_f32[buf], pcm_n * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaMemcpyAsync(p->h_consumed[slot] + (size_t)f0 * S, p->d_consumed[buf], np * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[buf], c->s_out));
+        if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][3], c->s_out));
         const double t3 = now();
         t_sync += t1 - t0; t_gather += t2 - t1; t_submit += t3 - t2;
     }
@@ -299,6 +318,18 @@ extern "C" int heaac_b200_parser_wait(HeaacGpuParser *p, long long ticket)
         p->user_consumed[slot] = nullptr;
     }
     return 0;
+}
+
+extern "C" void heaac_b200_parser_debug_timeline(HeaacGpuParser *p)
+{
+    if (!p || !p->dbg_on) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < p->dbg_n; i++) {
+        float t[4] = { 0, 0, 0, 0 };
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], p->dbg_base, p->dbg_ev[i][k]);
+        fprintf(stderr, "chunk %2d: h2d done %7.2f  parse done %7.2f  synth done %7.2f  d2h done %7.2f ms\n", i, t[0], t[1], t[2], t[3]);
+    }
+    p->dbg_n = 0;
 }
 
 extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const uint8_t *const *pkt, const int *size,

@@ -24,6 +24,19 @@ dec = hb.Decoder(S, z["extradata"].tobytes(), int(z["core_rate"]), int(z["channe
 import torch
 PCM_T = torch.empty(T * S * 2048 * 2 * 2, dtype=torch.uint8).pin_memory()
 PCM = PCM_T.numpy().view(np.int16).reshape(T, S, 2048, 2)
+PIPE = os.environ.get("PIPE") == "1"
+if PIPE:
+    PCM2_T = torch.empty(T * S * 2048 * 2 * 2, dtype=torch.uint8).pin_memory()
+    PCM2 = PCM2_T.numpy().view(np.int16).reshape(T, S, 2048, 2)
+    dec.decode(batches[0], pcm_out=PCM, out_shape=(2048, 2))
+    t0 = time.perf_counter(); prev = None
+    for i in range(steps):
+        tk = dec.submit(batches[(i + 1) % len(batches)], [PCM, PCM2][i % 2])
+        if prev is not None: dec.wait(prev)
+        prev = tk
+    dec.wait(prev)
+    print("pipelined: %.2f ms/step" % ((time.perf_counter() - t0) * 1e3 / steps))
+    steps = 0
 for i in range(steps):
     t0 = time.perf_counter()
     pcm, _, cons = dec.decode(batches[i % len(batches)], pcm_out=PCM, out_shape=(2048, 2))
