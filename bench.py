@@ -316,7 +316,7 @@ def main():
 
     # ---- packets leg: bitstreams in host memory -> PCM in host memory through heaac_dec_decode (own host
     #      parser on all host threads + the GPU back end); like-for-like with the reference arm's full decode ----
-    e2e_packets = None
+    e2e_packets = e2e_boundary = e2e_host_parser = None
     fixture = os.path.join(ROOT, "tests", "golden", "bench_%s_packets.npz" % args.workload)
     if not args.no_e2e and os.path.exists(fixture):
         z = np.load(fixture)
@@ -382,6 +382,13 @@ def main():
 
         e2e_packets = packets_run(True)
         e2e_packets["host_parser"] = packets_run(False)
+        # The packets -> PCM call is the whole decode, like the reference arm's: it is the headline `e2e`; the
+        # coefficient-level call at the spectral_to_sample boundary is kept beside it.
+        e2e_boundary, e2e = e2e, dict(e2e_packets)
+        e2e_host_parser = e2e.pop("host_parser")
+        e2e["api"] = "heaac_dec_submit / heaac_dec_wait: packets in host memory -> s16 PCM in host memory"
+        if e2e_boundary is not None:
+            e2e_boundary["api"] = "heaac_b200_synth: parsed coefficients + side info in host memory -> s16 PCM in host memory"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -395,7 +402,8 @@ def main():
         line = {"metric": "decoded audio-seconds per second (batched streams)", "value": value, "unit": "audio-s/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": cfg_desc, "clocks": clocks, "e2e": e2e, "e2e_packets": e2e_packets, "gpu_launches": int(launches), "roofline": roofline,
+                "config": cfg_desc, "clocks": clocks, "e2e": e2e, "e2e_boundary": e2e_boundary,
+                "e2e_host_parser": e2e_host_parser, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "wall_s_timed_region": wall}
         print(json.dumps(line))
     ctx.close()

@@ -65,6 +65,7 @@ class Config(C.Structure):
         ("elem_type", C.c_uint8 * MAX_ELEMS), ("sr_index", C.c_int32), ("sbr", C.c_int32), ("ps", C.c_int32),
         ("add_bias", C.c_float), ("sf_scale", C.c_float), ("max_frames_per_call", C.c_int32),
         ("want_float_out", C.c_int32), ("keep_intermediates", C.c_int32), ("out_slot", C.c_uint8 * 16),
+        ("chunk_frames", C.c_int32),
     ]
 
 

@@ -304,6 +304,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
     c->chunk = (int)((T + 3) / 4);
     if (c->chunk > 8) c->chunk = 8;
+    if (cfg->chunk_frames > 0) c->chunk = cfg->chunk_frames;
     if (getenv("HEAAC_CHUNK_FRAMES")) c->chunk = atoi(getenv("HEAAC_CHUNK_FRAMES"));     /* tuning knob */
     if (c->chunk > 32) c->chunk = 32;
     if ((size_t)c->chunk > T) c->chunk = (int)T;

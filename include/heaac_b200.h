@@ -176,6 +176,7 @@ typedef struct HeaacConfig {
      * aac_channel_layout_map (aacdectab.h:74-82, output_configure aacdec.c:214-272), e.g. 5.1 =
      * {CPE0, SCE0, LFE0, CPE1} while the bitstream order is {SCE0, CPE0, CPE1, LFE0}.  All zero = identity. */
     uint8_t  out_slot[HEAAC_MAX_CHANNELS];
+    int32_t  chunk_frames;          /* frames per staging chunk of the host-pointer path (1..32); 0 = automatic */
 } HeaacConfig;
 
 /* One call = `n_frames` consecutive frames of every stream.  Arrays are frame-major:
