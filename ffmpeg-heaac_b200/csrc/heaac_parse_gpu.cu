@@ -338,3 +338,39 @@ extern "C" int heaac_b200_parser_decode(HeaacGpuParser *p, int n_frames, const u
     long long t = heaac_b200_parser_submit(p, n_frames, pkt, size, pcm, pcm_f32, consumed);
     return t < 0 ? (int)t : heaac_b200_parser_wait(p, t);
 }
+
+/* ---- test hook: the device build of the sbr_reset table chain on arbitrary headers -------------------
+ * params[i] = { start_freq, stop_freq, xover_band, freq_scale, alter_scale, noise_bands, limiter_bands, 0 };
+ * out[i] / rc[i] = what fe_sbr_tables gives for it on the GPU.  Host pointers. */
+__global__ void k_sbr_tables_probe(int core_rate, int n, const uint8_t *params, HeaacSbrElem *out, int *rc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = params + 8 * (size_t)i;
+    HeaacSbrElem t;
+    memset(&t, 0, sizeof(t));
+    rc[i] = fe_sbr_tables(core_rate, p[0], p[1], p[2], p[3], p[4], p[5], p[6], &t);
+    out[i] = t;
+}
+
+extern "C" int heaac_b200_sbr_tables_device(HeaacContext *c, int core_rate, int n, const uint8_t *params,
+                                            HeaacSbrElem *out, int *rc)
+{
+    if (!c || n <= 0 || !params || !out || !rc) return HEAAC_E_INVAL;
+    CK(cudaSetDevice(c->cfg.device));
+    uint8_t *d_p = nullptr; HeaacSbrElem *d_o = nullptr; int *d_r = nullptr;
+    int r = 0;
+#define CKT(call) do { if (!r) r = heaac_cuda_err((call), #call); } while (0)
+    CKT(cudaMalloc(&d_p, 8 * (size_t)n));
+    CKT(cudaMalloc(&d_o, sizeof(HeaacSbrElem) * (size_t)n));
+    CKT(cudaMalloc(&d_r, sizeof(int) * (size_t)n));
+    CKT(cudaMemcpy(d_p, params, 8 * (size_t)n, cudaMemcpyHostToDevice));
+    if (!r) k_sbr_tables_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(core_rate, n, d_p, d_o, d_r);
+    CKT(cudaGetLastError());
+    CKT(cudaStreamSynchronize(c->stream));
+    CKT(cudaMemcpy(out, d_o, sizeof(HeaacSbrElem) * (size_t)n, cudaMemcpyDeviceToHost));
+    CKT(cudaMemcpy(rc, d_r, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+#undef CKT
+    cudaFree(d_p); cudaFree(d_o); cudaFree(d_r);
+    return r;
+}

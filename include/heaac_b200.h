@@ -370,6 +370,12 @@ long long heaac_b200_parser_launch_count(const HeaacGpuParser *p);
 /* average k_parse duration in ms (CUDA events on its stream) and how many launches that average covers */
 int  heaac_b200_parser_stats(const HeaacGpuParser *p, double *ms_per_launch, long long *timed_launches);
 
+/* test hook: heaac_b200_sbr_tables evaluated by the DEVICE build of the same source for n headers at once;
+ * params[i] = { start_freq, stop_freq, xover_band, freq_scale, alter_scale, noise_bands, limiter_bands, 0 }
+ * (host pointers).  tests hold it to the host result over the whole header space. */
+int  heaac_b200_sbr_tables_device(HeaacContext *ctx, int core_sample_rate, int n, const uint8_t *params,
+                                  HeaacSbrElem *out, int *rc);
+
 /* ---- batch-of-one shims with the reference's own transform signatures -----------------
  * ff_mdct_init / ff_imdct_half / ff_mdct_end (fft.h:44-48,166-186; mdct.c:61,124,226). */
 typedef struct HeaacMdct HeaacMdct;
