@@ -39,6 +39,12 @@ KERNEL_ALG_BYTES = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
+# (profiles/r01_ncu_summary.md, prof_r1d): keyed by (kernel, workload, streams per GPU).
+NCU_DRAM_BYTES_PER_LAUNCH = {("k_sbr", "heaac_v1_stereo", 1024): 33.671680e6 + 6.095872e6,
+                             ("k_core", "heaac_v1_stereo", 1024): 15.283712e6 + 0.025856e6}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -56,6 +62,22 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        try:                                             # NVML: sub-millisecond queries, many samples per timed region
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self._halt.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for b, n in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+                self._halt.wait(0.005)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -162,7 +184,7 @@ def cpu_reference_run(workload, seconds_budget, n_threads=None, n_streams=None, 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="heaac_v1_stereo")
@@ -276,7 +298,7 @@ def main():
     achieved = per_launch_units * dom_bytes / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
     path_achieved = units * unit_bytes * T * args.steps / (ms_max * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind, "kernel_share_of_step": kern[dom]["ms_per_launch"] / tot,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((dom, args.workload, S)), "peak_kind": peak_kind, "kernel_share_of_step": kern[dom]["ms_per_launch"] / tot,
                 "kernels": kern,
                 "path": {"achieved": path_achieved, "frac": path_achieved / peak, "alg_bytes_per_unit": unit_bytes, "unit_name": unit_name}}
 
