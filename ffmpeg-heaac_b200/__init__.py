@@ -39,6 +39,7 @@ EXPORTS = [
     "heaac_fe_parse_two_phase", "heaac_fe_copy_layout",
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
+    "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
 
@@ -107,6 +108,10 @@ def lib():
         L.heaac_b200_ticket.restype = C.c_longlong
         L.heaac_b200_ticket_wait.argtypes = [C.c_void_p, C.c_longlong]
         L.heaac_b200_sbr_tables_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.heaac_adts_write_header.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.heaac_adts_parse_header.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.heaac_adts_split.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.heaac_esds_find_asc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
         L.heaac_dec_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_longlong)] * 2
         L.heaac_dec_parse_kernel_ms.argtypes = [C.c_void_p]
         L.heaac_dec_parse_kernel_ms.restype = C.c_double

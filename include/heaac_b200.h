@@ -309,6 +309,17 @@ int  heaac_fe_copy_layout(HeaacFrontend *dst, const HeaacFrontend *src);
 int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,
                    uint8_t elem_type[HEAAC_MAX_ELEMS]);
 
+/* ---- containers (host C): ADTS framing and the MP4 `esds` descriptor ------------------------------------
+ * adts_write_header: 7-byte header (no CRC) for one raw_data_block, as adts_write_frame_header (adtsenc.c:84-147);
+ * adts_parse_header: ff_aac_parse_header (aac_parser.c:29-67); returns the header size (7 / 9) or < 0;
+ * adts_split: offsets and sizes of back-to-back ADTS frames in a buffer (a .aac file), returns the count;
+ * esds_find_asc: ES_Descriptor -> DecoderConfigDescriptor -> DecoderSpecificInfo (isom.c ff_mp4_read_descr*): the
+ * AudioSpecificConfig to pass as extradata. */
+int  heaac_adts_write_header(uint8_t out[7], int sr_index, int chan_config, int payload_bytes);
+int  heaac_adts_parse_header(const uint8_t *buf, int size, int *sr_index, int *chan_config, int *frame_bytes, int *n_blocks);
+int  heaac_adts_split(const uint8_t *buf, int size, int *offset, int *frame_size, int max_frames);
+int  heaac_esds_find_asc(const uint8_t *esds, int size, const uint8_t **asc, int *asc_size);
+
 /* ---- batched decoder: packets -> PCM ------------------------------------------------------------
  * S front ends + one back end behind the reference's AVCodec entry points (aacdec.c:2128-2142):
  *   heaac_dec_open   ~ init   (aac_decode_init,  aacdec.c:537-598)

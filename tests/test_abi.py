@@ -12,7 +12,7 @@ from common import ROOT, abi
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "heaac_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(heaac_(?:b200|fe|dec)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(heaac_(?:b200|fe|dec|adts|esds)_\w+)\s*\(", src)))
 
 
 def test_header_declares_the_expected_surface():
