@@ -39,7 +39,7 @@ EXPORTS = [
     "heaac_fe_parse_two_phase", "heaac_fe_copy_layout",
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
-    "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
+    "heaac_fe_sbr_downsampled", "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
         L.heaac_fe_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.heaac_fe_parse_two_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.heaac_fe_copy_layout.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_fe_sbr_downsampled.argtypes = [C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.heaac_b200_inputs_consumed.argtypes = [C.c_void_p]
@@ -288,6 +289,7 @@ class Frontend:
         et = (C.c_uint8 * 8)()
         n = lib().heaac_fe_info(self.h, *[C.byref(x) for x in v], et)
         self.ncc, self.nse, self.sbr, self.ps, self.sr_index = [x.value for x in v]
+        self.downsampled = bool(lib().heaac_fe_sbr_downsampled(self.h))
         self.elem_types = [int(et[i]) for i in range(max(n, 0))]
 
     def parse(self, pkt, two_phase=False):

@@ -65,7 +65,7 @@ class Config(C.Structure):
         ("elem_type", C.c_uint8 * MAX_ELEMS), ("sr_index", C.c_int32), ("sbr", C.c_int32), ("ps", C.c_int32),
         ("add_bias", C.c_float), ("sf_scale", C.c_float), ("max_frames_per_call", C.c_int32),
         ("want_float_out", C.c_int32), ("keep_intermediates", C.c_int32), ("out_slot", C.c_uint8 * 16),
-        ("chunk_frames", C.c_int32),
+        ("chunk_frames", C.c_int32), ("sbr_downsampled", C.c_int32),
     ]
 
 
@@ -119,7 +119,7 @@ def reference_out_slots(elem_types):
 
 
 def make_config(n_streams, elem_types, sr_index, sbr=False, ps=False, bias_mode=False, device=0,
-                max_frames=1, want_float=True, keep_intermediates=False, out_slots="reference"):
+                max_frames=1, want_float=True, keep_intermediates=False, out_slots="reference", downsampled=False):
     """Build a HeaacConfig.  bias_mode selects the reference's C 'bias' scaling (aacdec.c:573-576),
     otherwise the s16-unit scaling of its SIMD branch (aacdec.c:577-581)."""
     c = Config()
@@ -131,6 +131,7 @@ def make_config(n_streams, elem_types, sr_index, sbr=False, ps=False, bias_mode=
         c.elem_type[i] = t
     c.sr_index = sr_index
     c.sbr = int(bool(sbr))
+    c.sbr_downsampled = int(bool(downsampled) and bool(sbr))
     c.ps = int(bool(ps))
     if bias_mode:
         c.add_bias = 385.0

@@ -149,10 +149,16 @@ k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
-    heaac_synth_stream<128>(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
-                       pcm ? pcm + (size_t)s * 2048 * g.nout : nullptr,
-                       pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 2048 : nullptr,
-                       qmf_scale, g.add_bias, T, threadIdx.x);
+    if (g.ds)
+        heaac_synth_stream_ds<128>(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.nout, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
+                                   pcm ? pcm + (size_t)s * 1024 * g.nout : nullptr,
+                                   pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 1024 : nullptr,
+                                   qmf_scale, g.add_bias, T, threadIdx.x);
+    else
+        heaac_synth_stream<128>(sm, X + go * HEAAC_X_FLOATS, synth + go, nch, g.nout, g.out_slot[c0], g.out_slot[c0 + (nch > 1)],
+                                pcm ? pcm + (size_t)s * 2048 * g.nout : nullptr,
+                                pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 2048 : nullptr,
+                                qmf_scale, g.add_bias, T, threadIdx.x);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -200,7 +206,8 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
     g->ncc = ch;
     g->nse = se;
     g->nout = cfg->ps ? 2 : ch;
-    g->out_len = cfg->sbr ? 2048 : 1024;
+    g->ds = cfg->sbr && cfg->sbr_downsampled;
+    g->out_len = cfg->sbr && !g->ds ? 2048 : 1024;
     g->sr_index = cfg->sr_index;
     g->sbr = cfg->sbr != 0;
     g->ps = cfg->ps != 0;

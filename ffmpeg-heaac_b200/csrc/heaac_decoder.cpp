@@ -176,6 +176,7 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     cfg.sr_index = d->sr_index;
     cfg.sbr = d->sbr;
     cfg.ps = d->ps;
+    cfg.sbr_downsampled = heaac_fe_sbr_downsampled(probe);
     cfg.add_bias = 0.0f;
     cfg.sf_scale = -1.0f / 1024.0f;                   /* s16-unit convention, aacdec.c:577-581 */
     cfg.max_frames_per_call = d->cfg.max_frames_per_call;

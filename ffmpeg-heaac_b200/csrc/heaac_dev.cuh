@@ -135,6 +135,7 @@ struct HeaacPsState {
 /* compact per-launch geometry */
 struct HeaacGeom {
     int n_streams, ncc, nout, nse, out_len;
+    int ds;                          /* downsampled SBR synthesis (32 bands) */
     int sr_index, sbr, ps;
     float add_bias, sf_scale;
     int n_elems;

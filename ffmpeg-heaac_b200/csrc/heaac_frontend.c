@@ -201,6 +201,13 @@ int heaac_fe_copy_layout(FE *dst, const FE *src)
     return src->chan_config ? set_layout(dst, src->chan_config) : 0;
 }
 
+/* 1 when the stream asks for downsampled SBR: explicitly signalled extension rate below twice the core rate
+ * (ff_sbr_apply: downsampled = m4ac.ext_sample_rate < sbr->sample_rate, aacsbr.c:1719) */
+int heaac_fe_sbr_downsampled(const FE *fe)
+{
+    return fe && fe->sbr == 1 && fe->ext_sample_rate && fe->ext_sample_rate < 2 * fe->sample_rate;
+}
+
 /* the state block of an opened front end, for the device front end to replicate per stream */
 const void *heaac_fe_state_blob(const FE *fe) { return fe; }
 

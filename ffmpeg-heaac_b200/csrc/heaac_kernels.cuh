@@ -712,13 +712,13 @@ struct HeaacSynthSmem {
 };
 
 template <int NT>
-HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nout,
-                                  int out_slot0, int out_slot1, int16_t *pcm, float *pcm_f32, float scale, float bias,
+HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nch,
+                                  int nout, int out_slot0, int out_slot1, int16_t *pcm, float *pcm_f32, float scale, float bias,
                                   const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
     constexpr int nt = NT;
-    const int nthr = 64 * nout;
-    for (int w = tid; w < nout * 1152; w += nt) {          /* history -> blocks 32..40, asynchronously: first needed in phase 3 */
+    const int nthr = 64 * nch;                             /* nch = channels of this element, nout = of the stream */
+    for (int w = tid; w < nch * 1152; w += nt) {           /* history -> blocks 32..40, asynchronously: first needed in phase 3 */
         int c = w / 1152, r = w - c * 1152;
         heaac_cp_async4(&sm->ch[c][(32 + (r >> 7)) * HEAAC_V_STRIDE + (r & 127)], &st[c].v[r]);
     }
@@ -760,7 +760,7 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
     const int scale_and_bias = scale != 1.0f || bias != 0.0f;
     const int bias_mode = bias != 0.0f;
     for (int t = tid; t < nthr; t += nt) {
-        const int c = nout == 2 ? (t & 1) : 0, n = nout == 2 ? (t >> 1) : t;
+        const int c = nch == 2 ? (t & 1) : 0, n = nch == 2 ? (t >> 1) : t;
         float w[10];
         HEAAC_UNROLL
         for (int j = 0; j < 10; j++) w[j] = T->qmf_us[64 * j + n];
@@ -778,9 +778,61 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
             if (pcm_f32) pcm_f32[(size_t)slot * 2048 + o] = acc;
         }
     }
-    for (int w = tid; w < nout * 1152; w += nt) {          /* newest 9 blocks become the next frame's history */
+    for (int w = tid; w < nch * 1152; w += nt) {           /* newest 9 blocks become the next frame's history */
         int c = w / 1152, r = w - c * 1152;
         st[c].v[r] = sm->ch[c][(r >> 7) * HEAAC_V_STRIDE + (r & 127)];
+    }
+    HEAAC_SYNC();
+}
+
+
+/* Downsampled synthesis bank (div = 1, aacsbr.c:1194-1203): one N=128 half-IMDCT per slot on (-Re X[0..31], Im X[31..0]),
+ * 64 new v values per slot, 32 output samples per slot through the decimated prototype (sbr_qmf_window_ds[n] =
+ * us[2n]); history = 9 blocks of 64.  Same shared-memory rows as the 64-band bank, half of each row used. */
+template <int NT>
+HEAAC_DEV void heaac_synth_stream_ds(HeaacSynthSmem *sm, const float *HEAAC_RESTRICT X, HeaacSynthState *st, int nch,
+                                     int nout, int out_slot0, int out_slot1, int16_t *pcm, float *pcm_f32, float scale,
+                                     float bias, const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
+{
+    constexpr int nt = NT;
+    const int nthr = 32 * nch;
+    for (int w = tid; w < nch * 576; w += nt) {
+        int c = w / 576, r = w - c * 576;
+        sm->ch[c][(32 + (r >> 6)) * HEAAC_V_STRIDE + (r & 63)] = st[c].v[r];
+    }
+    for (int t = tid; t < nthr; t += nt) {
+        const int c = t >> 5, i = t & 31;
+        const float *x0 = X + (size_t)c * HEAAC_X_FLOATS + i, *x1 = x0 + HEAAC_X_PLANE;
+        float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;
+        heaac_imdct128_reg<HEAAC_MDCT_SYN>(
+            [&](int j) { return j < 32 ? -x0[j * HEAAC_XS] : x1[(63 - j) * HEAAC_XS]; },
+            [&](int j, float b) { if (j & 1) v[(63 - j) >> 1] = b; else v[63 - ((62 - j) >> 1)] = -b; });
+    }
+    HEAAC_SYNC();
+    const int scale_and_bias = scale != 1.0f || bias != 0.0f;
+    const int bias_mode = bias != 0.0f;
+    for (int t = tid; t < nthr; t += nt) {
+        const int c = nch == 2 ? (t & 1) : 0, n = nch == 2 ? (t >> 1) : t;
+        float w[10];
+        HEAAC_UNROLL
+        for (int j = 0; j < 10; j++) w[j] = T->qmf_us[2 * (32 * j + n)];
+        const float *vb = sm->ch[c] + n;
+        const int slot = c ? out_slot1 : out_slot0;
+        for (int i = 0; i < 32; i++) {
+            const float *v = vb + (31 - i) * HEAAC_V_STRIDE;
+            float acc = v[0] * w[0] + 0.0f;
+            HEAAC_UNROLL
+            for (int j = 1; j < 10; j++)
+                acc = v[j * HEAAC_V_STRIDE + ((j & 1) ? 32 : 0)] * w[j] + acc;
+            if (scale_and_bias) acc = acc * scale + bias;
+            const int o = i * 32 + n;
+            if (pcm)     pcm[(size_t)o * nout + slot] = heaac_to_s16(acc, bias_mode);
+            if (pcm_f32) pcm_f32[(size_t)slot * 1024 + o] = acc;
+        }
+    }
+    for (int w = tid; w < nch * 576; w += nt) {            /* newest 9 blocks of 64 become the next frame's history */
+        int c = w / 576, r = w - c * 576;
+        st[c].v[r] = sm->ch[c][(r >> 6) * HEAAC_V_STRIDE + (r & 63)];
     }
     HEAAC_SYNC();
 }

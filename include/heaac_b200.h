@@ -177,6 +177,8 @@ typedef struct HeaacConfig {
      * {CPE0, SCE0, LFE0, CPE1} while the bitstream order is {SCE0, CPE0, CPE1, LFE0}.  All zero = identity. */
     uint8_t  out_slot[HEAAC_MAX_CHANNELS];
     int32_t  chunk_frames;          /* frames per staging chunk of the host-pointer path (1..32); 0 = automatic */
+    int32_t  sbr_downsampled;       /* 1: downsampled SBR (m4ac.ext_sample_rate < 2 x core rate, aacsbr.c:1719): 32-band
+                                     * synthesis QMF, 1024 output samples per frame at the core rate */
 } HeaacConfig;
 
 /* One call = `n_frames` consecutive frames of every stream.  Arrays are frame-major:
@@ -302,6 +304,8 @@ int  heaac_fe_parse(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coef
  * sequential pass over the SBR / PS payloads); same results, kept callable for tests.  tns must not be NULL. */
 int  heaac_fe_parse_two_phase(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                               HeaacSbrElem *sbr, HeaacPsFrame *ps);
+/* 1 if the stream signals downsampled SBR (extension rate below twice the core rate): HeaacConfig.sbr_downsampled */
+int  heaac_fe_sbr_downsampled(const HeaacFrontend *fe);
 /* copy sample rate and channel layout (not the stream state) from a front end that has seen a frame */
 int  heaac_fe_copy_layout(HeaacFrontend *dst, const HeaacFrontend *src);
 /* layout of the stream: returns the number of elements and fills the optional outputs; sbr / ps reflect

@@ -66,7 +66,7 @@ class Oracle:
         self.ncc = abi.n_core_channels(et)
         self.nse = abi.n_sbr_elems(et)
         self.nout = 2 if cfg.ps else self.ncc
-        self.out_len = 2048 if cfg.sbr else 1024
+        self.out_len = 2048 if cfg.sbr and not cfg.sbr_downsampled else 1024
 
     def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, n_threads=1, want_float=True):
         """coeffs [T,S,ncc,1024] f32; ics [T,S,ncc]; tns [T,S,ncc]; sbr [T,S,nse]; ps [T,S].

@@ -8,7 +8,7 @@ import pyoracle
 abi = pyref.abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ("lc_stereo_44k", "lc_51_48k", "lc_51_tns_rich", "heaac_v1_stereo", "heaac_v2_ps")
+GOLDEN_CASES = ("lc_stereo_44k", "lc_51_48k", "lc_51_tns_rich", "heaac_v1_stereo", "heaac_v2_ps", "heaac_v1_downsampled")
 
 # north_star tolerance: max abs error <= 1e-5 of full scale on float PCM, or +-1 LSB after s16 conversion
 TOL_FS = 1e-5
@@ -25,7 +25,7 @@ def golden_config(d, n_streams=1, bias_mode=False, max_frames=None):
     et = [int(x) for x in d["elem_types"]]
     T = d["coeffs"].shape[0]
     return abi.make_config(n_streams, et, int(d["sr_index"]), sbr=bool(d["sbr_flag"]), ps=bool(d["ps_flag"]),
-                           bias_mode=bias_mode, max_frames=max_frames or T)
+                           bias_mode=bias_mode, max_frames=max_frames or T, downsampled=bool(d.get("downsampled", 0)))
 
 
 def golden_args(d, n_streams=1, bias_mode=False):

@@ -39,7 +39,7 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
         }
         if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
     }
-    g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch; g->out_len = cfg->sbr ? 2048 : 1024;
+    g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch; g->ds = cfg->sbr && cfg->sbr_downsampled; g->out_len = cfg->sbr && !g->ds ? 2048 : 1024;
     g->sr_index = cfg->sr_index; g->sbr = cfg->sbr != 0; g->ps = cfg->ps != 0;
     g->add_bias = cfg->add_bias; g->sf_scale = cfg->sf_scale;
     int any = 0;
@@ -135,10 +135,16 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
                     int no = g.ps ? 2 : nch;
                     size_t go = s * g.nout + o;
                     memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));
-                    heaac_synth_stream<1>(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no,
-                                       g.out_slot[o], g.out_slot[o + (no > 1)],
-                                       pc ? pc + s * 2048 * g.nout : nullptr, pf ? pf + s * g.nout * 2048 : nullptr,
-                                       qmf_scale, g.add_bias, c->T, 0);
+                    if (g.ds)
+                        heaac_synth_stream_ds<1>(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no, g.nout,
+                                                 g.out_slot[o], g.out_slot[o + (no > 1)],
+                                                 pc ? pc + s * 1024 * g.nout : nullptr, pf ? pf + s * g.nout * 1024 : nullptr,
+                                                 qmf_scale, g.add_bias, c->T, 0);
+                    else
+                        heaac_synth_stream<1>(c->sm_synth, c->X + go * HEAAC_X_FLOATS, c->synth + go, no, g.nout,
+                                              g.out_slot[o], g.out_slot[o + (no > 1)],
+                                              pc ? pc + s * 2048 * g.nout : nullptr, pf ? pf + s * g.nout * 2048 : nullptr,
+                                              qmf_scale, g.add_bias, c->T, 0);
                 }
                 o += nch;
             }

@@ -45,7 +45,7 @@ class Emu:
         et = [cfg.elem_type[i] for i in range(cfg.n_elems)]
         self.ncc = abi.n_core_channels(et)
         self.nout = 2 if cfg.ps else self.ncc
-        self.out_len = 2048 if cfg.sbr else 1024
+        self.out_len = 2048 if cfg.sbr and not cfg.sbr_downsampled else 1024
         self.S = cfg.n_streams
 
     def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=True):

@@ -50,6 +50,7 @@ def capture(pkts, ed, rate, channels, layout):
     out["pkt_sizes"] = np.asarray([len(p) for p in pkts], np.int32)
     out["pkt_blob"] = np.frombuffer(b"".join(pkts), np.uint8)
     out["core_rate"] = np.int32(rate)
+    out["downsampled"] = np.int32(fr[0]["pcm_f32"].shape[-1] == 1024 and df.sbr == 1)
     df.close(); db.close()
     return out
 
@@ -66,6 +67,9 @@ def main():
     pkts, ed, w = lc_writer.make_lc_stream(4004, 8, "5.1", 3)
     cases["lc_51_tns_rich"] = (pkts, ed, 48000, 6, "5.1")
     print("lc_51_tns_rich content:", w.stats)
+    # downsampled SBR: hierarchical explicit signalling (AOT 5) with the extension rate equal to the core rate
+    pkts, ed, info = hs.make_stream(31, 8, stereo=True, ps=False)
+    cases["heaac_v1_downsampled"] = (pkts, hs.asc_explicit(6, 2, 6), 24000, 2, "stereo")
     for name, c in cases.items():
         d = capture(*c)
         path = os.path.join(HERE, name + ".npz")

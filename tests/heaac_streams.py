@@ -535,6 +535,14 @@ def make_stream(seed, n_frames, stereo=True, ps=False, core_rate=24000, bitrate_
     return pkts, extradata, {"tables": gen.tables, "channels": ch, "core_rate": core_rate}
 
 
+def asc_explicit(core_idx, chan_config, ext_idx, ps=False):
+    """AudioSpecificConfig with hierarchical explicit SBR (AOT 5) / PS (AOT 29) signalling (mpeg4audio.c:77-130):
+    ext_idx == core_idx asks for downsampled SBR."""
+    bits = "{:05b}{:04b}{:04b}{:04b}{:05b}000".format(29 if ps else 5, core_idx, chan_config, ext_idx, 2)
+    bits += "0" * (-len(bits) % 8)
+    return int(bits, 2).to_bytes(len(bits) // 8, "big")
+
+
 def decode_with_reference(pkts, extradata, core_rate, channels, float_mode=True):
     """Decode with the unmodified reference; returns list of per-frame capture dicts and the decoder."""
     layout = "stereo" if channels == 2 else "mono"

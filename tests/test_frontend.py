@@ -42,7 +42,8 @@ def test_frontend_plus_oracle_reproduces_reference_pcm(name):
     d = load_golden(name)
     fe, frames, n_ch = parse_golden(d)
     st = lambda k: np.ascontiguousarray(np.stack([f[k] for f in frames])[:, None])
-    cfg = abi.make_config(1, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames))
+    cfg = abi.make_config(1, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames),
+                          downsampled=fe.downsampled)
     orc = pyoracle.Oracle(cfg)
     pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), st("sbr") if fe.sbr else None,
                          st("ps")[:, :, 0] if fe.ps else None)
@@ -134,7 +135,8 @@ def test_frontend_plus_cuda_reproduces_reference_pcm(name):
     fe, frames, n_ch = parse_golden(d)
     S = 2
     st = lambda k: np.ascontiguousarray(np.repeat(np.stack([f[k] for f in frames])[:, None], S, axis=1))
-    cfg = abi.make_config(S, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames))
+    cfg = abi.make_config(S, fe.elem_types, fe.sr_index, sbr=bool(fe.sbr), ps=bool(fe.ps), max_frames=len(frames),
+                          downsampled=fe.downsampled)
     ctx = hb.Context(cfg)
     pcm, f32 = ctx.synth(st("coeffs"), st("ics"), st("tns"), st("sbr") if fe.sbr else None,
                          st("ps")[:, :, 0] if fe.ps else None, want_float=True)
