@@ -138,7 +138,10 @@ k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__res
     heaac_ps_stream<HEAAC_THREADS>(sm, ps + s, pstate + s, XL, XR, (int)e->kx[1] + (int)e->m[1], T, threadIdx.x);
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef HEAAC_SYNTH_MIN_BLOCKS
+#define HEAAC_SYNTH_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, HEAAC_SYNTH_MIN_BLOCKS)
 k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
         int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {

@@ -723,35 +723,34 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
         heaac_cp_async4(&sm->ch[c][(32 + (r >> 7)) * HEAAC_V_STRIDE + (r & 127)], &st[c].v[r]);
     }
     heaac_cp_async_commit();
-    /* ---- phase 1: 64 transforms per channel ---- */
-    for (int t = tid; t < nthr; t += nt) {
+    /* ---- phase 1: 64 transforms per channel, all at once: the threads of the real plane park b0 in the slot's own
+     *      v block, those of the imaginary plane keep b1 in registers across the barrier; phase 2: v = (-b0 + b1, b0 + b1) ---- */
+    for (int t0 = 0; t0 < nthr; t0 += nt) {             /* trip count uniform over the CTA: the barrier inside is safe */
+        const int t = t0 + tid;
+        const bool act = t < nthr;
         const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
         const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
-        float *row = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;      /* b0 is parked in the slot's own v block */
-        if (plane == 0) {
+        float *v = sm->ch[act ? c : 0] + (31 - i) * HEAAC_V_STRIDE;
+        float b1[64];
+        if (act && plane == 0) {
             heaac_imdct128_reg<HEAAC_MDCT_SYN>(
                 [&](int j) { return x[j * HEAAC_XS]; },
-                [&](int j, float v) { row[j] = v; });
+                [&](int j, float b) { v[j] = b; });
+        } else if (act) {
+            heaac_imdct128_reg<HEAAC_MDCT_SYN>(
+                [&](int j) { float xv = x[j * HEAAC_XS]; return (j & 1) ? -xv : xv; },     /* aacsbr.c:1205-1207 */
+                [&](int j, float b) { b1[j] = b; });
         }
-    }
-    HEAAC_SYNC();
-    /* ---- phase 1b + 2: im-plane transform, then v = (-b0 + b1, b0 + b1) ---- */
-    for (int t = tid; t < nthr; t += nt) {
-        const int c = t >> 6, plane = (t >> 5) & 1, i = t & 31;
-        if (plane == 0) continue;
-        const float *x = X + (size_t)c * HEAAC_X_FLOATS + plane * HEAAC_X_PLANE + i;
-        float b1[64];
-        heaac_imdct128_reg<HEAAC_MDCT_SYN>(
-            [&](int j) { float v = x[j * HEAAC_XS]; return (j & 1) ? -v : v; },     /* aacsbr.c:1205-1207 */
-            [&](int j, float v) { b1[j] = v; });
-        float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;       /* holds b0[0..63]; becomes v[0..127] in place */
-        HEAAC_UNROLL
-        for (int n = 0; n < 32; n++) {
-            const float p1 = v[63 - n], p2 = v[n], q1 = b1[n], q2 = b1[63 - n];
-            v[n]       = -p1 + q1;
-            v[127 - n] =  p1 + q1;
-            v[63 - n]  = -p2 + q2;
-            v[64 + n]  =  p2 + q2;
+        HEAAC_SYNC();
+        if (act && plane == 1) {
+            HEAAC_UNROLL
+            for (int n = 0; n < 32; n++) {              /* v holds b0[0..63]; becomes v[0..127] in place */
+                const float p1 = v[63 - n], p2 = v[n], q1 = b1[n], q2 = b1[63 - n];
+                v[n]       = -p1 + q1;
+                v[127 - n] =  p1 + q1;
+                v[63 - n]  = -p2 + q2;
+                v[64 + n]  =  p2 + q2;
+            }
         }
     }
     heaac_cp_async_wait<0>();
