@@ -928,37 +928,58 @@ FE_FN void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cp
 /* ---------------------------------------------------------------- frame */
 /* HeaacSbrElem: 140 bytes of header + tables, then ch[2] of 592 bytes each (env_q at +88); HeaacPsFrame: 20 bytes of
  * header, then the four parameter arrays back to back.  Everything is 4-byte aligned, so the copies go by words. */
-FE_FN void pack_sbr(const FeSbr *s, HeaacSbrElem *o)
+/* The packers take (lane, nl): the word copies are strided over nl cooperating lanes, the scalar fields are written by
+ * lane 0.  The host passes (0, 1); the device front end calls them with all 32 lanes of the stream's warp. */
+FE_INL void fe_copy32_l(void *dst, const void *src, int nwords, int lane, int nl)
 {
-    fe_copy32(o, &s->t, 140 / 4);
-    o->start = s->start; o->reset = s->reset; o->bs_coupling = s->coupling;
-    o->bs_limiter_gains = s->limiter_gains; o->bs_interpol_freq = s->interpol_freq; o->bs_smoothing_mode = s->smoothing_mode;
+    uint32_t *d = (uint32_t *)dst;
+    const uint32_t *q = (const uint32_t *)src;
+    for (int i = lane; i < nwords; i += nl) d[i] = q[i];
+}
+FE_FN void pack_sbr_l(const FeSbr *s, HeaacSbrElem *o, int lane, int nl)
+{
+    fe_copy32_l(&o->n[0], &s->t.n[0], (140 - 8) / 4, lane, nl);      /* tables; the first 8 bytes are the flags below */
+    if (lane == 0) {
+        o->start = s->start; o->reset = s->reset; o->bs_coupling = s->coupling;
+        o->bs_limiter_gains = s->limiter_gains; o->bs_interpol_freq = s->interpol_freq; o->bs_smoothing_mode = s->smoothing_mode;
+        o->num_patches = s->t.num_patches; o->n_q = s->t.n_q;
+    }
     for (int c = 0; c < 2; c++) {
         const FeSbrCh *d = &s->ch[c];
         HeaacSbrChan *oc = &o->ch[c];
-        fe_zero32(oc, 88 / 4);
-        oc->bs_num_env = d->num_env; oc->bs_num_noise = d->num_noise; oc->bs_amp_res = d->amp_res;
-        oc->bs_add_harmonic_flag = d->add_harmonic_flag;
-        oc->e_a[0] = d->e_a[0]; oc->e_a[1] = d->e_a[1]; oc->t_env_num_env_old = d->t_env_num_env_old;
-        for (int i = 0; i < 7; i++) oc->bs_freq_res[i] = d->freq_res[i];
-        for (int i = 0; i < 8; i++) oc->t_env[i] = d->t_env[i];
-        for (int i = 0; i < 3; i++) oc->t_q[i] = d->t_q[i];
-        for (int i = 0; i < 5; i++) { oc->bs_invf_mode[0][i] = d->invf[0][i]; oc->bs_invf_mode[1][i] = d->invf[1][i]; }
-        if (d->add_harmonic_flag) fe_copy32(oc->bs_add_harmonic, d->add_harmonic, 48 / 4);
-        fe_copy32(oc->env_q, d->env[1], 5 * 48 * 2 / 4);
-        for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = d->noise[e + 1][k];
-        fe_zero32(oc->reserved2, 1);
+        if (d->add_harmonic_flag) fe_copy32_l(oc->bs_add_harmonic, d->add_harmonic, 48 / 4, lane, nl);
+        else for (int i = lane; i < 48 / 4; i += nl) ((uint32_t *)oc->bs_add_harmonic)[i] = 0;
+        fe_copy32_l(oc->env_q, d->env[1], 5 * 48 * 2 / 4, lane, nl);
+        if (lane == 0) {
+            fe_zero32(oc, 40 / 4);                                     /* everything before bs_add_harmonic */
+            oc->bs_num_env = d->num_env; oc->bs_num_noise = d->num_noise; oc->bs_amp_res = d->amp_res;
+            oc->bs_add_harmonic_flag = d->add_harmonic_flag;
+            oc->e_a[0] = d->e_a[0]; oc->e_a[1] = d->e_a[1]; oc->t_env_num_env_old = d->t_env_num_env_old;
+            for (int i = 0; i < 7; i++) oc->bs_freq_res[i] = d->freq_res[i];
+            for (int i = 0; i < 8; i++) oc->t_env[i] = d->t_env[i];
+            for (int i = 0; i < 3; i++) oc->t_q[i] = d->t_q[i];
+            for (int i = 0; i < 5; i++) { oc->bs_invf_mode[0][i] = d->invf[0][i]; oc->bs_invf_mode[1][i] = d->invf[1][i]; }
+            for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = d->noise[e + 1][k];
+            fe_zero32(oc->reserved2, 1);
+        }
     }
 }
-
-FE_FN void pack_ps(const FePs *p, HeaacPsFrame *o)
+FE_FN void pack_ps_l(const FePs *p, HeaacPsFrame *o, int lane, int nl)
 {
-    fe_zero32(o, 20 / 4);
-    o->start = p->start; o->num_env = p->num_env; o->num_env_old = p->num_env_old; o->iid_quant = p->iid_quant;
-    o->nr_iid_par = p->nr_iid_par; o->nr_icc_par = p->nr_icc_par; o->nr_ipdopd_par = p->nr_ipdopd_par; o->icc_mode = p->icc_mode;
-    o->enable_ipdopd = p->enable_ipdopd; o->is34bands = p->is34; o->is34bands_old = p->is34_old;
-    for (int i = 0; i < 6; i++) o->border_position[i] = (int8_t)p->border[i];
-    fe_copy32(o->iid_par, p->iid, 4 * 5 * 34 / 4);         /* iid, icc, ipd, opd are contiguous in both structures */
+    fe_copy32_l(o->iid_par, p->iid, 4 * 5 * 34 / 4, lane, nl);        /* iid, icc, ipd, opd are contiguous in both structures */
+    if (lane == 0) {
+        fe_zero32(o, 20 / 4);
+        o->start = p->start; o->num_env = p->num_env; o->num_env_old = p->num_env_old; o->iid_quant = p->iid_quant;
+        o->nr_iid_par = p->nr_iid_par; o->nr_icc_par = p->nr_icc_par; o->nr_ipdopd_par = p->nr_ipdopd_par; o->icc_mode = p->icc_mode;
+        o->enable_ipdopd = p->enable_ipdopd; o->is34bands = p->is34; o->is34bands_old = p->is34_old;
+        for (int i = 0; i < 6; i++) o->border_position[i] = (int8_t)p->border[i];
+    }
+}
+/* all SBR elements + PS of the frame the stream's state currently describes */
+FE_FN void fe_pack_l(const FE *fe, HeaacSbrElem *sbr, HeaacPsFrame *ps, int lane, int nl)
+{
+    if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr_l(&fe->sbr_el[se], &sbr[se], lane, nl), se++;
+    if (ps) pack_ps_l(&fe->psx, ps, lane, nl);
 }
 
 /* An SBR fill payload met after element `prev_elem` (decode_extension_payload, aacdec.c:1650-1690): implicit
@@ -1071,8 +1092,7 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
             else fe_zero32(tns[c].n_filt, 2);
         }
     }
-    if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr(&fe->sbr_el[se], &sbr[se]), se++;
-    if (ps) pack_ps(&fe->psx, ps);
+    fe_pack_l(fe, sbr, ps, 0, 1);
     int consumed = (b->pos + 7) >> 3;
     return consumed > size ? size : consumed;
 }
@@ -1129,8 +1149,7 @@ FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, f
         }
     }
     fe->locked = 1;
-    if (sbr) for (int e = 0, se = 0; e < fe->n_elems; e++) if (fe->elem_type[e] != HEAAC_TYPE_LFE) pack_sbr(&fe->sbr_el[se], &sbr[se]), se++;
-    if (ps) pack_ps(&fe->psx, ps);
+    fe_pack_l(fe, sbr, ps, 0, 1);
     return todo->result;
 }
 

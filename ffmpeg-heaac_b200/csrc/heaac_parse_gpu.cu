@@ -79,26 +79,32 @@ k_parse(FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const ui
                        blob + off[idx], size[idx], coeffs + idx * ncc * 1024, ics + idx * ncc, tns + idx * ncc);
         }
         __syncwarp();
-        if (lane == 0) {
-            const int n = n_frames - t0 < 32 ? n_frames - t0 : 32;
-            for (int k = 0; k < n; k++) {
-                const size_t idx = (size_t)(t0 + k) * S + s;
-                float *co = coeffs + idx * ncc * 1024;
-                HeaacIcs *ic = ics + idx * ncc;
-                HeaacTns *tn = tns + idx * ncc;
-                HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
-                HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
-                int r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, sb, pp);
+        const int n = n_frames - t0 < 32 ? n_frames - t0 : 32;
+        for (int k = 0; k < n; k++) {
+            const size_t idx = (size_t)(t0 + k) * S + s;
+            float *co = coeffs + idx * ncc * 1024;
+            HeaacIcs *ic = ics + idx * ncc;
+            HeaacTns *tn = tns + idx * ncc;
+            HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
+            HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
+            int r = 0;
+            if (lane == 0) {                                        /* sequential part; packing left to the whole warp */
+                r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, nullptr, nullptr);
                 if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;      /* layout differs from the batch's */
-                if (r < 0) {                                            /* silent frame; the batch goes on */
-                    fe_zero(co, ncc * 1024);
-                    fe_zero32(ic, (int)(sizeof(HeaacIcs) * ncc / 4));
-                    fe_zero32(tn, (int)(sizeof(HeaacTns) * ncc / 4));
-                    if (sb) fe_zero32(sb, (int)(sizeof(HeaacSbrElem) * nse / 4));
-                    if (pp) fe_zero32(pp, (int)(sizeof(HeaacPsFrame) / 4));
-                }
                 consumed[idx] = r;
             }
+            __syncwarp();                                           /* lane 0's state writes before the other lanes' reads */
+            r = __shfl_sync(0xffffffffu, r, 0);
+            if (r >= 0) {
+                fe_pack_l(fe, sb, pp, lane, 32);
+            } else {                                                /* silent frame; the batch goes on */
+                for (int i = lane; i < ncc * 1024; i += 32) co[i] = 0.0f;
+                for (int i = lane; i < (int)(sizeof(HeaacIcs) * ncc / 4); i += 32) ((uint32_t *)ic)[i] = 0;
+                for (int i = lane; i < (int)(sizeof(HeaacTns) * ncc / 4); i += 32) ((uint32_t *)tn)[i] = 0;
+                if (sb) for (int i = lane; i < (int)(sizeof(HeaacSbrElem) * nse / 4); i += 32) ((uint32_t *)sb)[i] = 0;
+                if (pp) for (int i = lane; i < (int)(sizeof(HeaacPsFrame) / 4); i += 32) ((uint32_t *)pp)[i] = 0;
+            }
+            __syncwarp();                                           /* the pack reads state the next frame's parse overwrites */
         }
         __syncwarp();
     }
