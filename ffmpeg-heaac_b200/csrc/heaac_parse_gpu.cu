@@ -36,7 +36,9 @@ struct HeaacGpuParser {
     FeTables *d_tb;
     uint8_t *d_scratch;              /* [S][32] frame-local parser states of phase A (head + channel blocks) */
     size_t scratch_stride;
-    FeTodo *d_todo;                  /* [S][32] */
+    FeTodo *d_todo[2];               /* [S][32] per staging set: phase B of chunk k reads one while phase A of k+1 fills the other */
+    cudaStream_t s_b;                /* phase B's stream */
+    cudaEvent_t ev_a[2];             /* phase A of the chunk in staging set i is done */
     /* per staging set: packets of one chunk, 8-byte aligned and zero padded */
     uint8_t *h_blob[2], *d_blob[2];
     uint32_t *h_off[2], *d_off[2];   /* [chunk][S] byte offset of each packet in the blob */
@@ -57,56 +59,59 @@ struct HeaacGpuParser {
     int dbg_n, dbg_on;
 };
 
-/* One warp per stream.  Phase A: lane t parses the core elements of the chunk's frame t on a frame-local scratch
- * state (independent of the other frames); phase B: lane 0 walks the frames in order on the stream's persistent
- * state (window history, SBR / PS payloads, packing).  See heaac_fe_core.h, "two-phase parse". */
+/* Two kernels per chunk, one warp per stream in both (see heaac_fe_core.h, "two-phase parse"):
+ *   k_parse_a  lane t parses the core elements of the chunk's frame t on a frame-local scratch state, independent of
+ *              the other frames and of the stream's history;
+ *   k_parse_b  lane 0 walks the frames in order on the stream's persistent state (window history, SBR / PS payloads);
+ *              the whole warp packs the result.
+ * They run on two CUDA streams, so phase B of chunk k overlaps phase A of chunk k+1. */
 #ifndef HEAAC_PARSE_MIN_BLOCKS
 #define HEAAC_PARSE_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(128, HEAAC_PARSE_MIN_BLOCKS)
-k_parse(FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const uint8_t *blob, const uint32_t *off,
-        const int *size, int n_frames, int S, int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics,
-        HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
+k_parse_a(const FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const uint8_t *blob, const uint32_t *off,
+          const int *size, int n_frames, int S, int ncc, float *coeffs, HeaacIcs *ics, HeaacTns *tns)
+{
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= S || lane >= n_frames) return;
+    const size_t idx = (size_t)lane * S + s;
+    fe_phase_a(fes + s, (FE *)(scratch + ((size_t)s * 32 + lane) * scratch_stride), todo + (size_t)s * 32 + lane,
+               blob + off[idx], size[idx], coeffs + idx * ncc * 1024, ics + idx * ncc, tns + idx * ncc);
+}
+
+__global__ void __launch_bounds__(128, HEAAC_PARSE_MIN_BLOCKS)
+k_parse_b(FE *fes, const FeTodo *todo, const uint8_t *blob, const uint32_t *off, const int *size, int n_frames, int S,
+          int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr,
+          HeaacPsFrame *ps, int *consumed)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= S) return;
     FE *fe = fes + s;
-    for (int t0 = 0; t0 < n_frames; t0 += 32) {
-        const int t = t0 + lane;
-        if (t < n_frames) {
-            const size_t idx = (size_t)t * S + s;
-            fe_phase_a(fe, (FE *)(scratch + ((size_t)s * 32 + lane) * scratch_stride), todo + (size_t)s * 32 + lane,
-                       blob + off[idx], size[idx], coeffs + idx * ncc * 1024, ics + idx * ncc, tns + idx * ncc);
+    for (int k = 0; k < n_frames; k++) {
+        const size_t idx = (size_t)k * S + s;
+        float *co = coeffs + idx * ncc * 1024;
+        HeaacIcs *ic = ics + idx * ncc;
+        HeaacTns *tn = tns + idx * ncc;
+        HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
+        HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
+        int r = 0;
+        if (lane == 0) {                                            /* sequential part; packing left to the whole warp */
+            r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, nullptr, nullptr);
+            if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;          /* layout differs from the batch's */
+            consumed[idx] = r;
         }
-        __syncwarp();
-        const int n = n_frames - t0 < 32 ? n_frames - t0 : 32;
-        for (int k = 0; k < n; k++) {
-            const size_t idx = (size_t)(t0 + k) * S + s;
-            float *co = coeffs + idx * ncc * 1024;
-            HeaacIcs *ic = ics + idx * ncc;
-            HeaacTns *tn = tns + idx * ncc;
-            HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
-            HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
-            int r = 0;
-            if (lane == 0) {                                        /* sequential part; packing left to the whole warp */
-                r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, nullptr, nullptr);
-                if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;      /* layout differs from the batch's */
-                consumed[idx] = r;
-            }
-            __syncwarp();                                           /* lane 0's state writes before the other lanes' reads */
-            r = __shfl_sync(0xffffffffu, r, 0);
-            if (r >= 0) {
-                fe_pack_l(fe, sb, pp, lane, 32);
-            } else {                                                /* silent frame; the batch goes on */
-                for (int i = lane; i < ncc * 1024; i += 32) co[i] = 0.0f;
-                for (int i = lane; i < (int)(sizeof(HeaacIcs) * ncc / 4); i += 32) ((uint32_t *)ic)[i] = 0;
-                for (int i = lane; i < (int)(sizeof(HeaacTns) * ncc / 4); i += 32) ((uint32_t *)tn)[i] = 0;
-                if (sb) for (int i = lane; i < (int)(sizeof(HeaacSbrElem) * nse / 4); i += 32) ((uint32_t *)sb)[i] = 0;
-                if (pp) for (int i = lane; i < (int)(sizeof(HeaacPsFrame) / 4); i += 32) ((uint32_t *)pp)[i] = 0;
-            }
-            __syncwarp();                                           /* the pack reads state the next frame's parse overwrites */
+        __syncwarp();                                               /* lane 0's state writes before the other lanes' reads */
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= 0) {
+            fe_pack_l(fe, sb, pp, lane, 32);
+        } else {                                                    /* silent frame; the batch goes on */
+            for (int i = lane; i < ncc * 1024; i += 32) co[i] = 0.0f;
+            for (int i = lane; i < (int)(sizeof(HeaacIcs) * ncc / 4); i += 32) ((uint32_t *)ic)[i] = 0;
+            for (int i = lane; i < (int)(sizeof(HeaacTns) * ncc / 4); i += 32) ((uint32_t *)tn)[i] = 0;
+            if (sb) for (int i = lane; i < (int)(sizeof(HeaacSbrElem) * nse / 4); i += 32) ((uint32_t *)sb)[i] = 0;
+            if (pp) for (int i = lane; i < (int)(sizeof(HeaacPsFrame) / 4); i += 32) ((uint32_t *)pp)[i] = 0;
         }
-        __syncwarp();
+        __syncwarp();                                               /* the pack reads state the next frame's parse overwrites */
     }
 }
 
@@ -129,7 +134,8 @@ static void parser_free(HeaacGpuParser *p)
     if (p->d_fe) cudaFree(p->d_fe);
     if (p->d_template) cudaFree(p->d_template);
     if (p->d_scratch) cudaFree(p->d_scratch);
-    if (p->d_todo) cudaFree(p->d_todo);
+    for (int i = 0; i < 2; i++) { if (p->d_todo[i]) cudaFree(p->d_todo[i]); if (p->ev_a[i]) cudaEventDestroy(p->ev_a[i]); }
+    if (p->s_b) cudaStreamDestroy(p->s_b);
     if (p->d_tb) cudaFree(p->d_tb);
     delete p;
 }
@@ -141,6 +147,7 @@ extern "C" void heaac_b200_parser_destroy(HeaacGpuParser *p)
     heaac_b200_parser_debug_timeline(p);
     cudaSetDevice(p->ctx->cfg.device);
     cudaStreamSynchronize(p->ctx->s_in);
+    cudaStreamSynchronize(p->s_b);
     cudaStreamSynchronize(p->ctx->stream);
     cudaStreamSynchronize(p->ctx->s_out);
     parser_free(p);
@@ -184,7 +191,11 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     CKP(cudaMalloc(&p->d_template, sizeof(FE)));
     p->scratch_stride = (offsetof(FE, ch) + (size_t)c->geom.ncc * sizeof(FeChan) + 15) & ~(size_t)15;
     CKP(cudaMalloc(&p->d_scratch, S * 32 * p->scratch_stride));
-    CKP(cudaMalloc(&p->d_todo, S * 32 * sizeof(FeTodo)));
+    for (int i = 0; i < 2; i++) {
+        CKP(cudaMalloc(&p->d_todo[i], S * 32 * sizeof(FeTodo)));
+        CKP(cudaEventCreateWithFlags(&p->ev_a[i], cudaEventDisableTiming));
+    }
+    CKP(cudaStreamCreateWithFlags(&p->s_b, cudaStreamNonBlocking));
     CKP(cudaMemcpy(p->d_template, heaac_fe_state_blob(fe), sizeof(FE), cudaMemcpyHostToDevice));
     for (int i = 0; i < 8; i++) CKP(cudaHostAlloc(&p->h_consumed[i], (size_t)c->cfg.max_frames_per_call * S * sizeof(int), cudaHostAllocDefault));
     for (int b = 0; b < 2 && !r; b++) {
@@ -280,15 +291,20 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
             const int threads = 128, warps_per_cta = threads / 32;
             const int grid = (int)((S + warps_per_cta - 1) / warps_per_cta);
             if (!p->timed[buf]) CK(cudaEventRecord(p->ev_k0[buf], c->s_in));
-            k_parse<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_scratch, p->scratch_stride, p->d_todo, p->d_blob[buf],
-                                                   p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc, g->nse, g->sbr, g->ps,
-                                                   c->s_coeffs[buf], c->s_ics[buf], c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf],
-                                                   p->d_consumed[buf]);
+            k_parse_a<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_scratch, p->scratch_stride, p->d_todo[buf], p->d_blob[buf],
+                                                     p->d_off[buf], p->d_size[buf], n, (int)S, g->ncc, c->s_coeffs[buf],
+                                                     c->s_ics[buf], c->s_tns[buf]);
             CK(cudaGetLastError());
-            if (!p->timed[buf]) { CK(cudaEventRecord(p->ev_k1[buf], c->s_in)); p->timed[buf] = 1; }
-            p->launches++;
+            CK(cudaEventRecord(p->ev_a[buf], c->s_in));
+            CK(cudaStreamWaitEvent(p->s_b, p->ev_a[buf], 0));
+            k_parse_b<<<grid, threads, 0, p->s_b>>>(p->d_fe, p->d_todo[buf], p->d_blob[buf], p->d_off[buf], p->d_size[buf], n,
+                                                     (int)S, g->ncc, g->nse, g->sbr, g->ps, c->s_coeffs[buf], c->s_ics[buf],
+                                                     c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf], p->d_consumed[buf]);
+            CK(cudaGetLastError());
+            if (!p->timed[buf]) { CK(cudaEventRecord(p->ev_k1[buf], p->s_b)); p->timed[buf] = 1; }
+            p->launches += 2;
         }
-        CK(cudaEventRecord(c->ev_in[buf], c->s_in));
+        CK(cudaEventRecord(c->ev_in[buf], p->s_b));
         if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][1], c->s_in));
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
