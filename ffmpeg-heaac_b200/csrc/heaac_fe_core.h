@@ -173,6 +173,11 @@ FE_INL void fe_zero32(void *dst, int nwords)
     uint32_t *d = (uint32_t *)dst;
     for (int i = 0; i < nwords; i++) d[i] = 0;
 }
+FE_INL void fe_zero16(void *dst, int nhalf)                     /* 2-byte aligned */
+{
+    uint16_t *d = (uint16_t *)dst;
+    for (int i = 0; i < nhalf; i++) d[i] = 0;
+}
 
 /* ---------------------------------------------------------------- state */
 typedef struct FeChan {
@@ -339,7 +344,7 @@ FE_FN int tns_data(FeChan *c, BR *b)                             /* aacdec.c:854
 {
     const int is8 = c->ws[0] == HEAAC_EIGHT_SHORT;
     const int max_order = is8 ? 7 : 12;
-    memset(&c->tns, 0, sizeof(c->tns));
+    fe_zero32(&c->tns, (int)(sizeof(c->tns) / 4));
     for (int w = 0; w < c->num_windows; w++) {
         int nf = br_get(b, 2 - is8);
         c->tns.n_filt[w] = nf;
@@ -514,11 +519,12 @@ FE_FN int decode_ics(FE *fe, FeChan *c, BR *b, float *coef, int common_window)  
 
 FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *co1)  /* aacdec.c:1460-1494 */
 {
-    uint8_t ms_mask[128];
+    uint32_t ms_mask_w[32];                                        /* 128 flags, cleared / set by words */
+    uint8_t *ms_mask = (uint8_t *)ms_mask_w;
     int r, ms_present = 0;
     int common = br_get1(b);
     fe->last_common = common;
-    memset(ms_mask, 0, sizeof(ms_mask));
+    fe_zero32(ms_mask_w, 32);
     if (common) {
         if ((r = ics_info(fe, c0, b))) return r;
         int keep = c1->shape[0];
@@ -528,7 +534,7 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
         ms_present = br_get(b, 2);
         if (ms_present == 3) return HEAAC_E_INVAL;
         if (ms_present == 1) for (int i = 0; i < c0->num_groups * c0->max_sfb; i++) ms_mask[i] = br_get1(b);
-        else if (ms_present == 2) memset(ms_mask, 1, c0->num_groups * c0->max_sfb);
+        else if (ms_present == 2) for (int i = 0; i < 32; i++) ms_mask_w[i] = 0x01010101u;
     }
     if ((r = decode_ics(fe, c0, b, co0, common))) return r;
     if ((r = decode_ics(fe, c1, b, co1, common))) return r;
@@ -729,7 +735,7 @@ FE_FN void sbr_envelope(FeSbr *s, FeSbrCh *c, BR *b, int ch)     /* read_sbr_env
             for (int j = 1; j < nb; j++) c->env[i + 1][j] = c->env[i + 1][j - 1] + delta * (vlc_get(b, &TB->vsbr[fh]) - sbr_lav[fh]);
         }
     }
-    memcpy(c->env[0], c->env[c->num_env], sizeof(c->env[0]));
+    fe_copy32(c->env[0], c->env[c->num_env], (int)(sizeof(c->env[0]) / 4));
 }
 
 FE_FN void sbr_noise(FeSbr *s, FeSbrCh *c, BR *b, int ch)        /* read_sbr_noise, aacsbr.c:856-890 */
@@ -810,13 +816,13 @@ FE_FN int ps_read(FePs *p, BR *host, int bits_left)
             int dt = br_get1(b);
             if (ps_par(p, b, p->iid, (dt ? (p->iid_quant ? PS_IID_DT1 : PS_IID_DT0) : (p->iid_quant ? PS_IID_DF1 : PS_IID_DF0)), e, dt, p->nr_iid_par, 0)) goto err;
         }
-    } else memset(p->iid, 0, sizeof(p->iid));
+    } else fe_zero16(p->iid, (int)(sizeof(p->iid) / 2));
     if (p->enable_icc) {
         for (int e = 0; e < p->num_env; e++) {
             int dt = br_get1(b);
             if (ps_par(p, b, p->icc, dt ? PS_ICC_DT : PS_ICC_DF, e, dt, p->nr_icc_par, 1)) goto err;
         }
-    } else memset(p->icc, 0, sizeof(p->icc));
+    } else fe_zero16(p->icc, (int)(sizeof(p->icc) / 2));
     if (p->enable_ext) {
         int cnt = br_get(b, 4);
         if (cnt == 15) cnt += br_get(b, 8);
@@ -854,7 +860,7 @@ FE_FN int ps_read(FePs *p, BR *host, int bits_left)
     p->is34_old = p->is34;
     if (p->enable_iid || p->enable_icc)
         p->is34 = (p->enable_iid && p->nr_iid_par == 34) || (p->enable_icc && p->nr_icc_par == 34);
-    if (!p->enable_ipdopd) { memset(p->ipd, 0, sizeof(p->ipd)); memset(p->opd, 0, sizeof(p->opd)); }
+    if (!p->enable_ipdopd) fe_zero32(p->ipd, (int)((sizeof(p->ipd) + sizeof(p->opd)) / 4));     /* contiguous, 4-byte aligned */
     if (header) p->start = 1;
     {
         int consumed = b->pos - start_pos;
