@@ -91,6 +91,9 @@ struct HeaacDevTables {
     float Q_fract_allpass[2][50][3][2], phi_fract[2][50][2];
     float g1_Q2[8];
     int8_t k_to_i_20[71 + 1], k_to_i_34[91 + 1];
+    /* inverse of k_to_i: the hybrid bands of parameter band i, in ascending order, are ps_inv_k[mode][ps_inv_off[mode][i] ..
+     * ps_inv_off[mode][i + 1]) (mode 0: 20-band, 1: 34-band) */
+    uint8_t ps_inv_off[2][36], ps_inv_k[2][92];
 };
 
 /* ---- per core channel state -------------------------------------------------------- */

@@ -473,9 +473,12 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     /* ---- decorrelation, aacps.c:645-754 ---- */
     for (int w = tid; w < nr_par * 32; w += nt) {
         int i = w >> 5, n = w & 31;
-        float pw = 0.0f;
-        for (int k = 0; k < nr_bands; k++)
-            if (k_to_i[k] == i) pw += sm->L[k][n][0] * sm->L[k][n][0] + sm->L[k][n][1] * sm->L[k][n][1];
+        float pw = 0.0f;                                  /* sum over the bands of parameter band i, ascending k (aacps.c:690-697) */
+        const uint8_t *kl = T->ps_inv_k[is34];
+        for (int q = T->ps_inv_off[is34][i]; q < T->ps_inv_off[is34][i + 1]; q++) {
+            const int k = kl[q];
+            pw += sm->L[k][n][0] * sm->L[k][n][0] + sm->L[k][n][1] * sm->L[k][n][1];
+        }
         sm->power[i][n] = pw;
     }
     HEAAC_SYNC();

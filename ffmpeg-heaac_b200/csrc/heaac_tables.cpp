@@ -166,6 +166,15 @@ static void ps_tables(HeaacDevTables *t)
     memcpy(t->g1_Q2, proto1_q2, sizeof(proto1_q2));
     memcpy(t->k_to_i_20, map20, sizeof(map20));
     memcpy(t->k_to_i_34, map34, sizeof(map34));
+    for (int mode = 0; mode < 2; mode++) {
+        const int8_t *map = mode ? t->k_to_i_34 : t->k_to_i_20;
+        const int nb = mode ? 91 : 71, np = mode ? 34 : 20;
+        int pos = 0;
+        for (int i = 0; i < 36; i++) {
+            t->ps_inv_off[mode][i] = (uint8_t)pos;
+            if (i < np) for (int k = 0; k < nb; k++) if (map[k] == i) t->ps_inv_k[mode][pos++] = (uint8_t)k;
+        }
+    }
 }
 
 extern "C" void heaac_build_tables(HeaacDevTables *t)

@@ -21,7 +21,7 @@ TABLES = np.dtype([
     ("pd_re_smooth", "f4", 512), ("pd_im_smooth", "f4", 512), ("HA", "f4", (46, 8, 4)), ("HB", "f4", (46, 8, 4)),
     ("f20_0_8", "f4", (8, 7, 2)), ("f34_0_12", "f4", (12, 7, 2)), ("f34_1_8", "f4", (8, 7, 2)), ("f34_2_4", "f4", (4, 7, 2)),
     ("Q_fract_allpass", "f4", (2, 50, 3, 2)), ("phi_fract", "f4", (2, 50, 2)), ("g1_Q2", "f4", 8),
-    ("k_to_i_20", "i1", 72), ("k_to_i_34", "i1", 92),
+    ("k_to_i_20", "i1", 72), ("k_to_i_34", "i1", 92), ("ps_inv_off", "u1", (2, 36)), ("ps_inv_k", "u1", (2, 92)),
 ], align=True)
 
 
