@@ -43,6 +43,30 @@ static void prof_end(HeaacContext *c)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* TNS pre-pass: one thread per (channel, chain slot).  The all-pole filters are serial in the coefficient index and
+ * only 1..8 of them exist per channel, so inside k_core they would hold a whole CTA for the length of the slowest
+ * chain; here every chain of the tick runs at once.  Reads the caller's coefficients, writes the filtered ranges to
+ * `done` (same indexing); k_core overlays them. */
+__global__ void __launch_bounds__(128)
+k_tns(int n_channels, int sr_index, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
+      const HeaacTns *__restrict__ tns, float *done, const HeaacDevTables *__restrict__ T)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gc = t >> 3, slot = t & 7;
+    if (gc >= n_channels) return;
+    const HeaacIcs ic = ics[gc];
+    if (!ic.tns_present) return;
+    int start, size, inc, order;
+    float lpc[HEAAC_TNS_MAX_ORDER];
+    if (!heaac_tns_chain(&ic, tns + gc, sr_index, T, slot, &start, &size, &inc, &order, lpc, 1)) return;
+    const float *in = coeffs + (size_t)gc * 1024;
+    float *out = done + (size_t)gc * 1024;
+    if (order <= 4)       heaac_tns_run<4>(in, out, start, size, inc, order, lpc);
+    else if (order <= 8)  heaac_tns_run<8>(in, out, start, size, inc, order, lpc);
+    else if (order <= 12) heaac_tns_run<12>(in, out, start, size, inc, order, lpc);
+    else                  heaac_tns_run<HEAAC_TNS_MAX_ORDER>(in, out, start, size, inc, order, lpc);
+}
+
 /* Persistent: the CTAs of the grid claim channels from a device counter (so CTAs that are scheduled late, e.g.
  * behind a concurrently running parse kernel, do not hold the kernel up) and stage the NEXT claimed channel's
  * coefficients into the other half of a double buffer with cp.async while working on the current one.
@@ -50,7 +74,8 @@ static void prof_end(HeaacContext *c)
 __global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
 k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
        const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
-       int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, unsigned *work)
+       int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, unsigned *work,
+       const float *__restrict__ tns_done)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_claim[2];
@@ -80,6 +105,7 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
             heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
         heaac_cp_async_commit();
         heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
+                                          tns_done ? tns_done + (size_t)gc * 1024 : nullptr,
                                           st, out, bias, g.sr_index, T, threadIdx.x);
         if (ana) {
             /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
@@ -304,6 +330,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     }
     size_t S = g->n_streams, T = cfg->max_frames_per_call;
     CKX(cudaMalloc(&c->d_chan, S * g->ncc * sizeof(HeaacChanState)));
+    if (!getenv("HEAAC_NO_TNS_PREPASS")) CKX(cudaMalloc(&c->d_tns_done, S * g->ncc * 1024 * sizeof(float)));
     CKX(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
     CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
     if (g->sbr) {
@@ -364,7 +391,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work);
+    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_tns_done);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
         cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
@@ -413,9 +440,14 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         prof_begin(c, HEAAC_K_CORE);
         {
             const unsigned n_ch = (unsigned)(S * g.ncc);
+            if (tn && c->d_tns_done) {
+                k_tns<<<(n_ch * 8 + 127) / 128, 128, 0, c->stream>>>((int)n_ch, g.sr_index, co, ic, tn, c->d_tns_done, c->d_tables);
+                c->launches++;
+            }
             const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
             k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(
-                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work);
+                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work,
+                tn ? c->d_tns_done : nullptr);
         }
         prof_end(c);
         c->launches++;

@@ -17,6 +17,7 @@ struct HeaacContext {
     HeaacChanState *d_chan;          /* [S][ncc] */
     HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
     HeaacPsState *d_ps;              /* [S] (PS only) */
+    float *d_tns_done;               /* [S][ncc][1024]: TNS-filtered coefficient ranges of the current tick (k_tns -> k_core) */
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
     float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
     float *d_X;                      /* [S][nout][2][38][64] (SBR only) */

@@ -165,12 +165,81 @@ HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const flo
     }
 }
 
+/* One of the (at most 8) independent TNS filters of a channel-frame (aacdec.c:1701-1728): slot = window for short
+ * blocks, filter index (< 3) for long ones.  Returns 0 if the slot holds no filter; else the coefficient range as
+ * (first index, count, step) and, if want_lpc, the direct-form coefficients (compute_lpc_coefs(normalize = 0),
+ * lpc.h:75-96). */
+HEAAC_DEV int heaac_tns_chain(const HeaacIcs *ics, const HeaacTns *HEAAC_RESTRICT tns, int sr_index,
+                              const HeaacDevTables *HEAAC_RESTRICT T, int slot, int *start_o, int *size_o, int *inc_o,
+                              int *order_o, float *lpc, int want_lpc)
+{
+    const int is8 = ics->window_sequence == HEAAC_EIGHT_SHORT;
+    const int w = is8 ? slot : 0, f = is8 ? 0 : slot;
+    const int nf = tns->n_filt[w];
+    if (f >= nf || (!is8 && slot >= 3)) return 0;
+    const uint16_t *swb = is8 ? T->swb_offset_128[sr_index] : T->swb_offset_1024[sr_index];
+    const int num_swb = is8 ? T->num_swb_128[sr_index] : T->num_swb_1024[sr_index];
+    const int tmb = is8 ? T->tns_max_bands_128[sr_index] : T->tns_max_bands_1024[sr_index];
+    const int mmm = HEAAC_MIN(tmb, (int)ics->max_sfb);
+    int bottom = num_swb, top = num_swb;
+    for (int g = 0; g <= f; g++) {                   /* walk down to this filter's band range */
+        const int sl = is8 ? w : g;
+        top = bottom;
+        bottom = HEAAC_MAX(0, top - (int)tns->length[sl]);
+    }
+    const int order = tns->order[slot];
+    if (!order) return 0;
+    int start = swb[HEAAC_MIN(bottom, mmm)];
+    const int end = swb[HEAAC_MIN(top, mmm)];
+    const int size = end - start;
+    int inc = 1;
+    if (size <= 0) return 0;
+    if (tns->direction[slot]) { inc = -1; start = end - 1; }
+    if (want_lpc)
+        for (int i = 0; i < order; i++) {
+            const float r = -tns->coef[slot][i];
+            lpc[i] = r;
+            for (int j = 0; j < (i + 1) >> 1; j++) {
+                const float a = lpc[j], b = lpc[i - 1 - j];
+                lpc[j] = a + r * b;
+                lpc[i - 1 - j] = b + r * a;
+            }
+        }
+    *start_o = start + w * 128; *size_o = size; *inc_o = inc; *order_o = order;
+    return 1;
+}
+
+#ifndef HEAAC_HOST_EMU
+/* The all-pole filter of one chain with the last ORD outputs and the coefficients in registers:
+ *   y[m] = (((x[m] - y[m-1] a[0]) - y[m-2] a[1]) - ...)      in exactly this order (apply_tns, aacdec.c:1729-1733);
+ * taps beyond the filter order have a = 0 and taps before the start of the range see y = 0, which leaves the sum
+ * unchanged bit for bit (x - 0 = x), so one unrolled form per order class serves every order. */
+template <int ORD>
+__device__ __forceinline__ void heaac_tns_run(const float *HEAAC_RESTRICT in, float *out, int start, int size, int inc,
+                                              int order, const float *lpc)
+{
+    float a[ORD], h[ORD];
+    HEAAC_UNROLL
+    for (int i = 0; i < ORD; i++) { a[i] = i < order ? lpc[i] : 0.0f; h[i] = 0.0f; }
+    for (int m = 0; m < size; m++, start += inc) {
+        float acc = in[start];
+        HEAAC_UNROLL
+        for (int i = 0; i < ORD; i++) acc -= h[i] * a[i];
+        out[start] = acc;
+        HEAAC_UNROLL
+        for (int i = ORD - 1; i > 0; i--) h[i] = h[i - 1];
+        h[0] = acc;
+    }
+}
+#endif
+
 /* `c`   : 1024 coefficients of this channel-frame, already staged in shared memory; overwritten (TNS in
  *         place, then the half-IMDCT output "buf")
  * `out` : 1024 floats in shared or global memory (time-domain output, bias included) */
 template <int NT>
 HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
                                   const HeaacIcs *HEAAC_RESTRICT ics_p, const HeaacTns *HEAAC_RESTRICT tns,
+                                  const float *HEAAC_RESTRICT tns_done,
                                   HeaacChanState *st, float *out, float bias, int sr_index,
                                   const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
@@ -181,49 +250,26 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
     const int shape_prev = ics.prev_valid ? (int)ics.prev_window_shape : st->prev_shape;
     const int is8 = ws0 == HEAAC_EIGHT_SHORT;
 
-    /* ---- TNS: set up the (at most 8) independent filters, aacdec.c:1701-1728 ---- */
+    /* ---- TNS, aacdec.c:1698-1736 ---- */
     const int use_tns = ics.tns_present && tns;
-    if (use_tns) {
-        for (int slot = tid; slot < 8; slot += nt) {
-            sm->tns_size[slot] = 0;
-            int w = is8 ? slot : 0;
-            int nf = tns->n_filt[w];
-            int f = is8 ? 0 : slot;
-            if (f >= nf || (is8 ? 0 : slot >= 3)) continue;
-            const uint16_t *swb = is8 ? T->swb_offset_128[sr_index] : T->swb_offset_1024[sr_index];
-            int num_swb = is8 ? T->num_swb_128[sr_index] : T->num_swb_1024[sr_index];
-            int tmb = is8 ? T->tns_max_bands_128[sr_index] : T->tns_max_bands_1024[sr_index];
-            int mmm = HEAAC_MIN(tmb, (int)ics.max_sfb);
-            int bottom = num_swb, top = num_swb;
-            for (int g = 0; g <= f; g++) {           /* walk down to this filter's band range */
-                int sl = is8 ? w : g;
-                top = bottom;
-                bottom = HEAAC_MAX(0, top - (int)tns->length[sl]);
-            }
-            int order = tns->order[slot];
-            if (!order) continue;
-            float *lpc = sm->lpc[slot];
-            for (int i = 0; i < order; i++) {        /* compute_lpc_coefs(normalize = 0), lpc.h:75-96 */
-                float r = -tns->coef[slot][i];
-                lpc[i] = r;
-                for (int j = 0; j < (i + 1) >> 1; j++) {
-                    float a = lpc[j], b = lpc[i - 1 - j];
-                    lpc[j] = a + r * b;
-                    lpc[i - 1 - j] = b + r * a;
-                }
-            }
-            int start = swb[HEAAC_MIN(bottom, mmm)], end = swb[HEAAC_MIN(top, mmm)];
-            int size = end - start, inc = 1;
-            if (size <= 0) continue;
-            if (tns->direction[slot]) { inc = -1; start = end - 1; }
-            sm->tns_start[slot] = start + w * 128;
-            sm->tns_size[slot] = size;
-            sm->tns_inc[slot] = inc;
-            sm->tns_order[slot] = order;
+    if (use_tns && tns_done) {
+        /* the filters already ran in k_tns (one thread per chain, registers only): take over the filtered ranges */
+        for (int slot = 0; slot < 8; slot++) {
+            int start, size, inc, order;
+            float lpc_unused[HEAAC_TNS_MAX_ORDER];
+            if (!heaac_tns_chain(&ics, tns, sr_index, T, slot, &start, &size, &inc, &order, lpc_unused, 0)) continue;
+            const int lo = inc > 0 ? start : start - (size - 1);
+            for (int i = tid; i < size; i += nt) c[lo + i] = tns_done[lo + i];
         }
-    }
-    HEAAC_SYNC();
-    if (use_tns) {
+        HEAAC_SYNC();
+    } else if (use_tns) {
+        for (int slot = tid; slot < 8; slot += nt) {
+            int start, size, inc, order;
+            sm->tns_size[slot] = 0;
+            if (!heaac_tns_chain(&ics, tns, sr_index, T, slot, &start, &size, &inc, &order, sm->lpc[slot], 1)) continue;
+            sm->tns_start[slot] = start; sm->tns_size[slot] = size; sm->tns_inc[slot] = inc; sm->tns_order[slot] = order;
+        }
+        HEAAC_SYNC();
         /* all-pole filters over disjoint coefficient ranges: one serial chain per work item */
         for (int slot = tid; slot < 8; slot += nt) {
             int size = sm->tns_size[slot];
@@ -238,6 +284,8 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
                 c[start] = acc;
             }
         }
+        HEAAC_SYNC();
+    } else {
         HEAAC_SYNC();
     }
 

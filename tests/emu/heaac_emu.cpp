@@ -99,7 +99,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             if (ana) memcpy(x, st->ana_hist, 288 * sizeof(float));
             static float cbuf[1024];
             memcpy(cbuf, co + gc * 1024, sizeof(cbuf));           /* the kernel stages the coefficients with cp.async */
-            heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, st, out, bias,
+            heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, nullptr, st, out, bias,
                                g.sr_index, c->T, 0);
             if (ana) {
                 const float ana_scale = 1 / qmf_scale;
