@@ -340,12 +340,15 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
 /* ====================================================================================
  * Parametric Stereo for one stream-frame (ff_ps_apply, aacps.c:973-992)
  * ================================================================================== */
+/* slot dimension padded to 33: the time-serial phases run with lanes = bands, and an unpadded row (64 floats) would put
+ * all lanes of a warp on the same bank */
+#define HEAAC_PS_NS 33
 struct HeaacPsSmem {
-    float L[91][32][2];             /* Lbuf: hybrid-domain mono signal, then left output */
-    float R[91][32][2];             /* Rbuf: decorrelated signal, then right output */
+    float L[91][HEAAC_PS_NS][2];    /* Lbuf: hybrid-domain mono signal, then left output */
+    float R[91][HEAAC_PS_NS][2];    /* Rbuf: decorrelated signal, then right output */
     float in[5][44][2];             /* in_buf: 6 history + 38 new slots of QMF bands 0..4 */
-    float power[34][32];
-    float tgain[34][32];
+    float power[34][HEAAC_PS_NS];
+    float tgain[34][HEAAC_PS_NS];
     float H[4][2][6][34];           /* H11,H12,H21,H22 [re/im][envelope 0..5][band] */
     int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
     HeaacPsFrame p;
@@ -719,7 +722,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     /* ---- hybrid synthesis x 2, aacps.c:397-445: back to 64 QMF bands, slots 0..31 ---- */
     for (int w = tid; w < 2 * 32 * 64; w += nt) {
         int side = w >> 11, q = (w >> 5) & 63, n = w & 31;      /* slot fastest */
-        const float (*in)[32][2] = side ? sm->R : sm->L;
+        const float (*in)[HEAAC_PS_NS][2] = side ? sm->R : sm->L;
         float *X = side ? XR : XL;
         float re, im;
         if (is34) {
