@@ -744,7 +744,7 @@ __global__ void k_imdct_half_one(float *out, const float *in, const float *tcos,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *buf = reinterpret_cast<float *>(smem_raw);
     const int n4 = 1 << log2n4, n2 = n4 * 2;
-    float *zr = buf + n2, *zi = zr + n4;
+    float *zr = buf + n2, *zi = zr + n4 + (n4 >> 3);           /* skewed layout: HEAAC_ZP */
     for (int i = threadIdx.x; i < n2; i += blockDim.x) buf[i] = in[i];
     __syncthreads();
     heaac_imdct_half_smem<HEAAC_THREADS>(buf, buf, zr, zi, log2n4, 1, tcos, tsin, T, threadIdx.x);
@@ -788,7 +788,7 @@ extern "C" void heaac_b200_imdct_half(HeaacMdct *m, float *output, const float *
     if (!m) return;
     int n = 1 << m->nbits, n2 = n >> 1, n4 = n >> 2;
     cudaMemcpy(m->d_in, input, sizeof(float) * n2, cudaMemcpyHostToDevice);
-    k_imdct_half_one<<<1, 256, sizeof(float) * (n2 + 2 * n4)>>>(m->d_out, m->d_in, m->d_tcos, m->d_tsin,
+    k_imdct_half_one<<<1, 256, sizeof(float) * (n2 + 2 * (n4 + (n4 >> 3)))>>>(m->d_out, m->d_in, m->d_tcos, m->d_tsin,
                                                                  m->nbits - 2, m->d_tables);
     cudaMemcpy(output, m->d_out, sizeof(float) * n2, cudaMemcpyDeviceToHost);
 }

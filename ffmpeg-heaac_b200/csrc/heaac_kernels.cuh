@@ -70,26 +70,75 @@ HEAAC_DEV int16_t heaac_to_s16(float x, int bias_mode)
  * Input must already be in bit-reversed order.  `nbatch` transforms of 2^log2n points lie
  * back to back.  Radix-2, one butterfly per work item, log2n barriers.
  * ---------------------------------------------------------------------------------- */
+/* element i of the FFT arrays lives at i + (i >> 3): with 8 consecutive points per work item in the first pass and
+ * strides of 8 and 64 in the later ones, the skew keeps every pass (nearly) free of bank conflicts */
+#define HEAAC_ZP(i) ((i) + ((i) >> 3))
+#define HEAAC_Z_FLOATS (512 + 64)
+
+/* One radix-2 butterfly of the network: (a, b) <- (a + w b, a - w b), w = exp(2 pi i j / 2^s) from the 512-point table. */
+#define HEAAC_BFLY(ar, ai, br, bi, wr, wi) do { \
+        const float tr_ = (br) * (wr) - (bi) * (wi), ti_ = (br) * (wi) + (bi) * (wr); \
+        (br) = (ar) - tr_; (bi) = (ai) - ti_; (ar) = (ar) + tr_; (ai) = (ai) + ti_; } while (0)
+
 template <int NT>
 HEAAC_DEV void heaac_fft_smem(float *re, float *im, int log2n, int nbatch,
                               const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
+    /* The same radix-2 decimation-in-time network as before (same butterflies, same twiddles, same operation order
+     * inside each butterfly), but three stages at a time: a work item loads the 8 points that stages 3p+1..3p+3
+     * connect, runs their 12 butterflies in registers and stores them back -- 3 passes and barriers for 512 points
+     * (2 for 64) instead of 9 (6), and a third of the shared-memory traffic. */
     constexpr int nt = NT;
-    const int hn = 1 << (log2n - 1);
-    const int total = nbatch * hn;
-    for (int s = 1; s <= log2n; s++) {
-        const int half = 1 << (s - 1);
-        const int tw_stride = 512 >> s;
-        for (int w = tid; w < total; w += nt) {
-            int b = w >> (log2n - 1), r = w & (hn - 1);
-            int j = r & (half - 1), grp = r >> (s - 1);
-            int i0 = (b << log2n) + (grp << s) + j, i1 = i0 + half;
-            float wr = T->fft_wre[j * tw_stride], wi = T->fft_wim[j * tw_stride];
-            float xr = re[i1], xi = im[i1];
-            float tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
-            float ar = re[i0], ai = im[i0];
-            re[i1] = ar - tr; im[i1] = ai - ti;
-            re[i0] = ar + tr; im[i0] = ai + ti;
+    const int n = 1 << log2n;
+    const int items = nbatch * (n >> 3);
+    const int lead = log2n % 3;                             /* sizes that are not a power of 8: plain stages first */
+    for (int s = 1; s <= lead; s++) {
+        const int half = 1 << (s - 1), hn = n >> 1;
+        for (int w = tid; w < nbatch * hn; w += nt) {
+            const int bt = w / hn, r = w - bt * hn;
+            const int j = r & (half - 1), grp = r >> (s - 1);
+            const int i0 = (bt << log2n) + (grp << s) + j, i1 = i0 + half;
+            const float wr = T->fft_wre[j * (512 >> s)], wi = T->fft_wim[j * (512 >> s)];
+            float ar = re[HEAAC_ZP(i0)], ai = im[HEAAC_ZP(i0)], br = re[HEAAC_ZP(i1)], bi = im[HEAAC_ZP(i1)];
+            HEAAC_BFLY(ar, ai, br, bi, wr, wi);
+            re[HEAAC_ZP(i0)] = ar; im[HEAAC_ZP(i0)] = ai; re[HEAAC_ZP(i1)] = br; im[HEAAC_ZP(i1)] = bi;
+        }
+        HEAAC_SYNC();
+    }
+    for (int p3 = lead; p3 < log2n; p3 += 3) {
+        const int h0 = 1 << p3;                             /* butterfly span of the first stage of this pass */
+        for (int w = tid; w < items; w += nt) {
+            const int bt = w / (n >> 3), r = w - bt * (n >> 3);
+            const int j = r & (h0 - 1), blk = r >> p3;
+            const int base = (bt << log2n) + (blk << (p3 + 3)) + j;
+            float xr[8], xi[8];
+            HEAAC_UNROLL
+            for (int m = 0; m < 8; m++) { const int e = HEAAC_ZP(base + m * h0); xr[m] = re[e]; xi[m] = im[e]; }
+            {                                               /* stage 3p+1: pairs (m, m+1), twiddle index j */
+                const int tw = j * (512 >> (p3 + 1));
+                const float wr = T->fft_wre[tw], wi = T->fft_wim[tw];
+                HEAAC_UNROLL
+                for (int m = 0; m < 8; m += 2) HEAAC_BFLY(xr[m], xi[m], xr[m + 1], xi[m + 1], wr, wi);
+            }
+            {                                               /* stage 3p+2: pairs (m, m+2), twiddle index j + (m & 1) h0 */
+                const int ts = 512 >> (p3 + 2);
+                const float w0r = T->fft_wre[j * ts], w0i = T->fft_wim[j * ts];
+                const float w1r = T->fft_wre[(j + h0) * ts], w1i = T->fft_wim[(j + h0) * ts];
+                HEAAC_BFLY(xr[0], xi[0], xr[2], xi[2], w0r, w0i);
+                HEAAC_BFLY(xr[1], xi[1], xr[3], xi[3], w1r, w1i);
+                HEAAC_BFLY(xr[4], xi[4], xr[6], xi[6], w0r, w0i);
+                HEAAC_BFLY(xr[5], xi[5], xr[7], xi[7], w1r, w1i);
+            }
+            {                                               /* stage 3p+3: pairs (m, m+4), twiddle index j + m h0 */
+                const int ts = 512 >> (p3 + 3);
+                HEAAC_UNROLL
+                for (int m = 0; m < 4; m++) {
+                    const float wr = T->fft_wre[(j + m * h0) * ts], wi = T->fft_wim[(j + m * h0) * ts];
+                    HEAAC_BFLY(xr[m], xi[m], xr[m + 4], xi[m + 4], wr, wi);
+                }
+            }
+            HEAAC_UNROLL
+            for (int m = 0; m < 8; m++) { const int e = HEAAC_ZP(base + m * h0); re[e] = xr[m]; im[e] = xi[m]; }
         }
         HEAAC_SYNC();
     }
@@ -122,20 +171,21 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
         const float *x = in + b * n2;
         float a = x[n2 - 1 - 2 * k], c = x[2 * k];
         int rk = heaac_bitrev(k, log2n4);
-        zr[b * n4 + rk] = a * tcos[k] - c * tsin[k];
-        zi[b * n4 + rk] = a * tsin[k] + c * tcos[k];
+        zr[HEAAC_ZP(b * n4 + rk)] = a * tcos[k] - c * tsin[k];
+        zi[HEAAC_ZP(b * n4 + rk)] = a * tsin[k] + c * tcos[k];
     }
     HEAAC_SYNC();
     heaac_fft_smem<NT>(zr, zi, log2n4, nbatch, T, tid);
     for (int w = tid; w < nbatch * n8; w += nt) {
         int b = w / n8, k = w - b * n8;
         int p = n8 - k - 1, q = n8 + k;
-        const float *r_ = zr + b * n4, *i_ = zi + b * n4;
         float *o = out + b * n2;
-        float r0 = i_[p] * tsin[p] - r_[p] * tcos[p];
-        float i1 = i_[p] * tcos[p] + r_[p] * tsin[p];
-        float r1 = i_[q] * tsin[q] - r_[q] * tcos[q];
-        float i0 = i_[q] * tcos[q] + r_[q] * tsin[q];
+        const float zrp = zr[HEAAC_ZP(b * n4 + p)], zip = zi[HEAAC_ZP(b * n4 + p)];
+        const float zrq = zr[HEAAC_ZP(b * n4 + q)], ziq = zi[HEAAC_ZP(b * n4 + q)];
+        float r0 = zip * tsin[p] - zrp * tcos[p];
+        float i1 = zip * tcos[p] + zrp * tsin[p];
+        float r1 = ziq * tsin[q] - zrq * tcos[q];
+        float i0 = ziq * tcos[q] + zrq * tsin[q];
         o[2 * p] = r0; o[2 * p + 1] = i0;
         o[2 * q] = r1; o[2 * q + 1] = i1;
     }
@@ -146,7 +196,7 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
  * AAC-LC core: TNS + IMDCT + windowing + overlap-add for one channel-frame
  * ================================================================================== */
 struct HeaacCoreSmem {
-    float zr[512], zi[512];
+    float zr[HEAAC_Z_FLOATS], zi[HEAAC_Z_FLOATS];
     float temp[128];
     float lpc[8][HEAAC_TNS_MAX_ORDER];
     int   tns_start[8], tns_size[8], tns_inc[8], tns_order[8];
