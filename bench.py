@@ -381,7 +381,7 @@ def main():
             pkt_step()
             drain()
             barrier()
-            n_pk = max(2, min(args.steps, 8))
+            n_pk = max(2, min(args.steps, 16))
             l0p = dec.info()["gpu_launches"]
             t0 = time.perf_counter()
             for _ in range(n_pk):
