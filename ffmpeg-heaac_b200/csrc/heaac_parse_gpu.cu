@@ -1,17 +1,15 @@
 /*
  * heaac_parse_gpu.cu -- the front end on the GPU: packets in, PCM out, nothing but bitstreams over PCIe.
  *
- * The same parser source as the host front end (heaac_fe_core.h, compiled here with FE_DEVICE) runs with one
- * GPU thread per stream: entropy decoding is serial inside a stream but the streams of a batch are independent,
- * and a B200 has room for thousands of such threads next to the synthesis kernels.  k_parse writes coeffs / ICS /
- * TNS / SBR / PS structures straight into the back end's device staging sets, so the host-to-device traffic of a
- * batch shrinks from the dequantised spectra (4 KiB per channel-frame) to the packets themselves (~0.2 KiB).
+ * The same parser source as the host front end (heaac_fe_core.h, compiled here with FE_DEVICE) runs with one warp
+ * per stream: entropy decoding is serial inside a frame but the streams of a batch are independent, and so are the
+ * core elements of different frames of one stream.  The parse kernels write coeffs / ICS / TNS / SBR / PS
+ * structures straight into the back end's device staging sets, so the host-to-device traffic of a batch shrinks
+ * from the dequantised spectra (4 KiB per channel-frame) to the packets themselves (~0.2 KiB).
  *
- * One warp per stream: the frames of a chunk are spread over the lanes for the stateless part of the parse and
- * finished in order by lane 0 (two-phase parse, heaac_fe_core.h); per-stream parser state (struct
- * HeaacFrontend) lives in HBM between calls.  Chunks are double buffered exactly like the
- * host-pointer path of heaac_b200_synth_submit: packets H2D + k_parse on s_in, synthesis kernels on the
- * context's stream, PCM D2H on s_out.
+ * Per-stream parser state (struct HeaacFrontend) lives in HBM between calls.  Chunks are double buffered exactly
+ * like the host-pointer path of heaac_b200_synth_submit: packets H2D + k_parse_a on s_in, k_parse_b on its own
+ * stream, synthesis kernels on the context's stream, PCM D2H on s_out.
  */
 #define FE_DEVICE 1
 #include <cuda_runtime.h>
@@ -20,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <mutex>
 #include <new>
 
 #include "heaac_context.cuh"
@@ -136,7 +135,6 @@ static void parser_free(HeaacGpuParser *p)
     if (p->d_scratch) cudaFree(p->d_scratch);
     for (int i = 0; i < 2; i++) { if (p->d_todo[i]) cudaFree(p->d_todo[i]); if (p->ev_a[i]) cudaEventDestroy(p->ev_a[i]); }
     if (p->s_b) cudaStreamDestroy(p->s_b);
-    if (p->d_tb) cudaFree(p->d_tb);
     delete p;
 }
 
@@ -184,9 +182,24 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     size_t tb_bytes = 0;
     const void *tb = heaac_fe_tables_blob(&tb_bytes);
     if (tb_bytes != sizeof(FeTables)) r = HEAAC_E_INVAL;
-    CKP(cudaMalloc(&p->d_tb, sizeof(FeTables)));
-    CKP(cudaMemcpy(p->d_tb, tb, sizeof(FeTables), cudaMemcpyHostToDevice));
-    CKP(cudaMemcpyToSymbol(fe_tb_dev, &p->d_tb, sizeof(p->d_tb)));
+    {
+        /* One copy of the parser tables per device for the life of the process: the kernels reach it through a
+         * __device__ pointer, so it must not go away while any parser on that device is alive. */
+        static std::mutex mu;
+        static FeTables *per_device[64];
+        std::lock_guard<std::mutex> lk(mu);
+        const int dev = c->cfg.device;
+        if (dev < 0 || dev >= 64) r = HEAAC_E_INVAL;
+        if (!r && !per_device[dev]) {
+            FeTables *d = nullptr;
+            CKP(cudaMalloc(&d, sizeof(FeTables)));
+            CKP(cudaMemcpy(d, tb, sizeof(FeTables), cudaMemcpyHostToDevice));
+            CKP(cudaMemcpyToSymbol(fe_tb_dev, &d, sizeof(d)));
+            if (!r) per_device[dev] = d;
+            else if (d) cudaFree(d);
+        }
+        if (!r) p->d_tb = per_device[dev];
+    }
     CKP(cudaMalloc(&p->d_fe, S * sizeof(FE)));
     CKP(cudaMalloc(&p->d_template, sizeof(FE)));
     p->scratch_stride = (offsetof(FE, ch) + (size_t)c->geom.ncc * sizeof(FeChan) + 15) & ~(size_t)15;

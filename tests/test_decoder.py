@@ -146,3 +146,25 @@ def test_decoder_pipelined_submit_wait(gpu_parse):
     dec.close()
     assert np.array_equal(np.concatenate([first] + outs), whole)
     assert np.array_equal(np.concatenate(cns), cons[4:])
+
+
+@pytest.mark.gpu
+def test_two_gpu_parse_decoders_share_the_device_tables():
+    """Two decoders with the device front end on one GPU, closed in either order, keep working (the parser tables
+    are one per-device copy reached through a __device__ pointer)."""
+    d = load_golden("lc_stereo_44k")
+    pk = golden_packets(d)
+    batch = hb.PacketBatch([[p] * 2 for p in pk])
+    a, b = open_for(d, 2, gpu_parse=True), open_for(d, 2, gpu_parse=True)
+    pa, _, _ = a.decode(batch)
+    pb, _, _ = b.decode(batch)
+    b.close()                                           # the second one goes first ...
+    c = open_for(d, 2, gpu_parse=True)
+    pc, _, _ = c.decode(batch)                          # ... a third comes, the first is still usable
+    a2 = open_for(d, 2, gpu_parse=True)
+    a.close()
+    pa2, _, _ = a2.decode(batch)
+    c.close(); a2.close()
+    assert np.array_equal(pa, pb) and np.array_equal(pa, pc) and np.array_equal(pa, pa2)
+    _, ref_s16 = golden_ref_pcm(d)
+    assert int(np.abs(pa[:, 0].astype(np.int32) - ref_s16).max()) <= 1
