@@ -498,14 +498,29 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                                const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
     constexpr int nt = NT;
+    const float *Lre = XL, *Lim = XL + HEAAC_X_PLANE;
+    /* Everything the first phases need comes from global memory (the frame's parameters, the QMF bands k_sbr has just
+     * written, the hybrid filter history): issue it all at once, one barrier, instead of three dependent round trips. */
+    const int start_g = frame->start, is34_g = frame->is34bands;
     {
         const uint32_t *src = (const uint32_t *)frame;
         uint32_t *dst = (uint32_t *)&sm->p;
         for (int i = tid; i < (int)(sizeof(HeaacPsFrame) / 4); i += nt) dst[i] = src[i];
     }
+    if (start_g) {
+        for (int w = tid; w < 5 * 44; w += nt) {              /* in_buf: 6 history slots + this frame, QMF bands 0..4 */
+            int i = w / 44, j = w - i * 44;
+            if (j < 6) { sm->in[i][j][0] = st->in_hist[i][j][0]; sm->in[i][j][1] = st->in_hist[i][j][1]; }
+            else       { sm->in[i][j][0] = Lre[i * HEAAC_XS + (j - 6)]; sm->in[i][j][1] = Lim[i * HEAAC_XS + (j - 6)]; }
+        }
+        const int nb = is34_g ? 59 : 61, q0 = is34_g ? 5 : 3, k0 = is34_g ? 32 : 10;   /* QMF bands that pass through */
+        for (int w = tid; w < nb * 32; w += nt) {
+            int i = w >> 5, n = w & 31;
+            sm->L[i + k0][n][0] = Lre[(i + q0) * HEAAC_XS + n]; sm->L[i + k0][n][1] = Lim[(i + q0) * HEAAC_XS + n];
+        }
+    }
     HEAAC_SYNC();
     const HeaacPsFrame *p = &sm->p;
-    const float *Lre = XL, *Lim = XL + HEAAC_X_PLANE;
     if (!p->start) {                                      /* aacsbr.c:1755: R = copy of L */
         for (int i = tid; i < HEAAC_X_FLOATS; i += nt) XR[i] = XL[i];
         HEAAC_SYNC();
@@ -518,13 +533,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     const int top = top_in + nr_bands - 64;
     const int switched = is34 != p->is34bands_old;        /* aacps.c:665-671: all decorrelator state is cleared */
 
-    /* ---- hybrid analysis, aacps.c:359-395 ---- */
-    for (int w = tid; w < 5 * 44; w += nt) {
-        int i = w / 44, j = w - i * 44;
-        if (j < 6) { sm->in[i][j][0] = st->in_hist[i][j][0]; sm->in[i][j][1] = st->in_hist[i][j][1]; }
-        else       { sm->in[i][j][0] = Lre[i * HEAAC_XS + (j - 6)]; sm->in[i][j][1] = Lim[i * HEAAC_XS + (j - 6)]; }
-    }
-    HEAAC_SYNC();
+    /* ---- hybrid analysis, aacps.c:359-395 (in_buf and the pass-through bands are already in shared memory) ---- */
     for (int w = tid; w < 5 * 6; w += nt) {
         int i = w / 6, j = w - i * 6;
         st->in_hist[i][j][0] = sm->in[i][32 + j][0]; st->in_hist[i][j][1] = sm->in[i][32 + j][1];
@@ -537,10 +546,6 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
             else if (q < 20) { band = 1; sub = q - 12; f = T->f34_1_8; }
             else             { band = 2 + ((q - 20) >> 2); sub = (q - 20) & 3; f = T->f34_2_4; }
             heaac_ps_hyb_cx(&sm->in[band][n], f[sub], &sm->L[q][n][0], &sm->L[q][n][1]);
-        }
-        for (int w = tid; w < 59 * 32; w += nt) {
-            int i = w >> 5, n = w & 31;
-            sm->L[i + 32][n][0] = Lre[(i + 5) * HEAAC_XS + n]; sm->L[i + 32][n][1] = Lim[(i + 5) * HEAAC_XS + n];
         }
     } else {
         for (int n = tid; n < 32; n += nt) {              /* hybrid6_cx + 2 x hybrid2_re */
@@ -563,10 +568,6 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                 sm->L[base + rev][n][0]  = re_in + re_op; sm->L[base + rev][n][1]  = im_in + im_op;
                 sm->L[base + !rev][n][0] = re_in - re_op; sm->L[base + !rev][n][1] = im_in - im_op;
             }
-        }
-        for (int w = tid; w < 61 * 32; w += nt) {
-            int i = w >> 5, n = w & 31;
-            sm->L[i + 10][n][0] = Lre[(i + 3) * HEAAC_XS + n]; sm->L[i + 10][n][1] = Lim[(i + 3) * HEAAC_XS + n];
         }
     }
     HEAAC_SYNC();
