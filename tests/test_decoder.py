@@ -104,7 +104,8 @@ def test_decoder_calls_chain_and_adts_input():
 
 
 @pytest.mark.gpu
-def test_decoder_survives_a_corrupt_packet():
+@pytest.mark.parametrize("gpu_parse", [False, True])
+def test_decoder_survives_a_corrupt_packet(gpu_parse):
     """A packet that fails to parse is reported through consumed[] and decoded as silence; the other streams of
     the batch are unaffected (the reference returns -1 for that packet only, aacdec.c:2064-2070)."""
     d = load_golden("lc_stereo_44k")
@@ -112,7 +113,7 @@ def test_decoder_survives_a_corrupt_packet():
     S = 3
     rows = [[p] * S for p in pk]
     rows[4] = [pk[4], b"\xff" * 40, pk[4]]
-    dec = open_for(d, S)
+    dec = open_for(d, S, gpu_parse=gpu_parse)
     pcm, _, consumed = dec.decode(hb.PacketBatch(rows))
     i = dec.info()
     dec.close()
@@ -168,3 +169,34 @@ def test_two_gpu_parse_decoders_share_the_device_tables():
     assert np.array_equal(pa, pb) and np.array_equal(pa, pc) and np.array_equal(pa, pa2)
     _, ref_s16 = golden_ref_pcm(d)
     assert int(np.abs(pa[:, 0].astype(np.int32) - ref_s16).max()) <= 1
+
+
+@pytest.mark.gpu
+def test_decoder_full_batch_properties():
+    """BASELINE-size batch (1024 HE-AAC v1 stereo streams x 32 frames) through the GPU-parse decoder: every packet
+    consumed completely, replicas of a fixture stream give identical PCM, distinct streams differ, and the whole
+    batch equals the host-parser decoder's output bit for bit."""
+    import os
+    from common import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "bench_heaac_v1_stereo_packets.npz"))
+    sizes, blob = z["pkt_sizes"], z["pkt_blob"].tobytes()
+    K, N = sizes.shape
+    ofs = np.concatenate([[0], np.cumsum(sizes.ravel())])
+    pk = [[blob[ofs[k * N + i]:ofs[k * N + i + 1]] for i in range(N)] for k in range(K)]
+    S, T = 1024, 32
+    batch = hb.PacketBatch([[pk[s % K][t] for s in range(S)] for t in range(T)])
+    ed, rate, ch = z["extradata"].tobytes(), int(z["core_rate"]), int(z["channels"])
+    gpu = hb.Decoder(S, ed, rate, ch, max_frames=T, gpu_parse=True)
+    a, _, ca = gpu.decode(batch)
+    ia = gpu.info()
+    gpu.close()
+    assert a.shape == (T, S, 2048, 2) and ia["parse_errors"] == 0
+    assert np.array_equal(ca, np.asarray([[sizes[s % K][t] for s in range(S)] for t in range(T)]))
+    for s in range(K, S, 97):
+        assert np.array_equal(a[:, s], a[:, s % K]), "replica %d differs from its source stream" % s
+    assert not np.array_equal(a[:, 0], a[:, 1])
+    assert int(np.abs(a.astype(np.int32)).max()) > 1000            # real audio, not silence
+    host = hb.Decoder(S, ed, rate, ch, max_frames=T)
+    b, _, cb = host.decode(batch)
+    host.close()
+    assert np.array_equal(ca, cb) and np.array_equal(a, b)
