@@ -194,3 +194,50 @@ def test_two_phase_parse_equals_one_pass(name):
             assert x[k].tobytes() == y[k].tobytes(), "%s frame %d: %s differs" % (name, t, k)
         assert not diff_parsed(x, y, a.ncc, bool(a.sbr), bool(a.ps)), (name, t)
     a.close(); b.close()
+
+
+def dump_fuzz_cases(path):
+    """cases.bin for tools/fuzz_frontend.c (the ASan / UBSan harness)."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("i", len(GOLDEN_CASES)))
+        for name in GOLDEN_CASES:
+            d = load_golden(name)
+            pk = golden_packets(d)
+            ch = d["pcm_f32"].shape[1] if not d["ps_flag"] else 1
+            ed = d["extradata"].tobytes()
+            f.write(struct.pack("iiii", len(ed), int(d["core_rate"]), ch, len(pk)) + ed)
+            for p in pk:
+                f.write(struct.pack("i", len(p)) + p)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_frontend_survives_corrupt_packets(name):
+    """Byte overwrites, truncations and bit flips: the parser either returns a frame or an error code, and the next
+    intact packet still parses (state stays usable).  tools/fuzz_frontend.c is the same loop under ASan/UBSan."""
+    d = load_golden(name)
+    pk = golden_packets(d)
+    ch = d["pcm_f32"].shape[1] if not d["ps_flag"] else 1
+    rng = np.random.default_rng(7)
+    errors = 0
+    for it in range(25):
+        fe = hb.Frontend(d["extradata"].tobytes(), int(d["core_rate"]), ch)
+        for i, p in enumerate(pk):
+            b = bytearray(p)
+            mode = int(rng.integers(0, 3))
+            if mode == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif mode == 1:
+                b = b[:int(rng.integers(1, len(b)))]
+            else:
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                fe.parse(bytes(b), two_phase=bool(it & 1))
+            except hb.HeaacError as e:
+                assert e.code in (-22, -38)
+                errors += 1
+        r = fe.parse(pk[-1])                           # an intact packet afterwards
+        assert r["consumed"] == len(pk[-1])
+        fe.close()
+    assert errors > 0
