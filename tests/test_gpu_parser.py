@@ -61,3 +61,45 @@ def test_gpu_parser_equals_host_parser_structures():
     gpu.close(); host.close()
     assert np.array_equal(ca, cb) and (ca > 0).all()
     assert np.array_equal(a, b), "PCM of the GPU-parse and host-parse decoders differs"
+
+
+@pytest.mark.parametrize("name", ["lc_51_tns_rich", "heaac_v1_stereo", "heaac_v2_ps"])
+def test_device_front_end_survives_corrupt_packets(name):
+    """Every stream of the batch gets its own corruption of the golden packets (overwrites, truncation, bit flips):
+    the call completes, failures come back through consumed[], PCM equals the host-parser decoder's for the same
+    corrupted input (both replace a failed frame by silence), and the decoder still decodes intact packets after.
+    (The same parser source runs under ASan/UBSan on the host: tools/fuzz_frontend.c.)"""
+    from common import golden_packets, load_golden
+    d = load_golden(name)
+    pk = golden_packets(d)
+    ch = d["pcm_f32"].shape[1] if not d["ps_flag"] else 1
+    S = 12
+    rng = np.random.default_rng(5)
+    rows = []
+    for p in pk:
+        row = []
+        for s in range(S):
+            b = bytearray(p)
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif mode == 1:
+                b = b[:int(rng.integers(1, len(b)))]
+            elif mode == 2:
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            row.append(bytes(b))
+        rows.append(row)
+    rows[0] = [pk[0]] * S                                  # the first packet configures the decoder
+    batch, good = hb.PacketBatch(rows), hb.PacketBatch([[p] * S for p in pk])
+    out = []
+    for gpu_parse in (True, False):
+        dec = hb.Decoder(S, d["extradata"].tobytes(), int(d["core_rate"]), ch, max_frames=len(pk), gpu_parse=gpu_parse)
+        pcm, _, cons = dec.decode(batch)
+        pcm2, _, cons2 = dec.decode(good)
+        dec.close()
+        assert (cons2 > 0).all()
+        out.append((pcm, cons, pcm2))
+    assert (out[0][1] < 0).any()
+    assert np.array_equal(out[0][1], out[1][1]), "consumed[] differs between the device and the host parser"
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2])
