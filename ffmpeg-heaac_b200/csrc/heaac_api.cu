@@ -3,11 +3,12 @@
  * synthesis back end.  sm_100a only; there is no CPU path: every entry point fails with
  * HEAAC_E_NODEV when no CUDA device is usable.
  *
- * One frame tick of a batch = up to four launches, each with one CTA per unit of work:
- *   k_core   one CTA per core channel   TNS + IMDCT + window + overlap-add   (aacdec.c:1698-1806)
- *   k_sbr    one CTA per SBR channel    QMF analysis .. X generation         (aacsbr.c:1089-1714)
- *   k_ps     one CTA per PS stream      hybrid analysis .. hybrid synthesis  (aacps.c:283-992)
- *   k_synth  one CTA per output channel QMF synthesis + float->s16           (aacsbr.c:1175-1230)
+ * One frame tick of a batch = up to five launches:
+ *   k_tns    one thread per TNS chain     all-pole filters, registers only (pre-pass)   (aacdec.c:1698-1736)
+ *   k_core   persistent, claims channels  IMDCT + window + overlap-add (+ QMF analysis)  (aacdec.c:1741-1806, aacsbr.c:1136-1169)
+ *   k_sbr    one CTA per SBR channel      X_low .. HF generation / adjustment .. X       (aacsbr.c:1089-1714)
+ *   k_ps     one CTA per PS stream        hybrid analysis .. hybrid synthesis            (aacps.c:283-992)
+ *   k_synth  one CTA per SBR element      QMF synthesis + float->s16                     (aacsbr.c:1175-1230)
  * All per-stream state stays in HBM between launches (heaac_dev.cuh).
  */
 #include <cuda_runtime.h>
