@@ -397,9 +397,7 @@ struct HeaacPsSmem {
     float L[91][HEAAC_PS_NS][2];    /* Lbuf: hybrid-domain mono signal, then left output */
     float R[91][HEAAC_PS_NS][2];    /* Rbuf: decorrelated signal, then right output */
     float in[5][44][2];             /* in_buf: 6 history + 38 new slots of QMF bands 0..4 */
-    float power[34][HEAAC_PS_NS];
-    float tgain[34][HEAAC_PS_NS];
-    float H[4][2][6][34];           /* H11,H12,H21,H22 [re/im][envelope 0..5][band] */
+    float power[34][HEAAC_PS_NS];   /* per parameter band and slot: the power, then (in place) the transient gain */
     int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
     HeaacPsFrame p;
 };
@@ -595,7 +593,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
             psm += 0.25f * (pw - psm);
             pds += 0.25f * (pdn - pw - pds);
             float denom = 1.5f * pds;
-            sm->tgain[i][n] = (denom > psm) ? heaac_fdiv(psm, denom) : 1.0f;
+            sm->power[i][n] = (denom > psm) ? heaac_fdiv(psm, denom) : 1.0f;
         }
         st->peak_decay_nrg[i] = pdn; st->power_smooth[i] = psm; st->peak_decay_diff_smooth[i] = pds;
     }
@@ -644,8 +642,8 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                     for (int j = 0; j < 4; j++) { ap[m][j][0] = ap[m][j + 1][0]; ap[m][j][1] = ap[m][j + 1][1]; }
                     ap[m][4][0] = nw_re; ap[m][4][1] = nw_im;
                 }
-                sm->R[k][n][0] = sm->tgain[b][n] * in_re;
-                sm->R[k][n][1] = sm->tgain[b][n] * in_im;
+                sm->R[k][n][0] = sm->power[b][n] * in_re;
+                sm->R[k][n][1] = sm->power[b][n] * in_im;
             }
             for (int m = 0; m < 3; m++)
                 for (int j = 0; j < 5; j++) { st->ap_delay[k][m][j][0] = ap[m][j][0]; st->ap_delay[k][m][j][1] = ap[m][j][1]; }
@@ -655,8 +653,8 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                 int pos = n + 14 - d;                     /* index into [hist(14) | this frame(32)] */
                 float d_re = pos < 14 ? hist[pos][0] : sm->L[k][pos - 14][0];
                 float d_im = pos < 14 ? hist[pos][1] : sm->L[k][pos - 14][1];
-                sm->R[k][n][0] = sm->tgain[b][n] * d_re;
-                sm->R[k][n][1] = sm->tgain[b][n] * d_im;
+                sm->R[k][n][0] = sm->power[b][n] * d_re;
+                sm->R[k][n][1] = sm->power[b][n] * d_im;
             }
         }
         for (int j = 0; j < 14; j++) { st->delay[k][j][0] = sm->L[k][18 + j][0]; st->delay[k][j][1] = sm->L[k][18 + j][1]; }
@@ -678,8 +676,9 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     /* ---- stereo_processing, aacps.c:794-971: H matrices ---- */
     for (int w = tid; w < 4 * 2 * 34; w += nt) {
         int h = w / 68, c = (w / 34) & 1, b = w % 34;
-        sm->H[h][c][0][b] = st->H[h][c][p->num_env_old][b];
-        for (int e = 1; e < 6; e++) sm->H[h][c][e][b] = st->H[h][c][e][b];
+        /* the matrices live in the stream's state block (all six rows persist: stale rows are re-read by later
+         * frames, aacps.c:816-823); row 0 becomes the previous frame's last envelope */
+        st->H[h][c][0][b] = st->H[h][c][p->num_env_old][b];
     }
     for (int w = tid; w < p->num_env * 34; w += nt) {
         int e = w / 34, b = w - e * 34;
@@ -693,7 +692,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     }
     HEAAC_SYNC();
     if (switched) {
-        for (int w = tid; w < 8; w += nt) heaac_ps_map_val(sm->H[w >> 1][w & 1][0], is34);
+        for (int w = tid; w < 8; w += nt) heaac_ps_map_val(st->H[w >> 1][w & 1][0], is34);
         for (int b = tid; b < 17; b += nt) { st->ipd_hist[b] = 0; st->opd_hist[b] = 0; }   /* ipdopd_reset, aacps.c:141-148 */
     }
     HEAAC_SYNC();
@@ -717,22 +716,18 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                     oh = opd_idx & 0x3F; ih = ipd_idx & 0x3F;
                     float adj_re = opd_re * ipd_re + opd_im * ipd_im;
                     float adj_im = opd_im * ipd_re - opd_re * ipd_im;
-                    sm->H[0][1][e + 1][b] = h11 * opd_im;  h11 = h11 * opd_re;
-                    sm->H[1][1][e + 1][b] = h12 * adj_im;  h12 = h12 * adj_re;
-                    sm->H[2][1][e + 1][b] = h21 * opd_im;  h21 = h21 * opd_re;
-                    sm->H[3][1][e + 1][b] = h22 * adj_im;  h22 = h22 * adj_re;
+                    st->H[0][1][e + 1][b] = h11 * opd_im;  h11 = h11 * opd_re;
+                    st->H[1][1][e + 1][b] = h12 * adj_im;  h12 = h12 * adj_re;
+                    st->H[2][1][e + 1][b] = h21 * opd_im;  h21 = h21 * opd_re;
+                    st->H[3][1][e + 1][b] = h22 * adj_im;  h22 = h22 * adj_re;
                 }
-                sm->H[0][0][e + 1][b] = h11; sm->H[1][0][e + 1][b] = h12;
-                sm->H[2][0][e + 1][b] = h21; sm->H[3][0][e + 1][b] = h22;
+                st->H[0][0][e + 1][b] = h11; st->H[1][0][e + 1][b] = h12;
+                st->H[2][0][e + 1][b] = h21; st->H[3][0][e + 1][b] = h22;
             }
             st->opd_hist[b] = (int8_t)oh; st->ipd_hist[b] = (int8_t)ih;
         }
     }
     HEAAC_SYNC();
-    for (int w = tid; w < 4 * 2 * 34; w += nt) {          /* persist H (all rows: stale rows are re-read by later frames) */
-        int h = w / 68, c = (w / 34) & 1, b = w % 34;
-        for (int e = 0; e < 6; e++) st->H[h][c][e][b] = sm->H[h][c][e][b];
-    }
     /* ---- mixing: one hybrid band per work item, serial over envelopes and slots ---- */
     for (int k = tid; k < nr_bands; k += nt) {
         const int b = k_to_i[k];
@@ -742,12 +737,12 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
             float width = heaac_fdiv(1.f, (float)(stop - start));
             float hr[4], hi[4], hrs[4], his[4];
             for (int h = 0; h < 4; h++) {
-                hr[h] = sm->H[h][0][e][b];
-                hrs[h] = (sm->H[h][0][e + 1][b] - hr[h]) * width;
+                hr[h] = st->H[h][0][e][b];
+                hrs[h] = (st->H[h][0][e + 1][b] - hr[h]) * width;
                 hi[h] = 0.0f; his[h] = 0.0f;
                 if (p->enable_ipdopd) {
-                    hi[h] = neg ? -sm->H[h][1][e][b] : sm->H[h][1][e][b];
-                    his[h] = (sm->H[h][1][e + 1][b] - hi[h]) * width;
+                    hi[h] = neg ? -st->H[h][1][e][b] : st->H[h][1][e][b];
+                    his[h] = (st->H[h][1][e + 1][b] - hi[h]) * width;
                 }
             }
             for (int n = start + 1; n <= stop; n++) {
