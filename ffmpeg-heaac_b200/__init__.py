@@ -39,6 +39,7 @@ EXPORTS = [
     "heaac_fe_parse_two_phase", "heaac_fe_copy_layout",
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
+    "heaac_b200_sbr_init", "heaac_b200_sbr_apply", "heaac_b200_ps_apply", "heaac_b200_sbr_close",
     "heaac_fe_sbr_downsampled", "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
@@ -113,6 +114,11 @@ def lib():
         L.heaac_adts_parse_header.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
         L.heaac_adts_split.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.heaac_esds_find_asc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.heaac_b200_sbr_init.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.heaac_b200_sbr_apply.argtypes = [C.c_void_p] * 5
+        L.heaac_b200_ps_apply.argtypes = [C.c_void_p] * 4 + [C.c_int]
+        L.heaac_b200_sbr_close.argtypes = [C.c_void_p]
+        L.heaac_b200_sbr_close.restype = None
         L.heaac_dec_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_longlong)] * 2
         L.heaac_dec_parse_kernel_ms.argtypes = [C.c_void_p]
         L.heaac_dec_parse_kernel_ms.restype = C.c_double

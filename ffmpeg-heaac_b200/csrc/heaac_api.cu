@@ -734,6 +734,133 @@ extern "C" int heaac_b200_debug_read(HeaacContext *c, const char *name, void *ds
     return heaac_b200_dev_download(c, dst, src, bytes) ? HEAAC_E_LAUNCH : (int)(bytes > 0x7fffffff ? 0x7fffffff : bytes);
 }
 
+/* ---- ff_sbr_apply / ff_ps_apply shims (batch of one) ---------------------------------------
+ * The reference's two stage entry points with plain arrays instead of its private structs: everything they keep
+ * between calls (QMF delay lines, W / Y tails, gain history, PS delay lines ...) lives in a one-stream context.
+ * For parity checks and incremental bring-up; the batched path does not go through them. */
+struct HeaacSbrShim {
+    HeaacContext *ctx;
+    float *d_time;                   /* [nch][1024] core output handed in */
+    HeaacSbrElem *d_elem;
+    HeaacPsFrame *d_psf;
+    float *d_out;                    /* [nout][2048] */
+    int nch, nout, ps;
+};
+
+/* QMF analysis alone, on time-domain input (what k_core does after the IMDCT): one CTA per channel */
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_ana(HeaacGeom g, const float *__restrict__ time, HeaacChanState *chan, float *W, const HeaacDevTables *__restrict__ T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *x = reinterpret_cast<float *>(smem_raw);     /* [288 history | 1024 new] + 64*33 scratch */
+    const int gc = blockIdx.x;
+    HeaacChanState *st = chan + gc;
+    const float ana_scale = 1 / (-1024.0f * g.sf_scale);                       /* aacsbr.c:1730 */
+    for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
+    for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) {
+        const float v = time[(size_t)gc * 1024 + i];
+        x[288 + i] = ana_scale != 1.0f ? v * ana_scale : v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
+    heaac_qmf_analysis<HEAAC_THREADS>(x, x + 1312, W + (size_t)gc * 2048, T, threadIdx.x);
+}
+
+extern "C" int heaac_b200_sbr_init(HeaacSbrShim **out, int id_aac, int core_sr_index, int ps, float sf_scale, float add_bias)
+{
+    if (!out || (id_aac != HEAAC_TYPE_SCE && id_aac != HEAAC_TYPE_CPE) || (ps && id_aac != HEAAC_TYPE_SCE)) return HEAAC_E_INVAL;
+    HeaacSbrShim *s = (HeaacSbrShim *)calloc(1, sizeof(*s));
+    if (!s) return HEAAC_E_NOMEM;
+    HeaacConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = HEAAC_ABI_VERSION; cfg.n_streams = 1; cfg.n_elems = 1; cfg.elem_type[0] = (uint8_t)id_aac;
+    cfg.sr_index = core_sr_index; cfg.sbr = 1; cfg.ps = ps ? 1 : 0; cfg.add_bias = add_bias; cfg.sf_scale = sf_scale;
+    cfg.max_frames_per_call = 1; cfg.want_float_out = 1;
+    int r = heaac_b200_create(&cfg, &s->ctx);
+    if (r) { free(s); return r; }
+    s->nch = id_aac == HEAAC_TYPE_CPE ? 2 : 1; s->nout = ps ? 2 : s->nch; s->ps = ps ? 1 : 0;
+    if (cudaMalloc(&s->d_time, sizeof(float) * 2 * 1024) != cudaSuccess || cudaMalloc(&s->d_elem, sizeof(HeaacSbrElem)) != cudaSuccess ||
+        cudaMalloc(&s->d_psf, sizeof(HeaacPsFrame)) != cudaSuccess || cudaMalloc(&s->d_out, sizeof(float) * 2 * 2048) != cudaSuccess) {
+        cudaGetLastError();
+        heaac_b200_destroy(s->ctx); cudaFree(s->d_time); cudaFree(s->d_elem); cudaFree(s->d_psf); cudaFree(s->d_out); free(s);
+        return HEAAC_E_NOMEM;
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" void heaac_b200_sbr_close(HeaacSbrShim *s)
+{
+    if (!s) return;
+    cudaFree(s->d_time); cudaFree(s->d_elem); cudaFree(s->d_psf); cudaFree(s->d_out);
+    heaac_b200_destroy(s->ctx);
+    free(s);
+}
+
+/* == ff_sbr_apply(ac, sbr, id_aac, L, R), aacsbr.c:1716-1771.  L (and R for a CPE) hold the 1024 core samples of the
+ * frame on entry (the element's ret[] after imdct_and_windowing) and the 2048 output samples on exit; with PS, R is
+ * output only.  `elem` is the element's SBR side info for this frame, `psf` the PS side info (PS streams). */
+extern "C" int heaac_b200_sbr_apply(HeaacSbrShim *s, const HeaacSbrElem *elem, const HeaacPsFrame *psf, float *L, float *R)
+{
+    if (!s || !elem || !L || (s->nout == 2 && !R) || (s->ps && !psf)) return HEAAC_E_INVAL;
+    HeaacContext *c = s->ctx;
+    const HeaacGeom g = c->geom;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(s->d_time, L, sizeof(float) * 1024, cudaMemcpyHostToDevice, c->stream));
+    if (s->nch == 2) CK(cudaMemcpyAsync(s->d_time + 1024, R, sizeof(float) * 1024, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(s->d_elem, elem, sizeof(HeaacSbrElem), cudaMemcpyHostToDevice, c->stream));
+    if (s->ps) CK(cudaMemcpyAsync(s->d_psf, psf, sizeof(HeaacPsFrame), cudaMemcpyHostToDevice, c->stream));
+    k_ana<<<s->nch, HEAAC_THREADS, (1312 + 64 * 33) * sizeof(float), c->stream>>>(g, s->d_time, c->d_chan, c->d_W, c->d_tables);
+    k_sbr<<<s->nch, HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(g, c->d_W, s->d_elem, c->d_chan, c->d_X, c->d_tables);
+    if (s->ps) k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
+    k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables);
+    c->launches += 3 + s->ps;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(L, s->d_out, sizeof(float) * 2048, cudaMemcpyDeviceToHost, c->stream));
+    if (s->nout == 2) CK(cudaMemcpyAsync(R, s->d_out + 2048, sizeof(float) * 2048, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* == ff_ps_apply(avctx, ps, L, R, top), aacps.c:973-992: L[2][38][64] (re / im planes, slot, QMF band) is processed in
+ * place for slots 0..31 (slots 32..37 are look-ahead), R[2][38][64] receives the second channel.  Uses the PS state
+ * of a shim created with ps = 1. */
+extern "C" int heaac_b200_ps_apply(HeaacSbrShim *s, const HeaacPsFrame *psf, float *L, float *R, int top)
+{
+    if (!s || !s->ps || !psf || !L || !R || top < 0 || top > 64) return HEAAC_E_INVAL;
+    HeaacContext *c = s->ctx;
+    const HeaacGeom g = c->geom;
+    CK(cudaSetDevice(c->cfg.device));
+    float *h = (float *)calloc(2 * HEAAC_X_FLOATS, sizeof(float));
+    if (!h) return HEAAC_E_NOMEM;
+    for (int pl = 0; pl < 2; pl++)                         /* reference [plane][slot][band] -> device [plane][band][slot] */
+        for (int i = 0; i < 38; i++)
+            for (int k = 0; k < 64; k++) h[pl * HEAAC_X_PLANE + k * HEAAC_XS + i] = L[(pl * 38 + i) * 64 + k];
+    HeaacSbrElem e;
+    memset(&e, 0, sizeof(e));
+    e.kx[1] = (uint8_t)top;                               /* k_ps derives `top` as kx + m */
+    int r = heaac_cuda_err(cudaMemcpyAsync(c->d_X, h, sizeof(float) * HEAAC_X_FLOATS, cudaMemcpyHostToDevice, c->stream), "upload X");
+    if (!r) r = heaac_cuda_err(cudaMemcpyAsync(s->d_elem, &e, sizeof(e), cudaMemcpyHostToDevice, c->stream), "upload elem");
+    if (!r) r = heaac_cuda_err(cudaMemcpyAsync(s->d_psf, psf, sizeof(HeaacPsFrame), cudaMemcpyHostToDevice, c->stream), "upload ps");
+    if (!r) {
+        k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
+        c->launches++;
+        r = heaac_cuda_err(cudaGetLastError(), "k_ps");
+    }
+    if (!r) r = heaac_cuda_err(cudaMemcpyAsync(h, c->d_X, sizeof(float) * 2 * HEAAC_X_FLOATS, cudaMemcpyDeviceToHost, c->stream), "download X");
+    if (!r) r = heaac_cuda_err(cudaStreamSynchronize(c->stream), "sync");
+    if (!r)
+        for (int ch = 0; ch < 2; ch++) {
+            float *dst = ch ? R : L;
+            for (int pl = 0; pl < 2; pl++)
+                for (int i = 0; i < 32; i++)
+                    for (int k = 0; k < 64; k++)
+                        dst[(pl * 38 + i) * 64 + k] = h[ch * HEAAC_X_FLOATS + pl * HEAAC_X_PLANE + k * HEAAC_XS + i];
+        }
+    free(h);
+    return r;
+}
+
 /* ---- ff_mdct_init / ff_imdct_half / ff_mdct_end shims (batch of one) -------------------- */
 struct HeaacMdct {
     int nbits; float *d_tcos, *d_tsin, *d_in, *d_out; HeaacDevTables *d_tables; cudaStream_t stream;

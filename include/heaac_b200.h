@@ -398,6 +398,19 @@ int  heaac_b200_mdct_init(HeaacMdct **s, int nbits, int inverse, double scale);
 void heaac_b200_imdct_half(HeaacMdct *s, float *output, const float *input);  /* host pointers, N/2 in, N/2 out */
 void heaac_b200_mdct_end(HeaacMdct *s);
 
+/* ff_sbr_apply / ff_ps_apply (aacsbr.h:45-46, aacps.h:80) with plain arrays; the state the reference keeps inside
+ * SpectralBandReplication / PSContext between calls lives in the shim (one stream).
+ *   sbr_init  ~ ff_aac_sbr_ctx_init (+ ff_ps_ctx_init when ps): id_aac = HEAAC_TYPE_SCE / _CPE, core sampling index,
+ *               scaling convention as in HeaacConfig
+ *   sbr_apply ~ ff_sbr_apply(ac, sbr, id_aac, L, R): L (and R for a CPE) = the element's ret[]: 1024 core samples in,
+ *               2048 output samples out; with PS, R is output only.  elem / psf = this frame's side info.
+ *   ps_apply  ~ ff_ps_apply(avctx, ps, L, R, top): L[2][38][64] in place for slots 0..31, R[2][38][64] out. */
+typedef struct HeaacSbrShim HeaacSbrShim;
+int  heaac_b200_sbr_init(HeaacSbrShim **s, int id_aac, int core_sr_index, int ps, float sf_scale, float add_bias);
+int  heaac_b200_sbr_apply(HeaacSbrShim *s, const HeaacSbrElem *elem, const HeaacPsFrame *psf, float *L, float *R);
+int  heaac_b200_ps_apply(HeaacSbrShim *s, const HeaacPsFrame *psf, float *L, float *R, int top);
+void heaac_b200_sbr_close(HeaacSbrShim *s);
+
 /* sizeof() of an ABI or device-state struct by name ("HeaacSbrElem", ...), -1 if unknown; lets
  * language bindings assert that their struct mirrors match this build. */
 int  heaac_b200_sizeof(const char *name);

@@ -196,3 +196,79 @@ def test_imdct_shim_matches_ff_imdct_half(hb):
         got = t.imdct_half(x)
         t.close()
         assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+class SbrShim:
+    """ctypes wrapper of the ff_sbr_apply / ff_ps_apply shims (heaac_b200_sbr_*)."""
+
+    def __init__(self, hb, id_aac, sr_index, ps):
+        import ctypes as C
+        self.L, self.C = hb.lib(), C
+        h = C.c_void_p()
+        r = self.L.heaac_b200_sbr_init(C.byref(h), id_aac, sr_index, int(ps), -1.0 / 1024.0, 0.0)
+        assert r == 0, r
+        self.h = h
+
+    def sbr_apply(self, elem, psf, L, R):
+        r = self.L.heaac_b200_sbr_apply(self.h, elem.ctypes.data, psf.ctypes.data if psf is not None else None,
+                                        L.ctypes.data, R.ctypes.data if R is not None else None)
+        assert r == 0, r
+
+    def ps_apply(self, psf, L, R, top):
+        r = self.L.heaac_b200_ps_apply(self.h, psf.ctypes.data, L.ctypes.data, R.ctypes.data, top)
+        assert r == 0, r
+
+    def close(self):
+        self.L.heaac_b200_sbr_close(self.h)
+
+
+@pytest.mark.parametrize("name", ["heaac_v1_stereo", "heaac_v2_ps"])
+def test_sbr_apply_shim_matches_reference(hb, name):
+    """heaac_b200_sbr_apply == ff_sbr_apply (aacsbr.c:1716-1771): fed with the core decoder's time-domain output and the
+    frame's side info, frame by frame, it reproduces the reference decoder's float PCM and the batched path exactly."""
+    d = load_golden(name)
+    T = d["coeffs"].shape[0]
+    et = [int(x) for x in d["elem_types"]]
+    ps = bool(d["ps_flag"])
+    lc = abi.make_config(1, et, int(d["sr_index"]), sbr=False, ps=False, max_frames=T)
+    args = golden_args(d)
+    _, ret = run_cuda(hb, lc, (args[0], args[1], args[2], None, None))       # [T, 1, ncc, 1024]: the elements' ret[]
+    _, full = run_cuda(hb, golden_config(d), args)                           # batched path, float PCM [T, 1, nout, 2048]
+    shim = SbrShim(hb, et[0], int(d["sr_index"]), ps)
+    ref_f32, _ = golden_ref_pcm(d)
+    for t in range(T):
+        L = np.zeros(2048, np.float32); R = np.zeros(2048, np.float32)
+        L[:1024] = ret[t, 0, 0]
+        if ret.shape[2] > 1:
+            R[:1024] = ret[t, 0, 1]
+        shim.sbr_apply(np.ascontiguousarray(d["sbr"][t, 0:1]), np.ascontiguousarray(d["ps"][t, 0:1]) if ps else None, L, R)
+        out = np.stack([L, R])
+        assert np.array_equal(out, full[t, 0]), "frame %d: shim differs from the batched path" % t
+        assert float(np.abs(out.astype(np.float64) - ref_f32[t]).max()) / FULL_SCALE <= TOL_FS
+    shim.close()
+
+
+def test_ps_apply_shim_matches_batched_path(hb):
+    """heaac_b200_ps_apply == ff_ps_apply (aacps.c:973-992) on the reference's own array layout L/R[2][38][64]: its
+    output equals what k_ps leaves in the batched path's X buffers, frame by frame."""
+    d = load_golden("heaac_v2_ps")
+    T = d["coeffs"].shape[0]
+    XS, PLANE = 40, 64 * 40
+    args = golden_args(d)
+    pre = hb.Context(abi.make_config(1, [abi.TYPE_SCE], int(d["sr_index"]), sbr=True, ps=False, max_frames=1))
+    post = hb.Context(golden_config(d, max_frames=1))
+    shim = SbrShim(hb, abi.TYPE_SCE, int(d["sr_index"]), True)
+    for t in range(T):
+        one = [a[t:t + 1] if a is not None else None for a in args]
+        pre.synth(one[0], one[1], one[2], one[3], None)
+        post.synth(*one)
+        x = pre.debug_read("X", np.float32, (1, 2, 64, XS))                 # before PS: [ch 0][plane][band][slot]
+        y = post.debug_read("X", np.float32, (2, 2, 64, XS))                # after PS:  [ch][plane][band][slot]
+        L = np.ascontiguousarray(x[0, :, :, :38].transpose(0, 2, 1))        # -> [plane][slot 38][band 64]
+        R = np.zeros_like(L)
+        e = d["sbr"][t, 0]
+        shim.ps_apply(np.ascontiguousarray(d["ps"][t, 0:1]), L, R, int(e["kx"][1]) + int(e["m"][1]))
+        for ch, got in ((0, L), (1, R)):
+            want = y[ch, :, :, :32].transpose(0, 2, 1)
+            assert np.array_equal(got[:, :32], want), "frame %d channel %d" % (t, ch)
+    pre.close(); post.close(); shim.close()
