@@ -168,7 +168,8 @@ def test_frontend_adts_framing_equals_raw_with_extradata(name, chan_config):
     raw.close(); adts.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES + ("bench_heaac_v1_stereo_packets", "bench_heaac_v2_ps_packets"))
+@pytest.mark.parametrize("name", GOLDEN_CASES + ("bench_heaac_v1_stereo_packets", "bench_heaac_v2_ps_packets",
+                                                 "bench_lc_51_48k_tns_packets", "bench_lc_stereo_44k_packets"))
 def test_two_phase_parse_equals_one_pass(name):
     """fe_phase_a + fe_phase_b (how the device front end spreads frames over lanes) == heaac_fe_parse, byte for byte,
     including streams with PNS (serial fallback), common_window transitions and looped bench fixtures."""
