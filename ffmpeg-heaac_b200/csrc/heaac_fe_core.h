@@ -478,7 +478,9 @@ FE_FN int spectrum(FE *fe, FeChan *c, BR *b, float *coef, int pulse_present, con
         for (int i = 0; i < npulse; i++) {
             float co = base[ppos[i]];
             while (off[idx + 1] <= ppos[i]) idx++;
-            if (c->band_type[idx] != 13 && c->sf[idx]) {
+            /* (a pulse beyond max_sfb would be scaled by whatever an EARLIER frame left in band_type / sf in the reference,
+             *  aacdec.c:1226; such streams are not conformant -- here the pulse is dropped, on every path alike) */
+            if (idx < c->max_sfb && c->band_type[idx] != 13 && c->sf[idx]) {
                 float ico = -pamp[i];
                 if (co) {
                     co /= c->sf[idx];

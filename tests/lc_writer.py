@@ -195,9 +195,10 @@ class LcWriter:
         sfb = int(r.integers(0, info["max_sfb"]))
         pos = int(info["swb"][sfb])
         offs = []
+        limit = int(info["swb"][info["max_sfb"]]) - 1     # conformant streams keep their pulses inside the coded bands
         for _ in range(n):
             o = int(r.integers(0, 32))
-            if pos + o > 1023:
+            if pos + o > limit:
                 break
             pos += o
             offs.append(o)
