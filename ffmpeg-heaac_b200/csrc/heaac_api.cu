@@ -97,13 +97,13 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
         const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
         float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
         if (threadIdx.x == 0) s_claim[(it + 1) & 1] = (int)atomicAdd(&work[0], 1u);
-        if (ana)
-            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
         heaac_cp_async_wait<0>();                    /* this channel's coefficients have landed */
         __syncthreads();
         const int gn = s_claim[(it + 1) & 1];
         if (gn < n_channels)
             heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
+        if (ana)                                     /* the analysis history is not needed before the IMDCT is done */
+            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) heaac_cp_async4(x + i, st->ana_hist + i);
         heaac_cp_async_commit();
         heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
                                           tns_done ? tns_done + (size_t)gc * 1024 : nullptr,
@@ -111,10 +111,10 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
         if (ana) {
             /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
             const float ana_scale = 1 / (-1024.0f * g.sf_scale);               /* aacsbr.c:1730 */
-            if (ana_scale != 1.0f) {
+            if (ana_scale != 1.0f)
                 for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) out[i] = out[i] * ana_scale;
-                __syncthreads();
-            }
+            heaac_cp_async_wait<0>();                /* history (and the next channel's coefficients) */
+            __syncthreads();
             for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
             float *tb = x + 1312;
             heaac_qmf_analysis<HEAAC_THREADS>(x, tb, W + (size_t)gc * 2048, T, threadIdx.x);
