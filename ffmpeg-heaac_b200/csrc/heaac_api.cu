@@ -85,6 +85,7 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
     float *x = stage + 2048;                         /* [288 history | 1024 new] (+ 64*33 analysis scratch) */
     float *out = x + 288;
     const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
+    asm volatile("griddepcontrol.launch_dependents;");   /* k_sbr's CTAs move in as this grid's leave, and wait */
     if (threadIdx.x == 0) s_claim[0] = (int)atomicAdd(&work[0], 1u);
     __syncthreads();
     int gc = s_claim[0];
@@ -133,8 +134,14 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
         gc = gn;
     }
     if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; }
+    /* launched early behind the previous frame's k_synth (programmatic dependent launch): nothing here reads what that
+     * kernel writes, but this grid must not retire before it, so that k_sbr -- which overwrites X -- stays behind it */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+#ifndef HEAAC_PDL
+#define HEAAC_PDL 1
+#endif
 #ifndef HEAAC_SBR_MIN_BLOCKS
 #define HEAAC_SBR_MIN_BLOCKS 5
 #endif
@@ -147,6 +154,8 @@ k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__
     const int gc = blockIdx.x;
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   /* W of this frame: k_core has retired */
+    asm volatile("griddepcontrol.launch_dependents;");
     if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
     float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
     heaac_hf_channel<HEAAC_SBR_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
@@ -177,6 +186,8 @@ k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
     /* one CTA per (stream, SBR element): its 1 or 2 output channels */
     const int s = blockIdx.x / g.nse, e = blockIdx.x - s * g.nse;
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   /* X of this frame: k_sbr / k_ps have retired */
+    asm volatile("griddepcontrol.launch_dependents;");   /* the next frame's k_core may fill this grid's last wave */
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
     if (g.ds)
@@ -426,6 +437,23 @@ extern "C" long long heaac_b200_launch_count(const HeaacContext *c) { return c ?
 extern "C" uintptr_t heaac_b200_stream(const HeaacContext *c) { return c ? (uintptr_t)c->stream : 0; }
 
 /* launches for frames [0, n) of a device-resident batch */
+/* Kernel launch, optionally as a programmatic dependent launch: with `early` the grid may begin once every CTA of the
+ * kernel before it in the stream has executed griddepcontrol.launch_dependents (or left); whatever it reads from that
+ * kernel it reads behind its own griddepcontrol.wait.  The chain per frame is k_core -> k_sbr -> (k_ps) -> k_synth ->
+ * next k_core: k_sbr and k_synth wait first thing (which hides their launch latency), k_core -- which needs nothing
+ * k_synth wrote -- waits last thing, so that its real work fills the tail of the synthesis grid. */
+template <typename... P, typename... A>
+static cudaError_t heaac_launch(bool early, void (*kern)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A... args)
+{
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = early ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kern, static_cast<P>(args)...);
+}
+
 int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
                          const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32)
 {
@@ -446,17 +474,20 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
                 c->launches++;
             }
             const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
-            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(
-                g, (int)n_ch, co, ic, tn, c->d_chan, c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work,
-                tn ? c->d_tns_done : nullptr);
+            /* behind a k_synth of the same batch (no k_tns, no profiling event in between) the core transform of the
+             * next frame depends on nothing that kernel writes: let it start while k_synth's last wave drains */
+            const bool early = HEAAC_PDL && g.sbr && f > 0 && !(tn && c->d_tns_done) && !c->prof_on;
+            CK(heaac_launch(early, k_core, grid, HEAAC_THREADS, c->smem_core, c->stream, g, (int)n_ch, co, ic, tn, c->d_chan,
+                            c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work,
+                            tn ? c->d_tns_done : nullptr));
         }
         prof_end(c);
         c->launches++;
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
             prof_begin(c, HEAAC_K_SBR);
-            k_sbr<<<(unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(
-                g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables);
+            CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_sbr, (unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream,
+                            g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables));
             prof_end(c);
             c->launches++;
             if (g.ps) {
@@ -467,8 +498,8 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            k_synth<<<(unsigned)(S * g.nse), 128, c->smem_synth, c->stream>>>(
-                g, c->d_X, c->d_synth, pc, pf, c->d_tables);
+            CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_synth, (unsigned)(S * g.nse), 128, c->smem_synth, c->stream,
+                            g, c->d_X, c->d_synth, pc, pf, c->d_tables));
             prof_end(c);
             c->launches++;
         }

@@ -64,10 +64,13 @@ struct HeaacGpuParser {
  *   k_parse_b  lane 0 walks the frames in order on the stream's persistent state (window history, SBR / PS payloads);
  *              the whole warp packs the result.
  * They run on two CUDA streams, so phase B of chunk k overlaps phase A of chunk k+1. */
-#ifndef HEAAC_PARSE_MIN_BLOCKS
-#define HEAAC_PARSE_MIN_BLOCKS 3
+#ifndef HEAAC_PARSE_THREADS
+#define HEAAC_PARSE_THREADS 128
 #endif
-__global__ void __launch_bounds__(128, HEAAC_PARSE_MIN_BLOCKS)
+#ifndef HEAAC_PARSE_MIN_BLOCKS
+#define HEAAC_PARSE_MIN_BLOCKS (384 / HEAAC_PARSE_THREADS)
+#endif
+__global__ void __launch_bounds__(HEAAC_PARSE_THREADS, HEAAC_PARSE_MIN_BLOCKS)
 k_parse_a(const FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, const uint8_t *blob, const uint32_t *off,
           const int *size, int n_frames, int S, int ncc, float *coeffs, HeaacIcs *ics, HeaacTns *tns)
 {
@@ -78,7 +81,7 @@ k_parse_a(const FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, 
                blob + off[idx], size[idx], coeffs + idx * ncc * 1024, ics + idx * ncc, tns + idx * ncc);
 }
 
-__global__ void __launch_bounds__(128, HEAAC_PARSE_MIN_BLOCKS)
+__global__ void __launch_bounds__(HEAAC_PARSE_THREADS, HEAAC_PARSE_MIN_BLOCKS)
 k_parse_b(FE *fes, const FeTodo *todo, const uint8_t *blob, const uint32_t *off, const int *size, int n_frames, int S,
           int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr,
           HeaacPsFrame *ps, int *consumed)
@@ -301,7 +304,7 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
         if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][0], c->s_in));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));      /* d_consumed[buf] drained */
         {
-            const int threads = 128, warps_per_cta = threads / 32;
+            const int threads = HEAAC_PARSE_THREADS, warps_per_cta = threads / 32;
             const int grid = (int)((S + warps_per_cta - 1) / warps_per_cta);
             if (!p->timed[buf]) CK(cudaEventRecord(p->ev_k0[buf], c->s_in));
             k_parse_a<<<grid, threads, 0, c->s_in>>>(p->d_fe, p->d_scratch, p->scratch_stride, p->d_todo[buf], p->d_blob[buf],
