@@ -142,12 +142,15 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
 #ifndef HEAAC_PDL
 #define HEAAC_PDL 1
 #endif
+#ifndef HEAAC_SBR_FLAGS
+#define HEAAC_SBR_FLAGS 1
+#endif
 #ifndef HEAAC_SBR_MIN_BLOCKS
 #define HEAAC_SBR_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(HEAAC_SBR_THREADS, HEAAC_SBR_MIN_BLOCKS)
 k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__ sbr,
-      HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T)
+      HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T, unsigned *done, unsigned tick)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacHfSmem *sm = reinterpret_cast<HeaacHfSmem *>(smem_raw);
@@ -160,6 +163,13 @@ k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__
     float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
     heaac_hf_channel<HEAAC_SBR_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
                      g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x);
+    if (done) {                                      /* X of this channel is complete: its k_synth CTA may go */
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(done + gc), "r"(tick) : "memory");
+        }
+    }
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)
@@ -178,15 +188,30 @@ k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__res
 #define HEAAC_SYNTH_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, HEAAC_SYNTH_MIN_BLOCKS)
-k_synth(HeaacGeom g, const float *__restrict__ X, HeaacSynthState *synth,
-        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
+k_synth(HeaacGeom g, const float *X, HeaacSynthState *synth,
+        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, const unsigned *sbr_done, unsigned tick)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacSynthSmem *sm = reinterpret_cast<HeaacSynthSmem *>(smem_raw);
     /* one CTA per (stream, SBR element): its 1 or 2 output channels */
     const int s = blockIdx.x / g.nse, e = blockIdx.x - s * g.nse;
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
-    asm volatile("griddepcontrol.wait;" ::: "memory");   /* X of this frame: k_sbr / k_ps have retired */
+    if (sbr_done) {
+        /* started while k_sbr's last wave is still running: wait for the channels of this element only.  (Every k_sbr
+         * CTA is resident or gone by the time this grid is launched, so the flags do arrive.) */
+        if ((int)threadIdx.x < nch) {
+            const unsigned *f = sbr_done + (size_t)s * g.ncc + c0 + threadIdx.x;
+            unsigned v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v == tick) break;
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");   /* X of this frame: k_sbr / k_ps have retired */
+    }
     asm volatile("griddepcontrol.launch_dependents;");   /* the next frame's k_core may fill this grid's last wave */
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
@@ -345,6 +370,8 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (!getenv("HEAAC_NO_TNS_PREPASS")) CKX(cudaMalloc(&c->d_tns_done, S * g->ncc * 1024 * sizeof(float)));
     CKX(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
     CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
+    CKX(cudaMalloc(&c->d_sbr_done, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
+    CKX(cudaMemset(c->d_sbr_done, 0, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
         CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
@@ -403,7 +430,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_tns_done);
+    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_sbr_done); cudaFree(c->d_tns_done);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
         cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
@@ -485,9 +512,12 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         c->launches++;
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
+            /* without PS, k_synth starts per element on k_sbr's per-channel flags instead of behind the whole grid */
+            unsigned *flags = HEAAC_PDL && HEAAC_SBR_FLAGS && !c->prof_on && !g.ps ? c->d_sbr_done : nullptr;
+            const unsigned tick = ++c->tick;
             prof_begin(c, HEAAC_K_SBR);
             CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_sbr, (unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream,
-                            g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables));
+                            g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables, flags, tick));
             prof_end(c);
             c->launches++;
             if (g.ps) {
@@ -499,7 +529,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             }
             prof_begin(c, HEAAC_K_SYNTH);
             CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_synth, (unsigned)(S * g.nse), 128, c->smem_synth, c->stream,
-                            g, c->d_X, c->d_synth, pc, pf, c->d_tables));
+                            g, c->d_X, c->d_synth, pc, pf, c->d_tables, flags, tick));
             prof_end(c);
             c->launches++;
         }
@@ -842,9 +872,9 @@ extern "C" int heaac_b200_sbr_apply(HeaacSbrShim *s, const HeaacSbrElem *elem, c
     CK(cudaMemcpyAsync(s->d_elem, elem, sizeof(HeaacSbrElem), cudaMemcpyHostToDevice, c->stream));
     if (s->ps) CK(cudaMemcpyAsync(s->d_psf, psf, sizeof(HeaacPsFrame), cudaMemcpyHostToDevice, c->stream));
     k_ana<<<s->nch, HEAAC_THREADS, (1312 + 64 * 33) * sizeof(float), c->stream>>>(g, s->d_time, c->d_chan, c->d_W, c->d_tables);
-    k_sbr<<<s->nch, HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(g, c->d_W, s->d_elem, c->d_chan, c->d_X, c->d_tables);
+    k_sbr<<<s->nch, HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(g, c->d_W, s->d_elem, c->d_chan, c->d_X, c->d_tables, nullptr, 0u);
     if (s->ps) k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
-    k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables);
+    k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables, nullptr, 0u);
     c->launches += 3 + s->ps;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(L, s->d_out, sizeof(float) * 2048, cudaMemcpyDeviceToHost, c->stream));

@@ -19,6 +19,8 @@ struct HeaacContext {
     HeaacPsState *d_ps;              /* [S] (PS only) */
     float *d_tns_done;               /* [S][ncc][1024]: TNS-filtered coefficient ranges of the current tick (k_tns -> k_core) */
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
+    unsigned *d_sbr_done;            /* per coded channel: tick of the last frame k_sbr finished (k_synth's start signal) */
+    unsigned tick;                   /* frames launched so far */
     float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
     float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
     /* staging for host-pointer batches, sized for max_frames_per_call */

@@ -21,6 +21,7 @@
 #ifdef HEAAC_HOST_EMU
 #define HEAAC_DEV   static inline
 #define HEAAC_SYNC() ((void)0)
+#define HEAAC_LDX(p) (*(p))
 #define HEAAC_RESTRICT
 #include <math.h>
 #include <string.h>
@@ -33,6 +34,9 @@ static inline float heaac_rint(float a) { return rintf(a); }
 #elif defined(__CUDACC__)
 #define HEAAC_DEV   __device__ __forceinline__
 #define HEAAC_SYNC() __syncthreads()
+/* X may still be being written elsewhere in the grid before (k_sbr / k_synth overlap through per-channel flags): read
+ * it through L2, never through the non-coherent path */
+#define HEAAC_LDX(p) __ldcg(p)
 #define HEAAC_RESTRICT __restrict__
 /* IEEE round-to-nearest, never contracted into FMA: used where the reference's result is
  * order-sensitive (aacsbr.c:1259 "does not seem numerically stable") */

@@ -834,11 +834,11 @@ HEAAC_DEV void heaac_synth_stream(HeaacSynthSmem *sm, const float *HEAAC_RESTRIC
         float b1[64];
         if (act && plane == 0) {
             heaac_imdct128_reg<HEAAC_MDCT_SYN>(
-                [&](int j) { return x[j * HEAAC_XS]; },
+                [&](int j) { return HEAAC_LDX(x + j * HEAAC_XS); },
                 [&](int j, float b) { v[j] = b; });
         } else if (act) {
             heaac_imdct128_reg<HEAAC_MDCT_SYN>(
-                [&](int j) { float xv = x[j * HEAAC_XS]; return (j & 1) ? -xv : xv; },     /* aacsbr.c:1205-1207 */
+                [&](int j) { float xv = HEAAC_LDX(x + j * HEAAC_XS); return (j & 1) ? -xv : xv; },     /* aacsbr.c:1205-1207 */
                 [&](int j, float b) { b1[j] = b; });
         }
         HEAAC_SYNC();
@@ -904,7 +904,7 @@ HEAAC_DEV void heaac_synth_stream_ds(HeaacSynthSmem *sm, const float *HEAAC_REST
         const float *x0 = X + (size_t)c * HEAAC_X_FLOATS + i, *x1 = x0 + HEAAC_X_PLANE;
         float *v = sm->ch[c] + (31 - i) * HEAAC_V_STRIDE;
         heaac_imdct128_reg<HEAAC_MDCT_SYN>(
-            [&](int j) { return j < 32 ? -x0[j * HEAAC_XS] : x1[(63 - j) * HEAAC_XS]; },
+            [&](int j) { return j < 32 ? -HEAAC_LDX(x0 + j * HEAAC_XS) : HEAAC_LDX(x1 + (63 - j) * HEAAC_XS); },
             [&](int j, float b) { if (j & 1) v[(63 - j) >> 1] = b; else v[63 - ((62 - j) >> 1)] = -b; });
     }
     HEAAC_SYNC();
