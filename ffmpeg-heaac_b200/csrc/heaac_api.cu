@@ -142,6 +142,9 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
 #ifndef HEAAC_PDL
 #define HEAAC_PDL 1
 #endif
+#ifndef HEAAC_PDL_MAX_CHANNELS
+#define HEAAC_PDL_MAX_CHANNELS 4096
+#endif
 #ifndef HEAAC_SBR_FLAGS
 #define HEAAC_SBR_FLAGS 1
 #endif
@@ -370,6 +373,10 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (!getenv("HEAAC_NO_TNS_PREPASS")) CKX(cudaMalloc(&c->d_tns_done, S * g->ncc * 1024 * sizeof(float)));
     CKX(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
     CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
+    /* overlapping the kernels' last waves pays while a launch is a few waves long (1024 stereo streams: +9 %); with
+     * 8192 channels or more per launch it costs 1-2 % (tools/pdl_sweep.sh), so large batches keep plain stream order */
+    c->pdl = HEAAC_PDL && (size_t)g->n_streams * g->ncc <= HEAAC_PDL_MAX_CHANNELS;
+    if (const char *e = getenv("HEAAC_B200_PDL")) c->pdl = HEAAC_PDL && atoi(e) != 0;      /* measurement knob */
     CKX(cudaMalloc(&c->d_sbr_done, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
     CKX(cudaMemset(c->d_sbr_done, 0, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
     if (g->sbr) {
@@ -503,7 +510,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
             /* behind a k_synth of the same batch (no k_tns, no profiling event in between) the core transform of the
              * next frame depends on nothing that kernel writes: let it start while k_synth's last wave drains */
-            const bool early = HEAAC_PDL && g.sbr && f > 0 && !(tn && c->d_tns_done) && !c->prof_on;
+            const bool early = c->pdl && g.sbr && f > 0 && !(tn && c->d_tns_done) && !c->prof_on;
             CK(heaac_launch(early, k_core, grid, HEAAC_THREADS, c->smem_core, c->stream, g, (int)n_ch, co, ic, tn, c->d_chan,
                             c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work,
                             tn ? c->d_tns_done : nullptr));
@@ -513,10 +520,10 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         if (g.sbr) {
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
             /* without PS, k_synth starts per element on k_sbr's per-channel flags instead of behind the whole grid */
-            unsigned *flags = HEAAC_PDL && HEAAC_SBR_FLAGS && !c->prof_on && !g.ps ? c->d_sbr_done : nullptr;
+            unsigned *flags = c->pdl && HEAAC_SBR_FLAGS && !c->prof_on && !g.ps ? c->d_sbr_done : nullptr;
             const unsigned tick = ++c->tick;
             prof_begin(c, HEAAC_K_SBR);
-            CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_sbr, (unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream,
+            CK(heaac_launch(c->pdl && !c->prof_on, k_sbr, (unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream,
                             g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables, flags, tick));
             prof_end(c);
             c->launches++;
@@ -528,7 +535,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            CK(heaac_launch(HEAAC_PDL && !c->prof_on, k_synth, (unsigned)(S * g.nse), 128, c->smem_synth, c->stream,
+            CK(heaac_launch(c->pdl && !c->prof_on, k_synth, (unsigned)(S * g.nse), 128, c->smem_synth, c->stream,
                             g, c->d_X, c->d_synth, pc, pf, c->d_tables, flags, tick));
             prof_end(c);
             c->launches++;

@@ -21,6 +21,7 @@ struct HeaacContext {
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
     unsigned *d_sbr_done;            /* per coded channel: tick of the last frame k_sbr finished (k_synth's start signal) */
     unsigned tick;                   /* frames launched so far */
+    int pdl;                         /* chain the kernels with programmatic dependent launches */
     float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
     float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
