@@ -300,6 +300,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((dom, args.workload, S)), "peak_kind": peak_kind, "kernel_share_of_step": kern[dom]["ms_per_launch"] / tot,
                 "kernels": kern,
+                # per-kernel times come from the serialised pass (an event pair around every launch); in the timed
+                # region the kernels of a tick are chained with programmatic dependent launches and their last waves
+                # overlap, so the step is shorter than launches x the sum of these
+                "kernel_timing": "serialised pass", "serialised_ms_per_step": tot * T,
                 "path": {"achieved": path_achieved, "frac": path_achieved / peak, "alg_bytes_per_unit": unit_bytes, "unit_name": unit_name}}
 
     # ---- e2e leg: host (pinned) buffers through the C-ABI, copies inside the timed region ----
