@@ -150,6 +150,23 @@ def test_full_batch_properties(hb, name, S):
     assert int(np.abs(pcm[:, :K].astype(np.int32) - opcm).max()) <= 1
 
 
+@pytest.mark.parametrize("name,S", [("heaac_v1_stereo", 1024), ("heaac_v2_ps", 1024)])
+def test_dependent_launch_chain_changes_nothing(hb, monkeypatch, name, S):
+    """The kernels of consecutive frame ticks overlap through programmatic dependent launches and per-channel
+    completion flags ("Launch chain"); with the chain forced off (plain stream order) every
+    sample of every stream must be the same, over enough frames for all hand-overs to recur many times."""
+    from ffmpeg_heaac_b200 import synthetic
+    T = 12
+    cfg, a = synthetic.make_workload(name, S, T, seed=5, K=32)
+    args = (a["coeffs"], a["ics"], a["tns"], a["sbr"], a["ps"])
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HEAAC_B200_PDL", mode)           # read when the context is created
+        out[mode], _ = run_cuda(hb, cfg, args, want_float=False)
+    assert out["1"].any()
+    assert np.array_equal(out["1"], out["0"])
+
+
 def test_pure_upsampling_and_ps_off(hb):
     """sbr->start == 0 (bad header: 'pure upsampling mode', aacsbr.c:1029-1033) and ps->start == 0
     (R = copy of L, aacsbr.c:1751-1756)."""
