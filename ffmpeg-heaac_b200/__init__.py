@@ -36,7 +36,7 @@ EXPORTS = [
     "heaac_dec_open", "heaac_dec_close", "heaac_dec_decode", "heaac_dec_info",
     "heaac_b200_parser_create", "heaac_b200_parser_destroy", "heaac_b200_parser_reset", "heaac_b200_parser_decode",
     "heaac_b200_parser_launch_count", "heaac_b200_parser_stats", "heaac_dec_parse_kernel_ms",
-    "heaac_fe_parse_two_phase", "heaac_fe_copy_layout",
+    "heaac_fe_parse_two_phase", "heaac_fe_copy_layout", "heaac_fe_fix_layout",
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
     "heaac_b200_sbr_init", "heaac_b200_sbr_apply", "heaac_b200_ps_apply", "heaac_b200_sbr_close",
@@ -90,6 +90,7 @@ def lib():
         L.heaac_fe_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.heaac_fe_parse_two_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.heaac_fe_copy_layout.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_fe_fix_layout.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_sbr_downsampled.argtypes = [C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]

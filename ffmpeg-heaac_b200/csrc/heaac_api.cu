@@ -606,6 +606,9 @@ extern "C" long long heaac_b200_ticket(HeaacContext *c)
 {
     if (!c) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
+    /* the event slot of the ticket issued 8 tickets ago is about to be reused: finish that ticket's work first (back
+     * pressure on the submitter), so that "its event was reused" really does mean "its PCM is in host memory" */
+    if (c->n_tickets >= 8) CK(cudaEventSynchronize(c->ev_ticket[c->n_tickets & 7]));
     CK(cudaEventRecord(c->ev_ticket[c->n_tickets & 7], c->s_out));
     return c->n_tickets++;
 }
@@ -614,7 +617,8 @@ extern "C" int heaac_b200_ticket_wait(HeaacContext *c, long long ticket)
 {
     if (!c || ticket < 0 || ticket >= c->n_tickets) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
-    if (c->n_tickets - ticket > 8) return 0;                   /* its event has been reused: that work finished long ago */
+    /* a reused slot holds a later event on the same stream (s_out): waiting for it covers the older ticket too, and
+     * heaac_b200_ticket() has already waited for the older work before reusing the slot */
     CK(cudaEventSynchronize(c->ev_ticket[ticket & 7]));
     return heaac_cuda_err(cudaGetLastError(), "ticket_wait");
 }

@@ -66,6 +66,7 @@ struct HeaacDecoder {
     unsigned long long generation = 0;
     int pending = 0;
     bool quit = false;
+    bool configured = false;                          /* set only when configure() succeeded as a whole */
 };
 
 namespace {
@@ -190,7 +191,8 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     if (d->cfg.gpu_parse) {
         HeaacFrontend *f = nullptr;
         if ((r = heaac_fe_open(&f, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0))) return r;
-        heaac_fe_copy_layout(f, probe);               /* ADTS input: every stream starts from the layout packet 0 announced */
+        /* every stream starts from the layout packet 0 announced, and is held to it: the staging slots are sized for it */
+        if ((r = heaac_fe_fix_layout(f, probe))) { heaac_fe_close(f); return r; }
         r = heaac_b200_parser_create(d->be, f, 0, &d->gpu);
         heaac_fe_close(f);
         return r;
@@ -208,12 +210,32 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
         HeaacFrontend *f = nullptr;
         if ((r = heaac_fe_open(&f, ed, (int)d->extradata.size(), d->cfg.sample_rate, d->cfg.channels, 0))) return r;
         d->fe.push_back(f);
+        if ((r = heaac_fe_fix_layout(f, probe))) return r;     /* a packet announcing another layout is rejected, not decoded */
     }
     int nt = d->cfg.n_threads > 0 ? d->cfg.n_threads : (int)std::thread::hardware_concurrency();
     if (nt > d->cfg.n_streams) nt = d->cfg.n_streams;
     if (nt > 1)
         for (int i = 0; i < nt; i++) d->workers.emplace_back(worker_main, d, i, nt);
     return 0;
+}
+
+/* undo a configure() that failed half way: the next call starts from scratch instead of running on a half-built decoder */
+void unconfigure(HeaacDecoder *d)
+{
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        d->quit = true;
+        d->cv_go.notify_all();
+    }
+    for (auto &t : d->workers) t.join();
+    d->workers.clear();
+    d->quit = false;
+    if (d->gpu) { heaac_b200_parser_destroy(d->gpu); d->gpu = nullptr; }
+    free_sets(d);
+    for (auto f : d->fe) heaac_fe_close(f);
+    d->fe.clear();
+    if (d->be) { heaac_b200_destroy(d->be); d->be = nullptr; }
+    d->configured = false;
 }
 
 }  // namespace
@@ -263,12 +285,17 @@ extern "C" long long heaac_dec_submit(HeaacDecoder *d, int n_frames, const uint8
     if (!d || n_frames <= 0 || !pkt || !pkt_size || (!pcm && !pcm_f32)) return HEAAC_E_INVAL;
     if (n_frames > d->cfg.max_frames_per_call) return HEAAC_E_INVAL;
     int r;
-    if (!d->be && (r = configure(d, pkt[0], pkt_size[0]))) return r;
+    if (!d->configured) {
+        if ((r = configure(d, pkt[0], pkt_size[0]))) { unconfigure(d); return r; }
+        d->configured = true;
+    }
     if (pcm_f32 && !d->cfg.want_float_out) return HEAAC_E_INVAL;
     const size_t S = d->cfg.n_streams;
     if (d->gpu) {
         int *cons = consumed;
         const int slot = (int)(d->n_submitted & 7);
+        /* 8 calls may be outstanding; the 9th first completes the oldest one that was never waited for */
+        if (d->pending_consumed[slot] && (r = heaac_dec_wait(d, d->pending_ticket[slot]))) return r;
         if (!cons) { d->scratch_consumed[slot].resize((size_t)n_frames * S); cons = d->scratch_consumed[slot].data(); }
         long long t = heaac_b200_parser_submit(d->gpu, n_frames, pkt, pkt_size, pcm, pcm_f32, cons);
         if (t < 0) return t;
@@ -301,7 +328,7 @@ extern "C" long long heaac_dec_submit(HeaacDecoder *d, int n_frames, const uint8
 
 extern "C" int heaac_dec_wait(HeaacDecoder *d, long long ticket)
 {
-    if (!d || !d->be) return HEAAC_E_INVAL;
+    if (!d || !d->configured) return HEAAC_E_INVAL;
     if (!d->gpu) return heaac_b200_ticket_wait(d->be, ticket);
     int r = heaac_b200_parser_wait(d->gpu, ticket);
     if (r) return r;
@@ -327,7 +354,7 @@ extern "C" int heaac_dec_info(const HeaacDecoder *d, int *n_out_channels, int *f
 {
     if (!d) return HEAAC_E_INVAL;
     if (parse_errors) *parse_errors = d->parse_errors.load();
-    if (!d->be) return 0;                              /* not configured yet: nothing decoded so far */
+    if (!d->configured) return 0;                      /* not configured yet: nothing decoded so far */
     if (n_out_channels) *n_out_channels = heaac_b200_n_out_channels(d->be);
     if (frame_out_len) *frame_out_len = heaac_b200_frame_out_len(d->be);
     if (sbr) *sbr = d->sbr;

@@ -226,6 +226,7 @@ struct HeaacFrontend {
     int sample_rate, sr_index, chan_config, object_type;
     int sbr, ps;                                /* -1 unknown (implicit signalling), 0 absent, 1 present */
     int ext_sample_rate, locked;
+    int layout_fixed;                           /* batch use: the layout was fixed when the stream was opened; a header that disagrees is an error */
     int n_elems, elem_type[HEAAC_MAX_ELEMS];
     int elem_ch0[HEAAC_MAX_ELEMS];              /* first core channel of each element */
     int ncc, nse;
@@ -1031,7 +1032,14 @@ FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, He
         int rdb = br_get(b, 2);
         if (rdb) return HEAAC_E_UNSUPPORTED;
         if (!crc_absent) br_skip(b, 16);
-        if (!fe->locked && ch) { int r = set_layout(fe, ch); if (r) return r; fe->sample_rate = sample_rates[sr]; fe->sr_index = sr; }
+        if (ch && (fe->locked || fe->layout_fixed)) {
+            /* Output slots (and the batch's staging buffers) are sized for the layout the stream was opened with: a
+             * header announcing another channel configuration or core rate is rejected before anything is written.
+             * (The reference reconfigures its output instead, aacdec.c:1994-2006; a batch cannot.) */
+            if (fe->chan_config && (ch != fe->chan_config || sr != fe->sr_index)) return HEAAC_E_INVAL;
+        } else if (ch) {
+            int r = set_layout(fe, ch); if (r) return r; fe->sample_rate = sample_rates[sr]; fe->sr_index = sr;
+        }
     }
     if (!fe->n_elems) return HEAAC_E_INVAL;
     int seen[4] = { 0, 0, 0, 0 };

@@ -201,6 +201,18 @@ int heaac_fe_copy_layout(FE *dst, const FE *src)
     return src->chan_config ? set_layout(dst, src->chan_config) : 0;
 }
 
+/* Batch use: give `dst` the layout and core rate `src` has found and FIX them -- the caller sizes every per-stream
+ * output slot for that layout, so from now on a packet whose ADTS header announces another channel configuration or
+ * sampling-rate index fails with HEAAC_E_INVAL before anything is written (fe_parse_frame). */
+int heaac_fe_fix_layout(FE *dst, const FE *src)
+{
+    int r = heaac_fe_copy_layout(dst, src);
+    if (r) return r;
+    if (!dst->chan_config) return HEAAC_E_INVAL;
+    dst->layout_fixed = 1;
+    return 0;
+}
+
 /* 1 when the stream asks for downsampled SBR: explicitly signalled extension rate below twice the core rate
  * (ff_sbr_apply: downsampled = m4ac.ext_sample_rate < sbr->sample_rate, aacsbr.c:1719) */
 int heaac_fe_sbr_downsampled(const FE *fe)

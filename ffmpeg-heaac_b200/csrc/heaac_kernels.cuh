@@ -237,7 +237,9 @@ HEAAC_DEV int heaac_tns_chain(const HeaacIcs *ics, const HeaacTns *HEAAC_RESTRIC
         top = bottom;
         bottom = HEAAC_MAX(0, top - (int)tns->length[sl]);
     }
-    const int order = tns->order[slot];
+    /* side info of device-resident batches reaches the kernels unchecked: an order beyond the coefficient array
+     * (aac.h:44, never produced by a parser) is cut, not followed out of bounds */
+    const int order = HEAAC_MIN((int)tns->order[slot], HEAAC_TNS_MAX_ORDER);
     if (!order) return 0;
     int start = swb[HEAAC_MIN(bottom, mmm)];
     const int end = swb[HEAAC_MIN(top, mmm)];
@@ -294,10 +296,11 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
                                   const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
 {
     constexpr int nt = NT;
-    const HeaacIcs ics = *ics_p;
+    HeaacIcs ics = *ics_p;
+    ics.window_sequence &= 3; ics.window_shape &= 1;         /* unchecked side info stays inside the case table */
     const int ws0 = ics.window_sequence;
-    const int ws1 = ics.prev_valid ? (int)ics.prev_window_sequence : st->prev_ws;
-    const int shape_prev = ics.prev_valid ? (int)ics.prev_window_shape : st->prev_shape;
+    const int ws1 = (ics.prev_valid ? (int)ics.prev_window_sequence : st->prev_ws) & 3;
+    const int shape_prev = (ics.prev_valid ? (int)ics.prev_window_shape : st->prev_shape) & 1;
     const int is8 = ws0 == HEAAC_EIGHT_SHORT;
 
     /* ---- TNS, aacdec.c:1698-1736 ---- */

@@ -266,6 +266,13 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
     const size_t S = g->n_streams;
     const int Tc = c->chunk;
     const int slot = (int)(c->n_tickets & 7);
+    if (c->n_tickets >= 8 && p->user_consumed[slot]) {
+        /* the call that used this slot 8 submissions ago was never waited for: complete it now (its consumed[] goes to
+         * its caller's array) before h_consumed[slot] / user_consumed[slot] are reused */
+        CK(cudaEventSynchronize(c->ev_ticket[slot]));
+        memcpy(p->user_consumed[slot], p->h_consumed[slot], (size_t)p->user_n[slot] * sizeof(int));
+        p->user_consumed[slot] = nullptr;
+    }
     static const int dbg = getenv("HEAAC_DEBUG_TIMING") != nullptr;
     double t_sync = 0, t_gather = 0, t_submit = 0, t_wait = 0;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -351,7 +358,7 @@ extern "C" int heaac_b200_parser_wait(HeaacGpuParser *p, long long ticket)
     int r = heaac_b200_ticket_wait(p->ctx, ticket);
     if (r) return r;
     const int slot = (int)(ticket & 7);
-    if (p->ctx->n_tickets - ticket <= 8 && p->user_consumed[slot]) {
+    if (p->ctx->n_tickets - ticket <= 8 && p->user_consumed[slot]) {      /* (an older ticket's consumed[] was delivered when its slot was reused) */
         memcpy(p->user_consumed[slot], p->h_consumed[slot], (size_t)p->user_n[slot] * sizeof(int));
         p->user_consumed[slot] = nullptr;
     }

@@ -308,6 +308,10 @@ int  heaac_fe_parse_two_phase(HeaacFrontend *fe, const uint8_t *pkt, int size, f
 int  heaac_fe_sbr_downsampled(const HeaacFrontend *fe);
 /* copy sample rate and channel layout (not the stream state) from a front end that has seen a frame */
 int  heaac_fe_copy_layout(HeaacFrontend *dst, const HeaacFrontend *src);
+/* batch use: copy_layout and FIX the layout -- afterwards a packet whose ADTS header announces another channel
+ * configuration or sampling-rate index fails with HEAAC_E_INVAL before anything is written (the caller's per-stream
+ * output slots are sized for the fixed layout; the reference would reconfigure, aacdec.c:1994-2006) */
+int  heaac_fe_fix_layout(HeaacFrontend *dst, const HeaacFrontend *src);
 /* layout of the stream: returns the number of elements and fills the optional outputs; sbr / ps reflect
  * implicit signalling once the first frame has been parsed (aacdec.c:1659-1676) */
 int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,

@@ -242,3 +242,44 @@ def test_frontend_survives_corrupt_packets(name):
         assert r["consumed"] == len(pk[-1])
         fe.close()
     assert errors > 0
+
+
+def test_adts_header_cannot_change_a_fixed_or_running_layout():
+    """A batch sizes every stream's output slots for one layout (heaac_decoder.cpp, heaac_parse_gpu.cu).  A packet whose
+    ADTS header announces another channel configuration or core rate -- a 5.1 stream in a stereo batch, or a crafted
+    header -- must be rejected before anything is written: (a) by a stream whose layout was fixed at open time
+    (heaac_fe_fix_layout), even as its very first packet, and (b) by a stream that has already decoded a frame."""
+    import ctypes as C
+    st, mc = load_golden("lc_stereo_44k"), load_golden("lc_51_48k")
+    stereo = [adts_wrap(p, int(st["sr_index"]), 2) for p in golden_packets(st)]
+    surround = [adts_wrap(p, int(mc["sr_index"]), 6) for p in golden_packets(mc)]
+    probe = hb.Frontend(b"", 0, 0)
+    probe.parse(stereo[0])
+    assert probe.ncc == 2
+    # (a) fixed before the first packet
+    f = hb.Frontend(b"", 0, 0)
+    assert hb.lib().heaac_fe_fix_layout(C.c_void_p(f.h), C.c_void_p(probe.h)) == 0
+    guard = np.full((16, 1024), 7.0, np.float32)
+    ics, tns = np.zeros(16, abi.ICS), np.zeros(16, abi.TNS)
+    buf = np.frombuffer(surround[0], np.uint8)
+    r = hb.lib().heaac_fe_parse(C.c_void_p(f.h), buf.ctypes.data, buf.size, guard.ctypes.data, ics.ctypes.data, tns.ctypes.data, None, None)
+    assert r == -22 and (guard == 7.0).all(), "a 5.1 header reached the decode stage of a stereo slot"
+    f._refresh()
+    assert f.ncc == 2 and f.sr_index == int(st["sr_index"])
+    # wrong sampling-rate index, right channel configuration
+    bad_rate = adts_wrap(golden_packets(st)[0], 3, 2)
+    buf = np.frombuffer(bad_rate, np.uint8)
+    assert hb.lib().heaac_fe_parse(C.c_void_p(f.h), buf.ctypes.data, buf.size, guard.ctypes.data, ics.ctypes.data, tns.ctypes.data, None, None) == -22
+    assert f.parse(stereo[0])["consumed"] == len(stereo[0])
+    f.close()
+    # (b) a running stream
+    with pytest.raises(hb.HeaacError):
+        probe.parse(surround[1])
+    assert probe.ncc == 2
+    probe.parse(stereo[1])
+    probe.close()
+    # without a fixed layout the first header still configures the stream (reference behaviour)
+    g = hb.Frontend(b"", 0, 0)
+    g.parse(surround[0])
+    assert g.ncc == 6
+    g.close()
