@@ -164,6 +164,7 @@ extern "C" int heaac_emu_peek(EmuCtx *c, const char *name, void *dst, int cap)
     else if (!strcmp(name, "chan_state")) { p = c->chan; n = S * c->g.ncc * sizeof(HeaacChanState); }
     else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacHfSmem); }
     else if (!strcmp(name, "ps_smem")) { p = c->sm_ps; n = sizeof(HeaacPsSmem); }
+    else if (!strcmp(name, "ps_state")) { p = c->ps; n = S * sizeof(HeaacPsState); }
     if (!p) return -1;
     if (n > (size_t)cap) n = cap;
     memcpy(dst, p, n);

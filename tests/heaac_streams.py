@@ -327,6 +327,11 @@ def write_ps_data(bw, rng, ps, frame_idx, header_period=8, ipdopd=True, fixed_mo
     frame_class = int(rng.integers(0, 2))
     bw.put(frame_class, 1)
     idx = int(rng.integers(0, 4))
+    if header and frame_class == 0 and idx == 0:
+        # num_env == 0 makes the decoder reuse the previous frame's last envelope (aacps.c:238-256); right after a header
+        # that switched to the coarse IID quantiser those values (up to +-15) index the reference's H LUT out of bounds
+        # (aacps.c:863): a second undefined corner the fixture must stay out of -- a header frame carries >= 1 envelope
+        idx = int(rng.integers(1, 4))
     num_env = [[0, 1, 2, 4], [1, 2, 3, 4]][frame_class][idx]
     bw.put(idx, 2)
     if frame_class:
