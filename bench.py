@@ -33,11 +33,13 @@ ALG_BYTES = {"lc_chframe": 10240, "v1_chframe": 38912, "v2_streamframe": 66392}
 # of which each kernel's share when the stages run as separate launches (state it owns + its I/O); DESIGN.md "kernels"
 KERNEL_ALG_BYTES = {
     "k_core":  4096 + 2 * 2048,                      # coeffs + saved R/W  (+ PCM 2048 when it is the last stage)
-    "k_sbr":   1536 + 2 * (1152 + 2048 + 3072 + 1536 + 128),   # params + ana hist, W tail, Y tail, g/q hist, scalars R+W
+    # k_chain, whole HE-AAC v1 channel-frame: coeffs + params + state R+W + PCM; when it stops at X (PS /
+    # downsampled SBR) it has neither the synthesis history nor the PCM
+    "k_chain": 38912,
+    "k_chain_x": 25600,
     "k_ps":    1024 + 13144,
-    "k_synth": 2 * 4608 + 4096,                      # v history R+W + PCM
+    "k_synth": 2 * 4608 + 4096,                      # v history R+W + PCM, per output channel
 }
-
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
 # (profiles/r01_ncu_summary.md, prof_r1d): keyed by (kernel, workload, streams per GPU).
@@ -294,7 +296,9 @@ def main():
     tot = sum(v["ms_per_launch"] for v in kern.values())
     dom = max(kern, key=lambda k: kern[k]["ms_per_launch"])
     per_launch_units = S if dom == "k_ps" else (S * ctx.nout if dom == "k_synth" else S * ctx.ncc)
-    dom_bytes = KERNEL_ALG_BYTES[dom] + (2048 if (dom == "k_core" and not cfg.sbr) else 0)
+    if dom == "k_chain":
+        per_launch_units *= kern[dom]["launches_per_step"] == 1 and T or 1      # one launch walks through all T frames (v1)
+    dom_bytes = KERNEL_ALG_BYTES["k_chain_x" if (dom == "k_chain" and cfg.ps) else dom] + (2048 if (dom == "k_core" and not cfg.sbr) else 0)
     achieved = per_launch_units * dom_bytes / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
     path_achieved = units * unit_bytes * T * args.steps / (ms_max * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

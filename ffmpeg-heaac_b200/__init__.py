@@ -245,7 +245,7 @@ class Context:
         ms = (C.c_float * 4)()
         n = (C.c_longlong * 4)()
         _check(lib().heaac_b200_profile_read(self.h, ms, n), "profile_read")
-        return {k: (ms[i], n[i]) for i, k in enumerate(("k_core", "k_sbr", "k_ps", "k_synth"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("k_core", "k_chain", "k_ps", "k_synth"))}
 
     @property
     def launch_count(self):

@@ -3,12 +3,11 @@
  * synthesis back end.  sm_100a only; there is no CPU path: every entry point fails with
  * HEAAC_E_NODEV when no CUDA device is usable.
  *
- * One frame tick of a batch = up to five launches:
- *   k_tns    one thread per TNS chain     all-pole filters, registers only (pre-pass)   (aacdec.c:1698-1736)
- *   k_core   persistent, claims channels  IMDCT + window + overlap-add (+ QMF analysis)  (aacdec.c:1741-1806, aacsbr.c:1136-1169)
- *   k_sbr    one CTA per SBR channel      X_low .. HF generation / adjustment .. X       (aacsbr.c:1089-1714)
- *   k_ps     one CTA per PS stream        hybrid analysis .. hybrid synthesis            (aacps.c:283-992)
- *   k_synth  one CTA per SBR element      QMF synthesis + float->s16                     (aacsbr.c:1175-1230)
+ * Launches per batch:
+ *   AAC-LC          per frame   k_tns (pre-pass, only with TNS) + k_core (IMDCT + window + overlap-add + s16)
+ *   HE-AAC v1       per CALL    k_chain: core transform -> QMF analysis -> HF generation / adjustment -> QMF synthesis
+ *                               -> s16 for every frame of the call, all intermediates in shared memory (heaac_chain.cuh)
+ *   HE-AAC v2 / downsampled SBR   per frame   k_chain (stops at X) + k_ps (hybrid analysis .. synthesis) + k_synth
  * All per-stream state stays in HBM between launches (heaac_dev.cuh).
  */
 #include <cuda_runtime.h>
@@ -17,7 +16,7 @@
 #include <string.h>
 #include <new>
 
-#include "heaac_kernels.cuh"
+#include "heaac_chain.cuh"
 #include "heaac_context.cuh"
 
 extern "C" void heaac_build_tables(HeaacDevTables *t);
@@ -68,13 +67,13 @@ k_tns(int n_channels, int sr_index, const float *__restrict__ coeffs, const Heaa
     else                  heaac_tns_run<HEAAC_TNS_MAX_ORDER>(in, out, start, size, inc, order, lpc);
 }
 
-/* Persistent: the CTAs of the grid claim channels from a device counter (so CTAs that are scheduled late, e.g.
- * behind a concurrently running parse kernel, do not hold the kernel up) and stage the NEXT claimed channel's
- * coefficients into the other half of a double buffer with cp.async while working on the current one.
+/* AAC-LC channel-frames (no SBR).  Persistent: the CTAs of the grid claim channels from a device counter (so CTAs that
+ * are scheduled late, e.g. behind a concurrently running parse kernel, do not hold the kernel up) and stage the NEXT
+ * claimed channel's coefficients into the other half of a double buffer with cp.async while working on the current one.
  * work[0] = next unclaimed channel, work[1] = CTAs finished; the last CTA out resets both for the next launch. */
 __global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
 k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
-       const HeaacTns *__restrict__ tns, HeaacChanState *chan, float *W,
+       const HeaacTns *__restrict__ tns, HeaacChanState *chan,
        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, unsigned *work,
        const float *__restrict__ tns_done)
 {
@@ -82,10 +81,7 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
     __shared__ int s_claim[2];
     HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
     float *stage = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [2][1024] */
-    float *x = stage + 2048;                         /* [288 history | 1024 new] (+ 64*33 analysis scratch) */
-    float *out = x + 288;
-    const float bias = g.sbr ? 0.0f : g.add_bias;    /* aacdec.c:1906 */
-    asm volatile("griddepcontrol.launch_dependents;");   /* k_sbr's CTAs move in as this grid's leave, and wait */
+    float *out = stage + 2048;                       /* [1024] */
     if (threadIdx.x == 0) s_claim[0] = (int)atomicAdd(&work[0], 1u);
     __syncthreads();
     int gc = s_claim[0];
@@ -94,8 +90,6 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
     heaac_cp_async_commit();
     for (int it = 0; gc < n_channels; it++) {
         const int s = gc / g.ncc, c = gc - s * g.ncc;
-        HeaacChanState *st = chan + gc;
-        const bool ana = g.sbr && g.ch_sbr_elem[c] != 0xff;
         float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
         if (threadIdx.x == 0) s_claim[(it + 1) & 1] = (int)atomicAdd(&work[0], 1u);
         heaac_cp_async_wait<0>();                    /* this channel's coefficients have landed */
@@ -103,74 +97,159 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
         const int gn = s_claim[(it + 1) & 1];
         if (gn < n_channels)
             heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
-        if (ana)                                     /* the analysis history is not needed before the IMDCT is done */
-            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) heaac_cp_async4(x + i, st->ana_hist + i);
         heaac_cp_async_commit();
         heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
                                           tns_done ? tns_done + (size_t)gc * 1024 : nullptr,
-                                          st, out, bias, g.sr_index, T, threadIdx.x);
-        if (ana) {
-            /* QMF analysis on the samples still in shared memory (sbr_qmf_analysis, aacsbr.c:1136-1169) */
-            const float ana_scale = 1 / (-1024.0f * g.sf_scale);               /* aacsbr.c:1730 */
-            if (ana_scale != 1.0f)
-                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) out[i] = out[i] * ana_scale;
-            heaac_cp_async_wait<0>();                /* history (and the next channel's coefficients) */
-            __syncthreads();
-            for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
-            float *tb = x + 1312;
-            heaac_qmf_analysis<HEAAC_THREADS>(x, tb, W + (size_t)gc * 2048, T, threadIdx.x);
-        } else if (!g.sbr) {
-            const int bias_mode = g.add_bias != 0.0f;
-            if (pcm) {
-                int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
-                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
-            }
-            if (pcm_f32) {
-                float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
-                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
-            }
+                                          chan + gc, out, g.add_bias, g.sr_index, T, threadIdx.x);
+        const int bias_mode = g.add_bias != 0.0f;
+        if (pcm) {
+            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
+            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
         }
-        __syncthreads();                             /* x / tb / stage are reused by the next channel */
+        if (pcm_f32) {
+            float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
+            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
+        }
+        __syncthreads();                             /* out / stage are reused by the next channel */
         gc = gn;
     }
     if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; }
-    /* launched early behind the previous frame's k_synth (programmatic dependent launch): nothing here reads what that
-     * kernel writes, but this grid must not retire before it, so that k_sbr -- which overwrites X -- stays behind it */
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-#ifndef HEAAC_PDL
-#define HEAAC_PDL 1
+/* ------------------------------------------------------------------------------------
+ * k_chain: the whole SBR channel pipeline of a batch in ONE launch.  One CTA owns one coded channel and walks through the
+ * frames of the call: core transform (IMDCT + window + overlap-add) -> 32-band QMF analysis -> HF generation / adjustment
+ * -> 64-band QMF synthesis -> s16, with every intermediate (the time samples, W, X_low, X_high, Y, X, the v buffer) in
+ * shared memory: HBM sees the frame's coefficients and side info, the channel's state and the PCM, nothing else.
+ * The coefficients of frame f + 1 are fetched with a bulk asynchronous copy (cp.async.bulk + mbarrier, issued by one
+ * thread) while frame f is being processed; the synthesis history stays in shared memory between frames.
+ * emit = 1 (Parametric Stereo, downsampled SBR): the chain stops at X, which goes to the inter-kernel buffer;
+ * emit = 2 (keep_intermediates): X is written out as well, and the chain goes on.
+ * `time_in` (ff_sbr_apply shim): the element's time samples are given, there is no core transform.
+ * ---------------------------------------------------------------------------------- */
+#ifndef HEAAC_CHAIN_THREADS
+#define HEAAC_CHAIN_THREADS 256
 #endif
-#ifndef HEAAC_PDL_MAX_CHANNELS
-#define HEAAC_PDL_MAX_CHANNELS 4096
+#ifndef HEAAC_CHAIN_MIN_BLOCKS
+#define HEAAC_CHAIN_MIN_BLOCKS 4
 #endif
-#ifndef HEAAC_SBR_FLAGS
-#define HEAAC_SBR_FLAGS 1
-#endif
-#ifndef HEAAC_SBR_MIN_BLOCKS
-#define HEAAC_SBR_MIN_BLOCKS 5
-#endif
-__global__ void __launch_bounds__(HEAAC_SBR_THREADS, HEAAC_SBR_MIN_BLOCKS)
-k_sbr(HeaacGeom g, const float *__restrict__ W, const HeaacSbrElem *__restrict__ sbr,
-      HeaacChanState *chan, float *X, const HeaacDevTables *__restrict__ T, unsigned *done, unsigned tick)
+
+struct HeaacChainSmem {
+    float u[2 * HEAAC_U_PLANE];          /* the QMF-domain array of heaac_chain.cuh */
+    float vh[1152];                      /* synthesis history: the 9 v blocks before the current frame */
+    float coef[1024];                    /* coefficients of the current frame, then the half-IMDCT output */
+    HeaacSbrElem p;                      /* SBR side info of the current frame */
+    union alignas(16) {
+        struct { HeaacCoreSmem core; float x[1312]; float tb[64 * 33]; } c;   /* core transform + analysis */
+        HeaacHfScratch hf;                                                     /* HF stage */
+    } s;
+    alignas(8) unsigned long long mbar[2];
+};
+
+__device__ __forceinline__ unsigned heaac_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void heaac_mbar_init(unsigned long long *b, unsigned count)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    HeaacHfSmem *sm = reinterpret_cast<HeaacHfSmem *>(smem_raw);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(heaac_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void heaac_mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(heaac_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void heaac_mbar_wait(unsigned long long *b, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(heaac_smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+/* global -> shared bulk copy (TMA engine, no registers involved); completion is signalled on the mbarrier.
+ * dst, src and bytes must be multiples of 16. */
+__device__ __forceinline__ void heaac_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(heaac_smem_u32(dst)), "l"(src), "r"(bytes), "r"(heaac_smem_u32(b)) : "memory");
+}
+
+__global__ void __launch_bounds__(HEAAC_CHAIN_THREADS, HEAAC_CHAIN_MIN_BLOCKS)
+k_chain(HeaacGeom g, int n_frames, int emit, const float *__restrict__ coeffs, const float *__restrict__ time_in,
+        const HeaacIcs *__restrict__ ics, const HeaacTns *__restrict__ tns, const float *__restrict__ tns_done,
+        const HeaacSbrElem *__restrict__ sbr, HeaacChanState *chan, HeaacSynthState *synth, float *X,
+        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
+{
+    constexpr int NT = HEAAC_CHAIN_THREADS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    HeaacChainSmem *sm = reinterpret_cast<HeaacChainSmem *>(smem_raw);
+    const int tid = threadIdx.x;
     const int gc = blockIdx.x;
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
-    asm volatile("griddepcontrol.wait;" ::: "memory");   /* W of this frame: k_core has retired */
-    asm volatile("griddepcontrol.launch_dependents;");
-    if (se == 0xff) return;                          /* LFE: no SBR (uniform per CTA) */
-    float *Xc = X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS;
-    heaac_hf_channel<HEAAC_SBR_THREADS>(sm, W + (size_t)gc * 2048, sbr + (size_t)s * g.nse + se, g.ch_in_elem[c],
-                     g.elem_is_cpe[c], chan + gc, Xc, T, threadIdx.x);
-    if (done) {                                      /* X of this channel is complete: its k_synth CTA may go */
+    if (se == 0xff) return;                          /* a channel without SBR (uniform per CTA) */
+    const size_t frame_ch = (size_t)g.n_streams * g.ncc;
+    HeaacChanState *st = chan + gc;
+    HeaacSynthState *sy = synth + (size_t)s * g.nout + c;
+    float *x = sm->s.c.x, *out = x + 288;
+    const float qmf_scale = -1024.0f * g.sf_scale;
+    const float ana_scale = 1 / qmf_scale;                                      /* aacsbr.c:1730 */
+
+    if (tid == 0) {
+        heaac_mbar_init(&sm->mbar[0], 1);
+        heaac_mbar_init(&sm->mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (coeffs) {
+            heaac_mbar_expect_tx(&sm->mbar[0], 4096);
+            heaac_bulk_g2s(sm->coef, coeffs + (size_t)gc * 1024, 4096, &sm->mbar[0]);
+        }
+        if (emit != 1) {
+            heaac_mbar_expect_tx(&sm->mbar[1], sizeof(HeaacSynthState));
+            heaac_bulk_g2s(sm->vh, sy->v, sizeof(HeaacSynthState), &sm->mbar[1]);
+        }
+    }
+    for (int f = 0; f < n_frames; f++) {
+        const size_t fo = (size_t)f * frame_ch + gc;
+        {   /* this frame's SBR side info and the analysis history: needed after the core transform */
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(sbr + ((size_t)f * g.n_streams + s) * g.nse + se);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm->p);
+            for (int i = tid; i < (int)(sizeof(HeaacSbrElem) / 4); i += NT) dst[i] = src[i];
+            for (int i = tid; i < 288; i += NT) heaac_cp_async4(x + i, st->ana_hist + i);
+            heaac_cp_async_commit();
+        }
+        if (coeffs) {
+            heaac_mbar_wait(&sm->mbar[0], (unsigned)f & 1u);     /* the coefficients have landed */
+            heaac_core_channel<NT>(&sm->s.c.core, sm->coef, ics + fo, tns ? tns + fo : nullptr,
+                                   tns_done ? tns_done + fo * 1024 : nullptr, st, out, 0.0f, g.sr_index, T, tid);
+            /* (ends with a barrier) the coefficient buffer is free: fetch the next frame's while this one goes on */
+            if (tid == 0 && f + 1 < n_frames) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                heaac_mbar_expect_tx(&sm->mbar[0], 4096);
+                heaac_bulk_g2s(sm->coef, coeffs + (fo + frame_ch) * 1024, 4096, &sm->mbar[0]);
+            }
+            if (ana_scale != 1.0f)
+                for (int i = tid; i < 1024; i += NT) out[i] = out[i] * ana_scale;
+        } else {
+            for (int i = tid; i < 1024; i += NT) {
+                const float v = time_in[fo * 1024 + i];
+                out[i] = ana_scale != 1.0f ? v * ana_scale : v;
+            }
+        }
+        heaac_cp_async_wait<0>();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(done + gc), "r"(tick) : "memory");
+        for (int i = tid; i < 288; i += NT) st->ana_hist[i] = x[1024 + i];
+        heaac_qmf_analysis_u<NT>(x, sm->s.c.tb, sm->u, T, tid);
+        __syncthreads();                             /* U holds W; the core scratch becomes the HF scratch */
+        heaac_hf_stage<NT>(sm->u, &sm->s.hf, &sm->p, g.ch_in_elem[c], g.elem_is_cpe[c], st, T, tid);
+        if (emit) {
+            heaac_x_emit<NT>(sm->u, X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS, tid);
+            __syncthreads();
+        }
+        if (emit != 1) {
+            if (f == 0) heaac_mbar_wait(&sm->mbar[1], 0);
+            const size_t po = ((size_t)f * g.n_streams + s) * 2048 * g.nout;
+            heaac_synth_inplace<NT>(sm->u, sm->vh, sy, f == n_frames - 1, g.nout, g.out_slot[c], pcm ? pcm + po : nullptr,
+                                    pcm_f32 ? pcm_f32 + po : nullptr, qmf_scale, g.add_bias, T, tid);
         }
     }
 }
@@ -190,32 +269,16 @@ k_ps(HeaacGeom g, const HeaacPsFrame *__restrict__ ps, const HeaacSbrElem *__res
 #ifndef HEAAC_SYNTH_MIN_BLOCKS
 #define HEAAC_SYNTH_MIN_BLOCKS 4
 #endif
+/* QMF synthesis from the inter-kernel X buffer: the two output channels of a Parametric Stereo stream, and downsampled SBR */
 __global__ void __launch_bounds__(128, HEAAC_SYNTH_MIN_BLOCKS)
 k_synth(HeaacGeom g, const float *X, HeaacSynthState *synth,
-        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, const unsigned *sbr_done, unsigned tick)
+        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacSynthSmem *sm = reinterpret_cast<HeaacSynthSmem *>(smem_raw);
     /* one CTA per (stream, SBR element): its 1 or 2 output channels */
     const int s = blockIdx.x / g.nse, e = blockIdx.x - s * g.nse;
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
-    if (sbr_done) {
-        /* started while k_sbr's last wave is still running: wait for the channels of this element only.  (Every k_sbr
-         * CTA is resident or gone by the time this grid is launched, so the flags do arrive.) */
-        if ((int)threadIdx.x < nch) {
-            const unsigned *f = sbr_done + (size_t)s * g.ncc + c0 + threadIdx.x;
-            unsigned v;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (v == tick) break;
-                __nanosleep(100);
-            }
-        }
-        __syncthreads();
-    } else {
-        asm volatile("griddepcontrol.wait;" ::: "memory");   /* X of this frame: k_sbr / k_ps have retired */
-    }
-    asm volatile("griddepcontrol.launch_dependents;");   /* the next frame's k_core may fill this grid's last wave */
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
     if (g.ds)
@@ -296,8 +359,7 @@ static int init_state(HeaacContext *c)
     CK(cudaMemsetAsync(c->d_chan, 0, nch * sizeof(HeaacChanState), c->stream));
     if (g->sbr) {
         CK(cudaMemsetAsync(c->d_synth, 0, (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState), c->stream));
-        CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
-        CK(cudaMemsetAsync(c->d_W, 0, nch * 2048 * sizeof(float), c->stream));
+        if (c->d_X) CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
     }
     if (g->ps) CK(cudaMemsetAsync(c->d_ps, 0, (size_t)g->n_streams * sizeof(HeaacPsState), c->stream));
     /* everything the reference initialises to non-zero (kx' = 32, e_a[1] = -1; aacsbr.c:128-137) lives in
@@ -370,25 +432,20 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     }
     size_t S = g->n_streams, T = cfg->max_frames_per_call;
     CKX(cudaMalloc(&c->d_chan, S * g->ncc * sizeof(HeaacChanState)));
-    if (!getenv("HEAAC_NO_TNS_PREPASS")) CKX(cudaMalloc(&c->d_tns_done, S * g->ncc * 1024 * sizeof(float)));
+    if (!g->sbr) {                                   /* AAC-LC: one frame tick of TNS scratch; with SBR it is sized on first use */
+        CKX(cudaMalloc(&c->d_tns_done, S * g->ncc * 1024 * sizeof(float)));
+        c->tns_done_frames = 1;
+    }
     CKX(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
     CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
-    /* overlapping the kernels' last waves pays while a launch is a few waves long (1024 stereo streams: +9 %); with
-     * 8192 channels or more per launch it costs 1-2 % (tools/pdl_sweep.sh), so large batches keep plain stream order */
-    c->pdl = HEAAC_PDL && (size_t)g->n_streams * g->ncc <= HEAAC_PDL_MAX_CHANNELS;
-    if (const char *e = getenv("HEAAC_B200_PDL")) c->pdl = HEAAC_PDL && atoi(e) != 0;      /* measurement knob */
-    CKX(cudaMalloc(&c->d_sbr_done, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
-    CKX(cudaMemset(c->d_sbr_done, 0, (size_t)g->n_streams * g->ncc * sizeof(unsigned)));
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
-        CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
-        CKX(cudaMalloc(&c->d_W, S * g->ncc * 2048 * sizeof(float)));
+        if (g->ps || g->ds || cfg->keep_intermediates) CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
     c->chunk = (int)((T + 3) / 4);
     if (c->chunk > 8) c->chunk = 8;
     if (cfg->chunk_frames > 0) c->chunk = cfg->chunk_frames;
-    if (getenv("HEAAC_CHUNK_FRAMES")) c->chunk = atoi(getenv("HEAAC_CHUNK_FRAMES"));     /* tuning knob */
     if (c->chunk > 32) c->chunk = 32;
     if ((size_t)c->chunk > T) c->chunk = (int)T;
     if (c->chunk < 1) c->chunk = 1;
@@ -411,12 +468,12 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
         }
     }
 
-    c->smem_core = sizeof(HeaacCoreSmem) + (2048 + (g->sbr ? 1312 + 64 * 33 : 1312)) * sizeof(float);
-    c->smem_sbr = sizeof(HeaacHfSmem);
+    c->smem_core = sizeof(HeaacCoreSmem) + (2048 + 1024) * sizeof(float);
+    c->smem_chain = sizeof(HeaacChainSmem);
     c->smem_ps = sizeof(HeaacPsSmem);
     c->smem_synth = sizeof(HeaacSynthSmem);
     CKX(cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_core));
-    CKX(cudaFuncSetAttribute(k_sbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sbr));
+    CKX(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_chain));
     CKX(cudaFuncSetAttribute(k_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_ps));
     CKX(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_synth));
     {
@@ -437,7 +494,7 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_W); cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_sbr_done); cudaFree(c->d_tns_done);
+    cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_tns_done);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
         cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
@@ -470,76 +527,78 @@ extern "C" int heaac_b200_n_sbr_elems(const HeaacContext *c)     { return c ? c-
 extern "C" long long heaac_b200_launch_count(const HeaacContext *c) { return c ? c->launches : 0; }
 extern "C" uintptr_t heaac_b200_stream(const HeaacContext *c) { return c ? (uintptr_t)c->stream : 0; }
 
-/* launches for frames [0, n) of a device-resident batch */
-/* Kernel launch, optionally as a programmatic dependent launch: with `early` the grid may begin once every CTA of the
- * kernel before it in the stream has executed griddepcontrol.launch_dependents (or left); whatever it reads from that
- * kernel it reads behind its own griddepcontrol.wait.  The chain per frame is k_core -> k_sbr -> (k_ps) -> k_synth ->
- * next k_core: k_sbr and k_synth wait first thing (which hides their launch latency), k_core -- which needs nothing
- * k_synth wrote -- waits last thing, so that its real work fills the tail of the synthesis grid. */
-template <typename... P, typename... A>
-static cudaError_t heaac_launch(bool early, void (*kern)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A... args)
-{
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = early ? 1 : 0;
-    return cudaLaunchKernelEx(&lc, kern, static_cast<P>(args)...);
-}
-
+/* launches for frames [0, n) of a device-resident batch on c->stream */
 int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
                          const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32)
 {
     const HeaacGeom g = c->geom;
     const size_t S = g.n_streams;
     const size_t pcm_frame = S * g.out_len * g.nout;
-    for (int f = 0; f < n_frames; f++) {
-        const float *co = coeffs + (size_t)f * S * g.ncc * 1024;
-        const HeaacIcs *ic = ics + (size_t)f * S * g.ncc;
-        const HeaacTns *tn = tns ? tns + (size_t)f * S * g.ncc : nullptr;
-        int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
-        float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
-        prof_begin(c, HEAAC_K_CORE);
-        {
-            const unsigned n_ch = (unsigned)(S * g.ncc);
-            if (tn && c->d_tns_done) {
-                k_tns<<<(n_ch * 8 + 127) / 128, 128, 0, c->stream>>>((int)n_ch, g.sr_index, co, ic, tn, c->d_tns_done, c->d_tables);
-                c->launches++;
+    const unsigned n_ch = (unsigned)(S * g.ncc);
+    if (g.sbr) {
+        const float *tns_done = nullptr;
+        if (tns) {
+            /* TNS pre-pass for every frame of the call at once (the filters of different frames are independent) */
+            if (c->tns_done_frames < (size_t)n_frames) {
+                CK(cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_tns_done); c->d_tns_done = nullptr; c->tns_done_frames = 0;
+                CK(cudaMalloc(&c->d_tns_done, (size_t)n_frames * n_ch * 1024 * sizeof(float)));
+                c->tns_done_frames = n_frames;
             }
-            const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
-            /* behind a k_synth of the same batch (no k_tns, no profiling event in between) the core transform of the
-             * next frame depends on nothing that kernel writes: let it start while k_synth's last wave drains */
-            const bool early = c->pdl && g.sbr && f > 0 && !(tn && c->d_tns_done) && !c->prof_on;
-            CK(heaac_launch(early, k_core, grid, HEAAC_THREADS, c->smem_core, c->stream, g, (int)n_ch, co, ic, tn, c->d_chan,
-                            c->d_W, g.sbr ? nullptr : pc, g.sbr ? nullptr : pf, c->d_tables, c->d_work,
-                            tn ? c->d_tns_done : nullptr));
+            const size_t n_all = (size_t)n_frames * n_ch;
+            k_tns<<<(unsigned)((n_all * 8 + 127) / 128), 128, 0, c->stream>>>((int)n_all, g.sr_index, coeffs, ics, tns, c->d_tns_done, c->d_tables);
+            c->launches++;
+            tns_done = c->d_tns_done;
         }
-        prof_end(c);
-        c->launches++;
-        if (g.sbr) {
+        const int with_x = c->cfg.keep_intermediates != 0;
+        if (!g.ps && !g.ds) {                        /* HE-AAC v1: the whole call is one launch */
+            prof_begin(c, HEAAC_K_CHAIN);
+            k_chain<<<n_ch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, n_frames, with_x ? 2 : 0, coeffs, nullptr, ics, tns, tns_done, sbr,
+                                                                               c->d_chan, c->d_synth, c->d_X, pcm, pcm_f32, c->d_tables);
+            prof_end(c);
+            c->launches++;
+            return heaac_cuda_err(cudaGetLastError(), "kernel launch");
+        }
+        for (int f = 0; f < n_frames; f++) {         /* Parametric Stereo / downsampled SBR: X goes through the inter-kernel buffer */
+            const size_t fo = (size_t)f * n_ch;
             const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
-            /* without PS, k_synth starts per element on k_sbr's per-channel flags instead of behind the whole grid */
-            unsigned *flags = c->pdl && HEAAC_SBR_FLAGS && !c->prof_on && !g.ps ? c->d_sbr_done : nullptr;
-            const unsigned tick = ++c->tick;
-            prof_begin(c, HEAAC_K_SBR);
-            CK(heaac_launch(c->pdl && !c->prof_on, k_sbr, (unsigned)(S * g.ncc), HEAAC_SBR_THREADS, c->smem_sbr, c->stream,
-                            g, c->d_W, sb, c->d_chan, c->d_X, c->d_tables, flags, tick));
+            int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
+            float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+            prof_begin(c, HEAAC_K_CHAIN);
+            k_chain<<<n_ch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, 1, 1, coeffs + fo * 1024, nullptr, ics + fo, tns ? tns + fo : nullptr,
+                                                                               tns_done ? tns_done + fo * 1024 : nullptr, sb, c->d_chan, c->d_synth,
+                                                                               c->d_X, nullptr, nullptr, c->d_tables);
             prof_end(c);
             c->launches++;
             if (g.ps) {
                 prof_begin(c, HEAAC_K_PS);
-                k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(
-                    g, ps + (size_t)f * S, sb, c->d_ps, c->d_X, c->d_tables);
+                k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, ps + (size_t)f * S, sb, c->d_ps, c->d_X, c->d_tables);
                 prof_end(c);
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            CK(heaac_launch(c->pdl && !c->prof_on, k_synth, (unsigned)(S * g.nse), 128, c->smem_synth, c->stream,
-                            g, c->d_X, c->d_synth, pc, pf, c->d_tables, flags, tick));
+            k_synth<<<(unsigned)(S * g.nse), 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, pc, pf, c->d_tables);
             prof_end(c);
             c->launches++;
         }
+        return heaac_cuda_err(cudaGetLastError(), "kernel launch");
+    }
+    for (int f = 0; f < n_frames; f++) {             /* AAC-LC */
+        const float *co = coeffs + (size_t)f * n_ch * 1024;
+        const HeaacIcs *ic = ics + (size_t)f * n_ch;
+        const HeaacTns *tn = tns ? tns + (size_t)f * n_ch : nullptr;
+        int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
+        float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+        prof_begin(c, HEAAC_K_CORE);
+        if (tn) {
+            k_tns<<<(n_ch * 8 + 127) / 128, 128, 0, c->stream>>>((int)n_ch, g.sr_index, co, ic, tn, c->d_tns_done, c->d_tables);
+            c->launches++;
+        }
+        const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
+        k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, co, ic, tn, c->d_chan, pc, pf, c->d_tables, c->d_work,
+                                                                   tn ? c->d_tns_done : nullptr);
+        prof_end(c);
+        c->launches++;
     }
     return heaac_cuda_err(cudaGetLastError(), "kernel launch");
 }
@@ -796,7 +855,6 @@ extern "C" int heaac_b200_debug_read(HeaacContext *c, const char *name, void *ds
     const HeaacGeom *g = &c->geom;
     const void *src = nullptr; size_t avail = 0;
     if (!strcmp(name, "X") && c->d_X) { src = c->d_X; avail = (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float); }
-    else if (!strcmp(name, "W") && c->d_W) { src = c->d_W; avail = (size_t)g->n_streams * g->ncc * 2048 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { src = c->d_chan; avail = (size_t)g->n_streams * g->ncc * sizeof(HeaacChanState); }
     else if (!strcmp(name, "synth_state") && c->d_synth) { src = c->d_synth; avail = (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState); }
     else if (!strcmp(name, "ps_state") && c->d_ps) { src = c->d_ps; avail = (size_t)g->n_streams * sizeof(HeaacPsState); }
@@ -818,25 +876,6 @@ struct HeaacSbrShim {
     float *d_out;                    /* [nout][2048] */
     int nch, nout, ps;
 };
-
-/* QMF analysis alone, on time-domain input (what k_core does after the IMDCT): one CTA per channel */
-__global__ void __launch_bounds__(HEAAC_THREADS)
-k_ana(HeaacGeom g, const float *__restrict__ time, HeaacChanState *chan, float *W, const HeaacDevTables *__restrict__ T)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *x = reinterpret_cast<float *>(smem_raw);     /* [288 history | 1024 new] + 64*33 scratch */
-    const int gc = blockIdx.x;
-    HeaacChanState *st = chan + gc;
-    const float ana_scale = 1 / (-1024.0f * g.sf_scale);                       /* aacsbr.c:1730 */
-    for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) x[i] = st->ana_hist[i];
-    for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) {
-        const float v = time[(size_t)gc * 1024 + i];
-        x[288 + i] = ana_scale != 1.0f ? v * ana_scale : v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 288; i += HEAAC_THREADS) st->ana_hist[i] = x[1024 + i];
-    heaac_qmf_analysis<HEAAC_THREADS>(x, x + 1312, W + (size_t)gc * 2048, T, threadIdx.x);
-}
 
 extern "C" int heaac_b200_sbr_init(HeaacSbrShim **out, int id_aac, int core_sr_index, int ps, float sf_scale, float add_bias)
 {
@@ -882,11 +921,14 @@ extern "C" int heaac_b200_sbr_apply(HeaacSbrShim *s, const HeaacSbrElem *elem, c
     if (s->nch == 2) CK(cudaMemcpyAsync(s->d_time + 1024, R, sizeof(float) * 1024, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(s->d_elem, elem, sizeof(HeaacSbrElem), cudaMemcpyHostToDevice, c->stream));
     if (s->ps) CK(cudaMemcpyAsync(s->d_psf, psf, sizeof(HeaacPsFrame), cudaMemcpyHostToDevice, c->stream));
-    k_ana<<<s->nch, HEAAC_THREADS, (1312 + 64 * 33) * sizeof(float), c->stream>>>(g, s->d_time, c->d_chan, c->d_W, c->d_tables);
-    k_sbr<<<s->nch, HEAAC_SBR_THREADS, c->smem_sbr, c->stream>>>(g, c->d_W, s->d_elem, c->d_chan, c->d_X, c->d_tables, nullptr, 0u);
-    if (s->ps) k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
-    k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables, nullptr, 0u);
-    c->launches += 3 + s->ps;
+    /* the chain from the element's time samples (no core transform): QMF analysis .. X (.. synthesis without PS) */
+    k_chain<<<s->nch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, 1, s->ps ? 1 : 0, nullptr, s->d_time, nullptr, nullptr, nullptr, s->d_elem,
+                                                                         c->d_chan, c->d_synth, c->d_X, nullptr, s->ps ? nullptr : s->d_out, c->d_tables);
+    if (s->ps) {
+        k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
+        k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables);
+    }
+    c->launches += 1 + 2 * s->ps;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(L, s->d_out, sizeof(float) * 2048, cudaMemcpyDeviceToHost, c->stream));
     if (s->nout == 2) CK(cudaMemcpyAsync(R, s->d_out + 2048, sizeof(float) * 2048, cudaMemcpyDeviceToHost, c->stream));

@@ -17,13 +17,10 @@ struct HeaacContext {
     HeaacChanState *d_chan;          /* [S][ncc] */
     HeaacSynthState *d_synth;        /* [S][nout] (SBR only) */
     HeaacPsState *d_ps;              /* [S] (PS only) */
-    float *d_tns_done;               /* [S][ncc][1024]: TNS-filtered coefficient ranges of the current tick (k_tns -> k_core) */
+    float *d_tns_done;               /* TNS-filtered coefficient ranges (k_tns -> k_core / k_chain), frame-major like coeffs */
+    size_t tns_done_frames;          /* frames d_tns_done holds: 1 for AAC-LC (per frame tick), the call's frames with SBR */
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
-    unsigned *d_sbr_done;            /* per coded channel: tick of the last frame k_sbr finished (k_synth's start signal) */
-    unsigned tick;                   /* frames launched so far */
-    int pdl;                         /* chain the kernels with programmatic dependent launches */
-    float *d_W;                      /* [S][ncc][2][32][32] QMF analysis output of the current frame (SBR only) */
-    float *d_X;                      /* [S][nout][2][38][64] (SBR only) */
+    float *d_X;                      /* [S][nout][2][64][40]: X between k_chain, k_ps and k_synth (PS / downsampled SBR / keep_intermediates) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
     /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
      * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
@@ -36,7 +33,7 @@ struct HeaacContext {
     cudaEvent_t ev_ticket[8];          /* completion marks on s_out, heaac_b200_ticket_* */
     long long n_tickets;
     long long launches;
-    size_t smem_core, smem_sbr, smem_ps, smem_synth;
+    size_t smem_core, smem_chain, smem_ps, smem_synth;
     int core_grid;                   /* persistent k_core: resident CTAs on the whole GPU */
     /* optional per-kernel event timing (heaac_b200_profile_*) */
     int prof_on, prof_n, prof_cap;
@@ -44,7 +41,7 @@ struct HeaacContext {
     unsigned char *prof_kind;        /* HEAAC_K_* per recorded launch */
 };
 
-enum { HEAAC_K_CORE = 0, HEAAC_K_SBR = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
+enum { HEAAC_K_CORE = 0, HEAAC_K_CHAIN = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
 
 /* launches for frames [0, n) of a device-resident batch on c->stream (heaac_api.cu) */
 int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,

@@ -100,10 +100,11 @@ struct HeaacDevTables {
     uint8_t ps_inv_off[2][36], ps_inv_k[2][92];
 };
 
-/* ---- per core channel state -------------------------------------------------------- */
+/* ---- per core channel state --------------------------------------------------------
+ * Members that are moved as blocks start at multiples of 16 bytes and the struct size is a multiple of 16
+ * (cp.async.bulk needs 16-byte aligned addresses and sizes). */
 struct HeaacChanState {
     float saved[512];               /* overlap-add history, sce->saved[0..511] */
-    int32_t prev_ws, prev_shape;    /* ics.window_sequence[1], ics.use_kb_window[1] */
     /* SBR (only touched when cfg.sbr) */
     float ana_hist[288];            /* analysis_filterbank_samples[0..287] */
     float w_tail[2 * 32 * 8];       /* W[1][24..31] of the previous frame, [plane][band][slot - 24] */
@@ -111,10 +112,11 @@ struct HeaacChanState {
     float g_hist[10 * 48];          /* g_temp rows 32..41 (the only rows ever read as history) */
     float q_hist[10 * 48];          /* q_temp rows 32..41 */
     float bw_array[8];
+    int32_t prev_ws, prev_shape;    /* ics.window_sequence[1], ics.use_kb_window[1] */
     uint32_t f_indexnoise, f_indexsine;
     uint8_t s_index0[48];           /* s_indexmapped[0] */
-    uint32_t pad[2];
 };
+static_assert(sizeof(HeaacChanState) % 16 == 0, "HeaacChanState must keep 16-byte granularity");
 
 /* ---- per OUTPUT channel state (QMF synthesis history) ------------------------------- */
 struct HeaacSynthState {

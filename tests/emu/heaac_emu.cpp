@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
-#include "../../ffmpeg-heaac_b200/csrc/heaac_kernels.cuh"
+#include "../../ffmpeg-heaac_b200/csrc/heaac_chain.cuh"
 
 extern "C" void heaac_build_tables(HeaacDevTables *t);
 
@@ -22,6 +22,9 @@ struct EmuCtx {
     HeaacChanState *chan; HeaacSynthState *synth; HeaacPsState *ps;
     float *W, *X;
     HeaacCoreSmem *sm_core; HeaacHfSmem *sm_sbr; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
+    HeaacHfScratch *sm_hf; float *u, *vh;            /* the fused chain's "shared memory" */
+    HeaacSbrElem elem;
+    int old_path;                                    /* 1: round-1 kernels (k_sbr + k_synth) instead of the chain */
 };
 
 static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
@@ -63,6 +66,10 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
     c->sm_sbr = (HeaacHfSmem *)calloc(1, sizeof(HeaacHfSmem));
     c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
     c->sm_synth = (HeaacSynthSmem *)calloc(1, sizeof(HeaacSynthSmem));
+    c->sm_hf = (HeaacHfScratch *)calloc(1, sizeof(HeaacHfScratch));
+    c->u = (float *)calloc(2 * HEAAC_U_PLANE, sizeof(float));
+    c->vh = (float *)calloc(1152, sizeof(float));
+    c->old_path = getenv("HEAAC_EMU_OLD") != nullptr;
     return c;
 }
 
@@ -70,7 +77,7 @@ extern "C" void heaac_emu_destroy(EmuCtx *c)
 {
     if (!c) return;
     free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->W); free(c->X);
-    free(c->sm_core); free(c->sm_sbr); free(c->sm_ps); free(c->sm_synth); free(c);
+    free(c->sm_core); free(c->sm_sbr); free(c->sm_ps); free(c->sm_synth); free(c->sm_hf); free(c->u); free(c->vh); free(c);
 }
 
 extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
@@ -101,7 +108,26 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             memcpy(cbuf, co + gc * 1024, sizeof(cbuf));           /* the kernel stages the coefficients with cp.async */
             heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, nullptr, st, out, bias,
                                g.sr_index, c->T, 0);
-            if (ana) {
+            if (ana && !c->old_path) {
+                /* the fused chain of k_chain: analysis -> HF stage -> synthesis, all on U */
+                const float ana_scale = 1 / qmf_scale;
+                if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
+                memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
+                for (int i = 0; i < 2 * HEAAC_U_PLANE; i++) { uint32_t poison = 0xA5A5A5A5u; memcpy(c->u + i, &poison, 4); }
+                memset(c->sm_hf, 0xA5, sizeof(HeaacHfScratch));
+                heaac_qmf_analysis_u<1>(x, x + 1312, c->u, c->T, 0);
+                const int se = g.ch_sbr_elem[ch];
+                c->elem = sb[s * g.nse + se];
+                heaac_hf_stage<1>(c->u, c->sm_hf, &c->elem, g.ch_in_elem[ch], g.elem_is_cpe[ch], st, c->T, 0);
+                if (g.ps || g.ds) {
+                    heaac_x_emit<1>(c->u, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, 0);
+                } else {
+                    HeaacSynthState *sy = c->synth + gc;
+                    memcpy(c->vh, sy->v, sizeof(sy->v));
+                    heaac_synth_inplace<1>(c->u, c->vh, sy, 1, g.nout, g.out_slot[ch], pc ? pc + s * 2048 * g.nout : nullptr,
+                                           pf ? pf + s * g.nout * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0);
+                }
+            } else if (ana) {
                 const float ana_scale = 1 / qmf_scale;
                 if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
                 memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
@@ -112,7 +138,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             }
         }
         if (!g.sbr) continue;
-        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_sbr */
+        for (size_t gc = 0; c->old_path && gc < S * g.ncc; gc++) {   /* k_sbr (round-1 kernels) */
             size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
             int se = g.ch_sbr_elem[ch];
             if (se == 0xff) continue;
@@ -127,6 +153,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
                 memset(c->sm_ps, 0xA5, sizeof(HeaacPsSmem));
                 heaac_ps_stream<1>(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0);
             }
+        if (!c->old_path && !g.ps && !g.ds) continue;             /* the chain has already produced the PCM */
         for (size_t s = 0; s < S; s++) {                          /* k_synth: one CTA per (stream, SBR element) */
             int o = 0;
             for (int e = 0; e < g.n_elems; e++) {

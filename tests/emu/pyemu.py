@@ -17,7 +17,7 @@ _lib = None
 
 def build():
     srcs = [os.path.join(_HERE, "heaac_emu.cpp"), os.path.join(_ROOT, "ffmpeg-heaac_b200", "csrc", "heaac_tables.cpp")]
-    deps = srcs + [os.path.join(_ROOT, "ffmpeg-heaac_b200", "csrc", f) for f in ("heaac_kernels.cuh", "heaac_dev.cuh")]
+    deps = srcs + [os.path.join(_ROOT, "ffmpeg-heaac_b200", "csrc", f) for f in ("heaac_kernels.cuh", "heaac_dev.cuh", "heaac_chain.cuh", "heaac_sbr.cuh", "heaac_regfft.cuh")]
     if os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno",
