@@ -120,56 +120,19 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
  * k_chain: the whole SBR channel pipeline of a batch in ONE launch.  One CTA owns one coded channel and walks through the
  * frames of the call: core transform (IMDCT + window + overlap-add) -> 32-band QMF analysis -> HF generation / adjustment
  * -> 64-band QMF synthesis -> s16, with every intermediate (the time samples, W, X_low, X_high, Y, X, the v buffer) in
- * shared memory: HBM sees the frame's coefficients and side info, the channel's state and the PCM, nothing else.
- * The coefficients of frame f + 1 are fetched with a bulk asynchronous copy (cp.async.bulk + mbarrier, issued by one
- * thread) while frame f is being processed; the synthesis history stays in shared memory between frames.
+ * shared memory (heaac_chain.cuh): HBM sees the frame's coefficients and side info, the channel's state and the PCM,
+ * nothing else.  The coefficients of frame f + 1 are fetched with a bulk asynchronous copy (cp.async.bulk + mbarrier,
+ * issued by one thread) while frame f is being synthesised; the synthesis history stays in shared memory between frames.
  * emit = 1 (Parametric Stereo, downsampled SBR): the chain stops at X, which goes to the inter-kernel buffer;
  * emit = 2 (keep_intermediates): X is written out as well, and the chain goes on.
  * `time_in` (ff_sbr_apply shim): the element's time samples are given, there is no core transform.
  * ---------------------------------------------------------------------------------- */
 #ifndef HEAAC_CHAIN_THREADS
-#define HEAAC_CHAIN_THREADS 256
+#define HEAAC_CHAIN_THREADS 128
 #endif
 #ifndef HEAAC_CHAIN_MIN_BLOCKS
-#define HEAAC_CHAIN_MIN_BLOCKS 4
+#define HEAAC_CHAIN_MIN_BLOCKS 5
 #endif
-
-struct HeaacChainSmem {
-    float u[2 * HEAAC_U_PLANE];          /* the QMF-domain array of heaac_chain.cuh */
-    float vh[1152];                      /* synthesis history: the 9 v blocks before the current frame */
-    float coef[1024];                    /* coefficients of the current frame, then the half-IMDCT output */
-    HeaacSbrElem p;                      /* SBR side info of the current frame */
-    union alignas(16) {
-        struct { HeaacCoreSmem core; float x[1312]; float tb[64 * 33]; } c;   /* core transform + analysis */
-        HeaacHfScratch hf;                                                     /* HF stage */
-    } s;
-    alignas(8) unsigned long long mbar[2];
-};
-
-__device__ __forceinline__ unsigned heaac_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void heaac_mbar_init(unsigned long long *b, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(heaac_smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void heaac_mbar_expect_tx(unsigned long long *b, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(heaac_smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void heaac_mbar_wait(unsigned long long *b, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(heaac_smem_u32(b)), "r"(parity) : "memory");
-    } while (!ok);
-}
-/* global -> shared bulk copy (TMA engine, no registers involved); completion is signalled on the mbarrier.
- * dst, src and bytes must be multiples of 16. */
-__device__ __forceinline__ void heaac_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(heaac_smem_u32(dst)), "l"(src), "r"(bytes), "r"(heaac_smem_u32(b)) : "memory");
-}
 
 __global__ void __launch_bounds__(HEAAC_CHAIN_THREADS, HEAAC_CHAIN_MIN_BLOCKS)
 k_chain(HeaacGeom g, int n_frames, int emit, const float *__restrict__ coeffs, const float *__restrict__ time_in,
@@ -177,81 +140,31 @@ k_chain(HeaacGeom g, int n_frames, int emit, const float *__restrict__ coeffs, c
         const HeaacSbrElem *__restrict__ sbr, HeaacChanState *chan, HeaacSynthState *synth, float *X,
         int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
-    constexpr int NT = HEAAC_CHAIN_THREADS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     HeaacChainSmem *sm = reinterpret_cast<HeaacChainSmem *>(smem_raw);
-    const int tid = threadIdx.x;
     const int gc = blockIdx.x;
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
     if (se == 0xff) return;                          /* a channel without SBR (uniform per CTA) */
-    const size_t frame_ch = (size_t)g.n_streams * g.ncc;
-    HeaacChanState *st = chan + gc;
-    HeaacSynthState *sy = synth + (size_t)s * g.nout + c;
-    float *x = sm->s.c.x, *out = x + 288;
-    const float qmf_scale = -1024.0f * g.sf_scale;
-    const float ana_scale = 1 / qmf_scale;                                      /* aacsbr.c:1730 */
-
-    if (tid == 0) {
-        heaac_mbar_init(&sm->mbar[0], 1);
-        heaac_mbar_init(&sm->mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (coeffs) {
-            heaac_mbar_expect_tx(&sm->mbar[0], 4096);
-            heaac_bulk_g2s(sm->coef, coeffs + (size_t)gc * 1024, 4096, &sm->mbar[0]);
-        }
-        if (emit != 1) {
-            heaac_mbar_expect_tx(&sm->mbar[1], sizeof(HeaacSynthState));
-            heaac_bulk_g2s(sm->vh, sy->v, sizeof(HeaacSynthState), &sm->mbar[1]);
-        }
-    }
-    for (int f = 0; f < n_frames; f++) {
-        const size_t fo = (size_t)f * frame_ch + gc;
-        {   /* this frame's SBR side info and the analysis history: needed after the core transform */
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(sbr + ((size_t)f * g.n_streams + s) * g.nse + se);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm->p);
-            for (int i = tid; i < (int)(sizeof(HeaacSbrElem) / 4); i += NT) dst[i] = src[i];
-            for (int i = tid; i < 288; i += NT) heaac_cp_async4(x + i, st->ana_hist + i);
-            heaac_cp_async_commit();
-        }
-        if (coeffs) {
-            heaac_mbar_wait(&sm->mbar[0], (unsigned)f & 1u);     /* the coefficients have landed */
-            heaac_core_channel<NT>(&sm->s.c.core, sm->coef, ics + fo, tns ? tns + fo : nullptr,
-                                   tns_done ? tns_done + fo * 1024 : nullptr, st, out, 0.0f, g.sr_index, T, tid);
-            /* (ends with a barrier) the coefficient buffer is free: fetch the next frame's while this one goes on */
-            if (tid == 0 && f + 1 < n_frames) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                heaac_mbar_expect_tx(&sm->mbar[0], 4096);
-                heaac_bulk_g2s(sm->coef, coeffs + (fo + frame_ch) * 1024, 4096, &sm->mbar[0]);
-            }
-            if (ana_scale != 1.0f)
-                for (int i = tid; i < 1024; i += NT) out[i] = out[i] * ana_scale;
-        } else {
-            for (int i = tid; i < 1024; i += NT) {
-                const float v = time_in[fo * 1024 + i];
-                out[i] = ana_scale != 1.0f ? v * ana_scale : v;
-            }
-        }
-        heaac_cp_async_wait<0>();
-        __syncthreads();
-        for (int i = tid; i < 288; i += NT) st->ana_hist[i] = x[1024 + i];
-        heaac_qmf_analysis_u<NT>(x, sm->s.c.tb, sm->u, T, tid);
-        __syncthreads();                             /* U holds W; the core scratch becomes the HF scratch */
-        heaac_hf_stage<NT>(sm->u, &sm->s.hf, &sm->p, g.ch_in_elem[c], g.elem_is_cpe[c], st, T, tid);
-        if (emit) {
-            heaac_x_emit<NT>(sm->u, X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS, tid);
-            __syncthreads();
-        }
-        if (emit != 1) {
-            if (f == 0) heaac_mbar_wait(&sm->mbar[1], 0);
-            const size_t po = ((size_t)f * g.n_streams + s) * 2048 * g.nout;
-            heaac_synth_inplace<NT>(sm->u, sm->vh, sy, f == n_frames - 1, g.nout, g.out_slot[c], pcm ? pcm + po : nullptr,
-                                    pcm_f32 ? pcm_f32 + po : nullptr, qmf_scale, g.add_bias, T, tid);
-        }
-    }
+    HeaacChainArgs a;
+    a.n_frames = n_frames; a.emit = emit;
+    a.frame_ch = (size_t)g.n_streams * g.ncc;
+    a.frame_elems = (size_t)g.n_streams * g.nse;
+    a.pcm_frame = (size_t)g.n_streams * 2048 * g.nout;
+    a.coeffs = coeffs ? coeffs + (size_t)gc * 1024 : nullptr;
+    a.time_in = time_in ? time_in + (size_t)gc * 1024 : nullptr;
+    a.ics = ics ? ics + gc : nullptr;
+    a.tns = tns ? tns + gc : nullptr;
+    a.tns_done = tns_done ? tns_done + (size_t)gc * 1024 : nullptr;
+    a.sbr = sbr + (size_t)s * g.nse + se;
+    a.st = chan + gc;
+    a.sy = synth + (size_t)s * g.nout + c;
+    a.X = X ? X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS : nullptr;
+    a.pcm = pcm ? pcm + (size_t)s * 2048 * g.nout : nullptr;
+    a.pcm_f32 = pcm_f32 ? pcm_f32 + (size_t)s * 2048 * g.nout : nullptr;
+    a.ch_in_elem = g.ch_in_elem[c]; a.is_cpe = g.elem_is_cpe[c]; a.nout = g.nout; a.out_slot = g.out_slot[c]; a.sr_index = g.sr_index;
+    a.qmf_scale = -1024.0f * g.sf_scale; a.add_bias = g.add_bias;
+    heaac_chain_channel<HEAAC_CHAIN_THREADS>(sm, a, T, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)

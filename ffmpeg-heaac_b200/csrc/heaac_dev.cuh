@@ -21,6 +21,7 @@
 #ifdef HEAAC_HOST_EMU
 #define HEAAC_DEV   static inline
 #define HEAAC_SYNC() ((void)0)
+#define HEAAC_SYNCWARP() ((void)0)
 #define HEAAC_LDX(p) (*(p))
 #define HEAAC_RESTRICT
 #include <math.h>
@@ -34,6 +35,7 @@ static inline float heaac_rint(float a) { return rintf(a); }
 #elif defined(__CUDACC__)
 #define HEAAC_DEV   __device__ __forceinline__
 #define HEAAC_SYNC() __syncthreads()
+#define HEAAC_SYNCWARP() __syncwarp()
 /* X may still be being written elsewhere in the grid before (k_sbr / k_synth overlap through per-channel flags): read
  * it through L2, never through the non-coherent path */
 #define HEAAC_LDX(p) __ldcg(p)
@@ -43,8 +45,10 @@ static inline float heaac_rint(float a) { return rintf(a); }
 __device__ __forceinline__ float heaac_fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float heaac_fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float heaac_fsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float heaac_fdiv(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ float heaac_fsqrt(float a) { return __fsqrt_rn(a); }
+/* (division and square root expand to 10-20 instructions plus a slow path each and are used at some thirty places of the
+ * chain kernel, none of them hot: called, not inlined, they keep the kernel's instruction footprint down) */
+static __device__ __noinline__ float heaac_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+static __device__ __noinline__ float heaac_fsqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ float heaac_rint(float a) { return rintf(a); }
 #endif
 

@@ -315,7 +315,9 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
             for (int i = tid; i < size; i += nt) c[lo + i] = tns_done[lo + i];
         }
         HEAAC_SYNC();
-    } else if (use_tns) {
+    }
+#ifdef HEAAC_HOST_EMU                                    /* (the kernels always run the pre-pass; the in-place form serves the logic tests) */
+    else if (use_tns) {
         for (int slot = tid; slot < 8; slot += nt) {
             int start, size, inc, order;
             sm->tns_size[slot] = 0;
@@ -338,7 +340,9 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
             }
         }
         HEAAC_SYNC();
-    } else {
+    }
+#endif
+    else {
         HEAAC_SYNC();
     }
 

@@ -21,10 +21,8 @@ struct EmuCtx {
     HeaacDevTables *T;
     HeaacChanState *chan; HeaacSynthState *synth; HeaacPsState *ps;
     float *W, *X;
-    HeaacCoreSmem *sm_core; HeaacHfSmem *sm_sbr; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
-    HeaacHfScratch *sm_hf; float *u, *vh;            /* the fused chain's "shared memory" */
-    HeaacSbrElem elem;
-    int old_path;                                    /* 1: round-1 kernels (k_sbr + k_synth) instead of the chain */
+    HeaacCoreSmem *sm_core; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
+    HeaacChainSmem *sm_chain;                        /* the fused chain's "shared memory" */
 };
 
 static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
@@ -63,13 +61,9 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
     c->W = (float *)calloc(S * c->g.ncc * 2048, sizeof(float));
     c->X = (float *)calloc(S * c->g.nout * HEAAC_X_FLOATS, sizeof(float));
     c->sm_core = (HeaacCoreSmem *)calloc(1, sizeof(HeaacCoreSmem));
-    c->sm_sbr = (HeaacHfSmem *)calloc(1, sizeof(HeaacHfSmem));
     c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
     c->sm_synth = (HeaacSynthSmem *)calloc(1, sizeof(HeaacSynthSmem));
-    c->sm_hf = (HeaacHfScratch *)calloc(1, sizeof(HeaacHfScratch));
-    c->u = (float *)calloc(2 * HEAAC_U_PLANE, sizeof(float));
-    c->vh = (float *)calloc(1152, sizeof(float));
-    c->old_path = getenv("HEAAC_EMU_OLD") != nullptr;
+    c->sm_chain = (HeaacChainSmem *)calloc(1, sizeof(HeaacChainSmem));
     return c;
 }
 
@@ -77,7 +71,33 @@ extern "C" void heaac_emu_destroy(EmuCtx *c)
 {
     if (!c) return;
     free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->W); free(c->X);
-    free(c->sm_core); free(c->sm_sbr); free(c->sm_ps); free(c->sm_synth); free(c->sm_hf); free(c->u); free(c->vh); free(c);
+    free(c->sm_core); free(c->sm_ps); free(c->sm_synth); free(c->sm_chain); free(c);
+}
+
+/* one coded channel through the fused chain (what one CTA of k_chain does), frames [f0, f0 + n) of the batch */
+static void emu_chain(EmuCtx *c, const HeaacBatch *b, size_t gc, int f0, int n, int emit)
+{
+    const HeaacGeom g = c->g;
+    const size_t S = g.n_streams;
+    const size_t s = gc / g.ncc; const int ch = (int)(gc - s * g.ncc);
+    const int se = g.ch_sbr_elem[ch];
+    HeaacChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_frames = n; a.emit = emit;
+    a.frame_ch = S * g.ncc; a.frame_elems = S * g.nse; a.pcm_frame = S * 2048 * g.nout;
+    a.coeffs = b->coeffs + ((size_t)f0 * a.frame_ch + gc) * 1024;
+    a.ics = b->ics + (size_t)f0 * a.frame_ch + gc;
+    a.tns = b->tns ? b->tns + (size_t)f0 * a.frame_ch + gc : nullptr;
+    a.sbr = b->sbr + (size_t)f0 * a.frame_elems + s * g.nse + se;
+    a.st = c->chan + gc;
+    a.sy = c->synth + s * g.nout + ch;
+    a.X = c->X + (s * g.nout + ch) * HEAAC_X_FLOATS;
+    a.pcm = b->pcm ? b->pcm + (size_t)f0 * a.pcm_frame + s * 2048 * g.nout : nullptr;
+    a.pcm_f32 = b->pcm_f32 ? b->pcm_f32 + (size_t)f0 * a.pcm_frame + s * 2048 * g.nout : nullptr;
+    a.ch_in_elem = g.ch_in_elem[ch]; a.is_cpe = g.elem_is_cpe[ch]; a.nout = g.nout; a.out_slot = g.out_slot[ch]; a.sr_index = g.sr_index;
+    a.qmf_scale = -1024.0f * g.sf_scale; a.add_bias = g.add_bias;
+    memset(c->sm_chain, 0xA5, sizeof(HeaacChainSmem));            /* poison "shared memory" */
+    heaac_chain_channel<1>(c->sm_chain, a, c->T, 0);
 }
 
 extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
@@ -85,6 +105,11 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
     const HeaacGeom g = c->g;
     const size_t S = g.n_streams;
     const float qmf_scale = -1024.0f * g.sf_scale;
+    if (g.sbr && !g.ps && !g.ds) {                                /* HE-AAC v1: k_chain, the whole call per channel */
+        for (size_t gc = 0; gc < S * g.ncc; gc++)
+            if (g.ch_sbr_elem[gc % g.ncc] != 0xff) emu_chain(c, b, gc, 0, b->n_frames, 0);
+        return 0;
+    }
     for (int f = 0; f < b->n_frames; f++) {
         const float *co = b->coeffs + (size_t)f * S * g.ncc * 1024;
         const HeaacIcs *ic = b->ics + (size_t)f * S * g.ncc;
@@ -94,58 +119,25 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
         size_t pcm_frame = S * g.out_len * g.nout;
         int16_t *pc = b->pcm ? b->pcm + (size_t)f * pcm_frame : nullptr;
         float *pf = b->pcm_f32 ? b->pcm_f32 + (size_t)f * pcm_frame : nullptr;
-        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core (+ QMF analysis) */
+        for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core, or k_chain up to X */
             size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
-            static float x[1312 + 64 * 33];
-            float *out = x + 288;
-            float bias = g.sbr ? 0.0f : g.add_bias;
+            if (g.sbr) {
+                if (g.ch_sbr_elem[ch] != 0xff) emu_chain(c, b, gc, f, 1, 1);
+                continue;
+            }
+            static float out[1024];
             HeaacChanState *st = c->chan + gc;
-            bool ana = g.sbr && g.ch_sbr_elem[ch] != 0xff;
             memset(c->sm_core, 0xA5, sizeof(HeaacCoreSmem));      /* poison "shared memory" */
-            memset(x, 0xA5, sizeof(x));
-            if (ana) memcpy(x, st->ana_hist, 288 * sizeof(float));
             static float cbuf[1024];
             memcpy(cbuf, co + gc * 1024, sizeof(cbuf));           /* the kernel stages the coefficients with cp.async */
-            heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, nullptr, st, out, bias,
+            heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, nullptr, st, out, g.add_bias,
                                g.sr_index, c->T, 0);
-            if (ana && !c->old_path) {
-                /* the fused chain of k_chain: analysis -> HF stage -> synthesis, all on U */
-                const float ana_scale = 1 / qmf_scale;
-                if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
-                memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
-                for (int i = 0; i < 2 * HEAAC_U_PLANE; i++) { uint32_t poison = 0xA5A5A5A5u; memcpy(c->u + i, &poison, 4); }
-                memset(c->sm_hf, 0xA5, sizeof(HeaacHfScratch));
-                heaac_qmf_analysis_u<1>(x, x + 1312, c->u, c->T, 0);
-                const int se = g.ch_sbr_elem[ch];
-                c->elem = sb[s * g.nse + se];
-                heaac_hf_stage<1>(c->u, c->sm_hf, &c->elem, g.ch_in_elem[ch], g.elem_is_cpe[ch], st, c->T, 0);
-                if (g.ps || g.ds) {
-                    heaac_x_emit<1>(c->u, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, 0);
-                } else {
-                    HeaacSynthState *sy = c->synth + gc;
-                    memcpy(c->vh, sy->v, sizeof(sy->v));
-                    heaac_synth_inplace<1>(c->u, c->vh, sy, 1, g.nout, g.out_slot[ch], pc ? pc + s * 2048 * g.nout : nullptr,
-                                           pf ? pf + s * g.nout * 2048 : nullptr, qmf_scale, g.add_bias, c->T, 0);
-                }
-            } else if (ana) {
-                const float ana_scale = 1 / qmf_scale;
-                if (ana_scale != 1.0f) for (int i = 0; i < 1024; i++) out[i] = out[i] * ana_scale;
-                memcpy(st->ana_hist, x + 1024, 288 * sizeof(float));
-                heaac_qmf_analysis<1>(x, x + 1312, c->W + gc * 2048, c->T, 0);
-            } else if (!g.sbr) for (int i = 0; i < 1024; i++) {
+            for (int i = 0; i < 1024; i++) {
                 if (pc) pc[(s * 1024 + i) * g.nout + g.out_slot[ch]] = heaac_to_s16(out[i], g.add_bias != 0.0f);
                 if (pf) pf[(s * g.nout + g.out_slot[ch]) * 1024 + i] = out[i];
             }
         }
         if (!g.sbr) continue;
-        for (size_t gc = 0; c->old_path && gc < S * g.ncc; gc++) {   /* k_sbr (round-1 kernels) */
-            size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
-            int se = g.ch_sbr_elem[ch];
-            if (se == 0xff) continue;
-            memset(c->sm_sbr, 0xA5, sizeof(HeaacHfSmem));
-            heaac_hf_channel<1>(c->sm_sbr, c->W + gc * 2048, sb + s * g.nse + se, g.ch_in_elem[ch], g.elem_is_cpe[ch],
-                             c->chan + gc, c->X + (s * g.nout + ch) * HEAAC_X_FLOATS, c->T, 0);
-        }
         if (g.ps)
             for (size_t s = 0; s < S; s++) {                      /* k_ps */
                 float *XL = c->X + s * 2 * (HEAAC_X_FLOATS), *XR = XL + HEAAC_X_FLOATS;
@@ -153,7 +145,6 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
                 memset(c->sm_ps, 0xA5, sizeof(HeaacPsSmem));
                 heaac_ps_stream<1>(c->sm_ps, ps + s, c->ps + s, XL, XR, (int)e->kx[1] + (int)e->m[1], c->T, 0);
             }
-        if (!c->old_path && !g.ps && !g.ds) continue;             /* the chain has already produced the PCM */
         for (size_t s = 0; s < S; s++) {                          /* k_synth: one CTA per (stream, SBR element) */
             int o = 0;
             for (int e = 0; e < g.n_elems; e++) {
@@ -189,7 +180,6 @@ extern "C" int heaac_emu_peek(EmuCtx *c, const char *name, void *dst, int cap)
     if (!strcmp(name, "X")) { p = c->X; n = S * c->g.nout * HEAAC_X_FLOATS * sizeof(float); }
     else if (!strcmp(name, "W")) { p = c->W; n = S * c->g.ncc * 2048 * sizeof(float); }
     else if (!strcmp(name, "chan_state")) { p = c->chan; n = S * c->g.ncc * sizeof(HeaacChanState); }
-    else if (!strcmp(name, "sbr_smem")) { p = c->sm_sbr; n = sizeof(HeaacHfSmem); }
     else if (!strcmp(name, "ps_smem")) { p = c->sm_ps; n = sizeof(HeaacPsSmem); }
     else if (!strcmp(name, "ps_state")) { p = c->ps; n = S * sizeof(HeaacPsState); }
     if (!p) return -1;
