@@ -128,24 +128,31 @@ k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const Heaa
  * `time_in` (ff_sbr_apply shim): the element's time samples are given, there is no core transform.
  * ---------------------------------------------------------------------------------- */
 #ifndef HEAAC_CHAIN_THREADS
-#define HEAAC_CHAIN_THREADS 128
+#define HEAAC_CHAIN_THREADS 128              /* threads per channel */
+#endif
+#ifndef HEAAC_CHAIN_CH
+#define HEAAC_CHAIN_CH 1                     /* channels per CTA (measured: 1 and 2 give the same throughput) */
 #endif
 #ifndef HEAAC_CHAIN_MIN_BLOCKS
-#define HEAAC_CHAIN_MIN_BLOCKS 5
+#define HEAAC_CHAIN_MIN_BLOCKS 5             /* CTAs per SM (shared memory allows 5 channels) */
 #endif
 
-__global__ void __launch_bounds__(HEAAC_CHAIN_THREADS, HEAAC_CHAIN_MIN_BLOCKS)
-k_chain(HeaacGeom g, int n_frames, int emit, const float *__restrict__ coeffs, const float *__restrict__ time_in,
+/* CH channels per CTA, HEAAC_CHAIN_THREADS threads each, in lockstep (every barrier is CTA-wide and reached by all threads
+ * whatever the channels' side info says): the kernel is bound by instruction fetch -- a CTA runs through nearly all of its code
+ * once per frame -- and the channels of a CTA share every fetched line.  `first_ch`: global index of the grid's first channel. */
+template <int CH>
+__global__ void __launch_bounds__(HEAAC_CHAIN_THREADS * CH, CH == HEAAC_CHAIN_CH ? HEAAC_CHAIN_MIN_BLOCKS : 4)
+k_chain(HeaacGeom g, int first_ch, int n_frames, int emit, const float *__restrict__ coeffs, const float *__restrict__ time_in,
         const HeaacIcs *__restrict__ ics, const HeaacTns *__restrict__ tns, const float *__restrict__ tns_done,
         const HeaacSbrElem *__restrict__ sbr, HeaacChanState *chan, HeaacSynthState *synth, float *X,
         int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    HeaacChainSmem *sm = reinterpret_cast<HeaacChainSmem *>(smem_raw);
-    const int gc = blockIdx.x;
+    const int half = threadIdx.x / HEAAC_CHAIN_THREADS, tid = threadIdx.x - half * HEAAC_CHAIN_THREADS;
+    HeaacChainSmem *sm = reinterpret_cast<HeaacChainSmem *>(smem_raw) + half;
+    const int gc = first_ch + blockIdx.x * CH + half;
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
-    if (se == 0xff) return;                          /* a channel without SBR (uniform per CTA) */
     HeaacChainArgs a;
     a.n_frames = n_frames; a.emit = emit;
     a.frame_ch = (size_t)g.n_streams * g.ncc;
@@ -164,7 +171,22 @@ k_chain(HeaacGeom g, int n_frames, int emit, const float *__restrict__ coeffs, c
     a.pcm_f32 = pcm_f32 ? pcm_f32 + (size_t)s * 2048 * g.nout : nullptr;
     a.ch_in_elem = g.ch_in_elem[c]; a.is_cpe = g.elem_is_cpe[c]; a.nout = g.nout; a.out_slot = g.out_slot[c]; a.sr_index = g.sr_index;
     a.qmf_scale = -1024.0f * g.sf_scale; a.add_bias = g.add_bias;
-    heaac_chain_channel<HEAAC_CHAIN_THREADS>(sm, a, T, threadIdx.x);
+    heaac_chain_channel<HEAAC_CHAIN_THREADS>(sm, a, T, tid);
+}
+
+/* all n_ch channels (every channel of an SBR configuration carries SBR): CTAs of HEAAC_CHAIN_CH channels, then the rest one by one */
+static void launch_chain(HeaacContext *c, unsigned n_ch, int n_frames, int emit, const float *coeffs, const float *time_in,
+                         const HeaacIcs *ics, const HeaacTns *tns, const float *tns_done, const HeaacSbrElem *sbr, HeaacChanState *chan,
+                         HeaacSynthState *synth, float *X, int16_t *pcm, float *pcm_f32)
+{
+    const HeaacGeom g = c->geom;
+    const unsigned groups = n_ch / HEAAC_CHAIN_CH, rest = n_ch - groups * HEAAC_CHAIN_CH;
+    if (groups)
+        k_chain<HEAAC_CHAIN_CH><<<groups, HEAAC_CHAIN_THREADS * HEAAC_CHAIN_CH, c->smem_chain * HEAAC_CHAIN_CH, c->stream>>>(
+            g, 0, n_frames, emit, coeffs, time_in, ics, tns, tns_done, sbr, chan, synth, X, pcm, pcm_f32, c->d_tables);
+    if (rest)
+        k_chain<1><<<rest, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(
+            g, (int)(groups * HEAAC_CHAIN_CH), n_frames, emit, coeffs, time_in, ics, tns, tns_done, sbr, chan, synth, X, pcm, pcm_f32, c->d_tables);
 }
 
 __global__ void __launch_bounds__(HEAAC_THREADS)
@@ -386,7 +408,8 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     c->smem_ps = sizeof(HeaacPsSmem);
     c->smem_synth = sizeof(HeaacSynthSmem);
     CKX(cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_core));
-    CKX(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_chain));
+    CKX(cudaFuncSetAttribute(k_chain<HEAAC_CHAIN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_chain * HEAAC_CHAIN_CH));
+    CKX(cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_chain));
     CKX(cudaFuncSetAttribute(k_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_ps));
     CKX(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_synth));
     {
@@ -466,8 +489,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         const int with_x = c->cfg.keep_intermediates != 0;
         if (!g.ps && !g.ds) {                        /* HE-AAC v1: the whole call is one launch */
             prof_begin(c, HEAAC_K_CHAIN);
-            k_chain<<<n_ch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, n_frames, with_x ? 2 : 0, coeffs, nullptr, ics, tns, tns_done, sbr,
-                                                                               c->d_chan, c->d_synth, c->d_X, pcm, pcm_f32, c->d_tables);
+            launch_chain(c, n_ch, n_frames, with_x ? 2 : 0, coeffs, nullptr, ics, tns, tns_done, sbr, c->d_chan, c->d_synth, c->d_X, pcm, pcm_f32);
             prof_end(c);
             c->launches++;
             return heaac_cuda_err(cudaGetLastError(), "kernel launch");
@@ -478,9 +500,8 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
             float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
             prof_begin(c, HEAAC_K_CHAIN);
-            k_chain<<<n_ch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, 1, 1, coeffs + fo * 1024, nullptr, ics + fo, tns ? tns + fo : nullptr,
-                                                                               tns_done ? tns_done + fo * 1024 : nullptr, sb, c->d_chan, c->d_synth,
-                                                                               c->d_X, nullptr, nullptr, c->d_tables);
+            launch_chain(c, n_ch, 1, 1, coeffs + fo * 1024, nullptr, ics + fo, tns ? tns + fo : nullptr, tns_done ? tns_done + fo * 1024 : nullptr,
+                         sb, c->d_chan, c->d_synth, c->d_X, nullptr, nullptr);
             prof_end(c);
             c->launches++;
             if (g.ps) {
@@ -835,8 +856,8 @@ extern "C" int heaac_b200_sbr_apply(HeaacSbrShim *s, const HeaacSbrElem *elem, c
     CK(cudaMemcpyAsync(s->d_elem, elem, sizeof(HeaacSbrElem), cudaMemcpyHostToDevice, c->stream));
     if (s->ps) CK(cudaMemcpyAsync(s->d_psf, psf, sizeof(HeaacPsFrame), cudaMemcpyHostToDevice, c->stream));
     /* the chain from the element's time samples (no core transform): QMF analysis .. X (.. synthesis without PS) */
-    k_chain<<<s->nch, HEAAC_CHAIN_THREADS, c->smem_chain, c->stream>>>(g, 1, s->ps ? 1 : 0, nullptr, s->d_time, nullptr, nullptr, nullptr, s->d_elem,
-                                                                         c->d_chan, c->d_synth, c->d_X, nullptr, s->ps ? nullptr : s->d_out, c->d_tables);
+    launch_chain(c, (unsigned)s->nch, 1, s->ps ? 1 : 0, nullptr, s->d_time, nullptr, nullptr, nullptr, s->d_elem, c->d_chan, c->d_synth, c->d_X,
+                 nullptr, s->ps ? nullptr : s->d_out);
     if (s->ps) {
         k_ps<<<1, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, s->d_psf, s->d_elem, c->d_ps, c->d_X, c->d_tables);
         k_synth<<<1, 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, nullptr, s->d_out, c->d_tables);

@@ -62,6 +62,13 @@ struct HeaacHfTables {
     uint8_t is_mid[48];             /* kx + m is the middle sub-band of its high-resolution band (where a sinusoid sits) */
 };
 
+/* small per-channel state that lives in shared memory for the length of a call (HeaacChanState holds it between calls) */
+struct HeaacHfKeep {
+    uint32_t f_indexnoise, f_indexsine;
+    float bw_array[8];
+    uint8_t s_index0[48];
+};
+
 struct HeaacHfScratch {
     float phi[32][5];               /* per low band: rs0, rs1, is1, rs2, is2 (sums over t = 1..37) */
     float alpha[32][4];             /* a0.re a0.im a1.re a1.im */
@@ -113,6 +120,7 @@ HEAAC_DEV void heaac_hf_build_tables(HeaacHfTables *tb, const HeaacSbrElem *p, c
     const int kx = d->kx;
     for (int w = tid; w < 6 * 48; w += nt) (&tb->band_idx[0][0])[w] = w >= 4 * 48 && w < 5 * 48 ? 255 : 0;
     HEAAC_SYNC();
+    HEAAC_NOUNROLL
     for (int w = tid; w < 152; w += nt) {
         if (w < 49) {                                      /* f_tablehigh band w */
             if (w < d->n_hi) {
@@ -208,6 +216,7 @@ HEAAC_DEV void heaac_ana_window(const float *x, float *u, const HeaacDevTables *
     constexpr int nt = NT;
     constexpr int NG = nt >= 512 ? 8 : nt >= 256 ? 4 : nt >= 128 ? 2 : 1;      /* slot groups */
     constexpr int SL = 32 / NG;
+    HEAAC_NOUNROLL
     for (int w = tid; w < 64 * NG; w += nt) {
         const int k = w & 63, i0 = (w >> 6) * SL;
         const float c0 = T->qmf_ds[k], c1 = T->qmf_ds[k + 64], c2 = T->qmf_ds[k + 128], c3 = T->qmf_ds[k + 192], c4 = T->qmf_ds[k + 256];
@@ -218,7 +227,7 @@ HEAAC_DEV void heaac_ana_window(const float *x, float *u, const HeaacDevTables *
         else { pos = 2 * (64 - k); neg = true; }
         float *dst = u + (pos >> 5) * HEAAC_U_PLANE + (32 + (pos & 31)) * HEAAC_US + HEAAC_UC0 + i0;
         const float *xs = x + 32 * i0 + 319 - k;
-        HEAAC_UNROLL
+        HEAAC_UNROLL4
         for (int i = 0; i < SL; i++, xs += 32) {
             float f = c0 * xs[0];
             f = f + c1 * xs[-64];
@@ -237,6 +246,7 @@ HEAAC_DEV void heaac_ana_transform(float *u, float *qx, const HeaacDevTables *HE
 {
     constexpr int nt = NT < 128 ? NT : 128;
     if (tid < nt)
+        HEAAC_NOUNROLL
         for (int w = tid; w < 128; w += nt) {
             const int q = w & 7, t = (w >> 3) & 3, grp = w >> 5, i = grp * 8 + q;
             const float *src = u + 32 * HEAAC_US + HEAAC_UC0 + i;
@@ -246,6 +256,7 @@ HEAAC_DEV void heaac_ana_transform(float *u, float *qx, const HeaacDevTables *HE
         }
     HEAAC_SYNCWARP();
     if (tid < nt)
+        HEAAC_NOUNROLL
         for (int w = tid; w < 128; w += nt) {
             const int q = w & 7, t = (w >> 3) & 3, grp = w >> 5, i = grp * 8 + q;
             float *ure = u + HEAAC_UC0 + 8 + i, *uim = u + HEAAC_U_PLANE + HEAAC_UC0 + 8 + i;
@@ -262,19 +273,20 @@ HEAAC_DEV void heaac_ana_transform(float *u, float *qx, const HeaacDevTables *HE
  * on threads t = 0 .. n-1 (any n; no barriers inside, every item is computed from the side info alone).
  * ---------------------------------------------------------------------------------- */
 HEAAC_DEV void heaac_hf_params(float *u, HeaacHfScratch *sm, const HeaacHfTables *tb, const HeaacHfDims *d,
-                               const HeaacSbrElem *p, int ch, HeaacChanState *st, int t, int n)
+                               const HeaacSbrElem *p, int ch, HeaacChanState *st, HeaacHfKeep *keep, int t, int n)
 {
     float (*ure)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u);
     float (*uim)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u + HEAAC_U_PLANE);
     const HeaacSbrChan *pc = &p->ch[ch];
-    const int kx0 = d->kx0, m_max = d->m_max, nenv = d->nenv;
-    for (int w = t; w < 32 * 8; w += n) {                  /* sbr_lf_gen: t < 8 = previous frame's W[k][24..31], k < kx' */
-        const int k = w >> 3, i = w & 7, old = k < kx0;
-        ure[k][HEAAC_UC0 + i] = old ? st->w_tail[w] : 0.0f;
-        uim[k][HEAAC_UC0 + i] = old ? st->w_tail[256 + w] : 0.0f;
+    const int m_max = d->m_max, nenv = d->nenv;
+    HEAAC_NOUNROLL
+    for (int w = t; w < 2 * 32 * 8; w += n) {              /* next frame's W tail: t = 32..39, all 32 bands (before anything overwrites them) */
+        const int pl = w >> 8, k = (w >> 3) & 31, i = w & 7;
+        st->w_tail[w] = pl ? uim[k][HEAAC_UC0 + 32 + i] : ure[k][HEAAC_UC0 + 32 + i];
     }
     if (!d->start) return;
     const int smooth = d->h_SL != 0;
+    HEAAC_NOUNROLL
     for (int i = t; i < 40; i += n) {                      /* time grid: envelope of each output slot */
         int e = -1;
         for (int q2 = 0; q2 < nenv; q2++)
@@ -289,6 +301,7 @@ HEAAC_DEV void heaac_hf_params(float *u, HeaacHfScratch *sm, const HeaacHfTables
     }
     /* the g_temp / q_temp rows the smoother reads below the first envelope: rows 2 t_old .. 2 t_old + 3 of the
      * previous frame (aacsbr.c:1637-1640), kept in the state as rows 32..41 */
+    HEAAC_NOUNROLL
     for (int w = t; w < 5 * 48; w += n) {
         const int r = w / 48, m = w - r * 48;
         const int hr = d->t_old2 - 32 + r;
@@ -296,8 +309,9 @@ HEAAC_DEV void heaac_hf_params(float *u, HeaacHfScratch *sm, const HeaacHfTables
         sm->gall[5 + r][m] = have ? st->g_hist[hr * 48 + m] : 0.0f;
         sm->qall[5 + r][m] = have ? st->q_hist[hr * 48 + m] : 0.0f;
     }
+    HEAAC_NOUNROLL
     for (int i = t; i < d->n_q; i += n) {                  /* sbr_chirp */
-        float old = st->bw_array[i], nb;
+        float old = keep->bw_array[i], nb;
         const int m0_ = pc->bs_invf_mode[0][i], m1_ = pc->bs_invf_mode[1][i];
         if (m0_ + m1_ == 1) nb = 0.6f;
         else nb = m0_ == 0 ? 0.0f : m0_ == 1 ? 0.75f : m0_ == 2 ? 0.9f : 0.98f;
@@ -305,9 +319,10 @@ HEAAC_DEV void heaac_hf_params(float *u, HeaacHfScratch *sm, const HeaacHfTables
         else          nb = heaac_fadd(heaac_fmul(0.90625f, nb), heaac_fmul(0.09375f, old));
         nb = nb < 0.015625f ? 0.0f : nb;
         sm->bw[i] = nb;
-        st->bw_array[i] = nb;
+        keep->bw_array[i] = nb;
     }
     /* sbr_dequant + sbr_mapping + the signal-independent halves of sbr_gain_calc (aacsbr.c:1566-1571), per (envelope, band) */
+    HEAAC_NOUNROLL
     for (int w = t; w < nenv * 48; w += n) {
         const int e = w / 48, m = w - e * 48;
         if (m >= m_max) continue;
@@ -316,12 +331,12 @@ HEAAC_DEV void heaac_hf_params(float *u, HeaacHfScratch *sm, const HeaacHfTables
         const int kq = (d->nnoise > 1) && (pc->t_env[e] >= pc->t_q[1]);
         const float eo = heaac_env_dequant(p, ch, d->coupled, e, b);
         const float qm = heaac_noise_dequant(p, ch, d->coupled, kq, tb->noise_idx[m]);
-        const int sine = heaac_sine_at(pc, tb, st->s_index0, d->e_a1, e, m);
+        const int sine = heaac_sine_at(pc, tb, keep->s_index0, d->e_a1, e, m);
         const uint8_t *tab = fr ? p->f_tablehigh : p->f_tablelow;
         int present = 0;
         if (pc->bs_add_harmonic_flag)
             for (int mm = tab[b]; mm < (int)tab[b + 1]; mm++)
-                if ((unsigned)(mm - d->kx) < 48u && heaac_sine_at(pc, tb, st->s_index0, d->e_a1, e, mm - d->kx)) { present = 1; break; }
+                if ((unsigned)(mm - d->kx) < 48u && heaac_sine_at(pc, tb, keep->s_index0, d->e_a1, e, mm - d->kx)) { present = 1; break; }
         const float temp = heaac_fdiv(eo, heaac_fadd(1.0f, qm));
         sm->e_orig[e][m] = eo;
         sm->q_map[e][m] = qm;
@@ -355,69 +370,32 @@ HEAAC_DEV void heaac_limit(const HeaacHfScratch *sm, const HeaacHfTables *tb, in
     *g_o = HEAAC_MIN(g, gain_max);
 }
 
-/* u    : U of this channel; rows < 32: X_low complete (analysis output of this frame in t = 8..39, the previous frame's
- *        tail in t < 8), heaac_hf_params done
- * After the call U[k][i + 2], i = 0..37, k < d->top is X[i][k] of sbr_x_gen (both planes). */
-template <int NT>
-HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables *tb, const HeaacHfDims *d,
-                              const HeaacSbrElem *p, int ch, HeaacChanState *st, int zero_to,
-                              const HeaacDevTables *HEAAC_RESTRICT T, int tid)
+/* ------------------------------------------------------------------------------------
+ * sbr_hf_inverse_filter (aacsbr.c:1261-1313) with its autocorrelation (1232-1255): one thread per low band, the five sums of
+ * a band share the loads of x[t], x[t+1], x[t+2] and each keeps the reference's order over t = 1..37.  Runs on one warp
+ * beside heaac_hf_params.  Threads t = 0 .. n-1.
+ * ---------------------------------------------------------------------------------- */
+HEAAC_DEV void heaac_hf_lpc(const float *u, HeaacHfScratch *sm, const HeaacHfDims *d, int t, int n)
 {
-    constexpr int nt = NT;
-    float (*ure)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u);
-    float (*uim)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u + HEAAC_U_PLANE);
-    const HeaacSbrChan *pc = &p->ch[ch];
-    const int kx = d->kx, m_max = d->m_max, nenv = d->nenv, i_lo = d->i_lo, i_hi = d->i_hi;
-    const int warp = HEAAC_WARP(tid, nt), nwarps = HEAAC_NWARPS(nt), lane = HEAAC_LANE(tid, nt), ls = HEAAC_LSTRIDE(nt);
-    const int smooth = d->start && d->h_SL;
+    if (!d->start) return;
     constexpr int C0 = HEAAC_UC0;
-
-    /* ================= phase 2: autocorrelation | next frame's W tail ================= */
-    if (d->start) {
-        /* aacsbr.c:1232-1255.  Two work items per low band: the three "real" sums and the two "imaginary" ones; each
-         * keeps the reference's own order over t = 1..37 and shares the loads of x[t], x[t+1], x[t+2] */
-        for (int w = tid; w < 64; w += nt) {
-            const int k = w & 31, part = w >> 5;
-            if (k >= d->k0) continue;
-            const float *xr = &ure[k][C0], *xi = &uim[k][C0];
+    HEAAC_NOUNROLL
+    for (int k = t; k < d->k0; k += n) {
+        const float *xr = u + k * HEAAC_US + C0, *xi = xr + HEAAC_U_PLANE;
+        float rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, is1 = 0.0f, is2 = 0.0f;
+        {
             float r1 = xr[1], i1 = xi[1], r2 = xr[2], i2 = xi[2];
-            if (part == 0) {
-                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-                for (int i = 1; i < 38; i++) {
-                    const float r3 = xr[i + 2], i3 = xi[i + 2];
-                    s0 = heaac_fadd(s0, heaac_fadd(heaac_fmul(r1, r1), heaac_fmul(i1, i1)));
-                    s1 = heaac_fadd(s1, heaac_fadd(heaac_fmul(r1, r2), heaac_fmul(i1, i2)));
-                    s2 = heaac_fadd(s2, heaac_fadd(heaac_fmul(r1, r3), heaac_fmul(i1, i3)));
-                    r1 = r2; i1 = i2; r2 = r3; i2 = i3;
-                }
-                sm->phi[k][0] = s0; sm->phi[k][1] = s1; sm->phi[k][3] = s2;
-            } else {
-                float s1 = 0.0f, s2 = 0.0f;
-                for (int i = 1; i < 38; i++) {
-                    const float r3 = xr[i + 2], i3 = xi[i + 2];
-                    s1 = heaac_fadd(s1, heaac_fsub(heaac_fmul(r1, i2), heaac_fmul(i1, r2)));
-                    s2 = heaac_fadd(s2, heaac_fsub(heaac_fmul(r1, i3), heaac_fmul(i1, r3)));
-                    r1 = r2; i1 = i2; r2 = r3; i2 = i3;
-                }
-                sm->phi[k][2] = s1; sm->phi[k][4] = s2;
+            HEAAC_UNROLL4
+            for (int i = 1; i < 38; i++) {
+                const float r3 = xr[i + 2], i3 = xi[i + 2];
+                rs0 = heaac_fadd(rs0, heaac_fadd(heaac_fmul(r1, r1), heaac_fmul(i1, i1)));
+                rs1 = heaac_fadd(rs1, heaac_fadd(heaac_fmul(r1, r2), heaac_fmul(i1, i2)));
+                is1 = heaac_fadd(is1, heaac_fsub(heaac_fmul(r1, i2), heaac_fmul(i1, r2)));
+                rs2 = heaac_fadd(rs2, heaac_fadd(heaac_fmul(r1, r3), heaac_fmul(i1, i3)));
+                is2 = heaac_fadd(is2, heaac_fsub(heaac_fmul(r1, i3), heaac_fmul(i1, r3)));
+                r1 = r2; i1 = i2; r2 = r3; i2 = i3;
             }
         }
-    }
-    {   /* next frame's W tail: t = 32..39, all 32 bands (before anything overwrites them); the threads without an
-         * autocorrelation item go first */
-        constexpr int first = nt > 64 ? 64 : 0;
-        for (int w = (tid + nt - first) % nt; w < 2 * 32 * 8; w += nt) {
-            const int pl = w >> 8, k = (w >> 3) & 31, i = w & 7;
-            st->w_tail[w] = pl ? uim[k][C0 + 32 + i] : ure[k][C0 + 32 + i];
-        }
-    }
-    HEAAC_SYNC();
-
-    if (d->start) {
-        /* ================= phase 3: LPC per low band (aacsbr.c:1261-1313) ================= */
-        for (int k = tid; k < d->k0; k += nt) {
-            const float *xr = &ure[k][C0], *xi = &uim[k][C0];
-            const float rs0 = sm->phi[k][0], rs1 = sm->phi[k][1], is1 = sm->phi[k][2], rs2 = sm->phi[k][3], is2 = sm->phi[k][4];
             float phi210 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(xr[0], xr[0])), heaac_fmul(xi[0], xi[0]));
             float phi100 = heaac_fadd(heaac_fadd(rs0, heaac_fmul(xr[38], xr[38])), heaac_fmul(xi[38], xi[38]));
             float phi110 = heaac_fadd(heaac_fadd(rs1, heaac_fmul(xr[0], xr[1])), heaac_fmul(xi[0], xi[1]));
@@ -449,8 +427,30 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 heaac_fadd(heaac_fmul(a0r, a0r), heaac_fmul(a0i, a0i)) >= 16.0f)
                 a1r = a1i = a0r = a0i = 0.0f;
             sm->alpha[k][0] = a0r; sm->alpha[k][1] = a0i; sm->alpha[k][2] = a1r; sm->alpha[k][3] = a1i;
-        }
-        HEAAC_SYNC();
+    }
+}
+
+/* u    : U of this channel; rows < 32: X_low complete (analysis output of this frame in t = 8..39, the previous frame's
+ *        tail in t < 8), heaac_hf_params done
+ * After the call U[k][i + 2], i = 0..37, k < d->top is X[i][k] of sbr_x_gen (both planes). */
+template <int NT>
+HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables *tb, const HeaacHfDims *d,
+                              const HeaacSbrElem *p, int ch, HeaacChanState *st, const HeaacHfKeep *keep, int zero_to,
+                              const HeaacDevTables *HEAAC_RESTRICT T, int tid)
+{
+    constexpr int nt = NT;
+    float (*ure)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u);
+    float (*uim)[HEAAC_US] = reinterpret_cast<float (*)[HEAAC_US]>(u + HEAAC_U_PLANE);
+    const HeaacSbrChan *pc = &p->ch[ch];
+    const int kx = d->kx, m_max = d->m_max, nenv = d->nenv, i_lo = d->i_lo, i_hi = d->i_hi;
+    const int warp = HEAAC_WARP(tid, nt), nwarps = HEAAC_NWARPS(nt), lane = HEAAC_LANE(tid, nt), ls = HEAAC_LSTRIDE(nt);
+    const int smooth = d->start && d->h_SL;
+    constexpr int C0 = HEAAC_UC0;
+
+    /* (every barrier below is reached by every thread whatever the side info says: two channels with different side info may share
+     * a CTA, heaac_chain_channel) */
+    const bool on = d->start;
+    if (on) {
 
         /* ================= phase 4: sbr_hf_gen, lanes = target bands, each warp item one stretch of time slots with the
          * two previous low-band samples carried in registers ================= */
@@ -459,6 +459,7 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
             const int t_first = i_lo + 2, t_end = i_hi + 2;
             const int len = (t_end - t_first + NCH - 1) / NCH;
             const int groups = (m_max + 31) >> 5;
+            HEAAC_NOUNROLL
             for (int w = tid; w < NCH * groups * 32; w += nt) {
                 const int m = (w & 31) + 32 * ((w >> 5) / NCH), c = (w >> 5) % NCH;
                 if (m >= m_max) continue;
@@ -483,10 +484,13 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 }
             }
         }
-        HEAAC_SYNC();
+    }
+    HEAAC_SYNC();
+    if (on) {
 
         /* ================= phase 5: sbr_env_estimate, one item per (envelope, band), serial over the envelope's slots ================= */
         if (p->bs_interpol_freq) {
+            HEAAC_NOUNROLL
             for (int w = tid; w < nenv * 48; w += nt) {
                 const int e = w / 48, m = w - e * 48;
                 if (m >= m_max) continue;
@@ -499,6 +503,7 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 sm->e_curr[e][m] = heaac_fmul(sum, recip);
             }
         } else {
+            HEAAC_NOUNROLL
             for (int w = tid; w < nenv * 64; w += nt) {    /* one item per envelope band: the whole group in the reference's order */
                 const int e = w >> 6, b = w & 63;
                 const int fr = pc->bs_freq_res[e + 1] & 1;
@@ -517,10 +522,13 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 for (int k = lo; k < hi; k++) sm->e_curr[e][k - kx] = sum;
             }
         }
-        HEAAC_SYNC();
+    }
+    HEAAC_SYNC();
+    if (on) {
 
         /* ================= phase 6: sbr_gain_calc, aacsbr.c:1552-1605 ================= */
         /* (a) the gain of every (envelope, band) and the limit of every (envelope, limiter band) */
+        HEAAC_NOUNROLL
         for (int w = tid; w < nenv * 48; w += nt) {
             const int e = w / 48, m = w - e * 48;
             if (m >= m_max) continue;
@@ -533,6 +541,7 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 sm->gall[e][m] = heaac_fsqrt(heaac_fdiv(heaac_fmul(eo, qm),
                                              heaac_fmul(heaac_fadd(1.0f, ec), heaac_fadd(1.0f, qm))));
         }
+        HEAAC_NOUNROLL
         for (int w = nt - 1 - tid; w < nenv * HEAAC_MAX_LIM; w += nt) {   /* (from the far end of the CTA: those threads have no gain item) */
             const int e = w / HEAAC_MAX_LIM, k = w - e * HEAAC_MAX_LIM;
             if (k >= d->n_lim) continue;
@@ -545,8 +554,11 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
             sm->gmax[e][k] = HEAAC_MIN(100000.0f, gain_max);
             sm->sum0[e][k] = sum0;
         }
-        HEAAC_SYNC();
+    }
+    HEAAC_SYNC();
+    if (on) {
         /* (b) the boost of every (envelope, limiter band), from the limited gains (worked out on the fly) */
+        HEAAC_NOUNROLL
         for (int w = tid; w < nenv * HEAAC_MAX_LIM; w += nt) {
             const int e = w / HEAAC_MAX_LIM, k = w - e * HEAAC_MAX_LIM;
             if (k >= d->n_lim) continue;
@@ -566,8 +578,11 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
             /* FFMIN(1.584893192 (double), gain_boost) then narrowed to float */
             sm->gboost[e][k] = (1.584893192 > (double)gain_boost) ? gain_boost : (float)1.584893192;
         }
-        HEAAC_SYNC();
+    }
+    HEAAC_SYNC();
+    if (on) {
         /* (c) limit + boost of every (envelope, band) */
+        HEAAC_NOUNROLL
         for (int w = tid; w < nenv * 48; w += nt) {
             const int e = w / 48, m = w - e * 48;
             if (m >= m_max) continue;
@@ -588,10 +603,12 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 sm->gsm[e][m] = g_filt; sm->qsm[e][m] = q_filt;
             }
         }
-        HEAAC_SYNC();
+    }
+    HEAAC_SYNC();
+    if (on) {
 
         /* ================= phase 7: sbr_hf_assemble in place, U[kx + m][i + 2] <- Y[i][kx + m] ================= */
-        const uint32_t noise0 = d->reset ? 0u : st->f_indexnoise, sine0 = st->f_indexsine;
+        const uint32_t noise0 = d->reset ? 0u : keep->f_indexnoise, sine0 = keep->f_indexsine;
         const int kx_sign = 1 - 2 * (kx & 1);
         {   /* (a) slots 0..31 whose gain is constant per (envelope, band): rows = bands, lanes = slots; everything that
              * depends on the slot only is worked out once per lane */
@@ -669,8 +686,8 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
                 }
             }
         }
-        HEAAC_SYNC();
     }
+    HEAAC_SYNC();
 
     /* ================= phase 8: sbr_x_gen -- cells no stage wrote, below `top` only ================= */
     {
@@ -678,6 +695,7 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
         const int hf_lo = d->start ? kx : 64, hf_hi = d->start ? kx + m_max : 64;
         /* (a) slots below i_temp still belong to the previous frame's grid (aacsbr.c:1420-1431): its Y tail, zeros above its band range */
         if (i_temp > 0)
+            HEAAC_NOUNROLL
             for (int w = tid; w < 64 * 8; w += nt) {
                 const int k = w >> 3, j = w & 7;
                 if (j >= i_temp || j >= 6 || k < kx0 || k >= top) continue;
@@ -701,19 +719,21 @@ HEAAC_DEV void heaac_hf_stage(float *u, HeaacHfScratch *sm, const HeaacHfTables 
 
 /* The state the next frame needs from this one (reads U slots 32..37 and the scratch only: may run beside the
  * synthesis transforms, which work on slots 0..31); threads t = 0 .. n-1 */
-HEAAC_DEV void heaac_hf_save(const float *u, const HeaacHfScratch *sm, const HeaacHfDims *d, HeaacChanState *st, int t, int n)
+HEAAC_DEV void heaac_hf_save(const float *u, const HeaacHfScratch *sm, const HeaacHfDims *d, HeaacChanState *st, HeaacHfKeep *keep, int t, int n)
 {
     if (!d->start) return;
     const float (*ure)[HEAAC_US] = reinterpret_cast<const float (*)[HEAAC_US]>(u);
     const float (*uim)[HEAAC_US] = reinterpret_cast<const float (*)[HEAAC_US]>(u + HEAAC_U_PLANE);
     const int kx = d->kx, m_max = d->m_max, i_lo = d->i_lo, i_hi = d->i_hi, nenv = d->nenv;
     constexpr int C0 = HEAAC_UC0;
+    HEAAC_NOUNROLL
     for (int w = t; w < m_max * 8; w += n) {               /* the Y tail: slots 32..37 of the high band */
         const int k = kx + (w >> 3), j = w & 7;
         if (j < 6 && 32 + j >= i_lo && 32 + j < i_hi) {
             st->y_tail[k * 8 + j] = ure[k][C0 + 34 + j]; st->y_tail[512 + k * 8 + j] = uim[k][C0 + 34 + j];
         }
     }
+    HEAAC_NOUNROLL
     for (int w = t; w < 10 * 48; w += n) {                 /* g_temp / q_temp rows 32..41 for the next frame, aacsbr.c:1642-1647 */
         const int r = 32 + w / 48, m = w % 48;
         const int src = r - d->h_SL;
@@ -722,11 +742,12 @@ HEAAC_DEV void heaac_hf_save(const float *u, const HeaacHfScratch *sm, const Hea
             if (es >= 0) { st->g_hist[w] = sm->gall[es][m]; st->q_hist[w] = sm->qall[es][m]; }
         }
     }
-    for (int m = t; m < 48; m += n) st->s_index0[m] = m < m_max ? sm->s_idx[nenv - 1][m] : 0;
+    HEAAC_NOUNROLL
+    for (int m = t; m < 48; m += n) keep->s_index0[m] = m < m_max ? sm->s_idx[nenv - 1][m] : 0;
     if (t == 0) {
-        const uint32_t noise0 = d->reset ? 0u : st->f_indexnoise;
-        st->f_indexnoise = (noise0 + (uint32_t)(i_hi - i_lo) * (uint32_t)m_max) & 0x1ff;
-        st->f_indexsine = (st->f_indexsine + (uint32_t)(i_hi - i_lo)) & 3;
+        const uint32_t noise0 = d->reset ? 0u : keep->f_indexnoise;
+        keep->f_indexnoise = (noise0 + (uint32_t)(i_hi - i_lo) * (uint32_t)m_max) & 0x1ff;
+        keep->f_indexsine = (keep->f_indexsine + (uint32_t)(i_hi - i_lo)) & 3;
     }
 }
 
@@ -761,6 +782,7 @@ HEAAC_DEV void heaac_synth_transforms(float *u, float *qx, int top, const HeaacD
     constexpr int nt = NT < 128 ? NT : 128;
     for (int round = 0; round < 2; round++) {              /* round = plane */
         if (tid < nt)
+            HEAAC_NOUNROLL
             for (int w = tid; w < 128; w += nt) {
                 const int q = w & 7, t = (w >> 3) & 3, grp = w >> 5, i = grp * 8 + q;
                 const float *col = u + round * HEAAC_U_PLANE + HEAAC_UC0 + 2 + i;
@@ -773,6 +795,7 @@ HEAAC_DEV void heaac_synth_transforms(float *u, float *qx, int top, const HeaacD
             }
         HEAAC_SYNCWARP();
         if (tid < nt)
+            HEAAC_NOUNROLL
             for (int w = tid; w < 128; w += nt) {
                 const int q = w & 7, t = (w >> 3) & 3, grp = w >> 5, i = grp * 8 + q;
                 float *col = u + round * HEAAC_U_PLANE + HEAAC_UC0 + 2 + i;
@@ -806,36 +829,45 @@ HEAAC_DEV void heaac_synth_output(float *u, int nout, int out_slot, int16_t *pcm
      *      imaginary (j even) or real (j odd) plane -- two rows per output sample, walked with a register window; the first
      *      group of slots runs on into the history columns (which lie 2 columns further left) ---- */
     constexpr int G = NT >= 256 ? 4 : NT >= 128 ? 2 : 1;   /* groups of consecutive slots */
-    constexpr int L = 32 / G;
+    constexpr int L = 32 / G, CH = 8;                      /* a group is worked off in chunks of CH slots: the loop stays rolled */
     const int scale_and_bias = scale != 1.0f || bias != 0.0f;
     const int bias_mode = bias != 0.0f;
+    HEAAC_NOUNROLL
     for (int w = tid; w < 64 * G; w += nt) {
         const int n = w & 63, i0 = (w >> 6) * L;
-        float wj[10], im[L + 9], re[L + 9];
+        float wj[10], im[CH + 9], re[CH + 9];
         HEAAC_UNROLL
         for (int j = 0; j < 10; j++) wj[j] = T->qmf_us[64 * j + n];
         const int gap = i0 == 0 ? 2 : 0;
-        const float *rowi = uim + n * HEAAC_US + CS + i0 - 9, *rowr = ure + n * HEAAC_US + CS + i0 - 9;
+        const float *rowi = uim + n * HEAAC_US + CS + i0, *rowr = ure + n * HEAAC_US + CS + i0;
         HEAAC_UNROLL
-        for (int a = 0; a < L + 9; a++) {                  /* a <-> slot i0 - 9 + a */
-            im[a] = rowi[a < 9 ? a - gap : a];
-            re[a] = rowr[a < 9 ? a - gap : a];
+        for (int a = 0; a < 9; a++) {                      /* a <-> slot i0 - 9 + a */
+            im[a] = rowi[a - 9 - gap];
+            re[a] = rowr[a - 9 - gap];
         }
         int16_t *po = pcm ? pcm + ((size_t)i0 * 64 + n) * nout + out_slot : nullptr;
         float *pf = pcm_f32 ? pcm_f32 + (size_t)out_slot * 2048 + i0 * 64 + n : nullptr;
-        HEAAC_UNROLL
-        for (int ii = 0; ii < L; ii++) {
-            float acc = im[9 + ii] * wj[0] + 0.0f;
+        HEAAC_NOUNROLL
+        for (int c = 0; c < L; c += CH) {
             HEAAC_UNROLL
-            for (int j = 1; j < 10; j++)
-                acc = ((j & 1) ? re[9 + ii - j] : im[9 + ii - j]) * wj[j] + acc;
-            if (scale_and_bias) acc = acc * scale + bias;
-            if (po) po[(size_t)ii * 64 * nout] = heaac_to_s16(acc, bias_mode);
-            if (pf) pf[ii * 64] = acc;
+            for (int a = 0; a < CH; a++) { im[9 + a] = rowi[c + a]; re[9 + a] = rowr[c + a]; }
+            HEAAC_UNROLL
+            for (int ii = 0; ii < CH; ii++) {
+                float acc = im[9 + ii] * wj[0] + 0.0f;
+                HEAAC_UNROLL
+                for (int j = 1; j < 10; j++)
+                    acc = ((j & 1) ? re[9 + ii - j] : im[9 + ii - j]) * wj[j] + acc;
+                if (scale_and_bias) acc = acc * scale + bias;
+                if (po) po[(size_t)(c + ii) * 64 * nout] = heaac_to_s16(acc, bias_mode);
+                if (pf) pf[(c + ii) * 64] = acc;
+            }
+            HEAAC_UNROLL
+            for (int a = 0; a < 9; a++) { im[a] = im[CH + a]; re[a] = re[CH + a]; }
         }
     }
     HEAAC_SYNC();
     /* the newest 9 blocks (slots 23..31) become the history: columns CS + 23 .. CS + 31 -> 0 .. 8 */
+    HEAAC_NOUNROLL
     for (int w = tid; w < 128 * 9; w += nt) {
         const int r = w / 9, b = w - r * 9;
         u[r * HEAAC_US + b] = u[r * HEAAC_US + CS + 23 + b];
@@ -848,6 +880,7 @@ template <int NT>
 HEAAC_DEV void heaac_synth_hist_load(float *u, const HeaacSynthState *st, int tid)
 {
     constexpr int nt = NT;
+    HEAAC_NOUNROLL
     for (int w = tid; w < 1152; w += nt) {
         const int b = w >> 7, idx = w & 127;
         u[(idx < 64 ? HEAAC_U_PLANE + idx * HEAAC_US : (idx - 64) * HEAAC_US) + 8 - b] = st->v[w];
@@ -857,6 +890,7 @@ template <int NT>
 HEAAC_DEV void heaac_synth_hist_store(const float *u, HeaacSynthState *st, int tid)
 {
     constexpr int nt = NT;
+    HEAAC_NOUNROLL
     for (int w = tid; w < 1152; w += nt) {
         const int b = w >> 7, idx = w & 127;
         st->v[w] = u[(idx < 64 ? HEAAC_U_PLANE + idx * HEAAC_US : (idx - 64) * HEAAC_US) + 8 - b];
@@ -868,8 +902,9 @@ HEAAC_DEV void heaac_synth_hist_store(const float *u, HeaacSynthState *st, int t
  * ---------------------------------------------------------------------------------- */
 struct HeaacChainSmem {
     float u[HEAAC_U_FLOATS];
-    HeaacSbrElem p;                      /* SBR side info of the current frame */
+    HeaacSbrElem p2[2];                  /* SBR side info of the current frame and (being fetched) of the next one */
     HeaacHfTables tb;
+    HeaacHfKeep keep;
     HeaacHfDims d;
     int hdr_changed;
     union alignas(16) {
@@ -930,37 +965,54 @@ template <int NT>
 HEAAC_DEV void heaac_chain_channel(HeaacChainSmem *sm, const HeaacChainArgs &a, const HeaacDevTables *HEAAC_RESTRICT T, int tid)
 {
     constexpr int nt = NT;
+    constexpr bool SPLIT = nt > 32;                  /* one warp runs the inverse filter while the others do the side-info work */
     float *x = sm->s.c.x, *out = x + 288;
     const float ana_scale = 1 / a.qmf_scale;                                    /* aacsbr.c:1730 */
     HeaacChanState *st = a.st;
+    constexpr int P_WORDS = (int)(sizeof(HeaacSbrElem) / 4);
 
     if (tid == 0) { heaac_fetch_setup(&sm->mbar[0]); sm->hdr_changed = 1; }
     HEAAC_SYNC();
     if (tid == 0 && a.coeffs) heaac_fetch_issue(sm->s.c.coef, a.coeffs, 4096, &sm->mbar[0]);
     if (a.emit != 1) heaac_synth_hist_load<NT>(sm->u, a.sy, tid);
+    for (int i = tid; i < 8; i += nt) sm->keep.bw_array[i] = st->bw_array[i];
+    for (int i = tid; i < 48; i += nt) sm->keep.s_index0[i] = st->s_index0[i];
+    if (tid == 0) { sm->keep.f_indexnoise = st->f_indexnoise; sm->keep.f_indexsine = st->f_indexsine; }
+    for (int i = tid; i < P_WORDS; i += nt)          /* the first frame's side info */
+        heaac_cp_async4(reinterpret_cast<float *>(&sm->p2[0]) + i, reinterpret_cast<const float *>(a.sbr) + i);
+    heaac_cp_async_commit();
     for (int f = 0; f < a.n_frames; f++) {
         const size_t fo = (size_t)f * a.frame_ch;
-        {   /* this frame's SBR side info; did the header part (frequency tables, patches) change? */
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sbr + (size_t)f * a.frame_elems);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm->p);
-            for (int i = tid; i < (int)(sizeof(HeaacSbrElem) / 4); i += nt) {
-                const uint32_t v = src[i];
-                if (i < HEAAC_HDR_WORDS && v != dst[i]) sm->hdr_changed = 1;
-                dst[i] = v;
+        const HeaacSbrElem *p = &sm->p2[f & 1];
+        /* fetched while the previous frame was synthesised: this frame's side info; now under way: the analysis history, the
+         * overlap-add history (straight to where the windowing puts its output) and the low band's first 8 time slots
+         * (sbr_lf_gen, aacsbr.c:1337-1357: the previous frame's W[k][24..31]) */
+        heaac_cp_async_wait<0>();
+        for (int i = tid; i < 72; i += nt) heaac_cp_async16(x + 4 * i, st->ana_hist + 4 * i);
+        if (a.coeffs)
+            for (int i = tid; i < 128; i += nt) heaac_cp_async16(out + 4 * i, st->saved + 4 * i);
+        for (int w = tid; w < 2 * 32 * 8; w += nt)
+            heaac_cp_async4(sm->u + (w >> 8) * HEAAC_U_PLANE + ((w >> 3) & 31) * HEAAC_US + HEAAC_UC0 + (w & 7), st->w_tail + w);
+        heaac_cp_async_commit();
+        HEAAC_SYNC();
+        {   /* did the header part (frequency tables, patches) change? */
+            if (f > 0) {
+                const uint32_t *cur = reinterpret_cast<const uint32_t *>(p), *old = reinterpret_cast<const uint32_t *>(&sm->p2[(f & 1) ^ 1]);
+                for (int i = tid; i < HEAAC_HDR_WORDS; i += nt)
+                    if (cur[i] != old[i]) sm->hdr_changed = 1;
             }
-            for (int i = tid; i < 72; i += nt) heaac_cp_async16(x + 4 * i, st->ana_hist + 4 * i);
-            heaac_cp_async_commit();
-            HEAAC_SYNC();
-            if (tid == 0) heaac_hf_dims(&sm->d, &sm->p, a.ch_in_elem, a.is_cpe);
-            if (sm->hdr_changed || sm->p.reset) {    /* (uniform; the flag is cleared behind the next barriers) */
+            /* barrier; rebuild the tables when any channel of the CTA needs it (the barriers inside must be uniform) */
+            const int rebuild = HEAAC_SYNC_OR(sm->hdr_changed || p->reset);
+            if (tid == 0) heaac_hf_dims(&sm->d, p, a.ch_in_elem, a.is_cpe);
+            if (rebuild) {
                 HEAAC_SYNC();
-                heaac_hf_build_tables<NT>(&sm->tb, &sm->p, &sm->d, tid);
+                heaac_hf_build_tables<NT>(&sm->tb, p, &sm->d, tid);
             }
         }
         if (a.coeffs) {
             heaac_fetch_wait(&sm->mbar[0], (unsigned)f & 1u);    /* the coefficients have landed */
             heaac_core_channel<NT>(&sm->s.c.core, sm->s.c.coef, a.ics + fo, a.tns ? a.tns + fo : nullptr,
-                                   a.tns_done ? a.tns_done + fo * 1024 : nullptr, st, out, 0.0f, a.sr_index, T, tid);
+                                   a.tns_done ? a.tns_done + fo * 1024 : nullptr, st, out, 0.0f, a.sr_index, T, tid, out);
             if (ana_scale != 1.0f)
                 for (int i = tid; i < 1024; i += nt) out[i] = out[i] * ana_scale;
         } else {
@@ -968,41 +1020,49 @@ HEAAC_DEV void heaac_chain_channel(HeaacChainSmem *sm, const HeaacChainArgs &a, 
                 const float v = a.time_in[fo * 1024 + i];
                 out[i] = ana_scale != 1.0f ? v * ana_scale : v;
             }
+            heaac_cp_async_wait<0>();
         }
-        heaac_cp_async_wait<0>();
         HEAAC_SYNC();
         if (tid == 0) sm->hdr_changed = 0;
         for (int i = tid; i < 288; i += nt) st->ana_hist[i] = x[1024 + i];
+        for (int w = tid; w < 32 * 8; w += nt) {             /* X_low[k][t < 8] = 0 for k >= kx' */
+            const int k = w >> 3, i = w & 7;
+            if (k >= sm->d.kx0) { sm->u[k * HEAAC_US + HEAAC_UC0 + i] = 0.0f; sm->u[HEAAC_U_PLANE + k * HEAAC_US + HEAAC_UC0 + i] = 0.0f; }
+        }
         heaac_ana_window<NT>(x, sm->u, T, tid);
-        HEAAC_SYNC();                                /* the core scratch becomes the HF scratch */
-        /* (the exchange buffer of the transforms lies in the dead core scratch: the side-info work, which fills the HF scratch
-         * over it, follows; with more than 128 threads the rest of the CTA does it at the same time on the upper part) */
+        HEAAC_SYNC();
+        /* (the exchange buffer of the transforms lies in the dead core scratch; the HF scratch takes its place afterwards) */
         heaac_ana_transform<NT>(sm->u, reinterpret_cast<float *>(&sm->s), T, tid);
         HEAAC_SYNC();
-        heaac_hf_params(sm->u, &sm->s.hf, &sm->tb, &sm->d, &sm->p, a.ch_in_elem, st, tid, nt);
+        if (!SPLIT || tid < 32) heaac_hf_lpc(sm->u, &sm->s.hf, &sm->d, tid, SPLIT ? 32 : nt);
+        if (!SPLIT || tid >= 32)
+            heaac_hf_params(sm->u, &sm->s.hf, &sm->tb, &sm->d, p, a.ch_in_elem, st, &sm->keep, SPLIT ? tid - 32 : tid, SPLIT ? nt - 32 : nt);
         HEAAC_SYNC();
-        heaac_hf_stage<NT>(sm->u, &sm->s.hf, &sm->tb, &sm->d, &sm->p, a.ch_in_elem, st, a.emit ? 38 : 32, T, tid);
+        heaac_hf_stage<NT>(sm->u, &sm->s.hf, &sm->tb, &sm->d, p, a.ch_in_elem, st, &sm->keep, a.emit ? 38 : 32, T, tid);
         if (a.emit) heaac_x_emit<NT>(sm->u, a.X, sm->d.top, tid);
-        if (a.emit != 1) {
-            heaac_hf_save(sm->u, &sm->s.hf, &sm->d, st, tid, nt);
-            HEAAC_SYNC();
-            /* the scratch is free: fetch the next frame's coefficients while the synthesis goes on (the exchange buffer of
-             * the transforms lies below the coefficient buffer) */
-            if (tid == 0 && a.coeffs && f + 1 < a.n_frames)
-                heaac_fetch_issue(sm->s.c.coef, a.coeffs + (fo + a.frame_ch) * 1024, 4096, &sm->mbar[0]);
-            heaac_synth_transforms<NT>(sm->u, reinterpret_cast<float *>(&sm->s), sm->d.top, T, tid);
-        } else {
-            heaac_hf_save(sm->u, &sm->s.hf, &sm->d, st, tid, nt);
-            HEAAC_SYNC();
-            if (tid == 0 && a.coeffs && f + 1 < a.n_frames)
-                heaac_fetch_issue(sm->s.c.coef, a.coeffs + (fo + a.frame_ch) * 1024, 4096, &sm->mbar[0]);
-        }
+        heaac_hf_save(sm->u, &sm->s.hf, &sm->d, st, &sm->keep, tid, nt);
         HEAAC_SYNC();
-        if (a.emit != 1)
+        /* the scratch is free: fetch the next frame's coefficients and side info while the synthesis goes on (the exchange
+         * buffer of the transforms lies below the coefficient buffer) */
+        if (f + 1 < a.n_frames) {
+            if (tid == 0 && a.coeffs) heaac_fetch_issue(sm->s.c.coef, a.coeffs + (fo + a.frame_ch) * 1024, 4096, &sm->mbar[0]);
+            const float *src = reinterpret_cast<const float *>(a.sbr + (size_t)(f + 1) * a.frame_elems);
+            float *dst = reinterpret_cast<float *>(&sm->p2[(f & 1) ^ 1]);
+            for (int i = tid; i < P_WORDS; i += nt) heaac_cp_async4(dst + i, src + i);
+        }
+        heaac_cp_async_commit();
+        if (a.emit != 1) {
+            heaac_synth_transforms<NT>(sm->u, reinterpret_cast<float *>(&sm->s), sm->d.top, T, tid);
+            HEAAC_SYNC();
             heaac_synth_output<NT>(sm->u, a.nout, a.out_slot, a.pcm ? a.pcm + (size_t)f * a.pcm_frame : nullptr,
                                    a.pcm_f32 ? a.pcm_f32 + (size_t)f * a.pcm_frame : nullptr, a.qmf_scale, a.add_bias, T, tid);
+        }
     }
+    heaac_cp_async_wait<0>();
     if (a.emit != 1) heaac_synth_hist_store<NT>(sm->u, a.sy, tid);
+    for (int i = tid; i < 8; i += nt) st->bw_array[i] = sm->keep.bw_array[i];
+    for (int i = tid; i < 48; i += nt) st->s_index0[i] = sm->keep.s_index0[i];
+    if (tid == 0) { st->f_indexnoise = sm->keep.f_indexnoise; st->f_indexsine = sm->keep.f_indexsine; }
 }
 
 #endif /* HEAAC_CHAIN_CUH */

@@ -22,6 +22,7 @@
 #define HEAAC_DEV   static inline
 #define HEAAC_SYNC() ((void)0)
 #define HEAAC_SYNCWARP() ((void)0)
+#define HEAAC_SYNC_OR(x) ((x) != 0)
 #define HEAAC_LDX(p) (*(p))
 #define HEAAC_RESTRICT
 #include <math.h>
@@ -36,6 +37,7 @@ static inline float heaac_rint(float a) { return rintf(a); }
 #define HEAAC_DEV   __device__ __forceinline__
 #define HEAAC_SYNC() __syncthreads()
 #define HEAAC_SYNCWARP() __syncwarp()
+#define HEAAC_SYNC_OR(x) __syncthreads_or(x)      /* barrier + "does the predicate hold for any thread of the CTA" */
 /* X may still be being written elsewhere in the grid before (k_sbr / k_synth overlap through per-channel flags): read
  * it through L2, never through the non-coherent path */
 #define HEAAC_LDX(p) __ldcg(p)

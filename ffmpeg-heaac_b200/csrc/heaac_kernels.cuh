@@ -94,6 +94,7 @@ HEAAC_DEV void heaac_fft_smem(float *re, float *im, int log2n, int nbatch,
     const int lead = log2n % 3;                             /* sizes that are not a power of 8: plain stages first */
     for (int s = 1; s <= lead; s++) {
         const int half = 1 << (s - 1), hn = n >> 1;
+        HEAAC_NOUNROLL
         for (int w = tid; w < nbatch * hn; w += nt) {
             const int bt = w / hn, r = w - bt * hn;
             const int j = r & (half - 1), grp = r >> (s - 1);
@@ -107,6 +108,7 @@ HEAAC_DEV void heaac_fft_smem(float *re, float *im, int log2n, int nbatch,
     }
     for (int p3 = lead; p3 < log2n; p3 += 3) {
         const int h0 = 1 << p3;                             /* butterfly span of the first stage of this pass */
+        HEAAC_NOUNROLL
         for (int w = tid; w < items; w += nt) {
             const int bt = w / (n >> 3), r = w - bt * (n >> 3);
             const int j = r & (h0 - 1), blk = r >> p3;
@@ -166,6 +168,7 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
 {
     constexpr int nt = NT;
     const int n4 = 1 << log2n4, n2 = n4 << 1, n8 = n4 >> 1;
+    HEAAC_NOUNROLL
     for (int w = tid; w < nbatch * n4; w += nt) {
         int b = w >> log2n4, k = w & (n4 - 1);
         const float *x = in + b * n2;
@@ -176,6 +179,8 @@ HEAAC_DEV void heaac_imdct_half_smem(float *out, const float *in, float *zr, flo
     }
     HEAAC_SYNC();
     heaac_fft_smem<NT>(zr, zi, log2n4, nbatch, T, tid);
+    heaac_cp_async_wait<0>();        /* what the caller fetched ahead for the windowing is visible behind the barrier below */
+    HEAAC_NOUNROLL
     for (int w = tid; w < nbatch * n8; w += nt) {
         int b = w / n8, k = w - b * n8;
         int p = n8 - k - 1, q = n8 + k;
@@ -207,6 +212,7 @@ HEAAC_DEV void heaac_vfw(float *dst, const float *s0, const float *s1, const flo
                          float bias, int len,  int tid)
 {
     constexpr int nt = NT;
+    HEAAC_NOUNROLL
     for (int i = tid; i < len; i += nt) {
         int j = 2 * len - 1 - i;
         float a = s0[i], b = s1[len - 1 - i], wi = win[i], wj = win[j];
@@ -293,8 +299,10 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
                                   const HeaacIcs *HEAAC_RESTRICT ics_p, const HeaacTns *HEAAC_RESTRICT tns,
                                   const float *HEAAC_RESTRICT tns_done,
                                   HeaacChanState *st, float *out, float bias, int sr_index,
-                                  const HeaacDevTables *HEAAC_RESTRICT T,  int tid)
+                                  const HeaacDevTables *HEAAC_RESTRICT T,  int tid, const float *saved_rd = nullptr)
 {
+    /* saved_rd: where to read the overlap-add history from (a copy the caller fetched ahead of time; it may be `out` itself:
+     * every output sample is computed by the thread that reads the history value at the same index); NULL: the state block */
     constexpr int nt = NT;
     HeaacIcs ics = *ics_p;
     ics.window_sequence &= 3; ics.window_shape &= 1;         /* unchecked side info stays inside the case table */
@@ -312,6 +320,7 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
             float lpc_unused[HEAAC_TNS_MAX_ORDER];
             if (!heaac_tns_chain(&ics, tns, sr_index, T, slot, &start, &size, &inc, &order, lpc_unused, 0)) continue;
             const int lo = inc > 0 ? start : start - (size - 1);
+            HEAAC_NOUNROLL
             for (int i = tid; i < size; i += nt) c[lo + i] = tns_done[lo + i];
         }
         HEAAC_SYNC();
@@ -347,45 +356,55 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
     }
 
     /* ---- half IMDCT: 1 x N=2048 or 8 x N=256, aacdec.c:1755-1763 ---- */
-    if (is8)
+    if (is8) {
         heaac_imdct_half_smem<NT>(c, c, sm->zr, sm->zi, 6, 8, T->tcos_256, T->tsin_256, T, tid);
-    else
+        HEAAC_SYNC();        /* (the 64-point FFTs take one pass less than the 512-point one: every path through this routine crosses
+                              * the same number of barriers, so that channels with different window sequences may share a CTA) */
+    } else
         heaac_imdct_half_smem<NT>(c, c, sm->zr, sm->zi, 9, 1, T->tcos_2048, T->tsin_2048, T, tid);
 
     /* ---- windowing + overlap-add, aacdec.c:1771-1805 ---- */
     const float *buf = c;
     float *saved = st->saved;
+    const float *saved_r = saved_rd ? saved_rd : st->saved;
     const float *sw      = ics.window_shape ? T->kbd_128 : T->sine_128;
     const float *lw_prev = shape_prev ? T->kbd_1024 : T->sine_1024;
     const float *sw_prev = shape_prev ? T->kbd_128 : T->sine_128;
     const int prev_long = ws1 == HEAAC_ONLY_LONG || ws1 == HEAAC_LONG_STOP;
 
     if (prev_long && (ws0 == HEAAC_ONLY_LONG || ws0 == HEAAC_LONG_START)) {
-        heaac_vfw<NT>(out, saved, buf, lw_prev, bias, 512, tid);
+        heaac_vfw<NT>(out, saved_r, buf, lw_prev, bias, 512, tid);
     } else {
-        for (int i = tid; i < 448; i += nt) out[i] = saved[i] + bias;
-        heaac_vfw<NT>(out + 448, saved + 448, buf, sw_prev, bias, 64, tid);
+        HEAAC_NOUNROLL
+        for (int i = tid; i < 448; i += nt) out[i] = saved_r[i] + bias;
+        heaac_vfw<NT>(out + 448, saved_r + 448, buf, sw_prev, bias, 64, tid);
         if (is8) {
             for (int j = 1; j < 4; j++)
                 heaac_vfw<NT>(out + 448 + 128 * j, buf + 128 * (j - 1) + 64, buf + 128 * j, sw, bias, 64, tid);
             heaac_vfw<NT>(sm->temp, buf + 3 * 128 + 64, buf + 4 * 128, sw, bias, 64, tid);
         } else {
+            HEAAC_NOUNROLL
             for (int i = 576 + tid; i < 1024; i += nt) out[i] = buf[i - 512] + bias;
         }
     }
     HEAAC_SYNC();        /* all reads of the old `saved` are done; temp[] is complete */
     if (is8) {
+        HEAAC_NOUNROLL
         for (int i = tid; i < 64; i += nt) {
             out[960 + i] = sm->temp[i];
             saved[i] = sm->temp[64 + i] - bias;
         }
         for (int j = 0; j < 3; j++)
             heaac_vfw<NT>(saved + 64 + 128 * j, buf + (4 + j) * 128 + 64, buf + (5 + j) * 128, sw, 0.0f, 64, tid);
+        HEAAC_NOUNROLL
         for (int i = tid; i < 64; i += nt) saved[448 + i] = buf[7 * 128 + 64 + i];
     } else if (ws0 == HEAAC_LONG_START) {
+        HEAAC_NOUNROLL
         for (int i = tid; i < 448; i += nt) saved[i] = buf[512 + i];
+        HEAAC_NOUNROLL
         for (int i = tid; i < 64; i += nt)  saved[448 + i] = buf[7 * 128 + 64 + i];
     } else {
+        HEAAC_NOUNROLL
         for (int i = tid; i < 512; i += nt) saved[i] = buf[512 + i];
     }
     if (tid == 0) { st->prev_ws = ws0; st->prev_shape = ics.window_shape; }

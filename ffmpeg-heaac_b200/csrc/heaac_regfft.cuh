@@ -19,8 +19,13 @@
 
 #ifdef HEAAC_HOST_EMU
 #define HEAAC_UNROLL
+#define HEAAC_NOUNROLL
+#define HEAAC_UNROLL4
 #else
 #define HEAAC_UNROLL _Pragma("unroll")
+/* work-item loops stay rolled: the kernels are bound by instruction fetch, not by loop overhead */
+#define HEAAC_NOUNROLL _Pragma("unroll 1")
+#define HEAAC_UNROLL4 _Pragma("unroll 4")
 #endif
 
 HEAAC_HD constexpr int heaac_brev5(int k)

@@ -38,12 +38,14 @@ def test_emulated_kernels_equal_oracle_on_synthetic_workloads(name):
     assert (np.abs(op) >= 32767).mean() < 1e-3
 
 
-def test_frame_by_frame_equals_batched_call():
-    """State hand-over: T frames in one call == T calls of one frame."""
-    cfg, a = synthetic.make_workload("heaac_v2_ps", 2, 8, seed=3, K=2)
+@pytest.mark.parametrize("name", ["heaac_v1_stereo", "heaac_v2_ps"])
+def test_frame_by_frame_equals_batched_call(name):
+    """State hand-over: T frames in one call == T calls of one frame (v1: the chain keeps part of the state in "shared memory"
+    for the length of a call)."""
+    cfg, a = synthetic.make_workload(name, 2, 8, seed=3, K=2)
     e1, e2 = pyemu.Emu(cfg), pyemu.Emu(cfg)
     p1, f1 = e1.synth(a["coeffs"], a["ics"], a["tns"], a["sbr"], a["ps"])
     for t in range(8):
-        p2, f2 = e2.synth(a["coeffs"][t:t + 1], a["ics"][t:t + 1], None, a["sbr"][t:t + 1], a["ps"][t:t + 1])
+        p2, f2 = e2.synth(a["coeffs"][t:t + 1], a["ics"][t:t + 1], None, a["sbr"][t:t + 1], a["ps"][t:t + 1] if a["ps"] is not None else None)
         assert np.array_equal(f2[0], f1[t])
     e1.close(); e2.close()
