@@ -163,7 +163,7 @@ k_chain(HeaacGeom g, int first_ch, int n_frames, int emit, const float *__restri
     a.ics = ics ? ics + gc : nullptr;
     a.tns = tns ? tns + gc : nullptr;
     a.tns_done = tns_done ? tns_done + (size_t)gc * 1024 : nullptr;
-    a.sbr = sbr + (size_t)s * g.nse + se;
+    a.sbr = se == 0xff ? nullptr : sbr + (size_t)s * g.nse + se;      /* an LFE carries no SBR data: upsampled only */
     a.st = chan + gc;
     a.sy = synth + (size_t)s * g.nout + c;
     a.X = X ? X + ((size_t)s * g.nout + c) * HEAAC_X_FLOATS : nullptr;
@@ -211,8 +211,8 @@ k_synth(HeaacGeom g, const float *X, HeaacSynthState *synth,
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeaacSynthSmem *sm = reinterpret_cast<HeaacSynthSmem *>(smem_raw);
-    /* one CTA per (stream, SBR element): its 1 or 2 output channels */
-    const int s = blockIdx.x / g.nse, e = blockIdx.x - s * g.nse;
+    /* one CTA per (stream, element): its 1 or 2 output channels */
+    const int s = blockIdx.x / g.n_elems, e = blockIdx.x - s * g.n_elems;
     const int c0 = g.elem_first_out[e], nch = g.elem_nout[e];
     const float qmf_scale = -1024.0f * g.sf_scale;
     const size_t go = (size_t)s * g.nout + c0;
@@ -255,18 +255,16 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
         }
         if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
     }
-    /* synthesis works per SBR element: its first output channel and channel count (PS: mono in, 2 out) */
+    /* k_synth works per element (an LFE included: it is upsampled like the others): its first output channel and channel count
+     * (PS: mono in, 2 out) */
     {
-        int o = 0, k = 0;
+        int o = 0;
         g->max_elem_ch = 1;
         for (int e = 0; e < cfg->n_elems; e++) {
             int nch = cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
-            if (cfg->elem_type[e] != HEAAC_TYPE_LFE) {
-                g->elem_first_out[k] = (uint8_t)o;
-                g->elem_nout[k] = (uint8_t)(cfg->ps ? 2 : nch);
-                if (nch > g->max_elem_ch) g->max_elem_ch = nch;
-                k++;
-            }
+            g->elem_first_out[e] = (uint8_t)o;
+            g->elem_nout[e] = (uint8_t)(cfg->ps ? 2 : nch);
+            if (nch > g->max_elem_ch) g->max_elem_ch = nch;
             o += nch;
         }
     }
@@ -320,7 +318,6 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     }
     if (nch > HEAAC_MAX_CHANNELS) return HEAAC_E_INVAL;
     if (cfg->ps && !(cfg->sbr && cfg->n_elems == 1 && cfg->elem_type[0] == HEAAC_TYPE_SCE)) return HEAAC_E_INVAL;
-    if (cfg->sbr && has_lfe) return HEAAC_E_UNSUPPORTED;     /* see DESIGN.md "out of scope" */
     {
         int any = 0, seen = 0;
         for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
@@ -511,7 +508,7 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
                 c->launches++;
             }
             prof_begin(c, HEAAC_K_SYNTH);
-            k_synth<<<(unsigned)(S * g.nse), 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, pc, pf, c->d_tables);
+            k_synth<<<(unsigned)(S * g.n_elems), 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, pc, pf, c->d_tables);
             prof_end(c);
             c->launches++;
         }

@@ -978,8 +978,16 @@ HEAAC_DEV void heaac_chain_channel(HeaacChainSmem *sm, const HeaacChainArgs &a, 
     for (int i = tid; i < 8; i += nt) sm->keep.bw_array[i] = st->bw_array[i];
     for (int i = tid; i < 48; i += nt) sm->keep.s_index0[i] = st->s_index0[i];
     if (tid == 0) { sm->keep.f_indexnoise = st->f_indexnoise; sm->keep.f_indexsine = st->f_indexsine; }
-    for (int i = tid; i < P_WORDS; i += nt)          /* the first frame's side info */
-        heaac_cp_async4(reinterpret_cast<float *>(&sm->p2[0]) + i, reinterpret_cast<const float *>(a.sbr) + i);
+    if (a.sbr) {
+        for (int i = tid; i < P_WORDS; i += nt)      /* the first frame's side info */
+            heaac_cp_async4(reinterpret_cast<float *>(&sm->p2[0]) + i, reinterpret_cast<const float *>(a.sbr) + i);
+    } else {
+        /* an element without SBR data in an SBR stream (LFE): the reference still runs ff_sbr_apply on it (aacdec.c:1923-1925) with
+         * the SpectralBandReplication in its initial state -- start = 0, kx = kx' = 32, M = 0 (aacsbr.c:128-137): upsampling only */
+        for (int i = tid; i < 2 * P_WORDS; i += nt) reinterpret_cast<uint32_t *>(&sm->p2[0])[i] = 0;
+        HEAAC_SYNC();
+        if (tid == 0) { sm->p2[0].kx[0] = sm->p2[0].kx[1] = 32; sm->p2[1].kx[0] = sm->p2[1].kx[1] = 32; }
+    }
     heaac_cp_async_commit();
     for (int f = 0; f < a.n_frames; f++) {
         const size_t fo = (size_t)f * a.frame_ch;
@@ -1046,6 +1054,8 @@ HEAAC_DEV void heaac_chain_channel(HeaacChainSmem *sm, const HeaacChainArgs &a, 
          * buffer of the transforms lies below the coefficient buffer) */
         if (f + 1 < a.n_frames) {
             if (tid == 0 && a.coeffs) heaac_fetch_issue(sm->s.c.coef, a.coeffs + (fo + a.frame_ch) * 1024, 4096, &sm->mbar[0]);
+        }
+        if (f + 1 < a.n_frames && a.sbr) {
             const float *src = reinterpret_cast<const float *>(a.sbr + (size_t)(f + 1) * a.frame_elems);
             float *dst = reinterpret_cast<float *>(&sm->p2[(f & 1) ^ 1]);
             for (int i = tid; i < P_WORDS; i += nt) heaac_cp_async4(dst + i, src + i);

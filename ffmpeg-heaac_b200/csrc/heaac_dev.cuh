@@ -160,8 +160,8 @@ struct HeaacGeom {
     uint8_t ch_sbr_elem[HEAAC_MAX_CHANNELS]; /* core channel -> SBR element index (0xff for LFE) */
     uint8_t elem_is_cpe[HEAAC_MAX_CHANNELS]; /* per core channel: its element is a CPE */
     uint8_t out_slot[HEAAC_MAX_CHANNELS];    /* core (or synthesised) channel -> position in the output */
-    uint8_t elem_first_out[HEAAC_MAX_ELEMS]; /* SBR element -> its first output channel */
-    uint8_t elem_nout[HEAAC_MAX_ELEMS];      /* SBR element -> number of output channels (2 with PS) */
+    uint8_t elem_first_out[HEAAC_MAX_ELEMS]; /* element -> its first output channel */
+    uint8_t elem_nout[HEAAC_MAX_ELEMS];      /* element -> number of output channels (2 with PS) */
     int max_elem_ch;
 };
 

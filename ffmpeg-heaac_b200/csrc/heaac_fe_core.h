@@ -1002,6 +1002,10 @@ FE_FN void fe_sbr_payload(FE *fe, BR *b, int crc, int cnt, int prev_elem, int pr
     }
     if (fe->ps == -1 && !fe->locked && fe->ncc == 1) { fe->sbr = 1; fe->ps = 1; }
     else fe->sbr = 1;
+    if (prev_type == HEAAC_TYPE_LFE) {     /* read_sbr_data rejects the element type (aacsbr.c:997-1002): the LFE stays without SBR data */
+        br_skip(b, 8 * cnt - 4);
+        return;
+    }
     int se = 0;
     for (int i = 0; i < prev_elem; i++) se += fe->elem_type[i] != HEAAC_TYPE_LFE;
     sbr_extension(fe, &fe->sbr_el[se], b, crc, cnt, prev_type == 1);

@@ -252,6 +252,8 @@ WORKLOADS = {
     "heaac_v1_stereo": dict(layout="stereo", sr_index=6, sbr=True,  ps=False, p_short=0.02, tns=0.0),
     "heaac_v2_ps":     dict(layout="mono",   sr_index=6, sbr=True,  ps=True,  p_short=0.02, tns=0.0),
     "lc_51_48k_tns":   dict(layout="5.1",    sr_index=3, sbr=False, ps=False, p_short=0.35, tns=0.55),
+    # HE-AAC 5.1: SBR on the SCE and the two CPEs, the LFE is upsampled only (aacdec.c:1923-1925)
+    "heaac_v1_51":     dict(layout="5.1",    sr_index=6, sbr=True,  ps=False, p_short=0.05, tns=0.3),
 }
 
 
@@ -287,7 +289,7 @@ def make_workload(name, S, T, seed=0, K=32, bias_mode=False):
         sbr_k = np.zeros((T, K, nse), abi.SBR_ELEM)
         for k in range(K):
             for e in range(nse):
-                sbr_k[:, k, e] = sbr_frames(rng, T, et[e] == abi.TYPE_CPE)
+                sbr_k[:, k, e] = sbr_frames(rng, T, [t for t in et if t != abi.TYPE_LFE][e] == abi.TYPE_CPE)
         arrays["sbr"] = np.ascontiguousarray(np.tile(sbr_k, (1, reps, 1))[:, :S])
     if w["ps"]:
         ps_k = np.zeros((T, K), abi.PS_FRAME)

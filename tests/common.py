@@ -8,7 +8,7 @@ import pyoracle
 abi = pyref.abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ("lc_stereo_44k", "lc_51_48k", "lc_51_tns_rich", "heaac_v1_stereo", "heaac_v2_ps", "heaac_v1_downsampled")
+GOLDEN_CASES = ("lc_stereo_44k", "lc_51_48k", "lc_51_tns_rich", "heaac_v1_stereo", "heaac_v2_ps", "heaac_v1_downsampled", "heaac_v1_51")
 
 # north_star tolerance: max abs error <= 1e-5 of full scale on float PCM, or +-1 LSB after s16 conversion
 TOL_FS = 1e-5

@@ -88,7 +88,7 @@ static void emu_chain(EmuCtx *c, const HeaacBatch *b, size_t gc, int f0, int n, 
     a.coeffs = b->coeffs + ((size_t)f0 * a.frame_ch + gc) * 1024;
     a.ics = b->ics + (size_t)f0 * a.frame_ch + gc;
     a.tns = b->tns ? b->tns + (size_t)f0 * a.frame_ch + gc : nullptr;
-    a.sbr = b->sbr + (size_t)f0 * a.frame_elems + s * g.nse + se;
+    a.sbr = se == 0xff ? nullptr : b->sbr + (size_t)f0 * a.frame_elems + s * g.nse + se;
     a.st = c->chan + gc;
     a.sy = c->synth + s * g.nout + ch;
     a.X = c->X + (s * g.nout + ch) * HEAAC_X_FLOATS;
@@ -107,7 +107,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
     const float qmf_scale = -1024.0f * g.sf_scale;
     if (g.sbr && !g.ps && !g.ds) {                                /* HE-AAC v1: k_chain, the whole call per channel */
         for (size_t gc = 0; gc < S * g.ncc; gc++)
-            if (g.ch_sbr_elem[gc % g.ncc] != 0xff) emu_chain(c, b, gc, 0, b->n_frames, 0);
+            emu_chain(c, b, gc, 0, b->n_frames, 0);
         return 0;
     }
     for (int f = 0; f < b->n_frames; f++) {
@@ -122,7 +122,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
         for (size_t gc = 0; gc < S * g.ncc; gc++) {               /* k_core, or k_chain up to X */
             size_t s = gc / g.ncc; int ch = (int)(gc - s * g.ncc);
             if (g.sbr) {
-                if (g.ch_sbr_elem[ch] != 0xff) emu_chain(c, b, gc, f, 1, 1);
+                emu_chain(c, b, gc, f, 1, 1);
                 continue;
             }
             static float out[1024];
@@ -149,7 +149,7 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             int o = 0;
             for (int e = 0; e < g.n_elems; e++) {
                 int nch = g.elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
-                if (g.elem_type[e] != HEAAC_TYPE_LFE) {
+                {
                     int no = g.ps ? 2 : nch;
                     size_t go = s * g.nout + o;
                     memset(c->sm_synth, 0xA5, sizeof(HeaacSynthSmem));

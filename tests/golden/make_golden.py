@@ -70,7 +70,13 @@ def main():
     # downsampled SBR: hierarchical explicit signalling (AOT 5) with the extension rate equal to the core rate
     pkts, ed, info = hs.make_stream(31, 8, stereo=True, ps=False)
     cases["heaac_v1_downsampled"] = (pkts, hs.asc_explicit(6, 2, 6), 24000, 2, "stereo")
+    # HE-AAC 5.1: SBR on SCE + 2 CPE, the LFE upsampled only (aacdec.c:1923-1925)
+    pkts, ed, info = hs.make_stream_51(51, 8)
+    cases["heaac_v1_51"] = (pkts, ed, 24000, 6, "5.1")
+    only = sys.argv[1:]
     for name, c in cases.items():
+        if only and name not in only:
+            continue
         d = capture(*c)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)

@@ -540,6 +540,29 @@ def make_stream(seed, n_frames, stereo=True, ps=False, core_rate=24000, bitrate_
     return pkts, extradata, {"tables": gen.tables, "channels": ch, "core_rate": core_rate}
 
 
+def make_stream_51(seed, n_frames, core_sr_index=6, **gen_kw):
+    """HE-AAC 5.1 (SCE CPE CPE LFE, implicit SBR signalling): AAC-LC frames from the repo's own writer (tests/lc_writer.py:
+    it writes element by element, so the SBR fill elements can follow the SCE and the two CPEs) with one SBR generator per
+    element; the LFE carries none -- the reference upsamples it (aacdec.c:1923-1925).  Returns (packets, extradata, info)."""
+    import lc_writer
+    rate = [96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000][core_sr_index]
+    w = lc_writer.LcWriter(seed, core_sr_index, pyref.LAYOUTS["5.1"][0], tns_prob=0.3, short_bias=0.15)
+    # table sizes of each element's header from the reference, probed on a stereo scratch frame of the same core rate
+    enc = pyref.Encoder(rate, 2, 64000)
+    probe_core = enc.encode(core_noise(2048, 2, seed))[0]
+    probe_ed = enc.extradata
+    enc.close()
+    gens = {}
+    for ei, t in enumerate(pyref.LAYOUTS["5.1"][0]):
+        if t == abi.TYPE_LFE:
+            continue
+        g = HeAacStreamGen(seed * 7 + ei, t == abi.TYPE_CPE, **gen_kw)
+        g.tables = probe_tables(probe_core, probe_ed, rate, 2, g.hdr)
+        gens[ei] = g
+    pkts = [w.frame(fil={ei: g.sbr_payload() for ei, g in gens.items()}) for _ in range(n_frames)]
+    return pkts, lc_writer.audio_specific_config(core_sr_index, 6), {"core_rate": rate, "writer": w}
+
+
 def asc_explicit(core_idx, chan_config, ext_idx, ps=False):
     """AudioSpecificConfig with hierarchical explicit SBR (AOT 5) / PS (AOT 29) signalling (mpeg4audio.c:77-130):
     ext_idx == core_idx asks for downsampled SBR."""

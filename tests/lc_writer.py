@@ -288,12 +288,15 @@ class LcWriter:
         self.stats["short"] += info["ws"] == EIGHT_SHORT
         return info
 
-    def frame(self):
+    def frame(self, fil=None):
+        """One raw_data_block.  fil: {element index: BitWriter with an sbr_extension_data() payload} -- a FIL element
+        (EXT_SBR_DATA) is written right behind that element, where the reference attaches it to the element before it
+        (aacdec.c:2042-2064)."""
         r = self.rng
         bw = BitWriter()
         ch = 0
         tags = {}
-        for t in self.elem_types:
+        for ei, t in enumerate(self.elem_types):
             tag = tags.get(t, 0)
             tags[t] = tag + 1
             bw.put(t, 3); bw.put(tag, 4)
@@ -316,6 +319,18 @@ class LcWriter:
             else:
                 self._ics(bw, self.ch[ch], None, False)
                 ch += 1
+            if fil and ei in fil:
+                payload = fil[ei]
+                nbits = 4 + len(payload)
+                cnt = (nbits + 7) // 8
+                bw.put(6, 3)                            # TYPE_FIL
+                if cnt < 15:
+                    bw.put(cnt, 4)
+                else:
+                    bw.put(15, 4); bw.put(cnt - 14, 8)
+                bw.put(0xD, 4)                          # EXT_SBR_DATA
+                bw.bits += list(payload.bits)
+                bw.put(0, cnt * 8 - nbits)
         bw.put(7, 3)                                    # TYPE_END
         self.stats["frames"] += 1
         return bw.tobytes()
