@@ -283,7 +283,11 @@ def make_workload(name, S, T, seed=0, K=32, bias_mode=False):
     arrays = {"ics": np.ascontiguousarray(np.tile(ics_k, (1, reps, 1))[:, :S]),
               "tns": np.ascontiguousarray(np.tile(tns_k, (1, reps, 1))[:, :S]) if w["tns"] > 0 else None,
               "sbr": None, "ps": None}
-    arrays["coeffs"] = coeffs(rng, T, S, ncc, cfg.sf_scale, bins=1024 if not w["sbr"] else 640)
+    # spectra: independent noise per stream up to 4096 streams; larger batches (config 5's shards) tile 256 streams' worth --
+    # the kernels' work does not depend on the values, and drawing 10^9 normals would dominate the run
+    Sc = S if S <= 4096 else 256
+    c = coeffs(rng, T, Sc, ncc, cfg.sf_scale, bins=1024 if not w["sbr"] else 640)
+    arrays["coeffs"] = c if Sc == S else np.ascontiguousarray(np.tile(c, (1, -(-S // Sc), 1, 1))[:, :S])
     if w["sbr"]:
         nse = abi.n_sbr_elems(et)
         sbr_k = np.zeros((T, K, nse), abi.SBR_ELEM)
