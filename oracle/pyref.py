@@ -169,6 +169,21 @@ class Decoder:
         r["consumed"] = ret
         return r
 
+    def enable_dropin(self, libpath):
+        """DROP-IN mode: from now on this decoder hands every frame to the product library (dlopen'ed `libpath`,
+        heaac_b200_synth) where it would call spectral_to_sample (aacdec.c:2078) -- the unmodified front end and output
+        stage with the B200 back end, in one process.  GPU box only."""
+        L = lib()
+        L.ref_dec_enable_dropin.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_dec_dropin_frames.restype = C.c_longlong
+        L.ref_dec_dropin_frames.argtypes = [C.c_void_p]
+        r = L.ref_dec_enable_dropin(self.h, libpath.encode())
+        if r:
+            raise RuntimeError("ref_dec_enable_dropin failed (%d)" % r)
+
+    def dropin_frames(self):
+        return int(lib().ref_dec_dropin_frames(self.h))
+
     def decode_many(self, pkts, repeat=1):
         """Decode the packet list `repeat` times in one C call (CPU-baseline timing); returns samples/channel."""
         sizes = np.asarray([len(p) for p in pkts], np.int32)

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <dlfcn.h>
 
 #include "libavcodec/avcodec.h"
 #include "libavcodec/aac.h"
@@ -69,6 +70,11 @@ typedef struct RefDec {
     int           last_samples;
     int           last_channels;
     int           hook_calls;
+    /* drop-in mode: the product back end in place of spectral_to_sample (ref_dec_enable_dropin) */
+    int           dropin;
+    HeaacContext *be;
+    int           be_sbr, be_ps, be_ds, be_ncc;
+    long long     dropin_frames;
 } RefDec;
 
 static __thread RefDec *cur_dec;
@@ -175,11 +181,101 @@ static void pack_ps(HeaacPsFrame *o, const PSContext *p)
     memcpy(o->opd_par, p->opd_par, sizeof(o->opd_par));
 }
 
-/* called from aac_decode_frame right before spectral_to_sample(ac) */
-void heaac_ref_pre_hook(AACContext *ac)
+/* ---- drop-in mode: the product library in place of spectral_to_sample, inside this process ------------------- */
+static struct {
+    void *lib;
+    int  (*create)(const HeaacConfig *, HeaacContext **);
+    void (*destroy)(HeaacContext *);
+    int  (*synth)(HeaacContext *, const HeaacBatch *);
+} g_be;
+
+/* Hand the current frame to heaac_b200_synth and put its float PCM where spectral_to_sample would have left it
+ * (che->ch[c].ret): the reference's own output stage (float_to_int16_interleave, aacdec.c:2096) runs on it afterwards.
+ * Returns 1 on success. */
+static int dropin_frame(RefDec *d, AACContext *ac)
+{
+    static __thread float coeffs[HEAAC_MAX_CHANNELS * 1024], pcm[HEAAC_MAX_CHANNELS * 2048];
+    HeaacIcs ics[HEAAC_MAX_CHANNELS]; HeaacTns tns[HEAAC_MAX_CHANNELS];
+    HeaacSbrElem sbr[REF_MAX_ELEMS]; HeaacPsFrame ps;
+    const int want_sbr = ac->m4ac.sbr == 1, want_ps = ac->m4ac.ps == 1 && d->avctx.channels <= 2 && d->n_elems == 1 && d->elem_type[0] == TYPE_SCE;
+    const int want_ds = want_sbr && ac->m4ac.ext_sample_rate < 2 * ac->m4ac.sample_rate;
+    int ncc = 0;
+    for (int e = 0; e < d->n_elems; e++) ncc += d->elem_type[e] == TYPE_CPE ? 2 : 1;
+    if (!d->be || d->be_sbr != want_sbr || d->be_ps != want_ps || d->be_ds != want_ds) {
+        /* (re)create the back end for what the front end has found out by now (implicit SBR / PS signalling is known
+         * once the first frame's fill elements are parsed, i.e. before the first spectral_to_sample) */
+        HeaacConfig cfg;
+        if (d->be) g_be.destroy(d->be);
+        d->be = NULL;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = HEAAC_ABI_VERSION;
+        cfg.n_streams = 1; cfg.n_elems = d->n_elems;
+        for (int e = 0; e < d->n_elems; e++) cfg.elem_type[e] = (uint8_t)d->elem_type[e];
+        cfg.sr_index = ac->m4ac.sampling_index;
+        cfg.sbr = want_sbr; cfg.ps = want_ps; cfg.sbr_downsampled = want_ds;
+        cfg.add_bias = ac->add_bias; cfg.sf_scale = ac->sf_scale;
+        cfg.max_frames_per_call = 1; cfg.want_float_out = 1;
+        if (g_be.create(&cfg, &d->be)) return 0;
+        d->be_sbr = want_sbr; d->be_ps = want_ps; d->be_ds = want_ds; d->be_ncc = ncc;
+    }
+    memset(&ps, 0, sizeof(ps));
+    int ch = 0, se = 0;
+    for (int e = 0; e < d->n_elems; e++) {
+        ChannelElement *che = ac->che[d->elem_type[e]][d->elem_id[e]];
+        int nch = d->elem_type[e] == TYPE_CPE ? 2 : 1;
+        if (!che) return 0;
+        for (int c = 0; c < nch; c++, ch++) {
+            memcpy(coeffs + 1024 * ch, che->ch[c].coeffs, 1024 * sizeof(float));
+            pack_ics(ics + ch, &che->ch[c]);
+            pack_tns(tns + ch, &che->ch[c]);
+        }
+        if (d->elem_type[e] != TYPE_LFE) {
+            pack_sbr(sbr + se, &che->sbr);
+            if (se == 0) pack_ps(&ps, &che->sbr.ps);
+            se++;
+        }
+    }
+    HeaacBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n_frames = 1; b.coeffs = coeffs; b.ics = ics; b.tns = tns;
+    b.sbr = want_sbr ? sbr : NULL; b.ps = want_ps ? &ps : NULL; b.pcm_f32 = pcm;
+    if (g_be.synth(d->be, &b)) return 0;
+    /* planar float PCM [out channel][len] -> the elements' ret buffers (with PS the SCE's second channel is R) */
+    const int len = (want_sbr && !want_ds) ? 2048 : 1024;
+    ch = 0;
+    for (int e = 0; e < d->n_elems; e++) {
+        ChannelElement *che = ac->che[d->elem_type[e]][d->elem_id[e]];
+        int nout = want_ps ? 2 : (d->elem_type[e] == TYPE_CPE ? 2 : 1);
+        for (int c = 0; c < nout; c++, ch++)
+            memcpy(che->ch[c].ret, pcm + (size_t)ch * len, len * sizeof(float));
+    }
+    d->dropin_frames++;
+    return 1;
+}
+
+/* dlopen the product library and switch this decoder to drop-in mode.  Returns 0 on success. */
+int ref_dec_enable_dropin(RefDec *d, const char *libpath)
+{
+    if (!g_be.lib) {
+        void *h = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
+        if (!h) { av_log(NULL, AV_LOG_ERROR, "ref_harness: dlopen(%s): %s\n", libpath, dlerror()); return -1; }
+        g_be.create  = (int (*)(const HeaacConfig *, HeaacContext **))dlsym(h, "heaac_b200_create");
+        g_be.destroy = (void (*)(HeaacContext *))dlsym(h, "heaac_b200_destroy");
+        g_be.synth   = (int (*)(HeaacContext *, const HeaacBatch *))dlsym(h, "heaac_b200_synth");
+        if (!g_be.create || !g_be.destroy || !g_be.synth) { dlclose(h); return -2; }
+        g_be.lib = h;
+    }
+    d->dropin = 1;
+    return 0;
+}
+long long ref_dec_dropin_frames(RefDec *d) { return d->dropin_frames; }
+
+/* called from aac_decode_frame in place of / right before spectral_to_sample(ac):
+ *   if (!heaac_ref_pre_hook(ac)) spectral_to_sample(ac); */
+int heaac_ref_pre_hook(AACContext *ac)
 {
     RefDec *d = cur_dec;
-    if (!d) return;
+    if (!d) return 0;
     d->hook_calls++;
     int ch = 0, se = 0;
     for (int e = 0; e < d->n_elems; e++) {
@@ -197,6 +293,7 @@ void heaac_ref_pre_hook(AACContext *ac)
             se++;
         }
     }
+    return d->dropin ? dropin_frame(d, ac) : 0;
 }
 
 void heaac_ref_post_hook(AACContext *ac) { }
@@ -242,6 +339,7 @@ RefDec *ref_dec_open(const uint8_t *extradata, int extradata_size, int sample_ra
 void ref_dec_close(RefDec *d)
 {
     if (!d) return;
+    if (d->be) g_be.destroy(d->be);
     aac_decoder.close(&d->avctx);
     av_free(d->avctx.priv_data);
     av_free(d->avctx.extradata);

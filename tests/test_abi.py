@@ -28,6 +28,14 @@ def test_library_exports_every_declared_symbol():
     assert not missing, "declared in include/heaac_b200.h but not exported: %s" % missing
 
 
+def test_library_exports_the_experimental_header_too():
+    src = open(os.path.join(ROOT, "include", "heaac_b200_experimental.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    lib = ctypes.CDLL(hb.LIB_PATH)
+    syms = sorted(set(re.findall(r"\b(heaac_b200_exp_\w+)\s*\(", src)))
+    assert syms and all(hasattr(lib, s) for s in syms)
+
+
 def test_python_mirror_lists_every_declared_symbol():
     assert sorted(hb.EXPORTS) == declared_symbols()
 

@@ -13,7 +13,7 @@ import pytest
 
 import pyoracle
 from common import (FULL_SCALE, GOLDEN_CASES, TOL_FS, abi, assert_pcm_close, golden_args, golden_config, golden_ref_pcm,
-                    load_golden)
+                    golden_packets, load_golden)
 from conftest import needs_ref
 
 pytestmark = pytest.mark.gpu
@@ -293,3 +293,34 @@ def test_ps_apply_shim_matches_batched_path(hb):
             want = y[ch, :, :, :32].transpose(0, 2, 1)
             assert np.array_equal(got[:, :32], want), "frame %d channel %d" % (t, ch)
     pre.close(); post.close(); shim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_live_dropin_inside_the_reference_decoder(name):
+    """the UNMODIFIED reference decoder (oracle/_ref: its own parsers, its own output stage) with the call
+    `spectral_to_sample(ac)` (aacdec.c:2078) replaced, in process, by heaac_b200_synth on this GPU: the decoder's PCM for the
+    golden packets must equal what the reference produced on its own (the golden file), frame by frame."""
+    import pyref
+    import ffmpeg_heaac_b200 as hb
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    d = load_golden(name)
+    pk = golden_packets(d)
+    et = [int(x) for x in d["elem_types"]]
+    layout = {(1,): "stereo", (0,): "mono"}.get(tuple(et), "5.1")
+    nch = sum(2 if t == 1 else 1 for t in et)
+    ref_f32, ref_s16 = golden_ref_pcm(d)
+    for float_mode in (True, False):
+        dec = pyref.Decoder(d["extradata"].tobytes(), int(d["core_rate"]), nch, layout, float_mode=float_mode)
+        dec.enable_dropin(hb.LIB_PATH)
+        worst_f, worst_s = 0.0, 0
+        for t, p in enumerate(pk):
+            r = dec.decode(p, capture=False)
+            worst_s = max(worst_s, int(np.abs(r["pcm"].astype(np.int32) - ref_s16[t].astype(np.int32)).max()))
+            if float_mode:
+                worst_f = max(worst_f, float(np.abs(r["pcm_f32"].astype(np.float64) - ref_f32[t]).max()) / 32768.0)
+        assert dec.dropin_frames() == len(pk), "the back end did not take every frame"
+        dec.close()
+        print("%s drop-in (%s path): max float err %.3g FS, max s16 diff %d LSB" % (name, "SIMD-scaling" if float_mode else "C bias", worst_f, worst_s))
+        assert worst_s <= 1 and worst_f <= 1e-5

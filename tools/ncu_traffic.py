@@ -19,7 +19,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "traffic_*.csv")))
     ii = hdr.index("ID")
     launches = {}
     for r in rows[1:]:
-        d = launches.setdefault(int(r[ii]), {"kernel": r[ki].split("(")[0].split("<")[0]})
+        d = launches.setdefault(int(r[ii]), {"kernel": r[ki].split("(")[0].split("<")[0].replace("void ", "").strip()})
         v = float(r[vi].replace(",", ""))
         u = r[ui].lower()
         if "byte" in u:
