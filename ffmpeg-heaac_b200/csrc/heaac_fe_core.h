@@ -306,37 +306,30 @@ FE_FN int band_types(FeChan *c, BR *b)                           /* aacdec.c:720
     return 0;
 }
 
-FE_FN int scalefactors(FE *fe, FeChan *c, BR *b, int global_gain)     /* aacdec.c:768-822 */
+/* Scale factor data (ISO/IEC 14496-3 4.6.2.3; what decode_scalefactors yields, aacdec.c:768-822).  Every coded band belongs to one
+ * of three KINDS -- spectral, noise (PNS), intensity position -- and each kind keeps one running value over the whole channel,
+ * advanced by a Huffman-coded difference per band (the first noise band carries a 9-bit PCM word instead).  A kind is described
+ * by how its running value is range-checked and where it points into the one 2^(x/4) table:
+ *     gain = sign * pow2sf[base + dir * value],   valid while 0 <= value + chk <= 255 */
+FE_FN int scalefactors(FE *fe, FeChan *c, BR *b, int global_gain)
 {
-    const int sf_offset = fe->sf_offset + (c->ws[0] == HEAAC_EIGHT_SHORT ? 12 : 0);
-    int idx = 0, noise_flag = 1;
-    int offset[3] = { global_gain, global_gain - 90, 100 };
-    for (int g = 0; g < c->num_groups; g++) {
-        for (int i = 0; i < c->max_sfb;) {
-            int end = c->run_end[idx], bt = c->band_type[idx];
-            if (bt == 0) {
-                for (; i < end; i++, idx++) c->sf[idx] = 0.f;
-            } else if (bt == 14 || bt == 15) {
-                for (; i < end; i++, idx++) {
-                    offset[2] += vlc_get(b, &TB->vsf) - 60;
-                    if ((unsigned)offset[2] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = TB->pow2sf[-offset[2] + 300];
-                }
-            } else if (bt == 13) {
-                for (; i < end; i++, idx++) {
-                    if (noise_flag-- > 0) offset[1] += br_get(b, 9) - 256;
-                    else offset[1] += vlc_get(b, &TB->vsf) - 60;
-                    if ((unsigned)offset[1] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = -TB->pow2sf[offset[1] + sf_offset + 100];
-                }
-            } else {
-                for (; i < end; i++, idx++) {
-                    offset[0] += vlc_get(b, &TB->vsf) - 60;
-                    if ((unsigned)offset[0] > 255U) return HEAAC_E_INVAL;
-                    c->sf[idx] = -TB->pow2sf[offset[0] + sf_offset];
-                }
-            }
-        }
+    enum { K_SPECTRAL, K_NOISE, K_INTENSITY, K_NONE };
+    const int sfo = fe->sf_offset + (c->ws[0] == HEAAC_EIGHT_SHORT ? 12 : 0);
+    const int   chk[3]  = { 0, 0, 100 };
+    const int   base[3] = { sfo, sfo + 100, 200 };
+    const int   dir[3]  = { 1, 1, -1 };
+    const float sign[3] = { -1.0f, -1.0f, 1.0f };
+    int value[3] = { global_gain, global_gain - 90, 0 };
+    int noise_pcm = 1;
+    const int n = c->num_groups * c->max_sfb;
+    for (int idx = 0; idx < n; idx++) {
+        const int bt = c->band_type[idx];
+        const int k = bt == 0 ? K_NONE : bt == 13 ? K_NOISE : bt >= 14 ? K_INTENSITY : K_SPECTRAL;
+        if (k == K_NONE) { c->sf[idx] = 0.f; continue; }
+        if (k == K_NOISE && noise_pcm) { value[k] += br_get(b, 9) - 256; noise_pcm = 0; }
+        else value[k] += vlc_get(b, &TB->vsf) - 60;
+        if ((unsigned)(value[k] + chk[k]) > 255U) return HEAAC_E_INVAL;
+        c->sf[idx] = sign[k] * TB->pow2sf[base[k] + dir[k] * value[k]];
     }
     return 0;
 }
@@ -585,7 +578,6 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
 }
 
 /* ---------------------------------------------------------------- SBR */
-FE_TAB int8_t ceil_log2[6] = { 0, 1, 2, 2, 3, 3 };
 
 FE_FN int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, aacsbr.c:1023-1034 */
 {
@@ -622,72 +614,68 @@ FE_FN void sbr_header(FE *fe, FeSbr *s, BR *b)                   /* read_sbr_hea
     }
 }
 
-FE_FN int sbr_grid(FeSbr *s, FeSbrCh *c, BR *b)                  /* read_sbr_grid, aacsbr.c:609-749 */
+/* The time grid of a channel (ISO/IEC 14496-3 4.6.18.3.3; what read_sbr_grid yields, aacsbr.c:609-749).  The four frame classes
+ * differ only in which ends of the frame are VARIABLE: class bit 1 = the leading border, bit 0 = the trailing one.  A variable end
+ * sends its absolute border and a count of relative borders that step inwards from it by 2 r + 2 slots each; a fixed end sits
+ * at slot 0 / 16.  With both ends fixed the envelopes divide the frame evenly instead. */
+FE_FN int sbr_grid(FeSbr *s, FeSbrCh *c, BR *b)
 {
-    unsigned ptr = 0;
-    int abs_trail = 16, nlead, ntrail, i;
-    int num_env_old = c->num_env;
+    const int num_env_old = c->num_env;
     c->freq_res[0] = c->freq_res[c->num_env];
     c->amp_res = s->amp_res_header;
     c->t_env_num_env_old = c->t_env[num_env_old];
-    switch (c->frame_class = br_get(b, 2)) {
-    case 0:
-        c->num_env = 1 << br_get(b, 2);
-        nlead = c->num_env - 1;
-        if (c->num_env == 1) c->amp_res = 0;
-        if (c->num_env > 4) return -1;
-        c->t_env[0] = 0; c->t_env[c->num_env] = abs_trail;
-        abs_trail = (abs_trail + (c->num_env >> 1)) / c->num_env;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + abs_trail;
-        c->freq_res[1] = br_get1(b);
-        for (i = 1; i < c->num_env; i++) c->freq_res[i + 1] = c->freq_res[1];
-        break;
-    case 1:
-        abs_trail += br_get(b, 2); ntrail = br_get(b, 2);
-        c->num_env = ntrail + 1;
-        c->t_env[0] = 0; c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < ntrail; i++) c->t_env[c->num_env - 1 - i] = c->t_env[c->num_env - i] - 2 * br_get(b, 2) - 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[c->num_env - i] = br_get1(b);
-        break;
-    case 2:
-        c->t_env[0] = br_get(b, 2); nlead = br_get(b, 2);
-        c->num_env = nlead + 1;
-        c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + 2 * br_get(b, 2) + 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[i + 1] = br_get1(b);
-        break;
-    default:
-        c->t_env[0] = br_get(b, 2); abs_trail += br_get(b, 2);
-        nlead = br_get(b, 2); ntrail = br_get(b, 2);
-        c->num_env = nlead + ntrail + 1;
-        if (c->num_env > 5) return -1;
-        c->t_env[c->num_env] = abs_trail;
-        for (i = 0; i < nlead; i++) c->t_env[i + 1] = c->t_env[i] + 2 * br_get(b, 2) + 2;
-        for (i = 0; i < ntrail; i++) c->t_env[c->num_env - 1 - i] = c->t_env[c->num_env - i] - 2 * br_get(b, 2) - 2;
-        ptr = br_get(b, ceil_log2[c->num_env]);
-        for (i = 0; i < c->num_env; i++) c->freq_res[i + 1] = br_get1(b);
-        break;
+    const int cls = c->frame_class = br_get(b, 2);
+    const int var_lead = cls >> 1, var_trail = cls & 1;
+    unsigned ptr = 0;
+    if (!cls) {
+        const int n = 1 << br_get(b, 2);
+        c->num_env = n;
+        if (n == 1) c->amp_res = 0;
+        if (n > 4) return -1;
+        const int step = (16 + (n >> 1)) / n;
+        for (int e = 0; e < n; e++) c->t_env[e] = (uint8_t)(e * step);
+        c->t_env[n] = 16;
+        const int res = br_get1(b);
+        for (int e = 1; e <= n; e++) c->freq_res[e] = (uint8_t)res;
+    } else {
+        const int first = var_lead ? br_get(b, 2) : 0;
+        const int last = 16 + (var_trail ? br_get(b, 2) : 0);
+        const int n_lead = var_lead ? br_get(b, 2) : 0, n_trail = var_trail ? br_get(b, 2) : 0;
+        const int n = n_lead + n_trail + 1;
+        c->num_env = n;
+        if (n > 5) return -1;
+        c->t_env[0] = (uint8_t)first;
+        c->t_env[n] = (uint8_t)last;
+        for (int e = 1; e <= n_lead; e++) c->t_env[e] = (uint8_t)(c->t_env[e - 1] + 2 * br_get(b, 2) + 2);
+        for (int e = n - 1; e >= n - n_trail; e--) c->t_env[e] = (uint8_t)(c->t_env[e + 1] - 2 * br_get(b, 2) - 2);
+        ptr = br_get(b, n > 3 ? 3 : n > 1 ? 2 : 1);                  /* enough bits for 0 .. n */
+        /* one resolution flag per envelope; a frame that is variable at the end only sends them last envelope first */
+        if (cls == 1) for (int e = n; e >= 1; e--) c->freq_res[e] = br_get1(b);
+        else          for (int e = 1; e <= n; e++) c->freq_res[e] = br_get1(b);
     }
-    if (ptr > (unsigned)c->num_env + 1) return -1;
-    for (i = 1; i <= c->num_env; i++) if (c->t_env[i - 1] > c->t_env[i]) return -1;
-    c->num_noise = (c->num_env > 1) + 1;
-    c->t_q[0] = c->t_env[0]; c->t_q[c->num_noise] = c->t_env[c->num_env];
-    if (c->num_noise > 1) {
-        unsigned idx;
-        if (c->frame_class == 0) idx = c->num_env >> 1;
-        else if (c->frame_class & 1) {                             /* FFMAX(bs_pointer - 1, 1) on an UNSIGNED pointer: 0 wraps, aacsbr.c:729 */
-            unsigned a = ptr - 1u;
-            idx = (unsigned)c->num_env - (a > 1u ? a : 1u);
-        }
-        else idx = !ptr ? 1 : (ptr == 1 ? (unsigned)c->num_env - 1 : ptr - 1);
-        c->t_q[1] = c->t_env[idx];
+    const int n = c->num_env;
+    if (ptr > (unsigned)n + 1) return -1;
+    for (int e = 1; e <= n; e++) if (c->t_env[e - 1] > c->t_env[e]) return -1;
+    /* noise floors: one for a single envelope, else two, split at the border the pointer selects (the middle one without a pointer) */
+    c->num_noise = n > 1 ? 2 : 1;
+    c->t_q[0] = c->t_env[0]; c->t_q[c->num_noise] = c->t_env[n];
+    if (n > 1) {
+        unsigned at;
+        if (!cls) at = n >> 1;
+        else if (var_trail) {
+            /* counted back from the end: max(pointer - 1, 1), in UNSIGNED arithmetic as in the reference (aacsbr.c:729): pointer 0
+             * wraps and lands one past the last border */
+            const unsigned back = ptr - 1u;
+            at = (unsigned)n - (back > 1u ? back : 1u);
+        } else
+            at = ptr == 0 ? 1u : ptr == 1 ? (unsigned)n - 1u : ptr - 1u;
+        c->t_q[1] = c->t_env[at];
     }
+    /* the envelope that starts at a transient (l_A), and whether the previous frame's one ended exactly at the frame border */
     c->e_a[0] = -(c->e_a[1] != num_env_old);
     c->e_a[1] = -1;
-    if ((c->frame_class & 1) && ptr) c->e_a[1] = c->num_env + 1 - ptr;
-    else if (c->frame_class == 2 && ptr > 1) c->e_a[1] = ptr - 1;
+    if (var_trail && ptr) c->e_a[1] = n + 1 - (int)ptr;
+    else if (cls == 2 && ptr > 1) c->e_a[1] = (int)ptr - 1;
     return 0;
 }
 
@@ -714,148 +702,146 @@ FE_FN void sbr_invf(FeSbr *s, FeSbrCh *c, BR *b)
     for (int i = 0; i < s->t.n_q; i++) c->invf[0][i] = br_get(b, 2);
 }
 
-FE_FN void sbr_envelope(FeSbr *s, FeSbrCh *c, BR *b, int ch)     /* read_sbr_envelope, aacsbr.c:787-854 */
+/* One matrix of delta-coded SBR parameters -- envelope scalefactors or noise floors (ISO/IEC 14496-3 4.6.18.3.5; what
+ * read_sbr_envelope / read_sbr_noise yield, aacsbr.c:787-890).  Row r + 1 is coded either along FREQUENCY (a start value of
+ * `start_bits`, then Huffman-coded differences between neighbouring bands) or along TIME (differences to row r).  The two rows of
+ * a time difference may sit on different band tables (res[]: 0 = low, 1 = high resolution): a high band then refers to the low
+ * band that contains it, a low band to the high band it starts with (`odd`: the high table has an odd number of bands, so the
+ * pairing is shifted by one).  Every value is scaled by `scale` (2 for the balance channel of a coupled pair).  Row 0 receives a
+ * copy of the last row: the base of the next frame's first time difference. */
+FE_FN void sbr_delta_rows(BR *b, int16_t *m, int stride, int rows, const uint8_t *along_time, const uint8_t *res,
+                          int n_low, int n_high, int odd, int tab_time, int tab_freq, int start_bits, int scale)
 {
-    int bits, th, fh;
-    const int delta = (ch == 1 && s->coupling == 1) + 1, odd = s->t.n[1] & 1;
-    if (s->coupling && ch) {
-        if (c->amp_res) { bits = 5; th = T_ENV_BAL_30; fh = F_ENV_BAL_30; } else { bits = 6; th = T_ENV_BAL_15; fh = F_ENV_BAL_15; }
-    } else {
-        if (c->amp_res) { bits = 6; th = T_ENV_30; fh = F_ENV_30; } else { bits = 7; th = T_ENV_15; fh = F_ENV_15; }
-    }
-    for (int i = 0; i < c->num_env; i++) {
-        const int nb = s->t.n[c->freq_res[i + 1]];
-        if (c->df_env[i]) {
-            if (c->freq_res[i + 1] == c->freq_res[i]) {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][j] + delta * (vlc_get(b, &TB->vsbr[th]) - sbr_lav[th]);
-            } else if (c->freq_res[i + 1]) {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][(j + odd) >> 1] + delta * (vlc_get(b, &TB->vsbr[th]) - sbr_lav[th]);
-            } else {
-                for (int j = 0; j < nb; j++) c->env[i + 1][j] = c->env[i][j ? 2 * j - odd : 0] + delta * (vlc_get(b, &TB->vsbr[th]) - sbr_lav[th]);
+    for (int r = 0; r < rows; r++) {
+        int16_t *cur = m + (r + 1) * stride;
+        const int16_t *prev = m + r * stride;
+        const int hi = res[r + 1], n = hi ? n_high : n_low;
+        if (along_time[r]) {
+            const int same = res[r + 1] == res[r];
+            for (int j = 0; j < n; j++) {
+                const int ref = same ? j : hi ? (j + odd) >> 1 : (j ? 2 * j - odd : 0);
+                cur[j] = (int16_t)(prev[ref] + scale * (vlc_get(b, &TB->vsbr[tab_time]) - sbr_lav[tab_time]));
             }
         } else {
-            c->env[i + 1][0] = delta * br_get(b, bits);
-            for (int j = 1; j < nb; j++) c->env[i + 1][j] = c->env[i + 1][j - 1] + delta * (vlc_get(b, &TB->vsbr[fh]) - sbr_lav[fh]);
+            cur[0] = (int16_t)(scale * br_get(b, start_bits));
+            for (int j = 1; j < n; j++)
+                cur[j] = (int16_t)(cur[j - 1] + scale * (vlc_get(b, &TB->vsbr[tab_freq]) - sbr_lav[tab_freq]));
         }
     }
+}
+
+FE_FN void sbr_envelope(FeSbr *s, FeSbrCh *c, BR *b, int ch)
+{
+    const int balance = s->coupling && ch, fine = !c->amp_res;          /* 1.5 dB steps need one more start bit and their own tables */
+    const int tab_time = balance ? (fine ? T_ENV_BAL_15 : T_ENV_BAL_30) : (fine ? T_ENV_15 : T_ENV_30);
+    const int tab_freq = balance ? (fine ? F_ENV_BAL_15 : F_ENV_BAL_30) : (fine ? F_ENV_15 : F_ENV_30);
+    sbr_delta_rows(b, &c->env[0][0], 48, c->num_env, c->df_env, c->freq_res, s->t.n[0], s->t.n[1], s->t.n[1] & 1,
+                   tab_time, tab_freq, (balance ? 5 : 6) + fine, (ch == 1 && s->coupling == 1) + 1);
     fe_copy32(c->env[0], c->env[c->num_env], (int)(sizeof(c->env[0]) / 4));
 }
 
-FE_FN void sbr_noise(FeSbr *s, FeSbrCh *c, BR *b, int ch)        /* read_sbr_noise, aacsbr.c:856-890 */
+FE_FN void sbr_noise(FeSbr *s, FeSbrCh *c, BR *b, int ch)
 {
-    int th, fh;
-    const int delta = (ch == 1 && s->coupling == 1) + 1;
-    if (s->coupling && ch) { th = T_NOISE_BAL_30; fh = F_ENV_BAL_30; } else { th = T_NOISE_30; fh = F_ENV_30; }
-    for (int i = 0; i < c->num_noise; i++) {
-        if (c->df_noise[i]) {
-            for (int j = 0; j < s->t.n_q; j++) c->noise[i + 1][j] = c->noise[i][j] + delta * (vlc_get(b, &TB->vsbr[th]) - sbr_lav[th]);
-        } else {
-            c->noise[i + 1][0] = delta * br_get(b, 5);
-            for (int j = 1; j < s->t.n_q; j++) c->noise[i + 1][j] = c->noise[i + 1][j - 1] + delta * (vlc_get(b, &TB->vsbr[fh]) - sbr_lav[fh]);
-        }
-    }
+    const int balance = s->coupling && ch;
+    const uint8_t one_table[4] = { 0, 0, 0, 0 };                         /* noise floors all sit on the noise band table */
+    sbr_delta_rows(b, &c->noise[0][0], 5, c->num_noise, c->df_noise, one_table, s->t.n_q, s->t.n_q, 0,
+                   balance ? T_NOISE_BAL_30 : T_NOISE_30, balance ? F_ENV_BAL_30 : F_ENV_30, 5, (ch == 1 && s->coupling == 1) + 1);
     memcpy(c->noise[0], c->noise[c->num_noise], sizeof(c->noise[0]));
 }
 
 /* ---------------------------------------------------------------- PS (ff_ps_read_data, aacps.c:150-279) */
-FE_TAB int8_t nr_iidicc_tab[6] = { 10, 20, 34, 10, 20, 34 }, nr_ipdopd_tab[6] = { 5, 11, 17, 5, 11, 17 };
-FE_TAB int8_t num_env_tab[2][4] = { { 0, 1, 2, 4 }, { 1, 2, 3, 4 } };
+/* parameter bands per iid / icc mode (modes 3..5: the same counts with the finer iid quantiser) and of the phase parameters */
+FE_TAB int8_t ps_bands_of_mode[6] = { 10, 20, 34, 10, 20, 34 }, ps_phase_bands_of_mode[6] = { 5, 11, 17, 5, 11, 17 };
 
-FE_FN int ps_par(FePs *p, BR *b, int8_t (*par)[34], int table, int e, int dt, int num, int kind)
+/* One envelope's worth of one Parametric Stereo parameter (iid, icc, ipd or opd; ISO/IEC 14496-3 8.6.4.6.2).  A parameter is
+ * described by its Huffman tables (frequency / time differences), the offset of their symbol range and how a value is kept in
+ * range: iid and icc are range-CHECKED (a violation invalidates the frame), the phase parameters WRAP modulo 8. */
+typedef struct PsParam { int8_t (*rows)[34]; int count, tab_freq, tab_time, lo, hi, wrap; } PsParam;
+
+FE_FN int ps_param_env(const FePs *p, BR *b, const PsParam *q, int e)
 {
-    /* kind 0: iid (range check), 1: icc, 2: ipd/opd (modulo 8, no offset) */
-    const int off = kind == 2 ? 0 : ps_off[table];
-    if (dt) {
-        int e_prev = e ? e - 1 : p->num_env_old - 1;
-        if (e_prev < 0) e_prev = 0;
-        for (int k = 0; k < num; k++) {
-            int val = par[e_prev][k] + vlc_get(b, &TB->vps[table]) - off;
-            if (kind == 2) val &= 7;
-            par[e][k] = (int8_t)val;
-            if (kind == 0 && abs(par[e][k]) > 7 + 8 * p->iid_quant) return -1;
-            if (kind == 1 && (unsigned)par[e][k] > 7U) return -1;
-        }
-    } else {
-        int val = 0;
-        for (int k = 0; k < num; k++) {
-            val += vlc_get(b, &TB->vps[table]) - off;
-            if (kind == 2) val &= 7;
-            par[e][k] = (int8_t)val;
-            if (kind == 0 && abs(par[e][k]) > 7 + 8 * p->iid_quant) return -1;
-            if (kind == 1 && (unsigned)par[e][k] > 7U) return -1;
-        }
+    const int along_time = br_get1(b);
+    const int table = along_time ? q->tab_time : q->tab_freq;
+    const int off = q->wrap ? 0 : ps_off[table];
+    int base_row = e ? e - 1 : p->num_env_old - 1;                  /* time differences refer to the previous envelope (of the previous frame) */
+    if (base_row < 0) base_row = 0;
+    int run = 0;
+    for (int k = 0; k < q->count; k++) {
+        int v = (along_time ? q->rows[base_row][k] : run) + vlc_get(b, &TB->vps[table]) - off;
+        if (q->wrap) v &= 7;
+        run = v;
+        q->rows[e][k] = (int8_t)v;
+        if (!q->wrap && (q->rows[e][k] < q->lo || q->rows[e][k] > q->hi)) return -1;     /* (the stored 8-bit value is what counts) */
     }
     return 0;
 }
 
+/* ps_data() (ISO/IEC 14496-3 8.6.4.6.2; what ff_ps_read_data yields, aacps.c:150-279): optional header, envelope borders, then
+ * the enabled parameters envelope by envelope, the phase parameters inside an extension container. */
 FE_FN int ps_read(FePs *p, BR *host, int bits_left)
 {
     BR bb = *host, *b = &bb;
     const int start_pos = host->pos;
-    int header = br_get1(b);
+    const int header = br_get1(b);
     if (header) {
-        p->enable_iid = br_get1(b);
-        if (p->enable_iid) {
-            int m = br_get(b, 3);
-            if (m > 5) goto err;
-            p->nr_iid_par = nr_iidicc_tab[m]; p->iid_quant = m > 2; p->nr_ipdopd_par = nr_ipdopd_tab[m];
+        if ((p->enable_iid = br_get1(b))) {
+            const int mode = br_get(b, 3);
+            if (mode > 5) goto err;
+            p->nr_iid_par = ps_bands_of_mode[mode]; p->iid_quant = mode > 2; p->nr_ipdopd_par = ps_phase_bands_of_mode[mode];
         }
-        p->enable_icc = br_get1(b);
-        if (p->enable_icc) {
+        if ((p->enable_icc = br_get1(b))) {
             p->icc_mode = br_get(b, 3);
             if (p->icc_mode > 5) goto err;
-            p->nr_icc_par = nr_iidicc_tab[p->icc_mode];
+            p->nr_icc_par = ps_bands_of_mode[p->icc_mode];
         }
         p->enable_ext = br_get1(b);
     }
+    /* envelopes: 0 / 1 / 2 / 4 evenly spaced (fixed class) or 1..4 with explicit borders */
     p->frame_class = br_get1(b);
     p->num_env_old = p->num_env;
-    p->num_env = num_env_tab[p->frame_class][br_get(b, 2)];
-    p->border[0] = -1;
-    if (p->frame_class) for (int e = 1; e <= p->num_env; e++) p->border[e] = br_get(b, 5);
-    else for (int e = 1; e <= p->num_env; e++) p->border[e] = (e * 32 >> (p->num_env == 4 ? 2 : p->num_env == 2 ? 1 : 0)) - 1;
-    if (p->enable_iid) {
-        for (int e = 0; e < p->num_env; e++) {
-            int dt = br_get1(b);
-            if (ps_par(p, b, p->iid, (dt ? (p->iid_quant ? PS_IID_DT1 : PS_IID_DT0) : (p->iid_quant ? PS_IID_DF1 : PS_IID_DF0)), e, dt, p->nr_iid_par, 0)) goto err;
-        }
-    } else fe_zero16(p->iid, (int)(sizeof(p->iid) / 2));
-    if (p->enable_icc) {
-        for (int e = 0; e < p->num_env; e++) {
-            int dt = br_get1(b);
-            if (ps_par(p, b, p->icc, dt ? PS_ICC_DT : PS_ICC_DF, e, dt, p->nr_icc_par, 1)) goto err;
-        }
-    } else fe_zero16(p->icc, (int)(sizeof(p->icc) / 2));
-    if (p->enable_ext) {
-        int cnt = br_get(b, 4);
-        if (cnt == 15) cnt += br_get(b, 8);
-        cnt *= 8;
-        while (cnt > 7) {
-            int id = br_get(b, 2), used = 0;
-            if (id == 0) {                                         /* ps_read_extension_data, aacps.c:120-139 */
-                int p0 = b->pos;
-                p->enable_ipdopd = br_get1(b);
-                if (p->enable_ipdopd)
-                    for (int e = 0; e < p->num_env; e++) {
-                        int dt = br_get1(b);
-                        ps_par(p, b, p->ipd, dt ? PS_IPD_DT : PS_IPD_DF, e, dt, p->nr_ipdopd_par, 2);
-                        dt = br_get1(b);
-                        ps_par(p, b, p->opd, dt ? PS_OPD_DT : PS_OPD_DF, e, dt, p->nr_ipdopd_par, 2);
-                    }
-                br_skip(b, 1);
-                used = b->pos - p0;
-            }
-            cnt -= 2 + used;
-        }
-        if (cnt < 0) goto err;
-        br_skip(b, cnt);
+    {
+        const int code = br_get(b, 2);
+        p->num_env = p->frame_class ? code + 1 : (code == 3 ? 4 : code);
     }
-    if (!p->num_env || p->border[p->num_env] < 31) {               /* fake envelope, aacps.c:235-252 */
-        int source = p->num_env ? p->num_env - 1 : p->num_env_old - 1;
-        if (source >= 0 && source != p->num_env) {
-            if (p->enable_iid) memcpy(p->iid[p->num_env], p->iid[source], 34);
-            if (p->enable_icc) memcpy(p->icc[p->num_env], p->icc[source], 34);
-            if (p->enable_ipdopd) { memcpy(p->ipd[p->num_env], p->ipd[source], 34); memcpy(p->opd[p->num_env], p->opd[source], 34); }
+    p->border[0] = -1;
+    for (int e = 1; e <= p->num_env; e++)
+        p->border[e] = p->frame_class ? (int)br_get(b, 5) : e * (32 / p->num_env) - 1;
+    {
+        const PsParam iid = { p->iid, p->nr_iid_par, p->iid_quant ? PS_IID_DF1 : PS_IID_DF0, p->iid_quant ? PS_IID_DT1 : PS_IID_DT0,
+                              -(7 + 8 * p->iid_quant), 7 + 8 * p->iid_quant, 0 };
+        const PsParam icc = { p->icc, p->nr_icc_par, PS_ICC_DF, PS_ICC_DT, 0, 7, 0 };
+        if (p->enable_iid) { for (int e = 0; e < p->num_env; e++) if (ps_param_env(p, b, &iid, e)) goto err; }
+        else fe_zero16(p->iid, (int)(sizeof(p->iid) / 2));
+        if (p->enable_icc) { for (int e = 0; e < p->num_env; e++) if (ps_param_env(p, b, &icc, e)) goto err; }
+        else fe_zero16(p->icc, (int)(sizeof(p->icc) / 2));
+    }
+    if (p->enable_ext) {
+        /* extension container: a byte count, then elements of a 2-bit id each; id 0 carries the phase parameters (aacps.c:120-139) */
+        int left = br_get(b, 4);
+        if (left == 15) left += br_get(b, 8);
+        left *= 8;
+        while (left > 7) {
+            const int id = br_get(b, 2), at = b->pos;
+            if (id == 0) {
+                const PsParam ipd = { p->ipd, p->nr_ipdopd_par, PS_IPD_DF, PS_IPD_DT, 0, 7, 1 };
+                const PsParam opd = { p->opd, p->nr_ipdopd_par, PS_OPD_DF, PS_OPD_DT, 0, 7, 1 };
+                if ((p->enable_ipdopd = br_get1(b)))
+                    for (int e = 0; e < p->num_env; e++) { ps_param_env(p, b, &ipd, e); ps_param_env(p, b, &opd, e); }
+                br_skip(b, 1);
+            }
+            left -= 2 + (b->pos - at);
+        }
+        if (left < 0) goto err;
+        br_skip(b, left);
+    }
+    if (!p->num_env || p->border[p->num_env] < 31) {
+        /* the last envelope must end at the frame's last slot: if it does not (or there is none), one more envelope that repeats
+         * the last parameters is appended (aacps.c:235-252) */
+        const int last = p->num_env ? p->num_env - 1 : p->num_env_old - 1;
+        if (last >= 0 && last != p->num_env) {
+            if (p->enable_iid) memcpy(p->iid[p->num_env], p->iid[last], 34);
+            if (p->enable_icc) memcpy(p->icc[p->num_env], p->icc[last], 34);
+            if (p->enable_ipdopd) { memcpy(p->ipd[p->num_env], p->ipd[last], 34); memcpy(p->opd[p->num_env], p->opd[last], 34); }
         }
         p->num_env++;
         p->border[p->num_env] = 31;
@@ -866,7 +852,7 @@ FE_FN int ps_read(FePs *p, BR *host, int bits_left)
     if (!p->enable_ipdopd) fe_zero32(p->ipd, (int)((sizeof(p->ipd) + sizeof(p->opd)) / 4));     /* contiguous, 4-byte aligned */
     if (header) p->start = 1;
     {
-        int consumed = b->pos - start_pos;
+        const int consumed = b->pos - start_pos;
         if (consumed <= bits_left) { host->pos += consumed; return consumed; }
     }
 err:
