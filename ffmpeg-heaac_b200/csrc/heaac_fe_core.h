@@ -31,8 +31,13 @@
 #define FE_MAX_CH 16
 #ifdef FE_DEVICE
 #define FE_INL static __device__ __forceinline__
+/* big routines that a kernel reaches once per frame (or only on a rare path): called, not inlined -- one copy in the kernel instead
+ * of one per call site keeps the instruction footprint (the parse kernels are instruction-fetch bound) and the register
+ * allocation of the hot paths around them down */
+#define FE_BIG static __device__ __noinline__
 #else
 #define FE_INL static inline __attribute__((always_inline))
+#define FE_BIG static
 #endif
 
 /* ---------------------------------------------------------------- bit reader */
@@ -579,7 +584,7 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
 
 /* ---------------------------------------------------------------- SBR */
 
-FE_FN int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, aacsbr.c:1023-1034 */
+FE_BIG int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, aacsbr.c:1023-1034 */
 {
     HeaacSbrElem t = s->t;
     int r = fe_sbr_tables(fe->sample_rate, s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale,
@@ -778,7 +783,7 @@ FE_FN int ps_param_env(const FePs *p, BR *b, const PsParam *q, int e)
 
 /* ps_data() (ISO/IEC 14496-3 8.6.4.6.2; what ff_ps_read_data yields, aacps.c:150-279): optional header, envelope borders, then
  * the enabled parameters envelope by envelope, the phase parameters inside an extension container. */
-FE_FN int ps_read(FePs *p, BR *host, int bits_left)
+FE_BIG int ps_read(FePs *p, BR *host, int bits_left)
 {
     BR bb = *host, *b = &bb;
     const int start_pos = host->pos;
@@ -1000,7 +1005,7 @@ FE_FN void fe_sbr_payload(FE *fe, BR *b, int crc, int cnt, int prev_elem, int pr
 /* One packet (an ADTS frame or a bare raw_data_block) -> the frame's C-ABI structures.
  * coeffs [ncc][1024]; ics/tns [ncc]; sbr [nse] (may be NULL for LC); ps (may be NULL).
  * Returns bytes consumed (>= 0) or a negative HEAAC_E_* code (the reference returns -1). */
-FE_FN int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                          HeaacSbrElem *sbr, HeaacPsFrame *ps)
 {
     if (!fe || !pkt || size <= 0 || !coeffs || !ics) return HEAAC_E_INVAL;

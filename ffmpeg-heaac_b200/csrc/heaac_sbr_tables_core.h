@@ -261,7 +261,14 @@ FE_FN void sbt_limiter(HeaacSbrElem *o, int limiter_bands)
  * kx[0] / m[0] (previous frame's values) and all per-frame fields are left untouched.
  * Returns 0, or HEAAC_E_INVAL when the reference would reject the header ("pure upsampling").
  */
-FE_FN int fe_sbr_tables(int core_sample_rate, int bs_start_freq, int bs_stop_freq, int bs_xover_band,
+#ifndef FE_BIG
+#ifdef FE_DEVICE
+#define FE_BIG static __device__ __noinline__
+#else
+#define FE_BIG static
+#endif
+#endif
+FE_BIG int fe_sbr_tables(int core_sample_rate, int bs_start_freq, int bs_stop_freq, int bs_xover_band,
                           int bs_freq_scale, int bs_alter_scale, int bs_noise_bands, int bs_limiter_bands,
                           HeaacSbrElem *out)
 {
