@@ -188,14 +188,14 @@ class Context:
         self.S = cfg.n_streams
 
     # -- host-pointer path: copies H2D / D2H inside the call (the e2e path) --
-    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=False, pcm_out=None):
+    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=False, pcm_out=None, cce=None):
         coeffs = np.ascontiguousarray(coeffs, np.float32)
         T = coeffs.size // (self.S * self.ncc * 1024)
         keep = [coeffs, np.ascontiguousarray(ics, ICS)]
         b = Batch()
         b.n_frames, b.on_device = T, 0
         b.coeffs, b.ics = keep[0].ctypes.data, keep[1].ctypes.data
-        for name, arr, dt in (("tns", tns, TNS), ("sbr", sbr, SBR_ELEM), ("ps", ps, PS_FRAME)):
+        for name, arr, dt in (("tns", tns, TNS), ("sbr", sbr, SBR_ELEM), ("ps", ps, PS_FRAME), ("cce", cce, abi.CCE)):
             if arr is not None:
                 a = np.ascontiguousarray(arr, dt)
                 keep.append(a)

@@ -8,7 +8,7 @@ between this file and the header fails loudly.
 import numpy as np
 
 TNS_MAX_ORDER = 20
-TYPE_SCE, TYPE_CPE, TYPE_LFE = 0, 1, 3
+TYPE_SCE, TYPE_CPE, TYPE_CCE, TYPE_LFE = 0, 1, 2, 3
 ONLY_LONG, LONG_START, EIGHT_SHORT, LONG_STOP = 0, 1, 2, 3
 
 ICS = np.dtype([
@@ -49,13 +49,15 @@ PS_FRAME = np.dtype([
     ("ipd_par", "i1", (5, 34)), ("opd_par", "i1", (5, 34)),
 ], align=True)
 
-SIZES = {"HeaacIcs": ICS.itemsize, "HeaacTns": TNS.itemsize, "HeaacSbrChan": SBR_CHAN.itemsize,
+CCE = np.dtype([("coupling_point", "u1"), ("n_targets", "u1"), ("reserved", "u1", 2), ("target_ch", "u1", 16), ("gain", "f4", 16)])
+
+SIZES = {"HeaacCce": CCE.itemsize, "HeaacIcs": ICS.itemsize, "HeaacTns": TNS.itemsize, "HeaacSbrChan": SBR_CHAN.itemsize,
          "HeaacSbrElem": SBR_ELEM.itemsize, "HeaacPsFrame": PS_FRAME.itemsize}
 
 # ---- ctypes mirrors of HeaacConfig / HeaacBatch (include/heaac_b200.h) -------------
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_ELEMS = 8
 
 
@@ -73,7 +75,7 @@ class Batch(C.Structure):
     _fields_ = [
         ("n_frames", C.c_int32), ("on_device", C.c_int32),
         ("coeffs", C.c_void_p), ("ics", C.c_void_p), ("tns", C.c_void_p), ("sbr", C.c_void_p), ("ps", C.c_void_p),
-        ("pcm", C.c_void_p), ("pcm_f32", C.c_void_p),
+        ("pcm", C.c_void_p), ("pcm_f32", C.c_void_p), ("cce", C.c_void_p),
     ]
 
 

@@ -228,6 +228,16 @@ k_synth(HeaacGeom g, const float *X, HeaacSynthState *synth,
                                 qmf_scale, g.add_bias, T, threadIdx.x);
 }
 
+/* independent channel coupling + s16 epilogue, one CTA per stream (layouts with coupling channel elements only) */
+__global__ void __launch_bounds__(HEAAC_THREADS)
+k_couple(HeaacGeom g, const float *__restrict__ f32, const HeaacCce *__restrict__ cce, int16_t *pcm, float *pcm_f32)
+{
+    const int s = blockIdx.x;
+    heaac_couple_stream<HEAAC_THREADS>(&g, f32 + (size_t)s * g.ncc * 1024, cce + (size_t)s * g.n_cce,
+                                       pcm ? pcm + (size_t)s * 1024 * g.nout : nullptr,
+                                       pcm_f32 ? pcm_f32 + (size_t)s * g.nout * 1024 : nullptr, threadIdx.x);
+}
+
 /* ------------------------------------------------------------------------------------ */
 int heaac_cuda_err(cudaError_t e, const char *what)
 {
@@ -270,7 +280,9 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
     }
     g->ncc = ch;
     g->nse = se;
-    g->nout = cfg->ps ? 2 : ch;
+    for (int e = 0, c0 = 0; e < cfg->n_elems; c0 += cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1, e++)
+        if (cfg->elem_type[e] == HEAAC_TYPE_CCE) g->cce_ch[g->n_cce++] = (uint8_t)c0;
+    g->nout = cfg->ps ? 2 : ch - g->n_cce;
     g->ds = cfg->sbr && cfg->sbr_downsampled;
     g->out_len = cfg->sbr && !g->ds ? 2048 : 1024;
     g->sr_index = cfg->sr_index;
@@ -282,6 +294,14 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
         int any = 0;
         for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
         for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) g->out_slot[i] = (any && !cfg->ps) ? cfg->out_slot[i] : (uint8_t)i;
+        if (g->n_cce) {                              /* coupling channels have no output; the others keep their order */
+            int o = 0;
+            for (int i = 0; i < ch; i++) {
+                const bool is_cce = cfg->elem_type[g->ch_elem[i]] == HEAAC_TYPE_CCE;
+                g->out_slot[i] = is_cce ? 0xff : (any ? cfg->out_slot[i] : (uint8_t)o);
+                o += !is_cce;
+            }
+        }
     }
 }
 
@@ -309,21 +329,30 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     if (cfg->n_streams <= 0 || cfg->n_elems <= 0 || cfg->n_elems > HEAAC_MAX_ELEMS) return HEAAC_E_INVAL;
     if (cfg->sr_index < 0 || cfg->sr_index > 12) return HEAAC_E_INVAL;
     if (cfg->max_frames_per_call <= 0) return HEAAC_E_INVAL;
-    int nch = 0, has_lfe = 0;
+    int nch = 0, has_lfe = 0, n_cce = 0;
     for (int e = 0; e < cfg->n_elems; e++) {
         int t = cfg->elem_type[e];
-        if (t != HEAAC_TYPE_SCE && t != HEAAC_TYPE_CPE && t != HEAAC_TYPE_LFE) return HEAAC_E_INVAL;
+        if (t != HEAAC_TYPE_SCE && t != HEAAC_TYPE_CPE && t != HEAAC_TYPE_LFE && t != HEAAC_TYPE_CCE) return HEAAC_E_INVAL;
         nch += t == HEAAC_TYPE_CPE ? 2 : 1;
         has_lfe |= t == HEAAC_TYPE_LFE;
+        n_cce += t == HEAAC_TYPE_CCE;
     }
+    (void)has_lfe;
+    /* coupling channel elements: independent coupling of AAC-LC layouts (with SBR the coupled signal would have to go through
+     * ff_sbr_apply as well, aacdec.c:1923-1928: not built) */
+    if (n_cce && (cfg->sbr || cfg->ps)) return HEAAC_E_UNSUPPORTED;
     if (nch > HEAAC_MAX_CHANNELS) return HEAAC_E_INVAL;
     if (cfg->ps && !(cfg->sbr && cfg->n_elems == 1 && cfg->elem_type[0] == HEAAC_TYPE_SCE)) return HEAAC_E_INVAL;
     {
         int any = 0, seen = 0;
         for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
         if (any && !cfg->ps) {
-            for (int i = 0; i < nch; i++) {
-                if (cfg->out_slot[i] >= nch || (seen >> cfg->out_slot[i]) & 1) return HEAAC_E_INVAL;
+            for (int i = 0, e = 0, left = 0; i < nch; i++) {
+                if (!left) left = cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1;
+                const bool is_cce = cfg->elem_type[e] == HEAAC_TYPE_CCE;
+                if (!--left) e++;
+                if (is_cce) continue;
+                if (cfg->out_slot[i] >= nch - n_cce || (seen >> cfg->out_slot[i]) & 1) return HEAAC_E_INVAL;
                 seen |= 1 << cfg->out_slot[i];
             }
         }
@@ -375,6 +404,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
         if (g->ps || g->ds || cfg->keep_intermediates) CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
+    if (g->n_cce) CKX(cudaMalloc(&c->d_couple, S * g->ncc * 1024 * sizeof(float)));
     c->chunk = (int)((T + 3) / 4);
     if (c->chunk > 8) c->chunk = 8;
     if (cfg->chunk_frames > 0) c->chunk = cfg->chunk_frames;
@@ -395,6 +425,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
             CKX(cudaMalloc(&c->s_tns[i], Tc * S * g->ncc * sizeof(HeaacTns)));
             if (g->sbr) CKX(cudaMalloc(&c->s_sbr[i], Tc * S * g->nse * sizeof(HeaacSbrElem)));
             if (g->ps)  CKX(cudaMalloc(&c->s_ps[i], Tc * S * sizeof(HeaacPsFrame)));
+            if (g->n_cce) CKX(cudaMalloc(&c->s_cce[i], Tc * S * g->n_cce * sizeof(HeaacCce)));
             CKX(cudaMalloc(&c->s_pcm[i], Tc * S * g->out_len * g->nout * sizeof(int16_t)));
             if (cfg->want_float_out) CKX(cudaMalloc(&c->s_pcm_f32[i], Tc * S * g->out_len * g->nout * sizeof(float)));
         }
@@ -427,9 +458,9 @@ extern "C" void heaac_b200_destroy(HeaacContext *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tables); cudaFree(c->d_chan); cudaFree(c->d_synth); cudaFree(c->d_ps);
-    cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_tns_done);
+    cudaFree(c->d_X); cudaFree(c->d_work); cudaFree(c->d_tns_done); cudaFree(c->d_couple);
     for (int i = 0; i < 2; i++) {
-        cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]);
+        cudaFree(c->s_coeffs[i]); cudaFree(c->s_ics[i]); cudaFree(c->s_tns[i]); cudaFree(c->s_sbr[i]); cudaFree(c->s_ps[i]); cudaFree(c->s_cce[i]);
         cudaFree(c->s_pcm[i]); cudaFree(c->s_pcm_f32[i]);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -462,7 +493,7 @@ extern "C" uintptr_t heaac_b200_stream(const HeaacContext *c) { return c ? (uint
 
 /* launches for frames [0, n) of a device-resident batch on c->stream */
 int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
-                         const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32)
+                         const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32, const HeaacCce *cce)
 {
     const HeaacGeom g = c->geom;
     const size_t S = g.n_streams;
@@ -526,8 +557,19 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             c->launches++;
         }
         const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
-        k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, co, ic, tn, c->d_chan, pc, pf, c->d_tables, c->d_work,
-                                                                   tn ? c->d_tns_done : nullptr);
+        if (g.n_cce) {
+            /* coupling channel elements: every coded channel goes to the planar float buffer (its own slot each), k_couple adds
+             * the coupling channels to their targets and converts */
+            HeaacGeom gp = g;
+            gp.nout = g.ncc;
+            for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) gp.out_slot[i] = (uint8_t)i;
+            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(gp, (int)n_ch, co, ic, tn, c->d_chan, nullptr, c->d_couple, c->d_tables,
+                                                                       c->d_work, tn ? c->d_tns_done : nullptr);
+            k_couple<<<(unsigned)S, HEAAC_THREADS, 0, c->stream>>>(g, c->d_couple, cce + (size_t)f * S * g.n_cce, pc, pf);
+            c->launches++;
+        } else
+            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, co, ic, tn, c->d_chan, pc, pf, c->d_tables, c->d_work,
+                                                                       tn ? c->d_tns_done : nullptr);
         prof_end(c);
         c->launches++;
     }
@@ -542,10 +584,11 @@ extern "C" int heaac_b200_synth_submit(HeaacContext *c, const HeaacBatch *b)
     const HeaacGeom *g = &c->geom;
     if (g->sbr && !b->sbr) return HEAAC_E_INVAL;
     if (g->ps && !b->ps) return HEAAC_E_INVAL;
+    if (g->n_cce && !b->cce) return HEAAC_E_INVAL;
     if (!b->pcm && !b->pcm_f32) return HEAAC_E_INVAL;
     CK(cudaSetDevice(c->cfg.device));
     if (b->on_device)
-        return heaac_launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32);
+        return heaac_launch_frames(c, b->n_frames, b->coeffs, b->ics, b->tns, b->sbr, b->ps, b->pcm, b->pcm_f32, b->cce);
 
     if (b->pcm_f32 && !c->s_pcm_f32[0]) return HEAAC_E_INVAL;   /* context created without want_float_out */
     const size_t S = g->n_streams;
@@ -563,12 +606,14 @@ extern "C" int heaac_b200_synth_submit(HeaacContext *c, const HeaacBatch *b)
                                        cudaMemcpyHostToDevice, c->s_in));
         if (g->ps)  CK(cudaMemcpyAsync(c->s_ps[buf], b->ps + (size_t)f0 * S, (size_t)n * S * sizeof(HeaacPsFrame),
                                        cudaMemcpyHostToDevice, c->s_in));
+        if (g->n_cce) CK(cudaMemcpyAsync(c->s_cce[buf], b->cce + (size_t)f0 * S * g->n_cce, (size_t)n * S * g->n_cce * sizeof(HeaacCce),
+                                         cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(c->ev_in[buf], c->s_in));
         /* kernels on the context stream: need the inputs, and the PCM staging set drained by the D2H two chunks back */
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[buf], 0));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->stream, c->ev_out[buf], 0));
         int r = heaac_launch_frames(c, n, c->s_coeffs[buf], c->s_ics[buf], b->tns ? c->s_tns[buf] : nullptr, c->s_sbr[buf], c->s_ps[buf],
-                              c->s_pcm[buf], b->pcm_f32 ? c->s_pcm_f32[buf] : nullptr);
+                              c->s_pcm[buf], b->pcm_f32 ? c->s_pcm_f32[buf] : nullptr, c->s_cce[buf]);
         if (r) return r;
         CK(cudaEventRecord(c->ev_done[buf], c->stream));
         /* D2H on s_out */
@@ -995,6 +1040,7 @@ extern "C" int heaac_b200_sizeof(const char *name)
     if (!strcmp(name, "HeaacSbrChan")) return (int)sizeof(HeaacSbrChan);
     if (!strcmp(name, "HeaacSbrElem")) return (int)sizeof(HeaacSbrElem);
     if (!strcmp(name, "HeaacPsFrame")) return (int)sizeof(HeaacPsFrame);
+    if (!strcmp(name, "HeaacCce")) return (int)sizeof(HeaacCce);
     if (!strcmp(name, "HeaacConfig")) return (int)sizeof(HeaacConfig);
     if (!strcmp(name, "HeaacBatch")) return (int)sizeof(HeaacBatch);
     if (!strcmp(name, "HeaacDecoderConfig")) return (int)sizeof(HeaacDecoderConfig);

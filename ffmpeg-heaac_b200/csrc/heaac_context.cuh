@@ -20,6 +20,8 @@ struct HeaacContext {
     float *d_tns_done;               /* TNS-filtered coefficient ranges (k_tns -> k_core / k_chain), frame-major like coeffs */
     size_t tns_done_frames;          /* frames d_tns_done holds: 1 for AAC-LC (per frame tick), the call's frames with SBR */
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
+    float *d_couple;                 /* [S][ncc][1024] decoded channels of one frame tick, planar (layouts with coupling channel elements) */
+    HeaacCce *s_cce[2];              /* staging, like s_ics */
     float *d_X;                      /* [S][nout][2][64][40]: X between k_chain, k_ps and k_synth (PS / downsampled SBR / keep_intermediates) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
     /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
@@ -41,11 +43,11 @@ struct HeaacContext {
     unsigned char *prof_kind;        /* HEAAC_K_* per recorded launch */
 };
 
-enum { HEAAC_K_CORE = 0, HEAAC_K_CHAIN = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };
+enum { HEAAC_K_CORE = 0, HEAAC_K_CHAIN = 1, HEAAC_K_PS = 2, HEAAC_K_SYNTH = 3, HEAAC_K_COUNT = 4 };     /* (k_couple is timed with k_core) */
 
 /* launches for frames [0, n) of a device-resident batch on c->stream (heaac_api.cu) */
 int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, const HeaacIcs *ics, const HeaacTns *tns,
-                        const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32);
+                        const HeaacSbrElem *sbr, const HeaacPsFrame *ps, int16_t *pcm, float *pcm_f32, const HeaacCce *cce = nullptr);
 int heaac_cuda_err(cudaError_t e, const char *what);
 #define CK(call) do { int _r = heaac_cuda_err((call), #call); if (_r) return _r; } while (0)
 

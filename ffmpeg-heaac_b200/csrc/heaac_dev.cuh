@@ -163,6 +163,8 @@ struct HeaacGeom {
     uint8_t elem_first_out[HEAAC_MAX_ELEMS]; /* element -> its first output channel */
     uint8_t elem_nout[HEAAC_MAX_ELEMS];      /* element -> number of output channels (2 with PS) */
     int max_elem_ch;
+    int n_cce;                               /* coupling channel elements: coded channels without an output channel */
+    uint8_t cce_ch[HEAAC_MAX_ELEMS];         /* their core channel indices, in element order */
 };
 
 #endif

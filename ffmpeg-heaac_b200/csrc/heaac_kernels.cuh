@@ -411,6 +411,36 @@ HEAAC_DEV void heaac_core_channel(HeaacCoreSmem *sm, float *c,
     HEAAC_SYNC();
 }
 
+/* ====================================================================================
+ * Independent channel coupling + the float -> s16 epilogue for layouts with coupling channel elements
+ * (apply_channel_coupling / apply_independent_coupling, aacdec.c:1849-1898): every output channel of one stream-frame.
+ *   f32  : this stream's decoded channels, planar [ncc][1024], bias included (what imdct_and_windowing leaves in ret)
+ *   cce  : this stream-frame's coupling side info, [n_cce]
+ * ================================================================================== */
+template <int NT>
+HEAAC_DEV void heaac_couple_stream(const HeaacGeom *g, const float *f32, const HeaacCce *HEAAC_RESTRICT cce,
+                                   int16_t *pcm, float *pcm_f32, int tid)
+{
+    constexpr int nt = NT;
+    const float bias = g->add_bias;
+    const int bias_mode = bias != 0.0f;
+    for (int i = tid; i < 1024; i += nt)
+        for (int c = 0; c < g->ncc; c++) {
+            const int slot = g->out_slot[c];
+            if (slot == 0xff) continue;                      /* a coupling channel itself: no output */
+            float v = f32[c * 1024 + i];
+            for (int k = 0; k < g->n_cce; k++) {
+                if (cce[k].coupling_point != 3) continue;
+                const float src = heaac_fsub(f32[g->cce_ch[k] * 1024 + i], bias);
+                const int nt_ = HEAAC_MIN((int)cce[k].n_targets, HEAAC_CCE_MAX_TARGETS);
+                for (int t = 0; t < nt_; t++)
+                    if (cce[k].target_ch[t] == c) v = heaac_fadd(v, heaac_fmul(cce[k].gain[t], src));
+            }
+            if (pcm)     pcm[(size_t)i * g->nout + slot] = heaac_to_s16(v, bias_mode);
+            if (pcm_f32) pcm_f32[(size_t)slot * 1024 + i] = v;
+        }
+}
+
 #include "heaac_sbr.cuh"
 
 /* ====================================================================================

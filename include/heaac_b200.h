@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HEAAC_ABI_VERSION 1
+#define HEAAC_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define HEAAC_OK            0
@@ -40,7 +40,7 @@ extern "C" {
 #define HEAAC_E_UNSUPPORTED (-38)  /* valid request this build does not cover      */
 
 /* ---- element / window enums (values identical to aac.h:46-71) ------------------- */
-enum { HEAAC_TYPE_SCE = 0, HEAAC_TYPE_CPE = 1, HEAAC_TYPE_LFE = 3 };
+enum { HEAAC_TYPE_SCE = 0, HEAAC_TYPE_CPE = 1, HEAAC_TYPE_CCE = 2, HEAAC_TYPE_LFE = 3 };
 enum { HEAAC_ONLY_LONG = 0, HEAAC_LONG_START = 1, HEAAC_EIGHT_SHORT = 2, HEAAC_LONG_STOP = 3 };
 
 #define HEAAC_MAX_ELEMS     8      /* channel elements per stream in one layout      */
@@ -149,6 +149,24 @@ typedef struct HeaacPsFrame {
     int8_t  opd_par[5][34];
 } HeaacPsFrame;
 
+/* ---- per-frame side info: channel coupling -------------------------------------------
+ * A coupling channel element (HEAAC_TYPE_CCE in cfg.elem_type) is one more coded channel of the stream -- it takes a
+ * coefficient / ICS / TNS slot like an SCE -- but has no output channel of its own: its decoded signal is ADDED to other
+ * channels.  This struct mirrors what decode_cce leaves in ChannelCoupling (aac.h:165-177, aacdec.c:1503-1565) for an
+ * INDEPENDENTLY SWITCHED element (coupling_point == AFTER_IMDCT), with the element / channel selection of
+ * apply_channel_coupling (aacdec.c:1870-1898) already resolved by the front end into a list of axpy operations
+ *     ret[target_ch[i]][n] += gain[i] * (ret[cce][n] - add_bias)        (apply_independent_coupling, aacdec.c:1849-1862)
+ * applied in list order, CCEs in the order of their instance tags.  Dependent coupling (in the spectral domain, before or
+ * after TNS) is not part of this ABI: a front end meeting it reports HEAAC_E_UNSUPPORTED. */
+#define HEAAC_CCE_MAX_TARGETS 16
+typedef struct HeaacCce {
+    uint8_t coupling_point;         /* coup.coupling_point: must be 3 (AFTER_IMDCT); anything else = the element is ignored */
+    uint8_t n_targets;              /* axpy operations of this frame                  */
+    uint8_t reserved[2];
+    uint8_t target_ch[HEAAC_CCE_MAX_TARGETS];   /* core channel index (cfg.elem_type order) */
+    float   gain[HEAAC_CCE_MAX_TARGETS];        /* coup.gain[index][0]                      */
+} HeaacCce;
+
 /* ---- context configuration ---------------------------------------------------------
  * A context decodes `n_streams` independent streams that share one channel layout
  * (the BASELINE configs: stereo CPE, mono SCE + PS, 5.1 = SCE CPE CPE LFE, ...).
@@ -189,6 +207,7 @@ typedef struct HeaacConfig {
  *   ps     [n_frames][n_streams]                    (NULL unless cfg.ps)
  *   pcm    [n_frames][n_streams][frame_out_len][n_out_ch]  int16, interleaved
  *   pcm_f32[n_frames][n_streams][n_out_ch][frame_out_len]  float, planar (optional)
+ *   cce    [n_frames][n_streams][n_cce]             (NULL unless the layout has coupling channel elements)
  * frame_out_len = 1024 (no SBR) or 2048 (SBR).  n_out_ch = n_core_ch, or 2 for ps.
  * `on_device` != 0 means every pointer is a CUDA device pointer on cfg.device (no copies);
  * otherwise they are host pointers and the call copies H2D / D2H itself. */
@@ -202,6 +221,7 @@ typedef struct HeaacBatch {
     const HeaacPsFrame *ps;
     int16_t            *pcm;
     float              *pcm_f32;
+    const struct HeaacCce *cce;     /* [n_frames][n_streams][n_cce elements] (NULL unless cfg.elem_type has HEAAC_TYPE_CCE) */
 } HeaacBatch;
 
 typedef struct HeaacContext HeaacContext;

@@ -65,10 +65,10 @@ class Oracle:
         et = [cfg.elem_type[i] for i in range(cfg.n_elems)]
         self.ncc = abi.n_core_channels(et)
         self.nse = abi.n_sbr_elems(et)
-        self.nout = 2 if cfg.ps else self.ncc
+        self.nout = 2 if cfg.ps else self.ncc - sum(1 for t in et if t == abi.TYPE_CCE)
         self.out_len = 2048 if cfg.sbr and not cfg.sbr_downsampled else 1024
 
-    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, n_threads=1, want_float=True):
+    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, n_threads=1, want_float=True, cce=None):
         """coeffs [T,S,ncc,1024] f32; ics [T,S,ncc]; tns [T,S,ncc]; sbr [T,S,nse]; ps [T,S].
         Returns (pcm int16 [T,S,out_len,nout], pcm_f32 [T,S,nout,out_len])."""
         S = self.cfg.n_streams
@@ -80,7 +80,7 @@ class Oracle:
         b.n_frames = T
         b.coeffs = coeffs.ctypes.data
         b.ics = ics.ctypes.data
-        for name, arr, dt in (("tns", tns, abi.TNS), ("sbr", sbr, abi.SBR_ELEM), ("ps", ps, abi.PS_FRAME)):
+        for name, arr, dt in (("tns", tns, abi.TNS), ("sbr", sbr, abi.SBR_ELEM), ("ps", ps, abi.PS_FRAME), ("cce", cce, abi.CCE)):
             if arr is not None:
                 a = np.ascontiguousarray(arr, dt)
                 keep.append(a)

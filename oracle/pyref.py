@@ -154,6 +154,11 @@ class Decoder:
             r["tns"] = np.zeros(self.ncc, abi.TNS)
             r["sbr"] = np.zeros(max(self.nse, 1), abi.SBR_ELEM)
             r["ps"] = np.zeros(1, abi.PS_FRAME)
+            n_cce = sum(1 for x in self.elem_types if x == abi.TYPE_CCE)
+            if n_cce:
+                r["cce"] = np.zeros(n_cce, abi.CCE)
+                lib().ref_dec_set_capture_cce.argtypes = [C.c_void_p, C.c_void_p]
+                lib().ref_dec_set_capture_cce(self.h, _ptr(r["cce"]))
         f32 = np.zeros(8 * 2048, np.float32)
         lib().ref_dec_set_capture(self.h, _ptr(r.get("coeffs")), _ptr(r.get("ics")), _ptr(r.get("tns")),
                                   _ptr(r.get("sbr")), _ptr(r.get("ps")), _ptr(f32), f32.size)

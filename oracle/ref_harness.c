@@ -65,6 +65,7 @@ typedef struct RefDec {
     HeaacTns     *cap_tns;
     HeaacSbrElem *cap_sbr;
     HeaacPsFrame *cap_ps;
+    HeaacCce     *cap_cce;       /* one per TYPE_CCE element of the layout, in layout order */
     float        *cap_pcm_f32;   /* planar [ch][samples] */
     int           cap_pcm_f32_cap;
     int           last_samples;
@@ -181,6 +182,36 @@ static void pack_ps(HeaacPsFrame *o, const PSContext *p)
     memcpy(o->opd_par, p->opd_par, sizeof(o->opd_par));
 }
 
+/* ChannelCoupling (aac.h:165-177) of every TYPE_CCE element of the layout -> HeaacCce: the (type, id_select, ch_select) entries
+ * of apply_channel_coupling (aacdec.c:1870-1898) resolved into (core channel, gain) pairs -- the front-end half of the coupling
+ * boundary (include/heaac_b200.h).  Core channels count in layout order. */
+static void pack_cce_all(RefDec *d, AACContext *ac, HeaacCce *out)
+{
+    int first_ch[REF_MAX_ELEMS], ch = 0, k = 0;
+    for (int e = 0; e < d->n_elems; e++) { first_ch[e] = ch; ch += d->elem_type[e] == TYPE_CPE ? 2 : 1; }
+    for (int e = 0; e < d->n_elems; e++) {
+        if (d->elem_type[e] != TYPE_CCE) continue;
+        HeaacCce *o = out + k++;
+        ChannelElement *cce = ac->che[TYPE_CCE][d->elem_id[e]];
+        memset(o, 0, sizeof(*o));
+        if (!cce) continue;
+        const ChannelCoupling *coup = &cce->coup;
+        o->coupling_point = coup->coupling_point;
+        int index = 0, n = 0;
+        for (int c = 0; c <= coup->num_coupled; c++) {
+            int sel = coup->ch_select[c], te = -1;
+            for (int t = 0; t < d->n_elems; t++)
+                if (d->elem_type[t] == (int)coup->type[c] && d->elem_id[t] == coup->id_select[c]) te = t;
+            if (te >= 0) {
+                if (sel != 1 && n < HEAAC_CCE_MAX_TARGETS) { o->target_ch[n] = first_ch[te];     o->gain[n++] = coup->gain[index][0]; }
+                if (sel != 2 && n < HEAAC_CCE_MAX_TARGETS) { o->target_ch[n] = first_ch[te] + 1; o->gain[n++] = coup->gain[index + (sel == 3)][0]; }
+            }
+            index += 1 + (sel == 3);
+        }
+        o->n_targets = n;
+    }
+}
+
 /* ---- drop-in mode: the product library in place of spectral_to_sample, inside this process ------------------- */
 static struct {
     void *lib;
@@ -235,10 +266,15 @@ static int dropin_frame(RefDec *d, AACContext *ac)
             se++;
         }
     }
+    HeaacCce cce[REF_MAX_ELEMS];
+    int n_cce = 0;
+    for (int e = 0; e < d->n_elems; e++) n_cce += d->elem_type[e] == TYPE_CCE;
+    if (n_cce) pack_cce_all(d, ac, cce);
     HeaacBatch b;
     memset(&b, 0, sizeof(b));
     b.n_frames = 1; b.coeffs = coeffs; b.ics = ics; b.tns = tns;
     b.sbr = want_sbr ? sbr : NULL; b.ps = want_ps ? &ps : NULL; b.pcm_f32 = pcm;
+    b.cce = n_cce ? cce : NULL;
     if (g_be.synth(d->be, &b)) return 0;
     /* planar float PCM [out channel][len] -> the elements' ret buffers (with PS the SCE's second channel is R) */
     const int len = (want_sbr && !want_ds) ? 2048 : 1024;
@@ -246,6 +282,7 @@ static int dropin_frame(RefDec *d, AACContext *ac)
     for (int e = 0; e < d->n_elems; e++) {
         ChannelElement *che = ac->che[d->elem_type[e]][d->elem_id[e]];
         int nout = want_ps ? 2 : (d->elem_type[e] == TYPE_CPE ? 2 : 1);
+        if (d->elem_type[e] == TYPE_CCE) continue;          /* no output channel of its own (its signal is inside the targets now) */
         for (int c = 0; c < nout; c++, ch++)
             memcpy(che->ch[c].ret, pcm + (size_t)ch * len, len * sizeof(float));
     }
@@ -293,6 +330,7 @@ int heaac_ref_pre_hook(AACContext *ac)
             se++;
         }
     }
+    if (d->cap_cce) pack_cce_all(d, ac, d->cap_cce);
     return d->dropin ? dropin_frame(d, ac) : 0;
 }
 
@@ -345,6 +383,8 @@ void ref_dec_close(RefDec *d)
     av_free(d->avctx.extradata);
     av_free(d);
 }
+
+void ref_dec_set_capture_cce(RefDec *d, HeaacCce *cce) { d->cap_cce = cce; }
 
 void ref_dec_set_capture(RefDec *d, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                          HeaacSbrElem *sbr, HeaacPsFrame *ps, float *pcm_f32, int pcm_f32_cap)

@@ -23,6 +23,7 @@ struct EmuCtx {
     float *W, *X;
     HeaacCoreSmem *sm_core; HeaacPsSmem *sm_ps; HeaacSynthSmem *sm_synth;
     HeaacChainSmem *sm_chain;                        /* the fused chain's "shared memory" */
+    float *couple;                                   /* [S][ncc][1024]: k_core -> k_couple */
 };
 
 static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
@@ -40,12 +41,22 @@ static void build_geom(const HeaacConfig *cfg, HeaacGeom *g)
         }
         if (cfg->elem_type[e] != HEAAC_TYPE_LFE) se++;
     }
-    g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch; g->ds = cfg->sbr && cfg->sbr_downsampled; g->out_len = cfg->sbr && !g->ds ? 2048 : 1024;
+    for (int e = 0, c0 = 0; e < cfg->n_elems; c0 += cfg->elem_type[e] == HEAAC_TYPE_CPE ? 2 : 1, e++)
+        if (cfg->elem_type[e] == HEAAC_TYPE_CCE) g->cce_ch[g->n_cce++] = (uint8_t)c0;
+    g->ncc = ch; g->nse = se; g->nout = cfg->ps ? 2 : ch - g->n_cce; g->ds = cfg->sbr && cfg->sbr_downsampled; g->out_len = cfg->sbr && !g->ds ? 2048 : 1024;
     g->sr_index = cfg->sr_index; g->sbr = cfg->sbr != 0; g->ps = cfg->ps != 0;
     g->add_bias = cfg->add_bias; g->sf_scale = cfg->sf_scale;
     int any = 0;
     for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) any |= cfg->out_slot[i];
     for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) g->out_slot[i] = (any && !cfg->ps) ? cfg->out_slot[i] : (uint8_t)i;
+    if (g->n_cce) {
+        int o = 0;
+        for (int i = 0; i < ch; i++) {
+            const bool is_cce = cfg->elem_type[g->ch_elem[i]] == HEAAC_TYPE_CCE;
+            g->out_slot[i] = is_cce ? 0xff : (any ? cfg->out_slot[i] : (uint8_t)o);
+            o += !is_cce;
+        }
+    }
 }
 
 extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
@@ -64,6 +75,7 @@ extern "C" EmuCtx *heaac_emu_create(const HeaacConfig *cfg)
     c->sm_ps = (HeaacPsSmem *)calloc(1, sizeof(HeaacPsSmem));
     c->sm_synth = (HeaacSynthSmem *)calloc(1, sizeof(HeaacSynthSmem));
     c->sm_chain = (HeaacChainSmem *)calloc(1, sizeof(HeaacChainSmem));
+    c->couple = (float *)calloc(S * c->g.ncc * 1024, sizeof(float));
     return c;
 }
 
@@ -71,7 +83,7 @@ extern "C" void heaac_emu_destroy(EmuCtx *c)
 {
     if (!c) return;
     free(c->T); free(c->chan); free(c->synth); free(c->ps); free(c->W); free(c->X);
-    free(c->sm_core); free(c->sm_ps); free(c->sm_synth); free(c->sm_chain); free(c);
+    free(c->sm_core); free(c->sm_ps); free(c->sm_synth); free(c->sm_chain); free(c->couple); free(c);
 }
 
 /* one coded channel through the fused chain (what one CTA of k_chain does), frames [f0, f0 + n) of the batch */
@@ -132,11 +144,19 @@ extern "C" int heaac_emu_synth(EmuCtx *c, const HeaacBatch *b)
             memcpy(cbuf, co + gc * 1024, sizeof(cbuf));           /* the kernel stages the coefficients with cp.async */
             heaac_core_channel<1>(c->sm_core, cbuf, ic + gc, tn ? tn + gc : nullptr, nullptr, st, out, g.add_bias,
                                g.sr_index, c->T, 0);
+            if (g.n_cce) {                                        /* planar, one slot per coded channel: k_couple finishes */
+                memcpy(c->couple + gc * 1024, out, sizeof(out));
+                continue;
+            }
             for (int i = 0; i < 1024; i++) {
                 if (pc) pc[(s * 1024 + i) * g.nout + g.out_slot[ch]] = heaac_to_s16(out[i], g.add_bias != 0.0f);
                 if (pf) pf[(s * g.nout + g.out_slot[ch]) * 1024 + i] = out[i];
             }
         }
+        if (g.n_cce)
+            for (size_t s = 0; s < S; s++)                        /* k_couple */
+                heaac_couple_stream<1>(&g, c->couple + s * g.ncc * 1024, b->cce + ((size_t)f * S + s) * g.n_cce,
+                                       pc ? pc + s * 1024 * g.nout : nullptr, pf ? pf + s * g.nout * 1024 : nullptr, 0);
         if (!g.sbr) continue;
         if (g.ps)
             for (size_t s = 0; s < S; s++) {                      /* k_ps */

@@ -44,18 +44,18 @@ class Emu:
         self.h = lib().heaac_emu_create(C.byref(cfg))
         et = [cfg.elem_type[i] for i in range(cfg.n_elems)]
         self.ncc = abi.n_core_channels(et)
-        self.nout = 2 if cfg.ps else self.ncc
+        self.nout = 2 if cfg.ps else self.ncc - sum(1 for t in et if t == abi.TYPE_CCE)
         self.out_len = 2048 if cfg.sbr and not cfg.sbr_downsampled else 1024
         self.S = cfg.n_streams
 
-    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=True):
+    def synth(self, coeffs, ics, tns=None, sbr=None, ps=None, want_float=True, cce=None):
         coeffs = np.ascontiguousarray(coeffs, np.float32)
         T = coeffs.size // (self.S * self.ncc * 1024)
         keep = [coeffs, np.ascontiguousarray(ics, abi.ICS)]
         b = abi.Batch()
         b.n_frames = T
         b.coeffs, b.ics = keep[0].ctypes.data, keep[1].ctypes.data
-        for name, arr, dt in (("tns", tns, abi.TNS), ("sbr", sbr, abi.SBR_ELEM), ("ps", ps, abi.PS_FRAME)):
+        for name, arr, dt in (("tns", tns, abi.TNS), ("sbr", sbr, abi.SBR_ELEM), ("ps", ps, abi.PS_FRAME), ("cce", cce, abi.CCE)):
             if arr is not None:
                 a = np.ascontiguousarray(arr, dt)
                 keep.append(a)

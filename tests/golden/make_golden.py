@@ -55,6 +55,34 @@ def capture(pkts, ed, rate, channels, layout):
     return out
 
 
+def cce_stream(seed, n_frames):
+    """AAC-LC 48 kHz with a program_config_element: SCE + CPE and two independently switched coupling channel elements
+    (tests/lc_writer.py).  Returns (packets, extradata, (element types, element ids) in the reference's element order)."""
+    et = [abi.TYPE_SCE, abi.TYPE_CPE, abi.TYPE_CCE, abi.TYPE_CCE]
+    ed, ids, order = lc_writer.pce_config(3, et)
+    w = lc_writer.LcWriter(seed, 3, et, tns_prob=0.4, short_bias=0.3)
+    # CCE 0 -> the SCE and both channels of the CPE with separate gains; CCE 1 -> both CPE channels with one gain
+    w.set_coupling({2: [(0, 2), (1, 3)], 3: [(1, 0)]})
+    pk = [w.frame() for _ in range(n_frames)]
+    return pk, ed, ([et[e] for e in order], [ids[e] for e in order])
+
+
+def make_cce_golden():
+    """Independent channel coupling (apply_independent_coupling, aacdec.c:1849-1862): boundary-level golden -- what the
+    reference's parsers hand over (incl. the resolved coupling lists, oracle/ref_harness.c pack_cce_all) and its PCM."""
+    pk, ed, lay = cce_stream(4242, 10)
+    df = pyref.Decoder(ed, 48000, 3, lay, float_mode=True)
+    fr = [df.decode(p) for p in pk]
+    df.close()
+    out = {k: np.stack([f[k] for f in fr]) for k in ("coeffs", "ics", "tns", "cce", "pcm_f32")}
+    out["pcm_s16"] = np.stack([f["pcm"] for f in fr])
+    out["elem_types"] = np.asarray(lay[0], np.int32)
+    out["sr_index"] = np.int32(3)
+    path = os.path.join(HERE, "lc_cce.npz")
+    np.savez_compressed(path, **out)
+    print("lc_cce", out["coeffs"].shape, out["pcm_f32"].shape, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
 def main():
     cases = {
         "lc_stereo_44k": lc_stream(1234, 10, 2, 44100, "stereo"),
@@ -74,6 +102,8 @@ def main():
     pkts, ed, info = hs.make_stream_51(51, 8)
     cases["heaac_v1_51"] = (pkts, ed, 24000, 6, "5.1")
     only = sys.argv[1:]
+    if not only or "lc_cce" in only:
+        make_cce_golden()
     for name, c in cases.items():
         if only and name not in only:
             continue

@@ -288,6 +288,41 @@ class LcWriter:
         self.stats["short"] += info["ws"] == EIGHT_SHORT
         return info
 
+    # ---- coupling channel element (ISO/IEC 14496-3 table 4.8; decode_cce, aacdec.c:1503-1565), independently switched ----
+    def set_coupling(self, targets):
+        """targets: {element index of a CCE: [(target element index, ch_select), ...]} with ch_select as in the bitstream
+        (CPE targets: 0 = both channels with one gain, 1 = right only, 2 = left only, 3 = both with separate gains)."""
+        self.coupling = targets
+        self.cce_gain_lists = {}
+
+    def _cce_head(self, bw, ei):
+        r = self.rng
+        tg = self.coupling[ei]
+        tags = {}
+        elem_tag = []
+        for t in self.elem_types:
+            elem_tag.append(tags.get(t, 0)); tags[t] = tags.get(t, 0) + 1
+        bw.put(1, 1)                                    # ind_sw_cce_flag
+        bw.put(len(tg) - 1, 3)                          # num_coupled_elements
+        lists = 0
+        for te, sel in tg:
+            is_cpe = self.elem_types[te] == abi.TYPE_CPE
+            bw.put(int(is_cpe), 1); bw.put(elem_tag[te], 4)
+            lists += 1
+            if is_cpe:
+                bw.put(sel, 2)
+                lists += sel == 3
+        bw.put(int(r.integers(0, 2)), 1)                # cc_domain (irrelevant once independently switched)
+        bw.put(int(r.integers(0, 2)), 1)                # gain_element_sign
+        bw.put(int(r.integers(0, 4)), 2)                # gain_element_scale
+        self.cce_gain_lists[ei] = lists
+
+    def _cce_gains(self, bw, ei):
+        code, bits = _T["sf_code"], _T["sf_bits"]
+        for _ in range(1, self.cce_gain_lists[ei]):     # the first list has gain 1; the others one common gain element each
+            d = int(self.rng.integers(-6, 7))
+            bw.put(int(code[d + 60]), int(bits[d + 60]))
+
     def frame(self, fil=None):
         """One raw_data_block.  fil: {element index: BitWriter with an sbr_extension_data() payload} -- a FIL element
         (EXT_SBR_DATA) is written right behind that element, where the reference attaches it to the element before it
@@ -316,6 +351,11 @@ class LcWriter:
                 self._ics(bw, a, shared, False)
                 self._ics(bw, b, shared, self.intensity)
                 ch += 2
+            elif t == abi.TYPE_CCE:
+                self._cce_head(bw, ei)
+                self._ics(bw, self.ch[ch], None, False)
+                self._cce_gains(bw, ei)
+                ch += 1
             else:
                 self._ics(bw, self.ch[ch], None, False)
                 ch += 1
@@ -337,6 +377,36 @@ class LcWriter:
 
 
 CHAN_CONFIG = {"mono": 1, "stereo": 2, "5.1": 6}
+
+
+def pce_config(sr_index, elem_types):
+    """AudioSpecificConfig with channel_configuration 0 and a program_config_element (ISO/IEC 14496-3 table 4.2; decode_pce,
+    aacdec.c:280-340) listing the elements: SCE / CPE as front channels, LFE, CCE as (independently switched) coupling
+    channels.  Returns (extradata, elem_ids, order): the reference orders its elements -- and its output channels -- by
+    instance tag, then type (output_configure, aacdec.c:245-262); `order` lists the element indices that way."""
+    bw = BitWriter()
+    bw.put(2, 5); bw.put(sr_index, 4); bw.put(0, 4)           # AOT 2, rate, channel_configuration 0
+    bw.put(0, 3)                                             # frame_length_flag, depends_on_core_coder, extension_flag
+    tags, ids = {}, []
+    for t in elem_types:
+        ids.append(tags.get(t, 0)); tags[t] = tags.get(t, 0) + 1
+    front = [(t, i) for t, i in zip(elem_types, ids) if t in (abi.TYPE_SCE, abi.TYPE_CPE)]
+    lfe = [i for t, i in zip(elem_types, ids) if t == abi.TYPE_LFE]
+    cc = [i for t, i in zip(elem_types, ids) if t == abi.TYPE_CCE]
+    bw.put(0, 4)                                             # element_instance_tag
+    bw.put(1, 2); bw.put(sr_index, 4)                        # object_type (LC), sampling_frequency_index
+    bw.put(len(front), 4); bw.put(0, 4); bw.put(0, 4); bw.put(len(lfe), 2); bw.put(0, 3); bw.put(len(cc), 4)
+    bw.put(0, 1); bw.put(0, 1); bw.put(0, 1)                 # no mixdown elements
+    for t, i in front:
+        bw.put(int(t == abi.TYPE_CPE), 1); bw.put(i, 4)
+    for i in lfe:
+        bw.put(i, 4)
+    for i in cc:
+        bw.put(1, 1); bw.put(i, 4)                           # cc_element_is_ind_sw, tag
+    bw.put(0, (-len(bw)) % 8)                                # byte_alignment
+    bw.put(0, 8)                                             # comment_field_bytes
+    order = sorted(range(len(elem_types)), key=lambda e: (ids[e], elem_types[e]))
+    return bw.tobytes(), ids, order
 
 
 def make_lc_stream(seed, n_frames, layout="5.1", sr_index=3, **kw):

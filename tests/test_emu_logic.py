@@ -49,3 +49,20 @@ def test_frame_by_frame_equals_batched_call(name):
         p2, f2 = e2.synth(a["coeffs"][t:t + 1], a["ics"][t:t + 1], None, a["sbr"][t:t + 1], a["ps"][t:t + 1] if a["ps"] is not None else None)
         assert np.array_equal(f2[0], f1[t])
     e1.close(); e2.close()
+
+
+def test_emulated_coupling_equals_oracle():
+    """k_couple's routine (independent channel coupling + s16 epilogue) against the oracle on the coupling golden, both scalings."""
+    from test_oracle_vs_ref import _cce_golden
+    from common import abi
+    d = _cce_golden()
+    et = [int(x) for x in d["elem_types"]]
+    for bias_mode in (False, True):
+        cfg = abi.make_config(2, et, int(d["sr_index"]), max_frames=d["coeffs"].shape[0], out_slots=None, bias_mode=bias_mode)
+        rep = lambda a: np.ascontiguousarray(np.repeat(a[:, None], 2, axis=1))
+        co = rep(d["coeffs"]) * (np.float32(1.0 / 32768.0) if bias_mode else np.float32(1.0))
+        orc, emu = pyoracle.Oracle(cfg), pyemu.Emu(cfg)
+        op, of = orc.synth(co, rep(d["ics"]), rep(d["tns"]), None, None, cce=rep(d["cce"]))
+        ep, ef = emu.synth(co, rep(d["ics"]), rep(d["tns"]), None, None, cce=rep(d["cce"]))
+        orc.close(); emu.close()
+        assert np.array_equal(ef, of) and np.array_equal(ep, op)

@@ -324,3 +324,62 @@ def test_live_dropin_inside_the_reference_decoder(name):
         dec.close()
         print("%s drop-in (%s path): max float err %.3g FS, max s16 diff %d LSB" % (name, "SIMD-scaling" if float_mode else "C bias", worst_f, worst_s))
         assert worst_s <= 1 and worst_f <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bias_mode", [False, True])
+def test_channel_coupling_matches_oracle_and_reference(bias_mode):
+    """Independent channel coupling (k_couple; apply_independent_coupling, aacdec.c:1849-1898) on the reference-generated
+    golden: bit-exact against the oracle in both scalings, within tolerance of the reference's own PCM, batched."""
+    import ffmpeg_heaac_b200 as hb
+    from test_oracle_vs_ref import _cce_golden
+    d = _cce_golden()
+    et = [int(x) for x in d["elem_types"]]
+    S = 5
+    cfg = abi.make_config(S, et, int(d["sr_index"]), max_frames=d["coeffs"].shape[0], out_slots=None, bias_mode=bias_mode)
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[:, None], S, axis=1))
+    co = rep(d["coeffs"]) * (np.float32(1.0 / 32768.0) if bias_mode else np.float32(1.0))
+    ctx = hb.Context(cfg)
+    pcm, f32 = ctx.synth(co, rep(d["ics"]), rep(d["tns"]), None, None, want_float=True, cce=rep(d["cce"]))
+    assert ctx.nout == 3 and ctx.ncc == 5
+    ctx.close()
+    orc = pyoracle.Oracle(cfg)
+    opcm, of32 = orc.synth(co, rep(d["ics"]), rep(d["tns"]), None, None, cce=rep(d["cce"]))
+    orc.close()
+    assert np.array_equal(pcm, opcm) and np.array_equal(f32, of32)
+    if not bias_mode:
+        scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
+        for s in range(S):
+            assert float(np.abs(f32[:, s].astype(np.float64) - d["pcm_f32"]).max()) / scale <= 1e-5
+            assert int(np.abs(pcm[:, s].astype(np.int32) - d["pcm_s16"]).max()) <= 1
+
+
+@pytest.mark.gpu
+def test_live_dropin_with_channel_coupling():
+    """The drop-in run (reference front end, this back end, one process) on a program_config_element stream with coupling
+    channel elements: the front end's ChannelCoupling is resolved by the harness binding and applied by k_couple."""
+    import sys
+    import pyref
+    import ffmpeg_heaac_b200 as hb
+    from common import GOLDEN
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    from test_oracle_vs_ref import _cce_golden
+    d = _cce_golden()
+    # the golden holds no packets: regenerate the stream the golden was made from (pure Python, deterministic)
+    sys.path.insert(0, GOLDEN)
+    import lc_writer
+    et = [abi.TYPE_SCE, abi.TYPE_CPE, abi.TYPE_CCE, abi.TYPE_CCE]
+    ed, ids, order = lc_writer.pce_config(3, et)
+    w = lc_writer.LcWriter(4242, 3, et, tns_prob=0.4, short_bias=0.3)
+    w.set_coupling({2: [(0, 2), (1, 3)], 3: [(1, 0)]})
+    pk = [w.frame() for _ in range(d["coeffs"].shape[0])]
+    dec = pyref.Decoder(ed, 48000, 3, ([et[e] for e in order], [ids[e] for e in order]), float_mode=True)
+    dec.enable_dropin(hb.LIB_PATH)
+    scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
+    for t, p in enumerate(pk):
+        r = dec.decode(p, capture=False)
+        assert int(np.abs(r["pcm"].astype(np.int32) - d["pcm_s16"][t]).max()) <= 1
+        assert float(np.abs(r["pcm_f32"].astype(np.float64) - d["pcm_f32"][t]).max()) / scale <= 1e-5
+    assert dec.dropin_frames() == len(pk)
+    dec.close()

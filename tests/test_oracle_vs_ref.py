@@ -141,3 +141,61 @@ def test_reference_output_channel_order():
     orc.close()
     for c in range(6):
         assert np.abs(f32[:, 0, c] - d["pcm_f32"][:, c]).max() / 32768.0 <= 1e-5, "channel %d" % c
+
+
+def _cce_golden():
+    import os
+    from common import GOLDEN
+    d = dict(np.load(os.path.join(GOLDEN, "lc_cce.npz")))
+    d["ics"] = d["ics"].view(abi.ICS).reshape(d["coeffs"].shape[:2]) if d["ics"].dtype != abi.ICS else d["ics"]
+    return d
+
+
+def test_oracle_reproduces_the_channel_coupling_golden():
+    """Independent channel coupling (apply_channel_coupling + apply_independent_coupling, aacdec.c:1849-1898) on the
+    reference-generated golden: SCE + CPE + two coupling channel elements, program_config_element layout."""
+    d = _cce_golden()
+    et = [int(x) for x in d["elem_types"]]
+    assert et.count(abi.TYPE_CCE) == 2 and int(d["cce"]["n_targets"].max()) == 3
+    cfg = abi.make_config(1, et, int(d["sr_index"]), max_frames=d["coeffs"].shape[0], out_slots=None)
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(d["coeffs"][:, None], d["ics"][:, None], d["tns"][:, None], None, None, cce=d["cce"][:, None])
+    orc.close()
+    scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
+    assert float(np.abs(f32[:, 0].astype(np.float64) - d["pcm_f32"]).max()) / scale <= 1e-5
+    assert int(np.abs(pcm[:, 0].astype(np.int32) - d["pcm_s16"]).max()) <= 1
+    # the coupling really contributes: without it the PCM is far off
+    z = d["cce"].copy(); z["n_targets"] = 0
+    orc = pyoracle.Oracle(cfg)
+    pcm0, _ = orc.synth(d["coeffs"][:, None], d["ics"][:, None], d["tns"][:, None], None, None, cce=z[:, None])
+    orc.close()
+    assert int(np.abs(pcm0[:, 0].astype(np.int32) - d["pcm_s16"]).max()) > 100
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [3, 8])
+def test_oracle_matches_reference_on_fresh_coupled_streams(seed):
+    import pyref
+    sys_path_golden()
+    import make_golden
+    pk, ed, lay = make_golden.cce_stream(seed, 16)
+    dec = pyref.Decoder(ed, 48000, 3, lay, float_mode=True)
+    fr = [dec.decode(p) for p in pk]
+    dec.close()
+    cfg = abi.make_config(1, lay[0], 3, max_frames=len(fr), out_slots=None)
+    st = lambda k: np.stack([f[k] for f in fr])[:, None]
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), None, None, cce=st("cce"))
+    orc.close()
+    ref_f32 = np.stack([f["pcm_f32"] for f in fr])
+    scale = max(32768.0, float(np.abs(ref_f32).max()))
+    assert float(np.abs(f32[:, 0].astype(np.float64) - ref_f32).max()) / scale <= 1e-5
+    assert int(np.abs(pcm[:, 0].astype(np.int32) - np.stack([f["pcm"] for f in fr])).max()) <= 1
+
+
+def sys_path_golden():
+    import os
+    import sys
+    from common import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
