@@ -347,12 +347,13 @@ class Decoder:
     reference's aac_decode_init / aac_decode_frame / aac_decode_close for n_streams streams."""
 
     def __init__(self, n_streams, extradata=b"", sample_rate=0, channels=0, max_frames=32, n_threads=0, device=0,
-                 want_float=False, gpu_parse=False):
+                 want_float=False, gpu_parse=False, chunk_frames=0):
         self._ed = np.frombuffer(extradata, np.uint8).copy() if extradata else np.zeros(0, np.uint8)
         cfg = abi.DecoderConfig()
         cfg.abi_version, cfg.device, cfg.n_streams = abi.ABI_VERSION, device, n_streams
         cfg.sample_rate, cfg.channels, cfg.max_frames_per_call = sample_rate, channels, max_frames
         cfg.n_threads, cfg.want_float_out, cfg.gpu_parse = n_threads, int(bool(want_float)), int(bool(gpu_parse))
+        cfg.chunk_frames = int(chunk_frames)
         cfg.extradata, cfg.extradata_size = (self._ed.ctypes.data if self._ed.size else None), self._ed.size
         h = C.c_void_p()
         _check(lib().heaac_dec_open(C.byref(cfg), C.byref(h)), "heaac_dec_open")

@@ -84,6 +84,7 @@ class DecoderConfig(C.Structure):
         ("abi_version", C.c_uint32), ("device", C.c_int32), ("n_streams", C.c_int32), ("sample_rate", C.c_int32),
         ("channels", C.c_int32), ("max_frames_per_call", C.c_int32), ("n_threads", C.c_int32),
         ("want_float_out", C.c_int32), ("extradata", C.c_void_p), ("extradata_size", C.c_int32), ("gpu_parse", C.c_int32),
+        ("chunk_frames", C.c_int32),
     ]
 
 

@@ -183,7 +183,8 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     cfg.max_frames_per_call = d->cfg.max_frames_per_call;
     cfg.want_float_out = d->cfg.want_float_out;
     /* the device parser spreads a chunk's frames over the lanes of a warp: longer chunks, more lanes at work */
-    if (d->cfg.gpu_parse && d->cfg.max_frames_per_call >= 32) cfg.chunk_frames = 16;
+    if (d->cfg.gpu_parse && d->cfg.max_frames_per_call >= 32) cfg.chunk_frames = d->cfg.max_frames_per_call >= 64 ? 32 : 16;
+    if (d->cfg.chunk_frames > 0) cfg.chunk_frames = d->cfg.chunk_frames;
     heaac_b200_reference_out_slots(cfg.elem_type, cfg.n_elems, cfg.out_slot);
     if ((r = heaac_b200_create(&cfg, &d->be))) return r;
 

@@ -372,6 +372,7 @@ typedef struct HeaacDecoderConfig {
     const uint8_t *extradata;       /* AudioSpecificConfig, or NULL for ADTS input */
     int32_t  extradata_size;
     int32_t  gpu_parse;             /* 1: entropy decoding on the GPU too (heaac_b200_parser_*): only packets cross PCIe */
+    int32_t  chunk_frames;          /* frames per pipeline chunk (parse | copy | synthesise overlap chunk-wise); 0 = automatic */
 } HeaacDecoderConfig;
 int  heaac_dec_open(const HeaacDecoderConfig *cfg, HeaacDecoder **dec);
 void heaac_dec_close(HeaacDecoder *dec);
