@@ -661,59 +661,71 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     for (int k = tid; k < nr_bands; k += nt) {            /* one hybrid band per work item, serial in time */
         const int b = k_to_i[k];
         const int cleared = switched || k >= top;         /* aacps.c:980-983 + 665-671 */
-        float hist[14][2];
-        for (int j = 0; j < 14; j++) {
-            hist[j][0] = cleared ? 0.0f : st->delay[k][j][0];
-            hist[j][1] = cleared ? 0.0f : st->delay[k][j][1];
-        }
+        const float *pw = sm->power[b];
+        const float (*Lk)[2] = sm->L[k];
+        float (*Rk)[2] = sm->R[k];
         if (k < nr_ap) {
             float g = 1.f - 0.05f * (k - decay_cutoff);
             g = g < 0.f ? 0.f : (g > 1.f ? 1.f : g);
-            const float a_[3] = { 0.65143905753106f, 0.56471812200776f, 0.48954165955695f };
-            float ag[3], ap[3][5][2];
+            /* everything the recursion carries lives in registers: the three links' last five outputs (ap[m][4] newest), their
+             * coefficients, and the two input samples the 2-slot delay still needs from the previous frame (delay[k][12..13]) */
+            const float ag0 = 0.65143905753106f * g, ag1 = 0.56471812200776f * g, ag2 = 0.48954165955695f * g;
+            float ap[3][5][2];
+            HEAAC_UNROLL
             for (int m = 0; m < 3; m++) {
-                ag[m] = a_[m] * g;
+                HEAAC_UNROLL
                 for (int j = 0; j < 5; j++) {
                     ap[m][j][0] = cleared ? 0.0f : st->ap_delay[k][m][j][0];
                     ap[m][j][1] = cleared ? 0.0f : st->ap_delay[k][m][j][1];
                 }
             }
+            float fd[3][2];
+            HEAAC_UNROLL
+            for (int m = 0; m < 3; m++) { fd[m][0] = T->Q_fract_allpass[is34][k][m][0]; fd[m][1] = T->Q_fract_allpass[is34][k][m][1]; }
             const float pf_re = T->phi_fract[is34][k][0], pf_im = T->phi_fract[is34][k][1];
+            float d2_re = cleared ? 0.0f : st->delay[k][12][0], d2_im = cleared ? 0.0f : st->delay[k][12][1];     /* two slots back */
+            float d1_re = cleared ? 0.0f : st->delay[k][13][0], d1_im = cleared ? 0.0f : st->delay[k][13][1];     /* one slot back */
             for (int n = 0; n < 32; n++) {
-                /* delay[k][n + 12]: two slots back */
-                float d_re = n < 2 ? hist[12 + n][0] : sm->L[k][n - 2][0];
-                float d_im = n < 2 ? hist[12 + n][1] : sm->L[k][n - 2][1];
+                const float d_re = d2_re, d_im = d2_im;       /* delay[k][n + 12] */
+                d2_re = d1_re; d2_im = d1_im; d1_re = Lk[n][0]; d1_im = Lk[n][1];
                 float in_re = d_re * pf_re - d_im * pf_im;
                 float in_im = d_re * pf_im + d_im * pf_re;
+                HEAAC_UNROLL
                 for (int m = 0; m < 3; m++) {
                     /* ap_delay[k][m][n + 5 - link_delay], link_delay = 3 + m: ring of the last 5 values, ap[m][4] newest */
-                    float a_re = ag[m] * in_re, a_im = ag[m] * in_im;
+                    const float agm = m == 0 ? ag0 : m == 1 ? ag1 : ag2;
+                    float a_re = agm * in_re, a_im = agm * in_im;
                     float ld_re = ap[m][2 - m][0], ld_im = ap[m][2 - m][1];
-                    float fd_re = T->Q_fract_allpass[is34][k][m][0], fd_im = T->Q_fract_allpass[is34][k][m][1];
                     float nw_re = in_re, nw_im = in_im;
-                    in_re = ld_re * fd_re - ld_im * fd_im - a_re;
-                    in_im = ld_re * fd_im + ld_im * fd_re - a_im;
-                    nw_re += ag[m] * in_re;
-                    nw_im += ag[m] * in_im;
+                    in_re = ld_re * fd[m][0] - ld_im * fd[m][1] - a_re;
+                    in_im = ld_re * fd[m][1] + ld_im * fd[m][0] - a_im;
+                    nw_re += agm * in_re;
+                    nw_im += agm * in_im;
+                    HEAAC_UNROLL
                     for (int j = 0; j < 4; j++) { ap[m][j][0] = ap[m][j + 1][0]; ap[m][j][1] = ap[m][j + 1][1]; }
                     ap[m][4][0] = nw_re; ap[m][4][1] = nw_im;
                 }
-                sm->R[k][n][0] = sm->power[b][n] * in_re;
-                sm->R[k][n][1] = sm->power[b][n] * in_im;
+                const float tg = pw[n];
+                Rk[n][0] = tg * in_re;
+                Rk[n][1] = tg * in_im;
             }
-            for (int m = 0; m < 3; m++)
+            HEAAC_UNROLL
+            for (int m = 0; m < 3; m++) {
+                HEAAC_UNROLL
                 for (int j = 0; j < 5; j++) { st->ap_delay[k][m][j][0] = ap[m][j][0]; st->ap_delay[k][m][j][1] = ap[m][j][1]; }
+            }
         } else {
             const int d = k < short_delay_band ? 14 : 1;
             for (int n = 0; n < 32; n++) {
-                int pos = n + 14 - d;                     /* index into [hist(14) | this frame(32)] */
-                float d_re = pos < 14 ? hist[pos][0] : sm->L[k][pos - 14][0];
-                float d_im = pos < 14 ? hist[pos][1] : sm->L[k][pos - 14][1];
-                sm->R[k][n][0] = sm->power[b][n] * d_re;
-                sm->R[k][n][1] = sm->power[b][n] * d_im;
+                const int pos = n + 14 - d;               /* index into [previous frame's delay line (14) | this frame (32)] */
+                float d_re, d_im;
+                if (pos < 14) { d_re = cleared ? 0.0f : st->delay[k][pos][0]; d_im = cleared ? 0.0f : st->delay[k][pos][1]; }
+                else          { d_re = Lk[pos - 14][0]; d_im = Lk[pos - 14][1]; }
+                Rk[n][0] = pw[n] * d_re;
+                Rk[n][1] = pw[n] * d_im;
             }
         }
-        for (int j = 0; j < 14; j++) { st->delay[k][j][0] = sm->L[k][18 + j][0]; st->delay[k][j][1] = sm->L[k][18 + j][1]; }
+        for (int j = 0; j < 14; j++) { st->delay[k][j][0] = Lk[18 + j][0]; st->delay[k][j][1] = Lk[18 + j][1]; }
     }
     /* bands beyond nr_bands keep their state unless everything was cleared */
     if (switched) {
@@ -784,11 +796,14 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         }
     }
     HEAAC_SYNC();
-    /* ---- mixing: one hybrid band per work item, serial over envelopes and slots ---- */
-    for (int k = tid; k < nr_bands; k += nt) {
+    /* ---- mixing: one (hybrid band, envelope) per work item -- the interpolation of the matrices restarts from H[e] at every
+     *      envelope border (aacps.c:905-920), so envelopes are independent; serial over the envelope's slots (the interpolated
+     *      coefficients are running sums) ---- */
+    for (int w = tid; w < nr_bands * p->num_env; w += nt) {
+        const int e0 = w / nr_bands, k = w - e0 * nr_bands;
         const int b = k_to_i[k];
         const int neg = p->enable_ipdopd && ((is34 && k <= 13 && k >= 9) || (!is34 && k <= 1));
-        for (int e = 0; e < p->num_env; e++) {
+        for (int e = e0; e <= e0; e++) {
             int start = p->border_position[e], stop = p->border_position[e + 1];
             float width = heaac_fdiv(1.f, (float)(stop - start));
             float hr[4], hi[4], hrs[4], his[4];
