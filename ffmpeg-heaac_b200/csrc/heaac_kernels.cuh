@@ -454,7 +454,6 @@ struct HeaacPsSmem {
     float R[91][HEAAC_PS_NS][2];    /* Rbuf: decorrelated signal, then right output */
     float in[5][44][2];             /* in_buf: 6 history + 38 new slots of QMF bands 0..4 */
     float power[34][HEAAC_PS_NS];   /* per parameter band and slot: the power, then (in place) the transient gain */
-    int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
     HeaacPsFrame p;
 };
 
@@ -638,7 +637,16 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         sm->power[i][n] = pw;
     }
     HEAAC_SYNC();
-    for (int i = tid; i < nr_par; i += nt) {              /* transient detection: serial in time */
+    /* ---- one region without barriers: the transient detector (a serial recursion per parameter band), the decorrelator (a
+     *      serial recursion per hybrid band) and the mixing matrices (serial over envelopes per parameter band) are independent
+     *      of each other -- the transient gain only scales the decorrelator's output, which is done where that output is
+     *      read -- so with 256 threads they run side by side on thread groups T, H and A ---- */
+    constexpr bool PS_SPLIT = nt >= 256;
+    const bool inT = !PS_SPLIT || tid < 64, inH = !PS_SPLIT || (tid >= 64 && tid < 128), inA = !PS_SPLIT || tid >= 128;
+    const int tT = tid, nT = PS_SPLIT ? 64 : nt, tH = PS_SPLIT ? tid - 64 : tid, nH = PS_SPLIT ? 64 : nt;
+    const int tA = PS_SPLIT ? tid - 128 : tid, nA = PS_SPLIT ? nt - 128 : nt;
+    if (inT) {
+    for (int i = tT; i < nr_par; i += nT) {               /* transient detection: serial in time */
         float pdn = switched ? 0.0f : st->peak_decay_nrg[i];
         float psm = switched ? 0.0f : st->power_smooth[i];
         float pds = switched ? 0.0f : st->peak_decay_diff_smooth[i];
@@ -654,14 +662,13 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
         st->peak_decay_nrg[i] = pdn; st->power_smooth[i] = psm; st->peak_decay_diff_smooth[i] = pds;
     }
     if (switched)
-        for (int i = nr_par + tid; i < 34; i += nt) {
+        for (int i = nr_par + tT; i < 34; i += nT) {
             st->peak_decay_nrg[i] = 0.0f; st->power_smooth[i] = 0.0f; st->peak_decay_diff_smooth[i] = 0.0f;
         }
-    HEAAC_SYNC();
-    for (int k = tid; k < nr_bands; k += nt) {            /* one hybrid band per work item, serial in time */
-        const int b = k_to_i[k];
+    }
+    if (inA) {
+    for (int k = tA; k < nr_bands; k += nA) {             /* one hybrid band per work item, serial in time */
         const int cleared = switched || k >= top;         /* aacps.c:980-983 + 665-671 */
-        const float *pw = sm->power[b];
         const float (*Lk)[2] = sm->L[k];
         float (*Rk)[2] = sm->R[k];
         if (k < nr_ap) {
@@ -705,9 +712,8 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                     for (int j = 0; j < 4; j++) { ap[m][j][0] = ap[m][j + 1][0]; ap[m][j][1] = ap[m][j + 1][1]; }
                     ap[m][4][0] = nw_re; ap[m][4][1] = nw_im;
                 }
-                const float tg = pw[n];
-                Rk[n][0] = tg * in_re;
-                Rk[n][1] = tg * in_im;
+                Rk[n][0] = in_re;                             /* (the transient gain is applied where R is read: the mixing) */
+                Rk[n][1] = in_im;
             }
             HEAAC_UNROLL
             for (int m = 0; m < 3; m++) {
@@ -721,19 +727,19 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                 float d_re, d_im;
                 if (pos < 14) { d_re = cleared ? 0.0f : st->delay[k][pos][0]; d_im = cleared ? 0.0f : st->delay[k][pos][1]; }
                 else          { d_re = Lk[pos - 14][0]; d_im = Lk[pos - 14][1]; }
-                Rk[n][0] = pw[n] * d_re;
-                Rk[n][1] = pw[n] * d_im;
+                Rk[n][0] = d_re;
+                Rk[n][1] = d_im;
             }
         }
         for (int j = 0; j < 14; j++) { st->delay[k][j][0] = Lk[18 + j][0]; st->delay[k][j][1] = Lk[18 + j][1]; }
     }
     /* bands beyond nr_bands keep their state unless everything was cleared */
     if (switched) {
-        for (int w = tid; w < (91 - nr_bands) * 14; w += nt) {
+        for (int w = tA; w < (91 - nr_bands) * 14; w += nA) {
             int k = nr_bands + w / 14, j = w % 14;
             st->delay[k][j][0] = 0.0f; st->delay[k][j][1] = 0.0f;
         }
-        for (int w = tid; w < (50 - nr_ap) * 15; w += nt) {
+        for (int w = tA; w < (50 - nr_ap) * 15; w += nA) {
             int k = nr_ap + w / 15, r = w % 15;
             st->ap_delay[k][r / 5][r % 5][0] = 0.0f; st->ap_delay[k][r / 5][r % 5][1] = 0.0f;
         }
@@ -741,44 +747,39 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
     /* ap_delay of all-pass bands at or above `top` that this frame did not run: cleared (aacps.c:982-983) */
     /* (bands < nr_ap are always run above, with cleared history when k >= top) */
 
-    /* ---- stereo_processing, aacps.c:794-971: H matrices ---- */
-    for (int w = tid; w < 4 * 2 * 34; w += nt) {
-        int h = w / 68, c = (w / 34) & 1, b = w % 34;
-        /* the matrices live in the stream's state block (all six rows persist: stale rows are re-read by later
-         * frames, aacps.c:816-823); row 0 becomes the previous frame's last envelope */
-        st->H[h][c][0][b] = st->H[h][c][p->num_env_old][b];
     }
-    for (int w = tid; w < p->num_env * 34; w += nt) {
-        int e = w / 34, b = w - e * 34;
-        if (b >= nr_par) continue;
-        sm->iid[e][b] = (int8_t)heaac_ps_map_idx(p->iid_par[e], p->nr_iid_par, is34, 1, b);
-        sm->icc[e][b] = (int8_t)heaac_ps_map_idx(p->icc_par[e], p->nr_icc_par, is34, 1, b);
-        if (p->enable_ipdopd && b < (is34 ? 17 : 11)) {
-            sm->ipd[e][b] = (int8_t)heaac_ps_map_idx(p->ipd_par[e], p->nr_ipdopd_par, is34, 0, b);
-            sm->opd[e][b] = (int8_t)heaac_ps_map_idx(p->opd_par[e], p->nr_ipdopd_par, is34, 0, b);
-        }
-    }
-    HEAAC_SYNC();
-    if (switched) {
-        for (int w = tid; w < 8; w += nt) heaac_ps_map_val(st->H[w >> 1][w & 1][0], is34);
-        for (int b = tid; b < 17; b += nt) { st->ipd_hist[b] = 0; st->opd_hist[b] = 0; }   /* ipdopd_reset, aacps.c:141-148 */
-    }
-    HEAAC_SYNC();
+    if (inH) {
+    /* ---- stereo_processing, aacps.c:794-971: H matrices.  Work items own what they touch, so no barrier is needed inside:
+     *      one item per parameter band for the hand-over of the previous frame's last envelope, the index remapping and the
+     *      matrices of all envelopes ---- */
     {
         const float (*H_LUT)[8][4] = p->icc_mode < 3 ? T->HA : T->HB;
-        for (int b = tid; b < nr_par; b += nt) {          /* serial over envelopes: the phase smoother has memory */
+        for (int b = tH; b < 34; b += nH) {               /* serial over envelopes: the phase smoother has memory */
+            /* the matrices live in the stream's state block (all six rows persist: stale rows are re-read by later frames,
+             * aacps.c:816-823); row 0 becomes the previous frame's last envelope -- column b by the item that owns column b,
+             * before it overwrites the rows of this frame's envelopes */
+            for (int r = 0; r < 8; r++) st->H[r >> 1][r & 1][0][b] = st->H[r >> 1][r & 1][p->num_env_old][b];
+            if (switched && b < 17) { st->ipd_hist[b] = 0; st->opd_hist[b] = 0; }       /* ipdopd_reset, aacps.c:141-148 */
+            if (b >= nr_par) continue;
             int oh = st->opd_hist[b < 34 ? b : 0], ih = st->ipd_hist[b < 34 ? b : 0];
             for (int e = 0; e < p->num_env; e++) {
+                const int iid = heaac_ps_map_idx(p->iid_par[e], p->nr_iid_par, is34, 1, b);
+                const int icc = heaac_ps_map_idx(p->icc_par[e], p->nr_icc_par, is34, 1, b);
                 /* indices are range-checked by the parser (aacps.c:116-117); clamp so that a corrupt
                  * parameter block can never index outside the table */
-                int li = sm->iid[e][b] + 7 + 23 * p->iid_quant, lc = sm->icc[e][b];
+                int li = (int8_t)iid + 7 + 23 * p->iid_quant, lc = (int8_t)icc;
                 li = li < 0 ? 0 : (li > 45 ? 45 : li);
                 lc = lc < 0 ? 0 : (lc > 7 ? 7 : lc);
                 const float *lut = H_LUT[li][lc];
                 float h11 = lut[0], h12 = lut[1], h21 = lut[2], h22 = lut[3];
                 if (p->enable_ipdopd && b < p->nr_ipdopd_par) {
-                    int opd_idx = (oh * 8 + (sm->opd[e][b] & 7)) & 511;
-                    int ipd_idx = (ih * 8 + (sm->ipd[e][b] & 7)) & 511;
+                    /* (20-band processing with 17 phase parameters: bands 11..16 have no remapped value -- the reference reads
+                     * uninitialised memory there, aacps.c:845-848; zero here) */
+                    const int has_pd = b < (is34 ? 17 : 11);
+                    const int ipd = has_pd ? (int8_t)heaac_ps_map_idx(p->ipd_par[e], p->nr_ipdopd_par, is34, 0, b) : 0;
+                    const int opd = has_pd ? (int8_t)heaac_ps_map_idx(p->opd_par[e], p->nr_ipdopd_par, is34, 0, b) : 0;
+                    int opd_idx = (oh * 8 + (opd & 7)) & 511;
+                    int ipd_idx = (ih * 8 + (ipd & 7)) & 511;
                     float opd_re = T->pd_re_smooth[opd_idx], opd_im = T->pd_im_smooth[opd_idx];
                     float ipd_re = T->pd_re_smooth[ipd_idx], ipd_im = T->pd_im_smooth[ipd_idx];
                     oh = opd_idx & 0x3F; ih = ipd_idx & 0x3F;
@@ -795,7 +796,12 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
             st->opd_hist[b] = (int8_t)oh; st->ipd_hist[b] = (int8_t)ih;
         }
     }
+    }
     HEAAC_SYNC();
+    if (switched) {                                       /* 20 <-> 34 bands: the previous frame's matrices are remapped (aacps.c:824-843) */
+        for (int w = tid; w < 8; w += nt) heaac_ps_map_val(st->H[w >> 1][w & 1][0], is34);
+        HEAAC_SYNC();
+    }
     /* ---- mixing: one (hybrid band, envelope) per work item -- the interpolation of the matrices restarts from H[e] at every
      *      envelope border (aacps.c:905-920), so envelopes are independent; serial over the envelope's slots (the interpolated
      *      coefficients are running sums) ---- */
@@ -817,7 +823,8 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
                 }
             }
             for (int n = start + 1; n <= stop; n++) {
-                float l_re = sm->L[k][n][0], l_im = sm->L[k][n][1], r_re = sm->R[k][n][0], r_im = sm->R[k][n][1];
+                const float tg = sm->power[b][n];             /* transient gain of the decorrelated signal, aacps.c:747-752 */
+                float l_re = sm->L[k][n][0], l_im = sm->L[k][n][1], r_re = tg * sm->R[k][n][0], r_im = tg * sm->R[k][n][1];
                 for (int h = 0; h < 4; h++) hr[h] += hrs[h];
                 if (p->enable_ipdopd) {
                     for (int h = 0; h < 4; h++) hi[h] += his[h];
