@@ -38,8 +38,7 @@ static inline float heaac_rint(float a) { return rintf(a); }
 #define HEAAC_SYNC() __syncthreads()
 #define HEAAC_SYNCWARP() __syncwarp()
 #define HEAAC_SYNC_OR(x) __syncthreads_or(x)      /* barrier + "does the predicate hold for any thread of the CTA" */
-/* X may still be being written elsewhere in the grid before (k_sbr / k_synth overlap through per-channel flags): read
- * it through L2, never through the non-coherent path */
+/* the inter-kernel X buffer is written by the kernel before: read it through L2, never through the non-coherent path */
 #define HEAAC_LDX(p) __ldcg(p)
 #define HEAAC_RESTRICT __restrict__
 /* IEEE round-to-nearest, never contracted into FMA: used where the reference's result is

@@ -552,7 +552,7 @@ HEAAC_DEV void heaac_ps_stream(HeaacPsSmem *sm, const HeaacPsFrame *HEAAC_RESTRI
 {
     constexpr int nt = NT;
     const float *Lre = XL, *Lim = XL + HEAAC_X_PLANE;
-    /* Everything the first phases need comes from global memory (the frame's parameters, the QMF bands k_sbr has just
+    /* Everything the first phases need comes from global memory (the frame's parameters, the QMF bands k_chain has just
      * written, the hybrid filter history): issue it all at once, one barrier, instead of three dependent round trips. */
     const int start_g = frame->start, is34_g = frame->is34bands;
     {

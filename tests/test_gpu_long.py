@@ -112,8 +112,7 @@ def test_ten_second_lc_stereo_44k_matches_reference():
 
 
 def test_config5_shard_8192_streams_matches_oracle():
-    """One GPU's shard of BASELINE config 5 at 8 GPUs: 8192 HE-AAC v1 stereo streams (16,384 channels per launch -- the
-    launch path above HEAAC_PDL_MAX_CHANNELS), 32 frames.  A 32-stream sample spread over the batch is compared with the
+    """One GPU's shard of BASELINE config 5 at 8 GPUs: 8192 HE-AAC v1 stereo streams (16,384 CTAs of k_chain, 22 waves), 32 frames.  A 32-stream sample spread over the batch is compared with the
     oracle over all 32 frames; identical streams give identical PCM wherever they sit in the batch."""
     from ffmpeg_heaac_b200 import synthetic
     S, T, K = 8192, 32, 32
