@@ -31,10 +31,9 @@
 #define FE_MAX_CH 16
 #ifdef FE_DEVICE
 #define FE_INL static __device__ __forceinline__
-/* big routines that a kernel reaches once per frame (or only on a rare path): called, not inlined -- one copy in the kernel instead
- * of one per call site keeps the instruction footprint (the parse kernels are instruction-fetch bound) and the register
- * allocation of the hot paths around them down */
-#define FE_BIG static __device__ __noinline__
+/* (measured: calling instead of inlining the big routines -- fe_parse_frame, ps_read, the table derivation -- takes k_parse_b's
+ * spills from 10 KB to 0.9 KB per thread but costs the LC 5.1 packet path 40 %: they stay inlined) */
+#define FE_BIG static __device__
 #else
 #define FE_INL static inline __attribute__((always_inline))
 #define FE_BIG static
