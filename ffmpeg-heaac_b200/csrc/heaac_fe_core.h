@@ -31,9 +31,10 @@
 #define FE_MAX_CH 16
 #ifdef FE_DEVICE
 #define FE_INL static __device__ __forceinline__
-/* (measured: calling instead of inlining the big routines -- fe_parse_frame, ps_read, the table derivation -- takes k_parse_b's
- * spills from 10 KB to 0.9 KB per thread but costs the LC 5.1 packet path 40 %: they stay inlined) */
-#define FE_BIG static __device__
+/* big routines off the hot paths of the device kernels -- the one-pass frame parser (phase B's fallback for frames phase A could not
+ * do statelessly; phase A has its own inlined, specialised instance), ps_data, the table derivation: called, not inlined, so that
+ * their registers and code do not weigh on the paths around them */
+#define FE_BIG static __device__ __noinline__
 #else
 #define FE_INL static inline __attribute__((always_inline))
 #define FE_BIG static
@@ -313,27 +314,30 @@ FE_FN int band_types(FeChan *c, BR *b)                           /* aacdec.c:720
 /* Scale factor data (ISO/IEC 14496-3 4.6.2.3; what decode_scalefactors yields, aacdec.c:768-822).  Every coded band belongs to one
  * of three KINDS -- spectral, noise (PNS), intensity position -- and each kind keeps one running value over the whole channel,
  * advanced by a Huffman-coded difference per band (the first noise band carries a 9-bit PCM word instead).  A kind is described
- * by how its running value is range-checked and where it points into the one 2^(x/4) table:
- *     gain = sign * pow2sf[base + dir * value],   valid while 0 <= value + chk <= 255 */
+ * by how its running value is range-checked and where it points into the one 2^(x/4) table (the table in the function). */
 FE_FN int scalefactors(FE *fe, FeChan *c, BR *b, int global_gain)
 {
-    enum { K_SPECTRAL, K_NOISE, K_INTENSITY, K_NONE };
+    enum { K_SPECTRAL, K_NOISE, K_INTENSITY };
     const int sfo = fe->sf_offset + (c->ws[0] == HEAAC_EIGHT_SHORT ? 12 : 0);
-    const int   chk[3]  = { 0, 0, 100 };
-    const int   base[3] = { sfo, sfo + 100, 200 };
-    const int   dir[3]  = { 1, 1, -1 };
-    const float sign[3] = { -1.0f, -1.0f, 1.0f };
-    int value[3] = { global_gain, global_gain - 90, 0 };
+    /* kind:          spectral          noise             intensity
+     * running value  global_gain       global_gain - 90  0
+     * range check    value             value             value + 100          (each within 0..255)
+     * table index    sfo + value       sfo + 100 + value 200 - value
+     * sign           -                 -                 +                                                    */
+    int v_spectral = global_gain, v_noise = global_gain - 90, v_intensity = 0;      /* (scalars: they stay in registers on the device) */
     int noise_pcm = 1;
     const int n = c->num_groups * c->max_sfb;
     for (int idx = 0; idx < n; idx++) {
         const int bt = c->band_type[idx];
-        const int k = bt == 0 ? K_NONE : bt == 13 ? K_NOISE : bt >= 14 ? K_INTENSITY : K_SPECTRAL;
-        if (k == K_NONE) { c->sf[idx] = 0.f; continue; }
-        if (k == K_NOISE && noise_pcm) { value[k] += br_get(b, 9) - 256; noise_pcm = 0; }
-        else value[k] += vlc_get(b, &TB->vsf) - 60;
-        if ((unsigned)(value[k] + chk[k]) > 255U) return HEAAC_E_INVAL;
-        c->sf[idx] = sign[k] * TB->pow2sf[base[k] + dir[k] * value[k]];
+        if (bt == 0) { c->sf[idx] = 0.f; continue; }
+        const int k = bt == 13 ? K_NOISE : bt >= 14 ? K_INTENSITY : K_SPECTRAL;
+        int value = k == K_NOISE ? v_noise : k == K_INTENSITY ? v_intensity : v_spectral;
+        if (k == K_NOISE && noise_pcm) { value += br_get(b, 9) - 256; noise_pcm = 0; }
+        else value += vlc_get(b, &TB->vsf) - 60;
+        if ((unsigned)(value + (k == K_INTENSITY ? 100 : 0)) > 255U) return HEAAC_E_INVAL;
+        const float gain = TB->pow2sf[k == K_INTENSITY ? 200 - value : sfo + value + (k == K_NOISE ? 100 : 0)];
+        c->sf[idx] = k == K_INTENSITY ? gain : -gain;
+        if (k == K_NOISE) v_noise = value; else if (k == K_INTENSITY) v_intensity = value; else v_spectral = value;
     }
     return 0;
 }
@@ -1004,8 +1008,10 @@ FE_FN void fe_sbr_payload(FE *fe, BR *b, int crc, int cnt, int prev_elem, int pr
 /* One packet (an ADTS frame or a bare raw_data_block) -> the frame's C-ABI structures.
  * coeffs [ncc][1024]; ics/tns [ncc]; sbr [nse] (may be NULL for LC); ps (may be NULL).
  * Returns bytes consumed (>= 0) or a negative HEAAC_E_* code (the reference returns -1). */
-FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
-                         HeaacSbrElem *sbr, HeaacPsFrame *ps)
+/* pa: compile-time constant at both call sites -- 1 = the stateless first phase of the two-phase parse (SBR payloads are only
+ * noted: the whole SBR / PS parser drops out of that instance, and of the kernel built on it), 0 = the one-pass parser */
+FE_INL int fe_parse_frame_x(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                            HeaacSbrElem *sbr, HeaacPsFrame *ps, const int pa)
 {
     if (!fe || !pkt || size <= 0 || !coeffs || !ics) return HEAAC_E_INVAL;
     BR br, *b = &br;
@@ -1050,12 +1056,12 @@ FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, H
         switch (type) {
         case 0: case 3:
             r = decode_ics(fe, &fe->ch[fe->elem_ch0[e]], b, coeffs + 1024 * fe->elem_ch0[e], 0);
-            if (fe->phase_a) fe->todo->chan[fe->elem_ch0[e]] = 1;
+            if (pa) fe->todo->chan[fe->elem_ch0[e]] = 1;
             break;
         case 1:
             r = decode_cpe(fe, &fe->ch[fe->elem_ch0[e]], &fe->ch[fe->elem_ch0[e] + 1], b,
                            coeffs + 1024 * fe->elem_ch0[e], coeffs + 1024 * (fe->elem_ch0[e] + 1));
-            if (fe->phase_a) { fe->todo->chan[fe->elem_ch0[e]] = 1; fe->todo->chan[fe->elem_ch0[e] + 1] = fe->last_common ? 2 : 1; }
+            if (pa) { fe->todo->chan[fe->elem_ch0[e]] = 1; fe->todo->chan[fe->elem_ch0[e] + 1] = fe->last_common ? 2 : 1; }
             break;
         case 4: {                                                  /* DSE, aacdec.c:1190-1200 region */
             int align = br_get1(b), cnt = br_get(b, 8);
@@ -1070,7 +1076,7 @@ FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, H
             while (cnt > 0) {                                      /* decode_extension_payload, aacdec.c:1650-1690 */
                 int ext = br_get(b, 4), res = cnt;
                 if (ext == 0xd || ext == 0xe) {
-                    if (fe->phase_a) {                             /* stateless phase: note it for phase B, skip the bits */
+                    if (pa) {                                      /* stateless phase: note it for phase B, skip the bits */
                         FeTodo *td = fe->todo;
                         if (td->n_sbr < FE_MAX_TODO) {
                             td->sbr[td->n_sbr].pos = b->pos; td->sbr[td->n_sbr].cnt = cnt; td->sbr[td->n_sbr].crc = ext == 0xe;
@@ -1102,9 +1108,15 @@ FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, H
             else fe_zero32(tns[c].n_filt, 2);
         }
     }
-    fe_pack_l(fe, sbr, ps, 0, 1);
+    if (!pa) fe_pack_l(fe, sbr, ps, 0, 1);
     int consumed = (b->pos + 7) >> 3;
     return consumed > size ? size : consumed;
+}
+
+FE_BIG int fe_parse_frame(FE *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                         HeaacSbrElem *sbr, HeaacPsFrame *ps)
+{
+    return fe_parse_frame_x(fe, pkt, size, coeffs, ics, tns, sbr, ps, 0);
 }
 
 
@@ -1126,7 +1138,7 @@ FE_FN void fe_phase_a(const FE *stream, FE *scratch, FeTodo *todo, const uint8_t
     scratch->phase_a = 1; scratch->saw_pns = 0; scratch->todo = todo;
     todo->serial = 0; todo->n_sbr = 0;
     for (int c = 0; c < FE_MAX_CH; c++) todo->chan[c] = 0;
-    todo->result = fe_parse_frame(scratch, pkt, size, coeffs, ics, tns, NULL, NULL);
+    todo->result = fe_parse_frame_x(scratch, pkt, size, coeffs, ics, tns, NULL, NULL, 1);
     if (todo->result < 0 || scratch->saw_pns || scratch->ncc != stream->ncc) todo->serial = 1;
     else
         for (int c = 0; c < stream->ncc; c++) if (!todo->chan[c]) fe_zero(coeffs + 1024 * c, 1024);

@@ -263,7 +263,7 @@ FE_FN void sbt_limiter(HeaacSbrElem *o, int limiter_bands)
  */
 #ifndef FE_BIG
 #ifdef FE_DEVICE
-#define FE_BIG static __device__
+#define FE_BIG static __device__ __noinline__
 #else
 #define FE_BIG static
 #endif
