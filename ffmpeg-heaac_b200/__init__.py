@@ -40,6 +40,7 @@ EXPORTS = [
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
     "heaac_b200_sbr_init", "heaac_b200_sbr_apply", "heaac_b200_ps_apply", "heaac_b200_sbr_close",
+    "heaac_fe_cce", "heaac_fe_layout_from_pce",
     "heaac_fe_sbr_downsampled", "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
@@ -92,6 +93,8 @@ def lib():
         L.heaac_fe_copy_layout.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_fix_layout.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_sbr_downsampled.argtypes = [C.c_void_p]
+        L.heaac_fe_cce.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_fe_layout_from_pce.argtypes = [C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.heaac_b200_inputs_consumed.argtypes = [C.c_void_p]
@@ -298,6 +301,8 @@ class Frontend:
         self.ncc, self.nse, self.sbr, self.ps, self.sr_index = [x.value for x in v]
         self.downsampled = bool(lib().heaac_fe_sbr_downsampled(self.h))
         self.elem_types = [int(et[i]) for i in range(max(n, 0))]
+        self.n_cce = max(int(lib().heaac_fe_cce(self.h, None)), 0)
+        self.from_pce = bool(lib().heaac_fe_layout_from_pce(self.h))
 
     def parse(self, pkt, two_phase=False):
         """Returns dict(coeffs [ncc,1024], ics [ncc], tns [ncc], sbr [nse], ps [1], consumed).
@@ -315,6 +320,9 @@ class Frontend:
             r[k] = r[k][:max(self.ncc, 1)]
         r["sbr"] = r["sbr"][:max(self.nse, 1)]
         r["consumed"] = n
+        if self.n_cce:                                 # coupling side info of this frame (HeaacBatch.cce)
+            r["cce"] = np.zeros(self.n_cce, abi.CCE)
+            lib().heaac_fe_cce(self.h, r["cce"].ctypes.data)
         return r
 
     def close(self):

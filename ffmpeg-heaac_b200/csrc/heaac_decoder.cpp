@@ -30,6 +30,7 @@ struct ParamSet {                    /* one chunk of parsed frames, frame-major 
     HeaacTns *tns = nullptr;
     HeaacSbrElem *sbr = nullptr;
     HeaacPsFrame *ps = nullptr;
+    HeaacCce *cce = nullptr;         /* layouts with coupling channel elements */
 };
 
 struct Job {                         /* what the pool is working on */
@@ -53,7 +54,7 @@ struct HeaacDecoder {
     size_t pending_n[8] = { 0 };
     long long pending_ticket[8] = { 0 };
     long long n_submitted = 0, n_chunks = 0;
-    int ncc = 0, nse = 0, sbr = 0, ps = 0, sr_index = 0, n_elems = 0, chunk = 1;
+    int ncc = 0, nse = 0, sbr = 0, ps = 0, sr_index = 0, n_elems = 0, n_cce = 0, chunk = 1;
     uint8_t elem_type[HEAAC_MAX_ELEMS] = { 0 };
     ParamSet set[2];
     std::atomic<long long> parse_errors{0};
@@ -80,6 +81,7 @@ void silent_frame(HeaacDecoder *d, ParamSet *p, size_t idx)
     memset(p->tns + idx * d->ncc, 0, sizeof(HeaacTns) * d->ncc);
     if (d->sbr) memset(p->sbr + idx * d->nse, 0, sizeof(HeaacSbrElem) * d->nse);
     if (d->ps)  memset(p->ps + idx, 0, sizeof(HeaacPsFrame));
+    if (d->n_cce) memset(p->cce + idx * d->n_cce, 0, sizeof(HeaacCce) * d->n_cce);
 }
 
 void parse_range(HeaacDecoder *d, const Job &j, int s0, int s1)
@@ -92,6 +94,7 @@ void parse_range(HeaacDecoder *d, const Job &j, int s0, int s1)
             int r = heaac_fe_parse(d->fe[s], j.pkt[idx], j.size[idx], p->coeffs + idx * d->ncc * 1024, p->ics + idx * d->ncc,
                                    p->tns + idx * d->ncc, d->sbr ? p->sbr + idx * d->nse : nullptr, d->ps ? p->ps + idx : nullptr);
             if (r < 0) { silent_frame(d, p, idx); d->parse_errors++; }
+            else if (d->n_cce) heaac_fe_cce(d->fe[s], p->cce + idx * d->n_cce);
             if (j.consumed) j.consumed[idx] = r;
         }
     }
@@ -138,6 +141,7 @@ void free_sets(HeaacDecoder *d)
         if (p.ics) heaac_b200_host_free(d->be, p.ics);
         if (p.tns) heaac_b200_host_free(d->be, p.tns);
         if (p.sbr) heaac_b200_host_free(d->be, p.sbr);
+        if (p.cce) heaac_b200_host_free(d->be, p.cce);
         if (p.ps) heaac_b200_host_free(d->be, p.ps);
         p = ParamSet();
     }
@@ -162,6 +166,7 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     }
     if (r >= 0) {
         d->n_elems = heaac_fe_info(probe, &d->ncc, &d->nse, &d->sbr, &d->ps, &d->sr_index, d->elem_type);
+        d->n_cce = heaac_fe_cce(probe, nullptr);
         r = d->n_elems > 0 ? 0 : HEAAC_E_INVAL;
     }
     if (r < 0) { heaac_fe_close(probe); return r; }
@@ -182,10 +187,14 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
     cfg.sf_scale = -1.0f / 1024.0f;                   /* s16-unit convention, aacdec.c:577-581 */
     cfg.max_frames_per_call = d->cfg.max_frames_per_call;
     cfg.want_float_out = d->cfg.want_float_out;
+    /* the device front end takes channel_configuration layouts; streams with a program config element are parsed on the host */
+    if (heaac_fe_layout_from_pce(probe)) d->cfg.gpu_parse = 0;
     /* the device parser spreads a chunk's frames over the lanes of a warp: longer chunks, more lanes at work */
     if (d->cfg.gpu_parse && d->cfg.max_frames_per_call >= 32) cfg.chunk_frames = d->cfg.max_frames_per_call >= 64 ? 32 : 16;
     if (d->cfg.chunk_frames > 0) cfg.chunk_frames = d->cfg.chunk_frames;
-    heaac_b200_reference_out_slots(cfg.elem_type, cfg.n_elems, cfg.out_slot);
+    /* channel_configuration layouts: the reference's speaker order; program config element layouts: the elements already are
+     * in the reference's order (out_slot all zero = output channels in element order) */
+    if (!heaac_fe_layout_from_pce(probe)) heaac_b200_reference_out_slots(cfg.elem_type, cfg.n_elems, cfg.out_slot);
     if ((r = heaac_b200_create(&cfg, &d->be))) return r;
 
     d->chunk = heaac_b200_chunk_frames(d->be);
@@ -204,7 +213,8 @@ int configure(HeaacDecoder *d, const uint8_t *pkt, int size)
             heaac_b200_host_alloc(d->be, n * d->ncc * sizeof(HeaacIcs), (void **)&p.ics) ||
             heaac_b200_host_alloc(d->be, n * d->ncc * sizeof(HeaacTns), (void **)&p.tns) ||
             (d->sbr && heaac_b200_host_alloc(d->be, n * d->nse * sizeof(HeaacSbrElem), (void **)&p.sbr)) ||
-            (d->ps && heaac_b200_host_alloc(d->be, n * sizeof(HeaacPsFrame), (void **)&p.ps)))
+            (d->ps && heaac_b200_host_alloc(d->be, n * sizeof(HeaacPsFrame), (void **)&p.ps)) ||
+            (d->n_cce && heaac_b200_host_alloc(d->be, n * d->n_cce * sizeof(HeaacCce), (void **)&p.cce)))
             return HEAAC_E_NOMEM;
     }
     for (int s = 0; s < d->cfg.n_streams; s++) {
@@ -318,7 +328,7 @@ extern "C" long long heaac_dec_submit(HeaacDecoder *d, int n_frames, const uint8
         HeaacBatch b;
         memset(&b, 0, sizeof(b));
         b.n_frames = n;
-        b.coeffs = p->coeffs; b.ics = p->ics; b.tns = p->tns; b.sbr = p->sbr; b.ps = p->ps;
+        b.coeffs = p->coeffs; b.ics = p->ics; b.tns = p->tns; b.sbr = p->sbr; b.ps = p->ps; b.cce = p->cce;
         b.pcm = pcm ? pcm + (size_t)f0 * out_frame : nullptr;
         b.pcm_f32 = pcm_f32 ? pcm_f32 + (size_t)f0 * out_frame : nullptr;
         if ((r = heaac_b200_synth_submit(d->be, &b))) return r;

@@ -29,6 +29,7 @@
 #include "heaac_sbr_tables_core.h"
 
 #define FE_MAX_CH 16
+#define FE_MAX_CCE 4
 #ifdef FE_DEVICE
 #define FE_INL static __device__ __forceinline__
 /* big routines off the hot paths of the device kernels -- the one-pass frame parser (phase B's fallback for frames phase A could not
@@ -242,6 +243,11 @@ struct HeaacFrontend {
     FeChan ch[FE_MAX_CH];
     FeSbr sbr_el[HEAAC_MAX_ELEMS];
     FePs psx;
+    /* layouts from a program config element (host build only; the device front end takes channel_configuration 1-6) */
+    int by_tag;                                 /* elements are addressed by (type, instance tag) -- che[type][id] of the reference */
+    int elem_tag[HEAAC_MAX_ELEMS];
+    int n_cce;
+    HeaacCce cce[FE_MAX_CCE];                   /* coupling side info of the last parsed frame, one per CCE in layout order */
 };
 typedef struct HeaacFrontend FE;
 
@@ -258,6 +264,7 @@ FE_FN int set_layout(FE *fe, int chan_config)
     fe->chan_config = chan_config;
     fe->n_elems = fe_lay[chan_config][0];
     fe->ncc = fe->nse = 0;
+    fe->by_tag = 0; fe->n_cce = 0;
     for (int e = 0; e < fe->n_elems; e++) {
         fe->elem_type[e] = fe_lay[chan_config][1 + e];
         fe->elem_ch0[e] = fe->ncc;
@@ -266,6 +273,57 @@ FE_FN int set_layout(FE *fe, int chan_config)
     }
     return 0;
 }
+
+#ifndef FE_DEVICE
+/* program_config_element (ISO/IEC 14496-3 table 4.2; decode_pce, aacdec.c:280-340).  The reference marks che_pos[type][tag]
+ * for every listed element and then walks tags 0..15 x types SCE, CPE, CCE, LFE to allocate elements and number the output
+ * channels (output_configure, aacdec.c:246-262): the layout built here is that walk -- elements ordered by (tag, type), output
+ * channels in element order, coupling channels without an output of their own.
+ * apply != 0: make it the stream's layout; 0: only step over it (a further PCE of a configured stream is not evaluated,
+ * aacdec.c:2020-2030).  Returns 0 or a negative HEAAC_E_* code. */
+FE_FN int fe_pce(FE *fe, BR *b, int apply)
+{
+    uint8_t present[4][16];
+    memset(present, 0, sizeof(present));
+    br_skip(b, 2);                                                 /* object_type */
+    br_skip(b, 4);                                                 /* sampling_frequency_index (the container's wins, a mismatch is only a warning) */
+    int count[6];                                                  /* front, side, back, lfe, assoc_data, cc */
+    static const int width[6] = { 4, 4, 4, 2, 3, 4 };
+    for (int i = 0; i < 6; i++) count[i] = br_get(b, width[i]);
+    if (br_get1(b)) br_skip(b, 4);                                 /* mono_mixdown */
+    if (br_get1(b)) br_skip(b, 4);                                 /* stereo_mixdown */
+    if (br_get1(b)) br_skip(b, 3);                                 /* matrix_mixdown */
+    for (int grp = 0; grp < 6; grp++)
+        for (int i = 0; i < count[grp]; i++) {
+            if (grp == 4) { br_skip(b, 4); continue; }             /* associated data elements */
+            const int flag = grp == 3 ? 0 : br_get1(b), tag = br_get(b, 4);
+            const int type = grp == 3 ? HEAAC_TYPE_LFE : grp == 5 ? HEAAC_TYPE_CCE : flag ? HEAAC_TYPE_CPE : HEAAC_TYPE_SCE;
+            present[type][tag] = 1;                                /* (cc_element_is_ind_sw is not kept: every CCE says so itself) */
+        }
+    b->pos = (b->pos + 7) & ~7;
+    const int comment = 8 * br_get(b, 8);
+    if (br_left(b) < comment) return HEAAC_E_INVAL;
+    br_skip(b, comment);
+    if (!apply) return 0;
+    int n = 0, ncc = 0, nse = 0, n_cce = 0;
+    for (int tag = 0; tag < 16; tag++)
+        for (int type = 0; type < 4; type++) {
+            if (!present[type][tag]) continue;
+            if (n >= HEAAC_MAX_ELEMS || ncc + 1 + (type == HEAAC_TYPE_CPE) > FE_MAX_CH) return HEAAC_E_UNSUPPORTED;
+            if (type == HEAAC_TYPE_CCE && n_cce++ >= FE_MAX_CCE) return HEAAC_E_UNSUPPORTED;
+            fe->elem_type[n] = type; fe->elem_tag[n] = tag; fe->elem_ch0[n] = ncc;
+            ncc += type == HEAAC_TYPE_CPE ? 2 : 1;
+            nse += type == HEAAC_TYPE_SCE || type == HEAAC_TYPE_CPE;
+            n++;
+        }
+    if (!n) return HEAAC_E_INVAL;
+    fe->n_elems = n; fe->ncc = ncc; fe->nse = nse; fe->n_cce = n_cce;
+    fe->chan_config = 0; fe->by_tag = 1;
+    memset(fe->cce, 0, sizeof(fe->cce));
+    return 0;
+}
+
+#endif
 
 
 /* ---------------------------------------------------------------- ICS */
@@ -586,6 +644,52 @@ FE_FN int decode_cpe(FE *fe, FeChan *c0, FeChan *c1, BR *b, float *co0, float *c
 }
 
 /* ---------------------------------------------------------------- SBR */
+
+#ifndef FE_DEVICE
+/* coupling_channel_element (decode_cce, aacdec.c:1503-1568) for an INDEPENDENTLY SWITCHED element: one gain per list, the
+ * first list's being 1.  The element / channel selection that apply_channel_coupling (aacdec.c:1870-1898) makes when it meets
+ * a target is resolved here into the ABI's list of (target channel, gain) operations.  Anything else than AFTER_IMDCT
+ * coupling is outside the ABI (HEAAC_E_UNSUPPORTED). */
+FE_FN int decode_cce(FE *fe, int e, BR *b, float *coeffs)
+{
+    int k = 0;
+    for (int i = 0; i < e; i++) k += fe->elem_type[i] == HEAAC_TYPE_CCE;
+    HeaacCce *o = &fe->cce[k];
+    int sel_type[8], sel_tag[8], sel_ch[8], lists = 0;
+    const int ind_sw = br_get1(b), n_coupled = br_get(b, 3) + 1;
+    for (int c = 0; c < n_coupled; c++) {
+        sel_type[c] = br_get1(b) ? HEAAC_TYPE_CPE : HEAAC_TYPE_SCE;
+        sel_tag[c] = br_get(b, 4);
+        sel_ch[c] = sel_type[c] == HEAAC_TYPE_CPE ? (int)br_get(b, 2) : 2;
+        lists += 1 + (sel_ch[c] == 3);
+    }
+    br_skip(b, 1);                                                 /* cc_domain: only meaningful for dependent coupling */
+    if (!ind_sw) return HEAAC_E_UNSUPPORTED;
+    br_skip(b, 1);                                                 /* gain_element_sign: per-band gains only */
+    const float scale = (float)pow(2., pow(2., (int)br_get(b, 2) - 3));
+    int r = decode_ics(fe, &fe->ch[fe->elem_ch0[e]], b, coeffs + 1024 * fe->elem_ch0[e], 0);
+    if (r) return r;
+    float gain[16];
+    gain[0] = 1.f;
+    for (int c = 1; c < lists; c++)
+        gain[c] = (float)pow(scale, -(vlc_get(b, &TB->vsf) - 60));  /* common_gain_element_present is implied */
+    int n = 0, list = 0;
+    for (int c = 0; c < n_coupled; c++) {
+        int te = -1;
+        for (int t = 0; t < fe->n_elems; t++)
+            if (fe->elem_type[t] == sel_type[c] && fe->elem_tag[t] == sel_tag[c]) te = t;
+        if (te >= 0) {
+            if (sel_ch[c] != 1 && n < HEAAC_CCE_MAX_TARGETS) { o->target_ch[n] = (uint8_t)fe->elem_ch0[te];       o->gain[n++] = gain[list]; }
+            if (sel_ch[c] != 2 && n < HEAAC_CCE_MAX_TARGETS) { o->target_ch[n] = (uint8_t)(fe->elem_ch0[te] + 1); o->gain[n++] = gain[list + (sel_ch[c] == 3)]; }
+        }
+        list += 1 + (sel_ch[c] == 3);
+    }
+    for (int i = n; i < HEAAC_CCE_MAX_TARGETS; i++) { o->target_ch[i] = 0; o->gain[i] = 0.f; }
+    o->coupling_point = 3; o->n_targets = (uint8_t)n;
+    return 0;
+}
+#endif
+
 
 FE_BIG int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, aacsbr.c:1023-1034 */
 {
@@ -1040,12 +1144,26 @@ FE_INL int fe_parse_frame_x(FE *fe, const uint8_t *pkt, int size, float *coeffs,
         } else if (ch) {
             int r = set_layout(fe, ch); if (r) return r; fe->sample_rate = sample_rates[sr]; fe->sr_index = sr;
         }
+#ifndef FE_DEVICE
+        else if (!fe->locked && !fe->layout_fixed) {              /* channel_configuration 0: the layout follows as a PCE */
+            fe->sample_rate = sample_rates[sr]; fe->sr_index = sr;
+        }
+#endif
     }
+#ifdef FE_DEVICE
     if (!fe->n_elems) return HEAAC_E_INVAL;
+#endif
     int seen[4] = { 0, 0, 0, 0 };
     int prev_elem = -1, prev_type = 7, type;
     while ((type = br_get(b, 3)) != 7) {
         int id = br_get(b, 4), e = -1, r = 0;
+#ifndef FE_DEVICE
+        if (fe->by_tag && type <= 3) {                             /* the element with this tag (che[type][id], aacdec.c:118-128) */
+            for (int i = 0; i < fe->n_elems; i++)
+                if (fe->elem_type[i] == type && fe->elem_tag[i] == id) { e = i; break; }
+            if (e < 0) return HEAAC_E_INVAL;
+        } else
+#endif
         if (type == 0 || type == 1 || type == 3) {                 /* k-th element of this type in the layout */
             int k = 0;
             for (int i = 0; i < fe->n_elems; i++)
@@ -1090,12 +1208,25 @@ FE_INL int fe_parse_frame_x(FE *fe, const uint8_t *pkt, int size, float *coeffs,
                 cnt -= res;
             }
             break; }
-        default: return HEAAC_E_UNSUPPORTED;                       /* CCE, PCE */
+#ifndef FE_DEVICE
+        case 2:
+            if (e < 0) return HEAAC_E_UNSUPPORTED;                 /* a coupling channel needs a layout that lists it (a PCE) */
+            r = decode_cce(fe, e, b, coeffs);
+            if (pa) fe->todo->chan[fe->elem_ch0[e]] = 1;
+            break;
+        case 5:                                                    /* in band: configures a stream nothing else has configured */
+            r = fe_pce(fe, b, !fe->n_elems && !fe->locked && !fe->layout_fixed);
+            break;
+#endif
+        default: return HEAAC_E_UNSUPPORTED;                       /* device build: CCE, PCE */
         }
         if (r) return r;
         if (type <= 3) { prev_elem = e; prev_type = type; } else if (type != 6) { prev_elem = -1; prev_type = type; }
         if (br_left(b) < 3) return HEAAC_E_INVAL;
     }
+#ifndef FE_DEVICE
+    if (!fe->n_elems) return HEAAC_E_INVAL;
+#endif
     fe->locked = 1;
     for (int c = 0; c < fe->ncc; c++) {
         const FeChan *fc = &fe->ch[c];

@@ -123,9 +123,16 @@ static int parse_asc(FE *fe, const uint8_t *d, int size)
     }
     if (fe->object_type != 2) return HEAAC_E_UNSUPPORTED;          /* AAC-LC only */
     if (idx > 12) return HEAAC_E_INVAL;
+    const int specific = b.pos;                                    /* GASpecificConfig, aacdec.c:425-455 */
     if (br_get1(&b)) return HEAAC_E_UNSUPPORTED;                   /* frameLengthFlag: 960 */
     if (br_get1(&b)) br_skip(&b, 14);                              /* dependsOnCoreCoder */
     br_get1(&b);                                                   /* extensionFlag */
+    if (!chan_config) {                                            /* the layout comes as a program config element */
+        br_skip(&b, 4);                                            /* element_instance_tag */
+        int r = fe_pce(fe, &b, 1);
+        if (r) return r;
+    }
+    b.pos = specific;                                              /* the sync extension is looked for from here (mpeg4audio.c:105-125) */
     if (fe->sbr == -1 && br_left(&b) >= 16) {                      /* backward-compatible explicit signalling */
         while (br_left(&b) > 15) {
             if (br_show(&b, 11) == 0x2b7) {
@@ -138,7 +145,7 @@ static int parse_asc(FE *fe, const uint8_t *d, int size)
         }
     }
     if (fe->sbr == 1 && fe->ps == -1) fe->ps = 1;                  /* aacdec.c:478-479 */
-    return set_layout(fe, chan_config);
+    return chan_config ? set_layout(fe, chan_config) : 0;
 }
 
 
@@ -198,6 +205,15 @@ int heaac_fe_copy_layout(FE *dst, const FE *src)
 {
     if (!dst || !src) return HEAAC_E_INVAL;
     dst->sample_rate = src->sample_rate; dst->sr_index = src->sr_index;
+    if (src->by_tag) {                                             /* a layout from a program config element */
+        dst->n_elems = src->n_elems; dst->ncc = src->ncc; dst->nse = src->nse; dst->n_cce = src->n_cce;
+        dst->chan_config = 0; dst->by_tag = 1;
+        memcpy(dst->elem_type, src->elem_type, sizeof(dst->elem_type));
+        memcpy(dst->elem_tag, src->elem_tag, sizeof(dst->elem_tag));
+        memcpy(dst->elem_ch0, src->elem_ch0, sizeof(dst->elem_ch0));
+        memset(dst->cce, 0, sizeof(dst->cce));
+        return 0;
+    }
     return src->chan_config ? set_layout(dst, src->chan_config) : 0;
 }
 
@@ -208,7 +224,7 @@ int heaac_fe_fix_layout(FE *dst, const FE *src)
 {
     int r = heaac_fe_copy_layout(dst, src);
     if (r) return r;
-    if (!dst->chan_config) return HEAAC_E_INVAL;
+    if (!dst->chan_config && !dst->by_tag) return HEAAC_E_INVAL;
     dst->layout_fixed = 1;
     return 0;
 }
@@ -235,3 +251,15 @@ int heaac_fe_info(const FE *fe, int *ncc, int *nse, int *sbr, int *ps, int *sr_i
     if (elem_type) for (int e = 0; e < fe->n_elems; e++) elem_type[e] = (uint8_t)fe->elem_type[e];
     return fe->n_elems;
 }
+
+/* Layouts with coupling channel elements: the coupling side info of the frame heaac_fe_parse has just returned, one HeaacCce per
+ * CCE in layout order (what HeaacBatch.cce takes).  Returns the number of CCEs of the layout. */
+int heaac_fe_cce(const FE *fe, HeaacCce *out)
+{
+    if (!fe) return HEAAC_E_INVAL;
+    if (out) memcpy(out, fe->cce, sizeof(HeaacCce) * (size_t)fe->n_cce);
+    return fe->n_cce;
+}
+/* 1 when the layout came from a program config element: elements -- and output channels -- are then in the reference's
+ * (instance tag, type) order and HeaacConfig.out_slot is the identity */
+int heaac_fe_layout_from_pce(const FE *fe) { return fe && fe->by_tag; }

@@ -336,6 +336,16 @@ int  heaac_fe_fix_layout(HeaacFrontend *dst, const HeaacFrontend *src);
  * implicit signalling once the first frame has been parsed (aacdec.c:1659-1676) */
 int  heaac_fe_info(const HeaacFrontend *fe, int *n_core_ch, int *n_sbr_elems, int *sbr, int *ps, int *sr_index,
                    uint8_t elem_type[HEAAC_MAX_ELEMS]);
+/* Layouts given as a program config element (decode_pce, aacdec.c:280-340: AudioSpecificConfig with channel_configuration 0,
+ * or in band in the first raw_data_block) may hold coupling channel elements (decode_cce, aacdec.c:1503-1568).  A CCE takes a
+ * core channel slot like an SCE (HEAAC_TYPE_CCE in elem_type); heaac_fe_cce() returns the layout's number of CCEs and copies
+ * the coupling side info of the frame heaac_fe_parse has just returned -- one HeaacCce per CCE in layout order, with the
+ * target selection of apply_channel_coupling (aacdec.c:1870-1898) resolved -- which is what HeaacBatch.cce takes.  Only
+ * independently switched coupling is inside the ABI; a frame with another kind fails with HEAAC_E_UNSUPPORTED.
+ * heaac_fe_layout_from_pce() = 1: elements and output channels are in the reference's (instance tag, type) order
+ * (output_configure, aacdec.c:246-262) and HeaacConfig.out_slot is the identity. */
+int  heaac_fe_cce(const HeaacFrontend *fe, struct HeaacCce *out);
+int  heaac_fe_layout_from_pce(const HeaacFrontend *fe);
 
 /* ---- containers (host C): ADTS framing and the MP4 `esds` descriptor ------------------------------------
  * adts_write_header: 7-byte header (no CRC) for one raw_data_block, as adts_write_frame_header (adtsenc.c:84-147);

@@ -78,6 +78,9 @@ def make_cce_golden():
     out["pcm_s16"] = np.stack([f["pcm"] for f in fr])
     out["elem_types"] = np.asarray(lay[0], np.int32)
     out["sr_index"] = np.int32(3)
+    out["extradata"] = np.frombuffer(ed, np.uint8)           # AudioSpecificConfig with the program config element
+    out["pkt_sizes"] = np.asarray([len(p) for p in pk], np.int32)
+    out["pkt_blob"] = np.frombuffer(b"".join(pk), np.uint8)
     path = os.path.join(HERE, "lc_cce.npz")
     np.savez_compressed(path, **out)
     print("lc_cce", out["coeffs"].shape, out["pcm_f32"].shape, "%.0f KB" % (os.path.getsize(path) / 1024))

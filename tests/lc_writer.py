@@ -302,7 +302,7 @@ class LcWriter:
         elem_tag = []
         for t in self.elem_types:
             elem_tag.append(tags.get(t, 0)); tags[t] = tags.get(t, 0) + 1
-        bw.put(1, 1)                                    # ind_sw_cce_flag
+        bw.put(getattr(self, "cce_ind_sw", 1), 1)      # ind_sw_cce_flag
         bw.put(len(tg) - 1, 3)                          # num_coupled_elements
         lists = 0
         for te, sel in tg:
@@ -379,14 +379,9 @@ class LcWriter:
 CHAN_CONFIG = {"mono": 1, "stereo": 2, "5.1": 6}
 
 
-def pce_config(sr_index, elem_types):
-    """AudioSpecificConfig with channel_configuration 0 and a program_config_element (ISO/IEC 14496-3 table 4.2; decode_pce,
-    aacdec.c:280-340) listing the elements: SCE / CPE as front channels, LFE, CCE as (independently switched) coupling
-    channels.  Returns (extradata, elem_ids, order): the reference orders its elements -- and its output channels -- by
-    instance tag, then type (output_configure, aacdec.c:245-262); `order` lists the element indices that way."""
-    bw = BitWriter()
-    bw.put(2, 5); bw.put(sr_index, 4); bw.put(0, 4)           # AOT 2, rate, channel_configuration 0
-    bw.put(0, 3)                                             # frame_length_flag, depends_on_core_coder, extension_flag
+def _pce_body(bw, sr_index, elem_types):
+    """program_config_element() from element_instance_tag on (ISO/IEC 14496-3 table 4.2; decode_pce, aacdec.c:280-340):
+    SCE / CPE as front channels, LFE, CCE as (independently switched) coupling channels.  Returns the instance tags."""
     tags, ids = {}, []
     for t in elem_types:
         ids.append(tags.get(t, 0)); tags[t] = tags.get(t, 0) + 1
@@ -405,8 +400,28 @@ def pce_config(sr_index, elem_types):
         bw.put(1, 1); bw.put(i, 4)                           # cc_element_is_ind_sw, tag
     bw.put(0, (-len(bw)) % 8)                                # byte_alignment
     bw.put(0, 8)                                             # comment_field_bytes
+    return ids
+
+
+def pce_config(sr_index, elem_types):
+    """AudioSpecificConfig with channel_configuration 0 and a program_config_element listing the elements.  Returns
+    (extradata, elem_ids, order): the reference orders its elements -- and its output channels -- by instance tag, then
+    type (output_configure, aacdec.c:245-262); `order` lists the element indices that way."""
+    bw = BitWriter()
+    bw.put(2, 5); bw.put(sr_index, 4); bw.put(0, 4)           # AOT 2, rate, channel_configuration 0
+    bw.put(0, 3)                                             # frame_length_flag, depends_on_core_coder, extension_flag
+    ids = _pce_body(bw, sr_index, elem_types)
     order = sorted(range(len(elem_types)), key=lambda e: (ids[e], elem_types[e]))
     return bw.tobytes(), ids, order
+
+
+def pce_element(sr_index, elem_types):
+    """The same program_config_element as a syntactic element of a raw_data_block (ID_PCE = 5): a whole number of bytes,
+    to be put in front of a frame of a stream that has no other configuration (ADTS with channel_configuration 0)."""
+    bw = BitWriter()
+    bw.put(5, 3)
+    _pce_body(bw, sr_index, elem_types)
+    return bw.tobytes()
 
 
 def make_lc_stream(seed, n_frames, layout="5.1", sr_index=3, **kw):

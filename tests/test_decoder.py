@@ -200,3 +200,26 @@ def test_decoder_full_batch_properties():
     b, _, cb = host.decode(batch)
     host.close()
     assert np.array_equal(ca, cb) and np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpu_parse", [False, True])
+def test_decoder_decodes_a_pce_stream_with_coupling_elements(gpu_parse):
+    """Packets -> PCM for a stream whose layout is a program config element with two coupling channel elements (SCE + CPE
+    coded, CCEs added in by k_couple): own front end (decode_pce / decode_cce) + CUDA back end against the reference
+    decoder's PCM for the same packets.  Such layouts are parsed on the host whatever gpu_parse says."""
+    from test_oracle_vs_ref import _cce_golden
+    d = _cce_golden()
+    S, T = 4, len(d["pkt_sizes"])
+    dec = hb.Decoder(S, d["extradata"].tobytes(), 48000, 3, max_frames=T, want_float=True, gpu_parse=gpu_parse, n_threads=2)
+    pk = golden_packets(d)
+    pcm, f32, consumed = dec.decode(hb.PacketBatch([[p] * S for p in pk]))
+    i = dec.info()
+    dec.close()
+    assert i["configured"] and i["parse_errors"] == 0 and i["gpu_launches"] > 0 and i["k_parse_ms"] == 0
+    assert (i["frame_out_len"], i["n_out_channels"]) == (1024, 3)
+    assert np.array_equal(consumed, np.repeat(d["pkt_sizes"][:, None], S, axis=1))
+    scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
+    for s in range(S):
+        assert float(np.abs(f32[:, s].astype(np.float64) - d["pcm_f32"]).max()) / scale <= 1e-5
+        assert int(np.abs(pcm[:, s].astype(np.int32) - d["pcm_s16"]).max()) <= 1

@@ -283,3 +283,112 @@ def test_adts_header_cannot_change_a_fixed_or_running_layout():
     g.parse(surround[0])
     assert g.ncc == 6
     g.close()
+
+
+# ---------------------------------------------------------------- program config elements and coupling channel elements
+def _cce_golden():
+    from test_oracle_vs_ref import _cce_golden as g
+    return g()
+
+
+def test_frontend_parses_a_pce_layout_with_coupling_elements():
+    """AudioSpecificConfig with a program_config_element (decode_pce, aacdec.c:280-340) listing SCE + CPE + two coupling
+    channel elements, and the CCEs themselves (decode_cce, aacdec.c:1503-1568), against the committed capture of what the
+    reference's parsers left for spectral_to_sample on the same packets: coefficients, ICS and TNS of all five coded
+    channels and the resolved coupling lists (target channel, gain) -- bit for bit."""
+    d = _cce_golden()
+    fe = hb.Frontend(d["extradata"].tobytes())
+    assert fe.from_pce and fe.n_cce == 2 and fe.ncc == 5 and fe.sr_index == int(d["sr_index"])
+    assert fe.elem_types == [int(x) for x in d["elem_types"]]
+    for t, p in enumerate(golden_packets(d)):
+        m = fe.parse(p)
+        ref = {k: d[k][t] for k in ("coeffs", "ics", "tns")}
+        bad = diff_parsed(ref, m, 5, False, False)
+        assert not bad, "frame %d: %s" % (t, bad[:6])
+        assert m["cce"].tobytes() == d["cce"][t].tobytes()
+        assert m["consumed"] == int(d["pkt_sizes"][t])
+    fe.close()
+
+
+def test_frontend_pce_in_band_equals_pce_in_extradata():
+    """ADTS with channel_configuration 0: the layout arrives as a PCE inside the first raw_data_block (aacdec.c:2012-2030).
+    Same frames as with the PCE in the extradata; a PCE repeated in later frames is stepped over."""
+    import lc_writer
+    d = _cce_golden()
+    et = [int(x) for x in d["elem_types"]]
+    pce = lc_writer.pce_element(int(d["sr_index"]), et)
+    a, b = hb.Frontend(d["extradata"].tobytes()), hb.Frontend(b"", 0, 0)
+    assert b.ncc == 0
+    for t, p in enumerate(golden_packets(d)):
+        ma = a.parse(p)
+        mb = b.parse(adts_wrap((pce if t % 3 == 0 else b"") + p, int(d["sr_index"]), 0))
+        assert b.from_pce and b.elem_types == et
+        for k in ("coeffs", "ics", "tns", "cce"):
+            assert ma[k].tobytes() == mb[k].tobytes(), (t, k)
+        assert mb["consumed"] == 7 + (len(pce) if t % 3 == 0 else 0) + len(p)
+    a.close(); b.close()
+    c = hb.Frontend(b"", 48000, 0)
+    with pytest.raises(hb.HeaacError):                  # a channel element before any configuration
+        c.parse(adts_wrap(golden_packets(d)[0], 3, 0))
+    c.close()
+
+
+def test_frontend_rejects_dependent_coupling():
+    """Only independently switched coupling is inside the ABI: ind_sw_cce_flag = 0 -> HEAAC_E_UNSUPPORTED."""
+    d = _cce_golden()
+    fe = hb.Frontend(d["extradata"].tobytes())
+    import lc_writer
+    et = [int(x) for x in d["elem_types"]]
+    w = lc_writer.LcWriter(1, 3, et)
+    w.set_coupling({2: [(0, 2)], 3: [(1, 0)]})
+    w.cce_ind_sw = 0
+    with pytest.raises(hb.HeaacError) as e:
+        fe.parse(w.frame())
+    assert e.value.code == -38                        # HEAAC_E_UNSUPPORTED
+    fe.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,layout,coupling", [
+    (31, [0, 1, 3, 2], {3: [(1, 1), (0, 2)]}),                         # SCE CPE LFE + one CCE: right channel only, then the SCE
+    (32, [1, 1, 2, 2, 2], {2: [(0, 3), (1, 3)], 3: [(0, 0)], 4: [(1, 2), (0, 1)]}),   # two CPEs, three CCEs, every ch_select
+    (33, [0, 2], {1: [(0, 2)]}),
+])
+def test_frontend_matches_reference_parser_on_fresh_coupling_streams(seed, layout, coupling):
+    """Other layouts and target selections, against the reference's parsers run here (oracle/_ref): every ch_select value
+    (both channels with one gain, left only, right only, both with their own gains), several CCEs onto one target."""
+    import lc_writer
+    import pyref
+    ed, ids, order = lc_writer.pce_config(3, layout)
+    w = lc_writer.LcWriter(seed, 3, layout, tns_prob=0.3, short_bias=0.3)
+    w.set_coupling(coupling)
+    pk = [w.frame() for _ in range(12)]
+    lay = ([layout[e] for e in order], [ids[e] for e in order])
+    nout = sum(2 if t == abi.TYPE_CPE else 1 for t in layout if t != abi.TYPE_CCE)
+    ref = pyref.Decoder(ed, 48000, nout, lay, float_mode=True)
+    fe = hb.Frontend(ed)
+    assert fe.elem_types == lay[0]
+    for t, p in enumerate(pk):
+        r, m = ref.decode(p), fe.parse(p)
+        bad = diff_parsed(r, m, fe.ncc, False, False)
+        assert not bad, "seed %d frame %d: %s" % (seed, t, bad[:6])
+        assert r["cce"].tobytes() == m["cce"].tobytes(), (seed, t, r["cce"], m["cce"])
+        assert r["consumed"] == m["consumed"]
+    ref.close(); fe.close()
+
+
+def test_frontend_plus_oracle_reproduces_reference_pcm_with_coupling():
+    """End to end without the reference on the path: own front end (PCE layout, CCEs) -> oracle back end -> PCM, against the
+    reference decoder's PCM of the same packets."""
+    d = _cce_golden()
+    fe = hb.Frontend(d["extradata"].tobytes())
+    frames = [fe.parse(p) for p in golden_packets(d)]
+    st = lambda k: np.ascontiguousarray(np.stack([f[k] for f in frames])[:, None])
+    cfg = abi.make_config(1, fe.elem_types, fe.sr_index, max_frames=len(frames), out_slots=None)
+    fe.close()
+    orc = pyoracle.Oracle(cfg)
+    pcm, f32 = orc.synth(st("coeffs"), st("ics"), st("tns"), None, None, cce=st("cce"))
+    orc.close()
+    scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
+    assert float(np.abs(f32[:, 0].astype(np.float64) - d["pcm_f32"]).max()) / scale <= 1e-5
+    assert int(np.abs(pcm[:, 0].astype(np.int32) - d["pcm_s16"]).max()) <= 1
