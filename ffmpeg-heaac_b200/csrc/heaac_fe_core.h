@@ -274,22 +274,15 @@ FE_FN int set_layout(FE *fe, int chan_config)
     return 0;
 }
 
-#ifndef FE_DEVICE
-/* program_config_element (ISO/IEC 14496-3 table 4.2; decode_pce, aacdec.c:280-340).  The reference marks che_pos[type][tag]
- * for every listed element and then walks tags 0..15 x types SCE, CPE, CCE, LFE to allocate elements and number the output
- * channels (output_configure, aacdec.c:246-262): the layout built here is that walk -- elements ordered by (tag, type), output
- * channels in element order, coupling channels without an output of their own.
- * apply != 0: make it the stream's layout; 0: only step over it (a further PCE of a configured stream is not evaluated,
- * aacdec.c:2020-2030).  Returns 0 or a negative HEAAC_E_* code. */
-FE_FN int fe_pce(FE *fe, BR *b, int apply)
+/* program_config_element (ISO/IEC 14496-3 table 4.2; decode_pce, aacdec.c:280-340): reads the element and marks the listed
+ * (type, tag) pairs in `present` (NULL: only steps over it -- a further PCE of a configured stream is not evaluated,
+ * aacdec.c:2020-2030; that is all the device build needs).  Returns 0 or a negative HEAAC_E_* code. */
+FE_BIG int fe_pce_read(BR *b, uint8_t (*present)[16])
 {
-    uint8_t present[4][16];
-    memset(present, 0, sizeof(present));
     br_skip(b, 2);                                                 /* object_type */
     br_skip(b, 4);                                                 /* sampling_frequency_index (the container's wins, a mismatch is only a warning) */
     int count[6];                                                  /* front, side, back, lfe, assoc_data, cc */
-    static const int width[6] = { 4, 4, 4, 2, 3, 4 };
-    for (int i = 0; i < 6; i++) count[i] = br_get(b, width[i]);
+    for (int i = 0; i < 6; i++) count[i] = br_get(b, i == 3 ? 2 : i == 4 ? 3 : 4);
     if (br_get1(b)) br_skip(b, 4);                                 /* mono_mixdown */
     if (br_get1(b)) br_skip(b, 4);                                 /* stereo_mixdown */
     if (br_get1(b)) br_skip(b, 3);                                 /* matrix_mixdown */
@@ -298,12 +291,26 @@ FE_FN int fe_pce(FE *fe, BR *b, int apply)
             if (grp == 4) { br_skip(b, 4); continue; }             /* associated data elements */
             const int flag = grp == 3 ? 0 : br_get1(b), tag = br_get(b, 4);
             const int type = grp == 3 ? HEAAC_TYPE_LFE : grp == 5 ? HEAAC_TYPE_CCE : flag ? HEAAC_TYPE_CPE : HEAAC_TYPE_SCE;
-            present[type][tag] = 1;                                /* (cc_element_is_ind_sw is not kept: every CCE says so itself) */
+            if (present) present[type][tag] = 1;                   /* (cc_element_is_ind_sw is not kept: every CCE says so itself) */
         }
     b->pos = (b->pos + 7) & ~7;
     const int comment = 8 * br_get(b, 8);
     if (br_left(b) < comment) return HEAAC_E_INVAL;
     br_skip(b, comment);
+    return 0;
+}
+
+#ifndef FE_DEVICE
+/* The reference marks che_pos[type][tag] for every element a PCE lists and then walks tags 0..15 x types SCE, CPE, CCE, LFE
+ * to allocate elements and number the output channels (output_configure, aacdec.c:246-262): the layout built here is that
+ * walk -- elements ordered by (tag, type), output channels in element order, coupling channels without an output of their own.
+ * apply != 0: make it the stream's layout; 0: only step over it. */
+FE_FN int fe_pce(FE *fe, BR *b, int apply)
+{
+    uint8_t present[4][16];
+    memset(present, 0, sizeof(present));
+    int r = fe_pce_read(b, apply ? present : NULL);
+    if (r) return r;
     if (!apply) return 0;
     int n = 0, ncc = 0, nse = 0, n_cce = 0;
     for (int tag = 0; tag < 16; tag++)
@@ -1217,8 +1224,10 @@ FE_INL int fe_parse_frame_x(FE *fe, const uint8_t *pkt, int size, float *coeffs,
         case 5:                                                    /* in band: configures a stream nothing else has configured */
             r = fe_pce(fe, b, !fe->n_elems && !fe->locked && !fe->layout_fixed);
             break;
+#else
+        case 5: r = fe_pce_read(b, NULL); break;                   /* the stream is configured: stepped over */
 #endif
-        default: return HEAAC_E_UNSUPPORTED;                       /* device build: CCE, PCE */
+        default: return HEAAC_E_UNSUPPORTED;                       /* CCE outside a PCE layout (device build: any CCE) */
         }
         if (r) return r;
         if (type <= 3) { prev_elem = e; prev_type = type; } else if (type != 6) { prev_elem = -1; prev_type = type; }
