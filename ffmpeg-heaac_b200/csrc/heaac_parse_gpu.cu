@@ -24,6 +24,13 @@
 #include "heaac_context.cuh"
 #include "heaac_fe_core.h"
 
+/* pipeline trace (event times of every chunk on stderr): a debug build only, -DHEAAC_DEBUG_TIMING (make EXTRA=-DHEAAC_DEBUG_TIMING) */
+#ifdef HEAAC_DEBUG_TIMING
+#define HEAAC_DBG_TIMING 1
+#else
+#define HEAAC_DBG_TIMING 0
+#endif
+
 extern "C" const void *heaac_fe_tables_blob(size_t *bytes);
 extern "C" size_t heaac_fe_state_size(void);
 extern "C" const void *heaac_fe_state_blob(const HeaacFrontend *fe);
@@ -228,7 +235,7 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
     }
 #undef CKP
     if (r) { parser_free(p); return r; }
-    if (getenv("HEAAC_DEBUG_TIMING")) {
+    if (HEAAC_DBG_TIMING) {
         p->dbg_on = 1;
         cudaEventCreate(&p->dbg_base);
         for (int i = 0; i < 64; i++) for (int k = 0; k < 4; k++) cudaEventCreate(&p->dbg_ev[i][k]);
@@ -273,7 +280,7 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
         memcpy(p->user_consumed[slot], p->h_consumed[slot], (size_t)p->user_n[slot] * sizeof(int));
         p->user_consumed[slot] = nullptr;
     }
-    static const int dbg = getenv("HEAAC_DEBUG_TIMING") != nullptr;
+    const int dbg = HEAAC_DBG_TIMING;
     double t_sync = 0, t_gather = 0, t_submit = 0, t_wait = 0;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     for (int f0 = 0; f0 < n_frames; f0 += Tc, c->seq++) {
