@@ -40,6 +40,12 @@
 #define FE_INL static inline __attribute__((always_inline))
 #define FE_BIG static
 #endif
+/* lanes of a warp that walk a structure together (second step of the SBR payload, packing): host = one lane */
+#ifdef FE_DEVICE
+#define FE_SYNCWARP() __syncwarp()
+#else
+#define FE_SYNCWARP() ((void)0)
+#endif
 
 /* ---------------------------------------------------------------- bit reader */
 /* MSB-first, with a 64-bit window held in registers: `cache` = bits [cpos, cpos + 64) of the packet, cpos a
@@ -218,6 +224,16 @@ typedef struct FePs {
     int8_t iid[5][34], icc[5][34], ipd[5][34], opd[5][34];
 } FePs;
 
+/* What one SBR payload says, before it meets the element's running state (see "SBR payload, in two steps") */
+typedef struct FeSbrTape {
+    int header;                                 /* a header came with the payload: hdr[] (SBH_*) */
+    int hdr[11];
+    int status;                                 /* TAPE_* */
+    int coupling;
+    int ext_pos, ext_left;                      /* extension blocks behind the data: bit position and size in bits */
+    FeSbrCh ch[2];                              /* grid, flags, rows 1.. of env / noise (time-coded rows as differences) */
+} FeSbrTape;
+
 /* What the stateless first phase of the two-phase parse (fe_phase_a / fe_phase_b below) leaves for the second. */
 #define FE_MAX_TODO 8
 typedef struct FeTodo {
@@ -248,6 +264,7 @@ struct HeaacFrontend {
     int elem_tag[HEAAC_MAX_ELEMS];
     int n_cce;
     HeaacCce cce[FE_MAX_CCE];                   /* coupling side info of the last parsed frame, one per CCE in layout order */
+    FeSbrTape tape;                             /* the one-pass parser's tape */
 };
 typedef struct HeaacFrontend FE;
 
@@ -708,21 +725,56 @@ FE_BIG int sbr_tables(FE *fe, FeSbr *s)                           /* sbr_reset, 
     return 0;
 }
 
-FE_FN void sbr_header(FE *fe, FeSbr *s, BR *b)                   /* read_sbr_header, aacsbr.c:207-259 */
+/* ---------------------------------------------------------------- SBR payload, in two steps
+ * An SBR payload is read in two steps that meet at a FeSbrTape:
+ *   sbr_*_bits   what the payload SAYS, read with nothing from the previous frame: the header fields, the time grid, the
+ *                difference-coded envelope / noise rows with the differences along frequency already summed up and the
+ *                differences along time left as differences.  Needs only the band counts of the element's tables (which
+ *                change with a header that changes them, and with nothing else);
+ *   sbr_*_apply  folds a tape into the element's running state: previous-frame bookkeeping of the grid, time differences
+ *                added to the row before, last row carried over.  No bits are read; the rows are walked by `nl` cooperating
+ *                lanes (host: lane 0 of 1; device: the 32 lanes of the stream's warp).
+ * The one-pass parser runs both per payload.  The device front end runs the first step for all frames of a chunk at once,
+ * one frame per lane, and the second in frame order (fe_chunk_b). */
+enum { SBH_AMP_RES, SBH_START, SBH_STOP, SBH_XOVER, SBH_FREQ_SCALE, SBH_ALTER_SCALE, SBH_NOISE_BANDS,
+       SBH_LIM_BANDS, SBH_LIM_GAINS, SBH_INTERPOL, SBH_SMOOTHING, SBH_COUNT };
+enum { TAPE_DATA = 0,       /* ch[] hold the frame's data */
+       TAPE_NONE = 1,       /* the element has not seen a header yet: the payload carries nothing to read */
+       TAPE_BAD = 2,        /* invalid grid */
+       TAPE_STALE = 3,      /* a header that changes how the data is read: the payload has to go through the one-pass parser */
+       TAPE_SKIP = 4 };     /* a payload the frame parser steps over (nothing before it to attach it to, behind an LFE) */
+
+FE_FN void sbr_header_bits(BR *b, int *h)                         /* read_sbr_header, aacsbr.c:207-259 */
 {
-    int old[6] = { s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale, s->noise_bands };
-    int old_lim = s->limiter_bands;
-    s->start = 1;
-    s->amp_res_header = br_get1(b);
-    s->start_freq = br_get(b, 4); s->stop_freq = br_get(b, 4); s->xover = br_get(b, 3);
+    h[SBH_AMP_RES] = br_get1(b);
+    h[SBH_START] = br_get(b, 4); h[SBH_STOP] = br_get(b, 4); h[SBH_XOVER] = br_get(b, 3);
     br_skip(b, 2);
-    int extra1 = br_get1(b), extra2 = br_get1(b);
-    if (extra1) { s->freq_scale = br_get(b, 2); s->alter_scale = br_get1(b); s->noise_bands = br_get(b, 2); }
-    else { s->freq_scale = 2; s->alter_scale = 1; s->noise_bands = 2; }
-    int now[6] = { s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale, s->noise_bands };
-    for (int i = 0; i < 6; i++) if (old[i] != now[i]) s->reset = 1;
-    if (extra2) { s->limiter_bands = br_get(b, 2); s->limiter_gains = br_get(b, 2); s->interpol_freq = br_get1(b); s->smoothing_mode = br_get1(b); }
-    else { s->limiter_bands = 2; s->limiter_gains = 2; s->interpol_freq = 1; s->smoothing_mode = 1; }
+    const int extra1 = br_get1(b), extra2 = br_get1(b);
+    if (extra1) { h[SBH_FREQ_SCALE] = br_get(b, 2); h[SBH_ALTER_SCALE] = br_get1(b); h[SBH_NOISE_BANDS] = br_get(b, 2); }
+    else { h[SBH_FREQ_SCALE] = 2; h[SBH_ALTER_SCALE] = 1; h[SBH_NOISE_BANDS] = 2; }
+    if (extra2) { h[SBH_LIM_BANDS] = br_get(b, 2); h[SBH_LIM_GAINS] = br_get(b, 2); h[SBH_INTERPOL] = br_get1(b); h[SBH_SMOOTHING] = br_get1(b); }
+    else { h[SBH_LIM_BANDS] = 2; h[SBH_LIM_GAINS] = 2; h[SBH_INTERPOL] = 1; h[SBH_SMOOTHING] = 1; }
+}
+
+/* 1 if the element, as it stands, reads its data the way a stream with header h does (same amplitude resolution, same tables) */
+FE_FN int sbr_header_same(const FeSbr *s, const int *h)
+{
+    return s->start && s->amp_res_header == h[SBH_AMP_RES] && s->start_freq == h[SBH_START] && s->stop_freq == h[SBH_STOP] &&
+           s->xover == h[SBH_XOVER] && s->freq_scale == h[SBH_FREQ_SCALE] && s->alter_scale == h[SBH_ALTER_SCALE] &&
+           s->noise_bands == h[SBH_NOISE_BANDS];
+}
+
+FE_FN void sbr_header_apply(FE *fe, FeSbr *s, const int *h)
+{
+    if (s->start_freq != h[SBH_START] || s->stop_freq != h[SBH_STOP] || s->xover != h[SBH_XOVER] ||
+        s->freq_scale != h[SBH_FREQ_SCALE] || s->alter_scale != h[SBH_ALTER_SCALE] || s->noise_bands != h[SBH_NOISE_BANDS]) s->reset = 1;
+    const int old_lim = s->limiter_bands;
+    s->start = 1;
+    s->amp_res_header = h[SBH_AMP_RES];
+    s->start_freq = h[SBH_START]; s->stop_freq = h[SBH_STOP]; s->xover = h[SBH_XOVER];
+    s->freq_scale = h[SBH_FREQ_SCALE]; s->alter_scale = h[SBH_ALTER_SCALE]; s->noise_bands = h[SBH_NOISE_BANDS];
+    s->limiter_bands = h[SBH_LIM_BANDS]; s->limiter_gains = h[SBH_LIM_GAINS];
+    s->interpol_freq = h[SBH_INTERPOL]; s->smoothing_mode = h[SBH_SMOOTHING];
     if (s->limiter_bands != old_lim && !s->reset) {               /* sbr_make_f_tablelim only */
         HeaacSbrElem t = s->t;
         if (!fe_sbr_tables(fe->sample_rate, s->start_freq, s->stop_freq, s->xover, s->freq_scale, s->alter_scale,
@@ -736,13 +788,12 @@ FE_FN void sbr_header(FE *fe, FeSbr *s, BR *b)                   /* read_sbr_hea
 /* The time grid of a channel (ISO/IEC 14496-3 4.6.18.3.3; what read_sbr_grid yields, aacsbr.c:609-749).  The four frame classes
  * differ only in which ends of the frame are VARIABLE: class bit 1 = the leading border, bit 0 = the trailing one.  A variable end
  * sends its absolute border and a count of relative borders that step inwards from it by 2 r + 2 slots each; a fixed end sits
- * at slot 0 / 16.  With both ends fixed the envelopes divide the frame evenly instead. */
-FE_FN int sbr_grid(FeSbr *s, FeSbrCh *c, BR *b)
+ * at slot 0 / 16.  With both ends fixed the envelopes divide the frame evenly instead.
+ * Fills the grid fields of a tape channel (freq_res[1..], t_env, t_q, e_a[1]); what the grid takes over from the previous frame
+ * (freq_res[0], e_a[0], t_env_num_env_old) is sbr_chan_apply's. */
+FE_FN int sbr_grid_bits(FeSbrCh *c, BR *b, int amp_res_header)
 {
-    const int num_env_old = c->num_env;
-    c->freq_res[0] = c->freq_res[c->num_env];
-    c->amp_res = s->amp_res_header;
-    c->t_env_num_env_old = c->t_env[num_env_old];
+    c->amp_res = amp_res_header;
     const int cls = c->frame_class = br_get(b, 2);
     const int var_lead = cls >> 1, var_trail = cls & 1;
     unsigned ptr = 0;
@@ -790,82 +841,83 @@ FE_FN int sbr_grid(FeSbr *s, FeSbrCh *c, BR *b)
             at = ptr == 0 ? 1u : ptr == 1 ? (unsigned)n - 1u : ptr - 1u;
         c->t_q[1] = c->t_env[at];
     }
-    /* the envelope that starts at a transient (l_A), and whether the previous frame's one ended exactly at the frame border */
-    c->e_a[0] = -(c->e_a[1] != num_env_old);
+    /* the envelope that starts at a transient (l_A) */
     c->e_a[1] = -1;
     if (var_trail && ptr) c->e_a[1] = n + 1 - (int)ptr;
     else if (cls == 2 && ptr > 1) c->e_a[1] = (int)ptr - 1;
     return 0;
 }
 
-FE_FN void sbr_copy_grid(FeSbrCh *d, const FeSbrCh *s)           /* copy_sbr_grid, aacsbr.c:751-766 */
-{
-    d->freq_res[0] = d->freq_res[d->num_env];
-    d->t_env_num_env_old = d->t_env[d->num_env];
-    d->e_a[0] = -(d->e_a[1] != d->num_env);
-    memcpy(d->freq_res + 1, s->freq_res + 1, 6);
-    memcpy(d->t_env, s->t_env, sizeof(d->t_env));
-    memcpy(d->t_q, s->t_q, 3);
-    d->num_env = s->num_env; d->amp_res = s->amp_res; d->num_noise = s->num_noise;
-    d->frame_class = s->frame_class; d->e_a[1] = s->e_a[1];
-}
-
-FE_FN void sbr_dtdf(FeSbrCh *c, BR *b)
+FE_FN void sbr_dtdf_bits(FeSbrCh *c, BR *b)
 {
     for (int i = 0; i < c->num_env; i++) c->df_env[i] = br_get1(b);
     for (int i = 0; i < c->num_noise; i++) c->df_noise[i] = br_get1(b);
 }
-FE_FN void sbr_invf(FeSbr *s, FeSbrCh *c, BR *b)
-{
-    memcpy(c->invf[1], c->invf[0], 5);
-    for (int i = 0; i < s->t.n_q; i++) c->invf[0][i] = br_get(b, 2);
-}
 
 /* One matrix of delta-coded SBR parameters -- envelope scalefactors or noise floors (ISO/IEC 14496-3 4.6.18.3.5; what
  * read_sbr_envelope / read_sbr_noise yield, aacsbr.c:787-890).  Row r + 1 is coded either along FREQUENCY (a start value of
- * `start_bits`, then Huffman-coded differences between neighbouring bands) or along TIME (differences to row r).  The two rows of
- * a time difference may sit on different band tables (res[]: 0 = low, 1 = high resolution): a high band then refers to the low
- * band that contains it, a low band to the high band it starts with (`odd`: the high table has an odd number of bands, so the
- * pairing is shifted by one).  Every value is scaled by `scale` (2 for the balance channel of a coupled pair).  Row 0 receives a
- * copy of the last row: the base of the next frame's first time difference. */
-FE_FN void sbr_delta_rows(BR *b, int16_t *m, int stride, int rows, const uint8_t *along_time, const uint8_t *res,
-                          int n_low, int n_high, int odd, int tab_time, int tab_freq, int start_bits, int scale)
+ * `start_bits`, then Huffman-coded differences between neighbouring bands: summed up here) or along TIME (differences to row
+ * r: left as differences here).  Every value is scaled by `scale` (2 for the balance channel of a coupled pair). */
+FE_FN void sbr_rows_bits(BR *b, int16_t *m, int stride, int rows, const uint8_t *along_time, const uint8_t *res,
+                         int n_low, int n_high, int tab_time, int tab_freq, int start_bits, int scale)
 {
     for (int r = 0; r < rows; r++) {
         int16_t *cur = m + (r + 1) * stride;
-        const int16_t *prev = m + r * stride;
-        const int hi = res[r + 1], n = hi ? n_high : n_low;
+        const int n = res[r + 1] ? n_high : n_low;
         if (along_time[r]) {
-            const int same = res[r + 1] == res[r];
-            for (int j = 0; j < n; j++) {
-                const int ref = same ? j : hi ? (j + odd) >> 1 : (j ? 2 * j - odd : 0);
-                cur[j] = (int16_t)(prev[ref] + scale * (vlc_get(b, &TB->vsbr[tab_time]) - sbr_lav[tab_time]));
-            }
+            for (int j = 0; j < n; j++) cur[j] = (int16_t)(scale * (vlc_get(b, &TB->vsbr[tab_time]) - sbr_lav[tab_time]));
         } else {
-            cur[0] = (int16_t)(scale * br_get(b, start_bits));
-            for (int j = 1; j < n; j++)
-                cur[j] = (int16_t)(cur[j - 1] + scale * (vlc_get(b, &TB->vsbr[tab_freq]) - sbr_lav[tab_freq]));
+            int v = scale * (int)br_get(b, start_bits);
+            cur[0] = (int16_t)v;
+            for (int j = 1; j < n; j++) {
+                v = (int16_t)(v + scale * (vlc_get(b, &TB->vsbr[tab_freq]) - sbr_lav[tab_freq]));
+                cur[j] = (int16_t)v;
+            }
         }
     }
 }
 
-FE_FN void sbr_envelope(FeSbr *s, FeSbrCh *c, BR *b, int ch)
+/* The second step for such a matrix: rows along time are added to the row before them.  The two rows may sit on different band
+ * tables (res[]: 0 = low, 1 = high resolution; res[0] = the last row of the previous frame): a high band then refers to the
+ * low band that contains it, a low band to the high band it starts with (`odd`: the high table has an odd number of bands, so
+ * the pairing is shifted by one).  Row 0 receives a copy of the last row: the base of the next frame's first time difference. */
+FE_FN void sbr_rows_apply(int16_t *m, const int16_t *tape, int stride, int rows, const uint8_t *along_time, const uint8_t *res,
+                          int n_low, int n_high, int odd, int lane, int nl)
 {
-    const int balance = s->coupling && ch, fine = !c->amp_res;          /* 1.5 dB steps need one more start bit and their own tables */
-    const int tab_time = balance ? (fine ? T_ENV_BAL_15 : T_ENV_BAL_30) : (fine ? T_ENV_15 : T_ENV_30);
-    const int tab_freq = balance ? (fine ? F_ENV_BAL_15 : F_ENV_BAL_30) : (fine ? F_ENV_15 : F_ENV_30);
-    sbr_delta_rows(b, &c->env[0][0], 48, c->num_env, c->df_env, c->freq_res, s->t.n[0], s->t.n[1], s->t.n[1] & 1,
-                   tab_time, tab_freq, (balance ? 5 : 6) + fine, (ch == 1 && s->coupling == 1) + 1);
-    fe_copy32(c->env[0], c->env[c->num_env], (int)(sizeof(c->env[0]) / 4));
+    for (int r = 0; r < rows; r++) {
+        int16_t *cur = m + (r + 1) * stride;
+        const int16_t *prev = m + r * stride, *in = tape + (r + 1) * stride;
+        const int hi = res[r + 1], n = hi ? n_high : n_low;
+        const int time = along_time[r], same = res[r + 1] == res[r];
+        for (int j = lane; j < n; j += nl) {
+            int v = in[j];
+            if (time) {
+                const int ref = same ? j : hi ? (j + odd) >> 1 : (j ? 2 * j - odd : 0);
+                v = (int16_t)(prev[ref] + v);
+            }
+            cur[j] = (int16_t)v;
+        }
+        FE_SYNCWARP();
+    }
+    for (int j = lane; j < stride; j += nl) m[j] = m[rows * stride + j];
+    FE_SYNCWARP();
 }
 
-FE_FN void sbr_noise(FeSbr *s, FeSbrCh *c, BR *b, int ch)
+FE_FN void sbr_envelope_bits(const FeSbr *s, FeSbrCh *c, BR *b, int ch, int coupling)
 {
-    const int balance = s->coupling && ch;
+    const int balance = coupling && ch, fine = !c->amp_res;              /* 1.5 dB steps need one more start bit and their own tables */
+    const int tab_time = balance ? (fine ? T_ENV_BAL_15 : T_ENV_BAL_30) : (fine ? T_ENV_15 : T_ENV_30);
+    const int tab_freq = balance ? (fine ? F_ENV_BAL_15 : F_ENV_BAL_30) : (fine ? F_ENV_15 : F_ENV_30);
+    sbr_rows_bits(b, &c->env[0][0], 48, c->num_env, c->df_env, c->freq_res, s->t.n[0], s->t.n[1],
+                  tab_time, tab_freq, (balance ? 5 : 6) + fine, balance + 1);
+}
+
+FE_FN void sbr_noise_bits(const FeSbr *s, FeSbrCh *c, BR *b, int ch, int coupling)
+{
+    const int balance = coupling && ch;
     const uint8_t one_table[4] = { 0, 0, 0, 0 };                         /* noise floors all sit on the noise band table */
-    sbr_delta_rows(b, &c->noise[0][0], 5, c->num_noise, c->df_noise, one_table, s->t.n_q, s->t.n_q, 0,
-                   balance ? T_NOISE_BAL_30 : T_NOISE_30, balance ? F_ENV_BAL_30 : F_ENV_30, 5, (ch == 1 && s->coupling == 1) + 1);
-    memcpy(c->noise[0], c->noise[c->num_noise], sizeof(c->noise[0]));
+    sbr_rows_bits(b, &c->noise[0][0], 5, c->num_noise, c->df_noise, one_table, s->t.n_q, s->t.n_q,
+                  balance ? T_NOISE_BAL_30 : T_NOISE_30, balance ? F_ENV_BAL_30 : F_ENV_30, 5, balance + 1);
 }
 
 /* ---------------------------------------------------------------- PS (ff_ps_read_data, aacps.c:150-279) */
@@ -981,62 +1033,165 @@ err:
 }
 
 /* ---------------------------------------------------------------- SBR payload */
-FE_FN int sbr_data(FE *fe, FeSbr *s, BR *b, int is_cpe)          /* read_sbr_data, aacsbr.c:982-1021 */
+/* sbr_data (read_sbr_data, aacsbr.c:982-1021), first step: the payload behind the header into the tape.  `s` is only read: the
+ * band counts of its tables and the header's amplitude resolution.  Returns 0, or -1 for an invalid grid. */
+FE_FN int sbr_data_bits(const FeSbr *s, BR *b, int is_cpe, FeSbrTape *t)
 {
+    FeSbrCh *c0 = &t->ch[0], *c1 = &t->ch[1];
+    const int n_q = s->t.n_q, n_high = s->t.n[1];
+    t->coupling = 0;
     if (!is_cpe) {
         if (br_get1(b)) br_skip(b, 4);
-        if (sbr_grid(s, &s->ch[0], b)) return -1;
-        sbr_dtdf(&s->ch[0], b); sbr_invf(s, &s->ch[0], b);
-        sbr_envelope(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[0], b, 0);
-        if ((s->ch[0].add_harmonic_flag = br_get1(b))) for (int i = 0; i < s->t.n[1]; i++) s->ch[0].add_harmonic[i] = br_get1(b);
+        if (sbr_grid_bits(c0, b, s->amp_res_header)) return -1;
+        sbr_dtdf_bits(c0, b);
+        for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+        sbr_envelope_bits(s, c0, b, 0, 0); sbr_noise_bits(s, c0, b, 0, 0);
     } else {
         if (br_get1(b)) br_skip(b, 8);
-        if ((s->coupling = br_get1(b))) {
-            if (sbr_grid(s, &s->ch[0], b)) return -1;
-            sbr_copy_grid(&s->ch[1], &s->ch[0]);
-            sbr_dtdf(&s->ch[0], b); sbr_dtdf(&s->ch[1], b);
-            sbr_invf(s, &s->ch[0], b);
-            memcpy(s->ch[1].invf[1], s->ch[1].invf[0], 5);
-            memcpy(s->ch[1].invf[0], s->ch[0].invf[0], 5);
-            sbr_envelope(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[0], b, 0);
-            sbr_envelope(s, &s->ch[1], b, 1); sbr_noise(s, &s->ch[1], b, 1);
+        if ((t->coupling = br_get1(b))) {
+            if (sbr_grid_bits(c0, b, s->amp_res_header)) return -1;
+            /* the second channel shares the grid (copy_sbr_grid, aacsbr.c:751-766) */
+            c1->frame_class = c0->frame_class; c1->num_env = c0->num_env; c1->num_noise = c0->num_noise; c1->amp_res = c0->amp_res;
+            c1->e_a[1] = c0->e_a[1];
+            memcpy(c1->freq_res, c0->freq_res, sizeof(c0->freq_res));
+            memcpy(c1->t_env, c0->t_env, sizeof(c0->t_env));
+            memcpy(c1->t_q, c0->t_q, sizeof(c0->t_q));
+            sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
+            for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+            sbr_envelope_bits(s, c0, b, 0, 1); sbr_noise_bits(s, c0, b, 0, 1);
+            sbr_envelope_bits(s, c1, b, 1, 1); sbr_noise_bits(s, c1, b, 1, 1);
         } else {
-            if (sbr_grid(s, &s->ch[0], b) || sbr_grid(s, &s->ch[1], b)) return -1;
-            sbr_dtdf(&s->ch[0], b); sbr_dtdf(&s->ch[1], b);
-            sbr_invf(s, &s->ch[0], b); sbr_invf(s, &s->ch[1], b);
-            sbr_envelope(s, &s->ch[0], b, 0); sbr_envelope(s, &s->ch[1], b, 1);
-            sbr_noise(s, &s->ch[0], b, 0); sbr_noise(s, &s->ch[1], b, 1);
+            if (sbr_grid_bits(c0, b, s->amp_res_header) || sbr_grid_bits(c1, b, s->amp_res_header)) return -1;
+            sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
+            for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+            for (int i = 0; i < n_q; i++) c1->invf[0][i] = br_get(b, 2);
+            sbr_envelope_bits(s, c0, b, 0, 0); sbr_envelope_bits(s, c1, b, 1, 0);
+            sbr_noise_bits(s, c0, b, 0, 0); sbr_noise_bits(s, c1, b, 1, 0);
         }
-        for (int c = 0; c < 2; c++)
-            if ((s->ch[c].add_harmonic_flag = br_get1(b))) for (int i = 0; i < s->t.n[1]; i++) s->ch[c].add_harmonic[i] = br_get1(b);
     }
-    if (br_get1(b)) {                                              /* bs_extended_data */
+    for (int c = 0; c <= is_cpe; c++)
+        if ((t->ch[c].add_harmonic_flag = br_get1(b))) for (int i = 0; i < n_high; i++) t->ch[c].add_harmonic[i] = br_get1(b);
+    t->ext_pos = t->ext_left = 0;
+    if (br_get1(b)) {                                              /* bs_extended_data: noted, read by sbr_ext_apply */
         int left = br_get(b, 4);
         if (left == 15) left += br_get(b, 8);
-        left <<= 3;
-        while (left > 7) {
-            left -= 2;
-            int id = br_get(b, 2);
-            if (id == 2 && fe->ps == 1) left -= ps_read(&fe->psx, b, left);     /* EXTENSION_ID_PS */
-            else { br_skip(b, left); left = 0; }
-        }
-        if (left > 0) br_skip(b, left);
+        t->ext_left = left << 3;
+        t->ext_pos = b->pos;
     }
     return 0;
 }
 
-FE_FN void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cpe)   /* ff_decode_sbr_extension, aacsbr.c:1044-1086 */
+/* second step for one channel: the tape's grid and rows into the running state (read_sbr_grid's and copy_sbr_grid's
+ * previous-frame bookkeeping, read_sbr_invf's mode history, the time differences).  twin: the second channel of a coupled
+ * pair takes ALL its inverse filtering modes from the first channel's state (aacsbr.c:1006-1007). */
+FE_FN void sbr_chan_apply(const FeSbr *s, FeSbrCh *c, const FeSbrCh *t, const FeSbrCh *twin, int lane, int nl)
+{
+    const int num_env_old = c->num_env;
+    const int res_old = c->freq_res[num_env_old], t_old = c->t_env[num_env_old], e_a_old = -(c->e_a[1] != num_env_old);
+    const int n_q = s->t.n_q, n_high = s->t.n[1];
+    FE_SYNCWARP();                                                 /* every lane has the old values */
+    if (lane == 0) {
+        c->frame_class = t->frame_class; c->num_env = t->num_env; c->num_noise = t->num_noise; c->amp_res = t->amp_res;
+        c->add_harmonic_flag = t->add_harmonic_flag;
+        c->e_a[0] = e_a_old; c->e_a[1] = t->e_a[1];
+        c->t_env_num_env_old = t_old;
+        c->freq_res[0] = (uint8_t)res_old;
+    }
+    for (int i = lane; i < 8; i += nl) {
+        if (i) c->freq_res[i] = t->freq_res[i];
+        c->t_env[i] = t->t_env[i];
+        if (i < 4) c->t_q[i] = t->t_q[i];
+        if (i < 5) {
+            c->df_env[i] = t->df_env[i];
+            c->invf[1][i] = c->invf[0][i];
+            if (twin) c->invf[0][i] = twin->invf[0][i];
+            else if (i < n_q) c->invf[0][i] = t->invf[0][i];
+        }
+        if (i < 2) c->df_noise[i] = t->df_noise[i];
+    }
+    if (t->add_harmonic_flag) for (int i = lane; i < n_high; i += nl) c->add_harmonic[i] = t->add_harmonic[i];
+    uint8_t res[8];
+    res[0] = (uint8_t)res_old;
+    for (int e = 1; e < 8; e++) res[e] = t->freq_res[e];
+    const uint8_t one_table[4] = { 0, 0, 0, 0 };
+    sbr_rows_apply(&c->env[0][0], &t->env[0][0], 48, t->num_env, t->df_env, res, s->t.n[0], n_high, n_high & 1, lane, nl);
+    sbr_rows_apply(&c->noise[0][0], &t->noise[0][0], 5, t->num_noise, t->df_noise, one_table, n_q, n_q, 0, lane, nl);
+}
+
+FE_FN void sbr_data_apply(FeSbr *s, const FeSbrTape *t, int is_cpe, int lane, int nl)
+{
+    if (lane == 0 && is_cpe) s->coupling = t->coupling;
+    sbr_chan_apply(s, &s->ch[0], &t->ch[0], NULL, lane, nl);
+    if (is_cpe) sbr_chan_apply(s, &s->ch[1], &t->ch[1], t->coupling ? &s->ch[0] : NULL, lane, nl);
+}
+
+/* the extension blocks behind the SBR data (aacsbr.c:1009-1019 region): Parametric Stereo is the one that is read */
+FE_FN void sbr_ext_apply(FE *fe, BR *b, const FeSbrTape *t)
+{
+    int left = t->ext_left;
+    if (left <= 7 || fe->ps != 1) return;                          /* nothing but bits to step over */
+    b->pos = t->ext_pos;
+    while (left > 7) {
+        left -= 2;
+        int id = br_get(b, 2);
+        if (id == 2) left -= ps_read(&fe->psx, b, left);          /* EXTENSION_ID_PS */
+        else { br_skip(b, left); left = 0; }
+    }
+}
+
+/* ff_decode_sbr_extension (aacsbr.c:1044-1086), one pass: both steps for one payload */
+FE_FN void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cpe)
 {
     BR bb = *host, *b = &bb;
+    FeSbrTape *t = &fe->tape;
     host->pos += cnt * 8 - 4;
     s->reset = 0;
     if (!fe->ext_sample_rate) fe->ext_sample_rate = 2 * fe->sample_rate;
     if (crc) br_skip(b, 10);
     s->t.kx[0] = s->t.kx[1];
     s->t.m[0] = s->t.m[1];
-    if (br_get1(b)) sbr_header(fe, s, b);
+    if (br_get1(b)) { sbr_header_bits(b, t->hdr); sbr_header_apply(fe, s, t->hdr); }
     if (s->reset && sbr_tables(fe, s)) s->start = 0;               /* "pure upsampling mode" */
-    if (s->start && sbr_data(fe, s, b, is_cpe)) s->start = 0;
+    if (!s->start) return;
+    if (sbr_data_bits(s, b, is_cpe, t)) { s->start = 0; return; }
+    sbr_data_apply(s, t, is_cpe, 0, 1);
+    sbr_ext_apply(fe, b, t);
+}
+
+/* The first step alone, for a payload whose frame is not the stream's current one (the device front end: all frames of a chunk
+ * at once).  `s` is the element as the chunk's earlier frames will have left it PROVIDED none of them changes how data is read:
+ * a header that does makes the tape TAPE_STALE, and the caller sends the payload through sbr_extension when its turn comes. */
+FE_FN void sbr_tape_bits(const FeSbr *s, BR *host, int crc, int is_cpe, FeSbrTape *t)
+{
+    BR bb = *host, *b = &bb;
+    if (crc) br_skip(b, 10);
+    if ((t->header = br_get1(b))) {
+        sbr_header_bits(b, t->hdr);
+        if (!sbr_header_same(s, t->hdr)) { t->status = TAPE_STALE; return; }
+    }
+    if (!s->start) { t->status = TAPE_NONE; return; }
+    t->status = sbr_data_bits(s, b, is_cpe, t) ? TAPE_BAD : TAPE_DATA;
+}
+
+/* ... and the second step for such a tape, by nl cooperating lanes (scalars by lane 0) */
+FE_FN void sbr_tape_apply(FE *fe, FeSbr *s, const uint8_t *pkt, int size, int is_cpe, const FeSbrTape *t, int lane, int nl)
+{
+    if (lane == 0) {
+        s->reset = 0;
+        if (!fe->ext_sample_rate) fe->ext_sample_rate = 2 * fe->sample_rate;
+        s->t.kx[0] = s->t.kx[1];
+        s->t.m[0] = s->t.m[1];
+        if (t->header) sbr_header_apply(fe, s, t->hdr);           /* same tables: no reset */
+    }
+    FE_SYNCWARP();
+    if (!s->start || t->status == TAPE_NONE) return;
+    if (t->status == TAPE_BAD) { FE_SYNCWARP(); if (lane == 0) s->start = 0; return; }
+    sbr_data_apply(s, t, is_cpe, lane, nl);
+    if (lane == 0) {
+        BR br;
+        br_init(&br, pkt, size);
+        sbr_ext_apply(fe, &br, t);
+    }
 }
 
 /* ---------------------------------------------------------------- frame */
