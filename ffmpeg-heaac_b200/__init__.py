@@ -40,7 +40,7 @@ EXPORTS = [
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
     "heaac_b200_sbr_init", "heaac_b200_sbr_apply", "heaac_b200_ps_apply", "heaac_b200_sbr_close",
-    "heaac_fe_cce", "heaac_fe_layout_from_pce",
+    "heaac_fe_cce", "heaac_fe_layout_from_pce", "heaac_fe_parse_chunk",
     "heaac_fe_sbr_downsampled", "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
@@ -94,6 +94,7 @@ def lib():
         L.heaac_fe_fix_layout.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_sbr_downsampled.argtypes = [C.c_void_p]
         L.heaac_fe_cce.argtypes = [C.c_void_p, C.c_void_p]
+        L.heaac_fe_parse_chunk.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         L.heaac_fe_layout_from_pce.argtypes = [C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
@@ -323,6 +324,22 @@ class Frontend:
         if self.n_cce:                                 # coupling side info of this frame (HeaacBatch.cce)
             r["cce"] = np.zeros(self.n_cce, abi.CCE)
             lib().heaac_fe_cce(self.h, r["cce"].ctypes.data)
+        return r
+
+    def parse_chunk(self, pkts):
+        """Up to 32 consecutive packets the way the device front end treats a chunk (heaac_fe_parse_chunk).  Returns
+        dict(coeffs [T,ncc,1024], ics [T,ncc], tns [T,ncc], sbr [T,nse], ps [T], consumed [T]); a failed frame has
+        consumed < 0 and zeroed outputs.  The layout must be known (extradata)."""
+        T, ncc, nse = len(pkts), self.ncc, max(self.nse, 1)
+        bufs = [np.frombuffer(p, np.uint8) for p in pkts]
+        ptrs = (C.c_void_p * T)(*[b.ctypes.data for b in bufs])
+        sizes = np.asarray([b.size for b in bufs], np.int32)
+        r = {"coeffs": np.zeros((T, ncc, 1024), np.float32), "ics": np.zeros((T, ncc), ICS), "tns": np.zeros((T, ncc), TNS),
+             "sbr": np.zeros((T, nse), SBR_ELEM), "ps": np.zeros(T, PS_FRAME), "consumed": np.zeros(T, np.int32)}
+        _check(lib().heaac_fe_parse_chunk(self.h, T, C.cast(ptrs, C.c_void_p), sizes.ctypes.data, r["coeffs"].ctypes.data,
+                                          r["ics"].ctypes.data, r["tns"].ctypes.data, r["sbr"].ctypes.data,
+                                          r["ps"].ctypes.data, r["consumed"].ctypes.data), "heaac_fe_parse_chunk")
+        self._refresh()
         return r
 
     def close(self):

@@ -205,6 +205,7 @@ typedef struct FeChan {
 typedef struct FeSbrCh {
     int frame_class, num_env, num_noise, amp_res, add_harmonic_flag;
     uint8_t freq_res[8], t_env[8], t_q[4], add_harmonic[48] /* 4-byte aligned */, df_env[5], df_noise[2], invf[2][5];
+    uint8_t q_at;                               /* tapes: the border (index into t_env) where the second noise floor starts */
     int e_a[2], t_env_num_env_old;
     int16_t env[6][48], noise[3][5];            /* row 0 = last row of the previous frame (delta-time base) */
 } FeSbrCh;
@@ -839,7 +840,9 @@ FE_FN int sbr_grid_bits(FeSbrCh *c, BR *b, int amp_res_header)
             at = (unsigned)n - (back > 1u ? back : 1u);
         } else
             at = ptr == 0 ? 1u : ptr == 1 ? (unsigned)n - 1u : ptr - 1u;
-        c->t_q[1] = c->t_env[at];
+        /* `at` can be n + 1 (pointer 0): the reference then reads the entry behind the frame's last border, i.e. whatever an
+         * earlier frame left there (aacsbr.c:729-733) -- so the border is looked up when the grid meets the element's state */
+        c->q_at = (uint8_t)at;
     }
     /* the envelope that starts at a transient (l_A) */
     c->e_a[1] = -1;
@@ -1097,19 +1100,30 @@ FE_FN void sbr_chan_apply(const FeSbr *s, FeSbrCh *c, const FeSbrCh *t, const Fe
         c->t_env_num_env_old = t_old;
         c->freq_res[0] = (uint8_t)res_old;
     }
+    const int n_env = t->num_env, n_noise = t->num_noise;            /* only what the payload holds: the tape's other entries are stale */
     for (int i = lane; i < 8; i += nl) {
-        if (i) c->freq_res[i] = t->freq_res[i];
-        c->t_env[i] = t->t_env[i];
-        if (i < 4) c->t_q[i] = t->t_q[i];
+        if (twin) {                                                /* copy_sbr_grid, aacsbr.c:751-766 */
+            if (i >= 1 && i <= 6) c->freq_res[i] = twin->freq_res[i];
+            c->t_env[i] = twin->t_env[i];
+            if (i < 3) c->t_q[i] = twin->t_q[i];
+        } else {
+            if (i && i <= n_env) c->freq_res[i] = t->freq_res[i];
+            if (i <= n_env) c->t_env[i] = t->t_env[i];
+            if (i == 0 || i == n_noise) c->t_q[i] = t->t_q[i];
+        }
+        if (i < n_env) c->df_env[i] = t->df_env[i];
+        if (i < n_noise) c->df_noise[i] = t->df_noise[i];
         if (i < 5) {
-            c->df_env[i] = t->df_env[i];
             c->invf[1][i] = c->invf[0][i];
             if (twin) c->invf[0][i] = twin->invf[0][i];
             else if (i < n_q) c->invf[0][i] = t->invf[0][i];
         }
-        if (i < 2) c->df_noise[i] = t->df_noise[i];
     }
     if (t->add_harmonic_flag) for (int i = lane; i < n_high; i += nl) c->add_harmonic[i] = t->add_harmonic[i];
+    if (!twin && n_noise > 1) {                                    /* the second noise floor's border, from the borders as they stand now */
+        FE_SYNCWARP();
+        if (lane == 0) c->t_q[1] = c->t_env[t->q_at < 8 ? t->q_at : 7];
+    }
     uint8_t res[8];
     res[0] = (uint8_t)res_old;
     for (int e = 1; e < 8; e++) res[e] = t->freq_res[e];
@@ -1433,16 +1447,19 @@ FE_FN void fe_phase_a(const FE *stream, FE *scratch, FeTodo *todo, const uint8_t
     scratch->phase_a = 1; scratch->saw_pns = 0; scratch->todo = todo;
     todo->serial = 0; todo->n_sbr = 0;
     for (int c = 0; c < FE_MAX_CH; c++) todo->chan[c] = 0;
+#ifndef FE_DEVICE
+    scratch->by_tag = 0;                                           /* (beyond the head that was copied) */
+    if (stream->by_tag) { todo->serial = 1; todo->result = 0; return; }    /* program config element layouts: one-pass parser only */
+#endif
     todo->result = fe_parse_frame_x(scratch, pkt, size, coeffs, ics, tns, NULL, NULL, 1);
     if (todo->result < 0 || scratch->saw_pns || scratch->ncc != stream->ncc) todo->serial = 1;
     else
         for (int c = 0; c < stream->ncc; c++) if (!todo->chan[c]) fe_zero(coeffs + 1024 * c, 1024);
 }
 
-FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
-                     HeaacSbrElem *sbr, HeaacPsFrame *ps)
+/* previous-window bookkeeping of the frame phase A has parsed (ics_info and the common_window copy of decode_cpe) */
+FE_FN void fe_windows_b(FE *fe, const FeTodo *todo, HeaacIcs *ics)
 {
-    if (todo->serial) return fe_parse_frame(fe, pkt, size, coeffs, ics, tns, sbr, ps);
     for (int c = 0; c < fe->ncc; c++) {
         FeChan *st = &fe->ch[c];
         if (todo->chan[c] == 1) {
@@ -1457,6 +1474,13 @@ FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, f
         }
         ics[c].prev_valid = 1; ics[c].prev_window_sequence = (uint8_t)st->ws[1]; ics[c].prev_window_shape = (uint8_t)st->shape[1];
     }
+}
+
+FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
+                     HeaacSbrElem *sbr, HeaacPsFrame *ps)
+{
+    if (todo->serial) return fe_parse_frame(fe, pkt, size, coeffs, ics, tns, sbr, ps);
+    fe_windows_b(fe, todo, ics);
     if (todo->n_sbr) {
         BR br;
         br_init(&br, pkt, size);
@@ -1468,6 +1492,125 @@ FE_FN int fe_phase_b(FE *fe, const FeTodo *todo, const uint8_t *pkt, int size, f
     fe->locked = 1;
     fe_pack_l(fe, sbr, ps, 0, 1);
     return todo->result;
+}
+
+/* ---------------------------------------------------------------- phase B for a whole chunk of one stream
+ * The SBR payloads of a chunk's frames are read in two steps (see "SBR payload, in two steps"): the first step for ALL frames
+ * that are still to do at once -- one frame per lane -- against the element states as they stand; then the frames are finished
+ * in order: window bookkeeping, the second step of their payloads (the lanes walk the rows together), Parametric Stereo,
+ * packing.  A frame that has to go through the one-pass parser (fe_phase_b: flagged by phase A, or with a header that changes
+ * how SBR data is read) is done by lane 0 alone; if it changed what the tapes of the later frames were read with, those are
+ * read again.  Frame f's packet and outputs sit at index f * stride of the arrays (device: stride = streams of the batch). */
+typedef struct FeChunkIO {
+    int n_frames, ncc, nse;
+    size_t stride;
+    const FeTodo *todo;                         /* [n_frames], this stream's */
+    FeSbrTape *tape; int tapes_per_frame;       /* [n_frames][tapes_per_frame], this stream's */
+    const uint8_t *blob; const uint32_t *off; const int *size;
+    float *coeffs; HeaacIcs *ics; HeaacTns *tns; HeaacSbrElem *sbr; HeaacPsFrame *ps; int *consumed;
+} FeChunkIO;
+
+#ifdef FE_DEVICE
+#define FE_BCAST(v) __shfl_sync(0xffffffffu, (v), 0)
+#else
+#define FE_BCAST(v) (v)
+#endif
+
+/* everything of an element's state the first step reads */
+FE_FN uint64_t fe_sbr_reads(const FeSbr *s)
+{
+    return (uint64_t)(s->start & 1) | (uint64_t)(s->amp_res_header & 1) << 1 | (uint64_t)(s->start_freq & 15) << 2 |
+           (uint64_t)(s->stop_freq & 15) << 6 | (uint64_t)(s->xover & 7) << 10 | (uint64_t)(s->freq_scale & 3) << 13 |
+           (uint64_t)(s->alter_scale & 1) << 15 | (uint64_t)(s->noise_bands & 3) << 16 |
+           (uint64_t)(s->t.n[0] & 255) << 18 | (uint64_t)(s->t.n[1] & 255) << 26 | (uint64_t)(s->t.n_q & 255) << 34;
+}
+FE_FN int fe_sbr_elem_of(const FE *fe, int elem)
+{
+    int se = 0;
+    for (int i = 0; i < elem; i++) se += fe->elem_type[i] != HEAAC_TYPE_LFE;
+    return se;
+}
+
+FE_FN void fe_chunk_b(FE *fe, const FeChunkIO *io, int lane, int nl)
+{
+    const int n = io->n_frames, P = io->tapes_per_frame, ncc = io->ncc, nse = io->nse;
+    int k = 0;
+    while (k < n) {
+        const int taped = fe->sbr == 1;
+        if (taped)
+            for (int f = k + lane; f < n; f += nl) {               /* first step, one frame per lane */
+                const FeTodo *td = io->todo + f;
+                if (td->serial || td->n_sbr > P) continue;
+                BR br;
+                br_init(&br, io->blob + io->off[(size_t)f * io->stride], io->size[(size_t)f * io->stride]);
+                for (int p = 0; p < td->n_sbr; p++) {
+                    FeSbrTape *t = io->tape + (size_t)f * P + p;
+                    const int pe = td->sbr[p].prev_elem, pt = td->sbr[p].prev_type;
+                    if (pe < 0 || pt == HEAAC_TYPE_LFE) { t->status = TAPE_SKIP; continue; }
+                    br.pos = td->sbr[p].pos;
+                    sbr_tape_bits(&fe->sbr_el[fe_sbr_elem_of(fe, pe)], &br, td->sbr[p].crc, pt == 1, t);
+                }
+            }
+        FE_SYNCWARP();
+        int again = 0;
+        for (; k < n && !again; k++) {                             /* the frames in order */
+            const FeTodo *td = io->todo + k;
+            const size_t idx = (size_t)k * io->stride;
+            const uint8_t *pkt = io->blob + io->off[idx];
+            const int size = io->size[idx];
+            float *co = io->coeffs + idx * ncc * 1024;
+            HeaacIcs *ic = io->ics + idx * ncc;
+            HeaacTns *tn = io->tns + idx * ncc;
+            HeaacSbrElem *sb = io->sbr ? io->sbr + idx * nse : NULL;
+            HeaacPsFrame *pp = io->ps ? io->ps + idx : NULL;
+            int serial = !taped || td->serial || td->n_sbr > P, r;
+            if (!serial)
+                for (int p = 0; p < td->n_sbr; p++) serial |= io->tape[(size_t)k * P + p].status == TAPE_STALE;
+            if (serial) {
+                /* can this frame change what the first step reads?  only while SBR payloads are read at all */
+                const int live = k + 1 < n && (fe->sbr == 1 || (fe->sbr == -1 && !fe->locked));
+                const int sbr_before = fe->sbr;
+                uint64_t before[HEAAC_MAX_ELEMS];
+                if (live) for (int e = 0; e < nse; e++) before[e] = fe_sbr_reads(&fe->sbr_el[e]);
+                FE_SYNCWARP();
+                r = 0;
+                if (lane == 0) {
+                    r = fe_phase_b(fe, td, pkt, size, co, ic, tn, NULL, NULL);
+                    if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;   /* layout differs from the batch's */
+                    io->consumed[idx] = r;
+                }
+                FE_SYNCWARP();
+                r = FE_BCAST(r);
+                if (live) {
+                    again = fe->sbr != sbr_before;
+                    for (int e = 0; e < nse; e++) again |= before[e] != fe_sbr_reads(&fe->sbr_el[e]);
+                }
+            } else {
+                if (lane == 0) fe_windows_b(fe, td, ic);
+                for (int p = 0; p < td->n_sbr; p++) {
+                    const FeSbrTape *t = io->tape + (size_t)k * P + p;
+                    if (t->status == TAPE_SKIP) continue;
+                    if (lane == 0 && fe->ps == -1 && !fe->locked && fe->ncc == 1) fe->ps = 1;   /* implicit signalling, aacdec.c:1659-1676 */
+                    sbr_tape_apply(fe, &fe->sbr_el[fe_sbr_elem_of(fe, td->sbr[p].prev_elem)], pkt, size, td->sbr[p].prev_type == 1,
+                                   t, lane, nl);
+                    FE_SYNCWARP();
+                }
+                r = fe->ncc != ncc ? HEAAC_E_INVAL : td->result;
+                if (lane == 0) { fe->locked = 1; io->consumed[idx] = r; }
+            }
+            FE_SYNCWARP();                                         /* lane 0's state writes before the other lanes' reads */
+            if (r >= 0) {
+                fe_pack_l(fe, sb, pp, lane, nl);
+            } else {                                               /* silent frame; the batch goes on */
+                for (int i = lane; i < ncc * 1024; i += nl) co[i] = 0.0f;
+                for (int i = lane; i < (int)(sizeof(HeaacIcs) * ncc / 4); i += nl) ((uint32_t *)ic)[i] = 0;
+                for (int i = lane; i < (int)(sizeof(HeaacTns) * ncc / 4); i += nl) ((uint32_t *)tn)[i] = 0;
+                if (sb) for (int i = lane; i < (int)(sizeof(HeaacSbrElem) * nse / 4); i += nl) ((uint32_t *)sb)[i] = 0;
+                if (pp) for (int i = lane; i < (int)(sizeof(HeaacPsFrame) / 4); i += nl) ((uint32_t *)pp)[i] = 0;
+            }
+            FE_SYNCWARP();                                         /* the pack reads state the next frame overwrites */
+        }
+    }
 }
 
 #endif

@@ -263,3 +263,44 @@ int heaac_fe_cce(const FE *fe, HeaacCce *out)
 /* 1 when the layout came from a program config element: elements -- and output channels -- are then in the reference's
  * (instance tag, type) order and HeaacConfig.out_slot is the identity */
 int heaac_fe_layout_from_pce(const FE *fe) { return fe && fe->by_tag; }
+
+/* The device front end's handling of a chunk (phase A for every frame, then fe_chunk_b: the SBR payloads' first step for all
+ * frames at once, the rest in frame order), run on the host with one lane: same results as n_frames calls of heaac_fe_parse by
+ * construction -- tests hold it to that, including what a failed frame leaves behind (consumed[f] < 0, silent frame).
+ * Arrays are frame-major for the layout `fe` has (coeffs [n_frames][ncc][1024], ics / tns [n_frames][ncc], sbr
+ * [n_frames][n_sbr_elems] or NULL, ps [n_frames] or NULL); n_frames <= 32; the layout must be known (extradata). */
+int heaac_fe_parse_chunk(FE *fe, int n_frames, const uint8_t *const *pkt, const int *size, float *coeffs, HeaacIcs *ics,
+                         HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
+{
+    if (!fe || !pkt || !size || !coeffs || !ics || !tns || !consumed || n_frames < 1 || n_frames > 32 || !fe->ncc) return HEAAC_E_INVAL;
+    const int ncc = fe->ncc, nse = fe->nse, P = nse > 0 ? nse : 1;
+    size_t total = 0;
+    uint32_t off[32];
+    for (int f = 0; f < n_frames; f++) {
+        if (size[f] <= 0 || !pkt[f]) return HEAAC_E_INVAL;
+        off[f] = (uint32_t)total;
+        total += ((size_t)size[f] + 15) & ~(size_t)7;
+    }
+    uint8_t *blob = (uint8_t *)calloc(1, total + 8);
+    FE *scratch = (FE *)malloc(sizeof(FE));
+    FeTodo *todo = (FeTodo *)calloc(n_frames, sizeof(FeTodo));
+    FeSbrTape *tape = (FeSbrTape *)calloc((size_t)n_frames * P, sizeof(FeSbrTape));
+    int r = HEAAC_E_NOMEM;
+    if (blob && scratch && todo && tape) {
+        for (int f = 0; f < n_frames; f++) {
+            memcpy(blob + off[f], pkt[f], size[f]);
+            fe_phase_a(fe, scratch, &todo[f], blob + off[f], size[f], coeffs + (size_t)f * ncc * 1024, ics + (size_t)f * ncc,
+                       tns + (size_t)f * ncc);
+        }
+        FeChunkIO io;
+        memset(&io, 0, sizeof(io));
+        io.n_frames = n_frames; io.ncc = ncc; io.nse = nse; io.stride = 1;
+        io.todo = todo; io.tape = tape; io.tapes_per_frame = P;
+        io.blob = blob; io.off = off; io.size = size;
+        io.coeffs = coeffs; io.ics = ics; io.tns = tns; io.sbr = sbr; io.ps = ps; io.consumed = consumed;
+        fe_chunk_b(fe, &io, 0, 1);
+        r = 0;
+    }
+    free(blob); free(scratch); free(todo); free(tape);
+    return r;
+}

@@ -43,6 +43,8 @@ struct HeaacGpuParser {
     uint8_t *d_scratch;              /* [S][32] frame-local parser states of phase A (head + channel blocks) */
     size_t scratch_stride;
     FeTodo *d_todo[2];               /* [S][32] per staging set: phase B of chunk k reads one while phase A of k+1 fills the other */
+    FeSbrTape *d_tape;               /* [S][32][tapes_per_frame]: the SBR payloads' first step (k_parse_b; its launches are serialised on s_b) */
+    int tapes_per_frame;
     cudaStream_t s_b;                /* phase B's stream */
     cudaEvent_t ev_a[2];             /* phase A of the chunk in staging set i is done */
     /* per staging set: packets of one chunk, 8-byte aligned and zero padded */
@@ -89,39 +91,21 @@ k_parse_a(const FE *fes, uint8_t *scratch, size_t scratch_stride, FeTodo *todo, 
 }
 
 __global__ void __launch_bounds__(HEAAC_PARSE_THREADS, HEAAC_PARSE_MIN_BLOCKS)
-k_parse_b(FE *fes, const FeTodo *todo, const uint8_t *blob, const uint32_t *off, const int *size, int n_frames, int S,
-          int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr,
-          HeaacPsFrame *ps, int *consumed)
+k_parse_b(FE *fes, const FeTodo *todo, FeSbrTape *tape, int tapes_per_frame, const uint8_t *blob, const uint32_t *off,
+          const int *size, int n_frames, int S, int ncc, int nse, int has_sbr, int has_ps, float *coeffs, HeaacIcs *ics,
+          HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= S) return;
-    FE *fe = fes + s;
-    for (int k = 0; k < n_frames; k++) {
-        const size_t idx = (size_t)k * S + s;
-        float *co = coeffs + idx * ncc * 1024;
-        HeaacIcs *ic = ics + idx * ncc;
-        HeaacTns *tn = tns + idx * ncc;
-        HeaacSbrElem *sb = has_sbr ? sbr + idx * nse : nullptr;
-        HeaacPsFrame *pp = has_ps ? ps + idx : nullptr;
-        int r = 0;
-        if (lane == 0) {                                            /* sequential part; packing left to the whole warp */
-            r = fe_phase_b(fe, todo + (size_t)s * 32 + k, blob + off[idx], size[idx], co, ic, tn, nullptr, nullptr);
-            if (r >= 0 && fe->ncc != ncc) r = HEAAC_E_INVAL;          /* layout differs from the batch's */
-            consumed[idx] = r;
-        }
-        __syncwarp();                                               /* lane 0's state writes before the other lanes' reads */
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= 0) {
-            fe_pack_l(fe, sb, pp, lane, 32);
-        } else {                                                    /* silent frame; the batch goes on */
-            for (int i = lane; i < ncc * 1024; i += 32) co[i] = 0.0f;
-            for (int i = lane; i < (int)(sizeof(HeaacIcs) * ncc / 4); i += 32) ((uint32_t *)ic)[i] = 0;
-            for (int i = lane; i < (int)(sizeof(HeaacTns) * ncc / 4); i += 32) ((uint32_t *)tn)[i] = 0;
-            if (sb) for (int i = lane; i < (int)(sizeof(HeaacSbrElem) * nse / 4); i += 32) ((uint32_t *)sb)[i] = 0;
-            if (pp) for (int i = lane; i < (int)(sizeof(HeaacPsFrame) / 4); i += 32) ((uint32_t *)pp)[i] = 0;
-        }
-        __syncwarp();                                               /* the pack reads state the next frame's parse overwrites */
-    }
+    FeChunkIO io;
+    io.n_frames = n_frames; io.ncc = ncc; io.nse = nse; io.stride = (size_t)S;
+    io.todo = todo + (size_t)s * 32;
+    io.tape = tape + (size_t)s * 32 * tapes_per_frame; io.tapes_per_frame = tapes_per_frame;
+    io.blob = blob; io.off = off + s; io.size = size + s;
+    io.coeffs = coeffs + (size_t)s * ncc * 1024; io.ics = ics + (size_t)s * ncc; io.tns = tns + (size_t)s * ncc;
+    io.sbr = has_sbr ? sbr + (size_t)s * nse : nullptr; io.ps = has_ps ? ps + s : nullptr;
+    io.consumed = consumed + s;
+    fe_chunk_b(fes + s, &io, lane, 32);
 }
 
 static void parser_free(HeaacGpuParser *p)
@@ -143,6 +127,7 @@ static void parser_free(HeaacGpuParser *p)
     if (p->d_fe) cudaFree(p->d_fe);
     if (p->d_template) cudaFree(p->d_template);
     if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->d_tape) cudaFree(p->d_tape);
     for (int i = 0; i < 2; i++) { if (p->d_todo[i]) cudaFree(p->d_todo[i]); if (p->ev_a[i]) cudaEventDestroy(p->ev_a[i]); }
     if (p->s_b) cudaStreamDestroy(p->s_b);
     delete p;
@@ -218,6 +203,8 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
         CKP(cudaMalloc(&p->d_todo[i], S * 32 * sizeof(FeTodo)));
         CKP(cudaEventCreateWithFlags(&p->ev_a[i], cudaEventDisableTiming));
     }
+    p->tapes_per_frame = c->geom.nse > 0 ? c->geom.nse : 1;
+    CKP(cudaMalloc(&p->d_tape, (c->geom.sbr ? S * 32 * p->tapes_per_frame : 1) * sizeof(FeSbrTape)));
     CKP(cudaStreamCreateWithFlags(&p->s_b, cudaStreamNonBlocking));
     CKP(cudaMemcpy(p->d_template, heaac_fe_state_blob(fe), sizeof(FE), cudaMemcpyHostToDevice));
     for (int i = 0; i < 8; i++) CKP(cudaHostAlloc(&p->h_consumed[i], (size_t)c->cfg.max_frames_per_call * S * sizeof(int), cudaHostAllocDefault));
@@ -327,7 +314,8 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
             CK(cudaGetLastError());
             CK(cudaEventRecord(p->ev_a[buf], c->s_in));
             CK(cudaStreamWaitEvent(p->s_b, p->ev_a[buf], 0));
-            k_parse_b<<<grid, threads, 0, p->s_b>>>(p->d_fe, p->d_todo[buf], p->d_blob[buf], p->d_off[buf], p->d_size[buf], n,
+            k_parse_b<<<grid, threads, 0, p->s_b>>>(p->d_fe, p->d_todo[buf], p->d_tape, g->sbr ? p->tapes_per_frame : 0,
+                                                     p->d_blob[buf], p->d_off[buf], p->d_size[buf], n,
                                                      (int)S, g->ncc, g->nse, g->sbr, g->ps, c->s_coeffs[buf], c->s_ics[buf],
                                                      c->s_tns[buf], c->s_sbr[buf], c->s_ps[buf], p->d_consumed[buf]);
             CK(cudaGetLastError());

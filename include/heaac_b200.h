@@ -324,6 +324,12 @@ int  heaac_fe_parse(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coef
  * sequential pass over the SBR / PS payloads); same results, kept callable for tests.  tns must not be NULL. */
 int  heaac_fe_parse_two_phase(HeaacFrontend *fe, const uint8_t *pkt, int size, float *coeffs, HeaacIcs *ics, HeaacTns *tns,
                               HeaacSbrElem *sbr, HeaacPsFrame *ps);
+/* The device front end's treatment of a chunk of up to 32 consecutive frames of one stream (entropy decoding of the core elements
+ * frame by frame without the stream's history, the SBR payloads of all frames read side by side, then the frames finished in
+ * order), on the host: same results as n_frames calls of heaac_fe_parse, kept callable for tests.  Frame-major arrays for the
+ * stream's layout (which must be known: extradata); consumed[f] < 0 marks a frame that failed (its outputs are zeroed). */
+int  heaac_fe_parse_chunk(HeaacFrontend *fe, int n_frames, const uint8_t *const *pkt, const int *size, float *coeffs,
+                          HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed);
 /* 1 if the stream signals downsampled SBR (extension rate below twice the core rate): HeaacConfig.sbr_downsampled */
 int  heaac_fe_sbr_downsampled(const HeaacFrontend *fe);
 /* copy sample rate and channel layout (not the stream state) from a front end that has seen a frame */

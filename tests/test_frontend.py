@@ -392,3 +392,108 @@ def test_frontend_plus_oracle_reproduces_reference_pcm_with_coupling():
     scale = max(32768.0, float(np.abs(d["pcm_f32"]).max()))
     assert float(np.abs(f32[:, 0].astype(np.float64) - d["pcm_f32"]).max()) / scale <= 1e-5
     assert int(np.abs(pcm[:, 0].astype(np.int32) - d["pcm_s16"]).max()) <= 1
+
+
+# ---------------------------------------------------------------- a chunk of frames the way the device front end treats it
+def _fixture_or_golden(name, stream=2):
+    import os
+    from common import GOLDEN
+    if name.startswith("bench_"):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        ofs = np.concatenate([[0], np.cumsum(z["pkt_sizes"].ravel())])
+        blob = z["pkt_blob"].tobytes()
+        n = z["pkt_sizes"].shape[1]
+        pk = [blob[ofs[stream * n + i]:ofs[stream * n + i + 1]] for i in range(n)]
+        return pk + pk[:16], z["extradata"].tobytes(), int(z["core_rate"]), int(z["channels"])
+    d = load_golden(name)
+    return golden_packets(d), d["extradata"].tobytes(), int(d["core_rate"]), (d["pcm_f32"].shape[1] if not d["ps_flag"] else 1)
+
+
+def _chunk_vs_frames(pk, ed, rate, ch, chunk, what):
+    """heaac_fe_parse_chunk over `chunk` frames at a time == heaac_fe_parse frame by frame (a failed frame: same error code,
+    and the stream goes on identically)."""
+    a, b = hb.Frontend(ed, rate, ch), hb.Frontend(ed, rate, ch)
+    for t0 in range(0, len(pk), chunk):
+        part = pk[t0:t0 + chunk]
+        y = b.parse_chunk(part)
+        for i, p in enumerate(part):
+            try:
+                x = a.parse(p)
+            except hb.HeaacError as e:
+                assert int(y["consumed"][i]) == e.code, (what, t0 + i)
+                continue
+            assert x["consumed"] == int(y["consumed"][i]), (what, t0 + i, x["consumed"], int(y["consumed"][i]))
+            for k in ("coeffs", "ics"):
+                assert x[k].tobytes() == y[k][i].tobytes(), "%s frame %d: %s differs" % (what, t0 + i, k)
+            if a.sbr:
+                assert x["sbr"].tobytes() == y["sbr"][i][:len(x["sbr"])].tobytes(), "%s frame %d: sbr differs" % (what, t0 + i)
+            if a.ps:
+                assert x["ps"].tobytes() == y["ps"][i:i + 1].tobytes(), "%s frame %d: ps differs" % (what, t0 + i)
+            yi = {k: y[k][i] for k in ("coeffs", "ics", "tns", "sbr")}
+            yi["ps"] = y["ps"][i:i + 1]
+            assert not diff_parsed(x, yi, a.ncc, bool(a.sbr), bool(a.ps)), (what, t0 + i)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("chunk", [32, 7])
+@pytest.mark.parametrize("name", GOLDEN_CASES + ("bench_heaac_v1_stereo_packets", "bench_heaac_v2_ps_packets",
+                                                 "bench_lc_51_48k_tns_packets"))
+def test_chunk_parse_equals_frame_by_frame(name, chunk):
+    """The SBR payloads of a chunk read side by side (first step for all frames against the element states at the chunk's
+    start, re-read after a frame that changes them), then folded in frame order == the one-pass parser, byte for byte."""
+    pk, ed, rate, ch = _fixture_or_golden(name)
+    _chunk_vs_frames(pk, ed, rate, ch, chunk, name)
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,seed", [("v1", 301), ("v1", 302), ("v2", 303), ("v2", 304), ("51", 305)])
+def test_chunk_parse_on_long_generated_streams(mode, seed):
+    """96 frames of the stream generator (all frame classes, headers that repeat and headers that change the tables in the
+    middle of a chunk, coupling on and off, PS with 20 <-> 34 band switches), chunks of 32 and of 13."""
+    import heaac_streams as hs
+    if mode == "51":
+        pk, ed, _ = hs.make_stream_51(seed, 48)
+        rate, ch = 24000, 6
+    else:
+        pk, ed, _ = hs.make_stream(seed, 96, stereo=mode == "v1", ps=mode == "v2")
+        rate, ch = 24000, 2 if mode == "v1" else 1
+    for chunk in (32, 13):
+        _chunk_vs_frames(pk, ed, rate, ch, chunk, "%s/%d/%d" % (mode, seed, chunk))
+
+
+@pytest.mark.parametrize("name", ("heaac_v1_stereo", "heaac_v2_ps", "bench_heaac_v1_stereo_packets"))
+def test_chunk_parse_with_corrupt_packets(name):
+    """Bit flips, overwritten bytes and truncation inside a chunk: the same frames fail with the same codes, and every later
+    frame comes out as from the one-pass parser (a failed payload must leave the element state the same way in both)."""
+    pk, ed, rate, ch = _fixture_or_golden(name)
+    rng = np.random.default_rng(11)
+    bad = []
+    for t, p in enumerate(pk):
+        b = bytearray(p)
+        mode = int(rng.integers(0, 5)) if t else 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            b = b[:int(rng.integers(1, len(b)))]
+        elif mode == 2:
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        bad.append(bytes(b))
+    _chunk_vs_frames(bad, ed, rate, ch, 32, name + " corrupt")
+    _chunk_vs_frames(bad, ed, rate, ch, 5, name + " corrupt")
+
+
+@needs_ref
+@pytest.mark.parametrize("stereo", [True, False])
+def test_chunk_parse_when_a_header_changes_the_tables_inside_a_chunk(stereo):
+    """Three generated streams with different SBR headers (start / stop frequency, crossover band, header period) spliced at
+    frames 41 and 70: the frames behind a splice were read side by side with the OLD band counts, so they have to be read again
+    once the frame with the new header has gone through the one-pass parser -- and the limiter-bands-only change (a header
+    that differs in its second half only) must not trigger that."""
+    import heaac_streams as hs
+    a, ed, _ = hs.make_stream(401, 41, stereo=stereo, ps=not stereo, start_freq=5, stop_freq=9, header_period=8)
+    b, _, _ = hs.make_stream(402, 29, stereo=stereo, ps=not stereo, start_freq=4, stop_freq=7, xover=1, header_period=5)
+    c, _, _ = hs.make_stream(403, 30, stereo=stereo, ps=not stereo, start_freq=3, stop_freq=6, header_period=16)
+    pk = a + b + c
+    for chunk in (32, 16, 9):
+        _chunk_vs_frames(pk, ed, 24000, 2 if stereo else 1, chunk, "spliced/%d" % chunk)
