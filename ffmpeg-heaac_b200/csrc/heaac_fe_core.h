@@ -40,9 +40,11 @@
 #define FE_INL static inline __attribute__((always_inline))
 #define FE_BIG static
 #endif
-/* lanes of a warp that walk a structure together (second step of the SBR payload, packing): host = one lane */
+/* lanes of a warp that walk a structure together (second step of the SBR payload, packing); `nl` = the number of cooperating
+ * lanes in scope: 1 on the host, and on the device where lane 0 goes through the one-pass parser alone (no barrier there: the
+ * other lanes are not in that code) */
 #ifdef FE_DEVICE
-#define FE_SYNCWARP() __syncwarp()
+#define FE_SYNCWARP() do { if (nl > 1) __syncwarp(); } while (0)
 #else
 #define FE_SYNCWARP() ((void)0)
 #endif
@@ -1038,7 +1040,7 @@ err:
 /* ---------------------------------------------------------------- SBR payload */
 /* sbr_data (read_sbr_data, aacsbr.c:982-1021), first step: the payload behind the header into the tape.  `s` is only read: the
  * band counts of its tables and the header's amplitude resolution.  Returns 0, or -1 for an invalid grid. */
-FE_FN int sbr_data_bits(const FeSbr *s, BR *b, int is_cpe, FeSbrTape *t)
+FE_INL int sbr_data_bits(const FeSbr *s, BR *b, int is_cpe, FeSbrTape *t)
 {
     FeSbrCh *c0 = &t->ch[0], *c1 = &t->ch[1];
     const int n_q = s->t.n_q, n_high = s->t.n[1];
@@ -1154,7 +1156,7 @@ FE_FN void sbr_ext_apply(FE *fe, BR *b, const FeSbrTape *t)
 }
 
 /* ff_decode_sbr_extension (aacsbr.c:1044-1086), one pass: both steps for one payload */
-FE_FN void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cpe)
+FE_BIG void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_cpe)
 {
     BR bb = *host, *b = &bb;
     FeSbrTape *t = &fe->tape;
