@@ -40,7 +40,7 @@ EXPORTS = [
     "heaac_dec_submit", "heaac_dec_wait", "heaac_b200_parser_submit", "heaac_b200_parser_wait",
     "heaac_b200_ticket", "heaac_b200_ticket_wait", "heaac_b200_sbr_tables_device",
     "heaac_b200_sbr_init", "heaac_b200_sbr_apply", "heaac_b200_ps_apply", "heaac_b200_sbr_close",
-    "heaac_fe_cce", "heaac_fe_layout_from_pce", "heaac_fe_parse_chunk",
+    "heaac_fe_cce", "heaac_fe_layout_from_pce", "heaac_fe_parse_chunk", "heaac_fe_chunk_stats",
     "heaac_fe_sbr_downsampled", "heaac_adts_write_header", "heaac_adts_parse_header", "heaac_adts_split", "heaac_esds_find_asc",
 ]
 
@@ -95,6 +95,8 @@ def lib():
         L.heaac_fe_sbr_downsampled.argtypes = [C.c_void_p]
         L.heaac_fe_cce.argtypes = [C.c_void_p, C.c_void_p]
         L.heaac_fe_parse_chunk.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+        L.heaac_fe_chunk_stats.argtypes = [C.c_void_p]
+        L.heaac_fe_chunk_stats.restype = None
         L.heaac_fe_layout_from_pce.argtypes = [C.c_void_p]
         L.heaac_fe_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p]
         L.heaac_b200_synth_submit.argtypes = [C.c_void_p, C.POINTER(Batch)]
@@ -339,6 +341,9 @@ class Frontend:
         _check(lib().heaac_fe_parse_chunk(self.h, T, C.cast(ptrs, C.c_void_p), sizes.ctypes.data, r["coeffs"].ctypes.data,
                                           r["ics"].ctypes.data, r["tns"].ctypes.data, r["sbr"].ctypes.data,
                                           r["ps"].ctypes.data, r["consumed"].ctypes.data), "heaac_fe_parse_chunk")
+        st = (C.c_int * 4)()
+        lib().heaac_fe_chunk_stats(st)
+        r["stats"] = {"passes": st[0], "one_pass_frames": st[1], "stale": st[2]}
         self._refresh()
         return r
 

@@ -1510,6 +1510,7 @@ typedef struct FeChunkIO {
     FeSbrTape *tape; int tapes_per_frame;       /* [n_frames][tapes_per_frame], this stream's */
     const uint8_t *blob; const uint32_t *off; const int *size;
     float *coeffs; HeaacIcs *ics; HeaacTns *tns; HeaacSbrElem *sbr; HeaacPsFrame *ps; int *consumed;
+    int *stats;                                 /* optional (host): [0] first-step passes, [1] frames through the one-pass parser, [2] of those: stale tapes */
 } FeChunkIO;
 
 #ifdef FE_DEVICE
@@ -1539,6 +1540,7 @@ FE_FN void fe_chunk_b(FE *fe, const FeChunkIO *io, int lane, int nl)
     int k = 0;
     while (k < n) {
         const int taped = fe->sbr == 1;
+        if (io->stats && taped) io->stats[0]++;
         if (taped)
             for (int f = k + lane; f < n; f += nl) {               /* first step, one frame per lane */
                 const FeTodo *td = io->todo + f;
@@ -1568,6 +1570,7 @@ FE_FN void fe_chunk_b(FE *fe, const FeChunkIO *io, int lane, int nl)
             int serial = !taped || td->serial || td->n_sbr > P, r;
             if (!serial)
                 for (int p = 0; p < td->n_sbr; p++) serial |= io->tape[(size_t)k * P + p].status == TAPE_STALE;
+            if (io->stats && serial) { io->stats[1]++; io->stats[2] += taped && !td->serial && td->n_sbr <= P; }
             if (serial) {
                 /* can this frame change what the first step reads?  only while SBR payloads are read at all */
                 const int live = k + 1 < n && (fe->sbr == 1 || (fe->sbr == -1 && !fe->locked));

@@ -269,6 +269,11 @@ int heaac_fe_layout_from_pce(const FE *fe) { return fe && fe->by_tag; }
  * construction -- tests hold it to that, including what a failed frame leaves behind (consumed[f] < 0, silent frame).
  * Arrays are frame-major for the layout `fe` has (coeffs [n_frames][ncc][1024], ics / tns [n_frames][ncc], sbr
  * [n_frames][n_sbr_elems] or NULL, ps [n_frames] or NULL); n_frames <= 32; the layout must be known (extradata). */
+static __thread int chunk_stats[4];
+/* how the calling thread's last heaac_fe_parse_chunk went: [0] passes of the SBR payloads' first step, [1] frames that went through
+ * the one-pass parser, [2] of those: because a header changed how SBR data is read */
+void heaac_fe_chunk_stats(int out[4]) { memcpy(out, chunk_stats, sizeof(chunk_stats)); }
+
 int heaac_fe_parse_chunk(FE *fe, int n_frames, const uint8_t *const *pkt, const int *size, float *coeffs, HeaacIcs *ics,
                          HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed)
 {
@@ -298,6 +303,8 @@ int heaac_fe_parse_chunk(FE *fe, int n_frames, const uint8_t *const *pkt, const 
         io.todo = todo; io.tape = tape; io.tapes_per_frame = P;
         io.blob = blob; io.off = off; io.size = size;
         io.coeffs = coeffs; io.ics = ics; io.tns = tns; io.sbr = sbr; io.ps = ps; io.consumed = consumed;
+        memset(chunk_stats, 0, sizeof(chunk_stats));
+        io.stats = chunk_stats;
         fe_chunk_b(fe, &io, 0, 1);
         r = 0;
     }

@@ -104,7 +104,7 @@ k_parse_b(FE *fes, const FeTodo *todo, FeSbrTape *tape, int tapes_per_frame, con
     io.blob = blob; io.off = off + s; io.size = size + s;
     io.coeffs = coeffs + (size_t)s * ncc * 1024; io.ics = ics + (size_t)s * ncc; io.tns = tns + (size_t)s * ncc;
     io.sbr = has_sbr ? sbr + (size_t)s * nse : nullptr; io.ps = has_ps ? ps + s : nullptr;
-    io.consumed = consumed + s;
+    io.consumed = consumed + s; io.stats = nullptr;
     fe_chunk_b(fes + s, &io, lane, 32);
 }
 

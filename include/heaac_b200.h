@@ -330,6 +330,9 @@ int  heaac_fe_parse_two_phase(HeaacFrontend *fe, const uint8_t *pkt, int size, f
  * stream's layout (which must be known: extradata); consumed[f] < 0 marks a frame that failed (its outputs are zeroed). */
 int  heaac_fe_parse_chunk(HeaacFrontend *fe, int n_frames, const uint8_t *const *pkt, const int *size, float *coeffs,
                           HeaacIcs *ics, HeaacTns *tns, HeaacSbrElem *sbr, HeaacPsFrame *ps, int *consumed);
+/* how the calling thread's last heaac_fe_parse_chunk went: out[0] = passes of the SBR payloads' side-by-side step, out[1] = frames
+ * that went through the one-pass parser, out[2] = of those: because their header changes how SBR data is read */
+void heaac_fe_chunk_stats(int out[4]);
 /* 1 if the stream signals downsampled SBR (extension rate below twice the core rate): HeaacConfig.sbr_downsampled */
 int  heaac_fe_sbr_downsampled(const HeaacFrontend *fe);
 /* copy sample rate and channel layout (not the stream state) from a front end that has seen a frame */
