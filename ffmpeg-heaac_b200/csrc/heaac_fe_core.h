@@ -45,8 +45,12 @@
  * other lanes are not in that code) */
 #ifdef FE_DEVICE
 #define FE_SYNCWARP() do { if (nl > 1) __syncwarp(); } while (0)
+#define FE_SYNCWARP_ALL() __syncwarp()
+#define FE_ANY(x) __any_sync(0xffffffffu, (x))
 #else
 #define FE_SYNCWARP() ((void)0)
+#define FE_SYNCWARP_ALL() ((void)0)
+#define FE_ANY(x) (x)
 #endif
 
 /* ---------------------------------------------------------------- bit reader */
@@ -861,26 +865,16 @@ FE_FN void sbr_dtdf_bits(FeSbrCh *c, BR *b)
 
 /* One matrix of delta-coded SBR parameters -- envelope scalefactors or noise floors (ISO/IEC 14496-3 4.6.18.3.5; what
  * read_sbr_envelope / read_sbr_noise yield, aacsbr.c:787-890).  Row r + 1 is coded either along FREQUENCY (a start value of
- * `start_bits`, then Huffman-coded differences between neighbouring bands: summed up here) or along TIME (differences to row
- * r: left as differences here).  Every value is scaled by `scale` (2 for the balance channel of a coupled pair). */
-FE_FN void sbr_rows_bits(BR *b, int16_t *m, int stride, int rows, const uint8_t *along_time, const uint8_t *res,
-                         int n_low, int n_high, int tab_time, int tab_freq, int start_bits, int scale)
-{
-    for (int r = 0; r < rows; r++) {
-        int16_t *cur = m + (r + 1) * stride;
-        const int n = res[r + 1] ? n_high : n_low;
-        if (along_time[r]) {
-            for (int j = 0; j < n; j++) cur[j] = (int16_t)(scale * (vlc_get(b, &TB->vsbr[tab_time]) - sbr_lav[tab_time]));
-        } else {
-            int v = scale * (int)br_get(b, start_bits);
-            cur[0] = (int16_t)v;
-            for (int j = 1; j < n; j++) {
-                v = (int16_t)(v + scale * (vlc_get(b, &TB->vsbr[tab_freq]) - sbr_lav[tab_freq]));
-                cur[j] = (int16_t)v;
-            }
-        }
-    }
-}
+ * `start_bits`, then Huffman-coded differences between neighbouring bands: summed up in the first step) or along TIME
+ * (differences to row r: left as differences in the first step).  Every value is scaled by `scale` (2 for the balance channel of
+ * a coupled pair).  A payload holds two to four such matrices back to back; sbr_data_bits lists them in a plan and reads them
+ * ONE VALUE PER STEP (sbr_plan_step), so that lanes reading different frames side by side stay in lockstep. */
+typedef struct SbrRows {
+    int16_t *m;
+    const uint8_t *along_time, *res;            /* per row; res[r + 1]: 0 = low, 1 = high resolution band table */
+    int stride, rows, n_low, n_high, tab_time, tab_freq, start_bits, scale;
+} SbrRows;
+FE_TAB uint8_t sbr_res_none[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };       /* noise floors all sit on the noise band table */
 
 /* The second step for such a matrix: rows along time are added to the row before them.  The two rows may sit on different band
  * tables (res[]: 0 = low, 1 = high resolution; res[0] = the last row of the previous frame): a high band then refers to the
@@ -908,21 +902,23 @@ FE_FN void sbr_rows_apply(int16_t *m, const int16_t *tape, int stride, int rows,
     FE_SYNCWARP();
 }
 
-FE_FN void sbr_envelope_bits(const FeSbr *s, FeSbrCh *c, BR *b, int ch, int coupling)
+FE_FN void sbr_envelope_rows(SbrRows *q, const FeSbr *s, FeSbrCh *c, int ch, int coupling)
 {
     const int balance = coupling && ch, fine = !c->amp_res;              /* 1.5 dB steps need one more start bit and their own tables */
-    const int tab_time = balance ? (fine ? T_ENV_BAL_15 : T_ENV_BAL_30) : (fine ? T_ENV_15 : T_ENV_30);
-    const int tab_freq = balance ? (fine ? F_ENV_BAL_15 : F_ENV_BAL_30) : (fine ? F_ENV_15 : F_ENV_30);
-    sbr_rows_bits(b, &c->env[0][0], 48, c->num_env, c->df_env, c->freq_res, s->t.n[0], s->t.n[1],
-                  tab_time, tab_freq, (balance ? 5 : 6) + fine, balance + 1);
+    q->m = &c->env[0][0]; q->stride = 48; q->rows = c->num_env; q->along_time = c->df_env; q->res = c->freq_res;
+    q->n_low = s->t.n[0]; q->n_high = s->t.n[1];
+    q->tab_time = balance ? (fine ? T_ENV_BAL_15 : T_ENV_BAL_30) : (fine ? T_ENV_15 : T_ENV_30);
+    q->tab_freq = balance ? (fine ? F_ENV_BAL_15 : F_ENV_BAL_30) : (fine ? F_ENV_15 : F_ENV_30);
+    q->start_bits = (balance ? 5 : 6) + fine; q->scale = balance + 1;
 }
 
-FE_FN void sbr_noise_bits(const FeSbr *s, FeSbrCh *c, BR *b, int ch, int coupling)
+FE_FN void sbr_noise_rows(SbrRows *q, const FeSbr *s, FeSbrCh *c, int ch, int coupling)
 {
     const int balance = coupling && ch;
-    const uint8_t one_table[4] = { 0, 0, 0, 0 };                         /* noise floors all sit on the noise band table */
-    sbr_rows_bits(b, &c->noise[0][0], 5, c->num_noise, c->df_noise, one_table, s->t.n_q, s->t.n_q,
-                  balance ? T_NOISE_BAL_30 : T_NOISE_30, balance ? F_ENV_BAL_30 : F_ENV_30, 5, balance + 1);
+    q->m = &c->noise[0][0]; q->stride = 5; q->rows = c->num_noise; q->along_time = c->df_noise; q->res = sbr_res_none;
+    q->n_low = q->n_high = s->t.n_q;
+    q->tab_time = balance ? T_NOISE_BAL_30 : T_NOISE_30; q->tab_freq = balance ? F_ENV_BAL_30 : F_ENV_30;
+    q->start_bits = 5; q->scale = balance + 1;
 }
 
 /* ---------------------------------------------------------------- PS (ff_ps_read_data, aacps.c:150-279) */
@@ -1039,41 +1035,87 @@ err:
 
 /* ---------------------------------------------------------------- SBR payload */
 /* sbr_data (read_sbr_data, aacsbr.c:982-1021), first step: the payload behind the header into the tape.  `s` is only read: the
- * band counts of its tables and the header's amplitude resolution.  Returns 0, or -1 for an invalid grid. */
-FE_INL int sbr_data_bits(const FeSbr *s, BR *b, int is_cpe, FeSbrTape *t)
+ * band counts of its tables and the header's amplitude resolution.  Returns 0, or -1 for an invalid grid.
+ * wide: the 32 lanes of a warp are in here together, each with the payload of another frame (valid = 0: a lane that has none and
+ * only keeps the others company).  The envelope / noise values -- nearly all of the bits -- are then read in lockstep, one value
+ * per lane and step, until no lane has any left; grids and flags before, harmonics after are read lane by lane. */
+FE_INL int sbr_data_bits(const FeSbr *s, BR *b, int is_cpe, FeSbrTape *t, int wide, int valid)
 {
-    FeSbrCh *c0 = &t->ch[0], *c1 = &t->ch[1];
-    const int n_q = s->t.n_q, n_high = s->t.n[1];
-    t->coupling = 0;
-    if (!is_cpe) {
-        if (br_get1(b)) br_skip(b, 4);
-        if (sbr_grid_bits(c0, b, s->amp_res_header)) return -1;
-        sbr_dtdf_bits(c0, b);
-        for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
-        sbr_envelope_bits(s, c0, b, 0, 0); sbr_noise_bits(s, c0, b, 0, 0);
-    } else {
-        if (br_get1(b)) br_skip(b, 8);
-        if ((t->coupling = br_get1(b))) {
-            if (sbr_grid_bits(c0, b, s->amp_res_header)) return -1;
-            /* the second channel shares the grid (copy_sbr_grid, aacsbr.c:751-766) */
-            c1->frame_class = c0->frame_class; c1->num_env = c0->num_env; c1->num_noise = c0->num_noise; c1->amp_res = c0->amp_res;
-            c1->e_a[1] = c0->e_a[1];
-            memcpy(c1->freq_res, c0->freq_res, sizeof(c0->freq_res));
-            memcpy(c1->t_env, c0->t_env, sizeof(c0->t_env));
-            memcpy(c1->t_q, c0->t_q, sizeof(c0->t_q));
-            sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
-            for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
-            sbr_envelope_bits(s, c0, b, 0, 1); sbr_noise_bits(s, c0, b, 0, 1);
-            sbr_envelope_bits(s, c1, b, 1, 1); sbr_noise_bits(s, c1, b, 1, 1);
+    SbrRows plan[4];
+    int n_mat = 0, bad = 0;
+    if (valid) {
+        FeSbrCh *c0 = &t->ch[0], *c1 = &t->ch[1];
+        const int n_q = s->t.n_q;
+        t->coupling = 0;
+        if (!is_cpe) {
+            if (br_get1(b)) br_skip(b, 4);
+            if (sbr_grid_bits(c0, b, s->amp_res_header)) bad = 1;
+            else {
+                sbr_dtdf_bits(c0, b);
+                for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+                sbr_envelope_rows(&plan[0], s, c0, 0, 0); sbr_noise_rows(&plan[1], s, c0, 0, 0);
+                n_mat = 2;
+            }
         } else {
-            if (sbr_grid_bits(c0, b, s->amp_res_header) || sbr_grid_bits(c1, b, s->amp_res_header)) return -1;
-            sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
-            for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
-            for (int i = 0; i < n_q; i++) c1->invf[0][i] = br_get(b, 2);
-            sbr_envelope_bits(s, c0, b, 0, 0); sbr_envelope_bits(s, c1, b, 1, 0);
-            sbr_noise_bits(s, c0, b, 0, 0); sbr_noise_bits(s, c1, b, 1, 0);
+            if (br_get1(b)) br_skip(b, 8);
+            if ((t->coupling = br_get1(b))) {
+                if (sbr_grid_bits(c0, b, s->amp_res_header)) bad = 1;
+                else {
+                    /* the second channel shares the grid (copy_sbr_grid, aacsbr.c:751-766) */
+                    c1->frame_class = c0->frame_class; c1->num_env = c0->num_env; c1->num_noise = c0->num_noise; c1->amp_res = c0->amp_res;
+                    c1->e_a[1] = c0->e_a[1];
+                    memcpy(c1->freq_res, c0->freq_res, sizeof(c0->freq_res));
+                    memcpy(c1->t_env, c0->t_env, sizeof(c0->t_env));
+                    memcpy(c1->t_q, c0->t_q, sizeof(c0->t_q));
+                    sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
+                    for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+                    sbr_envelope_rows(&plan[0], s, c0, 0, 1); sbr_noise_rows(&plan[1], s, c0, 0, 1);
+                    sbr_envelope_rows(&plan[2], s, c1, 1, 1); sbr_noise_rows(&plan[3], s, c1, 1, 1);
+                    n_mat = 4;
+                }
+            } else {
+                if (sbr_grid_bits(c0, b, s->amp_res_header) || sbr_grid_bits(c1, b, s->amp_res_header)) bad = 1;
+                else {
+                    sbr_dtdf_bits(c0, b); sbr_dtdf_bits(c1, b);
+                    for (int i = 0; i < n_q; i++) c0->invf[0][i] = br_get(b, 2);
+                    for (int i = 0; i < n_q; i++) c1->invf[0][i] = br_get(b, 2);
+                    sbr_envelope_rows(&plan[0], s, c0, 0, 0); sbr_envelope_rows(&plan[1], s, c1, 1, 0);
+                    sbr_noise_rows(&plan[2], s, c0, 0, 0); sbr_noise_rows(&plan[3], s, c1, 1, 0);
+                    n_mat = 4;
+                }
+            }
         }
     }
+    /* the matrices, one value per step: (mi, r, j) = matrix, row, band of the next value; acc = the running sum of a row
+     * coded along frequency */
+    int mi = 0, r = 0, j = 0, acc = 0;
+    for (;;) {
+        while (mi < n_mat) {                                       /* step over finished rows and matrices (and empty ones) */
+            const SbrRows *q = &plan[mi];
+            if (r >= q->rows) { mi++; r = 0; j = 0; continue; }
+            if (j >= (q->res[r + 1] ? q->n_high : q->n_low)) { r++; j = 0; continue; }
+            break;
+        }
+        const int more = mi < n_mat;
+        if (!(wide ? FE_ANY(more) : more)) break;
+        if (more) {
+            const SbrRows *q = &plan[mi];
+            const int time = q->along_time[r];
+            int v;
+            if (!time && j == 0) v = q->scale * (int)br_get(b, q->start_bits);
+            else {
+                const int tab = time ? q->tab_time : q->tab_freq;
+                v = q->scale * (vlc_get(b, &TB->vsbr[tab]) - sbr_lav[tab]);
+                if (!time) v = (int16_t)(acc + v);
+            }
+            acc = v;
+            q->m[(r + 1) * q->stride + j] = (int16_t)v;
+            j++;
+        }
+        if (wide) FE_SYNCWARP_ALL();
+    }
+    if (!valid || bad) return -bad;
+    const int n_high = s->t.n[1];
     for (int c = 0; c <= is_cpe; c++)
         if ((t->ch[c].add_harmonic_flag = br_get1(b))) for (int i = 0; i < n_high; i++) t->ch[c].add_harmonic[i] = br_get1(b);
     t->ext_pos = t->ext_left = 0;
@@ -1169,7 +1211,7 @@ FE_BIG void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_c
     if (br_get1(b)) { sbr_header_bits(b, t->hdr); sbr_header_apply(fe, s, t->hdr); }
     if (s->reset && sbr_tables(fe, s)) s->start = 0;               /* "pure upsampling mode" */
     if (!s->start) return;
-    if (sbr_data_bits(s, b, is_cpe, t)) { s->start = 0; return; }
+    if (sbr_data_bits(s, b, is_cpe, t, 0, 1)) { s->start = 0; return; }
     sbr_data_apply(s, t, is_cpe, 0, 1);
     sbr_ext_apply(fe, b, t);
 }
@@ -1177,16 +1219,21 @@ FE_BIG void sbr_extension(FE *fe, FeSbr *s, BR *host, int crc, int cnt, int is_c
 /* The first step alone, for a payload whose frame is not the stream's current one (the device front end: all frames of a chunk
  * at once).  `s` is the element as the chunk's earlier frames will have left it PROVIDED none of them changes how data is read:
  * a header that does makes the tape TAPE_STALE, and the caller sends the payload through sbr_extension when its turn comes. */
-FE_FN void sbr_tape_bits(const FeSbr *s, BR *host, int crc, int is_cpe, FeSbrTape *t)
+FE_FN void sbr_tape_bits(const FeSbr *s, BR *host, int crc, int is_cpe, FeSbrTape *t, int wide, int valid)
 {
-    BR bb = *host, *b = &bb;
-    if (crc) br_skip(b, 10);
-    if ((t->header = br_get1(b))) {
-        sbr_header_bits(b, t->hdr);
-        if (!sbr_header_same(s, t->hdr)) { t->status = TAPE_STALE; return; }
+    BR bb, *b = &bb;
+    int go = 0;                                                    /* this lane has data to read */
+    if (valid) {
+        bb = *host;
+        if (crc) br_skip(b, 10);
+        if ((t->header = br_get1(b))) sbr_header_bits(b, t->hdr);
+        if (t->header && !sbr_header_same(s, t->hdr)) t->status = TAPE_STALE;
+        else if (!s->start) t->status = TAPE_NONE;
+        else go = 1;
     }
-    if (!s->start) { t->status = TAPE_NONE; return; }
-    t->status = sbr_data_bits(s, b, is_cpe, t) ? TAPE_BAD : TAPE_DATA;
+    if (!wide && !go) return;
+    const int r = sbr_data_bits(s, b, is_cpe, t, wide, go);
+    if (go) t->status = r ? TAPE_BAD : TAPE_DATA;
 }
 
 /* ... and the second step for such a tape, by nl cooperating lanes (scalars by lane 0) */
@@ -1542,17 +1589,22 @@ FE_FN void fe_chunk_b(FE *fe, const FeChunkIO *io, int lane, int nl)
         const int taped = fe->sbr == 1;
         if (io->stats && taped) io->stats[0]++;
         if (taped)
-            for (int f = k + lane; f < n; f += nl) {               /* first step, one frame per lane */
-                const FeTodo *td = io->todo + f;
-                if (td->serial || td->n_sbr > P) continue;
+            for (int f0 = k; f0 < n; f0 += nl) {                   /* first step, one frame per lane; the lanes stay together */
+                const int f = f0 + lane;
+                const FeTodo *td = io->todo + (f < n ? f : k);
+                const int use = f < n && !td->serial && td->n_sbr <= P;
                 BR br;
-                br_init(&br, io->blob + io->off[(size_t)f * io->stride], io->size[(size_t)f * io->stride]);
-                for (int p = 0; p < td->n_sbr; p++) {
-                    FeSbrTape *t = io->tape + (size_t)f * P + p;
-                    const int pe = td->sbr[p].prev_elem, pt = td->sbr[p].prev_type;
-                    if (pe < 0 || pt == HEAAC_TYPE_LFE) { t->status = TAPE_SKIP; continue; }
-                    br.pos = td->sbr[p].pos;
-                    sbr_tape_bits(&fe->sbr_el[fe_sbr_elem_of(fe, pe)], &br, td->sbr[p].crc, pt == 1, t);
+                if (use) br_init(&br, io->blob + io->off[(size_t)f * io->stride], io->size[(size_t)f * io->stride]);
+                for (int p = 0; p < P; p++) {
+                    FeSbrTape *t = io->tape + (size_t)(f < n ? f : k) * P + p;
+                    int valid = use && p < td->n_sbr, se = 0, pt = 0, crc = 0;
+                    if (valid) {
+                        const int pe = td->sbr[p].prev_elem;
+                        pt = td->sbr[p].prev_type; crc = td->sbr[p].crc;
+                        if (pe < 0 || pt == HEAAC_TYPE_LFE) { t->status = TAPE_SKIP; valid = 0; }
+                        else { br.pos = td->sbr[p].pos; se = fe_sbr_elem_of(fe, pe); }
+                    }
+                    if (valid || nl > 1) sbr_tape_bits(&fe->sbr_el[se], &br, crc, pt == 1, t, nl > 1, valid);
                 }
             }
         FE_SYNCWARP();
