@@ -1282,18 +1282,18 @@ FE_FN void pack_sbr_l(const FeSbr *s, HeaacSbrElem *o, int lane, int nl)
         if (d->add_harmonic_flag) fe_copy32_l(oc->bs_add_harmonic, d->add_harmonic, 48 / 4, lane, nl);
         else for (int i = lane; i < 48 / 4; i += nl) ((uint32_t *)oc->bs_add_harmonic)[i] = 0;
         fe_copy32_l(oc->env_q, d->env[1], 5 * 48 * 2 / 4, lane, nl);
-        if (lane == 0) {
-            fe_zero32(oc, 40 / 4);                                     /* everything before bs_add_harmonic */
-            oc->bs_num_env = d->num_env; oc->bs_num_noise = d->num_noise; oc->bs_amp_res = d->amp_res;
-            oc->bs_add_harmonic_flag = d->add_harmonic_flag;
-            oc->e_a[0] = d->e_a[0]; oc->e_a[1] = d->e_a[1]; oc->t_env_num_env_old = d->t_env_num_env_old;
-            for (int i = 0; i < 7; i++) oc->bs_freq_res[i] = d->freq_res[i];
-            for (int i = 0; i < 8; i++) oc->t_env[i] = d->t_env[i];
-            for (int i = 0; i < 3; i++) oc->t_q[i] = d->t_q[i];
-            for (int i = 0; i < 5; i++) { oc->bs_invf_mode[0][i] = d->invf[0][i]; oc->bs_invf_mode[1][i] = d->invf[1][i]; }
-            for (int e = 0; e < 2; e++) for (int k = 0; k < 5; k++) oc->noise_q[e][k] = d->noise[e + 1][k];
-            fe_zero32(oc->reserved2, 1);
+        /* the 40 bytes before bs_add_harmonic, one byte per lane and turn */
+        for (int i = lane; i < 40; i += nl) {
+            int v = 0;
+            if (i >= 28) { if (i < 38) v = d->invf[(i - 28) / 5][(i - 28) % 5]; }
+            else if (i >= 24) { if (i < 27) v = d->t_q[i - 24]; }
+            else if (i >= 16) v = d->t_env[i - 16];
+            else if (i >= 8) { if (i < 15) v = d->freq_res[i - 8]; }
+            else v = i == 0 ? d->num_env : i == 1 ? d->num_noise : i == 2 ? d->amp_res : i == 3 ? d->add_harmonic_flag :
+                     i == 4 ? d->e_a[0] : i == 5 ? d->e_a[1] : i == 6 ? d->t_env_num_env_old : 0;
+            ((uint8_t *)oc)[i] = (uint8_t)v;
         }
+        for (int i = lane; i < 12; i += nl) ((int16_t *)oc->noise_q)[i] = i < 10 ? d->noise[1 + i / 5][i % 5] : 0;   /* + reserved2 */
     }
 }
 FE_FN void pack_ps_l(const FePs *p, HeaacPsFrame *o, int lane, int nl)
