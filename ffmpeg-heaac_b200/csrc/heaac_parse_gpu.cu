@@ -20,6 +20,8 @@
 #include <time.h>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "heaac_context.cuh"
 #include "heaac_fe_core.h"
@@ -43,6 +45,7 @@ struct HeaacGpuParser {
     uint8_t *d_scratch;              /* [S][32] frame-local parser states of phase A (head + channel blocks) */
     size_t scratch_stride;
     FeTodo *d_todo[2];               /* [S][32] per staging set: phase B of chunk k reads one while phase A of k+1 fills the other */
+    int gather_threads;              /* host threads that copy a chunk's packets into the page-locked blob (chunks of 8 MB and more) */
     FeSbrTape *d_tape;               /* [S][32][tapes_per_frame]: the SBR payloads' first step (k_parse_b; its launches are serialised on s_b) */
     int tapes_per_frame;
     cudaStream_t s_b;                /* phase B's stream */
@@ -203,6 +206,10 @@ extern "C" int heaac_b200_parser_create(HeaacContext *c, const HeaacFrontend *fe
         CKP(cudaMalloc(&p->d_todo[i], S * 32 * sizeof(FeTodo)));
         CKP(cudaEventCreateWithFlags(&p->ev_a[i], cudaEventDisableTiming));
     }
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        p->gather_threads = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;
+    }
     p->tapes_per_frame = c->geom.nse > 0 ? c->geom.nse : 1;
     CKP(cudaMalloc(&p->d_tape, (c->geom.sbr ? S * 32 * p->tapes_per_frame : 1) * sizeof(FeSbrTape)));
     CKP(cudaStreamCreateWithFlags(&p->s_b, cudaStreamNonBlocking));
@@ -284,15 +291,34 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
         }
         const double t1 = now();
         size_t used = 0;
-        for (size_t i = 0; i < np; i++) {                          /* gather: 8-byte aligned, >= 8 zero bytes after each */
+        for (size_t i = 0; i < np; i++) {                          /* layout: 8-byte aligned, >= 8 zero bytes after each */
             const int sz = size[(size_t)f0 * S + i];
             const size_t room = ((size_t)(sz > 0 ? sz : 0) + 15) & ~(size_t)7;
             if (sz < 0 || used + room > p->blob_cap) return HEAAC_E_INVAL;
-            memcpy(p->h_blob[buf] + used, pkt[(size_t)f0 * S + i], sz);
-            memset(p->h_blob[buf] + used + sz, 0, room - sz);
             p->h_off[buf][i] = (uint32_t)used;
             p->h_size[buf][i] = sz;
             used += room;
+        }
+        {   /* gather into the page-locked blob; large chunks (AAC-LC 5.1: ~80 MB) by several host threads */
+            uint8_t *dst = p->h_blob[buf];
+            const uint32_t *off = p->h_off[buf];
+            const uint8_t *const *src = pkt + (size_t)f0 * S;
+            const int *sz = size + (size_t)f0 * S;
+            auto copy_range = [=](size_t i0, size_t i1) {
+                for (size_t i = i0; i < i1; i++) {
+                    const size_t room = ((size_t)sz[i] + 15) & ~(size_t)7;
+                    memcpy(dst + off[i], src[i], sz[i]);
+                    memset(dst + off[i] + sz[i], 0, room - sz[i]);
+                }
+            };
+            const int nt = used >= ((size_t)8 << 20) ? p->gather_threads : 1;
+            if (nt <= 1) copy_range(0, np);
+            else {
+                std::vector<std::thread> th;
+                for (int k = 1; k < nt; k++) th.emplace_back(copy_range, np * k / nt, np * (k + 1) / nt);
+                copy_range(0, np / nt);
+                for (auto &t : th) t.join();
+            }
         }
         const double t2 = now();
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf], 0));     /* staging set free again */
