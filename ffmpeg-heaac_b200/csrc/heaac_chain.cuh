@@ -912,6 +912,9 @@ struct HeaacChainSmem {
         HeaacHfScratch hf;                                                                           /* HF stage */
     } s;
     alignas(8) unsigned long long mbar[1];
+#ifdef HEAAC_CHAIN_PAD_BYTES
+    char occupancy_experiment_pad[HEAAC_CHAIN_PAD_BYTES];      /* tools/var_sweep.sh: fewer CTAs per SM */
+#endif
 };
 
 struct HeaacChainArgs {
