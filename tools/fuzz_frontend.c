@@ -5,7 +5,7 @@
  *   gcc -O1 -g -fsanitize=address,undefined -Iinclude -o /tmp/fz tools/fuzz_frontend.c \
  *       ffmpeg-heaac_b200/csrc/heaac_frontend.c ffmpeg-heaac_b200/csrc/heaac_sbr_tables.c -lm -lpthread
  *   ASAN_OPTIONS=detect_leaks=0 /tmp/fz 400 /tmp/cases.bin
- * Round 1: 22,400 corrupted packets, no finding. */
+ * Round 1: 22,400 corrupted packets, no finding.  Round 2 (two-step SBR payload, chunk routine added to the harness): see DESIGN.md. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +38,29 @@ int main(int argc, char **argv) {
                 free(bb); free(b);
             }
             heaac_fe_close(fe);
+            if (it % 3 == 0 && np <= 32) {                            /* the same kind of corruption through the chunk routine of the device front end */
+                if (heaac_fe_open(&fe, ed, h[0], h[1], h[2], 0)) { printf("open fail\n"); return 1; }
+                uint8_t ety[HEAAC_MAX_ELEMS]; int ncc = 0, nse = 0;
+                heaac_fe_info(fe, &ncc, &nse, NULL, NULL, NULL, ety);
+                if (ncc > 0) {
+                    unsigned char *cp[32]; int cs[32], cons[32];
+                    for (int i = 0; i < np; i++) {
+                        int n = sz[i]; int mode = rnd() % 5;
+                        if (mode == 1 && i) n = 1 + rnd() % n;
+                        cp[i] = malloc(n); memcpy(cp[i], pk[i], n); cs[i] = n;
+                        if (mode == 0 && i) { int k = 1 + rnd() % 6; while (k--) cp[i][rnd() % n] = rnd(); }
+                        else if (mode == 2 && i) cp[i][rnd() % n] ^= 1 << (rnd() % 8);
+                    }
+                    float *cco = malloc((size_t)np * ncc * 1024 * 4);
+                    HeaacIcs *cic = malloc(sizeof(HeaacIcs) * np * ncc); HeaacTns *ctn = malloc(sizeof(HeaacTns) * np * ncc);
+                    HeaacSbrElem *csb = malloc(sizeof(HeaacSbrElem) * np * (nse > 0 ? nse : 1)); HeaacPsFrame *cps = malloc(sizeof(HeaacPsFrame) * np);
+                    int r = heaac_fe_parse_chunk(fe, np, (const uint8_t *const *)cp, cs, cco, cic, ctn, csb, cps, cons);
+                    if (r) { printf("chunk call failed %d\n", r); return 1; }
+                    for (int i = 0; i < np; i++) { if (cons[i] < 0) err++; else ok++; free(cp[i]); }
+                    free(cco); free(cic); free(ctn); free(csb); free(cps);
+                }
+                heaac_fe_close(fe);
+            }
         }
         for (int i = 0; i < np; i++) free(pk[i]);
         free(co);
