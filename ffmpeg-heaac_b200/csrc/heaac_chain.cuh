@@ -807,9 +807,6 @@ HEAAC_DEV void heaac_synth_transforms(float *u, float *qx, int top, const HeaacD
     }
 }
 
-#ifndef HEAAC_PACKED_FP32
-#define HEAAC_PACKED_FP32 1
-#endif
 template <int NT>
 HEAAC_DEV void heaac_synth_output(float *u, int nout, int out_slot, int16_t *pcm, float *pcm_f32, float scale, float bias,
                                   const HeaacDevTables *HEAAC_RESTRICT T, int tid)
@@ -854,7 +851,6 @@ HEAAC_DEV void heaac_synth_output(float *u, int nout, int out_slot, int16_t *pcm
         for (int c = 0; c < L; c += CH) {
             HEAAC_UNROLL
             for (int a = 0; a < CH; a++) { im[9 + a] = rowi[c + a]; re[9 + a] = rowr[c + a]; }
-#if defined(HEAAC_HOST_EMU) || !HEAAC_PACKED_FP32
             HEAAC_UNROLL
             for (int ii = 0; ii < CH; ii++) {
                 float acc = im[9 + ii] * wj[0] + 0.0f;
@@ -865,27 +861,6 @@ HEAAC_DEV void heaac_synth_output(float *u, int nout, int out_slot, int16_t *pcm
                 if (po) po[(size_t)(c + ii) * 64 * nout] = heaac_to_s16(acc, bias_mode);
                 if (pf) pf[(c + ii) * 64] = acc;
             }
-#else
-            /* two consecutive slots per packed operation: the same products and sums in the same order, two lanes per issue slot */
-            HEAAC_UNROLL
-            for (int ii = 0; ii < CH; ii += 2) {
-                heaac_f2 acc2 = heaac_add2(heaac_mul2(heaac_pack2(im[9 + ii], im[10 + ii]), heaac_pack2(wj[0], wj[0])), 0ull);
-                HEAAC_UNROLL
-                for (int j = 1; j < 10; j++) {
-                    const heaac_f2 x2 = (j & 1) ? heaac_pack2(re[9 + ii - j], re[10 + ii - j]) : heaac_pack2(im[9 + ii - j], im[10 + ii - j]);
-                    acc2 = heaac_add2(heaac_mul2(x2, heaac_pack2(wj[j], wj[j])), acc2);
-                }
-                float a2[2];
-                heaac_unpack2(acc2, a2[0], a2[1]);
-                HEAAC_UNROLL
-                for (int h = 0; h < 2; h++) {
-                    float acc = a2[h];
-                    if (scale_and_bias) acc = acc * scale + bias;
-                    if (po) po[(size_t)(c + ii + h) * 64 * nout] = heaac_to_s16(acc, bias_mode);
-                    if (pf) pf[(c + ii + h) * 64] = acc;
-                }
-            }
-#endif
             HEAAC_UNROLL
             for (int a = 0; a < 9; a++) { im[a] = im[CH + a]; re[a] = re[CH + a]; }
         }

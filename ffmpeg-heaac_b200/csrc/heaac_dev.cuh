@@ -51,15 +51,6 @@ __device__ __forceinline__ float heaac_fsub(float a, float b) { return __fsub_rn
 static __device__ __noinline__ float heaac_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 static __device__ __noinline__ float heaac_fsqrt(float a) { return __fsqrt_rn(a); }
 __device__ __forceinline__ float heaac_rint(float a) { return rintf(a); }
-/* Packed FP32 (sm_100: fma.rn.f32x2 -> FFMA2, two lanes per issue slot).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
- * FFMA2 even with --fmad false, so the exact, unfused operations are spelled as FMAs whose extra operand cannot change the
- * rounded result: a * b = fma(a, b, -0), a + b = fma(a, 1, b). */
-typedef unsigned long long heaac_f2;
-__device__ __forceinline__ heaac_f2 heaac_pack2(float lo, float hi) { heaac_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void heaac_unpack2(heaac_f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ heaac_f2 heaac_fma2(heaac_f2 a, heaac_f2 b, heaac_f2 c) { heaac_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ heaac_f2 heaac_mul2(heaac_f2 a, heaac_f2 b) { return heaac_fma2(a, b, 0x8000000080000000ull); }
-__device__ __forceinline__ heaac_f2 heaac_add2(heaac_f2 a, heaac_f2 b) { return heaac_fma2(a, 0x3f8000003f800000ull, b); }
 #endif
 
 /* ---- asynchronous global -> shared copies (LDGSTS): issue early, wait right before first use ---- */
