@@ -58,8 +58,10 @@ def test_cuda_matches_oracle_on_synthetic_workloads(hb, name):
     opcm, of32 = orc.synth(*args, n_threads=8)
     orc.close()
     err = float(np.abs(f32 - of32).max()) / FULL_SCALE
-    assert err <= TOL_FS and int(np.abs(pcm.astype(np.int32) - opcm).max()) <= 1
     print("%s: max float err %.3g FS, bit-exact s16: %s" % (name, err, np.array_equal(pcm, opcm)))
+    # the CUDA path evaluates the oracle's IEEE operations in the oracle's order: not a tolerance, identity (a contracted
+    # multiply-add anywhere on the path shows up here as 1e-7 FS)
+    assert np.array_equal(f32, of32) and np.array_equal(pcm, opcm), "%s: max float err %.3g FS" % (name, err)
 
 
 @needs_ref
