@@ -24,6 +24,9 @@
 #include <vector>
 
 #include "heaac_context.cuh"
+#ifndef HEAAC_PARSE_AFTER_SYNTH
+#define HEAAC_PARSE_AFTER_SYNTH 1
+#endif
 #include "heaac_fe_core.h"
 
 /* pipeline trace (event times of every chunk on stderr): a debug build only, -DHEAAC_DEBUG_TIMING (make EXTRA=-DHEAAC_DEBUG_TIMING) */
@@ -330,6 +333,11 @@ extern "C" long long heaac_b200_parser_submit(HeaacGpuParser *p, int n_frames, c
         if (di == 0) CK(cudaEventRecord(p->dbg_base, c->s_in));
         if (di >= 0) CK(cudaEventRecord(p->dbg_ev[di][0], c->s_in));
         if (c->seq >= 2) CK(cudaStreamWaitEvent(c->s_in, c->ev_out[buf], 0));      /* d_consumed[buf] drained */
+#if HEAAC_PARSE_AFTER_SYNTH
+        /* the front end of this chunk starts when the synthesis of the chunk before has left the SMs: side by side the two
+         * latency-bound kernels only slow each other down (measured) */
+        if (c->seq >= 1) CK(cudaStreamWaitEvent(c->s_in, c->ev_done[buf ^ 1], 0));
+#endif
         {
             const int threads = HEAAC_PARSE_THREADS, warps_per_cta = threads / 32;
             const int grid = (int)((S + warps_per_cta - 1) / warps_per_cta);
