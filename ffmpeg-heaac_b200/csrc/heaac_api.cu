@@ -18,6 +18,9 @@
 
 #include "heaac_chain.cuh"
 #include "heaac_context.cuh"
+#ifndef HEAAC_X_GROUP
+#define HEAAC_X_GROUP 8            /* frames per chain launch on the paths that go through the inter-kernel X buffer */
+#endif
 
 extern "C" void heaac_build_tables(HeaacDevTables *t);
 
@@ -154,7 +157,8 @@ k_chain(HeaacGeom g, int first_ch, int n_frames, int emit, const float *__restri
     const int s = gc / g.ncc, c = gc - s * g.ncc;
     const int se = g.ch_sbr_elem[c];
     HeaacChainArgs a;
-    a.n_frames = n_frames; a.emit = emit;
+    a.n_frames = n_frames; a.emit = emit == 3 ? 1 : emit;      /* 3 = 1 with one X per frame of the launch */
+    a.x_frame = emit == 3 ? (size_t)g.n_streams * g.nout * HEAAC_X_FLOATS : 0;
     a.frame_ch = (size_t)g.n_streams * g.ncc;
     a.frame_elems = (size_t)g.n_streams * g.nse;
     a.pcm_frame = (size_t)g.n_streams * 2048 * g.nout;
@@ -312,7 +316,7 @@ static int init_state(HeaacContext *c)
     CK(cudaMemsetAsync(c->d_chan, 0, nch * sizeof(HeaacChanState), c->stream));
     if (g->sbr) {
         CK(cudaMemsetAsync(c->d_synth, 0, (size_t)g->n_streams * g->nout * sizeof(HeaacSynthState), c->stream));
-        if (c->d_X) CK(cudaMemsetAsync(c->d_X, 0, (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
+        if (c->d_X) CK(cudaMemsetAsync(c->d_X, 0, c->x_frames * (size_t)g->n_streams * g->nout * HEAAC_X_FLOATS * sizeof(float), c->stream));
     }
     if (g->ps) CK(cudaMemsetAsync(c->d_ps, 0, (size_t)g->n_streams * sizeof(HeaacPsState), c->stream));
     /* everything the reference initialises to non-zero (kx' = 32, e_a[1] = -1; aacsbr.c:128-137) lives in
@@ -401,7 +405,7 @@ extern "C" int heaac_b200_create(const HeaacConfig *cfg, HeaacContext **out)
     CKX(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned)));
     if (g->sbr) {
         CKX(cudaMalloc(&c->d_synth, S * g->nout * sizeof(HeaacSynthState)));
-        if (g->ps || g->ds || cfg->keep_intermediates) CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float)));
+        if (g->ps || g->ds || cfg->keep_intermediates) { CKX(cudaMalloc(&c->d_X, S * g->nout * HEAAC_X_FLOATS * sizeof(float))); c->x_frames = 1; }
     }
     if (g->ps) CKX(cudaMalloc(&c->d_ps, S * sizeof(HeaacPsState)));
     if (g->n_cce) CKX(cudaMalloc(&c->d_couple, S * g->ncc * 1024 * sizeof(float)));
@@ -522,26 +526,42 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             c->launches++;
             return heaac_cuda_err(cudaGetLastError(), "kernel launch");
         }
-        for (int f = 0; f < n_frames; f++) {         /* Parametric Stereo / downsampled SBR: X goes through the inter-kernel buffer */
-            const size_t fo = (size_t)f * n_ch;
-            const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
-            int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
-            float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+        /* Parametric Stereo / downsampled SBR: X goes through the inter-kernel buffer.  The chain runs for a group of frames per
+         * launch (channel state and history stay in shared memory, the next frame's inputs are fetched under the current one) and
+         * leaves one X per frame; Parametric Stereo and the synthesis bank follow frame by frame */
+        const size_t x_frame = S * g.nout * HEAAC_X_FLOATS;
+        const int group = n_frames < HEAAC_X_GROUP ? n_frames : HEAAC_X_GROUP;
+        if (c->x_frames < (size_t)group) {
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_X); c->d_X = nullptr; c->x_frames = 0;
+            CK(cudaMalloc(&c->d_X, (size_t)group * x_frame * sizeof(float)));
+            CK(cudaMemsetAsync(c->d_X, 0, (size_t)group * x_frame * sizeof(float), c->stream));
+            c->x_frames = group;
+        }
+        for (int f0 = 0; f0 < n_frames; f0 += group) {
+            const int nf = n_frames - f0 < group ? n_frames - f0 : group;
+            const size_t fo = (size_t)f0 * n_ch;
             prof_begin(c, HEAAC_K_CHAIN);
-            launch_chain(c, n_ch, 1, 1, coeffs + fo * 1024, nullptr, ics + fo, tns ? tns + fo : nullptr, tns_done ? tns_done + fo * 1024 : nullptr,
-                         sb, c->d_chan, c->d_synth, c->d_X, nullptr, nullptr);
+            launch_chain(c, n_ch, nf, 3, coeffs + fo * 1024, nullptr, ics + fo, tns ? tns + fo : nullptr, tns_done ? tns_done + fo * 1024 : nullptr,
+                         sbr + (size_t)f0 * S * g.nse, c->d_chan, c->d_synth, c->d_X, nullptr, nullptr);
             prof_end(c);
             c->launches++;
-            if (g.ps) {
-                prof_begin(c, HEAAC_K_PS);
-                k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, ps + (size_t)f * S, sb, c->d_ps, c->d_X, c->d_tables);
+            for (int f = f0; f < f0 + nf; f++) {
+                const HeaacSbrElem *sb = sbr + (size_t)f * S * g.nse;
+                float *X = c->d_X + (size_t)(f - f0) * x_frame;
+                int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
+                float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+                if (g.ps) {
+                    prof_begin(c, HEAAC_K_PS);
+                    k_ps<<<(unsigned)S, HEAAC_THREADS, c->smem_ps, c->stream>>>(g, ps + (size_t)f * S, sb, c->d_ps, X, c->d_tables);
+                    prof_end(c);
+                    c->launches++;
+                }
+                prof_begin(c, HEAAC_K_SYNTH);
+                k_synth<<<(unsigned)(S * g.n_elems), 128, c->smem_synth, c->stream>>>(g, X, c->d_synth, pc, pf, c->d_tables);
                 prof_end(c);
                 c->launches++;
             }
-            prof_begin(c, HEAAC_K_SYNTH);
-            k_synth<<<(unsigned)(S * g.n_elems), 128, c->smem_synth, c->stream>>>(g, c->d_X, c->d_synth, pc, pf, c->d_tables);
-            prof_end(c);
-            c->launches++;
         }
         return heaac_cuda_err(cudaGetLastError(), "kernel launch");
     }

@@ -929,6 +929,7 @@ struct HeaacChainArgs {
     const HeaacSbrElem *sbr;             /* this channel's element, frame 0 */
     HeaacChanState *st; HeaacSynthState *sy;
     float *X;                            /* this channel's inter-kernel X */
+    size_t x_frame;                      /* floats between the X of consecutive frames (0: every frame goes to the same place) */
     int16_t *pcm; float *pcm_f32;        /* this stream, frame 0 */
     int ch_in_elem, is_cpe, nout, out_slot, sr_index;
     float qmf_scale, add_bias;
@@ -1050,7 +1051,7 @@ HEAAC_DEV void heaac_chain_channel(HeaacChainSmem *sm, const HeaacChainArgs &a, 
             heaac_hf_params(sm->u, &sm->s.hf, &sm->tb, &sm->d, p, a.ch_in_elem, st, &sm->keep, SPLIT ? tid - 32 : tid, SPLIT ? nt - 32 : nt);
         HEAAC_SYNC();
         heaac_hf_stage<NT>(sm->u, &sm->s.hf, &sm->tb, &sm->d, p, a.ch_in_elem, st, &sm->keep, a.emit ? 38 : 32, T, tid);
-        if (a.emit) heaac_x_emit<NT>(sm->u, a.X, sm->d.top, tid);
+        if (a.emit) heaac_x_emit<NT>(sm->u, a.X + (size_t)f * a.x_frame, sm->d.top, tid);
         heaac_hf_save(sm->u, &sm->s.hf, &sm->d, st, &sm->keep, tid, nt);
         HEAAC_SYNC();
         /* the scratch is free: fetch the next frame's coefficients and side info while the synthesis goes on (the exchange

@@ -22,7 +22,8 @@ struct HeaacContext {
     unsigned *d_work;                /* k_core's channel counter + finished-CTA counter */
     float *d_couple;                 /* [S][ncc][1024] decoded channels of one frame tick, planar (layouts with coupling channel elements) */
     HeaacCce *s_cce[2];              /* staging, like s_ics */
-    float *d_X;                      /* [S][nout][2][64][40]: X between k_chain, k_ps and k_synth (PS / downsampled SBR / keep_intermediates) */
+    float *d_X;                      /* [x_frames][S][nout][2][64][40]: X between k_chain, k_ps and k_synth (PS / downsampled SBR / keep_intermediates) */
+    size_t x_frames;                 /* frames d_X holds (1, or the chain's frames per launch on the PS / downsampled paths) */
     /* staging for host-pointer batches, sized for max_frames_per_call */
     /* Host-pointer batches are streamed through two sets of device staging buffers of `chunk` frames each:
      * H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams. */
