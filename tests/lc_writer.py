@@ -94,6 +94,9 @@ class LcWriter:
         else:
             nswb = int(t["nswb1024"][self.sr_index])
             info["max_sfb"] = int(r.integers(nswb // 3, nswb + 1)) if r.random() < 0.95 else 0
+            if getattr(self, "force_max_sfb", None) is not None:
+                info["max_sfb"] = int(self.force_max_sfb)
+            info["nswb"] = nswb
             bw.put(info["max_sfb"], 6); bw.put(0, 1)                # no prediction in LC
             info["group_len"], info["swb"] = [1], t["swb1024"][self.sr_index]
         self.stats["sine"] += shape == 0
@@ -188,6 +191,13 @@ class LcWriter:
 
     def _pulses(self, bw, info):
         r = self.rng
+        if getattr(self, "overrun_pulse", False) and info["ws"] != EIGHT_SHORT and 0 < info["max_sfb"] < info["nswb"]:
+            # NON-CONFORMANT on purpose: one pulse in the band right behind the last coded one (the reference accepts it:
+            # decode_pulses only checks pulse_swb < num_swb and pos <= 1023, aacdec.c:826-852)
+            bw.put(1, 1); bw.put(0, 2); bw.put(info["max_sfb"], 6)
+            bw.put(1, 5); bw.put(9, 4)
+            self.overrun_at = int(info["swb"][info["max_sfb"]]) + 1
+            return
         if info["ws"] == EIGHT_SHORT or not self.pulses or r.random() > 0.2 or info["max_sfb"] == 0:
             bw.put(0, 1)
             return

@@ -497,3 +497,35 @@ def test_chunk_parse_when_a_header_changes_the_tables_inside_a_chunk(stereo):
     pk = a + b + c
     for chunk in (32, 16, 9):
         _chunk_vs_frames(pk, ed, 24000, 2 if stereo else 1, chunk, "spliced/%d" % chunk)
+
+
+@needs_ref
+def test_pulse_beyond_the_coded_bands_is_dropped_where_the_reference_uses_stale_state():
+    """A documented departure on non-conformant input: pulse data positioned in a band behind max_sfb.
+    The reference scales such a pulse by whatever an EARLIER frame left in the channel's band_type / sf arrays for that band
+    (aacdec.c:1226: frame 0 below codes all bands, so frame 1's stray pulse picks up frame 0's scale factor and comes out
+    non-zero); every parser here drops it.  Everything else of the frame -- all other coefficients, the side info, the bytes
+    consumed -- is the reference's."""
+    import lc_writer
+    import pyref
+    w = lc_writer.LcWriter(77, 4, [abi.TYPE_SCE], tns_prob=0.0, short_bias=0.0)
+    w.pulses = False
+    nswb = 49                                                    # 44.1 kHz long windows
+    w.force_max_sfb = nswb
+    p0 = w.frame()                                               # frame 0: every band coded
+    w.force_max_sfb, w.overrun_pulse = 20, True
+    p1 = w.frame()                                               # frame 1: 20 bands, one pulse in band 20
+    at = w.overrun_at
+    ed = lc_writer.audio_specific_config(4, 1)
+    ref = pyref.Decoder(ed, 44100, 1, "mono")
+    fe = hb.Frontend(ed, 44100, 1)
+    r0, m0 = ref.decode(p0), fe.parse(p0)
+    assert not diff_parsed(r0, m0, 1, False, False)
+    r1, m1 = ref.decode(p1), fe.parse(p1)
+    assert r1["consumed"] == m1["consumed"]
+    assert m1["coeffs"][0, at] == 0.0                            # dropped here ...
+    assert r1["coeffs"][0, at] != 0.0                            # ... scaled by frame 0's scale factor of that band in the reference
+    rest = np.ones(1024, bool); rest[at] = False
+    assert np.array_equal(r1["coeffs"][0, rest], m1["coeffs"][0, rest])
+    assert r1["ics"].tobytes() == m1["ics"].tobytes()
+    ref.close(); fe.close()
