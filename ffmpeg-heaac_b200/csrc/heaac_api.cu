@@ -565,17 +565,29 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         }
         return heaac_cuda_err(cudaGetLastError(), "kernel launch");
     }
+    if (tns) {
+        /* AAC-LC: the TNS pre-pass for every frame of the call at once, like on the SBR paths (the filters are serial chains: the
+         * more of them in flight, the better their latency is hidden) */
+        if (c->tns_done_frames < (size_t)n_frames) {
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_tns_done); c->d_tns_done = nullptr; c->tns_done_frames = 0;
+            CK(cudaMalloc(&c->d_tns_done, (size_t)n_frames * n_ch * 1024 * sizeof(float)));
+            c->tns_done_frames = n_frames;
+        }
+        const size_t n_all = (size_t)n_frames * n_ch;
+        prof_begin(c, HEAAC_K_CORE);
+        k_tns<<<(unsigned)((n_all * 8 + 127) / 128), 128, 0, c->stream>>>((int)n_all, g.sr_index, coeffs, ics, tns, c->d_tns_done, c->d_tables);
+        prof_end(c);
+        c->launches++;
+    }
     for (int f = 0; f < n_frames; f++) {             /* AAC-LC */
         const float *co = coeffs + (size_t)f * n_ch * 1024;
         const HeaacIcs *ic = ics + (size_t)f * n_ch;
         const HeaacTns *tn = tns ? tns + (size_t)f * n_ch : nullptr;
+        const float *tns_done = tns ? c->d_tns_done + (size_t)f * n_ch * 1024 : nullptr;
         int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
         float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
         prof_begin(c, HEAAC_K_CORE);
-        if (tn) {
-            k_tns<<<(n_ch * 8 + 127) / 128, 128, 0, c->stream>>>((int)n_ch, g.sr_index, co, ic, tn, c->d_tns_done, c->d_tables);
-            c->launches++;
-        }
         const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
         if (g.n_cce) {
             /* coupling channel elements: every coded channel goes to the planar float buffer (its own slot each), k_couple adds
@@ -584,12 +596,12 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
             gp.nout = g.ncc;
             for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) gp.out_slot[i] = (uint8_t)i;
             k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(gp, (int)n_ch, co, ic, tn, c->d_chan, nullptr, c->d_couple, c->d_tables,
-                                                                       c->d_work, tn ? c->d_tns_done : nullptr);
+                                                                       c->d_work, tns_done);
             k_couple<<<(unsigned)S, HEAAC_THREADS, 0, c->stream>>>(g, c->d_couple, cce + (size_t)f * S * g.n_cce, pc, pf);
             c->launches++;
         } else
             k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, co, ic, tn, c->d_chan, pc, pf, c->d_tables, c->d_work,
-                                                                       tn ? c->d_tns_done : nullptr);
+                                                                       tns_done);
         prof_end(c);
         c->launches++;
     }
