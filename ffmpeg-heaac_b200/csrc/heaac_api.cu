@@ -75,45 +75,57 @@ k_tns(int n_channels, int sr_index, const float *__restrict__ coeffs, const Heaa
  * claimed channel's coefficients into the other half of a double buffer with cp.async while working on the current one.
  * work[0] = next unclaimed channel, work[1] = CTAs finished; the last CTA out resets both for the next launch. */
 __global__ void __launch_bounds__(HEAAC_THREADS, HEAAC_CORE_MIN_BLOCKS)
-k_core(HeaacGeom g, int n_channels, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
+k_core(HeaacGeom g, int n_channels, int n_frames, const float *__restrict__ coeffs, const HeaacIcs *__restrict__ ics,
        const HeaacTns *__restrict__ tns, HeaacChanState *chan,
        int16_t *pcm, float *pcm_f32, const HeaacDevTables *__restrict__ T, unsigned *work,
        const float *__restrict__ tns_done)
 {
+    /* A CTA claims a channel and takes it through all n_frames frames of the call (frame-major arrays: frame f of channel gc
+     * at index f * n_channels + gc); the coefficients of the next frame -- or of the next channel's first frame -- are fetched
+     * while the current one is transformed. */
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_claim[2];
+    __shared__ int s_claim;
     HeaacCoreSmem *sm = reinterpret_cast<HeaacCoreSmem *>(smem_raw);
     float *stage = reinterpret_cast<float *>(smem_raw + sizeof(HeaacCoreSmem));   /* [2][1024] */
     float *out = stage + 2048;                       /* [1024] */
-    if (threadIdx.x == 0) s_claim[0] = (int)atomicAdd(&work[0], 1u);
+    const size_t pcm_frame = (size_t)g.n_streams * 1024 * g.nout;
+    if (threadIdx.x == 0) s_claim = (int)atomicAdd(&work[0], 1u);
     __syncthreads();
-    int gc = s_claim[0];
+    int gc = s_claim;
     if (gc < n_channels)
         heaac_cp_async16(stage + 4 * threadIdx.x, coeffs + (size_t)gc * 1024 + 4 * threadIdx.x);
     heaac_cp_async_commit();
-    for (int it = 0; gc < n_channels; it++) {
+    __syncthreads();                                 /* s_claim has been read by everyone */
+    for (int it = 0; gc < n_channels; ) {
         const int s = gc / g.ncc, c = gc - s * g.ncc;
-        float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
-        if (threadIdx.x == 0) s_claim[(it + 1) & 1] = (int)atomicAdd(&work[0], 1u);
-        heaac_cp_async_wait<0>();                    /* this channel's coefficients have landed */
-        __syncthreads();
-        const int gn = s_claim[(it + 1) & 1];
-        if (gn < n_channels)
-            heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + (size_t)gn * 1024 + 4 * threadIdx.x);
-        heaac_cp_async_commit();
-        heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + gc, tns ? tns + gc : nullptr,
-                                          tns_done ? tns_done + (size_t)gc * 1024 : nullptr,
-                                          chan + gc, out, g.add_bias, g.sr_index, T, threadIdx.x);
-        const int bias_mode = g.add_bias != 0.0f;
-        if (pcm) {
-            int16_t *dst = pcm + (size_t)s * 1024 * g.nout + g.out_slot[c];
-            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
+        int gn = gc;
+        for (int f = 0; f < n_frames; f++, it++) {
+            const size_t fc = (size_t)f * n_channels + gc;
+            const bool last = f == n_frames - 1;
+            float *cur = stage + (it & 1) * 1024, *nxt = stage + ((it + 1) & 1) * 1024;
+            if (last && threadIdx.x == 0) s_claim = (int)atomicAdd(&work[0], 1u);
+            heaac_cp_async_wait<0>();                /* this frame's coefficients have landed */
+            __syncthreads();
+            if (last) gn = s_claim;
+            if (!last || gn < n_channels) {
+                const size_t nc = last ? (size_t)gn : fc + n_channels;
+                heaac_cp_async16(nxt + 4 * threadIdx.x, coeffs + nc * 1024 + 4 * threadIdx.x);
+            }
+            heaac_cp_async_commit();
+            heaac_core_channel<HEAAC_THREADS>(sm, cur, ics + fc, tns ? tns + fc : nullptr,
+                                              tns_done ? tns_done + fc * 1024 : nullptr,
+                                              chan + gc, out, g.add_bias, g.sr_index, T, threadIdx.x);
+            const int bias_mode = g.add_bias != 0.0f;
+            if (pcm) {
+                int16_t *dst = pcm + (size_t)f * pcm_frame + (size_t)s * 1024 * g.nout + g.out_slot[c];
+                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[(size_t)i * g.nout] = heaac_to_s16(out[i], bias_mode);
+            }
+            if (pcm_f32) {
+                float *dst = pcm_f32 + (size_t)f * pcm_frame + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
+                for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
+            }
+            __syncthreads();                         /* out / stage / s_claim are reused by the next frame */
         }
-        if (pcm_f32) {
-            float *dst = pcm_f32 + ((size_t)s * g.nout + g.out_slot[c]) * 1024;
-            for (int i = threadIdx.x; i < 1024; i += HEAAC_THREADS) dst[i] = out[i];
-        }
-        __syncthreads();                             /* out / stage are reused by the next channel */
         gc = gn;
     }
     if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; }
@@ -580,30 +592,30 @@ int heaac_launch_frames(HeaacContext *c, int n_frames, const float *coeffs, cons
         prof_end(c);
         c->launches++;
     }
-    for (int f = 0; f < n_frames; f++) {             /* AAC-LC */
-        const float *co = coeffs + (size_t)f * n_ch * 1024;
-        const HeaacIcs *ic = ics + (size_t)f * n_ch;
-        const HeaacTns *tn = tns ? tns + (size_t)f * n_ch : nullptr;
-        const float *tns_done = tns ? c->d_tns_done + (size_t)f * n_ch * 1024 : nullptr;
-        int16_t *pc = pcm ? pcm + (size_t)f * pcm_frame : nullptr;
-        float *pf = pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr;
+    const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
+    if (!g.n_cce) {                                  /* AAC-LC: one launch for the whole call, every CTA takes its channels through all frames */
         prof_begin(c, HEAAC_K_CORE);
-        const unsigned grid = n_ch < (unsigned)c->core_grid ? n_ch : (unsigned)c->core_grid;
-        if (g.n_cce) {
-            /* coupling channel elements: every coded channel goes to the planar float buffer (its own slot each), k_couple adds
-             * the coupling channels to their targets and converts */
-            HeaacGeom gp = g;
-            gp.nout = g.ncc;
-            for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) gp.out_slot[i] = (uint8_t)i;
-            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(gp, (int)n_ch, co, ic, tn, c->d_chan, nullptr, c->d_couple, c->d_tables,
-                                                                       c->d_work, tns_done);
-            k_couple<<<(unsigned)S, HEAAC_THREADS, 0, c->stream>>>(g, c->d_couple, cce + (size_t)f * S * g.n_cce, pc, pf);
-            c->launches++;
-        } else
-            k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, co, ic, tn, c->d_chan, pc, pf, c->d_tables, c->d_work,
-                                                                       tns_done);
+        k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(g, (int)n_ch, n_frames, coeffs, ics, tns, c->d_chan, pcm, pcm_f32,
+                                                                   c->d_tables, c->d_work, tns ? c->d_tns_done : nullptr);
         prof_end(c);
         c->launches++;
+        return heaac_cuda_err(cudaGetLastError(), "kernel launch");
+    }
+    for (int f = 0; f < n_frames; f++) {
+        /* layouts with coupling channel elements, frame by frame: every coded channel goes to the planar float buffer (its own slot
+         * each), k_couple adds the coupling channels to their targets and converts */
+        const size_t fo = (size_t)f * n_ch;
+        HeaacGeom gp = g;
+        gp.nout = g.ncc;
+        for (int i = 0; i < HEAAC_MAX_CHANNELS; i++) gp.out_slot[i] = (uint8_t)i;
+        prof_begin(c, HEAAC_K_CORE);
+        k_core<<<grid, HEAAC_THREADS, c->smem_core, c->stream>>>(gp, (int)n_ch, 1, coeffs + fo * 1024, ics + fo, tns ? tns + fo : nullptr, c->d_chan,
+                                                                   nullptr, c->d_couple, c->d_tables, c->d_work,
+                                                                   tns ? c->d_tns_done + fo * 1024 : nullptr);
+        k_couple<<<(unsigned)S, HEAAC_THREADS, 0, c->stream>>>(g, c->d_couple, cce + (size_t)f * S * g.n_cce,
+                                                                 pcm ? pcm + (size_t)f * pcm_frame : nullptr, pcm_f32 ? pcm_f32 + (size_t)f * pcm_frame : nullptr);
+        prof_end(c);
+        c->launches += 2;
     }
     return heaac_cuda_err(cudaGetLastError(), "kernel launch");
 }
