@@ -529,3 +529,19 @@ def test_pulse_beyond_the_coded_bands_is_dropped_where_the_reference_uses_stale_
     assert np.array_equal(r1["coeffs"][0, rest], m1["coeffs"][0, rest])
     assert r1["ics"].tobytes() == m1["ics"].tobytes()
     ref.close(); fe.close()
+
+
+@pytest.mark.parametrize("name", ("bench_heaac_v1_stereo_packets", "bench_heaac_v2_ps_packets"))
+def test_chunk_parse_takes_the_side_by_side_path_in_steady_state(name):
+    """Performance semantics of the device front end's chunk routine, checked on the host: once a stream is under way, every
+    chunk is ONE pass of the side-by-side step and no frame goes through the one-pass parser (repeated, unchanged SBR headers
+    every 16 frames must not count as a change); only the chunk that holds the stream's very first header needs a second pass."""
+    pk, ed, rate, ch = _fixture_or_golden(name)
+    fe = hb.Frontend(ed, rate, ch)
+    first = fe.parse_chunk(pk[:32])["stats"]
+    assert first["one_pass_frames"] == 1 and first["passes"] <= 2, first
+    for rep in range(3):
+        for t0 in (32, 0):
+            st = fe.parse_chunk(pk[t0:t0 + 32])["stats"]
+            assert st == {"passes": 1, "one_pass_frames": 0, "stale": 0}, (rep, t0, st)
+    fe.close()
